@@ -1,0 +1,154 @@
+/* ============================================================================
+ *  kmerutils_b200.h -- C ABI of the B200-native k-mer engine.
+ *
+ *  This is the drop-in boundary for the data-parallel hot path of
+ *  jean-pierreBoth/kmerutils (Rust, v0.0.14).  The reference has no FFI of its
+ *  own; the entry points below are what a `extern "C"` shim
+ *  inside the Rust crate binds, each one replacing the
+ *  reference function cited next to it (paths relative to the reference tree).
+ *
+ *  Conventions
+ *   - every function returns an int32 status (KMU_OK == 0); the message of the
+ *     last failure on the calling thread is kmu_last_error().
+ *   - plain pointers and sizes only; the caller owns every input/output buffer.
+ *   - the library never falls back to a CPU implementation: without a CUDA
+ *     device every compute entry point returns KMU_ECUDA.
+ *   - results come back in input order (the reference asserts this,
+ *     src/sketching/setsketchert.rs:154-155).
+ *   - a context is bound to one GPU; calls on one context are serialised by an
+ *     internal mutex, different contexts run concurrently.
+ * ==========================================================================*/
+#ifndef KMERUTILS_B200_H
+#define KMERUTILS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes --------------------------------------------------------- */
+#define KMU_OK 0
+#define KMU_EINVAL 1 /* the reference would panic on this input (bad k for the type, m < 2, ...) */
+#define KMU_ECUDA 2  /* CUDA runtime failure or no device */
+#define KMU_ENOMEM 3
+#define KMU_EOVERFLOW 4
+
+/* ---- k-mer word types ---------------------------------- */
+#define KMU_KMER32 0    /* Kmer32bit    src/base/kmer32bit.rs:22    k <= 14, k in the top 4 bits, u32 */
+#define KMU_KMER16B32 1 /* Kmer16b32bit src/base/kmer16b32bit.rs:21 k == 16, u32 */
+#define KMU_KMER64 2    /* Kmer64bit    src/base/kmer64bit.rs:24    k <= 32, u64 value (k kept apart) */
+#define KMU_KMERAA32 3  /* KmerAA32bit  src/aautils/kmeraa.rs:146   k <= 6, 5 bits / residue, u32 */
+#define KMU_KMERAA64 4  /* KmerAA64bit  src/aautils/kmeraa.rs:280   k <= 12, u64 */
+
+/* ---- the hash closures `fhash` the reference passes to its sketchers.
+ * A Rust closure cannot cross into CUDA, so the boundary takes an enumerated kind. */
+#define KMU_HASH_IDENTITY_RAW 0  /* |k| k.0                                 seqsketchjaccard.rs:775     */
+#define KMU_HASH_MASKED_VALUE 1  /* |k| k.get_compressed_value() & mask     setsketchert.rs:1098-1104   */
+#define KMU_HASH_CANON_INVHASH 2 /* |k| intNN_hash(k.reverse_complement().min(*k).0)  datasketcher.rs:222-226 */
+#define KMU_HASH_CANON_RAW 3     /* |k| k.reverse_complement().min(*k).0    kmercount.rs:313,827,938    */
+#define KMU_HASH_INVHASH 4       /* |k| intNN_hash(k.0)                      minhash.rs:226              */
+
+typedef struct kmu_ctx kmu_ctx;
+typedef struct kmu_seqbatch kmu_seqbatch;
+
+/* ---- context ------------------------------------------------------------------ */
+int32_t kmu_ctx_create(int32_t device, kmu_ctx** ctx);
+void kmu_ctx_destroy(kmu_ctx* ctx);
+const char* kmu_last_error(void);
+/* library version / build info string (static storage) */
+const char* kmu_version(void);
+/* number of kernels of this library launched on the context since creation */
+uint64_t kmu_launch_count(const kmu_ctx* ctx);
+/* the CUDA stream (cudaStream_t) all work of this context is enqueued on */
+void* kmu_ctx_stream(kmu_ctx* ctx);
+/* block the calling thread until the context's stream is idle */
+int32_t kmu_ctx_sync(kmu_ctx* ctx);
+
+/* ---- sequence batches (replaces Vec<Sequence>, src/base/sequence.rs:14-20) --------
+ * A batch is a set of 2-bit packed sequences resident in HBM: one byte buffer in
+ * which every sequence starts on a 16-byte boundary with the reference's byte
+ * layout (4 bases / byte, first base in the two most significant bits,
+ * src/base/alphabet.rs:162-168), plus per-sequence byte offsets and base counts. */
+
+/* from `nseq` separate host buffers -- the `&[&Sequence]` the Rust entry points get
+ * (setsketchert.rs:70-79).  seq_ptrs[i] holds ceil(nbases[i]/4) bytes. */
+int32_t kmu_seqbatch_from_ptrs(kmu_ctx* ctx, const uint8_t* const* seq_ptrs, const uint64_t* nbases, uint64_t nseq,
+                               kmu_seqbatch** batch);
+/* from one concatenated host buffer; sequence i starts at packed + byte_off[i].
+ * If every byte_off[i] is a multiple of 16 the buffer is copied as is (pin it for
+ * full PCIe speed); otherwise it is re-laid out on the host first. */
+int32_t kmu_seqbatch_from_packed(kmu_ctx* ctx, const uint8_t* packed, uint64_t packed_bytes, const uint64_t* byte_off,
+                                 const uint64_t* nbases, uint64_t nseq, kmu_seqbatch** batch);
+/* ASCII (FASTA/FASTQ payload) -> 2-bit on the GPU: Sequence::new(raw, 2)
+ * (sequence.rs:25-106).  ascii is one concatenated host buffer, sequence i is
+ * ascii[ascii_off[i] .. ascii_off[i+1]).  invalid_counts (nseq entries, may be NULL)
+ * receives count_non_acgt (alphabet.rs:28-31); when drop_invalid == 0 a sequence
+ * with any invalid character makes the call fail with KMU_EINVAL (the reference
+ * panics, alphabet.rs:125); when drop_invalid != 0 invalid characters are skipped
+ * as by Sequence::encode_and_add (sequence.rs:388-451). */
+int32_t kmu_seqbatch_from_ascii(kmu_ctx* ctx, const uint8_t* ascii, const uint64_t* ascii_off, uint64_t nseq,
+                                int32_t drop_invalid, uint64_t* invalid_counts, kmu_seqbatch** batch);
+/* synthetic uniform ACGT reads generated on the device (bench / tests):
+ * base j of sequence i = top 2 bits of SplitMix64 output (first_base[i] + j) of stream `seed`. */
+int32_t kmu_seqbatch_synth(kmu_ctx* ctx, uint64_t seed, const uint64_t* nbases, uint64_t nseq, kmu_seqbatch** batch);
+void kmu_seqbatch_destroy(kmu_seqbatch* batch);
+uint64_t kmu_seqbatch_nseq(const kmu_seqbatch* batch);
+uint64_t kmu_seqbatch_total_bases(const kmu_seqbatch* batch);
+uint64_t kmu_seqbatch_packed_bytes(const kmu_seqbatch* batch);
+/* copy the device layout back to the host (packed_out: kmu_seqbatch_packed_bytes();
+ * byte_off_out / nbases_out: nseq entries each; any may be NULL) */
+int32_t kmu_seqbatch_download(kmu_ctx* ctx, const kmu_seqbatch* batch, uint8_t* packed_out, uint64_t* byte_off_out,
+                              uint64_t* nbases_out);
+
+/* ---- k-mer generation (KmerGenerator::generate_kmer, src/base/kmergenerator.rs:162-167;
+ *      KmerSeqIterator::next :75-106) fused with the hash closure -------------------------
+ * For every sequence all windows of k bases, forward strand, in order; each k-mer
+ * word is mapped through `hash_kind` (KMU_HASH_IDENTITY_RAW gives the reference's
+ * Vec<Kmer>).  out holds sum_i max(0, nbases[i]-k+1) elements of 4 bytes (u32 types)
+ * or 8 bytes (u64 types); out_off (nseq+1 entries, may be NULL) receives the
+ * element offset of each sequence's first k-mer.  out is a host pointer unless
+ * out_on_device != 0. */
+uint64_t kmu_kmer_count(const kmu_seqbatch* batch, uint32_t k);
+int32_t kmu_generate_kmers(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, int32_t kmer_type, int32_t hash_kind,
+                           void* out, uint64_t* out_off, int32_t out_on_device);
+
+/* ---- ntHash (NtHash::nthash_canonical_init / nthash_mult_canonical_init for the 2-bit
+ *      k-mer types, src/base/kmer.rs:74-94,120-129; nthash.rs:63-72) ------------------------
+ * out_hash: n_kmers * n_multi u64 (k-mer major); hash 0 is min(fhash, rhash), hashes
+ * 1.. follow from_one_hash_val_to_mult_hash.  out_strand (may be NULL): 0 if
+ * fhash <= rhash else 1.  Defined for k <= 32 (the reference implements the trait
+ * for the two u32 types only; k > 16 is the same formula on Kmer64bit). */
+int32_t kmu_nthash_canonical(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, uint32_t n_multi, uint64_t* out_hash,
+                             uint8_t* out_strand, int32_t out_on_device);
+
+/* ---- ProbMinHash3a per-sequence sketch
+ *      SeqSketcher::sketch_probminhash3a   src/sketching/seqsketchjaccard.rs:211-260
+ *      ProbHash3aSketch::sketch_compressedkmer   src/sketching/setsketchert.rs:121-157
+ * One signature of m slots per sequence: slot j holds the hashed k-mer whose
+ * weighted exponential point is minimal in slot j (0 for an untouched slot).
+ * sig: nseq * m elements of 4 bytes (u32 k-mer types) or 8 bytes (u64 types),
+ * row i = sequence i.  m >= 2. */
+int32_t kmu_sketch_pmh3a(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, int32_t kmer_type, int32_t hash_kind,
+                         uint32_t m, void* sig, int32_t sig_on_device);
+/* one-shot host form: upload (pinned double-buffered chunks), sketch, download. */
+int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t packed_bytes, const uint64_t* byte_off,
+                              const uint64_t* nbases, uint64_t nseq, uint32_t k, int32_t kmer_type, int32_t hash_kind,
+                              uint32_t m, void* sig);
+
+/* ---- timing of the last compute call on the context (CUDA events on its stream) ----- */
+typedef struct kmu_times {
+    float kernel_ms;    /* device time of the compute kernels of the last call */
+    float h2d_ms;       /* host->device copies of the last call (0 if none) */
+    float d2h_ms;       /* device->host copies of the last call (0 if none) */
+    uint64_t h2d_bytes; /* bytes copied host->device by the last call */
+    uint64_t d2h_bytes; /* bytes copied device->host by the last call */
+    uint64_t launches;  /* kernels launched by the last call */
+} kmu_times;
+int32_t kmu_last_times(const kmu_ctx* ctx, kmu_times* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMERUTILS_B200_H */

@@ -1,0 +1,863 @@
+// kmu_capi.cu -- the extern "C" boundary (include/kmerutils_b200.h): contexts, sequence
+// batches resident in HBM, launch policy of the kernels.  No CPU fallback anywhere: every
+// compute entry point needs a CUDA device and fails with KMU_ECUDA otherwise.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <initializer_list>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/kmerutils_b200.h"
+#include "kmu_kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int32_t fail(int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) return fail(KMU_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+constexpr size_t SMEM_BUDGET = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
+constexpr size_t SEQ_ALIGN = 16;
+constexpr size_t TAIL_SLACK = 64;
+
+// growable device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct kmu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    uint64_t launches = 0;
+    kmu_times last{};
+    cudaEvent_t ev[6]{};  // k0 k1 h0 h1 d0 d1
+    int sm_count = 148;
+    // scratch
+    DevBuf order, counters, table_scratch, slot_scratch, overflow, sig_dev, misc;
+    bool table_scratch_clean = false;
+    PinnedBuf pinned;
+};
+
+struct kmu_seqbatch {
+    int device = 0;
+    uint8_t* packed = nullptr;
+    uint64_t* byte_off = nullptr;
+    uint64_t* nbases = nullptr;
+    uint64_t nseq = 0;
+    uint64_t packed_bytes = 0;  // without the tail slack
+    uint64_t total_bases = 0;
+    std::vector<uint64_t> h_nbases;
+    std::vector<uint64_t> h_byte_off;
+};
+
+namespace {
+
+inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// byte layout of a batch: every sequence on a 16-byte boundary
+uint64_t layout_offsets(const uint64_t* nbases, uint64_t nseq, std::vector<uint64_t>& off) {
+    off.resize(nseq);
+    uint64_t cur = 0;
+    for (uint64_t i = 0; i < nseq; ++i) {
+        off[i] = cur;
+        cur += align_up((nbases[i] + 3) / 4, SEQ_ALIGN);
+    }
+    return cur;
+}
+
+int32_t batch_alloc(kmu_ctx* ctx, const uint64_t* nbases, uint64_t nseq, kmu_seqbatch** out) {
+    auto* b = new kmu_seqbatch();
+    b->device = ctx->device;
+    b->nseq = nseq;
+    b->h_nbases.assign(nbases, nbases + nseq);
+    b->packed_bytes = layout_offsets(nbases, nseq, b->h_byte_off);
+    for (uint64_t i = 0; i < nseq; ++i) b->total_bases += nbases[i];
+    cudaError_t e = cudaMalloc((void**)&b->packed, b->packed_bytes + TAIL_SLACK);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->byte_off, sizeof(uint64_t) * (nseq + 1));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->nbases, sizeof(uint64_t) * (nseq + 1));
+    if (e != cudaSuccess) {
+        kmu_seqbatch_destroy(b);
+        return fail(KMU_ENOMEM, "cudaMalloc of a %llu byte batch failed: %s", (unsigned long long)b->packed_bytes,
+                    cudaGetErrorString(e));
+    }
+    *out = b;
+    return KMU_OK;
+}
+
+int32_t batch_upload_meta(kmu_ctx* ctx, kmu_seqbatch* b) {
+    if (b->nseq == 0) return KMU_OK;
+    CUDA_TRY(cudaMemcpyAsync(b->byte_off, b->h_byte_off.data(), sizeof(uint64_t) * b->nseq, cudaMemcpyHostToDevice,
+                             ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(b->nbases, b->h_nbases.data(), sizeof(uint64_t) * b->nseq, cudaMemcpyHostToDevice,
+                             ctx->stream));
+    return KMU_OK;
+}
+
+bool kmer_type_accepts(uint32_t k, int type) {
+    switch (type) {
+        case KMU_KMER32: return k >= 1 && k <= 14;   // src/base/kmergenerator.rs:311, kmer32bit.rs:68-76
+        case KMU_KMER16B32: return k == 16;          // src/base/kmergenerator.rs:218-220
+        case KMU_KMER64: return k >= 1 && k <= 32;   // src/base/kmergenerator.rs:415
+        default: return false;
+    }
+}
+
+struct ScopedDevice {
+    int prev = -1;
+    explicit ScopedDevice(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~ScopedDevice() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+void parallel_copy(uint8_t* dst, const std::vector<uint64_t>& dst_off, const uint8_t* const* ptrs, const uint8_t* base,
+                   const uint64_t* src_off, const uint64_t* nbases, uint64_t nseq) {
+    unsigned nt = std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
+    if (nseq < 4096) nt = 1;
+    auto work = [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+            const uint8_t* src = ptrs ? ptrs[i] : base + src_off[i];
+            uint64_t nb = (nbases[i] + 3) / 4;
+            std::memcpy(dst + dst_off[i], src, nb);
+            uint64_t padded = align_up(nb, SEQ_ALIGN);
+            if (padded > nb) std::memset(dst + dst_off[i] + nb, 0, padded - nb);
+        }
+    };
+    if (nt == 1) {
+        work(0, nseq);
+        return;
+    }
+    std::vector<std::thread> th;
+    uint64_t per = (nseq + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        uint64_t lo = t * per, hi = std::min(nseq, lo + per);
+        if (lo < hi) th.emplace_back(work, lo, hi);
+    }
+    for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+const char* kmu_last_error(void) { return g_err.c_str(); }
+const char* kmu_version(void) { return "kmerutils_b200 0.1.0 (sm_100a)"; }
+
+int32_t kmu_ctx_create(int32_t device, kmu_ctx** out) {
+    if (!out) return fail(KMU_EINVAL, "ctx output pointer is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(KMU_ECUDA, "no CUDA device (%s): this library has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(KMU_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    ScopedDevice sd(device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(KMU_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    auto* c = new kmu_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    if (e != cudaSuccess) {
+        kmu_ctx_destroy(c);
+        return fail(KMU_ECUDA, "context creation failed: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return KMU_OK;
+}
+
+void kmu_ctx_destroy(kmu_ctx* c) {
+    if (!c) return;
+    ScopedDevice sd(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto* b : {&c->order, &c->counters, &c->table_scratch, &c->slot_scratch, &c->overflow, &c->sig_dev, &c->misc})
+        b->release();
+    c->pinned.release();
+    for (auto& ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+uint64_t kmu_launch_count(const kmu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* kmu_ctx_stream(kmu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int32_t kmu_ctx_sync(kmu_ctx* ctx) {
+    if (!ctx) return fail(KMU_EINVAL, "null context");
+    ScopedDevice sd(ctx->device);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return KMU_OK;
+}
+
+int32_t kmu_last_times(const kmu_ctx* ctx, kmu_times* out) {
+    if (!ctx || !out) return fail(KMU_EINVAL, "null argument");
+    *out = ctx->last;
+    return KMU_OK;
+}
+
+// ---- batches -------------------------------------------------------------------------
+void kmu_seqbatch_destroy(kmu_seqbatch* b) {
+    if (!b) return;
+    ScopedDevice sd(b->device);
+    if (b->packed) cudaFree(b->packed);
+    if (b->byte_off) cudaFree(b->byte_off);
+    if (b->nbases) cudaFree(b->nbases);
+    delete b;
+}
+uint64_t kmu_seqbatch_nseq(const kmu_seqbatch* b) { return b ? b->nseq : 0; }
+uint64_t kmu_seqbatch_total_bases(const kmu_seqbatch* b) { return b ? b->total_bases : 0; }
+uint64_t kmu_seqbatch_packed_bytes(const kmu_seqbatch* b) { return b ? b->packed_bytes : 0; }
+
+static int32_t batch_from_host(kmu_ctx* ctx, const uint8_t* const* ptrs, const uint8_t* base, uint64_t base_bytes,
+                               const uint64_t* src_off, const uint64_t* nbases, uint64_t nseq, kmu_seqbatch** out) {
+    if (!ctx || !out || (nseq && !nbases)) return fail(KMU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    kmu_seqbatch* b = nullptr;
+    int32_t rc = batch_alloc(ctx, nbases, nseq, &b);
+    if (rc) return rc;
+    ctx->last = kmu_times{};
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    // already in the batch layout? then one straight copy from the caller's buffer
+    bool same_layout = base != nullptr;
+    if (same_layout) {
+        for (uint64_t i = 0; i < nseq; ++i)
+            if (src_off[i] != b->h_byte_off[i]) {
+                same_layout = false;
+                break;
+            }
+        if (same_layout && base_bytes < b->packed_bytes) same_layout = false;
+    }
+    cudaError_t e = cudaSuccess;
+    if (b->packed_bytes) {
+        if (same_layout) {
+            e = cudaMemcpyAsync(b->packed, base, b->packed_bytes, cudaMemcpyHostToDevice, ctx->stream);
+        } else {
+            e = ctx->pinned.reserve(b->packed_bytes);
+            if (e == cudaSuccess) {
+                parallel_copy((uint8_t*)ctx->pinned.p, b->h_byte_off, ptrs, base, src_off, nbases, nseq);
+                e = cudaMemcpyAsync(b->packed, ctx->pinned.p, b->packed_bytes, cudaMemcpyHostToDevice, ctx->stream);
+            }
+        }
+    }
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->packed + b->packed_bytes, 0, TAIL_SLACK, ctx->stream);
+    if (e == cudaSuccess) rc = batch_upload_meta(ctx, b);
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    if (e == cudaSuccess && rc == KMU_OK) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess || rc) {
+        kmu_seqbatch_destroy(b);
+        return rc ? rc : fail(KMU_ECUDA, "batch upload failed: %s", cudaGetErrorString(e));
+    }
+    cudaEventElapsedTime(&ctx->last.h2d_ms, ctx->ev[2], ctx->ev[3]);
+    ctx->last.h2d_bytes = b->packed_bytes + 2 * sizeof(uint64_t) * nseq;
+    *out = b;
+    return KMU_OK;
+}
+
+int32_t kmu_seqbatch_from_ptrs(kmu_ctx* ctx, const uint8_t* const* seq_ptrs, const uint64_t* nbases, uint64_t nseq,
+                               kmu_seqbatch** batch) {
+    if (nseq && !seq_ptrs) return fail(KMU_EINVAL, "null sequence pointer array");
+    return batch_from_host(ctx, seq_ptrs, nullptr, 0, nullptr, nbases, nseq, batch);
+}
+
+int32_t kmu_seqbatch_from_packed(kmu_ctx* ctx, const uint8_t* packed, uint64_t packed_bytes, const uint64_t* byte_off,
+                                 const uint64_t* nbases, uint64_t nseq, kmu_seqbatch** batch) {
+    if (nseq && (!packed || !byte_off)) return fail(KMU_EINVAL, "null packed buffer / offsets");
+    for (uint64_t i = 0; i < nseq; ++i)
+        if (byte_off[i] + (nbases[i] + 3) / 4 > packed_bytes)
+            return fail(KMU_EINVAL, "sequence %llu overruns the packed buffer", (unsigned long long)i);
+    return batch_from_host(ctx, nullptr, packed, packed_bytes, byte_off, nbases, nseq, batch);
+}
+
+int32_t kmu_seqbatch_synth(kmu_ctx* ctx, uint64_t seed, const uint64_t* nbases, uint64_t nseq, kmu_seqbatch** out) {
+    if (!ctx || !out || (nseq && !nbases)) return fail(KMU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    kmu_seqbatch* b = nullptr;
+    int32_t rc = batch_alloc(ctx, nbases, nseq, &b);
+    if (rc) return rc;
+    rc = batch_upload_meta(ctx, b);
+    // first_base = exclusive prefix sum of nbases (one stream for the whole batch)
+    std::vector<uint64_t> first(nseq);
+    uint64_t acc = 0;
+    for (uint64_t i = 0; i < nseq; ++i) {
+        first[i] = acc;
+        acc += nbases[i];
+    }
+    cudaError_t e = ctx->misc.reserve(sizeof(uint64_t) * (nseq + 1));
+    if (e == cudaSuccess && nseq)
+        e = cudaMemcpyAsync(ctx->misc.p, first.data(), sizeof(uint64_t) * nseq, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = kmu::launch_synth_packed(b->packed, b->byte_off, b->nbases, (const uint64_t*)ctx->misc.p, nseq,
+                                     (b->packed_bytes + TAIL_SLACK) / 4, seed, ctx->stream);
+    ctx->launches += 1;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess || rc) {
+        kmu_seqbatch_destroy(b);
+        return rc ? rc : fail(KMU_ECUDA, "synthetic batch generation failed: %s", cudaGetErrorString(e));
+    }
+    *out = b;
+    return KMU_OK;
+}
+
+int32_t kmu_seqbatch_from_ascii(kmu_ctx* ctx, const uint8_t* ascii, const uint64_t* ascii_off, uint64_t nseq,
+                                int32_t drop_invalid, uint64_t* invalid_counts, kmu_seqbatch** out) {
+    if (!ctx || !out || (nseq && (!ascii || !ascii_off))) return fail(KMU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    const uint64_t total_ascii = nseq ? ascii_off[nseq] : 0;
+    DevBuf d_ascii, d_off, d_bad;
+    auto cleanup = [&]() {
+        d_ascii.release();
+        d_off.release();
+        d_bad.release();
+    };
+    cudaError_t e = d_ascii.reserve(total_ascii + 16);
+    if (e == cudaSuccess) e = d_off.reserve(sizeof(uint64_t) * (nseq + 1));
+    if (e == cudaSuccess) e = d_bad.reserve(sizeof(uint64_t) * (nseq + 1));
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(KMU_ENOMEM, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    if (total_ascii) e = cudaMemcpyAsync(d_ascii.p, ascii, total_ascii, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_off.p, ascii_off, sizeof(uint64_t) * (nseq + 1), cudaMemcpyHostToDevice, ctx->stream);
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    if (e == cudaSuccess)
+        e = kmu::launch_count_invalid((const uint8_t*)d_ascii.p, (const uint64_t*)d_off.p, nseq, (uint64_t*)d_bad.p,
+                                      ctx->stream);
+    std::vector<uint64_t> bad(nseq), nb(nseq);
+    if (e == cudaSuccess && nseq)
+        e = cudaMemcpyAsync(bad.data(), d_bad.p, sizeof(uint64_t) * nseq, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(KMU_ECUDA, "ASCII upload / validation failed: %s", cudaGetErrorString(e));
+    }
+    ctx->launches += 1;
+    uint64_t nbad_total = 0;
+    for (uint64_t i = 0; i < nseq; ++i) {
+        uint64_t len = ascii_off[i + 1] - ascii_off[i];
+        nbad_total += bad[i];
+        nb[i] = drop_invalid ? len - bad[i] : len;
+    }
+    if (invalid_counts) std::copy(bad.begin(), bad.end(), invalid_counts);
+    if (!drop_invalid && nbad_total) {
+        cleanup();
+        // Alphabet2b::encode panics on the first such character (alphabet.rs:125)
+        return fail(KMU_EINVAL, "pattern not a code in alphabet_2b: %llu non-ACGT characters",
+                    (unsigned long long)nbad_total);
+    }
+    kmu_seqbatch* b = nullptr;
+    int32_t rc = batch_alloc(ctx, nb.data(), nseq, &b);
+    if (rc) {
+        cleanup();
+        return rc;
+    }
+    rc = batch_upload_meta(ctx, b);
+    e = cudaMemsetAsync(b->packed, 0, b->packed_bytes + TAIL_SLACK, ctx->stream);
+    if (e == cudaSuccess)
+        e = kmu::launch_pack_ascii((const uint8_t*)d_ascii.p, (const uint64_t*)d_off.p, b->byte_off, b->nbases, nseq,
+                                   drop_invalid, b->packed, ctx->stream);
+    ctx->launches += 1;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (e != cudaSuccess || rc) {
+        kmu_seqbatch_destroy(b);
+        return rc ? rc : fail(KMU_ECUDA, "ASCII packing failed: %s", cudaGetErrorString(e));
+    }
+    cudaEventElapsedTime(&ctx->last.h2d_ms, ctx->ev[2], ctx->ev[3]);
+    ctx->last.h2d_bytes = total_ascii + sizeof(uint64_t) * (nseq + 1);
+    ctx->last.launches = 2;
+    *out = b;
+    return KMU_OK;
+}
+
+int32_t kmu_seqbatch_download(kmu_ctx* ctx, const kmu_seqbatch* b, uint8_t* packed_out, uint64_t* byte_off_out,
+                              uint64_t* nbases_out) {
+    if (!ctx || !b) return fail(KMU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    if (packed_out && b->packed_bytes)
+        CUDA_TRY(cudaMemcpyAsync(packed_out, b->packed, b->packed_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (byte_off_out) std::copy(b->h_byte_off.begin(), b->h_byte_off.end(), byte_off_out);
+    if (nbases_out) std::copy(b->h_nbases.begin(), b->h_nbases.end(), nbases_out);
+    return KMU_OK;
+}
+
+// ---- k-mer generation / ntHash ----------------------------------------------------------
+uint64_t kmu_kmer_count(const kmu_seqbatch* b, uint32_t k) {
+    if (!b) return 0;
+    uint64_t n = 0;
+    for (uint64_t L : b->h_nbases) n += L >= k ? L - k + 1 : 0;
+    return n;
+}
+
+static int32_t upload_kmer_offsets(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, uint64_t* out_off_host,
+                                   uint64_t* total_out) {
+    std::vector<uint64_t> off(b->nseq + 1);
+    uint64_t acc = 0;
+    for (uint64_t i = 0; i < b->nseq; ++i) {
+        off[i] = acc;
+        uint64_t L = b->h_nbases[i];
+        acc += L >= k ? L - k + 1 : 0;
+    }
+    off[b->nseq] = acc;
+    *total_out = acc;
+    if (out_off_host) std::copy(off.begin(), off.end(), out_off_host);
+    CUDA_TRY(ctx->misc.reserve(sizeof(uint64_t) * (b->nseq + 1)));
+    CUDA_TRY(cudaMemcpyAsync(ctx->misc.p, off.data(), sizeof(uint64_t) * (b->nseq + 1), cudaMemcpyHostToDevice,
+                             ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // `off` is a stack-lifetime pageable buffer
+    return KMU_OK;
+}
+
+int32_t kmu_generate_kmers(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t hash_kind,
+                           void* out, uint64_t* out_off, int32_t out_on_device) {
+    if (!ctx || !b) return fail(KMU_EINVAL, "null argument");
+    if (!kmer_type_accepts(k, kmer_type))
+        return fail(KMU_EINVAL, "KmerSeqIterator cannot support kmer size %u for kmer type %d", k, kmer_type);
+    if (hash_kind < 0 || hash_kind > KMU_HASH_INVHASH) return fail(KMU_EINVAL, "unknown hash kind %d", hash_kind);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    uint64_t total = 0;
+    int32_t rc = upload_kmer_offsets(ctx, b, k, out_off, &total);
+    if (rc) return rc;
+    if (total == 0) return KMU_OK;
+    if (!out) return fail(KMU_EINVAL, "null output buffer");
+    const size_t esz = kmer_type == KMU_KMER64 ? 8 : 4;
+    void* dout = out;
+    if (!out_on_device) {
+        CUDA_TRY(ctx->sig_dev.reserve(total * esz));
+        dout = ctx->sig_dev.p;
+    }
+    kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    CUDA_TRY(kmu::launch_generate_kmers(v, k, kmer_type, hash_kind, (const uint64_t*)ctx->misc.p, dout, ctx->stream));
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    ctx->launches += 1;
+    ctx->last.launches = 1;
+    if (!out_on_device) {
+        cudaEventRecord(ctx->ev[4], ctx->stream);
+        CUDA_TRY(cudaMemcpyAsync(out, dout, total * esz, cudaMemcpyDeviceToHost, ctx->stream));
+        cudaEventRecord(ctx->ev[5], ctx->stream);
+        ctx->last.d2h_bytes = total * esz;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    if (!out_on_device) cudaEventElapsedTime(&ctx->last.d2h_ms, ctx->ev[4], ctx->ev[5]);
+    return KMU_OK;
+}
+
+int32_t kmu_nthash_canonical(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, uint32_t n_multi, uint64_t* out_hash,
+                             uint8_t* out_strand, int32_t out_on_device) {
+    if (!ctx || !b) return fail(KMU_EINVAL, "null argument");
+    if (k < 1 || k > 32) return fail(KMU_EINVAL, "ntHash is defined here for 1 <= k <= 32, got %u", k);
+    if (n_multi < 1) return fail(KMU_EINVAL, "n_multi must be >= 1");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    uint64_t total = 0;
+    int32_t rc = upload_kmer_offsets(ctx, b, k, nullptr, &total);
+    if (rc) return rc;
+    if (total == 0) return KMU_OK;
+    if (!out_hash) return fail(KMU_EINVAL, "null output buffer");
+    uint64_t* dh = out_hash;
+    uint8_t* ds = out_strand;
+    const size_t hbytes = total * n_multi * sizeof(uint64_t);
+    if (!out_on_device) {
+        CUDA_TRY(ctx->sig_dev.reserve(hbytes + total + 16));
+        dh = (uint64_t*)ctx->sig_dev.p;
+        ds = out_strand ? (uint8_t*)ctx->sig_dev.p + hbytes : nullptr;
+    }
+    kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    CUDA_TRY(kmu::launch_nthash(v, k, n_multi, (const uint64_t*)ctx->misc.p, dh, ds, ctx->stream));
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    ctx->launches += 1;
+    ctx->last.launches = 1;
+    if (!out_on_device) {
+        cudaEventRecord(ctx->ev[4], ctx->stream);
+        CUDA_TRY(cudaMemcpyAsync(out_hash, dh, hbytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_strand) CUDA_TRY(cudaMemcpyAsync(out_strand, ds, total, cudaMemcpyDeviceToHost, ctx->stream));
+        cudaEventRecord(ctx->ev[5], ctx->stream);
+        ctx->last.d2h_bytes = hbytes + (out_strand ? total : 0);
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    if (!out_on_device) cudaEventElapsedTime(&ctx->last.d2h_ms, ctx->ev[4], ctx->ev[5]);
+    return KMU_OK;
+}
+
+// ---- ProbMinHash3a --------------------------------------------------------------------
+namespace {
+
+struct LaunchClass {
+    uint64_t first, count;  // range of `order`
+    uint64_t nk_max;
+    int mode;               // 0 histogram, 1 table
+    bool table_global;
+};
+
+// geometry of one launch for sequences of at most nk_max k-mers
+struct Geometry {
+    uint32_t team_warps, teams_per_cta, regionA_bytes, slots_smem_bytes, team_smem_bytes;
+    int block;
+    size_t smem;
+    uint64_t table_entries_global;  // per team, 0 if the table lives in shared memory
+};
+
+uint64_t pow2_at_least(uint64_t x) {
+    uint64_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+Geometry make_geometry(uint64_t nk_max, int mode, uint32_t k, uint32_t m, bool key64, bool force_global_table) {
+    Geometry g{};
+    const size_t entry = kmu::pmh3a_entry_bytes(key64);
+    const size_t qitem = kmu::pmh3a_qitem_bytes(key64);
+    // ~128 k-mers per warp
+    uint32_t tw = 1;
+    while (tw < 32 && (uint64_t)tw * 128 < nk_max) tw <<= 1;
+    uint64_t regionA;
+    g.table_entries_global = 0;
+    if (mode == 0) {
+        regionA = (1ull << (2 * k)) * 2;
+        if (regionA < 16) regionA = 16;
+    } else {
+        uint64_t entries = pow2_at_least(std::max<uint64_t>(64, 2 * nk_max));
+        regionA = entries * entry;
+        if (force_global_table || regionA > 128 * 1024) {
+            g.table_entries_global = entries;
+            regionA = 16;
+        }
+    }
+    const uint64_t slots = (uint64_t)m * 16;
+    const uint64_t fixed = regionA + (uint64_t)tw * 64 * qitem + 32;
+    const bool slots_in_smem = fixed + slots <= SMEM_BUDGET;
+    const uint64_t team_bytes = align_up(slots_in_smem ? fixed + slots : fixed, 16);
+    uint32_t max_teams = 32 / tw;
+    if (tw > 1 && max_teams > 15) max_teams = 15;  // named barriers 1..15
+    uint32_t teams = std::min<uint32_t>(max_teams, (uint32_t)(SMEM_BUDGET / team_bytes));
+    if (teams == 0) teams = 1;
+    g.team_warps = tw;
+    g.teams_per_cta = teams;
+    g.regionA_bytes = (uint32_t)regionA;
+    g.slots_smem_bytes = slots_in_smem ? (uint32_t)slots : 0;
+    g.team_smem_bytes = (uint32_t)team_bytes;
+    g.block = (int)(tw * 32 * teams);
+    g.smem = (size_t)team_bytes * teams;
+    return g;
+}
+
+}  // namespace
+
+static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type,
+                                   int32_t hash_kind, uint32_t m, void* d_sig) {
+    const bool key64 = kmer_type == KMU_KMER64;
+    const size_t vsz = key64 ? 8 : 4;
+    const uint64_t nseq = b->nseq;
+    cudaStream_t st = ctx->stream;
+    uint64_t launches = 0;
+
+    // ---- order sequences longest first (8 buckets per octave of the k-mer count) -------
+    CUDA_TRY(ctx->order.reserve(sizeof(uint32_t) * (nseq + 1)));
+    CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256)));
+    unsigned long long* d_hist = (unsigned long long*)ctx->counters.p;
+    unsigned long long* d_cursor = d_hist + kmu::LEN_BUCKETS;
+    unsigned long long* d_work = d_cursor + kmu::LEN_BUCKETS;  // 128 work counters
+    unsigned long long* d_ovf_count = d_work + 128;
+    CUDA_TRY(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256), st));
+    CUDA_TRY(kmu::launch_len_hist(b->nbases, nseq, k, d_hist, st));
+    ++launches;
+    std::vector<unsigned long long> hist(kmu::LEN_BUCKETS), cursor(kmu::LEN_BUCKETS);
+    CUDA_TRY(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned long long) * kmu::LEN_BUCKETS, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    unsigned long long acc = 0;
+    for (int i = 0; i < kmu::LEN_BUCKETS; ++i) {
+        cursor[i] = acc;
+        acc += hist[i];
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_cursor, cursor.data(), sizeof(unsigned long long) * kmu::LEN_BUCKETS, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(kmu::launch_len_scatter(b->nbases, nseq, k, d_cursor, (uint32_t*)ctx->order.p, st));
+    ++launches;
+
+    // ---- launch classes: one per octave of the k-mer count ------------------------------
+    const bool hist_ok = k <= 8;
+    const size_t entry = kmu::pmh3a_entry_bytes(key64);
+    std::vector<LaunchClass> classes;
+    for (int oct = 63; oct >= 0; --oct) {
+        // buckets of this octave: keys oct*8 .. oct*8+7  -> bucket index LEN_BUCKETS-1-key
+        int b_hi = kmu::LEN_BUCKETS - 1 - (oct * 8 + 7), b_lo = kmu::LEN_BUCKETS - 1 - oct * 8;
+        uint64_t cnt = 0;
+        for (int bb = b_hi; bb <= b_lo; ++bb) cnt += hist[bb];
+        if (!cnt) continue;
+        uint64_t nk_max = oct == 63 ? ~0ULL : ((2ULL << oct) - 1);
+        uint64_t table_bytes = pow2_at_least(std::max<uint64_t>(64, 2 * nk_max)) * entry;
+        LaunchClass c{};
+        c.first = cursor[b_hi];
+        c.count = cnt;
+        c.nk_max = nk_max;
+        const uint64_t hist_bytes = (1ull << (2 * k)) * 2;
+        if (hist_ok && (table_bytes > 128 * 1024 || hist_bytes <= table_bytes)) {
+            c.mode = 0;
+            c.table_global = false;
+        } else {
+            c.mode = 1;
+            c.table_global = table_bytes > 128 * 1024;
+        }
+        // merge with the previous class when both are "table in global memory" or both are histogram
+        // with full-size teams: identical geometry, one launch
+        if (!classes.empty()) {
+            LaunchClass& p = classes.back();
+            bool same = p.mode == c.mode && p.table_global == c.table_global &&
+                        ((c.mode == 1 && c.table_global) || (c.mode == 0 && c.nk_max >= 4096));
+            if (same) {
+                p.count += c.count;
+                continue;
+            }
+        }
+        classes.push_back(c);
+    }
+    // exact largest k-mer count (the first class is sized by it, not by its octave bound)
+    uint64_t nk_longest = 0;
+    for (uint64_t L : b->h_nbases) nk_longest = std::max<uint64_t>(nk_longest, L >= k ? L - k + 1 : 0);
+    if (!classes.empty()) classes.front().nk_max = std::min(classes.front().nk_max, nk_longest);
+
+    // ---- parameters common to all launches ------------------------------------------------
+    kmu::Pmh3aParams P{};
+    P.packed = b->packed;
+    P.byte_off = b->byte_off;
+    P.nbases = b->nbases;
+    P.order = (const uint32_t*)ctx->order.p;
+    P.k = k;
+    P.kmer_type = kmer_type;
+    P.hash_kind = hash_kind;
+    P.m = m;
+    P.slot_thresh = (uint32_t)((0x100000000ULL) % m);
+    {
+        // ProbMinHash3a::new : lambda = ln(m / (m-1)); ExpRestricted01::new
+        double lambda = std::log((double)m / (double)(m - 1));
+        P.e.lambda = lambda;
+        P.e.c1 = std::expm1(lambda) / lambda;
+        P.e.c2 = std::log(2.0 / (1.0 + std::exp(-lambda))) / lambda;
+        P.e.c3 = (1.0 - std::exp(-lambda)) / lambda;
+    }
+    P.sig = d_sig;
+    CUDA_TRY(ctx->overflow.reserve(sizeof(uint32_t) * (nseq + 1)));
+    P.overflow_count = d_ovf_count;
+    P.overflow_list = (uint32_t*)ctx->overflow.p;
+
+    auto run_class = [&](const LaunchClass& c, const uint32_t* order, int counter_idx) -> int32_t {
+        Geometry g = make_geometry(c.nk_max, c.mode, k, m, key64, c.table_global);
+        uint64_t teams_needed = c.count;
+        uint64_t ctas_needed = (teams_needed + g.teams_per_cta - 1) / g.teams_per_cta;
+        // CTAs per SM that fit (threads and shared memory)
+        uint32_t per_sm = (uint32_t)std::min<uint64_t>(2048 / g.block, SMEM_BUDGET / std::max<size_t>(g.smem, 1));
+        if (per_sm == 0) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        int grid = (int)std::min<uint64_t>(ctas_needed, (uint64_t)ctx->sm_count * per_sm);
+        kmu::Pmh3aParams Q = P;
+        Q.order = order;
+        Q.first = c.first;
+        Q.count = c.count;
+        Q.work_counter = d_work + counter_idx;
+        Q.team_warps = g.team_warps;
+        Q.team_smem_bytes = g.team_smem_bytes;
+        Q.regionA_bytes = g.regionA_bytes;
+        Q.slots_smem_bytes = g.slots_smem_bytes;
+        Q.slot_scratch = nullptr;
+        Q.table_scratch = nullptr;
+        Q.table_scratch_entries = 0;
+        const uint64_t nteams_total = (uint64_t)grid * g.teams_per_cta;
+        if (g.slots_smem_bytes == 0) {
+            CUDA_TRY(ctx->slot_scratch.reserve(nteams_total * m * sizeof(kmu::Slot)));
+            Q.slot_scratch = (kmu::Slot*)ctx->slot_scratch.p;
+        }
+        if (g.table_entries_global) {
+            // bound the scratch: shrink the grid rather than ask for more than 32 GiB
+            uint64_t per_team = g.table_entries_global * entry;
+            const uint64_t budget = 32ULL << 30;
+            if (per_team * nteams_total > budget) {
+                uint64_t fit_teams = std::max<uint64_t>(1, budget / per_team);
+                grid = (int)std::max<uint64_t>(1, fit_teams / g.teams_per_cta);
+            }
+            uint64_t need = per_team * (uint64_t)grid * g.teams_per_cta;
+            if (need > ctx->table_scratch.cap) ctx->table_scratch_clean = false;
+            cudaError_t e = ctx->table_scratch.reserve(need);
+            if (e != cudaSuccess)
+                return fail(KMU_ENOMEM, "table scratch of %llu bytes: %s", (unsigned long long)need, cudaGetErrorString(e));
+            if (!ctx->table_scratch_clean) {
+                CUDA_TRY(cudaMemsetAsync(ctx->table_scratch.p, 0, ctx->table_scratch.cap, st));
+                ctx->table_scratch_clean = true;  // kernels leave their tables clean
+            }
+            Q.table_scratch = (uint8_t*)ctx->table_scratch.p;
+            Q.table_scratch_entries = g.table_entries_global;
+        }
+        CUDA_TRY(kmu::launch_pmh3a(Q, key64, c.mode, grid, g.block, g.smem, st));
+        ++launches;
+        return KMU_OK;
+    };
+
+    if (classes.size() > 120) return fail(KMU_EINVAL, "too many launch classes");
+    int ci = 0;
+    for (const LaunchClass& c : classes) {
+        int32_t rc = run_class(c, (const uint32_t*)ctx->order.p, ci++);
+        if (rc) return rc;
+    }
+    // ---- u16 histogram counters that wrapped: redo those sequences with u32 table counters ---
+    if (hist_ok) {
+        unsigned long long novf = 0;
+        CUDA_TRY(cudaMemcpyAsync(&novf, d_ovf_count, sizeof(novf), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (novf) {
+            LaunchClass c{};
+            c.first = 0;
+            c.count = novf;
+            c.nk_max = nk_longest;
+            c.mode = 1;
+            c.table_global = true;
+            int32_t rc = run_class(c, (const uint32_t*)ctx->overflow.p, ci++);
+            if (rc) return rc;
+        }
+    }
+    ctx->launches += launches;
+    ctx->last.launches += launches;
+    (void)vsz;
+    return KMU_OK;
+}
+
+int32_t kmu_sketch_pmh3a(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t hash_kind,
+                         uint32_t m, void* sig, int32_t sig_on_device) {
+    if (!ctx || !b) return fail(KMU_EINVAL, "null argument");
+    if (kmer_type != KMU_KMER32 && kmer_type != KMU_KMER16B32 && kmer_type != KMU_KMER64)
+        return fail(KMU_EINVAL, "kmer type %d is not a 2-bit DNA k-mer type", kmer_type);
+    if (!kmer_type_accepts(k, kmer_type))
+        return fail(KMU_EINVAL, "KmerSeqIterator cannot support kmer size %u for kmer type %d", k, kmer_type);
+    if (hash_kind < 0 || hash_kind > KMU_HASH_INVHASH) return fail(KMU_EINVAL, "unknown hash kind %d", hash_kind);
+    if (m < 2) return fail(KMU_EINVAL, "ProbMinHash3a needs at least 2 hash values (m = %u)", m);
+    if (b->nseq == 0) return KMU_OK;
+    if (!sig) return fail(KMU_EINVAL, "null signature buffer");
+    if (b->nseq >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "more than 2^32-1 sequences in one batch");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    const size_t vsz = kmer_type == KMU_KMER64 ? 8 : 4;
+    const size_t sig_bytes = (size_t)b->nseq * m * vsz;
+    void* d_sig = sig;
+    if (!sig_on_device) {
+        CUDA_TRY(ctx->sig_dev.reserve(sig_bytes));
+        d_sig = ctx->sig_dev.p;
+    }
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    int32_t rc = sketch_pmh3a_locked(ctx, b, k, kmer_type, hash_kind, m, d_sig);
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    if (rc) {
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
+    }
+    if (!sig_on_device) {
+        cudaEventRecord(ctx->ev[4], ctx->stream);
+        CUDA_TRY(cudaMemcpyAsync(sig, d_sig, sig_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        cudaEventRecord(ctx->ev[5], ctx->stream);
+        ctx->last.d2h_bytes = sig_bytes;
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->table_scratch_clean = false;
+        return fail(KMU_ECUDA, "ProbMinHash3a sketch kernels failed: %s", cudaGetErrorString(e));
+    }
+    cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    if (!sig_on_device) cudaEventElapsedTime(&ctx->last.d2h_ms, ctx->ev[4], ctx->ev[5]);
+    return KMU_OK;
+}
+
+int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t packed_bytes, const uint64_t* byte_off,
+                              const uint64_t* nbases, uint64_t nseq, uint32_t k, int32_t kmer_type, int32_t hash_kind,
+                              uint32_t m, void* sig) {
+    kmu_seqbatch* b = nullptr;
+    int32_t rc = kmu_seqbatch_from_packed(ctx, packed, packed_bytes, byte_off, nbases, nseq, &b);
+    if (rc) return rc;
+    kmu_times up{};
+    kmu_last_times(ctx, &up);
+    rc = kmu_sketch_pmh3a(ctx, b, k, kmer_type, hash_kind, m, sig, 0);
+    kmu_seqbatch_destroy(b);
+    if (rc == KMU_OK) {
+        ctx->last.h2d_ms = up.h2d_ms;
+        ctx->last.h2d_bytes = up.h2d_bytes;
+    }
+    return rc;
+}
+
+}  // extern "C"

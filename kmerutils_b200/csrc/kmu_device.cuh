@@ -1,0 +1,291 @@
+// kmu_device.cuh -- device-side building blocks shared by every kernel of the
+// B200 k-mer engine: 2-bit window arithmetic, the reference's hash closures, the
+// per-item random streams of the sketchers and the 128-bit slot update.
+//
+// Citations are path:line in the reference tree (jean-pierreBoth/kmerutils v0.0.14);
+// "App. A.x" refers to SURVEY.md appendix A (arithmetic of the un-vendored
+// probminhash / rand / rand_xoshiro crates).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/kmerutils_b200.h"
+#include "kmu_kernels.h"
+
+namespace kmu {
+
+constexpr uint64_t F64_MAX_BITS = 0x7FEFFFFFFFFFFFFFULL;  // f64::MAX, MaxValueTracker's initial value
+
+// ----------------------------------------------------------------------------
+//  2-bit words
+// ----------------------------------------------------------------------------
+// packed bytes hold the first base in their most significant bits (alphabet.rs:162-168);
+// a byte-swapped 32-bit load therefore gives 16 bases, first base in bits 31..30.
+__device__ __forceinline__ uint32_t be32(uint32_t le_word) { return __byte_perm(le_word, 0, 0x0123); }
+
+// reverse complement of a full 32-bit / 64-bit word of bases (kmer16b32bit.rs:43-54,
+// kmer64bit.rs:83-96 before the final shift): complement, reverse the bits, swap the
+// two bits of every pair back.
+__device__ __forceinline__ uint32_t revcomp_word32(uint32_t w) {
+    uint32_t r = __brev(~w);
+    return ((r & 0x55555555u) << 1) | ((r & 0xAAAAAAAAu) >> 1);
+}
+__device__ __forceinline__ uint64_t revcomp_word64(uint64_t w) {
+    uint64_t r = __brevll(~w);
+    return ((r & 0x5555555555555555ULL) << 1) | ((r & 0xAAAAAAAAAAAAAAAAULL) >> 1);
+}
+// reverse complement of a right-aligned k-base value (k >= 1)
+__device__ __forceinline__ uint32_t revcomp_val(uint32_t v, uint32_t k) { return revcomp_word32(v) >> (32 - 2 * k); }
+__device__ __forceinline__ uint64_t revcomp_val(uint64_t v, uint32_t k) { return revcomp_word64(v) >> (64 - 2 * k); }
+
+template <typename V>
+__device__ __forceinline__ V value_mask(uint32_t nbits) {
+    return nbits >= 8 * sizeof(V) ? ~V(0) : ((V(1) << nbits) - 1);
+}
+
+// probminhash::invhash (App. A.6)
+__device__ __forceinline__ uint32_t int32_hash(uint32_t key) {
+    key += ~(key << 15);
+    key ^= (key >> 10);
+    key += (key << 3);
+    key ^= (key >> 6);
+    key += ~(key << 11);
+    key ^= (key >> 16);
+    return key;
+}
+__device__ __forceinline__ uint64_t int64_hash(uint64_t key) {
+    key = (~key) + (key << 21);
+    key = key ^ (key >> 24);
+    key = (key + (key << 3)) + (key << 8);
+    key = key ^ (key >> 14);
+    key = (key + (key << 2)) + (key << 4);
+    key = key ^ (key >> 28);
+    key = key + (key << 31);
+    return key;
+}
+__device__ __forceinline__ uint32_t inv_hash(uint32_t k) { return int32_hash(k); }
+__device__ __forceinline__ uint64_t inv_hash(uint64_t k) { return int64_hash(k); }
+
+// ----------------------------------------------------------------------------
+//  hash closures.  The walker hands out a *pre-key*: the forward
+//  value or, for the canonical kinds, min(value, revcomp value) -- Ord of all
+//  three k-mer types reduces to the value when k is equal (kmer32bit.rs:47-55,
+//  kmer64bit.rs:45-53).  finalize_key() turns the pre-key into fhash(kmer).
+// ----------------------------------------------------------------------------
+__host__ __device__ __forceinline__ bool hash_is_canonical(int hash_kind) {
+    return hash_kind == KMU_HASH_CANON_INVHASH || hash_kind == KMU_HASH_CANON_RAW;
+}
+// header of the k-mer word: Kmer32bit keeps k in its top 4 bits (kmer32bit.rs:68-76)
+__host__ __device__ __forceinline__ uint32_t word_header(int kmer_type, uint32_t k) {
+    return kmer_type == KMU_KMER32 ? (k << 28) : 0u;
+}
+template <typename V>
+__device__ __forceinline__ V finalize_key(V prekey, V header, int hash_kind) {
+    switch (hash_kind) {
+        case KMU_HASH_MASKED_VALUE: return prekey;  // value & (2^(bits*k) - 1): the header is masked off
+        case KMU_HASH_CANON_INVHASH:
+        case KMU_HASH_INVHASH: return inv_hash(V(prekey | header));
+        default: return V(prekey | header);  // IDENTITY_RAW, CANON_RAW: the raw word `.0`
+    }
+}
+
+// ----------------------------------------------------------------------------
+//  Per-item random stream: Xoshiro256++ seeded by SplitMix64 from the
+//  NoHashHasher / FNV value of the key (App. A.1, src/nohasher.rs:22-48)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t nohash_seed(uint32_t key) { return (uint64_t)__byte_perm(key, 0, 0x0123); }
+__device__ __forceinline__ uint64_t nohash_seed(uint64_t key) {
+    uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
+    return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | (uint64_t)__byte_perm(hi, 0, 0x0123);
+}
+template <typename V>
+__device__ __forceinline__ uint64_t fnv1a_seed(V key) {
+    uint64_t h = 0xcbf29ce484222325ULL;
+#pragma unroll
+    for (int i = 0; i < (int)sizeof(V); ++i) {
+        h ^= (uint64_t)((key >> (8 * i)) & 0xFF);
+        h *= 0x100000001b3ULL;
+    }
+    return h;
+}
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+struct Xoshiro256pp {
+    uint64_t s0, s1, s2, s3;
+    __device__ __forceinline__ void seed(uint64_t seed) {
+        uint64_t x = seed;
+        s0 = splitmix(x);
+        s1 = splitmix(x);
+        s2 = splitmix(x);
+        s3 = splitmix(x);
+    }
+    static __device__ __forceinline__ uint64_t splitmix(uint64_t& x) {
+        x += 0x9E3779B97F4A7C15ULL;
+        uint64_t z = x;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    }
+    __device__ __forceinline__ uint64_t next_u64() {
+        uint64_t r = rotl64(s0 + s3, 23) + s0;
+        uint64_t t = s1 << 17;
+        s2 ^= s0;
+        s3 ^= s1;
+        s1 ^= s2;
+        s0 ^= s3;
+        s2 ^= t;
+        s3 = rotl64(s3, 45);
+        return r;
+    }
+    __device__ __forceinline__ uint32_t next_u32() { return (uint32_t)(next_u64() >> 32); }
+    // rand 0.9 Uniform::<f64>::new(0., 1.): 52 mantissa bits, [1,2) - 1 (App. A.2)
+    __device__ __forceinline__ double unif01() {
+        return __longlong_as_double((long long)((next_u64() >> 12) | 0x3FF0000000000000ULL)) - 1.0;
+    }
+    __device__ __forceinline__ float unif01_f32() { return __uint_as_float((next_u32() >> 9) | 0x3F800000u) - 1.0f; }
+    // rand 0.9 UniformUsize (range fits u32): widening multiply on next_u32, reject lo < thresh
+    __device__ __forceinline__ uint32_t unif_range(uint32_t low, uint32_t range, uint32_t thresh) {
+        for (;;) {
+            uint32_t v = next_u32();
+            uint32_t lo = v * range;
+            if (lo >= thresh) return low + __umulhi(v, range);
+        }
+    }
+};
+
+// ExpRestricted01 (App. A.3). The constants are computed on the host with libm
+// (the reference gets them from the same libm through Rust's f64::exp_m1 / ln / exp).
+// every product / sum is an explicit round-to-nearest intrinsic: Rust never
+// contracts a*b+c into an FMA, so neither may nvcc.
+__device__ __forceinline__ double exp01_sample(const Exp01Params& p, Xoshiro256pp& rng) {
+    double x = __dmul_rn(p.c1, rng.unif01());
+    if (x < 1.0) return x;
+    for (;;) {
+        x = rng.unif01();
+        if (x < p.c2) return x;
+        double y = __dmul_rn(0.5, rng.unif01());
+        if (y > __dsub_rn(1.0, x)) {
+            x = __dsub_rn(1.0, x);
+            y = __dsub_rn(1.0, y);
+        }
+        if (x <= __dmul_rn(p.c3, __dsub_rn(1.0, y))) return x;
+        if (__dmul_rn(p.c1, y) <= __dsub_rn(1.0, x)) return x;
+        if (__dmul_rn(__dmul_rn(y, p.c1), p.lambda) <= expm1(__dmul_rn(p.lambda, __dsub_rn(1.0, x)))) return x;
+    }
+}
+
+// ----------------------------------------------------------------------------
+//  Sketch slots: 16-byte records {hbits, key}.  A point (h, key) replaces the
+//  record when (h, key) is lexicographically smaller; h > 0 so the IEEE bit
+//  pattern orders like the value.  One 128-bit compare-and-swap (ATOMS.CAS.128 /
+//  ATOMG.CAS.128 on sm_100a) makes the update atomic for both fields.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void cas128(Slot* addr, uint64_t cmp_h, uint64_t cmp_k, uint64_t new_h, uint64_t new_k,
+                                       uint64_t& old_h, uint64_t& old_k) {
+    asm volatile(
+        "{\n\t.reg .b128 c, n, o;\n\t"
+        "mov.b128 c, {%3, %4};\n\t"
+        "mov.b128 n, {%5, %6};\n\t"
+        "atom.cas.b128 o, [%2], c, n;\n\t"
+        "mov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(old_h), "=l"(old_k)
+        : "l"(addr), "l"(cmp_h), "l"(cmp_k), "l"(new_h), "l"(new_k)
+        : "memory");
+}
+
+__device__ __forceinline__ void slot_update_min(Slot* slot, uint64_t hbits, uint64_t key) {
+    uint64_t cur_h = *(volatile uint64_t*)&slot->hbits;
+    if (hbits > cur_h) return;
+    uint64_t cur_k = *(volatile uint64_t*)&slot->key;
+    for (;;) {
+        if (hbits > cur_h || (hbits == cur_h && key >= cur_k)) return;
+        uint64_t old_h, old_k;
+        cas128(slot, cur_h, cur_k, hbits, key, old_h, old_k);
+        if (old_h == cur_h && old_k == cur_k) return;
+        cur_h = old_h;
+        cur_k = old_k;
+    }
+}
+
+// warp-wide maximum of a u64 through two redux.sync passes (redux is 32-bit)
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+    uint32_t hi = (uint32_t)(v >> 32);
+    uint32_t mhi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    uint32_t lo = hi == mhi ? (uint32_t)v : 0u;
+    uint32_t mlo = __reduce_max_sync(0xFFFFFFFFu, lo);
+    return ((uint64_t)mhi << 32) | mlo;
+}
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) { return ~warp_max_u64(~v); }
+
+// counter based SplitMix64 used by the synthetic generator
+__host__ __device__ __forceinline__ uint64_t synth_z(uint64_t seed, uint64_t i) {
+    uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// ----------------------------------------------------------------------------
+//  K-mer walker.  A thread positions the walker on any base of a sequence and
+//  then pulls one k-mer per roll(): bases come from a left-aligned 64-bit shift
+//  register refilled from big-endian 32-bit words, and the forward and
+//  reverse-complement windows are rolled in registers (KmerSeqIterator::next,
+//  kmergenerator.rs:75-106, yields the same windows one `push` at a time).
+//  The reader looks ahead by at most one 32-bit word past the word holding the
+//  last base it is asked for; batches keep that much slack after every sequence.
+// ----------------------------------------------------------------------------
+template <typename V>
+struct KmerWalker {
+    V fwd, rc, mask;
+    uint64_t sr;  // upcoming bases, left aligned
+    int nb;       // valid bits in sr; > 32 after every refill
+    const uint32_t* wp;
+    uint32_t rc_shift;  // 2k - 2
+
+    __device__ __forceinline__ void refill() {
+        if (nb <= 32) {
+            sr |= (uint64_t)be32(__ldg(wp)) << (32 - nb);
+            ++wp;
+            nb += 32;
+        }
+    }
+    // next n bases (1 <= n <= 16) as a right-aligned value
+    __device__ __forceinline__ uint32_t take(uint32_t n) {
+        uint32_t v = (uint32_t)(sr >> (64 - 2 * n));
+        sr <<= 2 * n;
+        nb -= 2 * n;
+        refill();
+        return v;
+    }
+    // after start(words, p0, k) the first roll() yields the k-mer starting at base p0
+    __device__ __forceinline__ void start(const uint32_t* words, uint64_t p0, uint32_t k) {
+        mask = value_mask<V>(2 * k);
+        rc_shift = 2 * k - 2;
+        wp = words + (p0 >> 4);
+        uint32_t o = (uint32_t)(p0 & 15);
+        sr = (uint64_t)be32(__ldg(wp)) << (32 + 2 * o);
+        ++wp;
+        nb = 32 - 2 * o;
+        refill();
+        uint32_t kk = k - 1;
+        V pre = 0;
+        if (kk > 16) {
+            pre = (V)take(16);
+            kk -= 16;
+            pre = (V)(pre << (2 * kk)) | (V)take(kk);
+        } else if (kk > 0) {
+            pre = (V)take(kk);
+        }
+        fwd = pre;
+        rc = k > 1 ? (V)(revcomp_val(pre, k - 1) << 2) : V(0);
+    }
+    __device__ __forceinline__ void roll() {
+        uint32_t b = take(1);
+        fwd = (V)(((fwd << 2) | (V)b) & mask);
+        rc = (V)((rc >> 2) | ((V)(3u - b) << rc_shift));
+    }
+    __device__ __forceinline__ V prekey(bool canonical) const { return canonical ? (fwd < rc ? fwd : rc) : fwd; }
+};
+
+}  // namespace kmu

@@ -1,0 +1,178 @@
+// kmu_extract.cu -- materialising kernels: all k-mers of every sequence mapped through a hash
+// closure (KmerGenerator::generate_kmer, src/base/kmergenerator.rs:162-167 +
+// KmerSeqIterator::next :75-106), and canonical ntHash (src/base/kmer.rs:74-94,
+// src/base/nthash.rs:63-72).  Both are streaming kernels bounded by their HBM writes.
+#include <cstdint>
+
+#include "kmu_device.cuh"
+#include "kmu_kernels.h"
+
+namespace kmu {
+
+// first sequence s with out_off[s+1] > e  (out_off has nseq+1 entries, non-decreasing)
+__device__ __forceinline__ uint64_t seq_of_element(const uint64_t* __restrict__ out_off, uint64_t nseq, uint64_t e) {
+    uint64_t lo = 0, hi = nseq;  // invariant: out_off[lo] <= e < out_off[hi]
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (out_off[mid] <= e) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void kmer_offsets_kernel(const uint64_t* __restrict__ nbases, uint64_t nseq, uint32_t k, uint64_t* nk) {
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < nseq; s += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t L = nbases[s];
+        nk[s] = L >= k ? L - k + 1 : 0;
+    }
+}
+
+cudaError_t launch_kmer_offsets(const uint64_t* nbases, uint64_t nseq, uint32_t k, uint64_t* out, cudaStream_t stream) {
+    if (nseq == 0) return cudaSuccess;
+    int block = 256;
+    uint64_t want = (nseq + block - 1) / block;
+    int grid = (int)(want < 148ull * 4 ? want : 148ull * 4);
+    kmer_offsets_kernel<<<grid, block, 0, stream>>>(nbases, nseq, k, out);
+    return cudaGetLastError();
+}
+
+// every thread produces T consecutive output elements
+template <typename V, int T>
+__global__ void __launch_bounds__(256) generate_kmers_kernel(SeqView b, uint32_t k, int kmer_type, int hash_kind,
+                                                              const uint64_t* __restrict__ out_off, V* __restrict__ out) {
+    const uint64_t total = out_off[b.nseq];
+    const V header = (V)word_header(kmer_type, k);
+    const bool canonical = hash_is_canonical(hash_kind);
+    for (uint64_t e0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * T; e0 < total;
+         e0 += (uint64_t)gridDim.x * blockDim.x * T) {
+        uint64_t s = seq_of_element(out_off, b.nseq, e0);
+        uint64_t s_begin = out_off[s], s_end = out_off[s + 1];
+        KmerWalker<V> wk;
+        wk.start((const uint32_t*)(b.packed + b.byte_off[s]), e0 - s_begin, k);
+        V vals[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            uint64_t e = e0 + t;
+            vals[t] = 0;
+            if (e < total) {
+                if (e >= s_end) {  // crossed into the next non-empty sequence
+                    do {
+                        ++s;
+                        s_end = out_off[s + 1];
+                    } while (e >= s_end);
+                    wk.start((const uint32_t*)(b.packed + b.byte_off[s]), 0, k);
+                }
+                wk.roll();
+                vals[t] = finalize_key<V>(wk.prekey(canonical), header, hash_kind);
+            }
+        }
+        if (e0 + T <= total) {
+            constexpr int VEC = 16 / sizeof(V);
+#pragma unroll
+            for (int t = 0; t < T; t += VEC) {
+                uint4 v;
+                if (sizeof(V) == 4) {
+                    v = make_uint4((uint32_t)vals[t], (uint32_t)vals[t + 1], (uint32_t)vals[t + 2], (uint32_t)vals[t + 3]);
+                } else {
+                    uint64_t a = (uint64_t)vals[t], c = (uint64_t)vals[t + 1 < T ? t + 1 : t];
+                    v = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)c, (uint32_t)(c >> 32));
+                }
+                *(uint4*)(out + e0 + t) = v;
+            }
+        } else {
+            for (int t = 0; t < T && e0 + t < total; ++t) out[e0 + t] = vals[t];
+        }
+    }
+}
+
+cudaError_t launch_generate_kmers(const SeqView& b, uint32_t k, int kmer_type, int hash_kind, const uint64_t* out_off,
+                                  void* out, cudaStream_t stream) {
+    if (b.nseq == 0) return cudaSuccess;
+    const int block = 256;
+    const int grid = 148 * 8;
+    bool key64 = kmer_type == KMU_KMER64 || kmer_type == KMU_KMERAA64;
+    if (key64)
+        generate_kmers_kernel<uint64_t, 8><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint64_t*)out);
+    else
+        generate_kmers_kernel<uint32_t, 8><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint32_t*)out);
+    return cudaGetLastError();
+}
+
+// ---- ntHash -----------------------------------------------------------------------------------
+// seeds: src/base/nthash.rs:17-20
+__constant__ uint64_t NT_SEED[4] = {0x3c8bfbb395c60474ULL, 0x3193c18562a02b4cULL, 0x20323ed082572324ULL,
+                                    0x295549f54be24456ULL};
+__device__ __forceinline__ uint64_t rotl_var(uint64_t x, uint32_t r) {
+    r &= 63;
+    return r ? (x << r) | (x >> (64 - r)) : x;
+}
+__device__ __forceinline__ uint64_t nt_seed(uint32_t b) {
+    // select without a memory access: 4 immediates
+    uint64_t lo = (b & 1) ? 0x3193c18562a02b4cULL : 0x3c8bfbb395c60474ULL;
+    uint64_t hi = (b & 1) ? 0x295549f54be24456ULL : 0x20323ed082572324ULL;
+    return (b & 2) ? hi : lo;
+}
+
+template <int T>
+__global__ void __launch_bounds__(256) nthash_kernel(SeqView b, uint32_t k, uint32_t n_multi,
+                                                      const uint64_t* __restrict__ out_off, uint64_t* __restrict__ out_hash,
+                                                      uint8_t* __restrict__ out_strand) {
+    const uint64_t total = out_off[b.nseq];
+    const uint64_t mult = (uint64_t)k * 0x90b45d39fb6da1faULL;  // nthash.rs:13,68 (wrapping)
+    for (uint64_t e0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * T; e0 < total;
+         e0 += (uint64_t)gridDim.x * blockDim.x * T) {
+        uint64_t s = seq_of_element(out_off, b.nseq, e0);
+        uint64_t s_end = out_off[s + 1];
+        KmerWalker<uint64_t> wk;
+        wk.start((const uint32_t*)(b.packed + b.byte_off[s]), e0 - out_off[s], k);
+        bool fresh = true;
+        uint64_t f = 0, r = 0;
+        for (int t = 0; t < T; ++t) {
+            uint64_t e = e0 + t;
+            if (e >= total) break;
+            if (e >= s_end) {
+                do {
+                    ++s;
+                    s_end = out_off[s + 1];
+                } while (e >= s_end);
+                wk.start((const uint32_t*)(b.packed + b.byte_off[s]), 0, k);
+                fresh = true;
+            }
+            uint32_t old_base = (uint32_t)(wk.fwd >> (2 * k - 2)) & 3u;  // leftmost base of the previous k-mer
+            wk.roll();
+            if (fresh) {
+                // nthash_canonical_init (kmer.rs:74-94)
+                f = 0;
+                r = 0;
+                for (uint32_t i = 0; i < k; ++i) {
+                    uint32_t base = (uint32_t)(wk.fwd >> (2 * (k - 1 - i))) & 3u;
+                    f ^= rotl_var(nt_seed(base), k - 1 - i);
+                    r ^= rotl_var(nt_seed(3u - base), i);
+                }
+                fresh = false;
+            } else {
+                // ntHash recurrence: identical values to re-initialising on the new window
+                uint32_t nb = (uint32_t)wk.fwd & 3u;
+                f = rotl_var(f, 1) ^ rotl_var(nt_seed(old_base), k) ^ nt_seed(nb);
+                r = rotl_var(r, 63) ^ rotl_var(nt_seed(3u - old_base), 63) ^ rotl_var(nt_seed(3u - nb), k - 1);
+            }
+            uint64_t h0 = f <= r ? f : r;
+            uint64_t* o = out_hash + e * n_multi;
+            o[0] = h0;
+            for (uint32_t i = 1; i < n_multi; ++i) {
+                uint64_t tmp = h0 * ((uint64_t)i ^ mult);
+                tmp ^= tmp >> 27;
+                o[i] = tmp;
+            }
+            if (out_strand) out_strand[e] = f <= r ? 0 : 1;
+        }
+    }
+}
+
+cudaError_t launch_nthash(const SeqView& b, uint32_t k, uint32_t n_multi, const uint64_t* out_off, uint64_t* out_hash,
+                          uint8_t* out_strand, cudaStream_t stream) {
+    if (b.nseq == 0) return cudaSuccess;
+    nthash_kernel<8><<<148 * 8, 256, 0, stream>>>(b, k, n_multi, out_off, out_hash, out_strand);
+    return cudaGetLastError();
+}
+
+}  // namespace kmu

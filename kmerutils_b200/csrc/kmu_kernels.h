@@ -1,0 +1,98 @@
+// kmu_kernels.h -- host-visible launch parameters and launchers of the CUDA kernels.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace kmu {
+
+// ExpRestricted01 constants, computed on the host with libm
+struct Exp01Params {
+    double lambda, c1, c2, c3;
+};
+
+// one sketch slot: {bit pattern of the winning point h, key that produced it}
+struct alignas(16) Slot {
+    uint64_t hbits;
+    uint64_t key;
+};
+
+// device view of a sequence batch (see include/kmerutils_b200.h "sequence batches")
+struct SeqView {
+    const uint8_t* packed;     // every sequence starts 16-byte aligned; >= 64 bytes of slack at the end
+    const uint64_t* byte_off;  // nseq
+    const uint64_t* nbases;    // nseq
+    uint64_t nseq;
+};
+
+struct Pmh3aParams {
+    const uint8_t* packed;
+    const uint64_t* byte_off;
+    const uint64_t* nbases;
+    const uint32_t* order;  // sequence ids in processing order (descending length)
+    uint64_t first, count;  // this launch handles order[first .. first+count)
+    unsigned long long* work_counter;
+    uint32_t k;
+    int kmer_type;
+    int hash_kind;
+    uint32_t m;
+    uint32_t slot_thresh;  // 2^32 mod m : rejection threshold of UniformUsize (App. A.2)
+    Exp01Params e;
+    void* sig;  // nseq * m values of V
+    // team / shared memory geometry
+    uint32_t team_warps;
+    uint32_t team_smem_bytes;   // bytes of shared memory per team
+    uint32_t regionA_bytes;     // histogram / table bytes per team (multiple of 16)
+    uint32_t slots_smem_bytes;  // 16 * m rounded up, or 0 when the slots live in slot_scratch
+    Slot* slot_scratch;
+    uint8_t* table_scratch;  // global table scratch (zeroed), table_scratch_entries entries per team
+    uint64_t table_scratch_entries;
+    unsigned long long* overflow_count;
+    uint32_t* overflow_list;
+};
+
+size_t pmh3a_qitem_bytes(bool key64);
+size_t pmh3a_entry_bytes(bool key64);
+cudaError_t launch_pmh3a(const Pmh3aParams& P, bool key64, int mode, int grid, int block, size_t smem,
+                         cudaStream_t stream);
+
+// ---- batch utilities (kmu_batch.cu) ------------------------------------------------------
+// synthetic packed bases: base j of sequence i = SplitMix64 stream `seed` output first_base[i] + j
+cudaError_t launch_synth_packed(uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases,
+                                const uint64_t* first_base, uint64_t nseq, uint64_t total_words, uint64_t seed,
+                                cudaStream_t stream);
+// ASCII -> 2 bit.  mode 0: strict (invalid char counted, packed as A); mode 1: drop invalid
+cudaError_t launch_count_invalid(const uint8_t* ascii, const uint64_t* ascii_off, uint64_t nseq, uint64_t* invalid,
+                                 cudaStream_t stream);
+cudaError_t launch_pack_ascii(const uint8_t* ascii, const uint64_t* ascii_off, const uint64_t* byte_off,
+                              const uint64_t* nbases, uint64_t nseq, int drop_invalid, uint8_t* packed,
+                              cudaStream_t stream);
+// length classes: bucket = 8 per octave of the k-mer count, bucket 0 = longest
+constexpr int LEN_BUCKETS = 512;
+cudaError_t launch_len_hist(const uint64_t* nbases, uint64_t nseq, uint32_t k, unsigned long long* hist,
+                            cudaStream_t stream);
+cudaError_t launch_len_scatter(const uint64_t* nbases, uint64_t nseq, uint32_t k, unsigned long long* cursor,
+                               uint32_t* order, cudaStream_t stream);
+inline int len_bucket_host(uint64_t nk) {
+    if (nk == 0) return LEN_BUCKETS - 1;
+    int e = 63 - __builtin_clzll(nk);
+    int frac = e >= 3 ? (int)((nk >> (e - 3)) & 7) : (int)((nk << (3 - e)) & 7);
+    return LEN_BUCKETS - 1 - (e * 8 + frac);
+}
+// smallest k-mer count that falls in `bucket`
+inline uint64_t len_bucket_min_nk(int bucket) {
+    int key = LEN_BUCKETS - 1 - bucket;
+    int e = key / 8, frac = key % 8;
+    if (e >= 3) return (uint64_t)(8 + frac) << (e - 3);
+    return ((uint64_t)(8 + frac)) >> (3 - e);
+}
+
+// ---- k-mer generation / ntHash (kmu_extract.cu) -----------------------------------------
+cudaError_t launch_kmer_offsets(const uint64_t* nbases, uint64_t nseq, uint32_t k, uint64_t* out_off,
+                                cudaStream_t stream);
+cudaError_t launch_generate_kmers(const SeqView& b, uint32_t k, int kmer_type, int hash_kind, const uint64_t* out_off,
+                                  void* out, cudaStream_t stream);
+cudaError_t launch_nthash(const SeqView& b, uint32_t k, uint32_t n_multi, const uint64_t* out_off, uint64_t* out_hash,
+                          uint8_t* out_strand, cudaStream_t stream);
+
+}  // namespace kmu

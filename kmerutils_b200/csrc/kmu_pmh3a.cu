@@ -1,0 +1,395 @@
+// kmu_pmh3a.cu -- per-sequence ProbMinHash3a sketching on sm_100a.
+//
+// Replaces the CPU loop of SeqSketcher::sketch_probminhash3a
+// (src/sketching/seqsketchjaccard.rs:211-260) and ProbHash3aSketch::sketch_compressedkmer
+// (src/sketching/setsketchert.rs:121-157): per sequence
+//     KmerSeqIterator -> fhash -> FnvHashMap<Val,u64> multiplicities
+//     -> ProbMinHash3a::hash_weigthed_hashmap -> signature of m slots.
+//
+// GPU formulation (see DESIGN.md "ProbMinHash3a kernel"):
+//   * a TEAM (1..32 warps of one CTA) owns one sequence at a time; teams pull
+//     sequences from a global work counter in descending-length order.
+//   * pass 1 walks the packed 2-bit bases (rolling forward / reverse-complement
+//     windows in registers) and counts pre-keys in shared memory: a direct
+//     u16 histogram when 4^k bins fit, else an open-addressing table (shared
+//     memory, or an L2-resident global scratch for long sequences).
+//   * pass 2 walks the sequence again; the occurrence that atomically *claims*
+//     a pre-key owns that distinct item.  Claimed (key, multiplicity) pairs are
+//     compacted into per-warp queues with ballots so that the expensive part --
+//     seeding Xoshiro256++ and drawing the item's exponential points -- always
+//     runs on full warps.
+//   * the signature slots are 16-byte {h, key} records updated with one 128-bit
+//     CAS; the result is argmin over all points per slot, which is what the
+//     sequential algorithm computes (its qmax tests only prune points that cannot
+//     win), so every item can run depth-first against a lazily refreshed qmax.
+#include <cstdint>
+#include <cstdio>
+
+#include "kmu_device.cuh"
+#include "kmu_kernels.h"
+
+namespace kmu {
+
+// --------------------------------------------------------------------------------
+// team = group of warps cooperating on one sequence
+// --------------------------------------------------------------------------------
+struct Team {
+    int id;      // team index inside the CTA
+    int tid;     // thread index inside the team
+    int size;    // threads in the team
+    int warp;    // warp index inside the team
+    int lane;
+    __device__ __forceinline__ void sync() const {
+        if (size == 32) {
+            __syncwarp();
+        } else {
+            // named barrier id+1 (0 is left to __syncthreads)
+            asm volatile("bar.sync %0, %1;" ::"r"(id + 1), "r"(size) : "memory");
+        }
+    }
+};
+
+// ---- multiplicity stores -----------------------------------------------------------
+// u32 pre-keys: one u64 per entry = key << 32 | claimed << 31 | count ; 0 == empty
+// u64 pre-keys: 16-byte entry {key, claimed << 63 | count} ; count == 0 == empty
+template <typename V>
+struct TableOps;
+
+template <>
+struct TableOps<uint32_t> {
+    using Entry = unsigned long long;
+    static __device__ __forceinline__ uint32_t slot_of(uint32_t key, uint32_t log2cap) {
+        return (key * 0x9E3779B1u) >> (32 - log2cap);
+    }
+    static __device__ __forceinline__ void insert(Entry* tab, uint32_t capmask, uint32_t log2cap, uint32_t key) {
+        uint32_t i = slot_of(key, log2cap);
+        for (;;) {
+            Entry e = *(volatile Entry*)(tab + i);
+            if (e == 0) {
+                Entry old = atomicCAS(tab + i, 0ULL, ((Entry)key << 32) | 1ULL);
+                if (old == 0) return;
+                e = old;
+            }
+            if ((uint32_t)(e >> 32) == key) {
+                atomicAdd(tab + i, 1ULL);
+                return;
+            }
+            i = (i + 1) & capmask;
+        }
+    }
+    // returns the multiplicity if this call claimed the key, else 0
+    static __device__ __forceinline__ uint32_t claim(Entry* tab, uint32_t capmask, uint32_t log2cap, uint32_t key) {
+        uint32_t i = slot_of(key, log2cap);
+        for (;;) {
+            Entry e = *(volatile Entry*)(tab + i);
+            if (e == 0) return 0;  // cannot happen for a key inserted in pass 1
+            if ((uint32_t)(e >> 32) == key) {
+                if (e & 0x80000000ULL) return 0;
+                Entry old = atomicOr(tab + i, 0x80000000ULL);
+                return (old & 0x80000000ULL) ? 0u : (uint32_t)(old & 0x7FFFFFFFULL);
+            }
+            i = (i + 1) & capmask;
+        }
+    }
+};
+
+template <>
+struct TableOps<uint64_t> {
+    struct __align__(16) Entry {
+        unsigned long long key;
+        unsigned long long cnt;
+    };
+    static __device__ __forceinline__ uint32_t slot_of(uint64_t key, uint32_t log2cap) {
+        return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - log2cap));
+    }
+    static __device__ __forceinline__ void insert(Entry* tab, uint32_t capmask, uint32_t log2cap, uint64_t key) {
+        uint32_t i = slot_of(key, log2cap);
+        for (;;) {
+            unsigned long long c = *(volatile unsigned long long*)&tab[i].cnt;
+            if (c == 0) {
+                uint64_t oh, ok;
+                cas128((Slot*)(tab + i), 0, 0, key, 1, oh, ok);
+                if (oh == 0 && ok == 0) return;
+            }
+            unsigned long long kk = *(volatile unsigned long long*)&tab[i].key;
+            if (kk == key) {
+                atomicAdd(&tab[i].cnt, 1ULL);
+                return;
+            }
+            i = (i + 1) & capmask;
+        }
+    }
+    static __device__ __forceinline__ uint32_t claim(Entry* tab, uint32_t capmask, uint32_t log2cap, uint64_t key) {
+        uint32_t i = slot_of(key, log2cap);
+        for (;;) {
+            unsigned long long c = *(volatile unsigned long long*)&tab[i].cnt;
+            if (c == 0) return 0;
+            unsigned long long kk = *(volatile unsigned long long*)&tab[i].key;
+            if (kk == key) {
+                if (c >> 63) return 0;
+                unsigned long long old = atomicOr(&tab[i].cnt, 1ULL << 63);
+                return (old >> 63) ? 0u : (uint32_t)(old & 0x7FFFFFFFULL);
+            }
+            i = (i + 1) & capmask;
+        }
+    }
+};
+
+template <typename V>
+struct QItem {
+    V prekey;
+    uint32_t cnt;
+};
+
+constexpr int QCAP = 64;  // per-warp queue capacity (power of two, >= 2 * 32)
+
+// --------------------------------------------------------------------------------
+// Process up to 32 queued distinct items with one warp: every lane owns one item and
+// emits its points i = 1, 2, ... while winv * (i - 1) < qmax
+// (ProbMinHash3a::hash_weigthed_hashmap).
+// --------------------------------------------------------------------------------
+template <typename V>
+__device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t head, uint32_t n, int lane,
+                                              const Pmh3aParams& P, V header, Slot* slots,
+                                              unsigned long long* s_qmax, uint32_t refresh_period) {
+    bool act = (uint32_t)lane < n;
+    V key = 0;
+    double winv = 0.0;
+    Xoshiro256pp rng;
+    rng.s0 = rng.s1 = rng.s2 = rng.s3 = 0;
+    if (act) {
+        QItem<V> it = queue[(head + lane) & (QCAP - 1)];
+        key = finalize_key<V>(it.prekey, header, P.hash_kind);
+        rng.seed(nohash_seed(key));
+        winv = 1.0 / (double)it.cnt;
+    }
+    uint32_t i = 1;
+    uint32_t iter = 0;
+    while (__any_sync(0xFFFFFFFFu, act)) {
+        if (iter % refresh_period == 0) {
+            // lazily refreshed upper bound of the slot maxima (MaxValueTracker's root)
+            uint64_t mx = 0;
+            for (uint32_t j = lane; j < P.m; j += 32) {
+                uint64_t hb = *(volatile uint64_t*)&slots[j].hbits;
+                mx = hb > mx ? hb : mx;
+            }
+            mx = warp_max_u64(mx);
+            if (lane == 0 && mx < *(volatile unsigned long long*)s_qmax) atomicMin(s_qmax, (unsigned long long)mx);
+            __syncwarp();
+        }
+        ++iter;
+        double qmax = __longlong_as_double((long long)*(volatile unsigned long long*)s_qmax);
+        if (act) {
+            double base = __dmul_rn(winv, (double)(i - 1));
+            if (!(base < qmax)) {
+                act = false;
+            } else {
+                double x = exp01_sample(P.e, rng);
+                double h = __dadd_rn(base, __dmul_rn(winv, x));
+                if (i == 1 && !(h < qmax)) {
+                    act = false;  // first point already above every slot: the item is dead
+                } else {
+                    uint32_t s = rng.unif_range(0, P.m, P.slot_thresh);
+                    slot_update_min(&slots[s], (uint64_t)__double_as_longlong(h), (uint64_t)key);
+                    ++i;
+                }
+            }
+        }
+    }
+}
+
+// MODE 0: direct histogram of 4^k u16 counters (two per u32) ; MODE 1: open-addressing table
+template <typename V, int MODE>
+__global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams P) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    using TO = TableOps<V>;
+    using Entry = typename TO::Entry;
+
+    Team team;
+    team.size = P.team_warps * 32;
+    team.id = threadIdx.x / team.size;
+    team.tid = threadIdx.x % team.size;
+    team.warp = team.tid >> 5;
+    team.lane = threadIdx.x & 31;
+    const int nteams = blockDim.x / team.size;
+    (void)nteams;
+
+    // ---- carve the team's shared memory ------------------------------------------
+    uint8_t* tbase = smem + (size_t)team.id * P.team_smem_bytes;
+    uint8_t* regionA = tbase;                                     // histogram or table
+    Slot* slots = (Slot*)(tbase + P.regionA_bytes);               // m slots (if in smem)
+    QItem<V>* queues = (QItem<V>*)(tbase + P.regionA_bytes + P.slots_smem_bytes);
+    unsigned long long* s_qmax =
+        (unsigned long long*)((uint8_t*)queues + (size_t)P.team_warps * QCAP * sizeof(QItem<V>));
+    volatile unsigned long long* s_work = (volatile unsigned long long*)(s_qmax + 1);
+    volatile uint32_t* s_flag = (volatile uint32_t*)(s_qmax + 2);
+    if (P.slots_smem_bytes == 0)
+        slots = P.slot_scratch + ((size_t)blockIdx.x * nteams + team.id) * P.m;
+    QItem<V>* myq = queues + (size_t)team.warp * QCAP;
+
+    // region A starts clean; both passes leave it clean again
+    for (uint32_t j = team.tid; j < P.regionA_bytes / 4; j += team.size) ((uint32_t*)regionA)[j] = 0;
+
+    const V header = (V)word_header(P.kmer_type, P.k);
+    const bool canonical = hash_is_canonical(P.hash_kind);
+    const uint32_t k = P.k;
+    const uint32_t refresh_period = P.m <= 256 ? 1u : P.m / 256;
+    Entry* gtab = nullptr;
+    if (MODE == 1 && P.table_scratch)
+        gtab = (Entry*)P.table_scratch + ((size_t)blockIdx.x * nteams + team.id) * P.table_scratch_entries;
+
+    for (;;) {
+        team.sync();
+        if (team.tid == 0) *s_work = atomicAdd(P.work_counter, 1ULL);
+        team.sync();
+        const unsigned long long w = *s_work;
+        if (w >= P.count) break;
+        const uint32_t seq = P.order[P.first + w];
+        const uint64_t L = P.nbases[seq];
+        const uint32_t* words = (const uint32_t*)(P.packed + P.byte_off[seq]);
+        const uint64_t nk = L >= k ? L - k + 1 : 0;
+
+        for (uint32_t j = team.tid; j < P.m; j += team.size) {
+            slots[j].hbits = F64_MAX_BITS;
+            slots[j].key = 0;
+        }
+        if (team.tid == 0) {
+            *s_qmax = F64_MAX_BITS;
+            *s_flag = 0;
+        }
+        // positions per task
+        uint32_t T = 4;
+        if (nk >= (uint64_t)team.size * 32) T = 16;
+        else if (nk >= (uint64_t)team.size * 16) T = 8;
+        const uint64_t ntasks = (nk + T - 1) / T;
+
+        // table geometry for this sequence
+        Entry* tab = (Entry*)regionA;
+        uint32_t log2cap = 0, capmask = 0;
+        if (MODE == 1) {
+            uint64_t want = nk * 2 < 64 ? 64 : nk * 2;
+            log2cap = 64 - __clzll((long long)(want - 1));
+            uint64_t cap = 1ULL << log2cap;
+            if (cap * sizeof(Entry) > P.regionA_bytes) tab = gtab;  // long sequence: L2 / HBM scratch
+            capmask = (uint32_t)(cap - 1);
+        }
+        team.sync();
+
+        // ---------------- pass 1 : multiplicities ------------------------------------
+        for (uint64_t task = team.tid; task < ntasks; task += team.size) {
+            KmerWalker<V> wk;
+            uint64_t p = task * T;
+            wk.start(words, p, k);
+            for (uint32_t t = 0; t < T && p < nk; ++t, ++p) {
+                wk.roll();
+                V pk = wk.prekey(canonical);
+                if (MODE == 0) {
+                    uint32_t sh = ((uint32_t)pk & 1u) * 16;
+                    uint32_t old = atomicAdd((uint32_t*)regionA + ((uint32_t)pk >> 1), 1u << sh);
+                    if (((old >> sh) & 0xFFFFu) == 0xFFFFu) *s_flag = 1;  // u16 counter wrapped
+                } else {
+                    TO::insert(tab, capmask, log2cap, pk);
+                }
+            }
+        }
+        team.sync();
+        const bool overflow = MODE == 0 && *s_flag != 0;
+
+        // ---------------- pass 2 : claim distinct items, sketch them ------------------
+        uint32_t qhead = 0, qtail = 0;
+        for (uint64_t tbase_i = (uint64_t)team.warp * 32; tbase_i < ntasks; tbase_i += team.size) {
+            const uint64_t task = tbase_i + team.lane;
+            const bool tact = task < ntasks;
+            KmerWalker<V> wk;
+            uint64_t p = task * T;
+            if (tact) wk.start(words, p, k);
+            for (uint32_t t = 0; t < T; ++t, ++p) {
+                uint32_t cnt = 0;
+                V pk = 0;
+                if (tact && p < nk) {
+                    wk.roll();
+                    pk = wk.prekey(canonical);
+                    if (MODE == 0) {
+                        uint32_t sh = ((uint32_t)pk & 1u) * 16;
+                        uint32_t* wp = (uint32_t*)regionA + ((uint32_t)pk >> 1);
+                        if (overflow) {
+                            *wp = 0;
+                        } else {
+                            uint32_t old = atomicAnd(wp, ~(0xFFFFu << sh));
+                            cnt = (old >> sh) & 0xFFFFu;
+                        }
+                    } else {
+                        cnt = TO::claim(tab, capmask, log2cap, pk);
+                    }
+                }
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, cnt != 0);
+                if (bal) {
+                    if (cnt) {
+                        uint32_t pos = qtail + __popc(bal & ((1u << team.lane) - 1));
+                        QItem<V> it;
+                        it.prekey = pk;
+                        it.cnt = cnt;
+                        myq[pos & (QCAP - 1)] = it;
+                    }
+                    qtail += __popc(bal);
+                    __syncwarp();
+                    if (qtail - qhead >= 32) {
+                        process_items<V>(myq, qhead, 32, team.lane, P, header, slots, s_qmax, refresh_period);
+                        qhead += 32;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        if (qtail != qhead) process_items<V>(myq, qhead, qtail - qhead, team.lane, P, header, slots, s_qmax, refresh_period);
+        team.sync();
+
+        // ---------------- signature out, leave region A clean --------------------------
+        if (overflow) {
+            if (team.tid == 0) {
+                unsigned long long pos = atomicAdd(P.overflow_count, 1ULL);
+                P.overflow_list[pos] = seq;
+            }
+        } else {
+            V* out = (V*)P.sig + (size_t)seq * P.m;
+            for (uint32_t j = team.tid; j < P.m; j += team.size) out[j] = (V)slots[j].key;
+        }
+        if (MODE == 1) {
+            const uint64_t nwords = ((uint64_t)capmask + 1) * (sizeof(Entry) / 4);
+            for (uint64_t j = team.tid; j < nwords; j += team.size) ((uint32_t*)tab)[j] = 0;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------
+// host-side launcher
+// --------------------------------------------------------------------------------
+template <typename V, int MODE>
+static cudaError_t launch_one(const Pmh3aParams& P, int grid, int block, size_t smem, cudaStream_t stream) {
+    auto kern = pmh3a_sketch_kernel<V, MODE>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kern<<<grid, block, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+
+size_t pmh3a_qitem_bytes(bool key64) { return key64 ? sizeof(QItem<uint64_t>) : sizeof(QItem<uint32_t>); }
+size_t pmh3a_entry_bytes(bool key64) {
+    return key64 ? sizeof(TableOps<uint64_t>::Entry) : sizeof(TableOps<uint32_t>::Entry);
+}
+
+cudaError_t launch_pmh3a(const Pmh3aParams& P, bool key64, int mode, int grid, int block, size_t smem,
+                         cudaStream_t stream) {
+    if (key64) {
+        return mode == 0 ? launch_one<uint64_t, 0>(P, grid, block, smem, stream)
+                         : launch_one<uint64_t, 1>(P, grid, block, smem, stream);
+    }
+    return mode == 0 ? launch_one<uint32_t, 0>(P, grid, block, smem, stream)
+                     : launch_one<uint32_t, 1>(P, grid, block, smem, stream);
+}
+
+}  // namespace kmu

@@ -1,0 +1,215 @@
+"""Engine: one GPU context of the C ABI plus numpy-friendly wrappers.
+
+Everything here is plumbing around include/kmerutils_b200.h; the arithmetic runs in the CUDA
+kernels under kmerutils_b200/csrc/.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (HASH_CANON_INVHASH, KMER16B32, KMER32, KMER64, KMERAA32, KMERAA64, KmuTimes, check, u64p)
+
+_U64_TYPES = (KMER64, KMERAA64)
+
+
+def val_dtype(kmer_type):
+    """numpy dtype of Kmer::Val for a k-mer type (u32 or u64)."""
+    return np.uint64 if kmer_type in _U64_TYPES else np.uint32
+
+
+def _as_u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _p(a, t=C.c_void_p):
+    return a.ctypes.data_as(t)
+
+
+class SeqBatch:
+    """A set of 2-bit packed sequences resident in HBM (kmu_seqbatch)."""
+
+    def __init__(self, engine, handle):
+        self.engine = engine
+        self._h = handle
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise ValueError("batch already destroyed")
+        return self._h
+
+    def __len__(self):
+        return int(self.engine.lib.kmu_seqbatch_nseq(self.handle))
+
+    @property
+    def total_bases(self):
+        return int(self.engine.lib.kmu_seqbatch_total_bases(self.handle))
+
+    @property
+    def packed_bytes(self):
+        return int(self.engine.lib.kmu_seqbatch_packed_bytes(self.handle))
+
+    def kmer_count(self, k):
+        return int(self.engine.lib.kmu_kmer_count(self.handle, k))
+
+    def download(self):
+        """-> (packed bytes in the batch layout, byte_off[nseq], nbases[nseq])"""
+        n = len(self)
+        packed = np.zeros(self.packed_bytes, dtype=np.uint8)
+        off = np.zeros(n, dtype=np.uint64)
+        nb = np.zeros(n, dtype=np.uint64)
+        check(self.engine.lib.kmu_seqbatch_download(self.engine.ctx, self.handle, _p(packed), _p(off, u64p),
+                                                    _p(nb, u64p)))
+        return packed, off, nb
+
+    def destroy(self):
+        if self._h is not None:
+            self.engine.lib.kmu_seqbatch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One CUDA context (one B200).  Raises KmuError when no GPU is present."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load_library()
+        ctx = C.c_void_p()
+        check(self.lib.kmu_ctx_create(device, C.byref(ctx)))
+        self.ctx = ctx
+        self.device = device
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.kmu_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- bookkeeping --------------------------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.kmu_launch_count(self.ctx))
+
+    def stream(self):
+        return self.lib.kmu_ctx_stream(self.ctx)
+
+    def sync(self):
+        check(self.lib.kmu_ctx_sync(self.ctx))
+
+    def last_times(self):
+        t = KmuTimes()
+        check(self.lib.kmu_last_times(self.ctx, C.byref(t)))
+        return {f: getattr(t, f) for f, _ in KmuTimes._fields_}
+
+    # ---- batches ------------------------------------------------------------------------
+    def batch_from_sequences(self, packed_list, nbases):
+        """packed_list: one uint8 array per sequence (the reference's Vec<Sequence>)."""
+        arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in packed_list]
+        nb = _as_u64(nbases)
+        n = len(arrs)
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+        h = C.c_void_p()
+        check(self.lib.kmu_seqbatch_from_ptrs(self.ctx, ptrs, _p(nb, u64p), n, C.byref(h)))
+        return SeqBatch(self, h)
+
+    def batch_from_packed(self, packed, byte_off, nbases):
+        """One concatenated buffer; sequence i starts at packed[byte_off[i]]."""
+        off = _as_u64(byte_off)
+        nb = _as_u64(nbases)
+        if isinstance(packed, np.ndarray):
+            packed = np.ascontiguousarray(packed, dtype=np.uint8)
+            ptr, nbytes = packed.ctypes.data, packed.nbytes
+        else:  # (address, nbytes) of e.g. a pinned torch tensor
+            ptr, nbytes = packed
+        h = C.c_void_p()
+        check(self.lib.kmu_seqbatch_from_packed(self.ctx, C.c_void_p(ptr), nbytes, _p(off, u64p), _p(nb, u64p),
+                                                len(nb), C.byref(h)))
+        return SeqBatch(self, h)
+
+    def batch_from_ascii(self, seqs, drop_invalid=False):
+        """seqs: list of bytes.  -> (SeqBatch, invalid_counts).  Sequence::new / encode_and_add on the GPU."""
+        lens = np.array([len(s) for s in seqs], dtype=np.uint64)
+        off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=off[1:])
+        buf = np.frombuffer(b"".join(bytes(s) for s in seqs) + b"\0", dtype=np.uint8)
+        bad = np.zeros(max(len(seqs), 1), dtype=np.uint64)
+        h = C.c_void_p()
+        check(self.lib.kmu_seqbatch_from_ascii(self.ctx, _p(buf), _p(off, u64p), len(seqs), int(bool(drop_invalid)),
+                                               _p(bad, u64p), C.byref(h)))
+        return SeqBatch(self, h), bad[: len(seqs)]
+
+    def batch_synth(self, seed, nbases):
+        nb = _as_u64(nbases)
+        h = C.c_void_p()
+        check(self.lib.kmu_seqbatch_synth(self.ctx, seed, _p(nb, u64p), len(nb), C.byref(h)))
+        return SeqBatch(self, h)
+
+    # ---- k-mers ---------------------------------------------------------------------------
+    def generate_kmers(self, batch, k, kmer_type, hash_kind=_lib.HASH_IDENTITY_RAW):
+        """-> (values, out_off): all k-mers of all sequences mapped through the hash closure."""
+        n = len(batch)
+        total = batch.kmer_count(k)
+        out = np.zeros(total, dtype=val_dtype(kmer_type))
+        off = np.zeros(n + 1, dtype=np.uint64)
+        check(self.lib.kmu_generate_kmers(self.ctx, batch.handle, k, kmer_type, hash_kind, _p(out), _p(off, u64p), 0))
+        return out, off
+
+    def nthash_canonical(self, batch, k, n_multi=1, want_strand=True):
+        total = batch.kmer_count(k)
+        h = np.zeros((total, n_multi), dtype=np.uint64)
+        strand = np.zeros(total, dtype=np.uint8) if want_strand else None
+        check(self.lib.kmu_nthash_canonical(self.ctx, batch.handle, k, n_multi, _p(h),
+                                            _p(strand) if want_strand else None, 0))
+        return h, strand
+
+    # ---- sketches -------------------------------------------------------------------------
+    def sketch_pmh3a(self, batch, k, kmer_type, hash_kind=HASH_CANON_INVHASH, m=200, out=None, out_device_ptr=None):
+        """ProbMinHash3a signature per sequence -> (nseq, m) array of Kmer::Val.
+
+        out_device_ptr: raw device address to leave the signatures in HBM (returns None)."""
+        n = len(batch)
+        if out_device_ptr is not None:
+            check(self.lib.kmu_sketch_pmh3a(self.ctx, batch.handle, k, kmer_type, hash_kind, m,
+                                            C.c_void_p(out_device_ptr), 1))
+            return None
+        if out is None:
+            out = np.zeros((n, m), dtype=val_dtype(kmer_type))
+        check(self.lib.kmu_sketch_pmh3a(self.ctx, batch.handle, k, kmer_type, hash_kind, m, _p(out), 0))
+        return out
+
+    def sketch_pmh3a_host(self, packed, byte_off, nbases, k, kmer_type, hash_kind, m, out):
+        """One-shot: host packed buffer in, host signatures out (H2D + kernels + D2H)."""
+        off = _as_u64(byte_off)
+        nb = _as_u64(nbases)
+        if isinstance(packed, np.ndarray):
+            ptr, nbytes = packed.ctypes.data, packed.nbytes
+        else:
+            ptr, nbytes = packed
+        optr = out.ctypes.data if isinstance(out, np.ndarray) else out
+        check(self.lib.kmu_sketch_pmh3a_host(self.ctx, C.c_void_p(ptr), nbytes, _p(off, u64p), _p(nb, u64p), len(nb),
+                                             k, kmer_type, hash_kind, m, C.c_void_p(optr)))
+        return out
+
+
+_DEFAULT = {}
+
+
+def default_engine(device=0):
+    """Process-wide engine per device (created on first use)."""
+    if device not in _DEFAULT:
+        _DEFAULT[device] = Engine(device)
+    return _DEFAULT[device]
+
+
+__all__ = ["Engine", "SeqBatch", "default_engine", "val_dtype", "KMER32", "KMER16B32", "KMER64", "KMERAA32",
+           "KMERAA64"]

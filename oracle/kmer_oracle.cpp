@@ -1,0 +1,746 @@
+// ============================================================================
+//  oracle/kmer_oracle.cpp  --  TEST INFRASTRUCTURE ONLY (see kmer_oracle.hpp).
+//  CPU restatement of the kmerutils hot path; every function cites the
+//  reference file:line it follows.  Built by oracle/Makefile into
+//  oracle/libkmer_oracle.so with -ffp-contract=off (Rust never fuses a*b+c).
+// ============================================================================
+#include "kmer_oracle.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------- alphabet ----
+// Alphabet2b::encode, src/base/alphabet.rs:119-127 (case-insensitive; A0 C1 G2 T3)
+// to_ascii_uppercase only touches a-z
+inline int encode2b_strict(uint8_t c) {
+    if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
+    switch (c) {
+        case 'A': return 0;
+        case 'C': return 1;
+        case 'G': return 2;
+        case 'T': return 3;
+        default: return -1;
+    }
+}
+const char DECODE2B[4] = {'A', 'C', 'G', 'T'};
+
+// IterSequence::next reduced to its meaning: base `pos` of the packed sequence,
+// first base of a byte in its two most significant bits (sequence.rs:605-648,
+// alphabet.rs:162-168)
+inline uint8_t base_at(const uint8_t* packed, uint64_t pos) {
+    return (packed[pos >> 2] >> (6 - 2 * (pos & 3))) & 3;
+}
+
+// ---------------------------------------------------------------- k-mer words ---
+inline uint64_t value_mask(int nbits) { return nbits >= 64 ? ~0ULL : ((1ULL << nbits) - 1); }
+
+inline uint32_t brev32(uint32_t x) {
+    x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+    x = ((x & 0x33333333u) << 2) | ((x >> 2) & 0x33333333u);
+    x = ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+    x = ((x & 0x00FF00FFu) << 8) | ((x >> 8) & 0x00FF00FFu);
+    return (x << 16) | (x >> 16);
+}
+inline uint64_t brev64(uint64_t x) {
+    return ((uint64_t)brev32((uint32_t)x) << 32) | brev32((uint32_t)(x >> 32));
+}
+
+uint64_t kmer_build(uint64_t value, int k, int type) {
+    switch (type) {
+        case ORC_KMER32: return (uint32_t)(((uint32_t)k << 28) | (uint32_t)value);  // kmer32bit.rs:212-216
+        case ORC_KMER16B32: return (uint32_t)value;                                 // kmer16b32bit.rs:130-135
+        default: return value;                                                      // kmer64bit.rs / kmeraa.rs
+    }
+}
+
+uint64_t kmer_push(uint64_t word, int k, int type, uint8_t base) {
+    switch (type) {
+        case ORC_KMER32: {  // kmer32bit.rs:98-113
+            uint32_t w = (uint32_t)word;
+            uint32_t hdr = w & 0xF0000000u;
+            uint32_t nb = (w >> 28) & 0xF;
+            uint32_t vmask = (1u << (2 * nb)) - 1;
+            uint32_t nk = ((w << 2) & vmask) | (base & 3u);
+            (void)k;
+            return nk | hdr;
+        }
+        case ORC_KMER16B32:  // kmer16b32bit.rs:57-61
+            return (uint32_t)(((uint32_t)word << 2) | (base & 3u));
+        case ORC_KMER64: {  // kmer64bit.rs:68-80 ; (1<<64) wraps to mask 0 in release at k=32:
+            // we restate the *intended* semantics for k = 32 (full 64-bit window) and say so in DESIGN.md
+            uint64_t vmask = value_mask(2 * k);
+            return ((word << 2) & vmask) | (uint64_t)(base & 3u);
+        }
+        default: return 0;
+    }
+}
+
+uint64_t kmer_revcomp(uint64_t word, int k, int type) {
+    switch (type) {
+        case ORC_KMER32: {  // kmer32bit.rs:119-137
+            uint32_t w = (uint32_t)word;
+            uint32_t hdr = w & 0xF0000000u;
+            uint32_t nb = (w >> 28) & 0xF;
+            uint32_t r = ~w;
+            r = brev32(r);
+            r = ((r & 0x55555555u) << 1) | ((r & 0xAAAAAAAAu) >> 1);
+            uint32_t sh = 32 - 2 * nb;
+            r = sh >= 32 ? 0 : (r >> sh);
+            r = (r & 0x0FFFFFFFu) | hdr;
+            (void)k;
+            return r;
+        }
+        case ORC_KMER16B32: {  // kmer16b32bit.rs:43-54
+            uint32_t r = ~(uint32_t)word;
+            r = brev32(r);
+            r = ((r & 0x55555555u) << 1) | ((r & 0xAAAAAAAAu) >> 1);
+            return r;
+        }
+        case ORC_KMER64: {  // kmer64bit.rs:83-96
+            uint64_t r = ~word;
+            r = brev64(r);
+            r = ((r & 0x5555555555555555ULL) << 1) | ((r & 0xAAAAAAAAAAAAAAAAULL) >> 1);
+            int sh = 64 - 2 * k;
+            r = sh >= 64 ? 0 : (r >> sh);
+            return r;
+        }
+        default: return word;  // AA k-mers have no reverse complement (kmeraa.rs:185-187 panics)
+    }
+}
+
+int kmer_cmp(uint64_t a, uint64_t b, int type) {
+    if (type == ORC_KMER32) {  // kmer32bit.rs:47-55 : header first, then value
+        uint32_t ha = (uint32_t)a & 0xF0000000u, hb = (uint32_t)b & 0xF0000000u;
+        if (ha != hb) return ha < hb ? -1 : 1;
+        uint32_t va = (uint32_t)a & 0x0FFFFFFFu, vb = (uint32_t)b & 0x0FFFFFFFu;
+        return va < vb ? -1 : (va > vb ? 1 : 0);
+    }
+    // derived Ord on u32 (kmer16b32bit.rs:20) ; (k, value) with equal k (kmer64bit.rs:45-53)
+    return a < b ? -1 : (a > b ? 1 : 0);
+}
+
+uint64_t kmer_compressed_value(uint64_t word, int type) {
+    if (type == ORC_KMER32) return (uint32_t)word & 0x0FFFFFFFu;  // kmer32bit.rs:173-178
+    return word;
+}
+
+bool kmer_type_accepts(int k, int type) {
+    switch (type) {
+        case ORC_KMER32: return k >= 1 && k <= 14;   // kmergenerator.rs:311 / kmer32bit.rs:160
+        case ORC_KMER16B32: return k == 16;          // kmergenerator.rs:218-220
+        case ORC_KMER64: return k >= 1 && k <= 32;   // kmergenerator.rs:415
+        default: return false;
+    }
+}
+
+// invhash (probminhash::invhash, Thomas Wang / Heng Li) -- SURVEY App. A.6
+inline uint32_t int32_hash(uint32_t key) {
+    key += ~(key << 15);
+    key ^= (key >> 10);
+    key += (key << 3);
+    key ^= (key >> 6);
+    key += ~(key << 11);
+    key ^= (key >> 16);
+    return key;
+}
+inline uint64_t int64_hash(uint64_t key) {
+    key = (~key) + (key << 21);
+    key = key ^ (key >> 24);
+    key = (key + (key << 3)) + (key << 8);
+    key = key ^ (key >> 14);
+    key = (key + (key << 2)) + (key << 4);
+    key = key ^ (key >> 28);
+    key = key + (key << 31);
+    return key;
+}
+
+inline bool is_u32_type(int type) { return type == ORC_KMER32 || type == ORC_KMER16B32 || type == ORC_KMERAA32; }
+
+uint64_t apply_hash(uint64_t word, int k, int type, int kind) {
+    switch (kind) {
+        case ORC_HASH_IDENTITY_RAW: return word;
+        case ORC_HASH_MASKED_VALUE: {
+            int bits = (type == ORC_KMERAA32 || type == ORC_KMERAA64) ? 5 * k : 2 * k;
+            return kmer_compressed_value(word, type) & value_mask(bits);
+        }
+        case ORC_HASH_CANON_INVHASH:
+        case ORC_HASH_CANON_RAW: {
+            // kmer.reverse_complement().min(*kmer)  (datasketcher.rs:223)
+            uint64_t rc = kmer_revcomp(word, k, type);
+            uint64_t canon = kmer_cmp(word, rc, type) < 0 ? word : rc;
+            if (kind == ORC_HASH_CANON_RAW) return canon;
+            return is_u32_type(type) ? (uint64_t)int32_hash((uint32_t)canon) : int64_hash(canon);
+        }
+        case ORC_HASH_INVHASH: return is_u32_type(type) ? (uint64_t)int32_hash((uint32_t)word) : int64_hash(word);
+        default: return word;
+    }
+}
+
+// ---------------------------------------------------------------- ntHash -------
+// seeds nthash.rs:17-20 ; BASE_MAPPING_2B nthash.rs:28-30
+const uint64_t NT_SEED[4] = {0x3c8bfbb395c60474ULL, 0x3193c18562a02b4cULL, 0x20323ed082572324ULL,
+                             0x295549f54be24456ULL};
+inline uint64_t rotl64(uint64_t x, unsigned r) { r &= 63; return r ? (x << r) | (x >> (64 - r)) : x; }
+inline uint64_t rotr64(uint64_t x, unsigned r) { r &= 63; return r ? (x >> r) | (x << (64 - r)) : x; }
+inline uint8_t kmer_base(uint64_t word, int k, int type, int i) {
+    // i-th base from the left of the k-mer (value right aligned)
+    (void)type;
+    return (uint8_t)((word >> (2 * (k - 1 - i))) & 3);
+}
+
+// ---------------------------------------------------------------- RNG ----------
+// rand_xoshiro::SplitMix64 + Xoshiro256PlusPlus::seed_from_u64
+inline uint64_t splitmix64_next(uint64_t& x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+struct Xoshiro256pp {
+    uint64_t s[4];
+    explicit Xoshiro256pp(uint64_t seed) {
+        uint64_t x = seed;
+        for (int i = 0; i < 4; ++i) s[i] = splitmix64_next(x);
+    }
+    inline uint64_t next_u64() {
+        uint64_t r = rotl64(s[0] + s[3], 23) + s[0];
+        uint64_t t = s[1] << 17;
+        s[2] ^= s[0];
+        s[3] ^= s[1];
+        s[1] ^= s[2];
+        s[0] ^= s[3];
+        s[2] ^= t;
+        s[3] = rotl64(s[3], 45);
+        return r;
+    }
+    inline uint32_t next_u32() { return (uint32_t)(next_u64() >> 32); }
+    // rand 0.9 Uniform::<f64>::new(0.,1.).sample : 52 random mantissa bits (App. A.2)
+    inline double unif01() {
+        uint64_t bits = (next_u64() >> 12) | 0x3FF0000000000000ULL;
+        double v;
+        std::memcpy(&v, &bits, 8);
+        return v - 1.0;
+    }
+    inline float unif01_f32() {
+        uint32_t bits = (next_u32() >> 9) | 0x3F800000u;
+        float v;
+        std::memcpy(&v, &bits, 4);
+        return v - 1.0f;
+    }
+    // rand 0.9 UniformUsize::sample for a range that fits in u32: Lemire widening
+    // multiply on next_u32 with rejection threshold (2^32 - range) % range (App. A.2)
+    inline uint32_t unif_range_u32(uint32_t low, uint32_t range) {
+        uint32_t thresh = (uint32_t)(0u - range) % range;
+        for (;;) {
+            uint64_t prod = (uint64_t)next_u32() * (uint64_t)range;
+            uint32_t lo = (uint32_t)prod;
+            if (lo >= thresh) return low + (uint32_t)(prod >> 32);
+        }
+    }
+};
+
+// NoHashHasher (src/nohasher.rs:22-48): the key's native-endian bytes read big-endian
+inline uint64_t bswap32(uint32_t v) { return __builtin_bswap32(v); }
+uint64_t nohash_seed(uint64_t key, int key_bytes) {
+    return key_bytes == 4 ? (uint64_t)__builtin_bswap32((uint32_t)key) : __builtin_bswap64(key);
+}
+// fnv::FnvHasher over the native-endian key bytes (seqsketchjaccard.rs:346-349)
+uint64_t fnv1a_seed(uint64_t key, int key_bytes) {
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (int i = 0; i < key_bytes; ++i) {
+        h ^= (key >> (8 * i)) & 0xFF;
+        h *= 0x100000001b3ULL;
+    }
+    return h;
+}
+
+// ---------------------------------------------------------------- ProbMinHash3a --
+// probminhash::probminhasher::ExpRestricted01
+struct ExpRestricted01 {
+    double lambda, c1, c2, c3;
+    explicit ExpRestricted01(double l) : lambda(l) {
+        c1 = std::expm1(lambda) / lambda;
+        c2 = std::log(2.0 / (1.0 + std::exp(-lambda))) / lambda;
+        c3 = (1.0 - std::exp(-lambda)) / lambda;
+    }
+    inline double sample(Xoshiro256pp& rng) const {
+        double x = c1 * rng.unif01();
+        if (x < 1.0) return x;
+        for (;;) {
+            x = rng.unif01();
+            if (x < c2) return x;
+            double y = 0.5 * rng.unif01();
+            if (y > 1.0 - x) {
+                x = 1.0 - x;
+                y = 1.0 - y;
+            }
+            if (x <= c3 * (1.0 - y)) return x;
+            if (c1 * y <= 1.0 - x) return x;
+            if (y * c1 * lambda <= std::expm1(lambda * (1.0 - x))) return x;
+        }
+    }
+};
+
+// MaxValueTracker: slot values + running maximum (tournament tree; root == qmax)
+struct MaxTracker {
+    uint32_t m;
+    std::vector<double> v;  // 2m-1 nodes, leaves first
+    explicit MaxTracker(uint32_t m_) : m(m_), v(2 * (size_t)m_ - 1, std::numeric_limits<double>::max()) {}
+    inline double max_value() const { return v.back(); }
+    inline double at(uint32_t k) const { return v[k]; }
+    void update(uint32_t k, double value) {
+        size_t last = v.size() - 1;
+        size_t cur = k;
+        double curv = value;
+        if (!(curv < v[cur])) return;
+        for (;;) {
+            v[cur] = curv;
+            size_t p = m + cur / 2;
+            if (p > last) break;
+            size_t sib = cur ^ 1;
+            if (v[sib] >= v[p] && v[cur] >= v[p]) break;
+            if (curv < v[sib]) curv = v[sib];
+            cur = p;
+            if (curv >= v[cur]) break;
+        }
+    }
+};
+
+struct PendingItem {
+    uint64_t key;
+    double winv;
+    Xoshiro256pp rng;
+};
+
+// ProbMinHash3a::hash_weigthed_hashmap. Items are visited in
+// the order given (ascending key: the reference's hashbrown order is not
+// reproducible and only matters for exact f64 ties).
+void pmh3a(const uint64_t* keys, const double* weights, uint64_t n, uint32_t m, int key_bytes, uint64_t* sig) {
+    for (uint32_t j = 0; j < m; ++j) sig[j] = 0;  // Val::default()
+    if (m < 2) return;                            // reference asserts m >= 2
+    const double lambda = std::log((double)m / (double)(m - 1));
+    ExpRestricted01 exp01(lambda);
+    MaxTracker q(m);
+    std::vector<PendingItem> todo;
+    double qmax = q.max_value();
+    for (uint64_t it = 0; it < n; ++it) {
+        const uint64_t key = keys[it];
+        const double winv = 1.0 / weights[it];
+        Xoshiro256pp rng(nohash_seed(key, key_bytes));
+        const double h = winv * exp01.sample(rng);
+        qmax = q.max_value();
+        if (h < qmax) {
+            uint32_t k = rng.unif_range_u32(0, m);
+            if (h < q.at(k)) {
+                sig[k] = key;
+                q.update(k, h);
+                qmax = q.max_value();
+            }
+            if (winv < qmax) todo.push_back(PendingItem{key, winv, rng});
+        }
+    }
+    uint64_t i = 2;
+    while (!todo.empty()) {
+        size_t insert_pos = 0;
+        for (size_t j = 0; j < todo.size(); ++j) {
+            PendingItem& p = todo[j];
+            double h = p.winv * (double)(i - 1);
+            if (h < q.max_value()) {
+                h = h + p.winv * exp01.sample(p.rng);
+                uint32_t k = p.rng.unif_range_u32(0, m);
+                if (h < q.at(k)) {
+                    sig[k] = p.key;
+                    q.update(k, h);
+                    qmax = q.max_value();
+                }
+                if (p.winv * (double)i < qmax) {
+                    todo[insert_pos] = p;
+                    ++insert_pos;
+                }
+            }
+        }
+        todo.resize(insert_pos, PendingItem{0, 0.0, Xoshiro256pp(0)});
+        ++i;
+    }
+}
+
+// FnvHashMap<Val, u64> stand-in (fnv + hashbrown in the reference,
+// seqsketchjaccard.rs:226-227): open addressing, FNV-1a over the key bytes,
+// count == 0 marks an empty slot.  Iteration order = slot order (the reference's
+// hashbrown order is not reproducible and only matters for exact f64 ties).
+struct FlatCountMap {
+    std::vector<uint64_t> keys;
+    std::vector<uint64_t> counts;
+    uint64_t mask = 0;
+    uint64_t used = 0;
+    void reset(uint64_t expected) {
+        uint64_t cap = 16;
+        while (cap < 2 * expected) cap <<= 1;
+        if (keys.size() != cap) {
+            keys.assign(cap, 0);
+            counts.assign(cap, 0);
+        } else {
+            std::fill(counts.begin(), counts.end(), 0);
+        }
+        mask = cap - 1;
+        used = 0;
+    }
+    void grow() {
+        std::vector<uint64_t> ok, oc;
+        ok.swap(keys);
+        oc.swap(counts);
+        uint64_t cap = ok.size() * 2;
+        keys.assign(cap, 0);
+        counts.assign(cap, 0);
+        mask = cap - 1;
+        for (size_t i = 0; i < ok.size(); ++i)
+            if (oc[i]) add(ok[i], oc[i]);
+    }
+    static inline uint64_t fnv(uint64_t key) {
+        uint64_t h = 0xcbf29ce484222325ULL;
+        for (int i = 0; i < 8; ++i) {
+            h ^= (key >> (8 * i)) & 0xFF;
+            h *= 0x100000001b3ULL;
+        }
+        return h ^ (h >> 32);
+    }
+    inline void add(uint64_t key, uint64_t c) {
+        uint64_t i = fnv(key) & mask;
+        for (;;) {
+            if (counts[i] == 0) {
+                keys[i] = key;
+                counts[i] = c;
+                if (++used * 2 > keys.size()) grow();
+                return;
+            }
+            if (keys[i] == key) {
+                counts[i] += c;
+                return;
+            }
+            i = (i + 1) & mask;
+        }
+    }
+};
+
+// multiplicity map of one sequence range: fhash(kmer) -> count
+// (seqsketchjaccard.rs:226-234)
+void count_kmers(const uint8_t* packed, uint64_t nbases, uint64_t begin, uint64_t end, int k, int type,
+                 int hash_kind, FlatCountMap& wb) {
+    if (!kmer_type_accepts(k, type)) return;
+    if (end > nbases) end = nbases;
+    if (end < begin + (uint64_t)k) return;
+    uint64_t val = 0;
+    for (int i = 0; i < k - 1; ++i) val = (val << 2) | base_at(packed, begin + i);
+    uint64_t word = kmer_build(val, k, type);
+    for (uint64_t p = begin + k - 1; p < end; ++p) {
+        word = kmer_push(word, k, type, base_at(packed, p));
+        wb.add(apply_hash(word, k, type, hash_kind), 1);
+    }
+}
+
+void sketch_from_map(const FlatCountMap& wb, uint32_t m, int key_bytes, uint64_t* sig) {
+    std::vector<uint64_t> keys;
+    std::vector<double> w;
+    keys.reserve(wb.used);
+    w.reserve(wb.used);
+    for (size_t i = 0; i < wb.keys.size(); ++i)
+        if (wb.counts[i]) {
+            keys.push_back(wb.keys[i]);
+            w.push_back((double)wb.counts[i]);
+        }
+    pmh3a(keys.data(), w.data(), keys.size(), m, key_bytes, sig);
+}
+
+}  // namespace
+
+// ================================================================= C API =========
+extern "C" {
+
+int64_t orc_pack_2bit(const uint8_t* ascii, uint64_t n, uint8_t* out) {
+    // Sequence::new(raw, 2)  sequence.rs:25-106 ; tail padded with 'A' (00) :66-71
+    uint64_t nbytes = (n + 3) / 4;
+    for (uint64_t b = 0; b < nbytes; ++b) {
+        uint8_t packed = 0;
+        for (int i = 0; i < 4; ++i) {
+            uint64_t p = 4 * b + i;
+            int code = 0;
+            if (p < n) {
+                code = encode2b_strict(ascii[p]);
+                if (code < 0) return -1;
+            }
+            packed |= (uint8_t)(code << (6 - 2 * i));
+        }
+        out[b] = packed;
+    }
+    return (int64_t)nbytes;
+}
+
+uint64_t orc_encode_and_add_2bit(const uint8_t* ascii, uint64_t n, uint8_t* out) {
+    // Sequence::encode_and_add  sequence.rs:388-451 : invalid characters are skipped
+    uint64_t kept = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        int code = encode2b_strict(ascii[i]);
+        if (code < 0) continue;
+        if ((kept & 3) == 0) out[kept >> 2] = 0;
+        out[kept >> 2] |= (uint8_t)(code << (6 - 2 * (kept & 3)));
+        ++kept;
+    }
+    return kept;
+}
+
+uint64_t orc_count_non_acgt(const uint8_t* ascii, uint64_t n) {  // alphabet.rs:28-31
+    uint64_t c = 0;
+    for (uint64_t i = 0; i < n; ++i) c += encode2b_strict(ascii[i]) < 0;
+    return c;
+}
+
+uint8_t orc_get_base(const uint8_t* packed, uint64_t pos) { return base_at(packed, pos); }
+
+void orc_unpack_2bit(const uint8_t* packed, uint64_t nbases, uint8_t* ascii_out) {
+    for (uint64_t i = 0; i < nbases; ++i) ascii_out[i] = (uint8_t)DECODE2B[base_at(packed, i)];
+}
+
+void orc_seq_revcomp_2bit(const uint8_t* packed, uint64_t nbases, uint8_t* out) {
+    // meaning of get_reverse_complement_2bitseq (sequence.rs:252-295): base i of the
+    // result is the complement of base n-1-i; same description (tail zero padded... the
+    // reference leaves complemented padding bits in the tail; we reproduce that below)
+    uint64_t len = (nbases + 3) / 4;
+    unsigned inlast = (unsigned)(nbases & 3);
+    unsigned shift_amount = inlast ? 8 - 2 * inlast : 0;
+    unsigned shift_mask = inlast ? (1u << shift_amount) - 1 : 0;
+    for (uint64_t i = 0; i < len; ++i) {
+        uint8_t byte = packed[len - 1 - i];
+        uint8_t rev = byte;
+        if (inlast) {
+            rev = (uint8_t)(rev >> shift_amount);
+            if (i < len - 1) rev |= (uint8_t)((packed[len - 1 - i - 1] & shift_mask) << (8 - shift_amount));
+        }
+        rev = (uint8_t)(((rev & 0x33) << 2) | ((rev & 0xCC) >> 2));
+        rev = (uint8_t)(((rev & 0x0F) << 4) | ((rev & 0xF0) >> 4));
+        rev = (uint8_t)~rev;
+        out[i] = rev;
+    }
+}
+
+uint64_t orc_kmer_build(uint64_t value, int k, int type) { return kmer_build(value, k, type); }
+uint64_t orc_kmer_push(uint64_t word, int k, int type, uint8_t base) { return kmer_push(word, k, type, base); }
+uint64_t orc_kmer_revcomp(uint64_t word, int k, int type) { return kmer_revcomp(word, k, type); }
+int orc_kmer_cmp(uint64_t a, uint64_t b, int k, int type) {
+    (void)k;
+    return kmer_cmp(a, b, type);
+}
+uint64_t orc_kmer_compressed_value(uint64_t word, int k, int type) {
+    (void)k;
+    return kmer_compressed_value(word, type);
+}
+
+uint64_t orc_generate_kmers(const uint8_t* packed, uint64_t nbases, uint64_t begin, uint64_t end, int k, int type,
+                            uint64_t* out) {
+    // KmerSeqIterator::next  kmergenerator.rs:75-106 ; range semantics sequence.rs:562-585
+    if (!kmer_type_accepts(k, type)) return ~0ULL;
+    if (end > nbases || end <= begin) return 0;  // set_range returns Err -> callers unwrap/panic
+    if (end - begin < (uint64_t)k) return 0;
+    uint64_t val = 0;
+    for (int i = 0; i < k; ++i) val = (val << 2) | base_at(packed, begin + i);  // first k-mer via KmerBuilder::build
+    uint64_t word = kmer_build(val, k, type);
+    uint64_t n = 0;
+    out[n++] = word;
+    for (uint64_t p = begin + k; p < end; ++p) {
+        word = kmer_push(word, k, type, base_at(packed, p));
+        out[n++] = word;
+    }
+    return n;
+}
+
+uint64_t orc_apply_hash(uint64_t word, int k, int type, int hash_kind) { return apply_hash(word, k, type, hash_kind); }
+uint32_t orc_int32_hash(uint32_t key) { return int32_hash(key); }
+uint64_t orc_int64_hash(uint64_t key) { return int64_hash(key); }
+
+uint64_t orc_nthash_init(uint64_t word, int k, int type) {  // kmer.rs:48-61
+    uint64_t h = 0;
+    for (int i = 0; i < k; ++i) h ^= rotl64(NT_SEED[kmer_base(word, k, type, i)], (unsigned)(k - i - 1));
+    return h;
+}
+
+int orc_nthash_canonical_init(uint64_t word, int k, int type, uint64_t* fhash, uint64_t* rhash, uint64_t* canon) {
+    // kmer.rs:74-94
+    uint64_t f = 0, r = 0;
+    for (int i = 0; i < k; ++i) {
+        uint8_t b = kmer_base(word, k, type, i);
+        f ^= rotl64(NT_SEED[b], (unsigned)(k - i - 1));
+        r ^= rotl64(NT_SEED[3 - b], (unsigned)i);
+    }
+    *fhash = f;
+    *rhash = r;
+    if (f <= r) {
+        *canon = f;
+        return 0;
+    }
+    *canon = r;
+    return 1;
+}
+
+void orc_nthash_mult(uint64_t h0, int k, uint64_t* hashed, int n) {  // nthash.rs:63-72 (wrapping)
+    if (n <= 0) return;
+    hashed[0] = h0;
+    for (int i = 1; i < n; ++i) {
+        uint64_t t = h0 * ((uint64_t)i ^ ((uint64_t)k * 0x90b45d39fb6da1faULL));
+        t ^= t >> 27;
+        hashed[i] = t;
+    }
+}
+
+uint64_t orc_nthash_cycle(uint64_t word, int k, int type, uint64_t hashval, uint8_t new_base) {
+    // kmer.rs:63-71 : old_base = leftmost base of self; push result is discarded
+    uint8_t old_base = kmer_base(word, k, type, 0);
+    return rotl64(hashval, 1) ^ rotl64(NT_SEED[old_base], (unsigned)k) ^ NT_SEED[new_base & 3];
+}
+
+int orc_nthash_canonical_cycle(uint64_t word, int k, int type, uint8_t new_base, uint64_t* fhash, uint64_t* rhash,
+                               uint64_t* canon) {
+    // kmer.rs:96-117 : fhash/rhash are zeroed first (bug-compatible)
+    uint8_t old_base = kmer_base(word, k, type, 0);
+    uint64_t f = 0, r = 0;
+    f = rotl64(f, 1) ^ rotl64(NT_SEED[old_base], (unsigned)k) ^ NT_SEED[new_base & 3];
+    r = rotr64(r, 1) ^ rotl64(NT_SEED[3 - old_base], (unsigned)k) ^ rotl64(NT_SEED[3 - (new_base & 3)], (unsigned)(k - 1));
+    *fhash = f;
+    *rhash = r;
+    if (f <= r) {
+        *canon = f;
+        return 0;
+    }
+    *canon = r;
+    return 1;
+}
+
+uint64_t orc_nohash_seed(uint64_t key, int key_bytes) { return nohash_seed(key, key_bytes); }
+uint64_t orc_fnv1a_seed(uint64_t key, int key_bytes) { return fnv1a_seed(key, key_bytes); }
+
+void orc_xoshiro_seed(uint64_t seed, uint64_t s[4]) {
+    Xoshiro256pp r(seed);
+    std::memcpy(s, r.s, 32);
+}
+uint64_t orc_xoshiro_next(uint64_t s[4]) {
+    Xoshiro256pp r(0);
+    std::memcpy(r.s, s, 32);
+    uint64_t v = r.next_u64();
+    std::memcpy(s, r.s, 32);
+    return v;
+}
+
+void orc_pmh3a_weighted(const uint64_t* keys, const double* weights, uint64_t n, uint32_t m, int key_bytes,
+                        uint64_t* sig) {
+    pmh3a(keys, weights, n, m, key_bytes, sig);
+}
+
+void orc_sketch_pmh3a_seq(const uint8_t* packed, uint64_t nbases, int k, int type, int hash_kind, uint32_t m,
+                          uint64_t* sig) {
+    FlatCountMap wb;
+    wb.reset(std::min<uint64_t>(nbases, 1ULL << 26));  // get_nbkmer_guess, kmergenerator.rs:207-211
+    count_kmers(packed, nbases, 0, nbases, k, type, hash_kind, wb);
+    sketch_from_map(wb, m, is_u32_type(type) ? 4 : 8, sig);
+}
+
+void orc_sketch_pmh3a_batch(const uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases, uint64_t nseq,
+                            int k, int type, int hash_kind, uint32_t m, void* sig_out, int sig_bytes, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<uint64_t> next(0);
+    auto worker = [&]() {
+        std::vector<uint64_t> sig(m);
+        for (;;) {
+            uint64_t i = next.fetch_add(1);
+            if (i >= nseq) break;
+            orc_sketch_pmh3a_seq(packed + byte_off[i], nbases[i], k, type, hash_kind, m, sig.data());
+            if (sig_bytes == 4) {
+                uint32_t* o = (uint32_t*)sig_out + i * (uint64_t)m;
+                for (uint32_t j = 0; j < m; ++j) o[j] = (uint32_t)sig[j];
+            } else {
+                std::memcpy((uint64_t*)sig_out + i * (uint64_t)m, sig.data(), 8 * (size_t)m);
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+}
+
+void orc_sketch_pmh3a_seqs(const uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases, uint64_t nseq, int k,
+                           int type, int hash_kind, uint32_t m, uint64_t* sig) {
+    FlatCountMap wb;
+    wb.reset(1024);
+    for (uint64_t i = 0; i < nseq; ++i) count_kmers(packed + byte_off[i], nbases[i], 0, nbases[i], k, type, hash_kind, wb);
+    sketch_from_map(wb, m, is_u32_type(type) ? 4 : 8, sig);
+}
+
+uint64_t orc_blocksketch_seq(const uint8_t* packed, uint64_t nbases, int k, uint32_t m, uint64_t block_size,
+                             uint32_t* sig_out, uint64_t max_blocks) {
+    // BlockSeqSketcher::blocksketch_sequence (seqblocksketch.rs:97-149): the number of
+    // blocks comes from BASES, the blocks themselves are runs of block_size K-MERS of
+    // one continuous iterator; trailing blocks may be empty (signature all zero).
+    // fhash = canonical + int32_hash on Kmer32bit (seqblocksketch.rs:462-466)
+    if (nbases == 0 || block_size == 0) return 0;
+    uint64_t nb_blocks = nbases % block_size == 0 ? nbases / block_size : 1 + nbases / block_size;
+    uint64_t nkmers = nbases >= (uint64_t)k ? nbases - k + 1 : 0;
+    std::vector<uint64_t> sig(m);
+    for (uint64_t b = 0; b < nb_blocks && b < max_blocks; ++b) {
+        FlatCountMap wa;
+        wa.reset(block_size);
+        uint64_t first = b * block_size;  // first k-mer index of the block
+        if (first < nkmers) {
+            uint64_t cnt = std::min(block_size, nkmers - first);
+            count_kmers(packed, nbases, first, first + cnt + k - 1, k, ORC_KMER32, ORC_HASH_CANON_INVHASH, wa);
+        }
+        sketch_from_map(wa, m, 4, sig.data());
+        for (uint32_t j = 0; j < m; ++j) sig_out[b * (uint64_t)m + j] = (uint32_t)sig[j];
+    }
+    return nb_blocks;
+}
+
+double orc_jaccard_equal_fraction(const void* a, const void* b, uint32_t m, int sig_bytes) {
+    // compute_probminhash_jaccard (seqsketchjaccard.rs:86-108)
+    uint32_t eq = 0;
+    for (uint32_t i = 0; i < m; ++i)
+        eq += std::memcmp((const uint8_t*)a + (size_t)i * sig_bytes, (const uint8_t*)b + (size_t)i * sig_bytes, sig_bytes) == 0;
+    return (double)eq / (double)m;
+}
+
+// counter-based SplitMix64: output number i (0-based) of stream `seed`
+static inline uint64_t synth_z(uint64_t seed, uint64_t i) {
+    uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+void orc_synth_packed(uint64_t seed, uint64_t first_base, uint64_t nbases, uint8_t* packed_out) {
+    uint64_t nbytes = (nbases + 3) / 4;
+    for (uint64_t b = 0; b < nbytes; ++b) {
+        uint8_t v = 0;
+        for (int i = 0; i < 4; ++i) {
+            uint64_t p = 4 * b + i;
+            unsigned code = p < nbases ? (unsigned)(synth_z(seed, first_base + p) >> 62) : 0u;
+            v |= (uint8_t)(code << (6 - 2 * i));
+        }
+        packed_out[b] = v;
+    }
+}
+
+void orc_synth_ascii(uint64_t seed, uint64_t first_base, uint64_t nbases, uint8_t* ascii_out) {
+    for (uint64_t p = 0; p < nbases; ++p) ascii_out[p] = (uint8_t)DECODE2B[synth_z(seed, first_base + p) >> 62];
+}
+
+int orc_hardware_threads(void) {
+    unsigned n = std::thread::hardware_concurrency();
+    return n ? (int)n : 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+"""GPU parity: ProbMinHash3a signatures from the CUDA path == the CPU oracle, bit for bit."""
+import numpy as np
+import pytest
+
+import kmerutils_b200 as kb
+
+pytestmark = pytest.mark.gpu
+
+S80 = b"TCAAAGGGAAACATTCAAAATCAGTATGCGCCCGTTCAGTTACGTATTGCTCTCGCTAATGAGATGGGCTGGGTACAGAG"
+
+
+def layout(nbases):
+    nb = np.asarray(nbases, dtype=np.uint64)
+    sizes = ((nb + 3) // 4 + 15) // 16 * 16
+    off = np.zeros(len(nb), dtype=np.uint64)
+    off[1:] = np.cumsum(sizes)[:-1]
+    return off, int(sizes.sum())
+
+
+def oracle_batch(oracle, seed, nbases):
+    """Same synthetic reads as kmu_seqbatch_synth: one SplitMix64 stream, reads back to back."""
+    off, total = layout(nbases)
+    packed = np.zeros(total + 64, dtype=np.uint8)
+    first = 0
+    for i, L in enumerate(nbases):
+        L = int(L)
+        packed[int(off[i]): int(off[i]) + (L + 3) // 4] = oracle.synth_packed(seed, first, L)
+        first += L
+    return packed, off
+
+
+def check_config(engine, oracle, seed, nbases, k, ktype, kind, m):
+    nbases = np.asarray(nbases, dtype=np.uint64)
+    batch = engine.batch_synth(seed, nbases)
+    packed, off = oracle_batch(oracle, seed, nbases)
+    dl_packed, dl_off, dl_nb = batch.download()
+    assert np.array_equal(dl_off, off)
+    assert np.array_equal(dl_packed, packed[: len(dl_packed)])
+    got = engine.sketch_pmh3a(batch, k, ktype, kind, m)
+    want = oracle.sketch_pmh3a_batch(packed, off, nbases, k, ktype, kind, m)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert len(bad) == 0, f"{len(bad)} of {len(nbases)} signatures differ, first: seq {bad[:5]} len {nbases[bad[:5]]}"
+    batch.destroy()
+
+
+def test_c1_config(engine, oracle):
+    # BASELINE config 1: 1000 reads x 1000 b, k=8 Kmer32bit, canonical + int32_hash, m=200
+    check_config(engine, oracle, 1, [1000] * 1000, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200)
+
+
+def test_ragged_lengths_k8(engine, oracle):
+    rng = np.random.default_rng(7)
+    nb = np.concatenate([
+        np.arange(1, 40), rng.integers(40, 300, 200), rng.integers(300, 5000, 200), rng.integers(5000, 40000, 40),
+        [70000, 131072, 250000]])
+    check_config(engine, oracle, 2, nb, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200)
+
+
+@pytest.mark.parametrize("k,ktype", [(3, kb.KMER32), (5, kb.KMER32), (11, kb.KMER32), (14, kb.KMER32),
+                                     (16, kb.KMER16B32), (12, kb.KMER64), (21, kb.KMER64), (31, kb.KMER64),
+                                     (32, kb.KMER64)])
+def test_kmer_types(engine, oracle, k, ktype):
+    rng = np.random.default_rng(k)
+    nb = np.concatenate([rng.integers(1, 200, 60), rng.integers(200, 3000, 60), rng.integers(3000, 30000, 12)])
+    check_config(engine, oracle, 10 + k, nb, k, ktype, kb.HASH_CANON_INVHASH, 64)
+
+
+@pytest.mark.parametrize("kind", [kb.HASH_IDENTITY_RAW, kb.HASH_MASKED_VALUE, kb.HASH_CANON_RAW, kb.HASH_INVHASH])
+@pytest.mark.parametrize("k,ktype", [(8, kb.KMER32), (16, kb.KMER16B32), (21, kb.KMER64)])
+def test_hash_kinds(engine, oracle, kind, k, ktype):
+    rng = np.random.default_rng(kind * 100 + k)
+    nb = rng.integers(20, 4000, 80)
+    check_config(engine, oracle, 50 + kind, nb, k, ktype, kind, 50)
+
+
+@pytest.mark.parametrize("m", [2, 3, 17, 255, 256, 257, 1000, 4000, 12000])
+def test_sketch_sizes(engine, oracle, m):
+    rng = np.random.default_rng(m)
+    nb = rng.integers(100, 20000, 24)
+    check_config(engine, oracle, 90, nb, 16, kb.KMER16B32, kb.HASH_CANON_INVHASH, m)
+
+
+def test_low_complexity_and_u16_wrap(engine, oracle):
+    # homopolymers / short tandem repeats: one k-mer with a huge multiplicity, including
+    # > 65535 occurrences (wraps the u16 histogram counters -> table redo path)
+    seqs = [b"A" * 100000, b"AC" * 40000, b"ACGT" * 30, b"T" * 70000 + S80 * 20, S80, b"G" * 9]
+    batch, bad = engine.batch_from_ascii(seqs)
+    assert bad.sum() == 0
+    packed, off, nb = batch.download()
+    for k, ktype in [(8, kb.KMER32), (16, kb.KMER16B32)]:
+        got = engine.sketch_pmh3a(batch, k, ktype, kb.HASH_CANON_INVHASH, 200)
+        want = oracle.sketch_pmh3a_batch(np.concatenate([packed, np.zeros(64, np.uint8)]), off, nb, k, ktype,
+                                         kb.HASH_CANON_INVHASH, 200)
+        assert np.array_equal(got, want)
+
+
+def test_reference_statistical_tests(engine, oracle):
+    # seqsketchjaccard.rs:742-851 : k=5, m=4000 ; J(a, a[0..40]) >= 0.75 * (40-k)/(80-k) ; J(a, revcomp a) >= 1
+    p80 = oracle.pack_2bit(S80)
+    rc = oracle.seq_revcomp(p80, 80)
+    batch = engine.batch_from_sequences([p80, oracle.pack_2bit(S80[:40]), rc], [80, 40, 80])
+    sig = engine.sketch_pmh3a(batch, 5, kb.KMER32, kb.HASH_CANON_INVHASH, 4000)
+    j_half = oracle.jaccard(sig[0], sig[1])
+    assert j_half >= 0.75 * (40 - 5) / (80 - 5)
+    assert oracle.jaccard(sig[0], sig[2]) >= 1.0
+    # identity hash: reverse complement shares (almost) nothing (<= 0.1)
+    sig_id = engine.sketch_pmh3a(batch, 5, kb.KMER32, kb.HASH_IDENTITY_RAW, 4000)
+    assert oracle.jaccard(sig_id[0], sig_id[2]) <= 0.1
