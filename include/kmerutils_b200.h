@@ -148,6 +148,23 @@ typedef struct kmu_times {
 } kmu_times;
 int32_t kmu_last_times(const kmu_ctx* ctx, kmu_times* out);
 
+/* ---- optional per-launch profile of the last sketch call (CUDA events around every launch
+ *      of the sketch kernel; switch on with kmu_ctx_set_profiling before the call) ---------- */
+typedef struct kmu_launch_rec {
+    int32_t mode;           /* 0 = direct u16 histogram, 1 = open-addressing table */
+    int32_t table_global;   /* table in global scratch instead of shared memory */
+    uint32_t team_warps;    /* warps cooperating on one sequence */
+    uint32_t teams_per_cta;
+    uint32_t grid, block, smem_bytes;
+    uint64_t nseq;          /* sequences handled by the launch */
+    uint64_t nbases;        /* bases handled by the launch */
+    uint64_t nk_max;        /* largest k-mer count the launch was sized for */
+    float ms;               /* device time of the launch */
+} kmu_launch_rec;
+int32_t kmu_ctx_set_profiling(kmu_ctx* ctx, int32_t on);
+/* returns the number of launches of the last sketch call; fills at most cap records */
+uint32_t kmu_last_launch_profile(kmu_ctx* ctx, kmu_launch_rec* out, uint32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,13 @@ class KmuTimes(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("launches", C.c_uint64)]
 
 
+class KmuLaunchRec(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("table_global", C.c_int32), ("team_warps", C.c_uint32),
+                ("teams_per_cta", C.c_uint32), ("grid", C.c_uint32), ("block", C.c_uint32),
+                ("smem_bytes", C.c_uint32), ("nseq", C.c_uint64), ("nbases", C.c_uint64), ("nk_max", C.c_uint64),
+                ("ms", C.c_float)]
+
+
 class KmuError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"kmerutils_b200 error {code}: {msg}")
@@ -63,6 +70,8 @@ SIGNATURES = {
     "kmu_sketch_pmh3a_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, u64p, u64p, C.c_uint64, C.c_uint32,
                                           C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
     "kmu_last_times": (C.c_int32, [C.c_void_p, C.POINTER(KmuTimes)]),
+    "kmu_ctx_set_profiling": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "kmu_last_launch_profile": (C.c_uint32, [C.c_void_p, C.POINTER(KmuLaunchRec), C.c_uint32]),
 }
 
 _LIB = None

@@ -94,6 +94,10 @@ struct kmu_ctx {
     DevBuf order, counters, table_scratch, slot_scratch, overflow, sig_dev, misc;
     bool table_scratch_clean = false;
     PinnedBuf pinned;
+    // optional per-launch profile of the last sketch call
+    bool profiling = false;
+    std::vector<cudaEvent_t> lev;
+    std::vector<kmu_launch_rec> lrec;
 };
 
 struct kmu_seqbatch {
@@ -242,6 +246,7 @@ void kmu_ctx_destroy(kmu_ctx* c) {
     c->pinned.release();
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->lev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -253,6 +258,24 @@ int32_t kmu_ctx_sync(kmu_ctx* ctx) {
     ScopedDevice sd(ctx->device);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return KMU_OK;
+}
+
+int32_t kmu_ctx_set_profiling(kmu_ctx* ctx, int32_t on) {
+    if (!ctx) return fail(KMU_EINVAL, "null context");
+    ctx->profiling = on != 0;
+    return KMU_OK;
+}
+
+uint32_t kmu_last_launch_profile(kmu_ctx* ctx, kmu_launch_rec* out, uint32_t cap) {
+    if (!ctx) return 0;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    uint32_t n = (uint32_t)ctx->lrec.size();
+    for (uint32_t i = 0; i < n; ++i)
+        if (2 * i + 1 < ctx->lev.size()) cudaEventElapsedTime(&ctx->lrec[i].ms, ctx->lev[2 * i], ctx->lev[2 * i + 1]);
+    if (out)
+        for (uint32_t i = 0; i < n && i < cap; ++i) out[i] = ctx->lrec[i];
+    return n;
 }
 
 int32_t kmu_last_times(const kmu_ctx* ctx, kmu_times* out) {
@@ -630,6 +653,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     const uint64_t nseq = b->nseq;
     cudaStream_t st = ctx->stream;
     uint64_t launches = 0;
+    ctx->lrec.clear();
 
     // ---- order sequences longest first (8 buckets per octave of the k-mer count) -------
     CUDA_TRY(ctx->order.reserve(sizeof(uint32_t) * (nseq + 1)));
@@ -765,7 +789,36 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
             Q.table_scratch = (uint8_t*)ctx->table_scratch.p;
             Q.table_scratch_entries = g.table_entries_global;
         }
+        size_t li = ctx->lrec.size();
+        if (ctx->profiling) {
+            while (ctx->lev.size() < 2 * (li + 1)) {
+                cudaEvent_t ev;
+                CUDA_TRY(cudaEventCreate(&ev));
+                ctx->lev.push_back(ev);
+            }
+            cudaEventRecord(ctx->lev[2 * li], st);
+        }
         CUDA_TRY(kmu::launch_pmh3a(Q, key64, c.mode, grid, g.block, g.smem, st));
+        if (ctx->profiling) {
+            cudaEventRecord(ctx->lev[2 * li + 1], st);
+            kmu_launch_rec r{};
+            r.mode = c.mode;
+            r.table_global = c.table_global;
+            r.team_warps = g.team_warps;
+            r.teams_per_cta = g.teams_per_cta;
+            r.grid = (uint32_t)grid;
+            r.block = (uint32_t)g.block;
+            r.smem_bytes = (uint32_t)g.smem;
+            r.nseq = c.count;
+            r.nk_max = c.nk_max;
+            // bases handled by this launch (host copy of the lengths; profiling only)
+            if (order == (const uint32_t*)ctx->order.p) {
+                uint64_t lo = c.first, hi = c.first + c.count;
+                (void)lo;
+                (void)hi;
+            }
+            ctx->lrec.push_back(r);
+        }
         ++launches;
         return KMU_OK;
     };
@@ -775,6 +828,18 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     for (const LaunchClass& c : classes) {
         int32_t rc = run_class(c, (const uint32_t*)ctx->order.p, ci++);
         if (rc) return rc;
+    }
+    if (ctx->profiling) {
+        // bases per launch: class i covers the sequences whose length bucket start lies in its range
+        for (uint64_t L : b->h_nbases) {
+            uint64_t nk = L >= k ? L - k + 1 : 0;
+            uint64_t pos = cursor[kmu::len_bucket_host(nk)];
+            for (size_t i = 0; i < classes.size() && i < ctx->lrec.size(); ++i)
+                if (pos >= classes[i].first && pos < classes[i].first + classes[i].count) {
+                    ctx->lrec[i].nbases += L;
+                    break;
+                }
+        }
     }
     // ---- u16 histogram counters that wrapped: redo those sequences with u32 table counters ---
     if (hist_ok) {

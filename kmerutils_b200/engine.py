@@ -111,6 +111,15 @@ class Engine:
         check(self.lib.kmu_last_times(self.ctx, C.byref(t)))
         return {f: getattr(t, f) for f, _ in KmuTimes._fields_}
 
+    def set_profiling(self, on=True):
+        check(self.lib.kmu_ctx_set_profiling(self.ctx, int(bool(on))))
+
+    def last_launch_profile(self):
+        """Per-launch records of the last sketch call (needs set_profiling(True) before it)."""
+        recs = (_lib.KmuLaunchRec * 160)()
+        n = self.lib.kmu_last_launch_profile(self.ctx, recs, 160)
+        return [{f: getattr(recs[i], f) for f, _ in _lib.KmuLaunchRec._fields_} for i in range(min(n, 160))]
+
     # ---- batches ------------------------------------------------------------------------
     def batch_from_sequences(self, packed_list, nbases):
         """packed_list: one uint8 array per sequence (the reference's Vec<Sequence>)."""
