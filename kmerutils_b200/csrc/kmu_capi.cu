@@ -94,6 +94,10 @@ struct kmu_ctx {
     DevBuf order, counters, table_scratch, slot_scratch, overflow, sig_dev, misc;
     bool table_scratch_clean = false;
     PinnedBuf pinned;
+    // first-point table of the ProbMinHash3a kernels (small key spaces), see kmu_pmh3a.cu
+    DevBuf memo;
+    uint32_t memo_k = 0, memo_m = 0;
+    int memo_type = -1, memo_hash = -1;
     // optional per-launch profile of the last sketch call
     bool profiling = false;
     std::vector<cudaEvent_t> lev;
@@ -241,7 +245,7 @@ void kmu_ctx_destroy(kmu_ctx* c) {
     if (!c) return;
     ScopedDevice sd(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (auto* b : {&c->order, &c->counters, &c->table_scratch, &c->slot_scratch, &c->overflow, &c->sig_dev, &c->misc})
+    for (auto* b : {&c->order, &c->counters, &c->table_scratch, &c->slot_scratch, &c->overflow, &c->sig_dev, &c->misc, &c->memo})
         b->release();
     c->pinned.release();
     for (auto& ev : c->ev)
@@ -610,9 +614,9 @@ Geometry make_geometry(uint64_t nk_max, int mode, uint32_t k, uint32_t m, bool k
     Geometry g{};
     const size_t entry = kmu::pmh3a_entry_bytes(key64);
     const size_t qitem = kmu::pmh3a_qitem_bytes(key64);
-    // ~128 k-mers per warp
+    // about 512 k-mers per warp and pass (16 per lane)
     uint32_t tw = 1;
-    while (tw < 32 && (uint64_t)tw * 128 < nk_max) tw <<= 1;
+    while (tw < 32 && (uint64_t)tw * 512 < nk_max) tw <<= 1;
     uint64_t regionA;
     g.table_entries_global = 0;
     if (mode == 0) {
@@ -627,21 +631,28 @@ Geometry make_geometry(uint64_t nk_max, int mode, uint32_t k, uint32_t m, bool k
         }
     }
     const uint64_t slots = (uint64_t)m * 16;
-    const uint64_t fixed = regionA + (uint64_t)tw * 64 * qitem + 32;
-    const bool slots_in_smem = fixed + slots <= SMEM_BUDGET;
-    const uint64_t team_bytes = align_up(slots_in_smem ? fixed + slots : fixed, 16);
-    uint32_t max_teams = 32 / tw;
-    if (tw > 1 && max_teams > 15) max_teams = 15;  // named barriers 1..15
-    uint32_t teams = std::min<uint32_t>(max_teams, (uint32_t)(SMEM_BUDGET / team_bytes));
-    if (teams == 0) teams = 1;
-    g.team_warps = tw;
-    g.teams_per_cta = teams;
-    g.regionA_bytes = (uint32_t)regionA;
-    g.slots_smem_bytes = slots_in_smem ? (uint32_t)slots : 0;
-    g.team_smem_bytes = (uint32_t)team_bytes;
-    g.block = (int)(tw * 32 * teams);
-    g.smem = (size_t)team_bytes * teams;
-    return g;
+    for (;;) {
+        const uint64_t fixed = regionA + (uint64_t)tw * 64 * qitem + 32;
+        const bool slots_in_smem = fixed + slots <= SMEM_BUDGET;
+        const uint64_t team_bytes = align_up(slots_in_smem ? fixed + slots : fixed, 16);
+        const uint32_t teams_fit = std::max<uint32_t>(1, (uint32_t)(SMEM_BUDGET / team_bytes));
+        uint32_t max_teams = 32 / tw;
+        if (tw > 1 && max_teams > 15) max_teams = 15;  // named barriers 1..15
+        // shared memory limits the number of teams: widen the teams so that the SM still gets 32 warps
+        if (tw < 32 && teams_fit < 32 / tw) {
+            tw <<= 1;
+            continue;
+        }
+        const uint32_t teams = std::min(max_teams, teams_fit);
+        g.team_warps = tw;
+        g.teams_per_cta = teams;
+        g.regionA_bytes = (uint32_t)regionA;
+        g.slots_smem_bytes = slots_in_smem ? (uint32_t)slots : 0;
+        g.team_smem_bytes = (uint32_t)team_bytes;
+        g.block = (int)(tw * 32 * teams);
+        g.smem = (size_t)team_bytes * teams;
+        return g;
+    }
 }
 
 }  // namespace
@@ -706,7 +717,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         if (!classes.empty()) {
             LaunchClass& p = classes.back();
             bool same = p.mode == c.mode && p.table_global == c.table_global &&
-                        ((c.mode == 1 && c.table_global) || (c.mode == 0 && c.nk_max >= 4096));
+                        ((c.mode == 1 && c.table_global) || (c.mode == 0 && hist_bytes > 64 * 1024));
             if (same) {
                 p.count += c.count;
                 continue;
@@ -742,6 +753,23 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     CUDA_TRY(ctx->overflow.reserve(sizeof(uint32_t) * (nseq + 1)));
     P.overflow_count = d_ovf_count;
     P.overflow_list = (uint32_t*)ctx->overflow.p;
+    // first point of every possible pre-key, when the key space is small (k <= 10): built once per
+    // (k, type, hash, m) and kept in the context (16 B per key, L2 resident)
+    P.memo = nullptr;
+    if (2 * k <= 20) {
+        const uint32_t nkeys = 1u << (2 * k);
+        if (!(ctx->memo.p && ctx->memo_k == k && ctx->memo_m == m && ctx->memo_type == kmer_type &&
+              ctx->memo_hash == hash_kind)) {
+            CUDA_TRY(ctx->memo.reserve((size_t)nkeys * 16));
+            CUDA_TRY(kmu::launch_pmh3a_memo(P, key64, ctx->memo.p, nkeys, st));
+            ++launches;
+            ctx->memo_k = k;
+            ctx->memo_m = m;
+            ctx->memo_type = kmer_type;
+            ctx->memo_hash = hash_kind;
+        }
+        P.memo = ctx->memo.p;
+    }
 
     auto run_class = [&](const LaunchClass& c, const uint32_t* order, int counter_idx) -> int32_t {
         Geometry g = make_geometry(c.nk_max, c.mode, k, m, key64, c.table_global);
@@ -811,12 +839,6 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
             r.smem_bytes = (uint32_t)g.smem;
             r.nseq = c.count;
             r.nk_max = c.nk_max;
-            // bases handled by this launch (host copy of the lengths; profiling only)
-            if (order == (const uint32_t*)ctx->order.p) {
-                uint64_t lo = c.first, hi = c.first + c.count;
-                (void)lo;
-                (void)hi;
-            }
             ctx->lrec.push_back(r);
         }
         ++launches;

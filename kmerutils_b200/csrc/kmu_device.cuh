@@ -288,4 +288,47 @@ struct KmerWalker {
     __device__ __forceinline__ V prekey(bool canonical) const { return canonical ? (fwd < rc ? fwd : rc) : fwd; }
 };
 
+// ----------------------------------------------------------------------------
+//  TaskKmers: the k-mers of one task = T consecutive start positions (T in
+//  {4, 8, 16}, the first one a multiple of T).  For u32 k-mers (k <= 16) two
+//  big-endian words hold every window of the task, so each k-mer is two funnel
+//  shifts and a mask on the word pair and on its reverse complement; u64 k-mers
+//  roll through KmerWalker.  get(t) must be called for t = 0, 1, 2, ... in order
+//  and only for positions that exist.
+// ----------------------------------------------------------------------------
+template <typename V>
+struct TaskKmers;
+
+template <>
+struct TaskKmers<uint32_t> {
+    uint64_t W, RC;
+    uint32_t mask, sh0, j0;
+    __device__ __forceinline__ void init(const uint32_t* words, uint64_t p0, uint32_t k) {
+        const uint32_t* w = words + (p0 >> 4);
+        uint32_t w0 = be32(__ldg(w)), w1 = be32(__ldg(w + 1));
+        W = ((uint64_t)w0 << 32) | w1;
+        RC = revcomp_word64(W);
+        mask = value_mask<uint32_t>(2 * k);
+        sh0 = 64 - 2 * k;
+        j0 = (uint32_t)(p0 & 15);
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t t, bool canonical) {
+        uint32_t j = j0 + t;
+        uint32_t f = (uint32_t)(W >> (sh0 - 2 * j)) & mask;
+        if (!canonical) return f;
+        uint32_t r = (uint32_t)(RC >> (2 * j)) & mask;
+        return f < r ? f : r;
+    }
+};
+
+template <>
+struct TaskKmers<uint64_t> {
+    KmerWalker<uint64_t> wk;
+    __device__ __forceinline__ void init(const uint32_t* words, uint64_t p0, uint32_t k) { wk.start(words, p0, k); }
+    __device__ __forceinline__ uint64_t get(uint32_t, bool canonical) {
+        wk.roll();
+        return wk.prekey(canonical);
+    }
+};
+
 }  // namespace kmu

@@ -49,8 +49,11 @@ struct Pmh3aParams {
     uint64_t table_scratch_entries;
     unsigned long long* overflow_count;
     uint32_t* overflow_list;
+    // first point of every pre-key {x bits lo, x bits hi, slot, 0}, or nullptr (key space too large)
+    const void* memo;
 };
 
+cudaError_t launch_pmh3a_memo(const Pmh3aParams& P, bool key64, void* memo, uint32_t nkeys, cudaStream_t stream);
 size_t pmh3a_qitem_bytes(bool key64);
 size_t pmh3a_entry_bytes(bool key64);
 cudaError_t launch_pmh3a(const Pmh3aParams& P, bool key64, int mode, int grid, int block, size_t smem,

@@ -143,6 +143,24 @@ struct QItem {
 
 constexpr int QCAP = 64;  // per-warp queue capacity (power of two, >= 2 * 32)
 
+// Cheap upper bound of the slot maxima (MaxValueTracker's root): only the high words of the
+// h bit patterns are scanned, the bound is (max_hi, 0xFFFFFFFF).  Any stale or loose bound is
+// safe: qmax tests only prune points that cannot win a slot.
+__device__ __forceinline__ void refresh_qmax(const Slot* slots, uint32_t m, int lane, uint32_t* s_qmax_hi) {
+    uint32_t mx = 0;
+    for (uint32_t j = lane; j < m; j += 32) {
+        uint32_t hi = *((volatile const uint32_t*)&slots[j].hbits + 1);
+        mx = hi > mx ? hi : mx;
+    }
+    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+    if (lane == 0 && mx < *(volatile uint32_t*)s_qmax_hi) atomicMin(s_qmax_hi, mx);
+    __syncwarp();
+}
+__device__ __forceinline__ double load_qmax(const uint32_t* s_qmax_hi) {
+    uint32_t hi = *(volatile const uint32_t*)s_qmax_hi;
+    return __hiloint2double((int)hi, (int)0xFFFFFFFFu);
+}
+
 // --------------------------------------------------------------------------------
 // Process up to 32 queued distinct items with one warp: every lane owns one item and
 // emits its points i = 1, 2, ... while winv * (i - 1) < qmax
@@ -150,8 +168,8 @@ constexpr int QCAP = 64;  // per-warp queue capacity (power of two, >= 2 * 32)
 // --------------------------------------------------------------------------------
 template <typename V>
 __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t head, uint32_t n, int lane,
-                                              const Pmh3aParams& P, V header, Slot* slots,
-                                              unsigned long long* s_qmax, uint32_t refresh_period) {
+                                              const Pmh3aParams& P, V header, Slot* slots, uint32_t* s_qmax_hi,
+                                              uint32_t refresh_period) {
     bool act = (uint32_t)lane < n;
     V key = 0;
     double winv = 0.0;
@@ -165,20 +183,13 @@ __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t he
     }
     uint32_t i = 1;
     uint32_t iter = 0;
+    double qmax = load_qmax(s_qmax_hi);
     while (__any_sync(0xFFFFFFFFu, act)) {
-        if (iter % refresh_period == 0) {
-            // lazily refreshed upper bound of the slot maxima (MaxValueTracker's root)
-            uint64_t mx = 0;
-            for (uint32_t j = lane; j < P.m; j += 32) {
-                uint64_t hb = *(volatile uint64_t*)&slots[j].hbits;
-                mx = hb > mx ? hb : mx;
-            }
-            mx = warp_max_u64(mx);
-            if (lane == 0 && mx < *(volatile unsigned long long*)s_qmax) atomicMin(s_qmax, (unsigned long long)mx);
-            __syncwarp();
+        if (iter % refresh_period == refresh_period - 1) {
+            refresh_qmax(slots, P.m, lane, s_qmax_hi);
+            qmax = load_qmax(s_qmax_hi);
         }
         ++iter;
-        double qmax = __longlong_as_double((long long)*(volatile unsigned long long*)s_qmax);
         if (act) {
             double base = __dmul_rn(winv, (double)(i - 1));
             if (!(base < qmax)) {
@@ -192,6 +203,7 @@ __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t he
                     uint32_t s = rng.unif_range(0, P.m, P.slot_thresh);
                     slot_update_min(&slots[s], (uint64_t)__double_as_longlong(h), (uint64_t)key);
                     ++i;
+                    if (!(__dmul_rn(winv, (double)(i - 1)) < qmax)) act = false;
                 }
             }
         }
@@ -199,7 +211,10 @@ __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t he
 }
 
 // MODE 0: direct histogram of 4^k u16 counters (two per u32) ; MODE 1: open-addressing table
-template <typename V, int MODE>
+// MEMO : the first point of every possible pre-key (exp01 sample and slot, both functions of
+//        the key only) comes from a table built once per (k, type, hash, m); only items that
+//        need a second point are seeded on the fly.
+template <typename V, int MODE, bool MEMO>
 __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
     using TO = TableOps<V>;
@@ -208,21 +223,20 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
     Team team;
     team.size = P.team_warps * 32;
     team.id = threadIdx.x / team.size;
-    team.tid = threadIdx.x % team.size;
+    team.tid = threadIdx.x - team.id * team.size;
     team.warp = team.tid >> 5;
     team.lane = threadIdx.x & 31;
     const int nteams = blockDim.x / team.size;
-    (void)nteams;
 
     // ---- carve the team's shared memory ------------------------------------------
     uint8_t* tbase = smem + (size_t)team.id * P.team_smem_bytes;
     uint8_t* regionA = tbase;                                     // histogram or table
     Slot* slots = (Slot*)(tbase + P.regionA_bytes);               // m slots (if in smem)
     QItem<V>* queues = (QItem<V>*)(tbase + P.regionA_bytes + P.slots_smem_bytes);
-    unsigned long long* s_qmax =
-        (unsigned long long*)((uint8_t*)queues + (size_t)P.team_warps * QCAP * sizeof(QItem<V>));
-    volatile unsigned long long* s_work = (volatile unsigned long long*)(s_qmax + 1);
-    volatile uint32_t* s_flag = (volatile uint32_t*)(s_qmax + 2);
+    uint32_t* s_misc = (uint32_t*)((uint8_t*)queues + (size_t)P.team_warps * QCAP * sizeof(QItem<V>));
+    uint32_t* s_qmax_hi = s_misc;                                       // u32
+    volatile uint32_t* s_flag = s_misc + 1;                             // u32
+    volatile unsigned long long* s_work = (volatile unsigned long long*)(s_misc + 2);
     if (P.slots_smem_bytes == 0)
         slots = P.slot_scratch + ((size_t)blockIdx.x * nteams + team.id) * P.m;
     QItem<V>* myq = queues + (size_t)team.warp * QCAP;
@@ -233,7 +247,7 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
     const V header = (V)word_header(P.kmer_type, P.k);
     const bool canonical = hash_is_canonical(P.hash_kind);
     const uint32_t k = P.k;
-    const uint32_t refresh_period = P.m <= 256 ? 1u : P.m / 256;
+    const uint32_t refresh_period = P.m <= 512 ? 1u : P.m / 512;
     Entry* gtab = nullptr;
     if (MODE == 1 && P.table_scratch)
         gtab = (Entry*)P.table_scratch + ((size_t)blockIdx.x * nteams + team.id) * P.table_scratch_entries;
@@ -254,14 +268,15 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
             slots[j].key = 0;
         }
         if (team.tid == 0) {
-            *s_qmax = F64_MAX_BITS;
+            *s_qmax_hi = (uint32_t)(F64_MAX_BITS >> 32);
             *s_flag = 0;
         }
-        // positions per task
-        uint32_t T = 4;
-        if (nk >= (uint64_t)team.size * 32) T = 16;
-        else if (nk >= (uint64_t)team.size * 16) T = 8;
-        const uint64_t ntasks = (nk + T - 1) / T;
+        // positions per task: 16 (one word), or 8 / 4 when there are too few words to occupy the team
+        uint32_t log2T = 4;
+        if (nk < (uint64_t)team.size * 8) log2T = 2;
+        else if (nk < (uint64_t)team.size * 16) log2T = 3;
+        const uint32_t T = 1u << log2T;
+        const uint64_t ntasks = (nk + T - 1) >> log2T;
 
         // table geometry for this sequence
         Entry* tab = (Entry*)regionA;
@@ -276,17 +291,22 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
         team.sync();
 
         // ---------------- pass 1 : multiplicities ------------------------------------
+        const bool may_wrap = nk > 0xFFFFu;
         for (uint64_t task = team.tid; task < ntasks; task += team.size) {
-            KmerWalker<V> wk;
-            uint64_t p = task * T;
-            wk.start(words, p, k);
+            TaskKmers<V> tk;
+            uint64_t p = task << log2T;
+            tk.init(words, p, k);
             for (uint32_t t = 0; t < T && p < nk; ++t, ++p) {
-                wk.roll();
-                V pk = wk.prekey(canonical);
+                V pk = tk.get(t, canonical);
                 if (MODE == 0) {
                     uint32_t sh = ((uint32_t)pk & 1u) * 16;
-                    uint32_t old = atomicAdd((uint32_t*)regionA + ((uint32_t)pk >> 1), 1u << sh);
-                    if (((old >> sh) & 0xFFFFu) == 0xFFFFu) *s_flag = 1;  // u16 counter wrapped
+                    uint32_t* wp = (uint32_t*)regionA + ((uint32_t)pk >> 1);
+                    if (may_wrap) {
+                        uint32_t old = atomicAdd(wp, 1u << sh);
+                        if (((old >> sh) & 0xFFFFu) == 0xFFFFu) *s_flag = 1;  // u16 counter wrapped
+                    } else {
+                        atomicAdd(wp, 1u << sh);  // result unused: RED
+                    }
                 } else {
                     TO::insert(tab, capmask, log2cap, pk);
                 }
@@ -300,15 +320,19 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
         for (uint64_t tbase_i = (uint64_t)team.warp * 32; tbase_i < ntasks; tbase_i += team.size) {
             const uint64_t task = tbase_i + team.lane;
             const bool tact = task < ntasks;
-            KmerWalker<V> wk;
-            uint64_t p = task * T;
-            if (tact) wk.start(words, p, k);
+            TaskKmers<V> tk;
+            uint64_t p = task << log2T;
+            if (tact) tk.init(words, p, k);
+            double qmax = 0.0;
+            if (MEMO) {
+                refresh_qmax(slots, P.m, team.lane, s_qmax_hi);
+                qmax = load_qmax(s_qmax_hi);
+            }
             for (uint32_t t = 0; t < T; ++t, ++p) {
                 uint32_t cnt = 0;
                 V pk = 0;
                 if (tact && p < nk) {
-                    wk.roll();
-                    pk = wk.prekey(canonical);
+                    pk = tk.get(t, canonical);
                     if (MODE == 0) {
                         uint32_t sh = ((uint32_t)pk & 1u) * 16;
                         uint32_t* wp = (uint32_t*)regionA + ((uint32_t)pk >> 1);
@@ -320,6 +344,21 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
                         }
                     } else {
                         cnt = TO::claim(tab, capmask, log2cap, pk);
+                    }
+                }
+                if (MEMO) {
+                    // first point from the per-key table; only items that may need a second
+                    // point (winv < qmax) go to the queue
+                    if (cnt) {
+                        const uint4 e = __ldg((const uint4*)P.memo + (uint32_t)pk);
+                        const double x = __hiloint2double((int)e.y, (int)e.x);
+                        const double winv = cnt == 1 ? 1.0 : 1.0 / (double)cnt;
+                        const double h = __dmul_rn(winv, x);
+                        if (h < qmax) {
+                            const V key = finalize_key<V>(pk, header, P.hash_kind);
+                            slot_update_min(&slots[e.z], (uint64_t)__double_as_longlong(h), (uint64_t)key);
+                        }
+                        if (!(h < qmax) || !(winv < qmax)) cnt = 0;
                     }
                 }
                 const uint32_t bal = __ballot_sync(0xFFFFFFFFu, cnt != 0);
@@ -334,14 +373,16 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
                     qtail += __popc(bal);
                     __syncwarp();
                     if (qtail - qhead >= 32) {
-                        process_items<V>(myq, qhead, 32, team.lane, P, header, slots, s_qmax, refresh_period);
+                        process_items<V>(myq, qhead, 32, team.lane, P, header, slots, s_qmax_hi, refresh_period);
                         qhead += 32;
                         __syncwarp();
+                        if (MEMO) qmax = load_qmax(s_qmax_hi);
                     }
                 }
             }
         }
-        if (qtail != qhead) process_items<V>(myq, qhead, qtail - qhead, team.lane, P, header, slots, s_qmax, refresh_period);
+        if (qtail != qhead)
+            process_items<V>(myq, qhead, qtail - qhead, team.lane, P, header, slots, s_qmax_hi, refresh_period);
         team.sync();
 
         // ---------------- signature out, leave region A clean --------------------------
@@ -355,18 +396,43 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
             for (uint32_t j = team.tid; j < P.m; j += team.size) out[j] = (V)slots[j].key;
         }
         if (MODE == 1) {
-            const uint64_t nwords = ((uint64_t)capmask + 1) * (sizeof(Entry) / 4);
-            for (uint64_t j = team.tid; j < nwords; j += team.size) ((uint32_t*)tab)[j] = 0;
+            const uint64_t nvec = ((uint64_t)capmask + 1) * (sizeof(Entry) / 8) / 2;  // 16-byte vectors
+            for (uint64_t j = team.tid; j < nvec; j += team.size) ((uint4*)tab)[j] = make_uint4(0, 0, 0, 0);
         }
     }
+}
+
+// first point of every pre-key: {x bits lo, x bits hi, slot, 0}
+template <typename V>
+__global__ void pmh3a_memo_kernel(uint4* memo, uint32_t nkeys, Pmh3aParams P) {
+    const V header = (V)word_header(P.kmer_type, P.k);
+    for (uint32_t pk = blockIdx.x * blockDim.x + threadIdx.x; pk < nkeys; pk += gridDim.x * blockDim.x) {
+        V key = finalize_key<V>((V)pk, header, P.hash_kind);
+        Xoshiro256pp rng;
+        rng.seed(nohash_seed(key));
+        double x = exp01_sample(P.e, rng);
+        uint32_t s = rng.unif_range(0, P.m, P.slot_thresh);
+        memo[pk] = make_uint4((uint32_t)__double2loint(x), (uint32_t)__double2hiint(x), s, 0u);
+    }
+}
+
+cudaError_t launch_pmh3a_memo(const Pmh3aParams& P, bool key64, void* memo, uint32_t nkeys, cudaStream_t stream) {
+    int block = 256;
+    int grid = (int)((nkeys + block - 1) / block);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (key64)
+        pmh3a_memo_kernel<uint64_t><<<grid, block, 0, stream>>>((uint4*)memo, nkeys, P);
+    else
+        pmh3a_memo_kernel<uint32_t><<<grid, block, 0, stream>>>((uint4*)memo, nkeys, P);
+    return cudaGetLastError();
 }
 
 // --------------------------------------------------------------------------------
 // host-side launcher
 // --------------------------------------------------------------------------------
-template <typename V, int MODE>
+template <typename V, int MODE, bool MEMO>
 static cudaError_t launch_one(const Pmh3aParams& P, int grid, int block, size_t smem, cudaStream_t stream) {
-    auto kern = pmh3a_sketch_kernel<V, MODE>;
+    auto kern = pmh3a_sketch_kernel<V, MODE, MEMO>;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -384,12 +450,19 @@ size_t pmh3a_entry_bytes(bool key64) {
 
 cudaError_t launch_pmh3a(const Pmh3aParams& P, bool key64, int mode, int grid, int block, size_t smem,
                          cudaStream_t stream) {
+    const bool memo = P.memo != nullptr;
     if (key64) {
-        return mode == 0 ? launch_one<uint64_t, 0>(P, grid, block, smem, stream)
-                         : launch_one<uint64_t, 1>(P, grid, block, smem, stream);
+        if (memo)
+            return mode == 0 ? launch_one<uint64_t, 0, true>(P, grid, block, smem, stream)
+                             : launch_one<uint64_t, 1, true>(P, grid, block, smem, stream);
+        return mode == 0 ? launch_one<uint64_t, 0, false>(P, grid, block, smem, stream)
+                         : launch_one<uint64_t, 1, false>(P, grid, block, smem, stream);
     }
-    return mode == 0 ? launch_one<uint32_t, 0>(P, grid, block, smem, stream)
-                     : launch_one<uint32_t, 1>(P, grid, block, smem, stream);
+    if (memo)
+        return mode == 0 ? launch_one<uint32_t, 0, true>(P, grid, block, smem, stream)
+                         : launch_one<uint32_t, 1, true>(P, grid, block, smem, stream);
+    return mode == 0 ? launch_one<uint32_t, 0, false>(P, grid, block, smem, stream)
+                     : launch_one<uint32_t, 1, false>(P, grid, block, smem, stream);
 }
 
 }  // namespace kmu
