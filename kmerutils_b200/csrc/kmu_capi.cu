@@ -37,7 +37,7 @@ int32_t fail(int32_t code, const char* fmt, ...) {
         if (_e != cudaSuccess) return fail(KMU_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
     } while (0)
 
-constexpr size_t SMEM_BUDGET = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
+constexpr size_t SMEM_BUDGET = 227 * 1024 - 1024;  // opt-in shared memory per CTA on sm_100 minus static use
 constexpr size_t SEQ_ALIGN = 16;
 constexpr size_t TAIL_SLACK = 64;
 
@@ -598,7 +598,7 @@ struct LaunchClass {
 
 // geometry of one launch for sequences of at most nk_max k-mers
 struct Geometry {
-    uint32_t team_warps, teams_per_cta, regionA_bytes, slots_smem_bytes, team_smem_bytes;
+    uint32_t team_warps, teams_per_cta, regionA_bytes, slots_smem_bytes, team_smem_bytes, stage_bytes;
     int block;
     size_t smem;
     uint64_t table_entries_global;  // per team, 0 if the table lives in shared memory
@@ -620,7 +620,7 @@ Geometry make_geometry(uint64_t nk_max, int mode, uint32_t k, uint32_t m, bool k
     uint64_t regionA;
     g.table_entries_global = 0;
     if (mode == 0) {
-        regionA = (1ull << (2 * k)) * 2;
+        regionA = (1ull << (2 * k));  // u8 counters
         if (regionA < 16) regionA = 16;
     } else {
         uint64_t entries = pow2_at_least(std::max<uint64_t>(64, 2 * nk_max));
@@ -631,8 +631,18 @@ Geometry make_geometry(uint64_t nk_max, int mode, uint32_t k, uint32_t m, bool k
         }
     }
     const uint64_t slots = (uint64_t)m * 16;
+    // TMA staging buffers: two per team, each large enough for the longest sequence of the
+    // launch up to 16 KB (64 k bases); longer sequences are read from global memory
+    const uint64_t stage = std::min<uint64_t>(16 * 1024, align_up(nk_max / 4 + k + 32, 16));
+    g.stage_bytes = (uint32_t)stage;
+    if (tw == 32) {
+        // two 16-warp teams keep more sequences in flight than one 32-warp team, if both fit
+        const uint64_t fixed16 = regionA + 16ull * 64 * qitem + 2 * stage + kmu::PMH3A_TEAM_SHARED_BYTES;
+        const uint64_t team16 = align_up(fixed16 + slots <= SMEM_BUDGET ? fixed16 + slots : fixed16, 16);
+        if (2 * team16 <= SMEM_BUDGET) tw = 16;
+    }
     for (;;) {
-        const uint64_t fixed = regionA + (uint64_t)tw * 64 * qitem + 32;
+        const uint64_t fixed = regionA + (uint64_t)tw * 64 * qitem + 2 * stage + kmu::PMH3A_TEAM_SHARED_BYTES;
         const bool slots_in_smem = fixed + slots <= SMEM_BUDGET;
         const uint64_t team_bytes = align_up(slots_in_smem ? fixed + slots : fixed, 16);
         const uint32_t teams_fit = std::max<uint32_t>(1, (uint32_t)(SMEM_BUDGET / team_bytes));
@@ -704,7 +714,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         c.first = cursor[b_hi];
         c.count = cnt;
         c.nk_max = nk_max;
-        const uint64_t hist_bytes = (1ull << (2 * k)) * 2;
+        const uint64_t hist_bytes = (1ull << (2 * k));  // u8 counters
         if (hist_ok && (table_bytes > 128 * 1024 || hist_bytes <= table_bytes)) {
             c.mode = 0;
             c.table_global = false;
@@ -712,15 +722,17 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
             c.mode = 1;
             c.table_global = table_bytes > 128 * 1024;
         }
-        // merge with the previous class when both are "table in global memory" or both are histogram
-        // with full-size teams: identical geometry, one launch
+        // merge with the previous (longer) class when the team geometry is the same and the counting
+        // structure does not depend on the length (histogram, or table in global memory): one launch
         if (!classes.empty()) {
             LaunchClass& p = classes.back();
-            bool same = p.mode == c.mode && p.table_global == c.table_global &&
-                        ((c.mode == 1 && c.table_global) || (c.mode == 0 && hist_bytes > 64 * 1024));
-            if (same) {
-                p.count += c.count;
-                continue;
+            if (p.mode == c.mode && p.table_global == c.table_global && (c.mode == 0 || c.table_global)) {
+                Geometry gp = make_geometry(p.nk_max, p.mode, k, m, key64, p.table_global);
+                Geometry gc = make_geometry(c.nk_max, c.mode, k, m, key64, c.table_global);
+                if (gp.team_warps == gc.team_warps && gp.teams_per_cta == gc.teams_per_cta) {
+                    p.count += c.count;
+                    continue;
+                }
             }
         }
         classes.push_back(c);
@@ -753,22 +765,24 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     CUDA_TRY(ctx->overflow.reserve(sizeof(uint32_t) * (nseq + 1)));
     P.overflow_count = d_ovf_count;
     P.overflow_list = (uint32_t*)ctx->overflow.p;
-    // first point of every possible pre-key, when the key space is small (k <= 10): built once per
-    // (k, type, hash, m) and kept in the context (16 B per key, L2 resident)
-    P.memo = nullptr;
-    if (2 * k <= 20) {
+    // per pre-key tables when the key space is small (u32 key types, k <= 10): built once per
+    // (k, type, hash, m) and kept in the context (48 B per key, L2 resident)
+    P.memo_fast = nullptr;
+    P.memo_state = nullptr;
+    if (!key64 && 2 * k <= 20) {
         const uint32_t nkeys = 1u << (2 * k);
         if (!(ctx->memo.p && ctx->memo_k == k && ctx->memo_m == m && ctx->memo_type == kmer_type &&
               ctx->memo_hash == hash_kind)) {
-            CUDA_TRY(ctx->memo.reserve((size_t)nkeys * 16));
-            CUDA_TRY(kmu::launch_pmh3a_memo(P, key64, ctx->memo.p, nkeys, st));
+            CUDA_TRY(ctx->memo.reserve((size_t)nkeys * 48));
+            CUDA_TRY(kmu::launch_pmh3a_memo(P, ctx->memo.p, (uint8_t*)ctx->memo.p + (size_t)nkeys * 16, nkeys, st));
             ++launches;
             ctx->memo_k = k;
             ctx->memo_m = m;
             ctx->memo_type = kmer_type;
             ctx->memo_hash = hash_kind;
         }
-        P.memo = ctx->memo.p;
+        P.memo_fast = ctx->memo.p;
+        P.memo_state = (uint8_t*)ctx->memo.p + (size_t)nkeys * 16;
     }
 
     auto run_class = [&](const LaunchClass& c, const uint32_t* order, int counter_idx) -> int32_t {
@@ -776,7 +790,8 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         uint64_t teams_needed = c.count;
         uint64_t ctas_needed = (teams_needed + g.teams_per_cta - 1) / g.teams_per_cta;
         // CTAs per SM that fit (threads and shared memory)
-        uint32_t per_sm = (uint32_t)std::min<uint64_t>(2048 / g.block, SMEM_BUDGET / std::max<size_t>(g.smem, 1));
+        uint32_t per_sm = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(2048 / g.block, 65536 / (64 * (uint64_t)g.block)),
+                                                       SMEM_BUDGET / std::max<size_t>(g.smem, 1));
         if (per_sm == 0) per_sm = 1;
         if (per_sm > 8) per_sm = 8;
         int grid = (int)std::min<uint64_t>(ctas_needed, (uint64_t)ctx->sm_count * per_sm);
@@ -789,6 +804,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         Q.team_smem_bytes = g.team_smem_bytes;
         Q.regionA_bytes = g.regionA_bytes;
         Q.slots_smem_bytes = g.slots_smem_bytes;
+        Q.stage_bytes = g.stage_bytes;
         Q.slot_scratch = nullptr;
         Q.table_scratch = nullptr;
         Q.table_scratch_entries = 0;
@@ -897,6 +913,8 @@ int32_t kmu_sketch_pmh3a(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_
     if (b->nseq == 0) return KMU_OK;
     if (!sig) return fail(KMU_EINVAL, "null signature buffer");
     if (b->nseq >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "more than 2^32-1 sequences in one batch");
+    for (uint64_t L : b->h_nbases)
+        if (L >= 0xFFFFFF00ull) return fail(KMU_EINVAL, "a single sequence is limited to 2^32 - 256 bases");
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};

@@ -218,6 +218,37 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
 }
 __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) { return ~warp_max_u64(~v); }
 
+// ----------------------------------------------------------------------------
+//  TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier: stages the packed bytes of
+//  the next sequence into shared memory while the current one is processed.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_bytes(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    // dst, src 16-byte aligned; bytes a multiple of 16
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "KMU_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra KMU_DONE;\n\t"
+        "bra KMU_WAIT;\n\t"
+        "KMU_DONE:\n\t}" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // counter based SplitMix64 used by the synthetic generator
 __host__ __device__ __forceinline__ uint64_t synth_z(uint64_t seed, uint64_t i) {
     uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ULL;
@@ -245,7 +276,7 @@ struct KmerWalker {
 
     __device__ __forceinline__ void refill() {
         if (nb <= 32) {
-            sr |= (uint64_t)be32(__ldg(wp)) << (32 - nb);
+            sr |= (uint64_t)be32(*wp) << (32 - nb);
             ++wp;
             nb += 32;
         }
@@ -264,7 +295,7 @@ struct KmerWalker {
         rc_shift = 2 * k - 2;
         wp = words + (p0 >> 4);
         uint32_t o = (uint32_t)(p0 & 15);
-        sr = (uint64_t)be32(__ldg(wp)) << (32 + 2 * o);
+        sr = (uint64_t)be32(*wp) << (32 + 2 * o);
         ++wp;
         nb = 32 - 2 * o;
         refill();
@@ -305,7 +336,7 @@ struct TaskKmers<uint32_t> {
     uint32_t mask, sh0, j0;
     __device__ __forceinline__ void init(const uint32_t* words, uint64_t p0, uint32_t k) {
         const uint32_t* w = words + (p0 >> 4);
-        uint32_t w0 = be32(__ldg(w)), w1 = be32(__ldg(w + 1));
+        uint32_t w0 = be32(w[0]), w1 = be32(w[1]);
         W = ((uint64_t)w0 << 32) | w1;
         RC = revcomp_word64(W);
         mask = value_mask<uint32_t>(2 * k);

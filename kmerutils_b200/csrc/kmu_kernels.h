@@ -49,11 +49,18 @@ struct Pmh3aParams {
     uint64_t table_scratch_entries;
     unsigned long long* overflow_count;
     uint32_t* overflow_list;
-    // first point of every pre-key {x bits lo, x bits hi, slot, 0}, or nullptr (key space too large)
-    const void* memo;
+    // per pre-key tables (u32 key types with a small key space), or nullptr:
+    //   memo_fast  : {x bits lo, x bits hi, slot, hashed key} of the first point
+    //   memo_state : Xoshiro256++ state after the first point (32 bytes)
+    const void* memo_fast;
+    const void* memo_state;
+    // TMA staging: bytes per staging buffer (two per team); 0 disables staging
+    uint32_t stage_bytes;
 };
 
-cudaError_t launch_pmh3a_memo(const Pmh3aParams& P, bool key64, void* memo, uint32_t nkeys, cudaStream_t stream);
+constexpr size_t PMH3A_TEAM_SHARED_BYTES = 80;
+
+cudaError_t launch_pmh3a_memo(const Pmh3aParams& P, void* fast, void* state, uint32_t nkeys, cudaStream_t stream);
 size_t pmh3a_qitem_bytes(bool key64);
 size_t pmh3a_entry_bytes(bool key64);
 cudaError_t launch_pmh3a(const Pmh3aParams& P, bool key64, int mode, int grid, int block, size_t smem,

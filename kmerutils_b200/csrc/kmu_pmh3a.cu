@@ -143,6 +143,20 @@ struct QItem {
 
 constexpr int QCAP = 64;  // per-warp queue capacity (power of two, >= 2 * 32)
 
+// per-team bookkeeping in shared memory (double buffered work descriptors + TMA barriers)
+struct __align__(16) TeamShared {
+    uint64_t mbar[2];
+    uint64_t byte_off[2];
+    uint32_t seq[2];
+    uint32_t nbases[2];
+    uint32_t valid[2];
+    uint32_t staged[2];
+    uint32_t qmax_hi;
+    uint32_t flag;
+    uint32_t pad[2];
+};
+static_assert(sizeof(TeamShared) == PMH3A_TEAM_SHARED_BYTES, "TeamShared size");
+
 // Cheap upper bound of the slot maxima (MaxValueTracker's root): only the high words of the
 // h bit patterns are scanned, the bound is (max_hi, 0xFFFFFFFF).  Any stale or loose bound is
 // safe: qmax tests only prune points that cannot win a slot.
@@ -165,8 +179,10 @@ __device__ __forceinline__ double load_qmax(const uint32_t* s_qmax_hi) {
 // Process up to 32 queued distinct items with one warp: every lane owns one item and
 // emits its points i = 1, 2, ... while winv * (i - 1) < qmax
 // (ProbMinHash3a::hash_weigthed_hashmap).
+// With MEMO the first point was already applied by the caller and the generator state
+// after it comes from the per-key table, so the lane starts at i = 2.
 // --------------------------------------------------------------------------------
-template <typename V>
+template <typename V, bool MEMO>
 __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t head, uint32_t n, int lane,
                                               const Pmh3aParams& P, V header, Slot* slots, uint32_t* s_qmax_hi,
                                               uint32_t refresh_period) {
@@ -175,13 +191,24 @@ __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t he
     double winv = 0.0;
     Xoshiro256pp rng;
     rng.s0 = rng.s1 = rng.s2 = rng.s3 = 0;
+    uint32_t i = 1;
     if (act) {
         QItem<V> it = queue[(head + lane) & (QCAP - 1)];
-        key = finalize_key<V>(it.prekey, header, P.hash_kind);
-        rng.seed(nohash_seed(key));
         winv = 1.0 / (double)it.cnt;
+        if (MEMO) {
+            key = (V)__ldg((const uint32_t*)P.memo_fast + 4 * (size_t)it.prekey + 3);
+            const uint4 a = __ldg((const uint4*)P.memo_state + 2 * (size_t)it.prekey);
+            const uint4 b = __ldg((const uint4*)P.memo_state + 2 * (size_t)it.prekey + 1);
+            rng.s0 = ((uint64_t)a.y << 32) | a.x;
+            rng.s1 = ((uint64_t)a.w << 32) | a.z;
+            rng.s2 = ((uint64_t)b.y << 32) | b.x;
+            rng.s3 = ((uint64_t)b.w << 32) | b.z;
+            i = 2;
+        } else {
+            key = finalize_key<V>(it.prekey, header, P.hash_kind);
+            rng.seed(nohash_seed(key));
+        }
     }
-    uint32_t i = 1;
     uint32_t iter = 0;
     double qmax = load_qmax(s_qmax_hi);
     while (__any_sync(0xFFFFFFFFu, act)) {
@@ -210,13 +237,14 @@ __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t he
     }
 }
 
-// MODE 0: direct histogram of 4^k u16 counters (two per u32) ; MODE 1: open-addressing table
-// MEMO : the first point of every possible pre-key (exp01 sample and slot, both functions of
-//        the key only) comes from a table built once per (k, type, hash, m); only items that
-//        need a second point are seeded on the fly.
+// MODE 0: direct histogram of 4^k u8 counters (four per u32) ; MODE 1: open-addressing table
+// MEMO : the first point of every possible pre-key (exp01 sample, slot and hashed key: functions
+//        of the key only) and the generator state after it come from tables built once per
+//        (k, type, hash, m); no item is ever seeded inside this kernel.
 template <typename V, int MODE, bool MEMO>
 __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ double s_winv[64];
     using TO = TableOps<V>;
     using Entry = typename TO::Entry;
 
@@ -233,16 +261,22 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
     uint8_t* regionA = tbase;                                     // histogram or table
     Slot* slots = (Slot*)(tbase + P.regionA_bytes);               // m slots (if in smem)
     QItem<V>* queues = (QItem<V>*)(tbase + P.regionA_bytes + P.slots_smem_bytes);
-    uint32_t* s_misc = (uint32_t*)((uint8_t*)queues + (size_t)P.team_warps * QCAP * sizeof(QItem<V>));
-    uint32_t* s_qmax_hi = s_misc;                                       // u32
-    volatile uint32_t* s_flag = s_misc + 1;                             // u32
-    volatile unsigned long long* s_work = (volatile unsigned long long*)(s_misc + 2);
+    uint8_t* stage0 = (uint8_t*)queues + (size_t)P.team_warps * QCAP * sizeof(QItem<V>);
+    TeamShared* ts = (TeamShared*)(stage0 + 2 * (size_t)P.stage_bytes);
+    uint32_t* s_qmax_hi = &ts->qmax_hi;
     if (P.slots_smem_bytes == 0)
         slots = P.slot_scratch + ((size_t)blockIdx.x * nteams + team.id) * P.m;
     QItem<V>* myq = queues + (size_t)team.warp * QCAP;
 
+    if (threadIdx.x < 64) s_winv[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
     // region A starts clean; both passes leave it clean again
     for (uint32_t j = team.tid; j < P.regionA_bytes / 4; j += team.size) ((uint32_t*)regionA)[j] = 0;
+    if (team.tid == 0) {
+        mbar_init(&ts->mbar[0], 1);
+        mbar_init(&ts->mbar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
 
     const V header = (V)word_header(P.kmer_type, P.k);
     const bool canonical = hash_is_canonical(P.hash_kind);
@@ -252,37 +286,73 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
     if (MODE == 1 && P.table_scratch)
         gtab = (Entry*)P.table_scratch + ((size_t)blockIdx.x * nteams + team.id) * P.table_scratch_entries;
 
+    // fetch a work item into descriptor `d` and start the TMA copy of its packed bytes
+    auto fetch = [&](int d) {
+        if (team.tid == 0) {
+            const unsigned long long w = atomicAdd(P.work_counter, 1ULL);
+            uint32_t valid = w < P.count, staged = 0;
+            if (valid) {
+                const uint32_t seq = P.order[P.first + w];
+                const uint64_t off = P.byte_off[seq];
+                const uint32_t L = (uint32_t)P.nbases[seq];
+                // bytes the walkers may touch: ceil(L/4) plus one look-ahead word, rounded to 16
+                const uint32_t bytes = (((L + 3) >> 2) + 4 + 15) & ~15u;
+                ts->seq[d] = seq;
+                ts->byte_off[d] = off;
+                ts->nbases[d] = L;
+                if (bytes <= P.stage_bytes) {
+                    staged = 1;
+                    mbar_arrive_expect_tx(&ts->mbar[d], bytes);
+                    tma_load_bytes(stage0 + (size_t)d * P.stage_bytes, P.packed + off, bytes, &ts->mbar[d]);
+                }
+            }
+            ts->valid[d] = valid;
+            ts->staged[d] = staged;
+        }
+    };
+
+    uint32_t phase0 = 0, phase1 = 0;
+    int cur = 0;
+    fetch(0);
+    team.sync();
     for (;;) {
-        team.sync();
-        if (team.tid == 0) *s_work = atomicAdd(P.work_counter, 1ULL);
-        team.sync();
-        const unsigned long long w = *s_work;
-        if (w >= P.count) break;
-        const uint32_t seq = P.order[P.first + w];
-        const uint64_t L = P.nbases[seq];
-        const uint32_t* words = (const uint32_t*)(P.packed + P.byte_off[seq]);
-        const uint64_t nk = L >= k ? L - k + 1 : 0;
+        if (!ts->valid[cur]) break;
+        fetch(cur ^ 1);  // prefetch the next sequence while this one is processed
+        const uint32_t seq = ts->seq[cur];
+        const uint32_t L = ts->nbases[cur];
+        const uint32_t* words = (const uint32_t*)(P.packed + ts->byte_off[cur]);
+        if (ts->staged[cur]) {
+            words = (const uint32_t*)(stage0 + (size_t)cur * P.stage_bytes);
+            if (cur == 0) {
+                mbar_wait(&ts->mbar[0], phase0);
+                phase0 ^= 1;
+            } else {
+                mbar_wait(&ts->mbar[1], phase1);
+                phase1 ^= 1;
+            }
+        }
+        const uint32_t nk = L >= k ? L - k + 1 : 0;
 
         for (uint32_t j = team.tid; j < P.m; j += team.size) {
             slots[j].hbits = F64_MAX_BITS;
             slots[j].key = 0;
         }
         if (team.tid == 0) {
-            *s_qmax_hi = (uint32_t)(F64_MAX_BITS >> 32);
-            *s_flag = 0;
+            ts->qmax_hi = (uint32_t)(F64_MAX_BITS >> 32);
+            ts->flag = 0;
         }
         // positions per task: 16 (one word), or 8 / 4 when there are too few words to occupy the team
         uint32_t log2T = 4;
-        if (nk < (uint64_t)team.size * 8) log2T = 2;
-        else if (nk < (uint64_t)team.size * 16) log2T = 3;
+        if (nk < (uint32_t)team.size * 4) log2T = 2;
+        else if (nk < (uint32_t)team.size * 8) log2T = 3;
         const uint32_t T = 1u << log2T;
-        const uint64_t ntasks = (nk + T - 1) >> log2T;
+        const uint32_t ntasks = (nk + T - 1) >> log2T;
 
         // table geometry for this sequence
         Entry* tab = (Entry*)regionA;
         uint32_t log2cap = 0, capmask = 0;
         if (MODE == 1) {
-            uint64_t want = nk * 2 < 64 ? 64 : nk * 2;
+            uint64_t want = nk < 32 ? 64 : (uint64_t)nk * 2;
             log2cap = 64 - __clzll((long long)(want - 1));
             uint64_t cap = 1ULL << log2cap;
             if (cap * sizeof(Entry) > P.regionA_bytes) tab = gtab;  // long sequence: L2 / HBM scratch
@@ -291,19 +361,20 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
         team.sync();
 
         // ---------------- pass 1 : multiplicities ------------------------------------
-        const bool may_wrap = nk > 0xFFFFu;
-        for (uint64_t task = team.tid; task < ntasks; task += team.size) {
+        const bool may_wrap = nk > 0xFFu;
+        for (uint32_t task = team.tid; task < ntasks; task += team.size) {
             TaskKmers<V> tk;
-            uint64_t p = task << log2T;
+            uint32_t p = task << log2T;
             tk.init(words, p, k);
-            for (uint32_t t = 0; t < T && p < nk; ++t, ++p) {
+            const uint32_t pend = min(p + T, nk);
+            for (uint32_t t = 0; p < pend; ++t, ++p) {
                 V pk = tk.get(t, canonical);
                 if (MODE == 0) {
-                    uint32_t sh = ((uint32_t)pk & 1u) * 16;
-                    uint32_t* wp = (uint32_t*)regionA + ((uint32_t)pk >> 1);
+                    uint32_t sh = ((uint32_t)pk & 3u) * 8;
+                    uint32_t* wp = (uint32_t*)regionA + ((uint32_t)pk >> 2);
                     if (may_wrap) {
                         uint32_t old = atomicAdd(wp, 1u << sh);
-                        if (((old >> sh) & 0xFFFFu) == 0xFFFFu) *s_flag = 1;  // u16 counter wrapped
+                        if (((old >> sh) & 0xFFu) == 0xFFu) ts->flag = 1;  // u8 counter wrapped
                     } else {
                         atomicAdd(wp, 1u << sh);  // result unused: RED
                     }
@@ -313,15 +384,15 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
             }
         }
         team.sync();
-        const bool overflow = MODE == 0 && *s_flag != 0;
+        const bool overflow = MODE == 0 && ts->flag != 0;
 
         // ---------------- pass 2 : claim distinct items, sketch them ------------------
         uint32_t qhead = 0, qtail = 0;
-        for (uint64_t tbase_i = (uint64_t)team.warp * 32; tbase_i < ntasks; tbase_i += team.size) {
-            const uint64_t task = tbase_i + team.lane;
+        for (uint32_t tbase_i = (uint32_t)team.warp * 32; tbase_i < ntasks; tbase_i += team.size) {
+            const uint32_t task = tbase_i + team.lane;
             const bool tact = task < ntasks;
             TaskKmers<V> tk;
-            uint64_t p = task << log2T;
+            uint32_t p = task << log2T;
             if (tact) tk.init(words, p, k);
             double qmax = 0.0;
             if (MEMO) {
@@ -334,13 +405,13 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
                 if (tact && p < nk) {
                     pk = tk.get(t, canonical);
                     if (MODE == 0) {
-                        uint32_t sh = ((uint32_t)pk & 1u) * 16;
-                        uint32_t* wp = (uint32_t*)regionA + ((uint32_t)pk >> 1);
+                        uint32_t sh = ((uint32_t)pk & 3u) * 8;
+                        uint32_t* wp = (uint32_t*)regionA + ((uint32_t)pk >> 2);
                         if (overflow) {
                             *wp = 0;
                         } else {
-                            uint32_t old = atomicAnd(wp, ~(0xFFFFu << sh));
-                            cnt = (old >> sh) & 0xFFFFu;
+                            uint32_t old = atomicAnd(wp, ~(0xFFu << sh));
+                            cnt = (old >> sh) & 0xFFu;
                         }
                     } else {
                         cnt = TO::claim(tab, capmask, log2cap, pk);
@@ -348,17 +419,18 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
                 }
                 if (MEMO) {
                     // first point from the per-key table; only items that may need a second
-                    // point (winv < qmax) go to the queue
+                    // point (h < qmax and winv < qmax) go to the queue
                     if (cnt) {
-                        const uint4 e = __ldg((const uint4*)P.memo + (uint32_t)pk);
+                        const uint4 e = __ldg((const uint4*)P.memo_fast + (uint32_t)pk);
                         const double x = __hiloint2double((int)e.y, (int)e.x);
-                        const double winv = cnt == 1 ? 1.0 : 1.0 / (double)cnt;
+                        const double winv = cnt < 64 ? s_winv[cnt] : 1.0 / (double)cnt;
                         const double h = __dmul_rn(winv, x);
                         if (h < qmax) {
-                            const V key = finalize_key<V>(pk, header, P.hash_kind);
-                            slot_update_min(&slots[e.z], (uint64_t)__double_as_longlong(h), (uint64_t)key);
+                            slot_update_min(&slots[e.z], (uint64_t)__double_as_longlong(h), (uint64_t)e.w);
+                            if (!(winv < qmax)) cnt = 0;
+                        } else {
+                            cnt = 0;
                         }
-                        if (!(h < qmax) || !(winv < qmax)) cnt = 0;
                     }
                 }
                 const uint32_t bal = __ballot_sync(0xFFFFFFFFu, cnt != 0);
@@ -373,7 +445,7 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
                     qtail += __popc(bal);
                     __syncwarp();
                     if (qtail - qhead >= 32) {
-                        process_items<V>(myq, qhead, 32, team.lane, P, header, slots, s_qmax_hi, refresh_period);
+                        process_items<V, MEMO>(myq, qhead, 32, team.lane, P, header, slots, s_qmax_hi, refresh_period);
                         qhead += 32;
                         __syncwarp();
                         if (MEMO) qmax = load_qmax(s_qmax_hi);
@@ -382,7 +454,7 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
             }
         }
         if (qtail != qhead)
-            process_items<V>(myq, qhead, qtail - qhead, team.lane, P, header, slots, s_qmax_hi, refresh_period);
+            process_items<V, MEMO>(myq, qhead, qtail - qhead, team.lane, P, header, slots, s_qmax_hi, refresh_period);
         team.sync();
 
         // ---------------- signature out, leave region A clean --------------------------
@@ -396,15 +468,18 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
             for (uint32_t j = team.tid; j < P.m; j += team.size) out[j] = (V)slots[j].key;
         }
         if (MODE == 1) {
-            const uint64_t nvec = ((uint64_t)capmask + 1) * (sizeof(Entry) / 8) / 2;  // 16-byte vectors
-            for (uint64_t j = team.tid; j < nvec; j += team.size) ((uint4*)tab)[j] = make_uint4(0, 0, 0, 0);
+            const uint32_t nvec = (capmask + 1) / (16 / sizeof(Entry));  // 16-byte vectors
+            for (uint32_t j = team.tid; j < nvec; j += team.size) ((uint4*)tab)[j] = make_uint4(0, 0, 0, 0);
         }
+        cur ^= 1;
+        team.sync();  // descriptor `cur` was written before the passes; staging buffer cur^1 is free again
     }
 }
 
-// first point of every pre-key: {x bits lo, x bits hi, slot, 0}
+// per pre-key tables: fast = {x bits lo, x bits hi, slot, hashed key}; state = Xoshiro256++ state
+// after the first point (4 x u64)
 template <typename V>
-__global__ void pmh3a_memo_kernel(uint4* memo, uint32_t nkeys, Pmh3aParams P) {
+__global__ void pmh3a_memo_kernel(uint4* fast, uint4* state, uint32_t nkeys, Pmh3aParams P) {
     const V header = (V)word_header(P.kmer_type, P.k);
     for (uint32_t pk = blockIdx.x * blockDim.x + threadIdx.x; pk < nkeys; pk += gridDim.x * blockDim.x) {
         V key = finalize_key<V>((V)pk, header, P.hash_kind);
@@ -412,18 +487,17 @@ __global__ void pmh3a_memo_kernel(uint4* memo, uint32_t nkeys, Pmh3aParams P) {
         rng.seed(nohash_seed(key));
         double x = exp01_sample(P.e, rng);
         uint32_t s = rng.unif_range(0, P.m, P.slot_thresh);
-        memo[pk] = make_uint4((uint32_t)__double2loint(x), (uint32_t)__double2hiint(x), s, 0u);
+        fast[pk] = make_uint4((uint32_t)__double2loint(x), (uint32_t)__double2hiint(x), s, (uint32_t)key);
+        state[2 * (size_t)pk] = make_uint4((uint32_t)rng.s0, (uint32_t)(rng.s0 >> 32), (uint32_t)rng.s1, (uint32_t)(rng.s1 >> 32));
+        state[2 * (size_t)pk + 1] = make_uint4((uint32_t)rng.s2, (uint32_t)(rng.s2 >> 32), (uint32_t)rng.s3, (uint32_t)(rng.s3 >> 32));
     }
 }
 
-cudaError_t launch_pmh3a_memo(const Pmh3aParams& P, bool key64, void* memo, uint32_t nkeys, cudaStream_t stream) {
+cudaError_t launch_pmh3a_memo(const Pmh3aParams& P, void* fast, void* state, uint32_t nkeys, cudaStream_t stream) {
     int block = 256;
     int grid = (int)((nkeys + block - 1) / block);
     if (grid > 148 * 8) grid = 148 * 8;
-    if (key64)
-        pmh3a_memo_kernel<uint64_t><<<grid, block, 0, stream>>>((uint4*)memo, nkeys, P);
-    else
-        pmh3a_memo_kernel<uint32_t><<<grid, block, 0, stream>>>((uint4*)memo, nkeys, P);
+    pmh3a_memo_kernel<uint32_t><<<grid, block, 0, stream>>>((uint4*)fast, (uint4*)state, nkeys, P);
     return cudaGetLastError();
 }
 
@@ -450,11 +524,8 @@ size_t pmh3a_entry_bytes(bool key64) {
 
 cudaError_t launch_pmh3a(const Pmh3aParams& P, bool key64, int mode, int grid, int block, size_t smem,
                          cudaStream_t stream) {
-    const bool memo = P.memo != nullptr;
+    const bool memo = P.memo_fast != nullptr && !key64;
     if (key64) {
-        if (memo)
-            return mode == 0 ? launch_one<uint64_t, 0, true>(P, grid, block, smem, stream)
-                             : launch_one<uint64_t, 1, true>(P, grid, block, smem, stream);
         return mode == 0 ? launch_one<uint64_t, 0, false>(P, grid, block, smem, stream)
                          : launch_one<uint64_t, 1, false>(P, grid, block, smem, stream);
     }
