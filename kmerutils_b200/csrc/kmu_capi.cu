@@ -630,19 +630,19 @@ Geometry make_geometry(uint64_t nk_max, int mode, uint32_t k, uint32_t m, bool k
             regionA = 16;
         }
     }
-    const uint64_t slots = (uint64_t)m * 16;
+    const uint64_t slots = align_up((uint64_t)m * 20, 16);  // 16-byte records + u32 mirror of the high words
     // TMA staging buffers: two per team, each large enough for the longest sequence of the
     // launch up to 16 KB (64 k bases); longer sequences are read from global memory
-    const uint64_t stage = std::min<uint64_t>(16 * 1024, align_up(nk_max / 4 + k + 32, 16));
+    const uint64_t stage = std::min<uint64_t>(16 * 1024, align_up(nk_max / 4 + k + 32, 32));
     g.stage_bytes = (uint32_t)stage;
     if (tw == 32) {
         // two 16-warp teams keep more sequences in flight than one 32-warp team, if both fit
-        const uint64_t fixed16 = regionA + 16ull * 64 * qitem + 2 * stage + kmu::PMH3A_TEAM_SHARED_BYTES;
+        const uint64_t fixed16 = regionA + 16ull * 64 * qitem + 2 * stage + stage / 2 + kmu::PMH3A_TEAM_SHARED_BYTES;
         const uint64_t team16 = align_up(fixed16 + slots <= SMEM_BUDGET ? fixed16 + slots : fixed16, 16);
         if (2 * team16 <= SMEM_BUDGET) tw = 16;
     }
     for (;;) {
-        const uint64_t fixed = regionA + (uint64_t)tw * 64 * qitem + 2 * stage + kmu::PMH3A_TEAM_SHARED_BYTES;
+        const uint64_t fixed = regionA + (uint64_t)tw * 64 * qitem + 2 * stage + stage / 2 + kmu::PMH3A_TEAM_SHARED_BYTES;
         const bool slots_in_smem = fixed + slots <= SMEM_BUDGET;
         const uint64_t team_bytes = align_up(slots_in_smem ? fixed + slots : fixed, 16);
         const uint32_t teams_fit = std::max<uint32_t>(1, (uint32_t)(SMEM_BUDGET / team_bytes));
@@ -810,7 +810,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         Q.table_scratch_entries = 0;
         const uint64_t nteams_total = (uint64_t)grid * g.teams_per_cta;
         if (g.slots_smem_bytes == 0) {
-            CUDA_TRY(ctx->slot_scratch.reserve(nteams_total * m * sizeof(kmu::Slot)));
+            CUDA_TRY(ctx->slot_scratch.reserve(nteams_total * m * 20));
             Q.slot_scratch = (kmu::Slot*)ctx->slot_scratch.p;
         }
         if (g.table_entries_global) {

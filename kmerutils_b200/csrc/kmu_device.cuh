@@ -194,15 +194,16 @@ __device__ __forceinline__ void cas128(Slot* addr, uint64_t cmp_h, uint64_t cmp_
         : "memory");
 }
 
-__device__ __forceinline__ void slot_update_min(Slot* slot, uint64_t hbits, uint64_t key) {
+// returns true when the record was replaced
+__device__ __forceinline__ bool slot_update_min(Slot* slot, uint64_t hbits, uint64_t key) {
     uint64_t cur_h = *(volatile uint64_t*)&slot->hbits;
-    if (hbits > cur_h) return;
+    if (hbits > cur_h) return false;
     uint64_t cur_k = *(volatile uint64_t*)&slot->key;
     for (;;) {
-        if (hbits > cur_h || (hbits == cur_h && key >= cur_k)) return;
+        if (hbits > cur_h || (hbits == cur_h && key >= cur_k)) return false;
         uint64_t old_h, old_k;
         cas128(slot, cur_h, cur_k, hbits, key, old_h, old_k);
-        if (old_h == cur_h && old_k == cur_k) return;
+        if (old_h == cur_h && old_k == cur_k) return true;
         cur_h = old_h;
         cur_k = old_k;
     }

@@ -52,6 +52,7 @@ struct Team {
 // ---- multiplicity stores -----------------------------------------------------------
 // u32 pre-keys: one u64 per entry = key << 32 | claimed << 31 | count ; 0 == empty
 // u64 pre-keys: 16-byte entry {key, claimed << 63 | count} ; count == 0 == empty
+// insert() tells whether this call created the entry (first occurrence of the key).
 template <typename V>
 struct TableOps;
 
@@ -61,19 +62,29 @@ struct TableOps<uint32_t> {
     static __device__ __forceinline__ uint32_t slot_of(uint32_t key, uint32_t log2cap) {
         return (key * 0x9E3779B1u) >> (32 - log2cap);
     }
-    static __device__ __forceinline__ void insert(Entry* tab, uint32_t capmask, uint32_t log2cap, uint32_t key) {
+    static __device__ __forceinline__ bool insert(Entry* tab, uint32_t capmask, uint32_t log2cap, uint32_t key) {
         uint32_t i = slot_of(key, log2cap);
         for (;;) {
             Entry e = *(volatile Entry*)(tab + i);
             if (e == 0) {
                 Entry old = atomicCAS(tab + i, 0ULL, ((Entry)key << 32) | 1ULL);
-                if (old == 0) return;
+                if (old == 0) return true;
                 e = old;
             }
             if ((uint32_t)(e >> 32) == key) {
                 atomicAdd(tab + i, 1ULL);
-                return;
+                return false;
             }
+            i = (i + 1) & capmask;
+        }
+    }
+    // multiplicity of a key that is in the table (plain loads; after the pass-1 barrier)
+    static __device__ __forceinline__ uint32_t lookup(const Entry* tab, uint32_t capmask, uint32_t log2cap, uint32_t key) {
+        uint32_t i = slot_of(key, log2cap);
+        for (;;) {
+            Entry e = *(volatile const Entry*)(tab + i);
+            if (e == 0) return 0;
+            if ((uint32_t)(e >> 32) == key) return (uint32_t)e & 0x7FFFFFFFu;
             i = (i + 1) & capmask;
         }
     }
@@ -102,20 +113,29 @@ struct TableOps<uint64_t> {
     static __device__ __forceinline__ uint32_t slot_of(uint64_t key, uint32_t log2cap) {
         return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - log2cap));
     }
-    static __device__ __forceinline__ void insert(Entry* tab, uint32_t capmask, uint32_t log2cap, uint64_t key) {
+    static __device__ __forceinline__ bool insert(Entry* tab, uint32_t capmask, uint32_t log2cap, uint64_t key) {
         uint32_t i = slot_of(key, log2cap);
         for (;;) {
             unsigned long long c = *(volatile unsigned long long*)&tab[i].cnt;
             if (c == 0) {
                 uint64_t oh, ok;
                 cas128((Slot*)(tab + i), 0, 0, key, 1, oh, ok);
-                if (oh == 0 && ok == 0) return;
+                if (oh == 0 && ok == 0) return true;
             }
             unsigned long long kk = *(volatile unsigned long long*)&tab[i].key;
             if (kk == key) {
                 atomicAdd(&tab[i].cnt, 1ULL);
-                return;
+                return false;
             }
+            i = (i + 1) & capmask;
+        }
+    }
+    static __device__ __forceinline__ uint32_t lookup(const Entry* tab, uint32_t capmask, uint32_t log2cap, uint64_t key) {
+        uint32_t i = slot_of(key, log2cap);
+        for (;;) {
+            unsigned long long c = *(volatile const unsigned long long*)&tab[i].cnt;
+            if (c == 0) return 0;
+            if (*(volatile const unsigned long long*)&tab[i].key == key) return (uint32_t)(c & 0x7FFFFFFFULL);
             i = (i + 1) & capmask;
         }
     }
@@ -153,26 +173,37 @@ struct __align__(16) TeamShared {
     uint32_t staged[2];
     uint32_t qmax_hi;
     uint32_t flag;
-    uint32_t pad[2];
+    uint32_t next_task[2];  // dynamic task counters of pass 1 / pass 2
 };
 static_assert(sizeof(TeamShared) == PMH3A_TEAM_SHARED_BYTES, "TeamShared size");
 
-// Cheap upper bound of the slot maxima (MaxValueTracker's root): only the high words of the
-// h bit patterns are scanned, the bound is (max_hi, 0xFFFFFFFF).  Any stale or loose bound is
+// Sketch state of one team: the 16-byte slots and a mirror of the high words of their h values.
+struct SlotArray {
+    Slot* slots;
+    uint32_t* hi;  // hi[j] >= high word of slots[j].hbits at any time (stale values are larger)
+    uint32_t* s_qmax_hi;
+};
+
+// Cheap upper bound of the slot maxima (MaxValueTracker's root): only the mirrored high words
+// are scanned (conflict-free), the bound is (max_hi, 0xFFFFFFFF).  Any stale or loose bound is
 // safe: qmax tests only prune points that cannot win a slot.
-__device__ __forceinline__ void refresh_qmax(const Slot* slots, uint32_t m, int lane, uint32_t* s_qmax_hi) {
+__device__ __forceinline__ void refresh_qmax(const SlotArray& S, uint32_t m, int lane) {
     uint32_t mx = 0;
     for (uint32_t j = lane; j < m; j += 32) {
-        uint32_t hi = *((volatile const uint32_t*)&slots[j].hbits + 1);
+        uint32_t hi = *(volatile const uint32_t*)(S.hi + j);
         mx = hi > mx ? hi : mx;
     }
     mx = __reduce_max_sync(0xFFFFFFFFu, mx);
-    if (lane == 0 && mx < *(volatile uint32_t*)s_qmax_hi) atomicMin(s_qmax_hi, mx);
+    if (lane == 0 && mx < *(volatile uint32_t*)S.s_qmax_hi) atomicMin(S.s_qmax_hi, mx);
     __syncwarp();
 }
-__device__ __forceinline__ double load_qmax(const uint32_t* s_qmax_hi) {
-    uint32_t hi = *(volatile const uint32_t*)s_qmax_hi;
+__device__ __forceinline__ double load_qmax(const SlotArray& S) {
+    uint32_t hi = *(volatile const uint32_t*)S.s_qmax_hi;
     return __hiloint2double((int)hi, (int)0xFFFFFFFFu);
+}
+__device__ __forceinline__ void sketch_update(const SlotArray& S, uint32_t s, double h, uint64_t key) {
+    const uint64_t hbits = (uint64_t)__double_as_longlong(h);
+    if (slot_update_min(&S.slots[s], hbits, key)) *(volatile uint32_t*)(S.hi + s) = (uint32_t)(hbits >> 32);
 }
 
 // --------------------------------------------------------------------------------
@@ -184,7 +215,7 @@ __device__ __forceinline__ double load_qmax(const uint32_t* s_qmax_hi) {
 // --------------------------------------------------------------------------------
 template <typename V, bool MEMO>
 __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t head, uint32_t n, int lane,
-                                              const Pmh3aParams& P, V header, Slot* slots, uint32_t* s_qmax_hi,
+                                              const Pmh3aParams& P, V header, const SlotArray& S,
                                               uint32_t refresh_period) {
     bool act = (uint32_t)lane < n;
     V key = 0;
@@ -210,11 +241,11 @@ __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t he
         }
     }
     uint32_t iter = 0;
-    double qmax = load_qmax(s_qmax_hi);
+    double qmax = load_qmax(S);
     while (__any_sync(0xFFFFFFFFu, act)) {
         if (iter % refresh_period == refresh_period - 1) {
-            refresh_qmax(slots, P.m, lane, s_qmax_hi);
-            qmax = load_qmax(s_qmax_hi);
+            refresh_qmax(S, P.m, lane);
+            qmax = load_qmax(S);
         }
         ++iter;
         if (act) {
@@ -228,7 +259,7 @@ __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t he
                     act = false;  // first point already above every slot: the item is dead
                 } else {
                     uint32_t s = rng.unif_range(0, P.m, P.slot_thresh);
-                    slot_update_min(&slots[s], (uint64_t)__double_as_longlong(h), (uint64_t)key);
+                    sketch_update(S, s, h, (uint64_t)key);
                     ++i;
                     if (!(__dmul_rn(winv, (double)(i - 1)) < qmax)) act = false;
                 }
@@ -257,15 +288,22 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
     const int nteams = blockDim.x / team.size;
 
     // ---- carve the team's shared memory ------------------------------------------
+    // [region A: histogram / table][slots 16 m][slot hi mirror 4 m][queues][stage 0][stage 1][masks][TeamShared]
     uint8_t* tbase = smem + (size_t)team.id * P.team_smem_bytes;
-    uint8_t* regionA = tbase;                                     // histogram or table
-    Slot* slots = (Slot*)(tbase + P.regionA_bytes);               // m slots (if in smem)
+    uint8_t* regionA = tbase;
+    SlotArray S;
+    S.slots = (Slot*)(tbase + P.regionA_bytes);
+    S.hi = (uint32_t*)(tbase + P.regionA_bytes + (size_t)P.m * 16);
     QItem<V>* queues = (QItem<V>*)(tbase + P.regionA_bytes + P.slots_smem_bytes);
     uint8_t* stage0 = (uint8_t*)queues + (size_t)P.team_warps * QCAP * sizeof(QItem<V>);
-    TeamShared* ts = (TeamShared*)(stage0 + 2 * (size_t)P.stage_bytes);
-    uint32_t* s_qmax_hi = &ts->qmax_hi;
-    if (P.slots_smem_bytes == 0)
-        slots = P.slot_scratch + ((size_t)blockIdx.x * nteams + team.id) * P.m;
+    uint8_t* masks = stage0 + 2 * (size_t)P.stage_bytes;
+    TeamShared* ts = (TeamShared*)(masks + P.stage_bytes / 2);
+    S.s_qmax_hi = &ts->qmax_hi;
+    if (P.slots_smem_bytes == 0) {
+        uint8_t* g = (uint8_t*)P.slot_scratch + ((size_t)blockIdx.x * nteams + team.id) * ((size_t)P.m * 20);
+        S.slots = (Slot*)g;
+        S.hi = (uint32_t*)(g + (size_t)P.m * 16);
+    }
     QItem<V>* myq = queues + (size_t)team.warp * QCAP;
 
     if (threadIdx.x < 64) s_winv[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
@@ -281,7 +319,7 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
     const V header = (V)word_header(P.kmer_type, P.k);
     const bool canonical = hash_is_canonical(P.hash_kind);
     const uint32_t k = P.k;
-    const uint32_t refresh_period = P.m <= 512 ? 1u : P.m / 512;
+    const uint32_t refresh_period = P.m <= 2048 ? 1u : P.m / 2048;
     Entry* gtab = nullptr;
     if (MODE == 1 && P.table_scratch)
         gtab = (Entry*)P.table_scratch + ((size_t)blockIdx.x * nteams + team.id) * P.table_scratch_entries;
@@ -310,6 +348,12 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
             ts->staged[d] = staged;
         }
     };
+    // next block of 32 tasks of pass `which` for this warp
+    auto next_tasks = [&](int which) -> uint32_t {
+        uint32_t base = 0;
+        if (team.lane == 0) base = atomicAdd(&ts->next_task[which], 32u);
+        return __shfl_sync(0xFFFFFFFFu, base, 0);
+    };
 
     uint32_t phase0 = 0, phase1 = 0;
     int cur = 0;
@@ -321,7 +365,9 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
         const uint32_t seq = ts->seq[cur];
         const uint32_t L = ts->nbases[cur];
         const uint32_t* words = (const uint32_t*)(P.packed + ts->byte_off[cur]);
-        if (ts->staged[cur]) {
+        // sequences that fit the staging buffer also fit the first-occurrence masks
+        const bool use_masks = ts->staged[cur] != 0;
+        if (use_masks) {
             words = (const uint32_t*)(stage0 + (size_t)cur * P.stage_bytes);
             if (cur == 0) {
                 mbar_wait(&ts->mbar[0], phase0);
@@ -334,17 +380,18 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
         const uint32_t nk = L >= k ? L - k + 1 : 0;
 
         for (uint32_t j = team.tid; j < P.m; j += team.size) {
-            slots[j].hbits = F64_MAX_BITS;
-            slots[j].key = 0;
+            S.slots[j].hbits = F64_MAX_BITS;
+            S.slots[j].key = 0;
+            S.hi[j] = (uint32_t)(F64_MAX_BITS >> 32);
         }
         if (team.tid == 0) {
             ts->qmax_hi = (uint32_t)(F64_MAX_BITS >> 32);
             ts->flag = 0;
+            ts->next_task[0] = 0;
+            ts->next_task[1] = 0;
         }
-        // positions per task: 16 (one word), or 8 / 4 when there are too few words to occupy the team
-        uint32_t log2T = 4;
-        if (nk < (uint32_t)team.size * 4) log2T = 2;
-        else if (nk < (uint32_t)team.size * 8) log2T = 3;
+        // positions per task: 16 (one word), or 8 when there are too few words to occupy the team
+        const uint32_t log2T = nk < (uint32_t)team.size * 16 ? 3 : 4;
         const uint32_t T = 1u << log2T;
         const uint32_t ntasks = (nk + T - 1) >> log2T;
 
@@ -360,61 +407,76 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
         }
         team.sync();
 
-        // ---------------- pass 1 : multiplicities ------------------------------------
+        // ---------------- pass 1 : multiplicities + first-occurrence masks -------------------
         const bool may_wrap = nk > 0xFFu;
-        for (uint32_t task = team.tid; task < ntasks; task += team.size) {
-            TaskKmers<V> tk;
-            uint32_t p = task << log2T;
-            tk.init(words, p, k);
-            const uint32_t pend = min(p + T, nk);
-            for (uint32_t t = 0; p < pend; ++t, ++p) {
-                V pk = tk.get(t, canonical);
-                if (MODE == 0) {
-                    uint32_t sh = ((uint32_t)pk & 3u) * 8;
-                    uint32_t* wp = (uint32_t*)regionA + ((uint32_t)pk >> 2);
-                    if (may_wrap) {
-                        uint32_t old = atomicAdd(wp, 1u << sh);
-                        if (((old >> sh) & 0xFFu) == 0xFFu) ts->flag = 1;  // u8 counter wrapped
+        for (;;) {
+            const uint32_t task = next_tasks(0) + team.lane;
+            if (task - team.lane >= ntasks) break;
+            if (task < ntasks) {
+                TaskKmers<V> tk;
+                uint32_t p = task << log2T;
+                tk.init(words, p, k);
+                const uint32_t pend = min(p + T, nk);
+                uint32_t first = 0;
+                for (uint32_t t = 0; p < pend; ++t, ++p) {
+                    V pk = tk.get(t, canonical);
+                    if (MODE == 0) {
+                        const uint32_t sh = ((uint32_t)pk & 3u) * 8;
+                        const uint32_t old = atomicAdd((uint32_t*)regionA + ((uint32_t)pk >> 2), 1u << sh);
+                        const uint32_t c = (old >> sh) & 0xFFu;
+                        first |= (uint32_t)(c == 0) << t;
+                        if (may_wrap && c == 0xFFu) ts->flag = 1;  // u8 counter wrapped
                     } else {
-                        atomicAdd(wp, 1u << sh);  // result unused: RED
+                        first |= (uint32_t)TO::insert(tab, capmask, log2cap, pk) << t;
                     }
-                } else {
-                    TO::insert(tab, capmask, log2cap, pk);
+                }
+                if (use_masks) {
+                    if (log2T == 4) ((uint16_t*)masks)[task] = (uint16_t)first;
+                    else masks[task] = (uint8_t)first;
                 }
             }
         }
         team.sync();
         const bool overflow = MODE == 0 && ts->flag != 0;
 
-        // ---------------- pass 2 : claim distinct items, sketch them ------------------
+        // ---------------- pass 2 : owners sketch their distinct items -------------------------
         uint32_t qhead = 0, qtail = 0;
-        for (uint32_t tbase_i = (uint32_t)team.warp * 32; tbase_i < ntasks; tbase_i += team.size) {
-            const uint32_t task = tbase_i + team.lane;
+        for (;;) {
+            const uint32_t task = next_tasks(1) + team.lane;
+            if (task - team.lane >= ntasks) break;
             const bool tact = task < ntasks;
             TaskKmers<V> tk;
             uint32_t p = task << log2T;
-            if (tact) tk.init(words, p, k);
+            uint32_t own = 0xFFFFu;
+            if (tact) {
+                tk.init(words, p, k);
+                if (use_masks) own = log2T == 4 ? (uint32_t)((const uint16_t*)masks)[task] : (uint32_t)masks[task];
+            }
             double qmax = 0.0;
             if (MEMO) {
-                refresh_qmax(slots, P.m, team.lane, s_qmax_hi);
-                qmax = load_qmax(s_qmax_hi);
+                refresh_qmax(S, P.m, team.lane);
+                qmax = load_qmax(S);
             }
             for (uint32_t t = 0; t < T; ++t, ++p) {
                 uint32_t cnt = 0;
                 V pk = 0;
-                if (tact && p < nk) {
-                    pk = tk.get(t, canonical);
+                const bool in_range = tact && p < nk;
+                const bool mine = in_range && ((own >> t) & 1u);
+                if (sizeof(V) == 8 ? in_range : mine) pk = tk.get(t, canonical);  // the u64 walker must roll every position
+                if (mine) {
                     if (MODE == 0) {
-                        uint32_t sh = ((uint32_t)pk & 3u) * 8;
-                        uint32_t* wp = (uint32_t*)regionA + ((uint32_t)pk >> 2);
                         if (overflow) {
-                            *wp = 0;
+                            ((uint32_t*)regionA)[(uint32_t)pk >> 2] = 0;
+                        } else if (use_masks) {
+                            cnt = regionA[(uint32_t)pk];
+                            regionA[(uint32_t)pk] = 0;
                         } else {
-                            uint32_t old = atomicAnd(wp, ~(0xFFu << sh));
+                            const uint32_t sh = ((uint32_t)pk & 3u) * 8;
+                            const uint32_t old = atomicAnd((uint32_t*)regionA + ((uint32_t)pk >> 2), ~(0xFFu << sh));
                             cnt = (old >> sh) & 0xFFu;
                         }
                     } else {
-                        cnt = TO::claim(tab, capmask, log2cap, pk);
+                        cnt = use_masks ? TO::lookup(tab, capmask, log2cap, pk) : TO::claim(tab, capmask, log2cap, pk);
                     }
                 }
                 if (MEMO) {
@@ -426,7 +488,7 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
                         const double winv = cnt < 64 ? s_winv[cnt] : 1.0 / (double)cnt;
                         const double h = __dmul_rn(winv, x);
                         if (h < qmax) {
-                            slot_update_min(&slots[e.z], (uint64_t)__double_as_longlong(h), (uint64_t)e.w);
+                            sketch_update(S, e.z, h, (uint64_t)e.w);
                             if (!(winv < qmax)) cnt = 0;
                         } else {
                             cnt = 0;
@@ -445,16 +507,15 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
                     qtail += __popc(bal);
                     __syncwarp();
                     if (qtail - qhead >= 32) {
-                        process_items<V, MEMO>(myq, qhead, 32, team.lane, P, header, slots, s_qmax_hi, refresh_period);
+                        process_items<V, MEMO>(myq, qhead, 32, team.lane, P, header, S, refresh_period);
                         qhead += 32;
                         __syncwarp();
-                        if (MEMO) qmax = load_qmax(s_qmax_hi);
+                        if (MEMO) qmax = load_qmax(S);
                     }
                 }
             }
         }
-        if (qtail != qhead)
-            process_items<V, MEMO>(myq, qhead, qtail - qhead, team.lane, P, header, slots, s_qmax_hi, refresh_period);
+        if (qtail != qhead) process_items<V, MEMO>(myq, qhead, qtail - qhead, team.lane, P, header, S, refresh_period);
         team.sync();
 
         // ---------------- signature out, leave region A clean --------------------------
@@ -465,7 +526,7 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
             }
         } else {
             V* out = (V*)P.sig + (size_t)seq * P.m;
-            for (uint32_t j = team.tid; j < P.m; j += team.size) out[j] = (V)slots[j].key;
+            for (uint32_t j = team.tid; j < P.m; j += team.size) out[j] = (V)S.slots[j].key;
         }
         if (MODE == 1) {
             const uint32_t nvec = (capmask + 1) / (16 / sizeof(Entry));  // 16-byte vectors
