@@ -160,6 +160,9 @@ typedef struct kmu_launch_rec {
     uint64_t nbases;        /* bases handled by the launch */
     uint64_t nk_max;        /* largest k-mer count the launch was sized for */
     float ms;               /* device time of the launch */
+    uint32_t counter_idx;
+    /* SM clocks summed over teams: [0] fetch/wait/init [1] pass 1 [2] fill [3] pass 2 [4] output */
+    uint64_t phase_clocks[8];
 } kmu_launch_rec;
 int32_t kmu_ctx_set_profiling(kmu_ctx* ctx, int32_t on);
 /* returns the number of launches of the last sketch call; fills at most cap records */

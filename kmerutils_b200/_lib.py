@@ -29,7 +29,7 @@ class KmuLaunchRec(C.Structure):
     _fields_ = [("mode", C.c_int32), ("table_global", C.c_int32), ("team_warps", C.c_uint32),
                 ("teams_per_cta", C.c_uint32), ("grid", C.c_uint32), ("block", C.c_uint32),
                 ("smem_bytes", C.c_uint32), ("nseq", C.c_uint64), ("nbases", C.c_uint64), ("nk_max", C.c_uint64),
-                ("ms", C.c_float)]
+                ("ms", C.c_float), ("counter_idx", C.c_uint32), ("phase_clocks", C.c_uint64 * 8)]
 
 
 class KmuError(RuntimeError):

@@ -275,8 +275,14 @@ uint32_t kmu_last_launch_profile(kmu_ctx* ctx, kmu_launch_rec* out, uint32_t cap
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);
     uint32_t n = (uint32_t)ctx->lrec.size();
-    for (uint32_t i = 0; i < n; ++i)
+    std::vector<unsigned long long> ph(8 * 128, 0);
+    if (ctx->counters.p)
+        cudaMemcpy(ph.data(), (unsigned long long*)ctx->counters.p + 2 * kmu::LEN_BUCKETS + 256, sizeof(unsigned long long) * 8 * 128,
+                   cudaMemcpyDeviceToHost);
+    for (uint32_t i = 0; i < n; ++i) {
         if (2 * i + 1 < ctx->lev.size()) cudaEventElapsedTime(&ctx->lrec[i].ms, ctx->lev[2 * i], ctx->lev[2 * i + 1]);
+        for (int j = 0; j < 8; ++j) ctx->lrec[i].phase_clocks[j] = ph[8 * (ctx->lrec[i].counter_idx & 127) + j];
+    }
     if (out)
         for (uint32_t i = 0; i < n && i < cap; ++i) out[i] = ctx->lrec[i];
     return n;
@@ -678,12 +684,13 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
 
     // ---- order sequences longest first (8 buckets per octave of the k-mer count) -------
     CUDA_TRY(ctx->order.reserve(sizeof(uint32_t) * (nseq + 1)));
-    CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256)));
+    CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256 + 8 * 128)));
     unsigned long long* d_hist = (unsigned long long*)ctx->counters.p;
     unsigned long long* d_cursor = d_hist + kmu::LEN_BUCKETS;
     unsigned long long* d_work = d_cursor + kmu::LEN_BUCKETS;  // 128 work counters
     unsigned long long* d_ovf_count = d_work + 128;
-    CUDA_TRY(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256), st));
+    unsigned long long* d_phase = d_work + 256;  // 8 per launch, profiling only
+    CUDA_TRY(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256 + 8 * 128), st));
     CUDA_TRY(kmu::launch_len_hist(b->nbases, nseq, k, d_hist, st));
     ++launches;
     std::vector<unsigned long long> hist(kmu::LEN_BUCKETS), cursor(kmu::LEN_BUCKETS);
@@ -765,16 +772,15 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     CUDA_TRY(ctx->overflow.reserve(sizeof(uint32_t) * (nseq + 1)));
     P.overflow_count = d_ovf_count;
     P.overflow_list = (uint32_t*)ctx->overflow.p;
-    // per pre-key tables when the key space is small (u32 key types, k <= 10): built once per
-    // (k, type, hash, m) and kept in the context (48 B per key, L2 resident)
+    // first point of every possible pre-key when the key space is small (u32 key types, k <= 10):
+    // built once per (k, type, hash, m) and kept in the context (16 B per key, L2 resident)
     P.memo_fast = nullptr;
-    P.memo_state = nullptr;
     if (!key64 && 2 * k <= 20) {
         const uint32_t nkeys = 1u << (2 * k);
         if (!(ctx->memo.p && ctx->memo_k == k && ctx->memo_m == m && ctx->memo_type == kmer_type &&
               ctx->memo_hash == hash_kind)) {
-            CUDA_TRY(ctx->memo.reserve((size_t)nkeys * 48));
-            CUDA_TRY(kmu::launch_pmh3a_memo(P, ctx->memo.p, (uint8_t*)ctx->memo.p + (size_t)nkeys * 16, nkeys, st));
+            CUDA_TRY(ctx->memo.reserve((size_t)nkeys * 16));
+            CUDA_TRY(kmu::launch_pmh3a_memo(P, ctx->memo.p, nkeys, st));
             ++launches;
             ctx->memo_k = k;
             ctx->memo_m = m;
@@ -782,10 +788,9 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
             ctx->memo_hash = hash_kind;
         }
         P.memo_fast = ctx->memo.p;
-        P.memo_state = (uint8_t*)ctx->memo.p + (size_t)nkeys * 16;
     }
 
-    auto run_class = [&](const LaunchClass& c, const uint32_t* order, int counter_idx) -> int32_t {
+    auto run_class = [&](const LaunchClass& c, const uint32_t* order, int counter_idx, bool speculate) -> int32_t {
         Geometry g = make_geometry(c.nk_max, c.mode, k, m, key64, c.table_global);
         uint64_t teams_needed = c.count;
         uint64_t ctas_needed = (teams_needed + g.teams_per_cta - 1) / g.teams_per_cta;
@@ -800,6 +805,9 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         Q.first = c.first;
         Q.count = c.count;
         Q.work_counter = d_work + counter_idx;
+        Q.speculate = speculate ? 1u : 0u;
+        Q.spec_factor = (double)m * std::log((double)m / 1e-4);
+        Q.phase_clocks = ctx->profiling ? d_phase + 8 * counter_idx : nullptr;
         Q.team_warps = g.team_warps;
         Q.team_smem_bytes = g.team_smem_bytes;
         Q.regionA_bytes = g.regionA_bytes;
@@ -855,6 +863,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
             r.smem_bytes = (uint32_t)g.smem;
             r.nseq = c.count;
             r.nk_max = c.nk_max;
+            r.counter_idx = (uint32_t)counter_idx;
             ctx->lrec.push_back(r);
         }
         ++launches;
@@ -864,7 +873,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     if (classes.size() > 120) return fail(KMU_EINVAL, "too many launch classes");
     int ci = 0;
     for (const LaunchClass& c : classes) {
-        int32_t rc = run_class(c, (const uint32_t*)ctx->order.p, ci++);
+        int32_t rc = run_class(c, (const uint32_t*)ctx->order.p, ci++, true);
         if (rc) return rc;
     }
     if (ctx->profiling) {
@@ -879,8 +888,9 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
                 }
         }
     }
-    // ---- u16 histogram counters that wrapped: redo those sequences with u32 table counters ---
-    if (hist_ok) {
+    // ---- sequences whose u8 histogram counters wrapped or whose speculative qmax bound failed:
+    //      redo them with u32 table counters and without speculation ---------------------------
+    {
         unsigned long long novf = 0;
         CUDA_TRY(cudaMemcpyAsync(&novf, d_ovf_count, sizeof(novf), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -891,7 +901,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
             c.nk_max = nk_longest;
             c.mode = 1;
             c.table_global = true;
-            int32_t rc = run_class(c, (const uint32_t*)ctx->overflow.p, ci++);
+            int32_t rc = run_class(c, (const uint32_t*)ctx->overflow.p, ci++, false);
             if (rc) return rc;
         }
     }

@@ -49,18 +49,21 @@ struct Pmh3aParams {
     uint64_t table_scratch_entries;
     unsigned long long* overflow_count;
     uint32_t* overflow_list;
-    // per pre-key tables (u32 key types with a small key space), or nullptr:
-    //   memo_fast  : {x bits lo, x bits hi, slot, hashed key} of the first point
-    //   memo_state : Xoshiro256++ state after the first point (32 bytes)
+    // first point of every pre-key {x bits lo, x bits hi, slot, hashed key} (u32 key types with a
+    // small key space), or nullptr
     const void* memo_fast;
-    const void* memo_state;
+    // speculative qmax start: B = spec_factor / nk with spec_factor = m ln(m / 1e-4); 0 = off
+    uint32_t speculate;
+    double spec_factor;
     // TMA staging: bytes per staging buffer (two per team); 0 disables staging
     uint32_t stage_bytes;
+    // profiling only: 8 counters per launch, SM clocks spent per phase by thread 0 of every team
+    unsigned long long* phase_clocks;
 };
 
 constexpr size_t PMH3A_TEAM_SHARED_BYTES = 80;
 
-cudaError_t launch_pmh3a_memo(const Pmh3aParams& P, void* fast, void* state, uint32_t nkeys, cudaStream_t stream);
+cudaError_t launch_pmh3a_memo(const Pmh3aParams& P, void* fast, uint32_t nkeys, cudaStream_t stream);
 size_t pmh3a_qitem_bytes(bool key64);
 size_t pmh3a_entry_bytes(bool key64);
 cudaError_t launch_pmh3a(const Pmh3aParams& P, bool key64, int mode, int grid, int block, size_t smem,

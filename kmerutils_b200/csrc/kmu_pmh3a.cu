@@ -157,11 +157,11 @@ struct TableOps<uint64_t> {
 
 template <typename V>
 struct QItem {
-    V prekey;
+    V key;  // fhash(kmer): the value that goes into the signature
     uint32_t cnt;
 };
 
-constexpr int QCAP = 64;  // per-warp queue capacity (power of two, >= 2 * 32)
+constexpr int QCAP = 64;  // per-warp queue ring (power of two, >= 2 * 32)
 
 // per-team bookkeeping in shared memory (double buffered work descriptors + TMA barriers)
 struct __align__(16) TeamShared {
@@ -173,7 +173,7 @@ struct __align__(16) TeamShared {
     uint32_t staged[2];
     uint32_t qmax_hi;
     uint32_t flag;
-    uint32_t next_task[2];  // dynamic task counters of pass 1 / pass 2
+    uint32_t next_task[2];  // dynamic task counters: [0] pass 1 and fill phase, [1] pass 2
 };
 static_assert(sizeof(TeamShared) == PMH3A_TEAM_SHARED_BYTES, "TeamShared size");
 
@@ -206,17 +206,36 @@ __device__ __forceinline__ void sketch_update(const SlotArray& S, uint32_t s, do
     if (slot_update_min(&S.slots[s], hbits, key)) *(volatile uint32_t*)(S.hi + s) = (uint32_t)(hbits >> 32);
 }
 
+// Is an item still alive after its first point, i.e. winv * x1 < qmax ?  x1 = c1 * U where U comes
+// from the first output of the key's Xoshiro256++, which needs only the state words s0 and s3
+// (SplitMix64 outputs 1 and 4 of the seed): half a seeding, no memory.  Items on the rare
+// rejection branch of ExpRestricted01 (c1 * U >= 1) are left to the full path.
+template <typename V>
+__device__ __forceinline__ bool first_point_alive(V key, double winv, double qmax, double c1) {
+    const uint64_t seed = nohash_seed(key);
+    uint64_t z0 = seed + 0x9E3779B97F4A7C15ULL;
+    uint64_t z3 = seed + 4ULL * 0x9E3779B97F4A7C15ULL;
+    z0 = (z0 ^ (z0 >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z3 = (z3 ^ (z3 >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z0 = (z0 ^ (z0 >> 27)) * 0x94D049BB133111EBULL;
+    z3 = (z3 ^ (z3 >> 27)) * 0x94D049BB133111EBULL;
+    const uint64_t s0 = z0 ^ (z0 >> 31), s3 = z3 ^ (z3 >> 31);
+    const uint64_t r = rotl64(s0 + s3, 23) + s0;
+    const double u = __longlong_as_double((long long)((r >> 12) | 0x3FF0000000000000ULL)) - 1.0;
+    const double x = __dmul_rn(c1, u);
+    return !(x < 1.0) || __dmul_rn(winv, x) < qmax;
+}
+
+constexpr uint32_t QFLAG_SKIP_FIRST = 0x80000000u;  // QItem.cnt: the item's first point is already in the sketch
+
 // --------------------------------------------------------------------------------
 // Process up to 32 queued distinct items with one warp: every lane owns one item and
 // emits its points i = 1, 2, ... while winv * (i - 1) < qmax
 // (ProbMinHash3a::hash_weigthed_hashmap).
-// With MEMO the first point was already applied by the caller and the generator state
-// after it comes from the per-key table, so the lane starts at i = 2.
 // --------------------------------------------------------------------------------
-template <typename V, bool MEMO>
+template <typename V>
 __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t head, uint32_t n, int lane,
-                                              const Pmh3aParams& P, V header, const SlotArray& S,
-                                              uint32_t refresh_period) {
+                                              const Pmh3aParams& P, const SlotArray& S, uint32_t refresh_period) {
     bool act = (uint32_t)lane < n;
     V key = 0;
     double winv = 0.0;
@@ -225,25 +244,19 @@ __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t he
     uint32_t i = 1;
     if (act) {
         QItem<V> it = queue[(head + lane) & (QCAP - 1)];
-        winv = 1.0 / (double)it.cnt;
-        if (MEMO) {
-            key = (V)__ldg((const uint32_t*)P.memo_fast + 4 * (size_t)it.prekey + 3);
-            const uint4 a = __ldg((const uint4*)P.memo_state + 2 * (size_t)it.prekey);
-            const uint4 b = __ldg((const uint4*)P.memo_state + 2 * (size_t)it.prekey + 1);
-            rng.s0 = ((uint64_t)a.y << 32) | a.x;
-            rng.s1 = ((uint64_t)a.w << 32) | a.z;
-            rng.s2 = ((uint64_t)b.y << 32) | b.x;
-            rng.s3 = ((uint64_t)b.w << 32) | b.z;
+        winv = 1.0 / (double)(it.cnt & ~QFLAG_SKIP_FIRST);
+        key = it.key;
+        rng.seed(nohash_seed(key));
+        if (it.cnt & QFLAG_SKIP_FIRST) {  // first point applied by the caller: keep the stream aligned
+            (void)exp01_sample(P.e, rng);
+            (void)rng.unif_range(0, P.m, P.slot_thresh);
             i = 2;
-        } else {
-            key = finalize_key<V>(it.prekey, header, P.hash_kind);
-            rng.seed(nohash_seed(key));
         }
     }
     uint32_t iter = 0;
     double qmax = load_qmax(S);
     while (__any_sync(0xFFFFFFFFu, act)) {
-        if (iter % refresh_period == refresh_period - 1) {
+        if (iter && iter % refresh_period == 0) {  // only when some lane needs more than one point
             refresh_qmax(S, P.m, lane);
             qmax = load_qmax(S);
         }
@@ -269,9 +282,9 @@ __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t he
 }
 
 // MODE 0: direct histogram of 4^k u8 counters (four per u32) ; MODE 1: open-addressing table
-// MEMO : the first point of every possible pre-key (exp01 sample, slot and hashed key: functions
-//        of the key only) and the generator state after it come from tables built once per
-//        (k, type, hash, m); no item is ever seeded inside this kernel.
+// MEMO  : small key spaces (u32 k-mers, k <= 10): the first point of every pre-key -- exp01 sample,
+//         slot and hashed key, all functions of the key only -- comes from a table built once per
+//         (k, type, hash, m); otherwise the first point is half-recomputed by first_point_alive().
 template <typename V, int MODE, bool MEMO>
 __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -348,17 +361,27 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
             ts->staged[d] = staged;
         }
     };
-    // next block of 32 tasks of pass `which` for this warp
+    // next block of 32 tasks from counter `which` for this warp
     auto next_tasks = [&](int which) -> uint32_t {
         uint32_t base = 0;
         if (team.lane == 0) base = atomicAdd(&ts->next_task[which], 32u);
         return __shfl_sync(0xFFFFFFFFu, base, 0);
+    };
+    // optional phase timing (profiling runs only): team thread 0 accumulates clock deltas
+    long long t_mark = 0;
+    auto mark = [&](int phase) {
+        if (P.phase_clocks && team.tid == 0) {
+            long long now = clock64();
+            atomicAdd(P.phase_clocks + phase, (unsigned long long)(now - t_mark));
+            t_mark = now;
+        }
     };
 
     uint32_t phase0 = 0, phase1 = 0;
     int cur = 0;
     fetch(0);
     team.sync();
+    if (P.phase_clocks && team.tid == 0) t_mark = clock64();
     for (;;) {
         if (!ts->valid[cur]) break;
         fetch(cur ^ 1);  // prefetch the next sequence while this one is processed
@@ -384,8 +407,19 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
             S.slots[j].key = 0;
             S.hi[j] = (uint32_t)(F64_MAX_BITS >> 32);
         }
+        // Speculative start value of qmax.  The slot minima behave like Exp(nk / m) variables, so
+        // all of them end below B = (m / nk) ln(m / 1e-4) except with probability ~1e-4; pruning
+        // against min(B, actual) from the first item on is exactly as safe as pruning against the
+        // actual qmax PROVIDED the final maximum is below B -- which is verified before the
+        // signature is accepted (a failed sequence is redone without speculation).
+        uint32_t spec_hi = (uint32_t)(F64_MAX_BITS >> 32);
+        if (P.speculate && nk) {
+            const double B = P.spec_factor / (double)nk;
+            const uint32_t bhi = (uint32_t)__double2hiint(B);
+            if (bhi < spec_hi) spec_hi = bhi;
+        }
         if (team.tid == 0) {
-            ts->qmax_hi = (uint32_t)(F64_MAX_BITS >> 32);
+            ts->qmax_hi = spec_hi;
             ts->flag = 0;
             ts->next_task[0] = 0;
             ts->next_task[1] = 0;
@@ -406,18 +440,21 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
             capmask = (uint32_t)(cap - 1);
         }
         team.sync();
+        mark(0);  // fetch + wait for the staged bytes + slot init
 
         // ---------------- pass 1 : multiplicities + first-occurrence masks -------------------
         const bool may_wrap = nk > 0xFFu;
         for (;;) {
-            const uint32_t task = next_tasks(0) + team.lane;
-            if (task - team.lane >= ntasks) break;
+            const uint32_t base = next_tasks(0);
+            if (base >= ntasks) break;
+            const uint32_t task = base + team.lane;
             if (task < ntasks) {
                 TaskKmers<V> tk;
                 uint32_t p = task << log2T;
                 tk.init(words, p, k);
                 const uint32_t pend = min(p + T, nk);
                 uint32_t first = 0;
+#pragma unroll 1
                 for (uint32_t t = 0; p < pend; ++t, ++p) {
                     V pk = tk.get(t, canonical);
                     if (MODE == 0) {
@@ -437,13 +474,18 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
             }
         }
         team.sync();
+        mark(1);  // pass 1
         const bool overflow = MODE == 0 && ts->flag != 0;
 
         // ---------------- pass 2 : owners sketch their distinct items -------------------------
+        // Every owner reads its item's multiplicity, clears the counter and runs the first-point
+        // filter; items that are still alive are compacted into the warp queue and processed on
+        // full warps.  qmax starts from the speculative bound set up above instead of +inf.
         uint32_t qhead = 0, qtail = 0;
         for (;;) {
-            const uint32_t task = next_tasks(1) + team.lane;
-            if (task - team.lane >= ntasks) break;
+            const uint32_t base = next_tasks(1);
+            if (base >= ntasks) break;
+            const uint32_t task = base + team.lane;
             const bool tact = task < ntasks;
             TaskKmers<V> tk;
             uint32_t p = task << log2T;
@@ -452,11 +494,10 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
                 tk.init(words, p, k);
                 if (use_masks) own = log2T == 4 ? (uint32_t)((const uint16_t*)masks)[task] : (uint32_t)masks[task];
             }
-            double qmax = 0.0;
-            if (MEMO) {
-                refresh_qmax(S, P.m, team.lane);
-                qmax = load_qmax(S);
-            }
+            refresh_qmax(S, P.m, team.lane);
+            double qmax = load_qmax(S);
+            bool filter_off = qmax >= 0.75;
+#pragma unroll 1
             for (uint32_t t = 0; t < T; ++t, ++p) {
                 uint32_t cnt = 0;
                 V pk = 0;
@@ -479,19 +520,27 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
                         cnt = use_masks ? TO::lookup(tab, capmask, log2cap, pk) : TO::claim(tab, capmask, log2cap, pk);
                     }
                 }
-                if (MEMO) {
-                    // first point from the per-key table; only items that may need a second
-                    // point (h < qmax and winv < qmax) go to the queue
-                    if (cnt) {
+                V key = 0;
+                if (cnt) {
+                    if (MEMO) {
+                        // first point straight from the per-key table; only an item that may need a
+                        // second point (winv < qmax) goes to the queue
                         const uint4 e = __ldg((const uint4*)P.memo_fast + (uint32_t)pk);
-                        const double x = __hiloint2double((int)e.y, (int)e.x);
                         const double winv = cnt < 64 ? s_winv[cnt] : 1.0 / (double)cnt;
-                        const double h = __dmul_rn(winv, x);
+                        const double h = __dmul_rn(winv, __hiloint2double((int)e.y, (int)e.x));
+                        key = (V)e.w;
                         if (h < qmax) {
                             sketch_update(S, e.z, h, (uint64_t)e.w);
-                            if (!(winv < qmax)) cnt = 0;
+                            cnt = winv < qmax ? (cnt | QFLAG_SKIP_FIRST) : 0u;
                         } else {
                             cnt = 0;
+                        }
+                    } else {
+                        key = finalize_key<V>(pk, header, P.hash_kind);
+                        // while qmax is large nearly every item survives its first point: skip the filter
+                        if (!filter_off) {
+                            const double winv = cnt < 64 ? s_winv[cnt] : 1.0 / (double)cnt;
+                            if (!first_point_alive<V>(key, winv, qmax, P.e.c1)) cnt = 0;
                         }
                     }
                 }
@@ -500,33 +549,35 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
                     if (cnt) {
                         uint32_t pos = qtail + __popc(bal & ((1u << team.lane) - 1));
                         QItem<V> it;
-                        it.prekey = pk;
+                        it.key = key;
                         it.cnt = cnt;
                         myq[pos & (QCAP - 1)] = it;
                     }
                     qtail += __popc(bal);
                     __syncwarp();
                     if (qtail - qhead >= 32) {
-                        process_items<V, MEMO>(myq, qhead, 32, team.lane, P, header, S, refresh_period);
+                        process_items<V>(myq, qhead, 32, team.lane, P, S, refresh_period);
                         qhead += 32;
                         __syncwarp();
-                        if (MEMO) qmax = load_qmax(S);
+                        qmax = load_qmax(S);
+                        filter_off = qmax >= 0.75;
                     }
                 }
             }
         }
-        if (qtail != qhead) process_items<V, MEMO>(myq, qhead, qtail - qhead, team.lane, P, header, S, refresh_period);
+        if (qtail != qhead) process_items<V>(myq, qhead, qtail - qhead, team.lane, P, S, refresh_period);
         team.sync();
+        mark(3);  // pass 2
 
         // ---------------- signature out, leave region A clean --------------------------
-        if (overflow) {
-            if (team.tid == 0) {
-                unsigned long long pos = atomicAdd(P.overflow_count, 1ULL);
-                P.overflow_list[pos] = seq;
-            }
-        } else {
+        if (!overflow) {
             V* out = (V*)P.sig + (size_t)seq * P.m;
-            for (uint32_t j = team.tid; j < P.m; j += team.size) out[j] = (V)S.slots[j].key;
+            bool bad = false;
+            for (uint32_t j = team.tid; j < P.m; j += team.size) {
+                out[j] = (V)S.slots[j].key;
+                bad |= (uint32_t)(S.slots[j].hbits >> 32) > spec_hi;  // a slot ended above the speculative bound
+            }
+            if (bad) ts->flag = 2;
         }
         if (MODE == 1) {
             const uint32_t nvec = (capmask + 1) / (16 / sizeof(Entry));  // 16-byte vectors
@@ -534,31 +585,32 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
         }
         cur ^= 1;
         team.sync();  // descriptor `cur` was written before the passes; staging buffer cur^1 is free again
+        if (team.tid == 0 && ts->flag != 0) {  // u8 counter wrapped or speculation failed: redo this sequence
+            unsigned long long pos = atomicAdd(P.overflow_count, 1ULL);
+            P.overflow_list[pos] = seq;
+        }
+        mark(4);  // signature out + table clear
     }
 }
 
-// per pre-key tables: fast = {x bits lo, x bits hi, slot, hashed key}; state = Xoshiro256++ state
-// after the first point (4 x u64)
-template <typename V>
-__global__ void pmh3a_memo_kernel(uint4* fast, uint4* state, uint32_t nkeys, Pmh3aParams P) {
-    const V header = (V)word_header(P.kmer_type, P.k);
+// first point of every pre-key: {x bits lo, x bits hi, slot, hashed key}
+__global__ void pmh3a_memo_kernel(uint4* fast, uint32_t nkeys, Pmh3aParams P) {
+    const uint32_t header = word_header(P.kmer_type, P.k);
     for (uint32_t pk = blockIdx.x * blockDim.x + threadIdx.x; pk < nkeys; pk += gridDim.x * blockDim.x) {
-        V key = finalize_key<V>((V)pk, header, P.hash_kind);
+        const uint32_t key = finalize_key<uint32_t>(pk, header, P.hash_kind);
         Xoshiro256pp rng;
         rng.seed(nohash_seed(key));
-        double x = exp01_sample(P.e, rng);
-        uint32_t s = rng.unif_range(0, P.m, P.slot_thresh);
-        fast[pk] = make_uint4((uint32_t)__double2loint(x), (uint32_t)__double2hiint(x), s, (uint32_t)key);
-        state[2 * (size_t)pk] = make_uint4((uint32_t)rng.s0, (uint32_t)(rng.s0 >> 32), (uint32_t)rng.s1, (uint32_t)(rng.s1 >> 32));
-        state[2 * (size_t)pk + 1] = make_uint4((uint32_t)rng.s2, (uint32_t)(rng.s2 >> 32), (uint32_t)rng.s3, (uint32_t)(rng.s3 >> 32));
+        const double x = exp01_sample(P.e, rng);
+        const uint32_t s = rng.unif_range(0, P.m, P.slot_thresh);
+        fast[pk] = make_uint4((uint32_t)__double2loint(x), (uint32_t)__double2hiint(x), s, key);
     }
 }
 
-cudaError_t launch_pmh3a_memo(const Pmh3aParams& P, void* fast, void* state, uint32_t nkeys, cudaStream_t stream) {
+cudaError_t launch_pmh3a_memo(const Pmh3aParams& P, void* fast, uint32_t nkeys, cudaStream_t stream) {
     int block = 256;
     int grid = (int)((nkeys + block - 1) / block);
     if (grid > 148 * 8) grid = 148 * 8;
-    pmh3a_memo_kernel<uint32_t><<<grid, block, 0, stream>>>((uint4*)fast, (uint4*)state, nkeys, P);
+    pmh3a_memo_kernel<<<grid, block, 0, stream>>>((uint4*)fast, nkeys, P);
     return cudaGetLastError();
 }
 
@@ -585,12 +637,11 @@ size_t pmh3a_entry_bytes(bool key64) {
 
 cudaError_t launch_pmh3a(const Pmh3aParams& P, bool key64, int mode, int grid, int block, size_t smem,
                          cudaStream_t stream) {
-    const bool memo = P.memo_fast != nullptr && !key64;
     if (key64) {
         return mode == 0 ? launch_one<uint64_t, 0, false>(P, grid, block, smem, stream)
                          : launch_one<uint64_t, 1, false>(P, grid, block, smem, stream);
     }
-    if (memo)
+    if (P.memo_fast)
         return mode == 0 ? launch_one<uint32_t, 0, true>(P, grid, block, smem, stream)
                          : launch_one<uint32_t, 1, true>(P, grid, block, smem, stream);
     return mode == 0 ? launch_one<uint32_t, 0, false>(P, grid, block, smem, stream)

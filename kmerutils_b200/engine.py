@@ -118,7 +118,12 @@ class Engine:
         """Per-launch records of the last sketch call (needs set_profiling(True) before it)."""
         recs = (_lib.KmuLaunchRec * 160)()
         n = self.lib.kmu_last_launch_profile(self.ctx, recs, 160)
-        return [{f: getattr(recs[i], f) for f, _ in _lib.KmuLaunchRec._fields_} for i in range(min(n, 160))]
+        out = []
+        for i in range(min(n, 160)):
+            d = {f: getattr(recs[i], f) for f, _ in _lib.KmuLaunchRec._fields_}
+            d["phase_clocks"] = list(d["phase_clocks"])
+            out.append(d)
+        return out
 
     # ---- batches ------------------------------------------------------------------------
     def batch_from_sequences(self, packed_list, nbases):
