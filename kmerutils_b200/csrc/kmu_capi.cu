@@ -655,7 +655,7 @@ Geometry make_geometry(uint64_t nk_max, int mode, uint32_t k, uint32_t m, bool k
         uint32_t max_teams = 32 / tw;
         if (tw > 1 && max_teams > 15) max_teams = 15;  // named barriers 1..15
         // shared memory limits the number of teams: widen the teams so that the SM still gets 32 warps
-        if (tw < 32 && teams_fit < 32 / tw) {
+        if (tw < 32 && teams_fit * tw < 24) {
             tw <<= 1;
             continue;
         }
@@ -722,7 +722,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         c.count = cnt;
         c.nk_max = nk_max;
         const uint64_t hist_bytes = (1ull << (2 * k));  // u8 counters
-        if (hist_ok && (table_bytes > 128 * 1024 || hist_bytes <= table_bytes)) {
+        if (hist_ok && (table_bytes > 128 * 1024 || hist_bytes <= 4 * table_bytes)) {
             c.mode = 0;
             c.table_global = false;
         } else {
