@@ -132,10 +132,50 @@ int32_t kmu_nthash_canonical(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k
  * row i = sequence i.  m >= 2. */
 int32_t kmu_sketch_pmh3a(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, int32_t kmer_type, int32_t hash_kind,
                          uint32_t m, void* sig, int32_t sig_on_device);
-/* one-shot host form: upload (pinned double-buffered chunks), sketch, download. */
+/* one-shot host form: sequences in host memory in, signatures in host memory out.  The input is
+ * cut into chunks that are uploaded, sketched and downloaded on three streams (double buffered);
+ * pin the buffers (cudaHostRegister / cudaMallocHost) for full PCIe speed. */
 int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t packed_bytes, const uint64_t* byte_off,
                               const uint64_t* nbases, uint64_t nseq, uint32_t k, int32_t kmer_type, int32_t hash_kind,
                               uint32_t m, void* sig);
+
+/* ---- k-mer counting (replaces KmerCounter: cuckoo filter + counting Bloom filter,
+ *      src/base/kmercount.rs:70-83) -------------------------------------------------------
+ * One exact open-addressing table in HBM keyed by kmer.get_compressed_value().  Semantics are
+ * those of the reference with zero filter false positives: get_count = 0 (never inserted), 1
+ * (inserted once) or min(multiplicity, 2^count_bits - 1) (the counting Bloom filter saturates,
+ * test kmercount.rs:1615); nb_distinct = number of different k-mers; nb_unique = k-mers seen
+ * exactly once (KmerCountT, kmercount.rs:48-59).  `capacity` is the number of distinct k-mers
+ * the table must hold (KmerCounter::new(fpr, capacity, nb_bits), :88-98); inserting more fails
+ * with KMU_EOVERFLOW instead of degrading. */
+typedef struct kmu_counter kmu_counter;
+int32_t kmu_count_create(kmu_ctx* ctx, uint32_t k, int32_t kmer_type, uint32_t count_bits, uint64_t capacity,
+                         kmu_counter** counter);
+void kmu_count_destroy(kmu_counter* counter);
+uint64_t kmu_count_capacity(const kmu_counter* counter); /* slots allocated */
+/* count_kmer / count_kmer_threaded_one_to_many (kmercount.rs:293-362, 881-974): every k-mer of every
+ * sequence, canonical != 0 -> kmer.reverse_complement().min(kmer) first (:313,827,938) */
+int32_t kmu_count_insert_seqs(kmu_ctx* ctx, kmu_counter* counter, const kmu_seqbatch* batch, int32_t canonical);
+/* KmerCountT::insert_kmer for an array of compressed k-mer values (u32 or u64 by k-mer type) */
+int32_t kmu_count_insert_kmers(kmu_ctx* ctx, kmu_counter* counter, const void* kmers, uint64_t n, int32_t on_device);
+/* KmerCountT::get_count for an array of compressed k-mer values */
+int32_t kmu_count_query(kmu_ctx* ctx, const kmu_counter* counter, const void* kmers, uint64_t n, uint32_t* counts,
+                        int32_t on_device);
+/* get_nb_distinct / get_nb_unique, total multiplicity, and hist256[c] = number of k-mers with
+ * min(multiplicity, 255) == c (any output may be NULL) */
+int32_t kmu_count_stats(kmu_ctx* ctx, const kmu_counter* counter, uint64_t* nb_distinct, uint64_t* nb_unique,
+                        uint64_t* nb_inserted, uint64_t* hist256);
+/* the k-mers with multiplicity >= min_count and their counts, unordered (what
+ * threaded_dump_kmer_counter writes with min_count = 2, kmercount.rs:653-791); host buffers of `cap`
+ * entries; *n_out = number found (KMU_EOVERFLOW if > cap) */
+int32_t kmu_count_export(kmu_ctx* ctx, const kmu_counter* counter, uint32_t min_count, void* kmers, uint32_t* counts,
+                         uint64_t cap, uint64_t* n_out);
+/* DispatchableT::dispatch (kmercount.rs:382-420) for a whole batch: all (canonical) compressed k-mer
+ * values bucketed by owner = intNN_hash(value) % nparts.  kmers_out holds kmu_kmer_count() values,
+ * bucket p first-to-last at offset sum(part_counts[0..p)).  This is the send side of the multi-GPU
+ * exchange: bucket p goes to rank p, which feeds what it receives to kmu_count_insert_kmers. */
+int32_t kmu_count_partition(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, int32_t kmer_type, int32_t canonical,
+                            uint32_t nparts, void* kmers_out, uint64_t* part_counts, int32_t out_on_device);
 
 /* ---- timing of the last compute call on the context (CUDA events on its stream) ----- */
 typedef struct kmu_times {
@@ -145,6 +185,7 @@ typedef struct kmu_times {
     uint64_t h2d_bytes; /* bytes copied host->device by the last call */
     uint64_t d2h_bytes; /* bytes copied device->host by the last call */
     uint64_t launches;  /* kernels launched by the last call */
+    float host_ms;      /* wall time of the whole call on the host (one-shot host entry points) */
 } kmu_times;
 int32_t kmu_last_times(const kmu_ctx* ctx, kmu_times* out);
 

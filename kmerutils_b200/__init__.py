@@ -7,6 +7,6 @@ table can be checked), every compute call needs a B200.
 """
 from ._lib import (HASH_CANON_INVHASH, HASH_CANON_RAW, HASH_IDENTITY_RAW, HASH_INVHASH, HASH_MASKED_VALUE, KMER16B32,
                    KMER32, KMER64, KMERAA32, KMERAA64, KmuError, KmuInvalid, load_library)
-from .engine import Engine, SeqBatch, default_engine, val_dtype
+from .engine import Engine, KmerCounter, SeqBatch, default_engine, val_dtype
 
 __version__ = "0.1.0"

@@ -22,7 +22,8 @@ vpp = C.POINTER(C.c_void_p)
 
 class KmuTimes(C.Structure):
     _fields_ = [("kernel_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("launches", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("launches", C.c_uint64),
+                ("host_ms", C.c_float)]
 
 
 class KmuLaunchRec(C.Structure):
@@ -69,6 +70,16 @@ SIGNATURES = {
                                      C.c_int32]),
     "kmu_sketch_pmh3a_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, u64p, u64p, C.c_uint64, C.c_uint32,
                                           C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
+    "kmu_count_create": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint64, vpp]),
+    "kmu_count_destroy": (None, [C.c_void_p]),
+    "kmu_count_capacity": (C.c_uint64, [C.c_void_p]),
+    "kmu_count_insert_seqs": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "kmu_count_insert_kmers": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32]),
+    "kmu_count_query": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32]),
+    "kmu_count_stats": (C.c_int32, [C.c_void_p, C.c_void_p, u64p, u64p, u64p, u64p]),
+    "kmu_count_export": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
+    "kmu_count_partition": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32,
+                                        C.c_void_p, u64p, C.c_int32]),
     "kmu_last_times": (C.c_int32, [C.c_void_p, C.POINTER(KmuTimes)]),
     "kmu_ctx_set_profiling": (C.c_int32, [C.c_void_p, C.c_int32]),
     "kmu_last_launch_profile": (C.c_uint32, [C.c_void_p, C.POINTER(KmuLaunchRec), C.c_uint32]),

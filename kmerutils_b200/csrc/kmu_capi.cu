@@ -2,6 +2,7 @@
 // batches resident in HBM, launch policy of the kernels.  No CPU fallback anywhere: every
 // compute entry point needs a CUDA device and fails with KMU_ECUDA otherwise.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -15,13 +16,15 @@
 #include <cuda_runtime.h>
 
 #include "../../include/kmerutils_b200.h"
+#include "kmu_host.h"
 #include "kmu_kernels.h"
 
 namespace {
-
 thread_local std::string g_err;
+}  // namespace
 
-int32_t fail(int32_t code, const char* fmt, ...) {
+#undef fail
+int32_t kmu_fail(int32_t code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -30,95 +33,9 @@ int32_t fail(int32_t code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
-
-#define CUDA_TRY(expr)                                                                              \
-    do {                                                                                            \
-        cudaError_t _e = (expr);                                                                    \
-        if (_e != cudaSuccess) return fail(KMU_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
-    } while (0)
-
-constexpr size_t SMEM_BUDGET = 227 * 1024 - 1024;  // opt-in shared memory per CTA on sm_100 minus static use
-constexpr size_t SEQ_ALIGN = 16;
-constexpr size_t TAIL_SLACK = 64;
-
-// growable device buffer
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e == cudaSuccess) cap = bytes;
-        return e;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-struct PinnedBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMallocHost(&p, bytes);
-        if (e == cudaSuccess) cap = bytes;
-        return e;
-    }
-    void release() {
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-}  // namespace
-
-struct kmu_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    std::mutex mu;
-    uint64_t launches = 0;
-    kmu_times last{};
-    cudaEvent_t ev[6]{};  // k0 k1 h0 h1 d0 d1
-    int sm_count = 148;
-    // scratch
-    DevBuf order, counters, table_scratch, slot_scratch, overflow, sig_dev, misc;
-    bool table_scratch_clean = false;
-    PinnedBuf pinned;
-    // first-point table of the ProbMinHash3a kernels (small key spaces), see kmu_pmh3a.cu
-    DevBuf memo;
-    uint32_t memo_k = 0, memo_m = 0;
-    int memo_type = -1, memo_hash = -1;
-    // optional per-launch profile of the last sketch call
-    bool profiling = false;
-    std::vector<cudaEvent_t> lev;
-    std::vector<kmu_launch_rec> lrec;
-};
-
-struct kmu_seqbatch {
-    int device = 0;
-    uint8_t* packed = nullptr;
-    uint64_t* byte_off = nullptr;
-    uint64_t* nbases = nullptr;
-    uint64_t nseq = 0;
-    uint64_t packed_bytes = 0;  // without the tail slack
-    uint64_t total_bases = 0;
-    std::vector<uint64_t> h_nbases;
-    std::vector<uint64_t> h_byte_off;
-};
+#define fail kmu_fail
 
 namespace {
-
-inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 // byte layout of a batch: every sequence on a 16-byte boundary
 uint64_t layout_offsets(const uint64_t* nbases, uint64_t nseq, std::vector<uint64_t>& off) {
@@ -158,28 +75,6 @@ int32_t batch_upload_meta(kmu_ctx* ctx, kmu_seqbatch* b) {
                              ctx->stream));
     return KMU_OK;
 }
-
-bool kmer_type_accepts(uint32_t k, int type) {
-    switch (type) {
-        case KMU_KMER32: return k >= 1 && k <= 14;   // src/base/kmergenerator.rs:311, kmer32bit.rs:68-76
-        case KMU_KMER16B32: return k == 16;          // src/base/kmergenerator.rs:218-220
-        case KMU_KMER64: return k >= 1 && k <= 32;   // src/base/kmergenerator.rs:415
-        default: return false;
-    }
-}
-
-struct ScopedDevice {
-    int prev = -1;
-    explicit ScopedDevice(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-    }
-    ~ScopedDevice() {
-        int cur = -1;
-        cudaGetDevice(&cur);
-        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
-    }
-};
 
 void parallel_copy(uint8_t* dst, const std::vector<uint64_t>& dst_off, const uint8_t* const* ptrs, const uint8_t* base,
                    const uint64_t* src_off, const uint64_t* nbases, uint64_t nseq) {
@@ -248,6 +143,18 @@ void kmu_ctx_destroy(kmu_ctx* c) {
     for (auto* b : {&c->order, &c->counters, &c->table_scratch, &c->slot_scratch, &c->overflow, &c->sig_dev, &c->misc, &c->memo})
         b->release();
     c->pinned.release();
+    for (int i = 0; i < 2; ++i) {
+        c->pipe.packed[i].release();
+        c->pipe.meta[i].release();
+        c->pipe.sig[i].release();
+        c->pipe.stage[i].release();
+        c->pipe.meta_host[i].release();
+        for (cudaEvent_t ev : {c->pipe.in_begin[i], c->pipe.in_done[i], c->pipe.compute_done[i], c->pipe.out_begin[i],
+                               c->pipe.out_done[i]})
+            if (ev) cudaEventDestroy(ev);
+    }
+    if (c->pipe.copy_in) cudaStreamDestroy(c->pipe.copy_in);
+    if (c->pipe.copy_out) cudaStreamDestroy(c->pipe.copy_out);
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->lev) cudaEventDestroy(ev);
@@ -298,9 +205,12 @@ int32_t kmu_last_times(const kmu_ctx* ctx, kmu_times* out) {
 void kmu_seqbatch_destroy(kmu_seqbatch* b) {
     if (!b) return;
     ScopedDevice sd(b->device);
-    if (b->packed) cudaFree(b->packed);
-    if (b->byte_off) cudaFree(b->byte_off);
-    if (b->nbases) cudaFree(b->nbases);
+    b->order_cache.order.release();
+    if (b->owns) {
+        if (b->packed) cudaFree(b->packed);
+        if (b->byte_off) cudaFree(b->byte_off);
+        if (b->nbases) cudaFree(b->nbases);
+    }
     delete b;
 }
 uint64_t kmu_seqbatch_nseq(const kmu_seqbatch* b) { return b ? b->nseq : 0; }
@@ -683,7 +593,8 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     ctx->lrec.clear();
 
     // ---- order sequences longest first (8 buckets per octave of the k-mer count) -------
-    CUDA_TRY(ctx->order.reserve(sizeof(uint32_t) * (nseq + 1)));
+    // histogram and cursors come from the host copy of the lengths; the processing order is
+    // built on the device once per (batch, k) and kept with the batch
     CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256 + 8 * 128)));
     unsigned long long* d_hist = (unsigned long long*)ctx->counters.p;
     unsigned long long* d_cursor = d_hist + kmu::LEN_BUCKETS;
@@ -691,19 +602,33 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     unsigned long long* d_ovf_count = d_work + 128;
     unsigned long long* d_phase = d_work + 256;  // 8 per launch, profiling only
     CUDA_TRY(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256 + 8 * 128), st));
-    CUDA_TRY(kmu::launch_len_hist(b->nbases, nseq, k, d_hist, st));
-    ++launches;
-    std::vector<unsigned long long> hist(kmu::LEN_BUCKETS), cursor(kmu::LEN_BUCKETS);
-    CUDA_TRY(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned long long) * kmu::LEN_BUCKETS, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    unsigned long long acc = 0;
-    for (int i = 0; i < kmu::LEN_BUCKETS; ++i) {
-        cursor[i] = acc;
-        acc += hist[i];
+    OrderCache& oc = b->order_cache;
+    if (oc.k != k || oc.hist.empty()) {
+        oc.hist.assign(kmu::LEN_BUCKETS, 0);
+        oc.cursor.assign(kmu::LEN_BUCKETS, 0);
+        oc.nk_longest = 0;
+        for (uint64_t L : b->h_nbases) {
+            const uint64_t nk = L >= k ? L - k + 1 : 0;
+            ++oc.hist[kmu::len_bucket_host(nk)];
+            oc.nk_longest = std::max(oc.nk_longest, nk);
+        }
+        unsigned long long acc = 0;
+        for (int i = 0; i < kmu::LEN_BUCKETS; ++i) {
+            oc.cursor[i] = acc;
+            acc += oc.hist[i];
+        }
+        CUDA_TRY(oc.order.reserve(sizeof(uint32_t) * (nseq + 1)));
+        CUDA_TRY(cudaMemcpyAsync(d_cursor, oc.cursor.data(), sizeof(unsigned long long) * kmu::LEN_BUCKETS,
+                                 cudaMemcpyHostToDevice, st));
+        CUDA_TRY(kmu::launch_len_scatter(b->nbases, nseq, k, d_cursor, (uint32_t*)oc.order.p, st));
+        ++launches;
+        oc.k = k;
     }
-    CUDA_TRY(cudaMemcpyAsync(d_cursor, cursor.data(), sizeof(unsigned long long) * kmu::LEN_BUCKETS, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(kmu::launch_len_scatter(b->nbases, nseq, k, d_cursor, (uint32_t*)ctx->order.p, st));
-    ++launches;
+    (void)d_hist;
+    const std::vector<unsigned long long>& hist = oc.hist;
+    const std::vector<unsigned long long>& cursor = oc.cursor;
+    const uint64_t nk_longest = oc.nk_longest;
+    const uint32_t* d_order = (const uint32_t*)oc.order.p;
 
     // ---- launch classes: one per octave of the k-mer count ------------------------------
     const bool hist_ok = k <= 8;
@@ -745,8 +670,6 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         classes.push_back(c);
     }
     // exact largest k-mer count (the first class is sized by it, not by its octave bound)
-    uint64_t nk_longest = 0;
-    for (uint64_t L : b->h_nbases) nk_longest = std::max<uint64_t>(nk_longest, L >= k ? L - k + 1 : 0);
     if (!classes.empty()) classes.front().nk_max = std::min(classes.front().nk_max, nk_longest);
 
     // ---- parameters common to all launches ------------------------------------------------
@@ -754,7 +677,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     P.packed = b->packed;
     P.byte_off = b->byte_off;
     P.nbases = b->nbases;
-    P.order = (const uint32_t*)ctx->order.p;
+    P.order = d_order;
     P.k = k;
     P.kmer_type = kmer_type;
     P.hash_kind = hash_kind;
@@ -873,7 +796,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     if (classes.size() > 120) return fail(KMU_EINVAL, "too many launch classes");
     int ci = 0;
     for (const LaunchClass& c : classes) {
-        int32_t rc = run_class(c, (const uint32_t*)ctx->order.p, ci++, true);
+        int32_t rc = run_class(c, d_order, ci++, true);
         if (rc) return rc;
     }
     if (ctx->profiling) {
@@ -958,21 +881,163 @@ int32_t kmu_sketch_pmh3a(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_
     return KMU_OK;
 }
 
+// One-shot host form.  The sequences are cut into chunks of about 96 MB of packed bases; chunk
+// c+1 travels host->device on the copy-in stream while chunk c is sketched on the compute stream
+// and the signatures of chunk c-1 travel device->host on the copy-out stream (two device slots,
+// grow-only, owned by the context: no cudaMalloc / cudaFree per call).  A host buffer already in
+// the batch layout (every sequence on a 16-byte boundary, back to back) is copied straight from
+// the caller's memory -- pin it for full PCIe speed; any other layout is re-laid out through a
+// pinned staging buffer first.
 int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t packed_bytes, const uint64_t* byte_off,
                               const uint64_t* nbases, uint64_t nseq, uint32_t k, int32_t kmer_type, int32_t hash_kind,
                               uint32_t m, void* sig) {
-    kmu_seqbatch* b = nullptr;
-    int32_t rc = kmu_seqbatch_from_packed(ctx, packed, packed_bytes, byte_off, nbases, nseq, &b);
-    if (rc) return rc;
-    kmu_times up{};
-    kmu_last_times(ctx, &up);
-    rc = kmu_sketch_pmh3a(ctx, b, k, kmer_type, hash_kind, m, sig, 0);
-    kmu_seqbatch_destroy(b);
-    if (rc == KMU_OK) {
-        ctx->last.h2d_ms = up.h2d_ms;
-        ctx->last.h2d_bytes = up.h2d_bytes;
+    if (!ctx || (nseq && (!packed || !byte_off || !nbases))) return fail(KMU_EINVAL, "null argument");
+    if (kmer_type != KMU_KMER32 && kmer_type != KMU_KMER16B32 && kmer_type != KMU_KMER64)
+        return fail(KMU_EINVAL, "kmer type %d is not a 2-bit DNA k-mer type", kmer_type);
+    if (!kmer_type_accepts(k, kmer_type))
+        return fail(KMU_EINVAL, "KmerSeqIterator cannot support kmer size %u for kmer type %d", k, kmer_type);
+    if (hash_kind < 0 || hash_kind > KMU_HASH_INVHASH) return fail(KMU_EINVAL, "unknown hash kind %d", hash_kind);
+    if (m < 2) return fail(KMU_EINVAL, "ProbMinHash3a needs at least 2 hash values (m = %u)", m);
+    if (nseq == 0) return KMU_OK;
+    if (!sig) return fail(KMU_EINVAL, "null signature buffer");
+    if (nseq >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "more than 2^32-1 sequences in one batch");
+    for (uint64_t i = 0; i < nseq; ++i) {
+        if (byte_off[i] + (nbases[i] + 3) / 4 > packed_bytes)
+            return fail(KMU_EINVAL, "sequence %llu overruns the packed buffer", (unsigned long long)i);
+        if (nbases[i] >= 0xFFFFFF00ull) return fail(KMU_EINVAL, "a single sequence is limited to 2^32 - 256 bases");
     }
-    return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    const auto t_begin = std::chrono::steady_clock::now();
+    ctx->last = kmu_times{};
+    HostPipe& hp = ctx->pipe;
+    if (!hp.copy_in) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&hp.copy_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&hp.copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreate(&hp.in_begin[i]));
+            CUDA_TRY(cudaEventCreate(&hp.in_done[i]));
+            CUDA_TRY(cudaEventCreate(&hp.compute_done[i]));
+            CUDA_TRY(cudaEventCreate(&hp.out_begin[i]));
+            CUDA_TRY(cudaEventCreate(&hp.out_done[i]));
+        }
+    }
+    const size_t vsz = kmer_type == KMU_KMER64 ? 8 : 4;
+    // batch layout of the whole input and the chunk boundaries
+    std::vector<uint64_t> lay;
+    const uint64_t total_bytes = layout_offsets(nbases, nseq, lay);
+    bool same_layout = packed_bytes >= total_bytes;
+    for (uint64_t i = 0; i < nseq && same_layout; ++i) same_layout = byte_off[i] == lay[i];
+    const uint64_t target = 96ull << 20;
+    std::vector<uint64_t> cut{0};
+    for (uint64_t i = 0, start = 0; i < nseq; ++i) {
+        const uint64_t end = i + 1 < nseq ? lay[i + 1] : total_bytes;
+        if (end - lay[start] >= target || i + 1 == nseq) {
+            cut.push_back(i + 1);
+            start = i + 1;
+        }
+    }
+    const size_t nchunks = cut.size() - 1;
+    uint64_t max_bytes = 0, max_seqs = 0;
+    for (size_t c = 0; c < nchunks; ++c) {
+        const uint64_t e = cut[c + 1] < nseq ? lay[cut[c + 1]] : total_bytes;
+        max_bytes = std::max(max_bytes, e - lay[cut[c]]);
+        max_seqs = std::max(max_seqs, cut[c + 1] - cut[c]);
+    }
+    for (int sl = 0; sl < 2 && sl < (int)nchunks; ++sl) {
+        cudaError_t e = hp.packed[sl].reserve(max_bytes + TAIL_SLACK);
+        if (e == cudaSuccess) e = hp.meta[sl].reserve(2 * sizeof(uint64_t) * (max_seqs + 1));
+        if (e == cudaSuccess) e = hp.sig[sl].reserve(max_seqs * m * vsz);
+        if (e == cudaSuccess) e = hp.meta_host[sl].reserve(2 * sizeof(uint64_t) * (max_seqs + 1));
+        if (e == cudaSuccess && !same_layout) e = hp.stage[sl].reserve(max_bytes);
+        if (e != cudaSuccess) return fail(KMU_ENOMEM, "host pipeline buffers: %s", cudaGetErrorString(e));
+    }
+    std::vector<kmu_seqbatch> views(nchunks);
+    std::vector<char> timed_in(2, 0), timed_out(2, 0);
+    auto harvest = [&](int sl) {  // add the finished copies of a slot to the totals
+        float ms = 0;
+        if (timed_in[sl] && cudaEventElapsedTime(&ms, hp.in_begin[sl], hp.in_done[sl]) == cudaSuccess) ctx->last.h2d_ms += ms;
+        if (timed_out[sl] && cudaEventElapsedTime(&ms, hp.out_begin[sl], hp.out_done[sl]) == cudaSuccess) ctx->last.d2h_ms += ms;
+        timed_in[sl] = timed_out[sl] = 0;
+    };
+    auto upload = [&](size_t c) -> int32_t {
+        const int sl = (int)(c & 1);
+        const uint64_t s0 = cut[c], s1 = cut[c + 1], n = s1 - s0;
+        const uint64_t b0 = lay[s0], b1 = s1 < nseq ? lay[s1] : total_bytes;
+        kmu_seqbatch& v = views[c];
+        v.device = ctx->device;
+        v.owns = false;
+        v.packed = (uint8_t*)hp.packed[sl].p;
+        v.byte_off = (uint64_t*)hp.meta[sl].p;
+        v.nbases = (uint64_t*)hp.meta[sl].p + (max_seqs + 1);
+        v.nseq = n;
+        v.packed_bytes = b1 - b0;
+        v.h_nbases.assign(nbases + s0, nbases + s1);
+        v.h_byte_off.resize(n);
+        for (uint64_t i = 0; i < n; ++i) {
+            v.h_byte_off[i] = lay[s0 + i] - b0;
+            v.total_bases += nbases[s0 + i];
+        }
+        // the slot's previous occupant (chunk c-2) must have been sketched and its copies harvested
+        if (c >= 2) {
+            CUDA_TRY(cudaEventSynchronize(hp.compute_done[sl]));
+            harvest(sl);
+        }
+        uint64_t* mh = (uint64_t*)hp.meta_host[sl].p;
+        std::memcpy(mh, v.h_byte_off.data(), sizeof(uint64_t) * n);
+        std::memcpy(mh + (max_seqs + 1), v.h_nbases.data(), sizeof(uint64_t) * n);
+        const uint8_t* src = packed + b0;
+        if (!same_layout) {
+            parallel_copy((uint8_t*)hp.stage[sl].p, v.h_byte_off, nullptr, packed, byte_off + s0, nbases + s0, n);
+            src = (const uint8_t*)hp.stage[sl].p;
+        }
+        CUDA_TRY(cudaEventRecord(hp.in_begin[sl], hp.copy_in));
+        CUDA_TRY(cudaMemcpyAsync(v.packed, src, v.packed_bytes, cudaMemcpyHostToDevice, hp.copy_in));
+        CUDA_TRY(cudaMemsetAsync(v.packed + v.packed_bytes, 0, TAIL_SLACK, hp.copy_in));
+        CUDA_TRY(cudaMemcpyAsync(hp.meta[sl].p, mh, 2 * sizeof(uint64_t) * (max_seqs + 1), cudaMemcpyHostToDevice, hp.copy_in));
+        CUDA_TRY(cudaEventRecord(hp.in_done[sl], hp.copy_in));
+        timed_in[sl] = 1;
+        ctx->last.h2d_bytes += v.packed_bytes + 2 * sizeof(uint64_t) * n;
+        return KMU_OK;
+    };
+    int32_t rc = upload(0);
+    for (size_t c = 0; c < nchunks && rc == KMU_OK; ++c) {
+        const int sl = (int)(c & 1);
+        if (c + 1 < nchunks) rc = upload(c + 1);
+        if (rc) break;
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, hp.in_done[sl], 0));
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, hp.out_done[sl], 0));  // signature slot free again
+        cudaEventRecord(ctx->ev[0], ctx->stream);
+        rc = sketch_pmh3a_locked(ctx, &views[c], k, kmer_type, hash_kind, m, hp.sig[sl].p);
+        cudaEventRecord(ctx->ev[1], ctx->stream);
+        CUDA_TRY(cudaEventRecord(hp.compute_done[sl], ctx->stream));
+        if (rc) break;
+        CUDA_TRY(cudaStreamWaitEvent(hp.copy_out, hp.compute_done[sl], 0));
+        const size_t out_bytes = (size_t)views[c].nseq * m * vsz;
+        CUDA_TRY(cudaEventRecord(hp.out_begin[sl], hp.copy_out));
+        CUDA_TRY(cudaMemcpyAsync((uint8_t*)sig + (size_t)cut[c] * m * vsz, hp.sig[sl].p, out_bytes, cudaMemcpyDeviceToHost,
+                                 hp.copy_out));
+        CUDA_TRY(cudaEventRecord(hp.out_done[sl], hp.copy_out));
+        timed_out[sl] = 1;
+        ctx->last.d2h_bytes += out_bytes;
+        CUDA_TRY(cudaEventSynchronize(ctx->ev[1]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        ctx->last.kernel_ms += ms;
+    }
+    cudaError_t e1 = cudaStreamSynchronize(hp.copy_in);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e3 = cudaStreamSynchronize(hp.copy_out);
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        ctx->table_scratch_clean = false;
+        return fail(KMU_ECUDA, "host sketch pipeline failed: %s",
+                    cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    }
+    harvest(0);
+    harvest(1);
+    ctx->last.host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return KMU_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,282 @@
+// kmu_capi_count.cu -- C ABI of the counting table (include/kmerutils_b200.h "k-mer counting").
+// Replaces KmerCounter / KmerCounterPool and the count_kmer* drivers of src/base/kmercount.rs.
+#include <algorithm>
+#include <vector>
+
+#include "kmu_host.h"
+
+struct kmu_counter {
+    int device = 0;
+    uint32_t k = 0;
+    int kmer_type = 0;
+    uint32_t count_bits = 8;
+    bool key64 = false;
+    uint64_t capacity = 0;  // slots (power of two)
+    DevBuf slots, aux;      // aux: [0] special, [1] overflow, [2] export cursor, [8 .. 8+3+256) stats
+    uint64_t inserted = 0;  // k-mers inserted so far (multiplicity total)
+    kmu::CountTable view() const {
+        kmu::CountTable t;
+        t.slots = slots.p;
+        t.capmask = capacity - 1;
+        t.special = (unsigned long long*)aux.p;
+        t.overflow = (unsigned long long*)aux.p + 1;
+        return t;
+    }
+    uint32_t max_count() const { return count_bits >= 32 ? 0xFFFFFFFFu : ((1u << count_bits) - 1u); }
+};
+
+namespace {
+
+constexpr size_t AUX_WORDS = 8 + 3 + 256;
+
+int32_t check_overflow(kmu_ctx* ctx, kmu_counter* c) {
+    unsigned long long ovf = 0;
+    CUDA_TRY(cudaMemcpyAsync(&ovf, (unsigned long long*)c->aux.p + 1, sizeof(ovf), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ovf)
+        return fail(KMU_EOVERFLOW, "counting table of %llu slots is full: create the counter with a larger capacity",
+                    (unsigned long long)c->capacity);
+    return KMU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t kmu_count_create(kmu_ctx* ctx, uint32_t k, int32_t kmer_type, uint32_t count_bits, uint64_t capacity,
+                         kmu_counter** out) {
+    if (!ctx || !out) return fail(KMU_EINVAL, "null argument");
+    *out = nullptr;
+    if (!kmer_type_accepts(k, kmer_type))
+        return fail(KMU_EINVAL, "kmer size %u is not supported by kmer type %d", k, kmer_type);
+    if (count_bits < 1 || count_bits > 32) return fail(KMU_EINVAL, "count_bits must be in 1..32, got %u", count_bits);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    auto* c = new kmu_counter();
+    c->device = ctx->device;
+    c->k = k;
+    c->kmer_type = kmer_type;
+    c->count_bits = count_bits;
+    c->key64 = kmer_type == KMU_KMER64;
+    // load factor <= 0.5 at the stated capacity; never more slots than there are possible keys (x2)
+    uint64_t want = std::max<uint64_t>(1024, capacity * 2);
+    if (2 * k < 40) want = std::min<uint64_t>(want, std::max<uint64_t>(1024, 2ull << (2 * k)));
+    uint64_t cap = 1024;
+    while (cap < want) cap <<= 1;
+    c->capacity = cap;
+    const size_t slot_bytes = c->key64 ? 16 : 8;
+    cudaError_t e = c->slots.reserve(cap * slot_bytes);
+    if (e == cudaSuccess) e = c->aux.reserve(sizeof(unsigned long long) * AUX_WORDS);
+    if (e != cudaSuccess) {
+        c->slots.release();
+        c->aux.release();
+        delete c;
+        return fail(KMU_ENOMEM, "counting table of %llu slots (%llu bytes): %s", (unsigned long long)cap,
+                    (unsigned long long)(cap * slot_bytes), cudaGetErrorString(e));
+    }
+    e = cudaMemsetAsync(c->aux.p, 0, sizeof(unsigned long long) * AUX_WORDS, ctx->stream);
+    if (e == cudaSuccess) e = kmu::launch_count_init(c->view(), c->key64, ctx->sm_count, ctx->stream);
+    ctx->launches += 1;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        c->slots.release();
+        c->aux.release();
+        delete c;
+        return fail(KMU_ECUDA, "counting table initialisation failed: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return KMU_OK;
+}
+
+void kmu_count_destroy(kmu_counter* c) {
+    if (!c) return;
+    ScopedDevice sd(c->device);
+    c->slots.release();
+    c->aux.release();
+    delete c;
+}
+
+uint64_t kmu_count_capacity(const kmu_counter* c) { return c ? c->capacity : 0; }
+
+int32_t kmu_count_insert_seqs(kmu_ctx* ctx, kmu_counter* c, const kmu_seqbatch* b, int32_t canonical) {
+    if (!ctx || !c || !b) return fail(KMU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    if (b->nseq == 0) return KMU_OK;
+    kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    CUDA_TRY(kmu::launch_count_insert_seqs(v, b->packed_bytes, c->k, c->key64, canonical != 0, c->view(), ctx->sm_count,
+                                           ctx->stream));
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    ctx->launches += 1;
+    ctx->last.launches = 1;
+    int32_t rc = check_overflow(ctx, c);
+    cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    if (rc) return rc;
+    for (uint64_t L : b->h_nbases) c->inserted += L >= c->k ? L - c->k + 1 : 0;
+    return KMU_OK;
+}
+
+int32_t kmu_count_insert_kmers(kmu_ctx* ctx, kmu_counter* c, const void* kmers, uint64_t n, int32_t on_device) {
+    if (!ctx || !c || (n && !kmers)) return fail(KMU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    if (n == 0) return KMU_OK;
+    const size_t esz = c->key64 ? 8 : 4;
+    const void* d = kmers;
+    if (!on_device) {
+        CUDA_TRY(ctx->misc.reserve(n * esz));
+        cudaEventRecord(ctx->ev[2], ctx->stream);
+        CUDA_TRY(cudaMemcpyAsync(ctx->misc.p, kmers, n * esz, cudaMemcpyHostToDevice, ctx->stream));
+        cudaEventRecord(ctx->ev[3], ctx->stream);
+        ctx->last.h2d_bytes = n * esz;
+        d = ctx->misc.p;
+    }
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    CUDA_TRY(kmu::launch_count_insert_keys(d, n, c->key64, c->view(), ctx->sm_count, ctx->stream));
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    ctx->launches += 1;
+    ctx->last.launches = 1;
+    int32_t rc = check_overflow(ctx, c);
+    cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    if (!on_device) cudaEventElapsedTime(&ctx->last.h2d_ms, ctx->ev[2], ctx->ev[3]);
+    if (rc) return rc;
+    c->inserted += n;
+    return KMU_OK;
+}
+
+int32_t kmu_count_query(kmu_ctx* ctx, const kmu_counter* c, const void* kmers, uint64_t n, uint32_t* counts,
+                        int32_t on_device) {
+    if (!ctx || !c || (n && (!kmers || !counts))) return fail(KMU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    if (n == 0) return KMU_OK;
+    const size_t esz = c->key64 ? 8 : 4;
+    const void* dk = kmers;
+    uint32_t* dc = counts;
+    if (!on_device) {
+        CUDA_TRY(ctx->misc.reserve(n * (esz + 4) + 16));
+        CUDA_TRY(cudaMemcpyAsync(ctx->misc.p, kmers, n * esz, cudaMemcpyHostToDevice, ctx->stream));
+        dk = ctx->misc.p;
+        dc = (uint32_t*)((uint8_t*)ctx->misc.p + align_up(n * esz, 16));
+    }
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    CUDA_TRY(kmu::launch_count_query(dk, n, c->key64, c->view(), c->max_count(), dc, ctx->sm_count, ctx->stream));
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    ctx->launches += 1;
+    ctx->last.launches = 1;
+    if (!on_device) CUDA_TRY(cudaMemcpyAsync(counts, dc, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    return KMU_OK;
+}
+
+int32_t kmu_count_stats(kmu_ctx* ctx, const kmu_counter* c, uint64_t* nb_distinct, uint64_t* nb_unique,
+                        uint64_t* nb_inserted, uint64_t* hist256) {
+    if (!ctx || !c) return fail(KMU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    unsigned long long* stats = (unsigned long long*)c->aux.p + 8;
+    CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(unsigned long long) * (3 + 256), ctx->stream));
+    CUDA_TRY(kmu::launch_count_stats(c->view(), c->key64, stats, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    std::vector<unsigned long long> h(3 + 256);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), stats, sizeof(unsigned long long) * (3 + 256), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint64_t distinct = 0;
+    for (int i = 1; i < 256; ++i) distinct += h[3 + i];
+    if (nb_distinct) *nb_distinct = distinct;
+    if (nb_unique) *nb_unique = h[3 + 1];
+    if (nb_inserted) *nb_inserted = h[2];
+    if (hist256)
+        for (int i = 0; i < 256; ++i) hist256[i] = h[3 + i];
+    return KMU_OK;
+}
+
+int32_t kmu_count_export(kmu_ctx* ctx, const kmu_counter* c, uint32_t min_count, void* kmers, uint32_t* counts,
+                         uint64_t cap, uint64_t* n_out) {
+    if (!ctx || !c || !n_out || (cap && (!kmers || !counts))) return fail(KMU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    const size_t esz = c->key64 ? 8 : 4;
+    unsigned long long* cursor = (unsigned long long*)c->aux.p + 2;
+    CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), ctx->stream));
+    CUDA_TRY(ctx->misc.reserve(cap * (esz + 4) + 32));
+    void* dk = ctx->misc.p;
+    uint32_t* dc = (uint32_t*)((uint8_t*)ctx->misc.p + align_up(cap * esz, 16));
+    CUDA_TRY(kmu::launch_count_export(c->view(), c->key64, min_count, dk, dc, cursor, cap, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    unsigned long long n = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n, cursor, sizeof(n), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    // the u64 key equal to the empty sentinel lives outside the table
+    unsigned long long special = 0;
+    if (c->key64) CUDA_TRY(cudaMemcpy(&special, c->aux.p, sizeof(special), cudaMemcpyDeviceToHost));
+    const uint64_t take = std::min<uint64_t>(n, cap);
+    if (take) {
+        CUDA_TRY(cudaMemcpyAsync(kmers, dk, take * esz, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(counts, dc, take * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    uint64_t total = n;
+    if (special >= min_count && special > 0) {
+        if (total < cap) {
+            ((uint64_t*)kmers)[total] = ~0ULL;
+            counts[total] = special > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)special;
+        }
+        ++total;
+    }
+    *n_out = total;
+    if (total > cap) return fail(KMU_EOVERFLOW, "%llu k-mers to export, buffer holds %llu", (unsigned long long)total,
+                                 (unsigned long long)cap);
+    return KMU_OK;
+}
+
+int32_t kmu_count_partition(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t canonical,
+                            uint32_t nparts, void* kmers_out, uint64_t* part_counts, int32_t out_on_device) {
+    if (!ctx || !b || !part_counts) return fail(KMU_EINVAL, "null argument");
+    if (!kmer_type_accepts(k, kmer_type))
+        return fail(KMU_EINVAL, "kmer size %u is not supported by kmer type %d", k, kmer_type);
+    if (nparts < 1 || nparts > 64) return fail(KMU_EINVAL, "nparts must be in 1..64, got %u", nparts);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    for (uint32_t p = 0; p < nparts; ++p) part_counts[p] = 0;
+    uint64_t total = 0;
+    for (uint64_t L : b->h_nbases) total += L >= k ? L - k + 1 : 0;
+    if (total == 0) return KMU_OK;
+    if (!kmers_out) return fail(KMU_EINVAL, "null output buffer");
+    const bool key64 = kmer_type == KMU_KMER64;
+    const size_t esz = key64 ? 8 : 4;
+    const int grid = kmu::count_partition_grid(b->packed_bytes, ctx->sm_count);
+    CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * ((size_t)nparts * grid + 64)));
+    unsigned long long* block_counts = (unsigned long long*)ctx->counters.p;
+    unsigned long long* part_totals = block_counts + (size_t)nparts * grid;
+    void* dout = kmers_out;
+    if (!out_on_device) {
+        CUDA_TRY(ctx->sig_dev.reserve(total * esz));
+        dout = ctx->sig_dev.p;
+    }
+    kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    CUDA_TRY(kmu::launch_count_partition(v, b->packed_bytes, k, key64, canonical != 0, nparts, grid, block_counts,
+                                         part_totals, dout, ctx->stream));
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    ctx->launches += 3;
+    ctx->last.launches = 3;
+    std::vector<unsigned long long> pt(nparts);
+    CUDA_TRY(cudaMemcpyAsync(pt.data(), part_totals, sizeof(unsigned long long) * nparts, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!out_on_device) {
+        CUDA_TRY(cudaMemcpyAsync(kmers_out, dout, total * esz, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->last.d2h_bytes = total * esz;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    for (uint32_t p = 0; p < nparts; ++p) part_counts[p] = pt[p];
+    return KMU_OK;
+}
+
+}  // extern "C"

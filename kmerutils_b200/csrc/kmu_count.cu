@@ -1,0 +1,392 @@
+// kmu_count.cu -- exact k-mer multiplicity counting on sm_100a.
+//
+// Replaces KmerCounter (cuckoo filter for "seen once" + counting Bloom filter for "seen at least
+// twice", src/base/kmercount.rs:70-83,241-288) and its drivers count_kmer /
+// count_kmer_threaded_one_to_many (:293-362, :881-974) by ONE open-addressing table in HBM:
+// the key is kmer.get_compressed_value() of the canonical k-mer (kmer.reverse_complement().min(kmer),
+// :313,827,938), claimed with atomicCAS and counted with atomicAdd.  get_count / nb_distinct /
+// nb_unique are what the reference returns when its filters have no false positive.
+//
+// Layout (see DESIGN.md "counting table"):
+//   u32 k-mer types (Kmer32bit, Kmer16b32bit): 8-byte slot  key << 32 | count ; 0 == empty
+//   u64 k-mer type  (Kmer64bit)              : 16-byte slot {key, count}     ; key == ~0 == empty
+//     (the one key equal to the sentinel, 32 T's inserted non-canonically, is counted apart)
+// Work decomposition: the packed batch is cut into 64-byte chunks (256 bases); a thread owns the
+// k-mers that START in its chunk, finds the sequence(s) overlapping it by binary search in the
+// batch's byte offsets and rolls forward / reverse-complement windows in registers.
+#include <cstdint>
+
+#include "kmu_device.cuh"
+#include "kmu_kernels.h"
+
+namespace kmu {
+
+constexpr uint32_t CHUNK_BYTES = 64;
+
+__device__ __forceinline__ uint64_t fmix64(uint64_t h) {
+    h ^= h >> 33;
+    h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 33;
+    h *= 0xc4ceb9fe1a85ec53ULL;
+    h ^= h >> 33;
+    return h;
+}
+
+template <typename V>
+struct CountOps;
+
+template <>
+struct CountOps<uint32_t> {
+    static __device__ __forceinline__ bool insert(const CountTable& t, uint32_t key, uint32_t add) {
+        unsigned long long* tab = (unsigned long long*)t.slots;
+        uint64_t i = fmix64(key) & t.capmask;
+        for (uint64_t probe = 0; probe <= t.capmask; ++probe) {
+            unsigned long long e = *(volatile unsigned long long*)(tab + i);
+            if (e == 0) {
+                unsigned long long old = atomicCAS(tab + i, 0ULL, ((unsigned long long)key << 32) | add);
+                if (old == 0) return true;
+                e = old;
+            }
+            if ((uint32_t)(e >> 32) == key) {
+                unsigned long long old = atomicAdd(tab + i, (unsigned long long)add);
+                if ((uint32_t)old + (uint64_t)add >= 0xFFFFFFF0ull) atomicAdd(tab + i, (unsigned long long)(-(long long)add));  // saturate
+                return true;
+            }
+            i = (i + 1) & t.capmask;
+        }
+        return false;
+    }
+    static __device__ __forceinline__ uint32_t lookup(const CountTable& t, uint32_t key) {
+        const unsigned long long* tab = (const unsigned long long*)t.slots;
+        uint64_t i = fmix64(key) & t.capmask;
+        for (uint64_t probe = 0; probe <= t.capmask; ++probe) {
+            unsigned long long e = __ldg(tab + i);
+            if (e == 0) return 0;
+            if ((uint32_t)(e >> 32) == key) return (uint32_t)e;
+            i = (i + 1) & t.capmask;
+        }
+        return 0;
+    }
+    static __device__ __forceinline__ bool occupied(const CountTable& t, uint64_t i, uint64_t& key, uint64_t& cnt) {
+        unsigned long long e = ((const unsigned long long*)t.slots)[i];
+        key = e >> 32;
+        cnt = (uint32_t)e;
+        return e != 0;
+    }
+};
+
+template <>
+struct CountOps<uint64_t> {
+    static constexpr unsigned long long EMPTY = ~0ULL;
+    static __device__ __forceinline__ bool insert(const CountTable& t, uint64_t key, uint32_t add) {
+        if (key == EMPTY) {
+            atomicAdd(t.special, (unsigned long long)add);
+            return true;
+        }
+        unsigned long long* tab = (unsigned long long*)t.slots;
+        uint64_t i = fmix64(key) & t.capmask;
+        for (uint64_t probe = 0; probe <= t.capmask; ++probe) {
+            unsigned long long cur = *(volatile unsigned long long*)(tab + 2 * i);
+            if (cur == EMPTY) {
+                cur = atomicCAS(tab + 2 * i, EMPTY, (unsigned long long)key);
+                if (cur == EMPTY) cur = key;
+            }
+            if (cur == key) {
+                atomicAdd(tab + 2 * i + 1, (unsigned long long)add);
+                return true;
+            }
+            i = (i + 1) & t.capmask;
+        }
+        return false;
+    }
+    static __device__ __forceinline__ uint32_t lookup(const CountTable& t, uint64_t key) {
+        if (key == EMPTY) {
+            unsigned long long c = *t.special;
+            return c > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c;
+        }
+        const unsigned long long* tab = (const unsigned long long*)t.slots;
+        uint64_t i = fmix64(key) & t.capmask;
+        for (uint64_t probe = 0; probe <= t.capmask; ++probe) {
+            const ulonglong2 e = __ldg((const ulonglong2*)(tab + 2 * i));
+            if (e.x == EMPTY) return 0;
+            if (e.x == key) return e.y > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)e.y;
+            i = (i + 1) & t.capmask;
+        }
+        return 0;
+    }
+    static __device__ __forceinline__ bool occupied(const CountTable& t, uint64_t i, uint64_t& key, uint64_t& cnt) {
+        const ulonglong2 e = ((const ulonglong2*)t.slots)[i];
+        key = e.x;
+        cnt = e.y;
+        return e.x != EMPTY;
+    }
+};
+
+__global__ void count_init_kernel(CountTable t, int key64) {
+    const uint64_t n = t.capmask + 1;
+    if (key64) {
+        ulonglong2* s = (ulonglong2*)t.slots;
+        for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+            s[i] = make_ulonglong2(~0ULL, 0ULL);
+    } else {
+        unsigned long long* s = (unsigned long long*)t.slots;
+        for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+            s[i] = 0ULL;
+    }
+}
+
+// last sequence s with byte_off[s] <= byte (byte_off ascending, byte_off[0] == 0)
+__device__ __forceinline__ uint64_t seq_of_byte(const uint64_t* __restrict__ byte_off, uint64_t nseq, uint64_t byte) {
+    uint64_t lo = 0, hi = nseq;
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (__ldg(byte_off + mid) <= byte) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Calls f(compressed canonical-or-forward value) for every k-mer that starts inside chunk `c`.
+template <typename V, typename F>
+__device__ __forceinline__ void for_each_kmer_in_chunk(const SeqView& b, uint64_t total_bytes, uint64_t c, uint32_t k,
+                                                       bool canonical, F&& f) {
+    const uint64_t byte0 = c * CHUNK_BYTES;
+    const uint64_t byte1 = min(byte0 + (uint64_t)CHUNK_BYTES, total_bytes);
+    uint64_t s = seq_of_byte(b.byte_off, b.nseq, byte0);
+    while (s < b.nseq) {
+        const uint64_t sb = __ldg(b.byte_off + s);
+        if (sb >= byte1) break;
+        const uint64_t L = __ldg(b.nbases + s);
+        const uint64_t nk = L >= k ? L - k + 1 : 0;
+        const uint64_t p_lo = byte0 > sb ? (byte0 - sb) * 4 : 0;
+        const uint64_t p_hi = min(nk, (byte1 - sb) * 4);
+        if (p_lo < p_hi) {
+            KmerWalker<V> wk;
+            wk.start((const uint32_t*)(b.packed + sb), p_lo, k);
+            for (uint64_t p = p_lo; p < p_hi; ++p) {
+                wk.roll();
+                f(wk.prekey(canonical));
+            }
+        }
+        ++s;
+    }
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256) count_insert_seqs_kernel(SeqView b, uint64_t total_bytes, uint32_t k, int canonical,
+                                                                 CountTable t) {
+    const uint64_t nchunks = (total_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES;
+    bool ok = true;
+    for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < nchunks; c += (uint64_t)gridDim.x * blockDim.x)
+        for_each_kmer_in_chunk<V>(b, total_bytes, c, k, canonical != 0, [&](V key) { ok &= CountOps<V>::insert(t, key, 1u); });
+    if (!ok) *t.overflow = 1ULL;
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256) count_insert_keys_kernel(const V* __restrict__ keys, uint64_t n, CountTable t) {
+    bool ok = true;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        ok &= CountOps<V>::insert(t, keys[i], 1u);
+    if (!ok) *t.overflow = 1ULL;
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256) count_query_kernel(const V* __restrict__ keys, uint64_t n, CountTable t,
+                                                           uint32_t max_count, uint32_t* __restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t c = CountOps<V>::lookup(t, keys[i]);
+        out[i] = c < max_count ? c : max_count;
+    }
+}
+
+// stats[0] = distinct, stats[1] = unique, stats[2] = total multiplicity, stats[3 + c] = #keys with min(count, 255) == c
+template <typename V>
+__global__ void __launch_bounds__(256) count_stats_kernel(CountTable t, unsigned long long* stats) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long tot;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    if (threadIdx.x == 0) tot = 0;
+    __syncthreads();
+    const uint64_t n = t.capmask + 1;
+    unsigned long long mytot = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t key, cnt;
+        if (CountOps<V>::occupied(t, i, key, cnt)) {
+            atomicAdd(&hist[cnt < 255 ? (uint32_t)cnt : 255u], 1u);
+            mytot += cnt;
+        }
+    }
+    if (sizeof(V) == 8 && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long c = *t.special;
+        if (c) {
+            atomicAdd(&hist[c < 255 ? (uint32_t)c : 255u], 1u);
+            mytot += c;
+        }
+    }
+    atomicAdd(&tot, mytot);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (hist[i]) atomicAdd(stats + 3 + i, (unsigned long long)hist[i]);
+    if (threadIdx.x == 0 && tot) atomicAdd(stats + 2, tot);
+}
+
+// compacts the occupied slots into (keys, counts) -- the iteration of a counter (dump of the multiple k-mers)
+template <typename V>
+__global__ void __launch_bounds__(256) count_export_kernel(CountTable t, uint32_t min_count, V* __restrict__ keys,
+                                                            uint32_t* __restrict__ counts, unsigned long long* cursor,
+                                                            uint64_t cap) {
+    const uint64_t n = t.capmask + 1;
+    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x; i0 < n; i0 += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = i0 + threadIdx.x;
+        uint64_t key = 0, cnt = 0;
+        bool take = i < n && CountOps<V>::occupied(t, i, key, cnt) && cnt >= min_count;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, take);
+        uint64_t base = 0;
+        const int lane = threadIdx.x & 31;
+        if (lane == 0 && bal) base = atomicAdd(cursor, (unsigned long long)__popc(bal));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (take) {
+            const uint64_t pos = base + __popc(bal & ((1u << lane) - 1));
+            if (pos < cap) {
+                keys[pos] = (V)key;
+                counts[pos] = cnt > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cnt;
+            }
+        }
+    }
+}
+
+// ---- partition by owner: DispatchableT::dispatch (kmercount.rs:382-420) -------------------------
+// owner = intNN_hash(compressed canonical value) % nparts.  Two walks: (A) every block counts its
+// k-mers per owner into block_counts[part][block]; an exclusive scan of that matrix (part major)
+// gives every block its private output ranges; (B) the block recomputes the keys and writes them.
+constexpr int MAX_PARTS = 64;
+
+template <typename V>
+__device__ __forceinline__ uint32_t owner_of(V key, uint32_t nparts) {
+    return (uint32_t)(inv_hash(key) % (V)nparts);
+}
+
+template <typename V, bool WRITE>
+__global__ void __launch_bounds__(256) count_partition_kernel(SeqView b, uint64_t total_bytes, uint32_t k, int canonical,
+                                                               uint32_t nparts, unsigned long long* block_counts,
+                                                               V* __restrict__ out) {
+    __shared__ unsigned long long cur[MAX_PARTS];
+    for (int p = threadIdx.x; p < MAX_PARTS; p += blockDim.x)
+        cur[p] = (WRITE && (uint32_t)p < nparts) ? block_counts[(size_t)p * gridDim.x + blockIdx.x] : 0ULL;
+    __syncthreads();
+    const uint64_t nchunks = (total_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES;
+    // a block owns contiguous tiles of blockDim.x chunks so that both walks see the same k-mers
+    for (uint64_t tile = blockIdx.x; tile * blockDim.x < nchunks; tile += gridDim.x) {
+        const uint64_t c = tile * blockDim.x + threadIdx.x;
+        if (c < nchunks)
+            for_each_kmer_in_chunk<V>(b, total_bytes, c, k, canonical != 0, [&](V key) {
+                const uint32_t p = owner_of<V>(key, nparts);
+                const unsigned long long pos = atomicAdd(&cur[p], 1ULL);
+                if (WRITE) out[pos] = key;
+            });
+    }
+    if (!WRITE) {
+        __syncthreads();
+        for (int p = threadIdx.x; p < (int)nparts; p += blockDim.x) block_counts[(size_t)p * gridDim.x + blockIdx.x] = cur[p];
+    }
+}
+
+// exclusive scan of block_counts (nparts * nblocks entries, part major) in place; part_totals[p] = sum of part p
+__global__ void count_partition_scan_kernel(unsigned long long* block_counts, uint32_t nparts, uint32_t nblocks,
+                                            unsigned long long* part_totals) {
+    // one thread per part computes its row sum, then thread 0 chains the parts (nparts <= 64, nblocks ~ 1e3)
+    __shared__ unsigned long long tot[MAX_PARTS];
+    const uint32_t p = threadIdx.x;
+    if (p < nparts) {
+        unsigned long long s = 0;
+        for (uint32_t j = 0; j < nblocks; ++j) s += block_counts[(size_t)p * nblocks + j];
+        tot[p] = s;
+        part_totals[p] = s;
+    }
+    __syncthreads();
+    if (p < nparts) {
+        unsigned long long base = 0;
+        for (uint32_t q = 0; q < p; ++q) base += tot[q];
+        for (uint32_t j = 0; j < nblocks; ++j) {
+            unsigned long long v = block_counts[(size_t)p * nblocks + j];
+            block_counts[(size_t)p * nblocks + j] = base;
+            base += v;
+        }
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------
+static int grid_for(uint64_t work_items, int block, int sm_count, int per_sm) {
+    uint64_t want = (work_items + block - 1) / block;
+    uint64_t cap = (uint64_t)sm_count * per_sm;
+    return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+cudaError_t launch_count_init(const CountTable& t, bool key64, int sm_count, cudaStream_t st) {
+    count_init_kernel<<<grid_for(t.capmask + 1, 256, sm_count, 16), 256, 0, st>>>(t, key64 ? 1 : 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count_insert_seqs(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
+                                     const CountTable& t, int sm_count, cudaStream_t st) {
+    if (b.nseq == 0 || total_bytes == 0) return cudaSuccess;
+    const uint64_t nchunks = (total_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES;
+    const int grid = grid_for(nchunks, 256, sm_count, 8);
+    if (key64) count_insert_seqs_kernel<uint64_t><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, t);
+    else count_insert_seqs_kernel<uint32_t><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, t);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count_insert_keys(const void* keys, uint64_t n, bool key64, const CountTable& t, int sm_count,
+                                     cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const int grid = grid_for(n, 256, sm_count, 8);
+    if (key64) count_insert_keys_kernel<uint64_t><<<grid, 256, 0, st>>>((const uint64_t*)keys, n, t);
+    else count_insert_keys_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)keys, n, t);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count_query(const void* keys, uint64_t n, bool key64, const CountTable& t, uint32_t max_count,
+                               uint32_t* out, int sm_count, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const int grid = grid_for(n, 256, sm_count, 8);
+    if (key64) count_query_kernel<uint64_t><<<grid, 256, 0, st>>>((const uint64_t*)keys, n, t, max_count, out);
+    else count_query_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)keys, n, t, max_count, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count_stats(const CountTable& t, bool key64, unsigned long long* stats, int sm_count, cudaStream_t st) {
+    const int grid = grid_for(t.capmask + 1, 256, sm_count, 8);
+    if (key64) count_stats_kernel<uint64_t><<<grid, 256, 0, st>>>(t, stats);
+    else count_stats_kernel<uint32_t><<<grid, 256, 0, st>>>(t, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count_export(const CountTable& t, bool key64, uint32_t min_count, void* keys, uint32_t* counts,
+                                unsigned long long* cursor, uint64_t cap, int sm_count, cudaStream_t st) {
+    const int grid = grid_for(t.capmask + 1, 256, sm_count, 8);
+    if (key64) count_export_kernel<uint64_t><<<grid, 256, 0, st>>>(t, min_count, (uint64_t*)keys, counts, cursor, cap);
+    else count_export_kernel<uint32_t><<<grid, 256, 0, st>>>(t, min_count, (uint32_t*)keys, counts, cursor, cap);
+    return cudaGetLastError();
+}
+
+int count_partition_grid(uint64_t total_bytes, int sm_count) {
+    const uint64_t nchunks = (total_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES;
+    return grid_for(nchunks, 256, sm_count, 4);
+}
+
+cudaError_t launch_count_partition(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
+                                   uint32_t nparts, int grid, unsigned long long* block_counts,
+                                   unsigned long long* part_totals, void* out, cudaStream_t st) {
+    if (key64) {
+        count_partition_kernel<uint64_t, false><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, nparts, block_counts, nullptr);
+        count_partition_scan_kernel<<<1, MAX_PARTS, 0, st>>>(block_counts, nparts, (uint32_t)grid, part_totals);
+        count_partition_kernel<uint64_t, true><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, nparts, block_counts, (uint64_t*)out);
+    } else {
+        count_partition_kernel<uint32_t, false><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, nparts, block_counts, nullptr);
+        count_partition_scan_kernel<<<1, MAX_PARTS, 0, st>>>(block_counts, nparts, (uint32_t)grid, part_totals);
+        count_partition_kernel<uint32_t, true><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, nparts, block_counts, (uint32_t*)out);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace kmu

@@ -1,0 +1,145 @@
+// kmu_host.h -- host-side internals shared by the C-ABI translation units: error reporting,
+// growable device / pinned buffers, the context and the sequence batch.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/kmerutils_b200.h"
+#include "kmu_kernels.h"
+
+// sets the calling thread's last-error message (kmu_last_error) and returns `code`
+int32_t kmu_fail(int32_t code, const char* fmt, ...);
+#define fail kmu_fail
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) return fail(KMU_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+constexpr size_t SMEM_BUDGET = 227 * 1024 - 1024;  // opt-in shared memory per CTA on sm_100 minus static use
+constexpr size_t SEQ_ALIGN = 16;
+constexpr size_t TAIL_SLACK = 64;
+
+// growable device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// double-buffered host <-> device pipeline of the one-shot host entry points
+struct HostPipe {
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t in_begin[2]{}, in_done[2]{}, compute_done[2]{}, out_begin[2]{}, out_done[2]{};
+    DevBuf packed[2], meta[2], sig[2];
+    PinnedBuf stage[2], meta_host[2];
+};
+
+struct kmu_ctx {
+    HostPipe pipe;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    uint64_t launches = 0;
+    kmu_times last{};
+    cudaEvent_t ev[6]{};  // k0 k1 h0 h1 d0 d1
+    int sm_count = 148;
+    // scratch
+    DevBuf order, counters, table_scratch, slot_scratch, overflow, sig_dev, misc;
+    bool table_scratch_clean = false;
+    PinnedBuf pinned;
+    // first-point table of the ProbMinHash3a kernels (small key spaces), see kmu_pmh3a.cu
+    DevBuf memo;
+    uint32_t memo_k = 0, memo_m = 0;
+    int memo_type = -1, memo_hash = -1;
+    // optional per-launch profile of the last sketch call
+    bool profiling = false;
+    std::vector<cudaEvent_t> lev;
+    std::vector<kmu_launch_rec> lrec;
+};
+
+// processing order of a batch for the sketch kernels (longest sequences first), per k
+struct OrderCache {
+    uint32_t k = 0;
+    std::vector<unsigned long long> hist, cursor;
+    uint64_t nk_longest = 0;
+    DevBuf order;
+};
+
+struct kmu_seqbatch {
+    mutable OrderCache order_cache;
+    int device = 0;
+    uint8_t* packed = nullptr;
+    uint64_t* byte_off = nullptr;
+    uint64_t* nbases = nullptr;
+    uint64_t nseq = 0;
+    uint64_t packed_bytes = 0;  // without the tail slack
+    uint64_t total_bases = 0;
+    bool owns = true;           // false: the buffers belong to a context arena
+    std::vector<uint64_t> h_nbases;
+    std::vector<uint64_t> h_byte_off;
+};
+
+struct ScopedDevice {
+    int prev = -1;
+    explicit ScopedDevice(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~ScopedDevice() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// does the k-mer type accept this k? (the reference panics otherwise)
+inline bool kmer_type_accepts(uint32_t k, int type) {
+    switch (type) {
+        case KMU_KMER32: return k >= 1 && k <= 14;   // src/base/kmergenerator.rs:311, kmer32bit.rs:68-76
+        case KMU_KMER16B32: return k == 16;          // src/base/kmergenerator.rs:218-220
+        case KMU_KMER64: return k >= 1 && k <= 32;   // src/base/kmergenerator.rs:415
+        default: return false;
+    }
+}

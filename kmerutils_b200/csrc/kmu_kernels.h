@@ -108,4 +108,28 @@ cudaError_t launch_generate_kmers(const SeqView& b, uint32_t k, int kmer_type, i
 cudaError_t launch_nthash(const SeqView& b, uint32_t k, uint32_t n_multi, const uint64_t* out_off, uint64_t* out_hash,
                           uint8_t* out_strand, cudaStream_t stream);
 
+// ---- counting table (kmu_count.cu) ----------------------------------------------------------
+struct CountTable {
+    void* slots;                  // u32 keys: u64 slot (key << 32 | count); u64 keys: 16-byte slot {key, count}
+    uint64_t capmask;             // capacity - 1 (capacity is a power of two)
+    unsigned long long* special;  // multiplicity of the one u64 key equal to the empty sentinel
+    unsigned long long* overflow; // set to 1 when an insertion found no free slot
+};
+cudaError_t launch_count_init(const CountTable& t, bool key64, int sm_count, cudaStream_t st);
+cudaError_t launch_count_insert_seqs(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
+                                     const CountTable& t, int sm_count, cudaStream_t st);
+cudaError_t launch_count_insert_keys(const void* keys, uint64_t n, bool key64, const CountTable& t, int sm_count,
+                                     cudaStream_t st);
+cudaError_t launch_count_query(const void* keys, uint64_t n, bool key64, const CountTable& t, uint32_t max_count,
+                               uint32_t* out, int sm_count, cudaStream_t st);
+// stats: 3 + 256 counters {distinct (unused here), unique (unused here), total multiplicity, hist[min(count,255)]}
+cudaError_t launch_count_stats(const CountTable& t, bool key64, unsigned long long* stats, int sm_count, cudaStream_t st);
+cudaError_t launch_count_export(const CountTable& t, bool key64, uint32_t min_count, void* keys, uint32_t* counts,
+                                unsigned long long* cursor, uint64_t cap, int sm_count, cudaStream_t st);
+int count_partition_grid(uint64_t total_bytes, int sm_count);
+// block_counts: nparts * grid entries (scratch); part_totals: nparts entries; out: all k-mers, part major
+cudaError_t launch_count_partition(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
+                                   uint32_t nparts, int grid, unsigned long long* block_counts,
+                                   unsigned long long* part_totals, void* out, cudaStream_t st);
+
 }  // namespace kmu

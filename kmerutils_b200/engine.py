@@ -214,6 +214,98 @@ class Engine:
                                              k, kmer_type, hash_kind, m, C.c_void_p(optr)))
         return out
 
+    # ---- counting ---------------------------------------------------------------------------
+    def counter(self, k, kmer_type, capacity, count_bits=8):
+        return KmerCounter(self, k, kmer_type, capacity, count_bits)
+
+    def count_partition(self, batch, k, kmer_type, nparts, canonical=True, out_device_ptr=None):
+        """All (canonical) compressed k-mer values of the batch bucketed by DispatchableT::dispatch
+        (kmercount.rs:382-420) -> (kmers part-major, part_counts[nparts])."""
+        counts = np.zeros(nparts, dtype=np.uint64)
+        if out_device_ptr is not None:
+            check(self.lib.kmu_count_partition(self.ctx, batch.handle, k, kmer_type, int(bool(canonical)), nparts,
+                                               C.c_void_p(out_device_ptr), _p(counts, u64p), 1))
+            return None, counts
+        out = np.zeros(max(batch.kmer_count(k), 1), dtype=val_dtype(kmer_type))
+        check(self.lib.kmu_count_partition(self.ctx, batch.handle, k, kmer_type, int(bool(canonical)), nparts, _p(out),
+                                           _p(counts, u64p), 0))
+        return out[: batch.kmer_count(k)], counts
+
+
+class KmerCounter:
+    """Exact k-mer multiplicity table in HBM behind the KmerCountT interface
+    (src/base/kmercount.rs:48-59): insert_kmer / get_count / get_nb_distinct / get_nb_unique."""
+
+    def __init__(self, engine, k, kmer_type, capacity, count_bits=8):
+        self.engine = engine
+        self.k = k
+        self.kmer_type = kmer_type
+        self.count_bits = count_bits
+        h = C.c_void_p()
+        check(engine.lib.kmu_count_create(engine.ctx, k, kmer_type, count_bits, int(capacity), C.byref(h)))
+        self._h = h
+
+    @property
+    def dtype(self):
+        return val_dtype(self.kmer_type)
+
+    def capacity(self):
+        return int(self.engine.lib.kmu_count_capacity(self._h))
+
+    def insert_seqs(self, batch, canonical=True):
+        """count_kmer / count_kmer_threaded_one_to_many (kmercount.rs:293-362, 881-974)."""
+        check(self.engine.lib.kmu_count_insert_seqs(self.engine.ctx, self._h, batch.handle, int(bool(canonical))))
+
+    def insert_kmers(self, kmers=None, device_ptr=None, n=None):
+        """KmerCountT::insert_kmer for an array of compressed k-mer values (host array or device pointer)."""
+        if device_ptr is not None:
+            check(self.engine.lib.kmu_count_insert_kmers(self.engine.ctx, self._h, C.c_void_p(device_ptr), int(n), 1))
+            return
+        a = np.ascontiguousarray(kmers, dtype=self.dtype)
+        check(self.engine.lib.kmu_count_insert_kmers(self.engine.ctx, self._h, _p(a), len(a), 0))
+
+    def get_count(self, kmers):
+        a = np.ascontiguousarray(kmers, dtype=self.dtype)
+        out = np.zeros(len(a), dtype=np.uint32)
+        check(self.engine.lib.kmu_count_query(self.engine.ctx, self._h, _p(a), len(a), _p(out), 0))
+        return out
+
+    def stats(self):
+        """-> dict(nb_distinct, nb_unique, nb_inserted, hist) ; hist[c] = #k-mers with min(multiplicity, 255) == c"""
+        d, u, t = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        hist = np.zeros(256, dtype=np.uint64)
+        check(self.engine.lib.kmu_count_stats(self.engine.ctx, self._h, C.byref(d), C.byref(u), C.byref(t),
+                                              _p(hist, u64p)))
+        return {"nb_distinct": d.value, "nb_unique": u.value, "nb_inserted": t.value, "hist": hist}
+
+    def get_nb_distinct(self):
+        return self.stats()["nb_distinct"]
+
+    def get_nb_unique(self):
+        return self.stats()["nb_unique"]
+
+    def export(self, min_count=1):
+        """-> (kmers, counts) of every k-mer with multiplicity >= min_count, unordered."""
+        st = self.stats()
+        cap = int(st["hist"][max(min_count, 0):].sum()) if min_count < 256 else st["nb_distinct"]
+        kmers = np.zeros(max(cap, 1), dtype=self.dtype)
+        counts = np.zeros(max(cap, 1), dtype=np.uint32)
+        n = C.c_uint64()
+        check(self.engine.lib.kmu_count_export(self.engine.ctx, self._h, min_count, _p(kmers), _p(counts), cap,
+                                               C.byref(n)))
+        return kmers[: n.value], counts[: n.value]
+
+    def destroy(self):
+        if self._h is not None:
+            self.engine.lib.kmu_count_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
 
 _DEFAULT = {}
 
@@ -225,5 +317,5 @@ def default_engine(device=0):
     return _DEFAULT[device]
 
 
-__all__ = ["Engine", "SeqBatch", "default_engine", "val_dtype", "KMER32", "KMER16B32", "KMER64", "KMERAA32",
+__all__ = ["Engine", "SeqBatch", "KmerCounter", "default_engine", "val_dtype", "KMER32", "KMER16B32", "KMER64", "KMERAA32",
            "KMERAA64"]

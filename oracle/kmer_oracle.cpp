@@ -738,6 +738,50 @@ void orc_synth_ascii(uint64_t seed, uint64_t first_base, uint64_t nbases, uint8_
     for (uint64_t p = 0; p < nbases; ++p) ascii_out[p] = (uint8_t)DECODE2B[synth_z(seed, first_base + p) >> 62];
 }
 
+// ---------------------------------------------------------------- counting (A15) ----
+// Exact restatement of KmerCounter's meaning (kmercount.rs:241-288) with zero filter false
+// positives: the key is kmer.get_compressed_value() of the canonical k-mer
+// (kmer.reverse_complement().min(kmer), kmercount.rs:313,827,938); get_count = 0 if never
+// inserted, 1 if inserted once, else min(multiplicity, 2^nb_bits - 1) (counting Bloom saturation,
+// test kmercount.rs:1615 expects 255 for 8 bits); nb_distinct = #keys, nb_unique = #keys seen once.
+uint64_t orc_count_kmers(const uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases, uint64_t nseq, int k,
+                         int type, int canonical, uint64_t* keys_out, uint64_t* counts_out, uint64_t cap) {
+    if (!kmer_type_accepts(k, type)) return ~0ULL;
+    std::vector<uint64_t> all;
+    for (uint64_t s = 0; s < nseq; ++s) {
+        const uint8_t* p = packed + byte_off[s];
+        const uint64_t L = nbases[s];
+        if (L < (uint64_t)k) continue;
+        uint64_t val = 0;
+        for (int i = 0; i < k - 1; ++i) val = (val << 2) | base_at(p, i);
+        uint64_t word = kmer_build(val, k, type);
+        for (uint64_t q = k - 1; q < L; ++q) {
+            word = kmer_push(word, k, type, base_at(p, q));
+            uint64_t w = canonical ? apply_hash(word, k, type, ORC_HASH_CANON_RAW) : word;
+            all.push_back(kmer_compressed_value(w, type));
+        }
+    }
+    std::sort(all.begin(), all.end());
+    uint64_t n = 0;
+    for (size_t i = 0; i < all.size();) {
+        size_t j = i;
+        while (j < all.size() && all[j] == all[i]) ++j;
+        if (n < cap) {
+            keys_out[n] = all[i];
+            counts_out[n] = j - i;
+        }
+        ++n;
+        i = j;
+    }
+    return n;
+}
+
+// DispatchableT::dispatch (kmercount.rs:382-420): owner of a compressed k-mer value among nb_receiver
+uint64_t orc_dispatch(uint64_t compressed_value, int type, uint64_t nb_receiver) {
+    if (is_u32_type(type)) return (uint64_t)(int32_hash((uint32_t)compressed_value) % (uint32_t)nb_receiver);
+    return int64_hash(compressed_value) % nb_receiver;
+}
+
 int orc_hardware_threads(void) {
     unsigned n = std::thread::hardware_concurrency();
     return n ? (int)n : 1;

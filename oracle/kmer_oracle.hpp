@@ -114,6 +114,15 @@ uint64_t orc_blocksketch_seq(const uint8_t* packed, uint64_t nbases, int k, uint
                              uint64_t block_size, uint32_t* sig_out, uint64_t max_blocks);
 double orc_jaccard_equal_fraction(const void* a, const void* b, uint32_t m, int sig_bytes);
 
+// ---- A15 : counting (exact multiset semantics of KmerCounter, kmercount.rs:241-288) -----
+// distinct canonical compressed k-mer values in ascending order with their multiplicities;
+// returns the number of distinct keys (only the first `cap` are written); UINT64_MAX on a bad (k, type)
+uint64_t orc_count_kmers(const uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases,
+                         uint64_t nseq, int k, int type, int canonical, uint64_t* keys_out,
+                         uint64_t* counts_out, uint64_t cap);
+// DispatchableT::dispatch (kmercount.rs:382-420)
+uint64_t orc_dispatch(uint64_t compressed_value, int type, uint64_t nb_receiver);
+
 // ---- synthetic data ---------------------------------------------------
 // base i of stream `seed` = top 2 bits of SplitMix64 output number i (counter based)
 void orc_synth_packed(uint64_t seed, uint64_t first_base, uint64_t nbases, uint8_t* packed_out);

@@ -93,6 +93,10 @@ class Oracle:
         L.orc_blocksketch_seq.argtypes = [u8p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint64, u32p, C.c_uint64]
         L.orc_jaccard_equal_fraction.restype = C.c_double
         L.orc_jaccard_equal_fraction.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
+        L.orc_count_kmers.restype = C.c_uint64
+        L.orc_count_kmers.argtypes = [u8p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, u64p, u64p, C.c_uint64]
+        L.orc_dispatch.restype = C.c_uint64
+        L.orc_dispatch.argtypes = [C.c_uint64, C.c_int, C.c_uint64]
         L.orc_synth_packed.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, u8p]
         L.orc_synth_ascii.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, u8p]
         L.orc_hardware_threads.restype = C.c_int
@@ -200,6 +204,24 @@ class Oracle:
         assert a.dtype == b.dtype and a.shape == b.shape
         return float(self.L.orc_jaccard_equal_fraction(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
                                                        a.shape[-1], a.dtype.itemsize))
+
+    # ---- counting ----------------------------------------------------------------
+    def count_kmers(self, packed, byte_off, nbases, k, ktype, canonical=True):
+        """-> (distinct compressed canonical values ascending, multiplicities)"""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        byte_off = np.ascontiguousarray(byte_off, dtype=np.uint64)
+        nbases = np.ascontiguousarray(nbases, dtype=np.uint64)
+        cap = int(np.maximum(nbases.astype(np.int64) - k + 1, 0).sum()) + 1
+        keys = np.zeros(cap, dtype=np.uint64)
+        cnts = np.zeros(cap, dtype=np.uint64)
+        n = self.L.orc_count_kmers(_ptr(packed, u8p), _ptr(byte_off, u64p), _ptr(nbases, u64p), len(nbases), k, ktype,
+                                   int(bool(canonical)), _ptr(keys, u64p), _ptr(cnts, u64p), cap)
+        if n == 2**64 - 1:
+            raise ValueError("kmer size not supported by kmer type")
+        return keys[:n].copy(), cnts[:n].copy()
+
+    def dispatch(self, values, ktype, nb_receiver):
+        return np.array([self.L.orc_dispatch(int(v), ktype, nb_receiver) for v in values], dtype=np.uint64)
 
     # ---- synthetic ---------------------------------------------------------------
     def synth_packed(self, seed, first_base, nbases):

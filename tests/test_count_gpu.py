@@ -1,0 +1,143 @@
+"""GPU parity of the counting table against the oracle's exact multiset counts
+(KmerCounter semantics with zero filter false positives, kmercount.rs:241-288)."""
+import numpy as np
+import pytest
+
+import kmerutils_b200 as kb
+from test_pmh3a_gpu import oracle_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def genome_reads(oracle, seed, genome_len, nreads, read_len, rng):
+    """reads drawn from one random genome, random strand: overlapping reads give multiplicities > 1"""
+    g = oracle.synth_ascii(seed, 0, genome_len)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    reads = []
+    for _ in range(nreads):
+        s = int(rng.integers(0, genome_len - read_len + 1))
+        r = g[s:s + read_len]
+        if rng.integers(0, 2):
+            r = r.translate(comp)[::-1]
+        reads.append(r)
+    return reads
+
+
+@pytest.mark.parametrize("k,ktype", [(31, kb.KMER64), (21, kb.KMER64), (32, kb.KMER64), (16, kb.KMER16B32),
+                                     (12, kb.KMER32), (5, kb.KMER32)])
+def test_count_parity(engine, oracle, k, ktype):
+    rng = np.random.default_rng(k)
+    reads = genome_reads(oracle, 30 + k, 20000, 1500, 150, rng)
+    reads += [b"ACGT" * 3, b"A" * 400, b"ACGTTGCA" * 40, b"C"]  # short, homopolymer, periodic
+    batch, _ = engine.batch_from_ascii(reads)
+    packed, off, nb = batch.download()
+    keys, cnts = oracle.count_kmers(packed, off, nb, k, ktype, True)
+    ctr = engine.counter(k, ktype, capacity=len(keys), count_bits=8)
+    ctr.insert_seqs(batch, canonical=True)
+    st = ctr.stats()
+    assert st["nb_distinct"] == len(keys)
+    assert st["nb_unique"] == int((cnts == 1).sum())
+    assert st["nb_inserted"] == int(cnts.sum()) == batch.kmer_count(k)
+    got = ctr.get_count(keys)
+    assert np.array_equal(got, np.minimum(cnts, 255).astype(np.uint32))  # 8-bit saturation (kmercount.rs:1615)
+    # k-mers never inserted count 0 (kmercount.rs:1612)
+    absent = np.setdiff1d(rng.integers(0, 1 << min(2 * k, 62), 2000).astype(np.uint64), keys)
+    assert not ctr.get_count(absent).any()
+    want_hist = np.bincount(np.minimum(cnts, 255).astype(np.int64), minlength=256)
+    assert np.array_equal(st["hist"].astype(np.int64), want_hist)
+    # multiple k-mers, as dumped by threaded_dump_kmer_counter (kmercount.rs:653-791)
+    mk, mc = ctr.export(min_count=2)
+    order = np.argsort(mk)
+    sel = cnts >= 2
+    assert np.array_equal(mk[order].astype(np.uint64), keys[sel])
+    assert np.array_equal(mc[order].astype(np.uint64), cnts[sel])
+    ctr.destroy()
+
+
+def test_count_reference_semantics(engine):
+    # kmercount.rs:1523-1575: k0 inserted once, k1 twice among many others -> counts 1 and 2
+    rng = np.random.default_rng(5)
+    others = rng.integers(0, 1 << 32, 1_000_000, dtype=np.uint64).astype(np.uint32)
+    k0, k1 = np.uint32(0x12345678), np.uint32(0x0BADF00D)
+    others = others[(others != k0) & (others != k1)]
+    ctr = engine.counter(16, kb.KMER16B32, capacity=1_100_000, count_bits=8)
+    ctr.insert_kmers(np.array([k0, k1], dtype=np.uint32))
+    ctr.insert_kmers(others)
+    ctr.insert_kmers(np.array([k1], dtype=np.uint32))
+    c = ctr.get_count(np.array([k0, k1], dtype=np.uint32))
+    vals, mult = np.unique(others, return_counts=True)
+    assert c.tolist() == [1, 2]
+    st = ctr.stats()
+    assert st["nb_distinct"] == len(vals) + 2
+    assert st["nb_unique"] == int((mult == 1).sum()) + 1
+    ctr.destroy()
+
+
+def test_count_saturation(engine):
+    # kmercount.rs:1579-1621: keys of the upper half inserted many times -> 255 with 8-bit counters,
+    # the lower half stays 0
+    upper = (np.arange(1000, dtype=np.uint64) + (1 << 31)).astype(np.uint32)
+    ctr = engine.counter(16, kb.KMER16B32, capacity=4096, count_bits=8)
+    for _ in range(3):
+        ctr.insert_kmers(np.repeat(upper, 100))
+    assert (ctr.get_count(upper) == 255).all()
+    assert not ctr.get_count(np.arange(1000, dtype=np.uint32)).any()
+    ctr16 = engine.counter(16, kb.KMER16B32, capacity=4096, count_bits=16)
+    ctr16.insert_kmers(np.repeat(upper, 300))
+    assert (ctr16.get_count(upper) == 300).all()
+    ctr.destroy()
+    ctr16.destroy()
+
+
+def test_count_sentinel_key_and_overflow(engine):
+    # the u64 value ~0 (32 T's, only reachable non-canonically) is the table's empty mark: counted apart
+    ctr = engine.counter(32, kb.KMER64, capacity=1024)
+    allT = np.array([2**64 - 1] * 3 + [5, 5, 7], dtype=np.uint64)
+    ctr.insert_kmers(allT)
+    assert ctr.get_count(np.array([2**64 - 1, 5, 7, 9], dtype=np.uint64)).tolist() == [3, 2, 1, 0]
+    st = ctr.stats()
+    assert (st["nb_distinct"], st["nb_unique"], st["nb_inserted"]) == (3, 1, 6)
+    mk, mc = ctr.export(min_count=2)
+    assert sorted(zip(mk.tolist(), mc.tolist())) == [(5, 2), (2**64 - 1, 3)]
+    ctr.destroy()
+    small = engine.counter(31, kb.KMER64, capacity=16)
+    with pytest.raises(kb.KmuError) as ei:
+        small.insert_kmers(np.arange(1, 5000, dtype=np.uint64))
+    assert ei.value.code == 4  # KMU_EOVERFLOW: never degrades silently
+    small.destroy()
+
+
+def test_count_bad_arguments(engine):
+    with pytest.raises(kb.KmuInvalid):
+        engine.counter(15, kb.KMER32, 100)  # Kmer32bit holds k <= 14
+    with pytest.raises(kb.KmuInvalid):
+        engine.counter(31, kb.KMER64, 100, count_bits=0)
+
+
+@pytest.mark.parametrize("k,ktype,nparts", [(31, kb.KMER64, 8), (16, kb.KMER16B32, 2), (11, kb.KMER32, 5)])
+def test_partition_by_owner(engine, oracle, k, ktype, nparts):
+    rng = np.random.default_rng(nparts)
+    nb = rng.integers(1, 600, 300).astype(np.uint64)
+    batch = engine.batch_synth(77, nb)
+    packed, off = oracle_batch(oracle, 77, nb)
+    kmers, counts = engine.count_partition(batch, k, ktype, nparts, canonical=True)
+    assert int(counts.sum()) == len(kmers) == batch.kmer_count(k)
+    # every bucket holds exactly the k-mers DispatchableT::dispatch sends to that receiver
+    keys, cnts = oracle.count_kmers(packed, off, nb, k, ktype, True)
+    start = 0
+    seen = []
+    for p in range(nparts):
+        part = kmers[start:start + int(counts[p])].astype(np.uint64)
+        start += int(counts[p])
+        if len(part):
+            uniq = np.unique(part)
+            assert (oracle.dispatch(uniq[:200], ktype, nparts) == p).all()
+        seen.append(part)
+    allk, mult = np.unique(np.concatenate(seen), return_counts=True)
+    assert np.array_equal(allk, keys) and np.array_equal(mult.astype(np.uint64), cnts)
+    # receive side: inserting the buckets rank by rank gives the same table as inserting the sequences
+    ctr = engine.counter(k, ktype, capacity=len(keys))
+    for part in seen:
+        ctr.insert_kmers(part.astype(kb.val_dtype(ktype)))
+    assert np.array_equal(ctr.get_count(keys), np.minimum(cnts, 255).astype(np.uint32))
+    ctr.destroy()
