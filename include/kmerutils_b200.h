@@ -139,6 +139,19 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
                               const uint64_t* nbases, uint64_t nseq, uint32_t k, int32_t kmer_type, int32_t hash_kind,
                               uint32_t m, void* sig);
 
+/* ---- SuperMinHash per-sequence sketch
+ *      SeqSketcher::sketch_superminhash          src/sketching/seqsketchjaccard.rs:328-380  (key_hasher FNV, :346-349)
+ *      SuperHashSketch::sketch_compressedkmer    src/sketching/setsketchert.rs:255-296      (key_hasher NOHASH, :267-269)
+ * Every k-mer (duplicates included) is streamed through SuperMinHash::sketch; the signature is
+ * get_hsketch(): m floating point values per sequence, f32 (sig_bytes 4) or f64 (sig_bytes 8),
+ * mergeable by element-wise minimum.  A sequence without any k-mer keeps the initial value
+ * F::from(u32::MAX) in every slot. */
+#define KMU_HASHER_NOHASH 0 /* NoHashHasher  src/nohasher.rs:22-48 */
+#define KMU_HASHER_FNV 1    /* fnv::FnvHasher (FNV-1a 64 over the native-endian key bytes) */
+int32_t kmu_sketch_superminhash(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, int32_t kmer_type,
+                                int32_t hash_kind, uint32_t m, int32_t key_hasher, int32_t sig_bytes, void* sig,
+                                int32_t sig_on_device);
+
 /* ---- k-mer counting (replaces KmerCounter: cuckoo filter + counting Bloom filter,
  *      src/base/kmercount.rs:70-83) -------------------------------------------------------
  * One exact open-addressing table in HBM keyed by kmer.get_compressed_value().  Semantics are

@@ -14,6 +14,7 @@ KMU_OK, KMU_EINVAL, KMU_ECUDA, KMU_ENOMEM, KMU_EOVERFLOW = 0, 1, 2, 3, 4
 
 KMER32, KMER16B32, KMER64, KMERAA32, KMERAA64 = 0, 1, 2, 3, 4
 HASH_IDENTITY_RAW, HASH_MASKED_VALUE, HASH_CANON_INVHASH, HASH_CANON_RAW, HASH_INVHASH = 0, 1, 2, 3, 4
+HASHER_NOHASH, HASHER_FNV = 0, 1
 
 u8p = C.POINTER(C.c_uint8)
 u64p = C.POINTER(C.c_uint64)
@@ -70,6 +71,8 @@ SIGNATURES = {
                                      C.c_int32]),
     "kmu_sketch_pmh3a_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, u64p, u64p, C.c_uint64, C.c_uint32,
                                           C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
+    "kmu_sketch_superminhash": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32,
+                                            C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "kmu_count_create": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint64, vpp]),
     "kmu_count_destroy": (None, [C.c_void_p]),
     "kmu_count_capacity": (C.c_uint64, [C.c_void_p]),

@@ -206,6 +206,7 @@ void kmu_seqbatch_destroy(kmu_seqbatch* b) {
     if (!b) return;
     ScopedDevice sd(b->device);
     b->order_cache.order.release();
+    b->order_cache.cursor_dev.release();
     if (b->owns) {
         if (b->packed) cudaFree(b->packed);
         if (b->byte_off) cudaFree(b->byte_off);
@@ -583,6 +584,58 @@ Geometry make_geometry(uint64_t nk_max, int mode, uint32_t k, uint32_t m, bool k
 
 }  // namespace
 
+}  // extern "C"
+
+// processing order of a batch for the per-sequence sketch kernels: longest sequences first
+// (8 buckets per octave of the k-mer count); built once per (batch, k) and kept with the batch
+int32_t kmu_ensure_order(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, uint64_t* launches) {
+    OrderCache& oc = b->order_cache;
+    if (oc.k == k && !oc.hist.empty()) return KMU_OK;
+    cudaStream_t st = ctx->stream;
+    oc.hist.assign(kmu::LEN_BUCKETS, 0);
+    oc.cursor.assign(kmu::LEN_BUCKETS, 0);
+    oc.nk_longest = 0;
+    for (uint64_t L : b->h_nbases) {
+        const uint64_t nk = L >= k ? L - k + 1 : 0;
+        ++oc.hist[kmu::len_bucket_host(nk)];
+        oc.nk_longest = std::max(oc.nk_longest, nk);
+    }
+    unsigned long long acc = 0;
+    for (int i = 0; i < kmu::LEN_BUCKETS; ++i) {
+        oc.cursor[i] = acc;
+        acc += oc.hist[i];
+    }
+    CUDA_TRY(oc.order.reserve(sizeof(uint32_t) * (b->nseq + 1)));
+    CUDA_TRY(oc.cursor_dev.reserve(sizeof(unsigned long long) * kmu::LEN_BUCKETS));
+    CUDA_TRY(cudaMemcpyAsync(oc.cursor_dev.p, oc.cursor.data(), sizeof(unsigned long long) * kmu::LEN_BUCKETS,
+                             cudaMemcpyHostToDevice, st));
+    CUDA_TRY(kmu::launch_len_scatter(b->nbases, b->nseq, k, (unsigned long long*)oc.cursor_dev.p, (uint32_t*)oc.order.p, st));
+    if (launches) ++*launches;
+    oc.k = k;
+    return KMU_OK;
+}
+
+// octave classes of the cached order: sequences whose k-mer count lies in [2^oct, 2^(oct+1)), longest first
+std::vector<OctaveClass> kmu_octave_classes(const kmu_seqbatch* b) {
+    const OrderCache& oc = b->order_cache;
+    std::vector<OctaveClass> out;
+    for (int oct = 63; oct >= 0; --oct) {
+        int b_hi = kmu::LEN_BUCKETS - 1 - (oct * 8 + 7), b_lo = kmu::LEN_BUCKETS - 1 - oct * 8;
+        uint64_t cnt = 0;
+        for (int bb = b_hi; bb <= b_lo; ++bb) cnt += oc.hist[bb];
+        if (!cnt) continue;
+        OctaveClass c;
+        c.first = oc.cursor[b_hi];
+        c.count = cnt;
+        c.nk_max = oct == 63 ? ~0ULL : ((2ULL << oct) - 1);
+        out.push_back(c);
+    }
+    if (!out.empty()) out.front().nk_max = std::min(out.front().nk_max, oc.nk_longest);
+    return out;
+}
+
+extern "C" {
+
 static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type,
                                    int32_t hash_kind, uint32_t m, void* d_sig) {
     const bool key64 = kmer_type == KMU_KMER64;
@@ -602,28 +655,11 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     unsigned long long* d_ovf_count = d_work + 128;
     unsigned long long* d_phase = d_work + 256;  // 8 per launch, profiling only
     CUDA_TRY(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256 + 8 * 128), st));
-    OrderCache& oc = b->order_cache;
-    if (oc.k != k || oc.hist.empty()) {
-        oc.hist.assign(kmu::LEN_BUCKETS, 0);
-        oc.cursor.assign(kmu::LEN_BUCKETS, 0);
-        oc.nk_longest = 0;
-        for (uint64_t L : b->h_nbases) {
-            const uint64_t nk = L >= k ? L - k + 1 : 0;
-            ++oc.hist[kmu::len_bucket_host(nk)];
-            oc.nk_longest = std::max(oc.nk_longest, nk);
-        }
-        unsigned long long acc = 0;
-        for (int i = 0; i < kmu::LEN_BUCKETS; ++i) {
-            oc.cursor[i] = acc;
-            acc += oc.hist[i];
-        }
-        CUDA_TRY(oc.order.reserve(sizeof(uint32_t) * (nseq + 1)));
-        CUDA_TRY(cudaMemcpyAsync(d_cursor, oc.cursor.data(), sizeof(unsigned long long) * kmu::LEN_BUCKETS,
-                                 cudaMemcpyHostToDevice, st));
-        CUDA_TRY(kmu::launch_len_scatter(b->nbases, nseq, k, d_cursor, (uint32_t*)oc.order.p, st));
-        ++launches;
-        oc.k = k;
+    {
+        int32_t orc = kmu_ensure_order(ctx, b, k, &launches);
+        if (orc) return orc;
     }
+    OrderCache& oc = b->order_cache;
     (void)d_hist;
     const std::vector<unsigned long long>& hist = oc.hist;
     const std::vector<unsigned long long>& cursor = oc.cursor;

@@ -250,6 +250,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// --------------------------------------------------------------------------------
+// team = group of warps cooperating on one sequence
+// --------------------------------------------------------------------------------
+struct Team {
+    int id;      // team index inside the CTA
+    int tid;     // thread index inside the team
+    int size;    // threads in the team
+    int warp;    // warp index inside the team
+    int lane;
+    __device__ __forceinline__ void sync() const {
+        if (size == 32) {
+            __syncwarp();
+        } else {
+            // named barrier id+1 (0 is left to __syncthreads)
+            asm volatile("bar.sync %0, %1;" ::"r"(id + 1), "r"(size) : "memory");
+        }
+    }
+};
+
 // counter based SplitMix64 used by the synthetic generator
 __host__ __device__ __forceinline__ uint64_t synth_z(uint64_t seed, uint64_t i) {
     uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ULL;

@@ -102,7 +102,11 @@ struct OrderCache {
     uint32_t k = 0;
     std::vector<unsigned long long> hist, cursor;
     uint64_t nk_longest = 0;
-    DevBuf order;
+    DevBuf order, cursor_dev;
+};
+struct OctaveClass {
+    uint64_t first, count;  // range of the order array
+    uint64_t nk_max;        // largest k-mer count in the class (the last class also holds sequences without k-mers)
 };
 
 struct kmu_seqbatch {
@@ -143,3 +147,6 @@ inline bool kmer_type_accepts(uint32_t k, int type) {
         default: return false;
     }
 }
+
+int32_t kmu_ensure_order(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, uint64_t* launches);
+std::vector<OctaveClass> kmu_octave_classes(const kmu_seqbatch* b);

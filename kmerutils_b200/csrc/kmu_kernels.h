@@ -108,6 +108,29 @@ cudaError_t launch_generate_kmers(const SeqView& b, uint32_t k, int kmer_type, i
 cudaError_t launch_nthash(const SeqView& b, uint32_t k, uint32_t n_multi, const uint64_t* out_off, uint64_t* out_hash,
                           uint8_t* out_strand, cudaStream_t stream);
 
+// ---- SuperMinHash (kmu_smh.cu) ----------------------------------------------------------------
+struct SmhParams {
+    const uint8_t* packed;
+    const uint64_t* byte_off;
+    const uint64_t* nbases;
+    const uint32_t* order;
+    uint64_t first, count;
+    unsigned long long* work_counter;
+    uint32_t k;
+    int kmer_type, hash_kind;
+    uint32_t m;
+    int hasher;      // 0 NoHashHasher, 1 FnvHasher
+    void* sig;       // nseq * m values of S
+    uint32_t team_warps, team_smem_bytes;
+    double ln_term;  // ln(1e4 m)
+    unsigned long long* slow_count;
+    uint32_t* slow_list;
+    uint8_t* scratch;  // exact path
+    uint64_t scratch_per_warp;
+};
+cudaError_t launch_smh_fast(const SmhParams& P, bool key64, bool f64, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t launch_smh_exact(const SmhParams& P, bool key64, bool f64, int grid, cudaStream_t st);
+
 // ---- counting table (kmu_count.cu) ----------------------------------------------------------
 struct CountTable {
     void* slots;                  // u32 keys: u64 slot (key << 32 | count); u64 keys: 16-byte slot {key, count}

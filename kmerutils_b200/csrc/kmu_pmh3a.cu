@@ -30,25 +30,6 @@
 
 namespace kmu {
 
-// --------------------------------------------------------------------------------
-// team = group of warps cooperating on one sequence
-// --------------------------------------------------------------------------------
-struct Team {
-    int id;      // team index inside the CTA
-    int tid;     // thread index inside the team
-    int size;    // threads in the team
-    int warp;    // warp index inside the team
-    int lane;
-    __device__ __forceinline__ void sync() const {
-        if (size == 32) {
-            __syncwarp();
-        } else {
-            // named barrier id+1 (0 is left to __syncthreads)
-            asm volatile("bar.sync %0, %1;" ::"r"(id + 1), "r"(size) : "memory");
-        }
-    }
-};
-
 // ---- multiplicity stores -----------------------------------------------------------
 // u32 pre-keys: one u64 per entry = key << 32 | claimed << 31 | count ; 0 == empty
 // u64 pre-keys: 16-byte entry {key, claimed << 63 | count} ; count == 0 == empty

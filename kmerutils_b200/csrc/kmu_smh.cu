@@ -1,0 +1,296 @@
+// kmu_smh.cu -- SuperMinHash sketching on sm_100a.
+//
+// Replaces SeqSketcher::sketch_superminhash (src/sketching/seqsketchjaccard.rs:328-380, FnvHasher on the
+// key), SuperHashSketch::sketch_compressedkmer / sketch_compressedkmer_seqs
+// (src/sketching/setsketchert.rs:255-335, NoHashHasher) and sketch_seqrange_superminhash
+// (src/sketching/seqminhash.rs:19-62): every k-mer is streamed through probminhash's
+// SuperMinHash::sketch (Ertl 2017).
+//
+// GPU formulation.  Item x draws (r_j, k_j), j = 0, 1, ... from its private Xoshiro256++ stream, runs
+// an incremental Fisher-Yates shuffle (slot_j = p[j] after swapping p[j], p[k_j]) and offers the value
+// r_j + j to slot_j; the signature is the per-slot MINIMUM over all items and all j.  The sequential
+// algorithm only cuts an item's loop at j > a, where a = floor(max slot value): those points cannot
+// win.  Hence
+//   * fast path: every item evaluates j = 0 .. a_spec for a speculative a_spec derived from the k-mer
+//     count; the result is exact iff all slots end below a_spec + 1, which is verified -- sequences
+//     that fail are redone by the exact path.  For a_spec = 0 (the usual case: many more k-mers than
+//     slots) an item is one seed, two draws and one atomicMin in shared memory.
+//   * exact path (short sequences relative to m): one warp per sequence, 32 items per round with a
+//     full lazily-reset permutation per lane in global scratch, a = floor(max slot) between rounds.
+#include <cstdint>
+
+#include "kmu_device.cuh"
+#include "kmu_kernels.h"
+
+namespace kmu {
+
+template <typename S>
+struct FloatOps;
+template <>
+struct FloatOps<double> {
+    using B = unsigned long long;
+    static __device__ __forceinline__ double draw(Xoshiro256pp& rng) { return rng.unif01(); }
+    static __device__ __forceinline__ B bits(double v) { return (B)__double_as_longlong(v); }
+    static __device__ __forceinline__ double value(B b) { return __longlong_as_double((long long)b); }
+    static __device__ __forceinline__ double add(double r, uint32_t j) { return __dadd_rn(r, (double)j); }
+    static __device__ __forceinline__ B large() { return bits(4294967295.0); }  // F::from(u32::MAX)
+};
+template <>
+struct FloatOps<float> {
+    using B = unsigned int;
+    static __device__ __forceinline__ float draw(Xoshiro256pp& rng) { return rng.unif01_f32(); }
+    static __device__ __forceinline__ B bits(float v) { return __float_as_uint(v); }
+    static __device__ __forceinline__ float value(B b) { return __uint_as_float(b); }
+    static __device__ __forceinline__ float add(float r, uint32_t j) { return __fadd_rn(r, (float)j); }
+    static __device__ __forceinline__ B large() { return bits(4294967296.0f); }  // u32::MAX rounds up in f32
+};
+
+template <typename V>
+__device__ __forceinline__ uint64_t item_seed(V key, int hasher) {
+    return hasher == 0 ? nohash_seed(key) : fnv1a_seed<V>(key);
+}
+
+// Uniform::<usize>::new(low, low + range).sample (rand 0.9, 32-bit path)
+__device__ __forceinline__ uint32_t unif_from(Xoshiro256pp& rng, uint32_t low, uint32_t range) {
+    const uint32_t thresh = (0u - range) % range;
+    return rng.unif_range(low, range, thresh);
+}
+
+constexpr uint32_t SMH_FAST_MAX = 15;  // largest a_spec of the fast path (sparse permutation of <= 16 entries)
+
+// points j = 0 .. a_spec of one item against the slots h[0..m)
+template <typename S>
+__device__ __forceinline__ void smh_item_points(Xoshiro256pp& rng, uint32_t m, uint32_t a_spec,
+                                                typename FloatOps<S>::B* h) {
+    using F = FloatOps<S>;
+    using B = typename F::B;
+    if (a_spec == 0) {
+        const S r = F::draw(rng);
+        const uint32_t slot = unif_from(rng, 0, m);
+        const B vb = F::bits(r);
+        if (vb < *(volatile B*)(h + slot)) atomicMin(h + slot, vb);
+        return;
+    }
+    uint32_t idx[SMH_FAST_MAX + 1], val[SMH_FAST_MAX + 1];
+    uint32_t n = 0;
+    for (uint32_t j = 0; j <= a_spec; ++j) {
+        const S r = F::draw(rng);
+        const uint32_t kk = unif_from(rng, j, m - j);
+        uint32_t vj = j, vk = kk;
+        int pos_k = -1;
+        for (uint32_t e = 0; e < n; ++e) {
+            if (idx[e] == j) vj = val[e];
+            if (idx[e] == kk) {
+                vk = val[e];
+                pos_k = (int)e;
+            }
+        }
+        uint32_t slot = vj;
+        if (kk != j) {
+            slot = vk;  // p[j] after the swap is the old p[k]
+            if (pos_k >= 0) {
+                val[pos_k] = vj;
+            } else {
+                idx[n] = kk;
+                val[n] = vj;
+                ++n;
+            }
+        }
+        const B vb = F::bits(F::add(r, j));
+        if (vb < *(volatile B*)(h + slot)) atomicMin(h + slot, vb);
+    }
+}
+
+struct SmhTeamShared {
+    uint32_t seq, nbases, valid, flag;
+    uint64_t byte_off;
+};
+
+template <typename V, typename S>
+__global__ void __launch_bounds__(1024, 1) smh_fast_kernel(const SmhParams P) {
+    using F = FloatOps<S>;
+    using B = typename F::B;
+    extern __shared__ __align__(16) uint8_t smem[];
+    Team team;
+    team.size = P.team_warps * 32;
+    team.id = threadIdx.x / team.size;
+    team.tid = threadIdx.x - team.id * team.size;
+    team.warp = team.tid >> 5;
+    team.lane = threadIdx.x & 31;
+    uint8_t* tbase = smem + (size_t)team.id * P.team_smem_bytes;
+    B* h = (B*)tbase;
+    SmhTeamShared* ts = (SmhTeamShared*)(tbase + (((size_t)P.m * sizeof(B) + 15) & ~(size_t)15));
+    const V header = (V)word_header(P.kmer_type, P.k);
+    const bool canonical = hash_is_canonical(P.hash_kind);
+    const uint32_t k = P.k, m = P.m;
+
+    for (;;) {
+        team.sync();  // the previous sequence's shared state is no longer read
+        if (team.tid == 0) {
+            const unsigned long long w = atomicAdd(P.work_counter, 1ULL);
+            ts->valid = w < P.count;
+            if (w < P.count) {
+                const uint32_t seq = P.order[P.first + w];
+                ts->seq = seq;
+                ts->nbases = (uint32_t)P.nbases[seq];
+                ts->byte_off = P.byte_off[seq];
+            }
+            ts->flag = 0;
+        }
+        team.sync();
+        if (!ts->valid) break;
+        const uint32_t seq = ts->seq, L = ts->nbases;
+        const uint32_t* words = (const uint32_t*)(P.packed + ts->byte_off);
+        const uint32_t nk = L >= k ? L - k + 1 : 0;
+        // speculative loop bound: with a_spec + 1 points per item every slot is hit except with
+        // probability ~1e-4 when (a_spec + 1) nk >= m ln(1e4 m)
+        uint32_t a_spec = 0;
+        if (nk) {
+            const double need = (double)m / (double)nk * P.ln_term;
+            const uint32_t a1 = need >= (double)m ? m : (uint32_t)ceil(need);
+            a_spec = (a1 < 1 ? 1 : a1) - 1;
+        }
+        if (a_spec > SMH_FAST_MAX) {  // short sequence: exact path
+            if (team.tid == 0) P.slow_list[atomicAdd(P.slow_count, 1ULL)] = seq;
+            continue;
+        }
+        for (uint32_t j = team.tid; j < m; j += team.size) h[j] = F::large();
+        team.sync();
+        const uint32_t ntasks = (nk + 15) >> 4;
+        for (uint32_t task = team.tid; task < ntasks; task += team.size) {
+            TaskKmers<V> tk;
+            uint32_t p = task << 4;
+            tk.init(words, p, k);
+            const uint32_t pend = min(p + 16, nk);
+#pragma unroll 1
+            for (uint32_t t = 0; p < pend; ++t, ++p) {
+                const V key = finalize_key<V>(tk.get(t, canonical), header, P.hash_kind);
+                Xoshiro256pp rng;
+                rng.seed(item_seed<V>(key, P.hasher));
+                smh_item_points<S>(rng, m, a_spec, h);
+            }
+        }
+        team.sync();
+        S* out = (S*)P.sig + (size_t)seq * m;
+        const S bound = (S)(a_spec + 1);
+        bool bad = false;
+        for (uint32_t j = team.tid; j < m; j += team.size) {
+            const S v = F::value(h[j]);
+            out[j] = v;
+            bad |= !(v < bound);
+        }
+        if (bad && nk) ts->flag = 1;
+        team.sync();
+        if (team.tid == 0 && ts->flag) P.slow_list[atomicAdd(P.slow_count, 1ULL)] = seq;  // speculation failed
+    }
+}
+
+// exact path: one warp per sequence
+template <typename V, typename S>
+__global__ void __launch_bounds__(32) smh_exact_kernel(const SmhParams P) {
+    using F = FloatOps<S>;
+    using B = typename F::B;
+    const int lane = threadIdx.x;
+    const uint32_t k = P.k, m = P.m;
+    const V header = (V)word_header(P.kmer_type, P.k);
+    const bool canonical = hash_is_canonical(P.hash_kind);
+    // scratch of this warp: h[m] (B), then per lane p[m], q[m] (u32)
+    uint8_t* base = P.scratch + (size_t)blockIdx.x * P.scratch_per_warp;
+    B* h = (B*)base;
+    uint32_t* pl = (uint32_t*)(base + (((size_t)m * sizeof(B) + 15) & ~(size_t)15)) + (size_t)lane * 2 * m;
+    uint32_t* ql = pl + m;
+    uint32_t stamp = 0;  // q is zeroed before the launch; stamps only grow
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(P.work_counter, 1ULL);
+        w = __shfl_sync(0xFFFFFFFFu, w, 0);
+        if (w >= P.count) break;
+        const uint32_t seq = P.order[P.first + w];
+        const uint32_t L = (uint32_t)P.nbases[seq];
+        const uint32_t* words = (const uint32_t*)(P.packed + P.byte_off[seq]);
+        const uint32_t nk = L >= k ? L - k + 1 : 0;
+        for (uint32_t j = lane; j < m; j += 32) h[j] = F::large();
+        __syncwarp();
+        uint32_t a_cur = m - 1;
+        for (uint32_t p0 = 0; p0 < nk; p0 += 32) {
+            const uint32_t pos = p0 + lane;
+            if (pos < nk) {
+                KmerWalker<V> wk;
+                wk.start(words, pos, k);
+                wk.roll();
+                const V key = finalize_key<V>(wk.prekey(canonical), header, P.hash_kind);
+                Xoshiro256pp rng;
+                rng.seed(item_seed<V>(key, P.hasher));
+                ++stamp;
+                for (uint32_t j = 0; j <= a_cur; ++j) {
+                    const S r = F::draw(rng);
+                    const uint32_t kk = unif_from(rng, j, m - j);
+                    if (ql[j] != stamp) {
+                        ql[j] = stamp;
+                        pl[j] = j;
+                    }
+                    if (ql[kk] != stamp) {
+                        ql[kk] = stamp;
+                        pl[kk] = kk;
+                    }
+                    const uint32_t t = pl[j];
+                    pl[j] = pl[kk];
+                    pl[kk] = t;
+                    const uint32_t slot = pl[j];
+                    const B vb = F::bits(F::add(r, j));
+                    if (vb < *(volatile B*)(h + slot)) atomicMin(h + slot, vb);
+                }
+            } else {
+                ++stamp;
+            }
+            __syncwarp();
+            // a = floor(max slot value), capped at m - 1 (the sequential a_upper)
+            B mx = 0;
+            for (uint32_t j = lane; j < m; j += 32) {
+                const B v = *(volatile B*)(h + j);
+                mx = v > mx ? v : mx;
+            }
+            for (int o = 16; o; o >>= 1) {
+                const B other = __shfl_xor_sync(0xFFFFFFFFu, mx, o);
+                mx = other > mx ? other : mx;
+            }
+            const double top = (double)F::value(mx);
+            a_cur = top >= (double)(m - 1) ? m - 1 : (uint32_t)top;
+            __syncwarp();
+        }
+        S* out = (S*)P.sig + (size_t)seq * m;
+        for (uint32_t j = lane; j < m; j += 32) out[j] = F::value(h[j]);
+        __syncwarp();
+    }
+}
+
+template <typename V, typename S>
+static cudaError_t launch_fast(const SmhParams& P, int grid, int block, size_t smem, cudaStream_t st) {
+    auto kern = smh_fast_kernel<V, S>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kern<<<grid, block, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_smh_fast(const SmhParams& P, bool key64, bool f64, int grid, int block, size_t smem, cudaStream_t st) {
+    if (key64) return f64 ? launch_fast<uint64_t, double>(P, grid, block, smem, st) : launch_fast<uint64_t, float>(P, grid, block, smem, st);
+    return f64 ? launch_fast<uint32_t, double>(P, grid, block, smem, st) : launch_fast<uint32_t, float>(P, grid, block, smem, st);
+}
+
+cudaError_t launch_smh_exact(const SmhParams& P, bool key64, bool f64, int grid, cudaStream_t st) {
+    if (key64) {
+        if (f64) smh_exact_kernel<uint64_t, double><<<grid, 32, 0, st>>>(P);
+        else smh_exact_kernel<uint64_t, float><<<grid, 32, 0, st>>>(P);
+    } else {
+        if (f64) smh_exact_kernel<uint32_t, double><<<grid, 32, 0, st>>>(P);
+        else smh_exact_kernel<uint32_t, float><<<grid, 32, 0, st>>>(P);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace kmu

@@ -201,6 +201,21 @@ class Engine:
         check(self.lib.kmu_sketch_pmh3a(self.ctx, batch.handle, k, kmer_type, hash_kind, m, _p(out), 0))
         return out
 
+    def sketch_superminhash(self, batch, k, kmer_type, hash_kind=HASH_CANON_INVHASH, m=200, key_hasher=_lib.HASHER_NOHASH,
+                            dtype=np.float64, out_device_ptr=None):
+        """SuperMinHash signature per sequence -> (nseq, m) array of f32 / f64 (get_hsketch())."""
+        dtype = np.dtype(dtype)
+        if dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise ValueError("SuperMinHash signatures are f32 or f64")
+        if out_device_ptr is not None:
+            check(self.lib.kmu_sketch_superminhash(self.ctx, batch.handle, k, kmer_type, hash_kind, m, key_hasher,
+                                                   dtype.itemsize, C.c_void_p(out_device_ptr), 1))
+            return None
+        out = np.zeros((len(batch), m), dtype=dtype)
+        check(self.lib.kmu_sketch_superminhash(self.ctx, batch.handle, k, kmer_type, hash_kind, m, key_hasher,
+                                               dtype.itemsize, _p(out), 0))
+        return out
+
     def sketch_pmh3a_host(self, packed, byte_off, nbases, k, kmer_type, hash_kind, m, out):
         """One-shot: host packed buffer in, host signatures out (H2D + kernels + D2H)."""
         off = _as_u64(byte_off)

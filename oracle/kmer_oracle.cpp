@@ -459,6 +459,82 @@ void sketch_from_map(const FlatCountMap& wb, uint32_t m, int key_bytes, uint64_t
     pmh3a(keys.data(), w.data(), keys.size(), m, key_bytes, sig);
 }
 
+// ---------------------------------------------------------------- SuperMinHash ----
+// probminhash::superminhasher::SuperMinHash<F, T, H> (Ertl 2017), restated from the
+// published algorithm.  hsketch starts at F::from(u32::MAX) ("large"), q = -1, b[m-1] = m, a = m-1.
+template <typename S>
+struct SuperMinHashOrc {
+    uint32_t m;
+    std::vector<S> h;
+    std::vector<int64_t> q;
+    std::vector<uint32_t> p;
+    std::vector<int64_t> b;
+    int64_t item_rank = 0;
+    uint32_t a_upper;
+    explicit SuperMinHashOrc(uint32_t m_) : m(m_), h(m_, (S)4294967295.0), q(m_, -1), p(m_, 0), b(m_, 0), a_upper(m_ - 1) {
+        b[m - 1] = m;
+    }
+    static inline S unif01(Xoshiro256pp& rng);
+    void sketch(uint64_t seed) {
+        Xoshiro256pp rng(seed);
+        const int64_t irank = item_rank;
+        uint32_t j = 0;
+        while (j <= a_upper) {
+            const S r = unif01(rng);
+            const uint32_t k = rng.unif_range_u32(j, m - j);  // Uniform::<usize>::new(j, m)
+            if (q[j] != irank) {
+                q[j] = irank;
+                p[j] = j;
+            }
+            if (q[k] != irank) {
+                q[k] = irank;
+                p[k] = k;
+            }
+            std::swap(p[j], p[k]);
+            const S rpj = r + (S)j;
+            if (rpj < h[p[j]]) {
+                const double cur = (double)h[p[j]];
+                const uint32_t j2 = cur >= (double)(m - 1) ? m - 1 : (uint32_t)cur;
+                h[p[j]] = rpj;
+                if (j < j2) {
+                    b[j2] -= 1;
+                    b[j] += 1;
+                    while (b[a_upper] == 0) --a_upper;
+                }
+            }
+            ++j;
+        }
+        ++item_rank;
+    }
+};
+template <>
+inline double SuperMinHashOrc<double>::unif01(Xoshiro256pp& rng) { return rng.unif01(); }
+template <>
+inline float SuperMinHashOrc<float>::unif01(Xoshiro256pp& rng) { return rng.unif01_f32(); }
+
+template <typename S>
+void superminhash_seqs(const uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases, uint64_t nseq, int k,
+                       int type, int hash_kind, uint32_t m, int hasher, S* out) {
+    SuperMinHashOrc<S> smh(m);
+    const int key_bytes = is_u32_type(type) ? 4 : 8;
+    if (kmer_type_accepts(k, type)) {
+        for (uint64_t s = 0; s < nseq; ++s) {
+            const uint8_t* pk = packed + byte_off[s];
+            const uint64_t L = nbases[s];
+            if (L < (uint64_t)k) continue;
+            uint64_t val = 0;
+            for (int i = 0; i < k - 1; ++i) val = (val << 2) | base_at(pk, i);
+            uint64_t word = kmer_build(val, k, type);
+            for (uint64_t q = k - 1; q < L; ++q) {
+                word = kmer_push(word, k, type, base_at(pk, q));
+                const uint64_t key = apply_hash(word, k, type, hash_kind);
+                smh.sketch(hasher == 0 ? nohash_seed(key, key_bytes) : fnv1a_seed(key, key_bytes));
+            }
+        }
+    }
+    for (uint32_t j = 0; j < m; ++j) out[j] = smh.h[j];
+}
+
 }  // namespace
 
 // ================================================================= C API =========
@@ -780,6 +856,36 @@ uint64_t orc_count_kmers(const uint8_t* packed, const uint64_t* byte_off, const 
 uint64_t orc_dispatch(uint64_t compressed_value, int type, uint64_t nb_receiver) {
     if (is_u32_type(type)) return (uint64_t)(int32_hash((uint32_t)compressed_value) % (uint32_t)nb_receiver);
     return int64_hash(compressed_value) % nb_receiver;
+}
+
+// SuperMinHash of one group of sequences (nseq = 1: SeqSketcher::sketch_superminhash /
+// SuperHashSketch::sketch_compressedkmer per sequence, seqsketchjaccard.rs:328-380, setsketchert.rs:255-296;
+// nseq > 1: SuperHashSketch::sketch_compressedkmer_seqs, setsketchert.rs:299-335).
+// hasher: 0 = NoHashHasher (setsketchert.rs:267-269), 1 = fnv::FnvHasher (seqsketchjaccard.rs:346-349)
+// sig_bytes: 4 = f32, 8 = f64
+void orc_sketch_superminhash(const uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases, uint64_t nseq, int k,
+                             int type, int hash_kind, uint32_t m, int hasher, int sig_bytes, void* out) {
+    if (sig_bytes == 4) superminhash_seqs<float>(packed, byte_off, nbases, nseq, k, type, hash_kind, m, hasher, (float*)out);
+    else superminhash_seqs<double>(packed, byte_off, nbases, nseq, k, type, hash_kind, m, hasher, (double*)out);
+}
+
+void orc_sketch_superminhash_batch(const uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases, uint64_t nseq,
+                                   int k, int type, int hash_kind, uint32_t m, int hasher, int sig_bytes, void* out,
+                                   int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<uint64_t> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            uint64_t i = next.fetch_add(1);
+            if (i >= nseq) break;
+            orc_sketch_superminhash(packed, byte_off + i, nbases + i, 1, k, type, hash_kind, m, hasher, sig_bytes,
+                                    (uint8_t*)out + i * (uint64_t)m * sig_bytes);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
 }
 
 int orc_hardware_threads(void) {

@@ -114,6 +114,16 @@ uint64_t orc_blocksketch_seq(const uint8_t* packed, uint64_t nbases, int k, uint
                              uint64_t block_size, uint32_t* sig_out, uint64_t max_blocks);
 double orc_jaccard_equal_fraction(const void* a, const void* b, uint32_t m, int sig_bytes);
 
+// ---- A12 : SuperMinHash (probminhash::superminhasher, Ertl 2017; PARITY UNPINNED) ---------
+// one sketch over a group of nseq sequences; hasher 0 = NoHashHasher, 1 = FnvHasher; sig_bytes 4 = f32, 8 = f64
+void orc_sketch_superminhash(const uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases,
+                             uint64_t nseq, int k, int type, int hash_kind, uint32_t m, int hasher,
+                             int sig_bytes, void* out);
+// one sketch per sequence (rayon analogue), out: nseq * m values
+void orc_sketch_superminhash_batch(const uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases,
+                                   uint64_t nseq, int k, int type, int hash_kind, uint32_t m, int hasher,
+                                   int sig_bytes, void* out, int nthreads);
+
 // ---- A15 : counting (exact multiset semantics of KmerCounter, kmercount.rs:241-288) -----
 // distinct canonical compressed k-mer values in ascending order with their multiplicities;
 // returns the number of distinct keys (only the first `cap` are written); UINT64_MAX on a bad (k, type)

@@ -93,6 +93,10 @@ class Oracle:
         L.orc_blocksketch_seq.argtypes = [u8p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint64, u32p, C.c_uint64]
         L.orc_jaccard_equal_fraction.restype = C.c_double
         L.orc_jaccard_equal_fraction.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
+        L.orc_sketch_superminhash.argtypes = [u8p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int,
+                                              C.c_int, C.c_void_p]
+        L.orc_sketch_superminhash_batch.argtypes = [u8p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint32,
+                                                    C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orc_count_kmers.restype = C.c_uint64
         L.orc_count_kmers.argtypes = [u8p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, u64p, u64p, C.c_uint64]
         L.orc_dispatch.restype = C.c_uint64
@@ -204,6 +208,28 @@ class Oracle:
         assert a.dtype == b.dtype and a.shape == b.shape
         return float(self.L.orc_jaccard_equal_fraction(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
                                                        a.shape[-1], a.dtype.itemsize))
+
+    def sketch_superminhash_batch(self, packed, byte_off, nbases, k, ktype, kind, m, hasher=0, dtype=np.float64,
+                                  nthreads=0):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        byte_off = np.ascontiguousarray(byte_off, dtype=np.uint64)
+        nbases = np.ascontiguousarray(nbases, dtype=np.uint64)
+        out = np.zeros((len(nbases), m), dtype=dtype)
+        if nthreads <= 0:
+            nthreads = self.hardware_threads()
+        self.L.orc_sketch_superminhash_batch(_ptr(packed, u8p), _ptr(byte_off, u64p), _ptr(nbases, u64p), len(nbases), k,
+                                             ktype, kind, m, hasher, out.dtype.itemsize,
+                                             out.ctypes.data_as(C.c_void_p), nthreads)
+        return out
+
+    def sketch_superminhash_seqs(self, packed, byte_off, nbases, k, ktype, kind, m, hasher=0, dtype=np.float64):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        byte_off = np.ascontiguousarray(byte_off, dtype=np.uint64)
+        nbases = np.ascontiguousarray(nbases, dtype=np.uint64)
+        out = np.zeros(m, dtype=dtype)
+        self.L.orc_sketch_superminhash(_ptr(packed, u8p), _ptr(byte_off, u64p), _ptr(nbases, u64p), len(nbases), k, ktype,
+                                       kind, m, hasher, out.dtype.itemsize, out.ctypes.data_as(C.c_void_p))
+        return out
 
     # ---- counting ----------------------------------------------------------------
     def count_kmers(self, packed, byte_off, nbases, k, ktype, canonical=True):

@@ -234,3 +234,44 @@ def test_pmh3a_short_sequence_is_all_zero(oracle):
     # 0 < L < k: empty multiplicity map, signature = m copies of Val::default()
     sig = _sig(oracle, b"ACGTA", 8, ol.KMER32, ol.HASH_CANON_INVHASH, 200)
     assert not sig.any()
+
+
+# ---- SuperMinHash on the oracle: reference inequalities (seqsketchjaccard.rs:947-1005, seqminhash.rs:193-250) ----
+def _smh(oracle, seq, k, ktype, kind, m, hasher, dtype=np.float64):
+    packed = oracle.pack_2bit(seq)
+    return oracle.sketch_superminhash_batch(packed, np.zeros(1, np.uint64), np.array([len(seq)], np.uint64), k, ktype,
+                                            kind, m, hasher, dtype)[0]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("hasher", [0, 1])
+def test_superminhash_reference_inequalities(oracle, hasher, dtype):
+    k, ktype, m = 16, ol.KMER16B32, 50
+    a = _smh(oracle, S80, k, ktype, ol.HASH_CANON_INVHASH, m, hasher, dtype)
+    half = _smh(oracle, S80[:40], k, ktype, ol.HASH_CANON_INVHASH, m, hasher, dtype)
+    rc = _smh(oracle, _revcomp_str(S80), k, ktype, ol.HASH_CANON_INVHASH, m, hasher, dtype)
+    assert np.mean(a == half) >= 0.75 * (40 - k) / (80 - k)
+    assert np.mean(a == rc) >= 1.0
+    ia = _smh(oracle, S80, k, ktype, ol.HASH_IDENTITY_RAW, m, hasher, dtype)
+    irc = _smh(oracle, _revcomp_str(S80), k, ktype, ol.HASH_IDENTITY_RAW, m, hasher, dtype)
+    assert np.mean(ia == irc) <= 0.1
+
+
+def test_superminhash_properties(oracle):
+    # idempotent (a duplicated sequence changes nothing), order independent, mergeable by min
+    s1, s2 = S80[:50], S80[30:]
+    p1, p2 = oracle.pack_2bit(s1), oracle.pack_2bit(s2)
+    buf = np.zeros(64, np.uint8)
+    buf[:len(p1)] = p1
+    buf[32:32 + len(p2)] = p2
+    off = np.array([0, 32], np.uint64)
+    nb = np.array([len(s1), len(s2)], np.uint64)
+    both = oracle.sketch_superminhash_seqs(buf, off, nb, 8, ol.KMER32, ol.HASH_CANON_INVHASH, 64)
+    rev = oracle.sketch_superminhash_seqs(buf, off[::-1].copy(), nb[::-1].copy(), 8, ol.KMER32, ol.HASH_CANON_INVHASH, 64)
+    each = oracle.sketch_superminhash_batch(buf, off, nb, 8, ol.KMER32, ol.HASH_CANON_INVHASH, 64)
+    assert np.array_equal(both, rev)
+    assert np.array_equal(both, each.min(axis=0))
+    assert (both < 64).all() and (both >= 0).all()
+    # no k-mer at all: the initial value F::from(u32::MAX)
+    empty = _smh(oracle, b"ACG", 8, ol.KMER32, ol.HASH_CANON_INVHASH, 16, 0)
+    assert (empty == 4294967295.0).all()
