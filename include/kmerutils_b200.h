@@ -93,6 +93,16 @@ int32_t kmu_seqbatch_from_ascii(kmu_ctx* ctx, const uint8_t* ascii, const uint64
 /* synthetic uniform ACGT reads generated on the device (bench / tests):
  * base j of sequence i = top 2 bits of SplitMix64 output (first_base[i] + j) of stream `seed`. */
 int32_t kmu_seqbatch_synth(kmu_ctx* ctx, uint64_t seed, const uint64_t* nbases, uint64_t nseq, kmu_seqbatch** batch);
+/* amino-acid sequences: SequenceAA (src/aautils/kmeraa.rs:404-456), one ASCII residue per byte in,
+ * 5-bit codes (Alphabet::encode, :85-109) in HBM.  drop_invalid != 0 is SequenceAA::new_filtered
+ * (:447-456); otherwise any residue outside "ACDEFGHIKLMNPQRSTVWY" fails with KMU_EINVAL (the
+ * reference panics in Alphabet::encode, :106).  Use with KMU_KMERAA32 (k <= 6) / KMU_KMERAA64 (k <= 12). */
+int32_t kmu_seqbatch_from_aa(kmu_ctx* ctx, const uint8_t* ascii, const uint64_t* ascii_off, uint64_t nseq,
+                             int32_t drop_invalid, uint64_t* invalid_counts, kmu_seqbatch** batch);
+/* synthetic proteins: residue j of sequence i = "ACDEFGHIKLMNPQRSTVWY"[z % 20] */
+int32_t kmu_seqbatch_synth_aa(kmu_ctx* ctx, uint64_t seed, const uint64_t* nres, uint64_t nseq, kmu_seqbatch** batch);
+/* 0 = DNA (2 bits / base), 1 = amino acids (one 5-bit code per byte) */
+int32_t kmu_seqbatch_alphabet(const kmu_seqbatch* batch);
 void kmu_seqbatch_destroy(kmu_seqbatch* batch);
 uint64_t kmu_seqbatch_nseq(const kmu_seqbatch* batch);
 uint64_t kmu_seqbatch_total_bases(const kmu_seqbatch* batch);

@@ -123,6 +123,102 @@ cudaError_t launch_pack_ascii(const uint8_t* ascii, const uint64_t* ascii_off, c
     return cudaGetLastError();
 }
 
+// ---- amino-acid sequences (src/aautils/kmeraa.rs) ---------------------------------------------
+// Alphabet::encode (kmeraa.rs:85-109): 20 upper-case residues -> 5-bit codes (14 is skipped); 0 = invalid
+__device__ __forceinline__ uint32_t encode_aa(uint8_t c) {
+    switch (c) {
+        case 'A': return 1; case 'C': return 2; case 'D': return 3; case 'E': return 4; case 'F': return 5;
+        case 'G': return 6; case 'H': return 7; case 'I': return 8; case 'K': return 9; case 'L': return 10;
+        case 'M': return 11; case 'N': return 12; case 'P': return 13; case 'Q': return 15; case 'R': return 16;
+        case 'S': return 17; case 'T': return 18; case 'V': return 19; case 'W': return 20; case 'Y': return 21;
+        default: return 0;
+    }
+}
+
+__global__ void aa_count_invalid_kernel(const uint8_t* __restrict__ ascii, const uint64_t* __restrict__ ascii_off,
+                                        uint64_t nseq, uint64_t* invalid) {
+    uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    int lane = threadIdx.x & 31;
+    for (uint64_t s = warp; s < nseq; s += nwarps) {
+        uint64_t b = ascii_off[s], e = ascii_off[s + 1];
+        uint32_t bad = 0;
+        for (uint64_t i = b + lane; i < e; i += 32) bad += encode_aa(ascii[i]) == 0;
+        bad = __reduce_add_sync(0xFFFFFFFFu, bad);
+        if (lane == 0) invalid[s] = bad;
+    }
+}
+
+// one warp per sequence; valid residues are compacted (SequenceAA::new_filtered, kmeraa.rs:447-456) and
+// stored as one code per byte
+__global__ void aa_encode_kernel(const uint8_t* __restrict__ ascii, const uint64_t* __restrict__ ascii_off,
+                                 const uint64_t* __restrict__ byte_off, uint64_t nseq, uint8_t* codes) {
+    uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    int lane = threadIdx.x & 31;
+    for (uint64_t s = warp; s < nseq; s += nwarps) {
+        uint64_t b = ascii_off[s], e = ascii_off[s + 1];
+        uint8_t* dst = codes + byte_off[s];
+        uint64_t kept = 0;
+        for (uint64_t i0 = b; i0 < e; i0 += 32) {
+            uint64_t i = i0 + lane;
+            uint32_t code = i < e ? encode_aa(ascii[i]) : 0u;
+            uint32_t bal = __ballot_sync(0xFFFFFFFFu, code != 0);
+            if (code) dst[kept + __popc(bal & ((1u << lane) - 1))] = (uint8_t)code;
+            kept += __popc(bal);
+        }
+    }
+}
+
+cudaError_t launch_aa_count_invalid(const uint8_t* ascii, const uint64_t* ascii_off, uint64_t nseq, uint64_t* invalid,
+                                    cudaStream_t stream) {
+    if (nseq == 0) return cudaSuccess;
+    uint64_t want = (nseq * 32 + 255) / 256;
+    int grid = (int)(want < 148ull * 8 ? want : 148ull * 8);
+    aa_count_invalid_kernel<<<grid, 256, 0, stream>>>(ascii, ascii_off, nseq, invalid);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_aa_encode(const uint8_t* ascii, const uint64_t* ascii_off, const uint64_t* byte_off, uint64_t nseq,
+                             uint8_t* codes, cudaStream_t stream) {
+    if (nseq == 0) return cudaSuccess;
+    uint64_t want = (nseq * 32 + 255) / 256;
+    int grid = (int)(want < 148ull * 8 ? want : 148ull * 8);
+    aa_encode_kernel<<<grid, 256, 0, stream>>>(ascii, ascii_off, byte_off, nseq, codes);
+    return cudaGetLastError();
+}
+
+// synthetic proteins: residue j of sequence i = "ACDEFGHIKLMNPQRSTVWY"[z % 20],
+// z = SplitMix64 output first_res[i] + j of stream `seed`
+__global__ void synth_aa_kernel(uint8_t* codes, const uint64_t* __restrict__ byte_off, const uint64_t* __restrict__ nres,
+                                const uint64_t* __restrict__ first_res, uint64_t nseq, uint64_t total_bytes,
+                                uint64_t seed) {
+    for (uint64_t byte = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; byte < total_bytes;
+         byte += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t lo = 0, hi = nseq;
+        while (hi - lo > 1) {
+            uint64_t mid = (lo + hi) >> 1;
+            if (byte_off[mid] <= byte) lo = mid; else hi = mid;
+        }
+        const uint64_t p = byte - byte_off[lo];
+        uint32_t code = 0;
+        if (p < nres[lo]) {
+            const uint32_t r = (uint32_t)(synth_z(seed, first_res[lo] + p) % 20u);
+            code = r < 13 ? r + 1 : r + 2;  // codes 1..13, 15..21
+        }
+        codes[byte] = (uint8_t)code;
+    }
+}
+
+cudaError_t launch_synth_aa(uint8_t* codes, const uint64_t* byte_off, const uint64_t* nres, const uint64_t* first_res,
+                            uint64_t nseq, uint64_t total_bytes, uint64_t seed, cudaStream_t stream) {
+    if (total_bytes == 0 || nseq == 0) return cudaSuccess;
+    uint64_t want = (total_bytes + 255) / 256;
+    int grid = (int)(want < 148ull * 16 ? want : 148ull * 16);
+    synth_aa_kernel<<<grid, 256, 0, stream>>>(codes, byte_off, nres, first_res, nseq, total_bytes, seed);
+    return cudaGetLastError();
+}
+
 // ---- length classes ---------------------------------------------------------------------------
 __device__ __forceinline__ int len_bucket(uint64_t nk) {
     if (nk == 0) return LEN_BUCKETS - 1;

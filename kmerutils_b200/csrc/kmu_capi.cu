@@ -35,25 +35,40 @@ int32_t kmu_fail(int32_t code, const char* fmt, ...) {
 }
 #define fail kmu_fail
 
+int32_t kmu_check_kmer_args(const kmu_seqbatch* b, uint32_t k, int kmer_type, int hash_kind) {
+    if (kmer_type < KMU_KMER32 || kmer_type > KMU_KMERAA64) return fail(KMU_EINVAL, "unknown kmer type %d", kmer_type);
+    if (!kmer_type_accepts(k, kmer_type))
+        return fail(KMU_EINVAL, "KmerSeqIterator cannot support kmer size %u for kmer type %d", k, kmer_type);
+    if (hash_kind < 0 || hash_kind > KMU_HASH_INVHASH) return fail(KMU_EINVAL, "unknown hash kind %d", hash_kind);
+    const bool aa = kmer_type_is_aa(kmer_type);
+    if (b && aa != (b->alphabet == 1))
+        return fail(KMU_EINVAL, "kmer type %d does not match the alphabet of the batch (%s)", kmer_type,
+                    b->alphabet ? "amino acids" : "DNA");
+    if (aa && (hash_kind == KMU_HASH_CANON_INVHASH || hash_kind == KMU_HASH_CANON_RAW))
+        return fail(KMU_EINVAL, "amino-acid k-mers have no reverse complement (kmeraa.rs:185-187 panics)");
+    return KMU_OK;
+}
+
 namespace {
 
 // byte layout of a batch: every sequence on a 16-byte boundary
-uint64_t layout_offsets(const uint64_t* nbases, uint64_t nseq, std::vector<uint64_t>& off) {
+uint64_t layout_offsets(const uint64_t* nbases, uint64_t nseq, std::vector<uint64_t>& off, int alphabet = 0) {
     off.resize(nseq);
     uint64_t cur = 0;
     for (uint64_t i = 0; i < nseq; ++i) {
         off[i] = cur;
-        cur += align_up((nbases[i] + 3) / 4, SEQ_ALIGN);
+        cur += align_up(alphabet ? nbases[i] : (nbases[i] + 3) / 4, SEQ_ALIGN);
     }
     return cur;
 }
 
-int32_t batch_alloc(kmu_ctx* ctx, const uint64_t* nbases, uint64_t nseq, kmu_seqbatch** out) {
+int32_t batch_alloc(kmu_ctx* ctx, const uint64_t* nbases, uint64_t nseq, kmu_seqbatch** out, int alphabet = 0) {
     auto* b = new kmu_seqbatch();
     b->device = ctx->device;
     b->nseq = nseq;
+    b->alphabet = alphabet;
     b->h_nbases.assign(nbases, nbases + nseq);
-    b->packed_bytes = layout_offsets(nbases, nseq, b->h_byte_off);
+    b->packed_bytes = layout_offsets(nbases, nseq, b->h_byte_off, alphabet);
     for (uint64_t i = 0; i < nseq; ++i) b->total_bases += nbases[i];
     cudaError_t e = cudaMalloc((void**)&b->packed, b->packed_bytes + TAIL_SLACK);
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->byte_off, sizeof(uint64_t) * (nseq + 1));
@@ -385,6 +400,112 @@ int32_t kmu_seqbatch_from_ascii(kmu_ctx* ctx, const uint8_t* ascii, const uint64
     return KMU_OK;
 }
 
+// SequenceAA (src/aautils/kmeraa.rs:404-456): residues are validated and encoded to their 5-bit
+// codes once, on the GPU.  drop_invalid != 0 is SequenceAA::new_filtered (:447-456); otherwise a
+// residue outside the 20-letter upper-case alphabet fails the call (the reference panics in
+// Alphabet::encode as soon as a k-mer reaches it, :106).
+int32_t kmu_seqbatch_from_aa(kmu_ctx* ctx, const uint8_t* ascii, const uint64_t* ascii_off, uint64_t nseq,
+                             int32_t drop_invalid, uint64_t* invalid_counts, kmu_seqbatch** out) {
+    if (!ctx || !out || (nseq && (!ascii || !ascii_off))) return fail(KMU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    const uint64_t total_ascii = nseq ? ascii_off[nseq] : 0;
+    DevBuf d_ascii, d_off, d_bad;
+    auto cleanup = [&]() {
+        d_ascii.release();
+        d_off.release();
+        d_bad.release();
+    };
+    cudaError_t e = d_ascii.reserve(total_ascii + 16);
+    if (e == cudaSuccess) e = d_off.reserve(sizeof(uint64_t) * (nseq + 1));
+    if (e == cudaSuccess) e = d_bad.reserve(sizeof(uint64_t) * (nseq + 1));
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(KMU_ENOMEM, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    if (total_ascii) e = cudaMemcpyAsync(d_ascii.p, ascii, total_ascii, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_off.p, ascii_off, sizeof(uint64_t) * (nseq + 1), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = kmu::launch_aa_count_invalid((const uint8_t*)d_ascii.p, (const uint64_t*)d_off.p, nseq, (uint64_t*)d_bad.p,
+                                         ctx->stream);
+    std::vector<uint64_t> bad(nseq), nb(nseq);
+    if (e == cudaSuccess && nseq)
+        e = cudaMemcpyAsync(bad.data(), d_bad.p, sizeof(uint64_t) * nseq, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(KMU_ECUDA, "amino-acid upload / validation failed: %s", cudaGetErrorString(e));
+    }
+    ctx->launches += 1;
+    uint64_t nbad_total = 0;
+    for (uint64_t i = 0; i < nseq; ++i) {
+        nbad_total += bad[i];
+        nb[i] = ascii_off[i + 1] - ascii_off[i] - bad[i];
+    }
+    if (invalid_counts) std::copy(bad.begin(), bad.end(), invalid_counts);
+    if (!drop_invalid && nbad_total) {
+        cleanup();
+        return fail(KMU_EINVAL, "encode: not a code in alphabet for amino acid: %llu invalid residues",
+                    (unsigned long long)nbad_total);
+    }
+    kmu_seqbatch* b = nullptr;
+    int32_t rc = batch_alloc(ctx, nb.data(), nseq, &b, 1);
+    if (rc) {
+        cleanup();
+        return rc;
+    }
+    rc = batch_upload_meta(ctx, b);
+    e = cudaMemsetAsync(b->packed, 0, b->packed_bytes + TAIL_SLACK, ctx->stream);
+    if (e == cudaSuccess)
+        e = kmu::launch_aa_encode((const uint8_t*)d_ascii.p, (const uint64_t*)d_off.p, b->byte_off, nseq, b->packed,
+                                  ctx->stream);
+    ctx->launches += 1;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (e != cudaSuccess || rc) {
+        kmu_seqbatch_destroy(b);
+        return rc ? rc : fail(KMU_ECUDA, "amino-acid encoding failed: %s", cudaGetErrorString(e));
+    }
+    ctx->last.h2d_bytes = total_ascii + sizeof(uint64_t) * (nseq + 1);
+    ctx->last.launches = 2;
+    *out = b;
+    return KMU_OK;
+}
+
+int32_t kmu_seqbatch_synth_aa(kmu_ctx* ctx, uint64_t seed, const uint64_t* nres, uint64_t nseq, kmu_seqbatch** out) {
+    if (!ctx || !out || (nseq && !nres)) return fail(KMU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    kmu_seqbatch* b = nullptr;
+    int32_t rc = batch_alloc(ctx, nres, nseq, &b, 1);
+    if (rc) return rc;
+    rc = batch_upload_meta(ctx, b);
+    std::vector<uint64_t> first(nseq);
+    uint64_t acc = 0;
+    for (uint64_t i = 0; i < nseq; ++i) {
+        first[i] = acc;
+        acc += nres[i];
+    }
+    cudaError_t e = ctx->misc.reserve(sizeof(uint64_t) * (nseq + 1));
+    if (e == cudaSuccess && nseq)
+        e = cudaMemcpyAsync(ctx->misc.p, first.data(), sizeof(uint64_t) * nseq, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = kmu::launch_synth_aa(b->packed, b->byte_off, b->nbases, (const uint64_t*)ctx->misc.p, nseq,
+                                 b->packed_bytes + TAIL_SLACK, seed, ctx->stream);
+    ctx->launches += 1;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess || rc) {
+        kmu_seqbatch_destroy(b);
+        return rc ? rc : fail(KMU_ECUDA, "synthetic protein generation failed: %s", cudaGetErrorString(e));
+    }
+    *out = b;
+    return KMU_OK;
+}
+
+int32_t kmu_seqbatch_alphabet(const kmu_seqbatch* b) { return b ? b->alphabet : -1; }
+
 int32_t kmu_seqbatch_download(kmu_ctx* ctx, const kmu_seqbatch* b, uint8_t* packed_out, uint64_t* byte_off_out,
                               uint64_t* nbases_out) {
     if (!ctx || !b) return fail(KMU_EINVAL, "null argument");
@@ -428,9 +549,7 @@ static int32_t upload_kmer_offsets(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
 int32_t kmu_generate_kmers(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t hash_kind,
                            void* out, uint64_t* out_off, int32_t out_on_device) {
     if (!ctx || !b) return fail(KMU_EINVAL, "null argument");
-    if (!kmer_type_accepts(k, kmer_type))
-        return fail(KMU_EINVAL, "KmerSeqIterator cannot support kmer size %u for kmer type %d", k, kmer_type);
-    if (hash_kind < 0 || hash_kind > KMU_HASH_INVHASH) return fail(KMU_EINVAL, "unknown hash kind %d", hash_kind);
+    if (int32_t a = kmu_check_kmer_args(b, k, kmer_type, hash_kind)) return a;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};
@@ -439,7 +558,7 @@ int32_t kmu_generate_kmers(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int3
     if (rc) return rc;
     if (total == 0) return KMU_OK;
     if (!out) return fail(KMU_EINVAL, "null output buffer");
-    const size_t esz = kmer_type == KMU_KMER64 ? 8 : 4;
+    const size_t esz = kmer_type_is_u64(kmer_type) ? 8 : 4;
     void* dout = out;
     if (!out_on_device) {
         CUDA_TRY(ctx->sig_dev.reserve(total * esz));
@@ -467,6 +586,7 @@ int32_t kmu_nthash_canonical(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, ui
                              uint8_t* out_strand, int32_t out_on_device) {
     if (!ctx || !b) return fail(KMU_EINVAL, "null argument");
     if (k < 1 || k > 32) return fail(KMU_EINVAL, "ntHash is defined here for 1 <= k <= 32, got %u", k);
+    if (b->alphabet != 0) return fail(KMU_EINVAL, "ntHash is defined on DNA sequences");
     if (n_multi < 1) return fail(KMU_EINVAL, "n_multi must be >= 1");
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);
@@ -527,7 +647,8 @@ uint64_t pow2_at_least(uint64_t x) {
     return p;
 }
 
-Geometry make_geometry(uint64_t nk_max, int mode, uint32_t k, uint32_t m, bool key64, bool force_global_table) {
+Geometry make_geometry(uint64_t nk_max, int mode, uint32_t k, uint32_t m, bool key64, bool force_global_table,
+                       bool no_stage = false) {
     Geometry g{};
     const size_t entry = kmu::pmh3a_entry_bytes(key64);
     const size_t qitem = kmu::pmh3a_qitem_bytes(key64);
@@ -550,7 +671,8 @@ Geometry make_geometry(uint64_t nk_max, int mode, uint32_t k, uint32_t m, bool k
     const uint64_t slots = align_up((uint64_t)m * 20, 16);  // 16-byte records + u32 mirror of the high words
     // TMA staging buffers: two per team, each large enough for the longest sequence of the
     // launch up to 16 KB (64 k bases); longer sequences are read from global memory
-    const uint64_t stage = std::min<uint64_t>(16 * 1024, align_up(nk_max / 4 + k + 32, 32));
+    // (amino-acid sequences are one byte per residue and are read from global memory)
+    const uint64_t stage = no_stage ? 0 : std::min<uint64_t>(16 * 1024, align_up(nk_max / 4 + k + 32, 32));
     g.stage_bytes = (uint32_t)stage;
     if (tw == 32) {
         // two 16-warp teams keep more sequences in flight than one 32-warp team, if both fit
@@ -638,7 +760,8 @@ extern "C" {
 
 static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type,
                                    int32_t hash_kind, uint32_t m, void* d_sig) {
-    const bool key64 = kmer_type == KMU_KMER64;
+    const bool key64 = kmer_type_is_u64(kmer_type);
+    const bool aa = kmer_type_is_aa(kmer_type);
     const size_t vsz = key64 ? 8 : 4;
     const uint64_t nseq = b->nseq;
     cudaStream_t st = ctx->stream;
@@ -667,7 +790,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     const uint32_t* d_order = (const uint32_t*)oc.order.p;
 
     // ---- launch classes: one per octave of the k-mer count ------------------------------
-    const bool hist_ok = k <= 8;
+    const bool hist_ok = k <= 8 && !aa;
     const size_t entry = kmu::pmh3a_entry_bytes(key64);
     std::vector<LaunchClass> classes;
     for (int oct = 63; oct >= 0; --oct) {
@@ -695,8 +818,8 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         if (!classes.empty()) {
             LaunchClass& p = classes.back();
             if (p.mode == c.mode && p.table_global == c.table_global && (c.mode == 0 || c.table_global)) {
-                Geometry gp = make_geometry(p.nk_max, p.mode, k, m, key64, p.table_global);
-                Geometry gc = make_geometry(c.nk_max, c.mode, k, m, key64, c.table_global);
+                Geometry gp = make_geometry(p.nk_max, p.mode, k, m, key64, p.table_global, aa);
+                Geometry gc = make_geometry(c.nk_max, c.mode, k, m, key64, c.table_global, aa);
                 if (gp.team_warps == gc.team_warps && gp.teams_per_cta == gc.teams_per_cta) {
                     p.count += c.count;
                     continue;
@@ -734,7 +857,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     // first point of every possible pre-key when the key space is small (u32 key types, k <= 10):
     // built once per (k, type, hash, m) and kept in the context (16 B per key, L2 resident)
     P.memo_fast = nullptr;
-    if (!key64 && 2 * k <= 20) {
+    if (!key64 && !aa && 2 * k <= 20) {
         const uint32_t nkeys = 1u << (2 * k);
         if (!(ctx->memo.p && ctx->memo_k == k && ctx->memo_m == m && ctx->memo_type == kmer_type &&
               ctx->memo_hash == hash_kind)) {
@@ -750,7 +873,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     }
 
     auto run_class = [&](const LaunchClass& c, const uint32_t* order, int counter_idx, bool speculate) -> int32_t {
-        Geometry g = make_geometry(c.nk_max, c.mode, k, m, key64, c.table_global);
+        Geometry g = make_geometry(c.nk_max, c.mode, k, m, key64, c.table_global, aa);
         uint64_t teams_needed = c.count;
         uint64_t ctas_needed = (teams_needed + g.teams_per_cta - 1) / g.teams_per_cta;
         // CTAs per SM that fit (threads and shared memory)
@@ -873,11 +996,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
 int32_t kmu_sketch_pmh3a(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t hash_kind,
                          uint32_t m, void* sig, int32_t sig_on_device) {
     if (!ctx || !b) return fail(KMU_EINVAL, "null argument");
-    if (kmer_type != KMU_KMER32 && kmer_type != KMU_KMER16B32 && kmer_type != KMU_KMER64)
-        return fail(KMU_EINVAL, "kmer type %d is not a 2-bit DNA k-mer type", kmer_type);
-    if (!kmer_type_accepts(k, kmer_type))
-        return fail(KMU_EINVAL, "KmerSeqIterator cannot support kmer size %u for kmer type %d", k, kmer_type);
-    if (hash_kind < 0 || hash_kind > KMU_HASH_INVHASH) return fail(KMU_EINVAL, "unknown hash kind %d", hash_kind);
+    if (int32_t a = kmu_check_kmer_args(b, k, kmer_type, hash_kind)) return a;
     if (m < 2) return fail(KMU_EINVAL, "ProbMinHash3a needs at least 2 hash values (m = %u)", m);
     if (b->nseq == 0) return KMU_OK;
     if (!sig) return fail(KMU_EINVAL, "null signature buffer");
@@ -887,7 +1006,7 @@ int32_t kmu_sketch_pmh3a(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};
-    const size_t vsz = kmer_type == KMU_KMER64 ? 8 : 4;
+    const size_t vsz = kmer_type_is_u64(kmer_type) ? 8 : 4;
     const size_t sig_bytes = (size_t)b->nseq * m * vsz;
     void* d_sig = sig;
     if (!sig_on_device) {
@@ -928,11 +1047,8 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
                               const uint64_t* nbases, uint64_t nseq, uint32_t k, int32_t kmer_type, int32_t hash_kind,
                               uint32_t m, void* sig) {
     if (!ctx || (nseq && (!packed || !byte_off || !nbases))) return fail(KMU_EINVAL, "null argument");
-    if (kmer_type != KMU_KMER32 && kmer_type != KMU_KMER16B32 && kmer_type != KMU_KMER64)
-        return fail(KMU_EINVAL, "kmer type %d is not a 2-bit DNA k-mer type", kmer_type);
-    if (!kmer_type_accepts(k, kmer_type))
-        return fail(KMU_EINVAL, "KmerSeqIterator cannot support kmer size %u for kmer type %d", k, kmer_type);
-    if (hash_kind < 0 || hash_kind > KMU_HASH_INVHASH) return fail(KMU_EINVAL, "unknown hash kind %d", hash_kind);
+    if (kmer_type_is_aa(kmer_type)) return fail(KMU_EINVAL, "the one-shot host form takes 2-bit DNA sequences");
+    if (int32_t a = kmu_check_kmer_args(nullptr, k, kmer_type, hash_kind)) return a;
     if (m < 2) return fail(KMU_EINVAL, "ProbMinHash3a needs at least 2 hash values (m = %u)", m);
     if (nseq == 0) return KMU_OK;
     if (!sig) return fail(KMU_EINVAL, "null signature buffer");

@@ -47,6 +47,7 @@ int32_t kmu_count_create(kmu_ctx* ctx, uint32_t k, int32_t kmer_type, uint32_t c
                          kmu_counter** out) {
     if (!ctx || !out) return fail(KMU_EINVAL, "null argument");
     *out = nullptr;
+    if (kmer_type_is_aa(kmer_type)) return fail(KMU_EINVAL, "the counter takes DNA k-mer types (KmerCounter, kmercount.rs:70)");
     if (!kmer_type_accepts(k, kmer_type))
         return fail(KMU_EINVAL, "kmer size %u is not supported by kmer type %d", k, kmer_type);
     if (count_bits < 1 || count_bits > 32) return fail(KMU_EINVAL, "count_bits must be in 1..32, got %u", count_bits);
@@ -100,6 +101,7 @@ uint64_t kmu_count_capacity(const kmu_counter* c) { return c ? c->capacity : 0; 
 
 int32_t kmu_count_insert_seqs(kmu_ctx* ctx, kmu_counter* c, const kmu_seqbatch* b, int32_t canonical) {
     if (!ctx || !c || !b) return fail(KMU_EINVAL, "null argument");
+    if (b->alphabet != 0) return fail(KMU_EINVAL, "the counter takes DNA sequences");
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};
@@ -238,6 +240,7 @@ int32_t kmu_count_export(kmu_ctx* ctx, const kmu_counter* c, uint32_t min_count,
 int32_t kmu_count_partition(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t canonical,
                             uint32_t nparts, void* kmers_out, uint64_t* part_counts, int32_t out_on_device) {
     if (!ctx || !b || !part_counts) return fail(KMU_EINVAL, "null argument");
+    if (kmer_type_is_aa(kmer_type) || b->alphabet != 0) return fail(KMU_EINVAL, "partitioning takes DNA k-mers");
     if (!kmer_type_accepts(k, kmer_type))
         return fail(KMU_EINVAL, "kmer size %u is not supported by kmer type %d", k, kmer_type);
     if (nparts < 1 || nparts > 64) return fail(KMU_EINVAL, "nparts must be in 1..64, got %u", nparts);

@@ -44,11 +44,7 @@ extern "C" {
 int32_t kmu_sketch_superminhash(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t hash_kind,
                                 uint32_t m, int32_t key_hasher, int32_t sig_bytes, void* sig, int32_t sig_on_device) {
     if (!ctx || !b) return fail(KMU_EINVAL, "null argument");
-    if (kmer_type != KMU_KMER32 && kmer_type != KMU_KMER16B32 && kmer_type != KMU_KMER64)
-        return fail(KMU_EINVAL, "kmer type %d is not a 2-bit DNA k-mer type", kmer_type);
-    if (!kmer_type_accepts(k, kmer_type))
-        return fail(KMU_EINVAL, "KmerSeqIterator cannot support kmer size %u for kmer type %d", k, kmer_type);
-    if (hash_kind < 0 || hash_kind > KMU_HASH_INVHASH) return fail(KMU_EINVAL, "unknown hash kind %d", hash_kind);
+    if (int32_t a = kmu_check_kmer_args(b, k, kmer_type, hash_kind)) return a;
     if (key_hasher != KMU_HASHER_NOHASH && key_hasher != KMU_HASHER_FNV) return fail(KMU_EINVAL, "unknown key hasher %d", key_hasher);
     if (sig_bytes != 4 && sig_bytes != 8) return fail(KMU_EINVAL, "sig_bytes must be 4 (f32) or 8 (f64)");
     if (m < 1) return fail(KMU_EINVAL, "SuperMinHash needs a sketch size >= 1");
@@ -65,7 +61,7 @@ int32_t kmu_sketch_superminhash(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k,
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};
     cudaStream_t st = ctx->stream;
-    const bool key64 = kmer_type == KMU_KMER64, f64 = sig_bytes == 8;
+    const bool key64 = kmer_type_is_u64(kmer_type), f64 = sig_bytes == 8;
     const size_t out_bytes = (size_t)b->nseq * m * sig_bytes;
     void* d_sig = sig;
     if (!sig_on_device) {

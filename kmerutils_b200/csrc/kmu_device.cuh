@@ -352,6 +352,7 @@ struct TaskKmers;
 
 template <>
 struct TaskKmers<uint32_t> {
+    static constexpr bool SEQUENTIAL = false;  // get(t) may be called for any subset of t, in increasing order
     uint64_t W, RC;
     uint32_t mask, sh0, j0;
     __device__ __forceinline__ void init(const uint32_t* words, uint64_t p0, uint32_t k) {
@@ -374,12 +375,56 @@ struct TaskKmers<uint32_t> {
 
 template <>
 struct TaskKmers<uint64_t> {
+    static constexpr bool SEQUENTIAL = true;  // get(t) must be called for every t = 0, 1, 2, ...
     KmerWalker<uint64_t> wk;
     __device__ __forceinline__ void init(const uint32_t* words, uint64_t p0, uint32_t k) { wk.start(words, p0, k); }
     __device__ __forceinline__ uint64_t get(uint32_t, bool canonical) {
         wk.roll();
         return wk.prekey(canonical);
     }
+};
+
+// ----------------------------------------------------------------------------
+//  Amino-acid k-mers (src/aautils/kmeraa.rs): sequences are one 5-bit code per byte
+//  (Alphabet::encode, kmeraa.rs:85-109, applied once at ingest); a k-mer is
+//  sum code_i << 5 (k - 1 - i) in a u32 (KmerAA32bit, k <= 6) or u64 (KmerAA64bit,
+//  k <= 12); push = ((v << 5) & mask) | code (kmeraa.rs:171-182, 301-312).  There is
+//  no reverse complement (kmeraa.rs:185-187 panics), hence no canonical form.
+// ----------------------------------------------------------------------------
+template <typename V>
+struct KmerWalkerAA {
+    V fwd, mask;
+    const uint8_t* bp;
+    __device__ __forceinline__ void start(const void* codes, uint64_t p0, uint32_t k) {
+        mask = value_mask<V>(5 * k);
+        bp = (const uint8_t*)codes + p0;
+        fwd = 0;
+        for (uint32_t i = 0; i + 1 < k; ++i) fwd = (V)((fwd << 5) | (V)(*bp++));
+    }
+    __device__ __forceinline__ void roll() { fwd = (V)(((fwd << 5) | (V)(*bp++)) & mask); }
+    __device__ __forceinline__ V prekey(bool) const { return fwd; }
+};
+
+template <typename V>
+struct TaskKmersAA {
+    static constexpr bool SEQUENTIAL = true;
+    KmerWalkerAA<V> wk;
+    __device__ __forceinline__ void init(const uint32_t* codes, uint64_t p0, uint32_t k) { wk.start(codes, p0, k); }
+    __device__ __forceinline__ V get(uint32_t, bool) {
+        wk.roll();
+        return wk.fwd;
+    }
+};
+
+template <typename V, bool AA>
+struct KmerSource {
+    using Task = TaskKmers<V>;
+    using Walker = KmerWalker<V>;
+};
+template <typename V>
+struct KmerSource<V, true> {
+    using Task = TaskKmersAA<V>;
+    using Walker = KmerWalkerAA<V>;
 };
 
 }  // namespace kmu

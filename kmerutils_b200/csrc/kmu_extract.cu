@@ -36,7 +36,7 @@ cudaError_t launch_kmer_offsets(const uint64_t* nbases, uint64_t nseq, uint32_t 
 }
 
 // every thread produces T consecutive output elements
-template <typename V, int T>
+template <typename V, int T, bool AA>
 __global__ void __launch_bounds__(256) generate_kmers_kernel(SeqView b, uint32_t k, int kmer_type, int hash_kind,
                                                               const uint64_t* __restrict__ out_off, V* __restrict__ out) {
     const uint64_t total = out_off[b.nseq];
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) generate_kmers_kernel(SeqView b, uint32_t
          e0 += (uint64_t)gridDim.x * blockDim.x * T) {
         uint64_t s = seq_of_element(out_off, b.nseq, e0);
         uint64_t s_begin = out_off[s], s_end = out_off[s + 1];
-        KmerWalker<V> wk;
+        typename KmerSource<V, AA>::Walker wk;
         wk.start((const uint32_t*)(b.packed + b.byte_off[s]), e0 - s_begin, k);
         V vals[T];
 #pragma unroll
@@ -89,11 +89,14 @@ cudaError_t launch_generate_kmers(const SeqView& b, uint32_t k, int kmer_type, i
     if (b.nseq == 0) return cudaSuccess;
     const int block = 256;
     const int grid = 148 * 8;
-    bool key64 = kmer_type == KMU_KMER64 || kmer_type == KMU_KMERAA64;
-    if (key64)
-        generate_kmers_kernel<uint64_t, 8><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint64_t*)out);
+    if (kmer_type == KMU_KMERAA64)
+        generate_kmers_kernel<uint64_t, 8, true><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint64_t*)out);
+    else if (kmer_type == KMU_KMERAA32)
+        generate_kmers_kernel<uint32_t, 8, true><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint32_t*)out);
+    else if (kmer_type == KMU_KMER64)
+        generate_kmers_kernel<uint64_t, 8, false><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint64_t*)out);
     else
-        generate_kmers_kernel<uint32_t, 8><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint32_t*)out);
+        generate_kmers_kernel<uint32_t, 8, false><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint32_t*)out);
     return cudaGetLastError();
 }
 

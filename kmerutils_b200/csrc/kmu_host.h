@@ -119,6 +119,7 @@ struct kmu_seqbatch {
     uint64_t packed_bytes = 0;  // without the tail slack
     uint64_t total_bases = 0;
     bool owns = true;           // false: the buffers belong to a context arena
+    int alphabet = 0;           // 0: DNA, 2 bits per base packed; 1: amino acids, one 5-bit code per byte
     std::vector<uint64_t> h_nbases;
     std::vector<uint64_t> h_byte_off;
 };
@@ -137,6 +138,10 @@ struct ScopedDevice {
 };
 
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+inline bool kmer_type_is_aa(int type) { return type == KMU_KMERAA32 || type == KMU_KMERAA64; }
+inline bool kmer_type_is_u64(int type) { return type == KMU_KMER64 || type == KMU_KMERAA64; }
+// k-mer type, k, hash closure and batch alphabet must agree; returns KMU_OK or sets the error
+int32_t kmu_check_kmer_args(const kmu_seqbatch* b, uint32_t k, int kmer_type, int hash_kind);
 
 // does the k-mer type accept this k? (the reference panics otherwise)
 inline bool kmer_type_accepts(uint32_t k, int type) {
@@ -144,6 +149,8 @@ inline bool kmer_type_accepts(uint32_t k, int type) {
         case KMU_KMER32: return k >= 1 && k <= 14;   // src/base/kmergenerator.rs:311, kmer32bit.rs:68-76
         case KMU_KMER16B32: return k == 16;          // src/base/kmergenerator.rs:218-220
         case KMU_KMER64: return k >= 1 && k <= 32;   // src/base/kmergenerator.rs:415
+        case KMU_KMERAA32: return k >= 1 && k <= 6;  // src/aautils/kmeraa.rs:212-214,727-732
+        case KMU_KMERAA64: return k >= 1 && k <= 12; // src/aautils/kmeraa.rs:822-824
         default: return false;
     }
 }

@@ -80,6 +80,13 @@ cudaError_t launch_count_invalid(const uint8_t* ascii, const uint64_t* ascii_off
 cudaError_t launch_pack_ascii(const uint8_t* ascii, const uint64_t* ascii_off, const uint64_t* byte_off,
                               const uint64_t* nbases, uint64_t nseq, int drop_invalid, uint8_t* packed,
                               cudaStream_t stream);
+// amino-acid sequences: one 5-bit code per byte (kmeraa.rs:85-109)
+cudaError_t launch_aa_count_invalid(const uint8_t* ascii, const uint64_t* ascii_off, uint64_t nseq, uint64_t* invalid,
+                                    cudaStream_t stream);
+cudaError_t launch_aa_encode(const uint8_t* ascii, const uint64_t* ascii_off, const uint64_t* byte_off, uint64_t nseq,
+                             uint8_t* codes, cudaStream_t stream);
+cudaError_t launch_synth_aa(uint8_t* codes, const uint64_t* byte_off, const uint64_t* nres, const uint64_t* first_res,
+                            uint64_t nseq, uint64_t total_bytes, uint64_t seed, cudaStream_t stream);
 // length classes: bucket = 8 per octave of the k-mer count, bucket 0 = longest
 constexpr int LEN_BUCKETS = 512;
 cudaError_t launch_len_hist(const uint64_t* nbases, uint64_t nseq, uint32_t k, unsigned long long* hist,

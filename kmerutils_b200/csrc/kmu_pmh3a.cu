@@ -266,8 +266,9 @@ __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t he
 // MEMO  : small key spaces (u32 k-mers, k <= 10): the first point of every pre-key -- exp01 sample,
 //         slot and hashed key, all functions of the key only -- comes from a table built once per
 //         (k, type, hash, m); otherwise the first point is half-recomputed by first_point_alive().
-template <typename V, int MODE, bool MEMO>
+template <typename V, int MODE, bool MEMO, bool AA>
 __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams P) {
+    using TK = typename KmerSource<V, AA>::Task;
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ double s_winv[64];
     using TO = TableOps<V>;
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
             if (base >= ntasks) break;
             const uint32_t task = base + team.lane;
             if (task < ntasks) {
-                TaskKmers<V> tk;
+                TK tk;
                 uint32_t p = task << log2T;
                 tk.init(words, p, k);
                 const uint32_t pend = min(p + T, nk);
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
             if (base >= ntasks) break;
             const uint32_t task = base + team.lane;
             const bool tact = task < ntasks;
-            TaskKmers<V> tk;
+            TK tk;
             uint32_t p = task << log2T;
             uint32_t own = 0xFFFFu;
             if (tact) {
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
                 V pk = 0;
                 const bool in_range = tact && p < nk;
                 const bool mine = in_range && ((own >> t) & 1u);
-                if (sizeof(V) == 8 ? in_range : mine) pk = tk.get(t, canonical);  // the u64 walker must roll every position
+                if (TK::SEQUENTIAL ? in_range : mine) pk = tk.get(t, canonical);  // rolling walkers must see every position
                 if (mine) {
                     if (MODE == 0) {
                         if (overflow) {
@@ -598,9 +599,9 @@ cudaError_t launch_pmh3a_memo(const Pmh3aParams& P, void* fast, uint32_t nkeys, 
 // --------------------------------------------------------------------------------
 // host-side launcher
 // --------------------------------------------------------------------------------
-template <typename V, int MODE, bool MEMO>
+template <typename V, int MODE, bool MEMO, bool AA = false>
 static cudaError_t launch_one(const Pmh3aParams& P, int grid, int block, size_t smem, cudaStream_t stream) {
-    auto kern = pmh3a_sketch_kernel<V, MODE, MEMO>;
+    auto kern = pmh3a_sketch_kernel<V, MODE, MEMO, AA>;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -618,6 +619,8 @@ size_t pmh3a_entry_bytes(bool key64) {
 
 cudaError_t launch_pmh3a(const Pmh3aParams& P, bool key64, int mode, int grid, int block, size_t smem,
                          cudaStream_t stream) {
+    if (P.kmer_type == KMU_KMERAA32) return launch_one<uint32_t, 1, false, true>(P, grid, block, smem, stream);
+    if (P.kmer_type == KMU_KMERAA64) return launch_one<uint64_t, 1, false, true>(P, grid, block, smem, stream);
     if (key64) {
         return mode == 0 ? launch_one<uint64_t, 0, false>(P, grid, block, smem, stream)
                          : launch_one<uint64_t, 1, false>(P, grid, block, smem, stream);

@@ -106,8 +106,9 @@ struct SmhTeamShared {
     uint64_t byte_off;
 };
 
-template <typename V, typename S>
+template <typename V, typename S, bool AA>
 __global__ void __launch_bounds__(1024, 1) smh_fast_kernel(const SmhParams P) {
+    using TK = typename KmerSource<V, AA>::Task;
     using F = FloatOps<S>;
     using B = typename F::B;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(1024, 1) smh_fast_kernel(const SmhParams P) {
         team.sync();
         const uint32_t ntasks = (nk + 15) >> 4;
         for (uint32_t task = team.tid; task < ntasks; task += team.size) {
-            TaskKmers<V> tk;
+            TK tk;
             uint32_t p = task << 4;
             tk.init(words, p, k);
             const uint32_t pend = min(p + 16, nk);
@@ -186,8 +187,9 @@ __global__ void __launch_bounds__(1024, 1) smh_fast_kernel(const SmhParams P) {
 }
 
 // exact path: one warp per sequence
-template <typename V, typename S>
+template <typename V, typename S, bool AA>
 __global__ void __launch_bounds__(32) smh_exact_kernel(const SmhParams P) {
+    using Walker = typename KmerSource<V, AA>::Walker;
     using F = FloatOps<S>;
     using B = typename F::B;
     const int lane = threadIdx.x;
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(32) smh_exact_kernel(const SmhParams P) {
         for (uint32_t p0 = 0; p0 < nk; p0 += 32) {
             const uint32_t pos = p0 + lane;
             if (pos < nk) {
-                KmerWalker<V> wk;
+                Walker wk;
                 wk.start(words, pos, k);
                 wk.roll();
                 const V key = finalize_key<V>(wk.prekey(canonical), header, P.hash_kind);
@@ -264,9 +266,9 @@ __global__ void __launch_bounds__(32) smh_exact_kernel(const SmhParams P) {
     }
 }
 
-template <typename V, typename S>
+template <typename V, typename S, bool AA>
 static cudaError_t launch_fast(const SmhParams& P, int grid, int block, size_t smem, cudaStream_t st) {
-    auto kern = smh_fast_kernel<V, S>;
+    auto kern = smh_fast_kernel<V, S, AA>;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -277,19 +279,29 @@ static cudaError_t launch_fast(const SmhParams& P, int grid, int block, size_t s
     return cudaGetLastError();
 }
 
+template <typename V, bool AA>
+static cudaError_t launch_fast_s(const SmhParams& P, bool f64, int grid, int block, size_t smem, cudaStream_t st) {
+    return f64 ? launch_fast<V, double, AA>(P, grid, block, smem, st) : launch_fast<V, float, AA>(P, grid, block, smem, st);
+}
+
 cudaError_t launch_smh_fast(const SmhParams& P, bool key64, bool f64, int grid, int block, size_t smem, cudaStream_t st) {
-    if (key64) return f64 ? launch_fast<uint64_t, double>(P, grid, block, smem, st) : launch_fast<uint64_t, float>(P, grid, block, smem, st);
-    return f64 ? launch_fast<uint32_t, double>(P, grid, block, smem, st) : launch_fast<uint32_t, float>(P, grid, block, smem, st);
+    if (P.kmer_type == KMU_KMERAA32) return launch_fast_s<uint32_t, true>(P, f64, grid, block, smem, st);
+    if (P.kmer_type == KMU_KMERAA64) return launch_fast_s<uint64_t, true>(P, f64, grid, block, smem, st);
+    return key64 ? launch_fast_s<uint64_t, false>(P, f64, grid, block, smem, st)
+                 : launch_fast_s<uint32_t, false>(P, f64, grid, block, smem, st);
+}
+
+template <typename V, bool AA>
+static void launch_exact_s(const SmhParams& P, bool f64, int grid, cudaStream_t st) {
+    if (f64) smh_exact_kernel<V, double, AA><<<grid, 32, 0, st>>>(P);
+    else smh_exact_kernel<V, float, AA><<<grid, 32, 0, st>>>(P);
 }
 
 cudaError_t launch_smh_exact(const SmhParams& P, bool key64, bool f64, int grid, cudaStream_t st) {
-    if (key64) {
-        if (f64) smh_exact_kernel<uint64_t, double><<<grid, 32, 0, st>>>(P);
-        else smh_exact_kernel<uint64_t, float><<<grid, 32, 0, st>>>(P);
-    } else {
-        if (f64) smh_exact_kernel<uint32_t, double><<<grid, 32, 0, st>>>(P);
-        else smh_exact_kernel<uint32_t, float><<<grid, 32, 0, st>>>(P);
-    }
+    if (P.kmer_type == KMU_KMERAA32) launch_exact_s<uint32_t, true>(P, f64, grid, st);
+    else if (P.kmer_type == KMU_KMERAA64) launch_exact_s<uint64_t, true>(P, f64, grid, st);
+    else if (key64) launch_exact_s<uint64_t, false>(P, f64, grid, st);
+    else launch_exact_s<uint32_t, false>(P, f64, grid, st);
     return cudaGetLastError();
 }
 

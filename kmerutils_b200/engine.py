@@ -162,6 +162,25 @@ class Engine:
                                                _p(bad, u64p), C.byref(h)))
         return SeqBatch(self, h), bad[: len(seqs)]
 
+    def batch_from_aa(self, seqs, drop_invalid=False):
+        """seqs: list of bytes (proteins).  -> (SeqBatch of 5-bit codes, invalid_counts).  SequenceAA::new /
+        new_filtered (src/aautils/kmeraa.rs:404-456) on the GPU."""
+        lens = np.array([len(s) for s in seqs], dtype=np.uint64)
+        off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=off[1:])
+        buf = np.frombuffer(b"".join(bytes(s) for s in seqs) + b"\0", dtype=np.uint8)
+        bad = np.zeros(max(len(seqs), 1), dtype=np.uint64)
+        h = C.c_void_p()
+        check(self.lib.kmu_seqbatch_from_aa(self.ctx, _p(buf), _p(off, u64p), len(seqs), int(bool(drop_invalid)),
+                                            _p(bad, u64p), C.byref(h)))
+        return SeqBatch(self, h), bad[: len(seqs)]
+
+    def batch_synth_aa(self, seed, nres):
+        nb = _as_u64(nres)
+        h = C.c_void_p()
+        check(self.lib.kmu_seqbatch_synth_aa(self.ctx, seed, _p(nb, u64p), len(nb), C.byref(h)))
+        return SeqBatch(self, h)
+
     def batch_synth(self, seed, nbases):
         nb = _as_u64(nbases)
         h = C.c_void_p()

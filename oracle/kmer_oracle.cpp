@@ -136,7 +136,56 @@ bool kmer_type_accepts(int k, int type) {
         case ORC_KMER32: return k >= 1 && k <= 14;   // kmergenerator.rs:311 / kmer32bit.rs:160
         case ORC_KMER16B32: return k == 16;          // kmergenerator.rs:218-220
         case ORC_KMER64: return k >= 1 && k <= 32;   // kmergenerator.rs:415
+        case ORC_KMERAA32: return k >= 1 && k <= 6;  // aautils/kmeraa.rs:212-214, 727-732
+        case ORC_KMERAA64: return k >= 1 && k <= 12; // aautils/kmeraa.rs:822-824
         default: return false;
+    }
+}
+
+inline bool is_aa_type(int type) { return type == ORC_KMERAA32 || type == ORC_KMERAA64; }
+
+// aautils Alphabet::encode (kmeraa.rs:85-109): 5-bit codes, 14 is skipped; -1 = not in the alphabet (the reference panics)
+inline int encode_aa(uint8_t c) {
+    switch (c) {
+        case 'A': return 1; case 'C': return 2; case 'D': return 3; case 'E': return 4; case 'F': return 5;
+        case 'G': return 6; case 'H': return 7; case 'I': return 8; case 'K': return 9; case 'L': return 10;
+        case 'M': return 11; case 'N': return 12; case 'P': return 13; case 'Q': return 15; case 'R': return 16;
+        case 'S': return 17; case 'T': return 18; case 'V': return 19; case 'W': return 20; case 'Y': return 21;
+        default: return -1;
+    }
+}
+const char AA_LETTERS[21] = "ACDEFGHIKLMNPQRSTVWY";
+
+// KmerAA32bit::push / KmerAA64bit::push (kmeraa.rs:171-182, 301-312): the ASCII residue is encoded here
+inline uint64_t kmer_push_aa(uint64_t aa, int k, uint8_t residue) {
+    const uint64_t vmask = (1ULL << (5 * k)) - 1;
+    return ((aa << 5) & vmask) | ((uint64_t)encode_aa(residue) & 0x1F);
+}
+
+// All k-mer words of [begin, end) of one sequence, in order.  DNA: `seq` is 2-bit packed
+// (KmerSeqIterator::next, kmergenerator.rs:75-106); amino acids: `seq` is one ASCII residue per byte
+// (aautils KmerSeqIterator::next, kmeraa.rs:568-627).  f(word) gets the k-mer word (`.0` / `.aa`).
+template <typename F>
+void for_each_kmer(const uint8_t* seq, uint64_t nbases, uint64_t begin, uint64_t end, int k, int type, F&& f) {
+    if (!kmer_type_accepts(k, type)) return;
+    if (end > nbases) end = nbases;
+    if (end < begin + (uint64_t)k) return;
+    if (is_aa_type(type)) {
+        uint64_t v = 0;
+        for (int i = 0; i < k; ++i) v = (v << 5) | ((uint64_t)encode_aa(seq[begin + i]) & 0x1F);  // kmeraa.rs:598-621
+        f(v);
+        for (uint64_t p = begin + k; p < end; ++p) {
+            v = kmer_push_aa(v, k, seq[p]);
+            f(v);
+        }
+        return;
+    }
+    uint64_t val = 0;
+    for (int i = 0; i < k - 1; ++i) val = (val << 2) | base_at(seq, begin + i);
+    uint64_t word = kmer_build(val, k, type);
+    for (uint64_t p = begin + k - 1; p < end; ++p) {
+        word = kmer_push(word, k, type, base_at(seq, p));
+        f(word);
     }
 }
 
@@ -434,16 +483,8 @@ struct FlatCountMap {
 // (seqsketchjaccard.rs:226-234)
 void count_kmers(const uint8_t* packed, uint64_t nbases, uint64_t begin, uint64_t end, int k, int type,
                  int hash_kind, FlatCountMap& wb) {
-    if (!kmer_type_accepts(k, type)) return;
-    if (end > nbases) end = nbases;
-    if (end < begin + (uint64_t)k) return;
-    uint64_t val = 0;
-    for (int i = 0; i < k - 1; ++i) val = (val << 2) | base_at(packed, begin + i);
-    uint64_t word = kmer_build(val, k, type);
-    for (uint64_t p = begin + k - 1; p < end; ++p) {
-        word = kmer_push(word, k, type, base_at(packed, p));
-        wb.add(apply_hash(word, k, type, hash_kind), 1);
-    }
+    for_each_kmer(packed, nbases, begin, end, k, type,
+                  [&](uint64_t word) { wb.add(apply_hash(word, k, type, hash_kind), 1); });
 }
 
 void sketch_from_map(const FlatCountMap& wb, uint32_t m, int key_bytes, uint64_t* sig) {
@@ -517,21 +558,11 @@ void superminhash_seqs(const uint8_t* packed, const uint64_t* byte_off, const ui
                        int type, int hash_kind, uint32_t m, int hasher, S* out) {
     SuperMinHashOrc<S> smh(m);
     const int key_bytes = is_u32_type(type) ? 4 : 8;
-    if (kmer_type_accepts(k, type)) {
-        for (uint64_t s = 0; s < nseq; ++s) {
-            const uint8_t* pk = packed + byte_off[s];
-            const uint64_t L = nbases[s];
-            if (L < (uint64_t)k) continue;
-            uint64_t val = 0;
-            for (int i = 0; i < k - 1; ++i) val = (val << 2) | base_at(pk, i);
-            uint64_t word = kmer_build(val, k, type);
-            for (uint64_t q = k - 1; q < L; ++q) {
-                word = kmer_push(word, k, type, base_at(pk, q));
-                const uint64_t key = apply_hash(word, k, type, hash_kind);
-                smh.sketch(hasher == 0 ? nohash_seed(key, key_bytes) : fnv1a_seed(key, key_bytes));
-            }
-        }
-    }
+    for (uint64_t s = 0; s < nseq; ++s)
+        for_each_kmer(packed + byte_off[s], nbases[s], 0, nbases[s], k, type, [&](uint64_t word) {
+            const uint64_t key = apply_hash(word, k, type, hash_kind);
+            smh.sketch(hasher == 0 ? nohash_seed(key, key_bytes) : fnv1a_seed(key, key_bytes));
+        });
     for (uint32_t j = 0; j < m; ++j) out[j] = smh.h[j];
 }
 
@@ -624,6 +655,13 @@ uint64_t orc_generate_kmers(const uint8_t* packed, uint64_t nbases, uint64_t beg
     if (!kmer_type_accepts(k, type)) return ~0ULL;
     if (end > nbases || end <= begin) return 0;  // set_range returns Err -> callers unwrap/panic
     if (end - begin < (uint64_t)k) return 0;
+    if (is_aa_type(type)) {
+        for (uint64_t i = begin; i < end; ++i)
+            if (encode_aa(packed[i]) < 0) return ~0ULL - 1;  // Alphabet::encode panics (kmeraa.rs:106)
+        uint64_t na = 0;
+        for_each_kmer(packed, nbases, begin, end, k, type, [&](uint64_t w) { out[na++] = w; });
+        return na;
+    }
     uint64_t val = 0;
     for (int i = 0; i < k; ++i) val = (val << 2) | base_at(packed, begin + i);  // first k-mer via KmerBuilder::build
     uint64_t word = kmer_build(val, k, type);
@@ -886,6 +924,19 @@ void orc_sketch_superminhash_batch(const uint8_t* packed, const uint64_t* byte_o
     for (int t = 1; t < nthreads; ++t) th.emplace_back(worker);
     worker();
     for (auto& t : th) t.join();
+}
+
+// synthetic protein: residue i of stream `seed` = "ACDEFGHIKLMNPQRSTVWY"[z_i % 20]
+void orc_synth_aa(uint64_t seed, uint64_t first_res, uint64_t nres, uint8_t* ascii_out) {
+    for (uint64_t p = 0; p < nres; ++p) ascii_out[p] = (uint8_t)AA_LETTERS[synth_z(seed, first_res + p) % 20];
+}
+
+// SequenceAA::new_filtered (kmeraa.rs:447-456): keeps the residues of the alphabet; returns how many
+uint64_t orc_aa_filter(const uint8_t* ascii, uint64_t n, uint8_t* out) {
+    uint64_t kept = 0;
+    for (uint64_t i = 0; i < n; ++i)
+        if (encode_aa(ascii[i]) >= 0) out[kept++] = ascii[i];
+    return kept;
 }
 
 int orc_hardware_threads(void) {

@@ -138,6 +138,11 @@ uint64_t orc_dispatch(uint64_t compressed_value, int type, uint64_t nb_receiver)
 void orc_synth_packed(uint64_t seed, uint64_t first_base, uint64_t nbases, uint8_t* packed_out);
 void orc_synth_ascii(uint64_t seed, uint64_t first_base, uint64_t nbases, uint8_t* ascii_out);
 
+// ---- A14 : amino acids.  For the KMERAA types every `packed` argument above is the SequenceAA
+// payload: one ASCII residue per byte (kmeraa.rs:404-406), lengths in residues.
+void orc_synth_aa(uint64_t seed, uint64_t first_res, uint64_t nres, uint8_t* ascii_out);
+uint64_t orc_aa_filter(const uint8_t* ascii, uint64_t n, uint8_t* out);
+
 int orc_hardware_threads(void);
 
 #ifdef __cplusplus

@@ -103,6 +103,9 @@ class Oracle:
         L.orc_dispatch.argtypes = [C.c_uint64, C.c_int, C.c_uint64]
         L.orc_synth_packed.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, u8p]
         L.orc_synth_ascii.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, u8p]
+        L.orc_synth_aa.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, u8p]
+        L.orc_aa_filter.restype = C.c_uint64
+        L.orc_aa_filter.argtypes = [u8p, C.c_uint64, u8p]
         L.orc_hardware_threads.restype = C.c_int
 
     # ---- sequences -------------------------------------------------------------
@@ -144,6 +147,8 @@ class Oracle:
         n = self.L.orc_generate_kmers(_ptr(packed, u8p), nbases, begin, end, k, ktype, _ptr(out, u64p))
         if n == 2**64 - 1:
             raise ValueError("kmer size not supported by kmer type")
+        if n == 2**64 - 2:
+            raise ValueError("encode: not a code in alphabet for amino acid")
         return out[:n].copy()
 
     def apply_hash(self, words, k, ktype, kind):
@@ -259,6 +264,17 @@ class Oracle:
         out = np.zeros(nbases, dtype=np.uint8)
         self.L.orc_synth_ascii(seed, first_base, nbases, _ptr(out, u8p))
         return out.tobytes()
+
+    def synth_aa(self, seed, first_res, nres):
+        out = np.zeros(nres, dtype=np.uint8)
+        self.L.orc_synth_aa(seed, first_res, nres, _ptr(out, u8p))
+        return out.tobytes()
+
+    def aa_filter(self, ascii_bytes):
+        a = np.frombuffer(bytes(ascii_bytes), dtype=np.uint8)
+        out = np.zeros(len(a) + 1, dtype=np.uint8)
+        n = self.L.orc_aa_filter(_ptr(a, u8p), len(a), _ptr(out, u8p))
+        return out[:n].tobytes()
 
     def hardware_threads(self):
         return int(self.L.orc_hardware_threads())

@@ -275,3 +275,65 @@ def test_superminhash_properties(oracle):
     # no k-mer at all: the initial value F::from(u32::MAX)
     empty = _smh(oracle, b"ACG", 8, ol.KMER32, ol.HASH_CANON_INVHASH, 16, 0)
     assert (empty == 4294967295.0).all()
+
+
+# ---- amino-acid k-mers (src/aautils/kmeraa.rs:920-1021) ---------------------------------------------
+AA_CODES = {c: v for c, v in zip("ACDEFGHIKLMNP", range(1, 14))}
+AA_CODES.update({c: v for c, v in zip("QRSTVWY", range(15, 22))})
+AA_DECODE = {v: c for c, v in AA_CODES.items()}
+
+
+def aa_to_str(v, k):
+    return "".join(AA_DECODE[(int(v) >> (5 * (k - 1 - j))) & 31] for j in range(k))
+
+
+@pytest.mark.parametrize("ktype", [ol.KMERAA32, ol.KMERAA64])
+def test_aa_iterator_range(oracle, ktype):
+    g = GOLD["aa"]
+    prot = np.frombuffer(g["protein"].encode(), dtype=np.uint8)
+    got = oracle.generate_kmers(prot, len(prot), 4, ktype, 3, 10)
+    assert [aa_to_str(v, 4) for v in got] == g["range_3_10_4mers"]
+
+
+def test_aa_iterator_end_and_guards(oracle):
+    g = GOLD["aa"]
+    prot = np.frombuffer(g["protein"][:32].encode(), dtype=np.uint8)
+    got = oracle.generate_kmers(prot, 32, 8, ol.KMERAA64)
+    assert len(got) == 32 - 8 + 1 and aa_to_str(got[-1], 8) == g["last_8mer"]
+    for i, v in enumerate(got):
+        assert aa_to_str(v, 8) == g["protein"][i:i + 8]
+    with pytest.raises(ValueError):  # KmerAA32bit holds at most 6 residues (kmeraa.rs:212-214)
+        oracle.generate_kmers(prot, 32, 7, ol.KMERAA32)
+    with pytest.raises(ValueError):
+        oracle.generate_kmers(prot, 32, 13, ol.KMERAA64)
+    assert len(oracle.generate_kmers(prot, 32, 12, ol.KMERAA64)) == 21  # k = 12 works through KmerBuilder (:622-623)
+    bad = np.frombuffer(b"MTEQIELIKLYSTRILALAAQMPHVGXLDNPD", dtype=np.uint8)
+    with pytest.raises(ValueError):  # Alphabet::encode panics on 'X' (kmeraa.rs:106)
+        oracle.generate_kmers(bad, 32, 8, ol.KMERAA64)
+    assert oracle.aa_filter(b"MTxEQ*IB") == b"MTEQI"  # new_filtered (kmeraa.rs:447-456); B, x, * are not in the alphabet
+
+
+AA_STR1 = b"MTEQIELIKLYSTRILALAAQMPHVGSLDNPDASAMKRSPLCGSKVTVDVIMQNGKITFDGFEVLAPASEYKNRHASILLSLDATAEACASIAAQNSA"
+AA_STR2 = b"MTEQIELIKLYSTRILALAAQMPHVGSLDNPDASAMKRSPLCGSKVMTEQIELIKLYSTRILALAAQMPHVGSLDNPDASAMKRSPLCGSKV"
+
+
+@pytest.mark.parametrize("ktype,m", [(ol.KMERAA64, 400), (ol.KMERAA32, 800)])
+def test_aa_probminhash_reference_inequality(oracle, ktype, m):
+    # aautils/setsketchert.rs:1217-1265 (64 bit, m = 400) and :1267-1317 (32 bit): the second string is the
+    # first half of the first one repeated; k = 5, masked value, |J - 0.5| < 0.1
+    sigs = []
+    for s_ in (AA_STR1, AA_STR2):
+        a = np.frombuffer(s_, dtype=np.uint8)
+        sigs.append(oracle.sketch_pmh3a_seq(a, len(a), 5, ktype, ol.HASH_MASKED_VALUE, m))
+    assert abs(float(np.mean(sigs[0] == sigs[1])) - 0.5) < 0.1
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_aa_superminhash_reference_inequality(oracle, dtype):
+    # aautils/setsketchert.rs:1319-1391: SuperMinHash f64 / f32 on the same strings, |J - 0.5| < 0.1
+    sigs = []
+    for s_ in (AA_STR1, AA_STR2):
+        a = np.frombuffer(s_, dtype=np.uint8)
+        sigs.append(oracle.sketch_superminhash_batch(a, np.zeros(1, np.uint64), np.array([len(a)], np.uint64), 5,
+                                                     ol.KMERAA64, ol.HASH_MASKED_VALUE, 800, 0, dtype)[0])
+    assert abs(float(np.mean(sigs[0] == sigs[1])) - 0.5) < 0.1
