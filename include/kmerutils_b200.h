@@ -162,6 +162,24 @@ int32_t kmu_sketch_superminhash(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_
                                 int32_t hash_kind, uint32_t m, int32_t key_hasher, int32_t sig_bytes, void* sig,
                                 int32_t sig_on_device);
 
+/* ---- SetSketch / HyperLogLog registers
+ *      HyperLogLogSketch::sketch_compressedkmer        src/sketching/setsketchert.rs:758-802  (whole == 0: one sketch per sequence)
+ *      HyperLogLogSketch::sketch_compressedkmer_seqs   src/sketching/setsketchert.rs:811-895  (whole != 0: ONE sketch for the batch;
+ *                                                      the reference's block split + SetSketcher::merge is an element-wise max)
+ *      amino-acid mirror                               src/aautils/setsketchert.rs:790-1011
+ * Every k-mer is streamed through probminhash's SetSketcher::sketch with NoHashHasher keys; the
+ * signature is get_signature(): m registers of u16 / u32 / u64 (sig_bytes 2 / 4 / 8), mergeable by
+ * element-wise maximum.  params == NULL means SetSketchParams::default() = {b 1.001, m 4096, a 20, q 2^16 - 2}. */
+typedef struct kmu_setsketch_params {
+    double b;   /* base of the geometric levels, > 1 */
+    uint64_t m; /* number of registers */
+    double a;   /* rate of the exponential */
+    uint64_t q; /* registers saturate at q + 1 */
+} kmu_setsketch_params;
+int32_t kmu_sketch_setsketch(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, int32_t kmer_type, int32_t hash_kind,
+                             const kmu_setsketch_params* params, int32_t sig_bytes, int32_t whole, void* sig,
+                             int32_t sig_on_device);
+
 /* ---- k-mer counting (replaces KmerCounter: cuckoo filter + counting Bloom filter,
  *      src/base/kmercount.rs:70-83) -------------------------------------------------------
  * One exact open-addressing table in HBM keyed by kmer.get_compressed_value().  Semantics are

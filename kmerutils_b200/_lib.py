@@ -34,6 +34,10 @@ class KmuLaunchRec(C.Structure):
                 ("ms", C.c_float), ("counter_idx", C.c_uint32), ("phase_clocks", C.c_uint64 * 8)]
 
 
+class KmuSetSketchParams(C.Structure):
+    _fields_ = [("b", C.c_double), ("m", C.c_uint64), ("a", C.c_double), ("q", C.c_uint64)]
+
+
 class KmuError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"kmerutils_b200 error {code}: {msg}")
@@ -76,6 +80,8 @@ SIGNATURES = {
                                           C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
     "kmu_sketch_superminhash": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32,
                                             C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
+    "kmu_sketch_setsketch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32,
+                                         C.POINTER(KmuSetSketchParams), C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "kmu_count_create": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint64, vpp]),
     "kmu_count_destroy": (None, [C.c_void_p]),
     "kmu_count_capacity": (C.c_uint64, [C.c_void_p]),

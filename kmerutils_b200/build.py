@@ -13,7 +13,7 @@ LIB = os.path.join(HERE, "libkmerutils_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "--fmad=false", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-Xcompiler", "-ffp-contract=off", "--fmad=false", "-shared",
 ]
 
 

@@ -15,13 +15,13 @@ struct TeamGeometry {
 };
 
 // one team (1..32 warps) per sequence: about 1024 k-mers per warp, as many teams per CTA as fit
-TeamGeometry team_geometry(uint64_t nk_max, size_t team_bytes) {
+TeamGeometry team_geometry(uint64_t nk_max, size_t team_bytes, size_t cta_fixed_bytes = 0) {
     TeamGeometry g{};
     uint32_t tw = 1;
     while (tw < 32 && (uint64_t)tw * 1024 < nk_max) tw <<= 1;
     team_bytes = align_up(team_bytes, 16);
     for (;;) {
-        uint32_t fit = (uint32_t)std::max<size_t>(1, SMEM_BUDGET / team_bytes);
+        uint32_t fit = (uint32_t)std::max<size_t>(1, (SMEM_BUDGET - cta_fixed_bytes) / team_bytes);
         uint32_t max_teams = 32 / tw;
         if (tw > 1 && max_teams > 15) max_teams = 15;  // named barriers 1..15
         if (tw < 32 && fit * tw < 16) {  // shared memory leaves too few warps: widen the teams
@@ -32,12 +32,15 @@ TeamGeometry team_geometry(uint64_t nk_max, size_t team_bytes) {
         g.teams_per_cta = std::min(max_teams, fit);
         g.team_smem_bytes = (uint32_t)team_bytes;
         g.block = (int)(tw * 32 * g.teams_per_cta);
-        g.smem = team_bytes * g.teams_per_cta;
+        g.smem = cta_fixed_bytes + team_bytes * g.teams_per_cta;
         return g;
     }
 }
 
 }  // namespace
+
+// deterministic natural logarithm, host copy of kmu_detmath.cuh (same operations, same results)
+static double host_det_log(double x);
 
 extern "C" {
 
@@ -157,4 +160,267 @@ int32_t kmu_sketch_superminhash(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k,
     return KMU_OK;
 }
 
+int32_t kmu_sketch_setsketch(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t hash_kind,
+                             const kmu_setsketch_params* prm, int32_t sig_bytes, int32_t whole, void* sig,
+                             int32_t sig_on_device) {
+    if (!ctx || !b) return fail(KMU_EINVAL, "null argument");
+    if (int32_t a = kmu_check_kmer_args(b, k, kmer_type, hash_kind)) return a;
+    kmu_setsketch_params def{1.001, 4096, 20.0, 65534};  // SetSketchParams::default()
+    const kmu_setsketch_params P0 = prm ? *prm : def;
+    if (sig_bytes != 2 && sig_bytes != 4 && sig_bytes != 8) return fail(KMU_EINVAL, "sig_bytes must be 2, 4 or 8 (u16 / u32 / u64 registers)");
+    if (!(P0.b > 1.0) || !(P0.a > 0.0) || P0.m < 1) return fail(KMU_EINVAL, "SetSketch needs b > 1, a > 0, m >= 1");
+    const uint64_t reg_max = sig_bytes == 2 ? 0xFFFFull : 0x7FFFFFFEull;
+    if (P0.q + 1 > reg_max) return fail(KMU_EINVAL, "q + 1 = %llu does not fit the register type", (unsigned long long)(P0.q + 1));
+    const uint32_t m = (uint32_t)P0.m;
+    const size_t table_bytes = 2 * 264 * sizeof(double);
+    const size_t team_bytes = align_up((size_t)m * 4, 16) + 32;
+    if (P0.m > 0xFFFFFFull || team_bytes + table_bytes > SMEM_BUDGET)
+        return fail(KMU_EINVAL, "m = %llu registers do not fit the shared memory of one SM", (unsigned long long)P0.m);
+    if (b->nseq == 0 && !whole) return KMU_OK;
+    if (!sig) return fail(KMU_EINVAL, "null signature buffer");
+    if (b->nseq >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "more than 2^32-1 sequences in one batch");
+    uint64_t total_kmers = 0;
+    for (uint64_t L : b->h_nbases) {
+        if (L >= 0xFFFFFF00ull) return fail(KMU_EINVAL, "a single sequence is limited to 2^32 - 256 bases");
+        total_kmers += L >= k ? L - k + 1 : 0;
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    cudaStream_t st = ctx->stream;
+    const size_t nrows = whole ? 1 : b->nseq;
+    const size_t out_bytes = nrows * m * (size_t)sig_bytes;
+    void* d_sig = sig;
+    if (!sig_on_device) {
+        CUDA_TRY(ctx->sig_dev.reserve(out_bytes));
+        d_sig = ctx->sig_dev.p;
+    }
+    uint64_t launches = 0;
+    cudaEventRecord(ctx->ev[0], st);
+    int32_t rc = kmu_ensure_order(ctx, b, k, &launches);
+    if (rc) return rc;
+    // counters: [0..127] work counters, [128] slow count, [129] exact count
+    CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * 256));
+    CUDA_TRY(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * 256, st));
+    unsigned long long* d_work = (unsigned long long*)ctx->counters.p;
+    // lists: slow | exact | kmin, nseq + 1 entries each; then m whole-batch registers
+    CUDA_TRY(ctx->overflow.reserve(sizeof(uint32_t) * (3 * (b->nseq + 1) + m)));
+    uint32_t* d_slow = (uint32_t*)ctx->overflow.p;
+    uint32_t* d_exact = d_slow + (b->nseq + 1);
+    uint32_t* d_kmin = d_exact + (b->nseq + 1);
+    uint32_t* d_whole = d_kmin + (b->nseq + 1);
+    kmu::SskParams P{};
+    P.packed = b->packed;
+    P.byte_off = b->byte_off;
+    P.nbases = b->nbases;
+    P.order = (const uint32_t*)b->order_cache.order.p;
+    P.k = k;
+    P.kmer_type = kmer_type;
+    P.hash_kind = hash_kind;
+    P.C.a = P0.a;
+    P.C.inva = 1.0 / P0.a;
+    P.C.lnb = host_det_log(P0.b);
+    P.C.ln_term = std::log(1e4 * (double)m);
+    P.C.m = m;
+    P.C.iq1 = (int)P0.q + 1;
+    P.sig = d_sig;
+    P.sig_bytes = sig_bytes;
+    P.kmin_out = d_kmin;
+    P.slow_count = d_work + 128;
+    P.slow_list = d_slow;
+    P.exact_count = d_work + 129;
+    P.exact_list = d_exact;
+    P.exact_nk_max = 16 * m;
+    P.whole_regs = d_whole;
+    int ci = 0;
+    auto run_exact = [&](const uint32_t* list, uint64_t count, bool group) -> int32_t {
+        kmu::SskParams Q = P;
+        Q.order = list;
+        Q.first = 0;
+        Q.count = count;
+        Q.group = group ? 1 : 0;
+        Q.work_counter = d_work + ci++;
+        const uint64_t per_warp = align_up((uint64_t)m * 4, 16) + 32ull * 2 * m * sizeof(uint32_t);
+        uint64_t warps = group ? 1 : std::min<uint64_t>(count, (uint64_t)ctx->sm_count * 8);
+        const uint64_t budget = 8ull << 30;
+        if (warps * per_warp > budget) warps = std::max<uint64_t>(1, budget / per_warp);
+        CUDA_TRY(ctx->table_scratch.reserve(warps * per_warp));
+        ctx->table_scratch_clean = false;
+        CUDA_TRY(cudaMemsetAsync(ctx->table_scratch.p, 0, warps * per_warp, st));
+        Q.scratch = (uint8_t*)ctx->table_scratch.p;
+        Q.scratch_per_warp = per_warp;
+        CUDA_TRY(kmu::launch_ssk_exact(Q, (int)warps, st));
+        ++launches;
+        return KMU_OK;
+    };
+
+    if (whole) {
+        // the speculative level from the total number of k-mers (same formula as the device side)
+        const double ratio = (double)total_kmers * 0.25 * P.C.a / P.C.ln_term;
+        uint32_t kspec = 0;
+        if (ratio > 1.0) {
+            const double kf = 1.0 + std::floor(std::log(ratio) / P.C.lnb);
+            kspec = (uint32_t)std::min(kf, (double)(P.C.iq1 - 1));
+        }
+        bool done = false;
+        if (total_kmers > P.exact_nk_max && kspec > 0) {
+            kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
+            const size_t smem = table_bytes + (size_t)m * 4;
+            std::vector<uint32_t> regs(m);
+            for (int pass = 0; pass < 2 && !done; ++pass) {
+                CUDA_TRY(cudaMemsetAsync(d_whole, 0, sizeof(uint32_t) * m, st));
+                CUDA_TRY(cudaMemsetAsync(P.slow_count, 0, sizeof(unsigned long long), st));
+                const double xcut = std::exp(-(double)kspec * P.C.lnb) * (1.0 + 1e-6);
+                const uint64_t nchunks = (b->packed_bytes + 63) / 64;
+                const int grid = (int)std::min<uint64_t>((nchunks + 511) / 512, (uint64_t)ctx->sm_count * 2);
+                CUDA_TRY(kmu::launch_ssk_whole(P, v, b->packed_bytes, kspec, xcut, std::max(grid, 1), smem, st));
+                ++launches;
+                unsigned long long ovf = 0;
+                CUDA_TRY(cudaMemcpyAsync(regs.data(), d_whole, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaMemcpyAsync(&ovf, P.slow_count, sizeof(ovf), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                const uint32_t mn = *std::min_element(regs.begin(), regs.end());
+                if (!ovf && mn >= kspec) done = true;
+                else if (ovf || mn == 0) break;  // exact path
+                else kspec = mn;                 // a true lower bound of every final register: cannot fail again
+            }
+            if (done) {
+                CUDA_TRY(kmu::launch_ssk_store(d_whole, m, d_sig, sig_bytes, st));
+                ++launches;
+            }
+        }
+        if (!done) {
+            if (b->nseq == 0) {
+                CUDA_TRY(cudaMemsetAsync(d_sig, 0, out_bytes, st));
+            } else {
+                rc = run_exact((const uint32_t*)b->order_cache.order.p, b->nseq, true);
+                if (rc) return rc;
+            }
+        }
+    } else {
+        std::vector<OctaveClass> classes = kmu_octave_classes(b);
+        if (classes.size() > 100) return fail(KMU_EINVAL, "too many launch classes");
+        struct Launch { uint64_t first, count; TeamGeometry g; };
+        std::vector<Launch> ls;
+        for (const OctaveClass& c : classes) {
+            TeamGeometry g = team_geometry(c.nk_max, team_bytes, table_bytes);
+            if (!ls.empty() && ls.back().g.team_warps == g.team_warps && ls.back().g.teams_per_cta == g.teams_per_cta &&
+                ls.back().first + ls.back().count == c.first) {
+                ls.back().count += c.count;
+            } else {
+                ls.push_back({c.first, c.count, g});
+            }
+        }
+        auto run_team = [&](const kmu::SskParams& base, const uint32_t* order, uint64_t first, uint64_t count,
+                            const TeamGeometry& g) -> int32_t {
+            kmu::SskParams Q = base;
+            Q.order = order;
+            Q.first = first;
+            Q.count = count;
+            Q.work_counter = d_work + ci++;
+            Q.team_warps = g.team_warps;
+            Q.team_smem_bytes = g.team_smem_bytes;
+            const uint64_t ctas_needed = (count + g.teams_per_cta - 1) / g.teams_per_cta;
+            const int grid = (int)std::min<uint64_t>(ctas_needed, (uint64_t)ctx->sm_count);
+            CUDA_TRY(kmu::launch_ssk_team(Q, std::max(grid, 1), g.block, g.smem, st));
+            ++launches;
+            return KMU_OK;
+        };
+        for (const Launch& l : ls) {
+            rc = run_team(P, P.order, l.first, l.count, l.g);
+            if (rc) return rc;
+        }
+        unsigned long long cnt[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(cnt, P.slow_count, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (cnt[0]) {  // failed speculations: once more with the level they reached; anything left goes to the exact path
+            kmu::SskParams Q = P;
+            Q.kspec_in = d_kmin;
+            Q.slow_count = P.exact_count;
+            Q.slow_list = P.exact_list;
+            rc = run_team(Q, d_slow, 0, cnt[0], team_geometry(b->order_cache.nk_longest, team_bytes, table_bytes));
+            if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(cnt, P.slow_count, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        if (cnt[1]) {
+            rc = run_exact(d_exact, cnt[1], false);
+            if (rc) return rc;
+        }
+    }
+    cudaEventRecord(ctx->ev[1], st);
+    if (!sig_on_device) {
+        cudaEventRecord(ctx->ev[4], st);
+        CUDA_TRY(cudaMemcpyAsync(sig, d_sig, out_bytes, cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(ctx->ev[5], st);
+        ctx->last.d2h_bytes = out_bytes;
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(KMU_ECUDA, "SetSketch kernels failed: %s", cudaGetErrorString(e));
+    cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    if (!sig_on_device) cudaEventElapsedTime(&ctx->last.d2h_ms, ctx->ev[4], ctx->ev[5]);
+    ctx->launches += launches;
+    ctx->last.launches = launches;
+    return KMU_OK;
+}
+
 }  // extern "C"
+
+// ---- host copy of det_log (kmu_detmath.cuh): ln(b) must be the same double on the host, on the
+// device and in the oracle.  This translation unit is compiled with --fmad=false.
+#include <cstring>
+static inline uint64_t hd_bits(double v) { uint64_t b; std::memcpy(&b, &v, 8); return b; }
+static inline double hd_from(uint64_t b) { double v; std::memcpy(&v, &b, 8); return v; }
+static double host_det_log(double x) {
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+                 Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+                 Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    uint64_t bits = hd_bits(x);  // callers pass 1 < b < 2^1000: normal, positive
+    int32_t hx = (int32_t)(bits >> 32);
+    const uint32_t lx = (uint32_t)bits;
+    int32_t k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int32_t i0 = (hx + 0x95f64) & 0x100000;
+    x = hd_from(((uint64_t)(uint32_t)(hx | (i0 ^ 0x3ff00000)) << 32) | lx);
+    k += (i0 >> 20);
+    const volatile double f = x - 1.0;
+    const double dk = (double)k;
+    if ((0x000fffff & (2 + hx)) < 3) {
+        if (f == 0.0) return k == 0 ? 0.0 : dk * ln2_hi + dk * ln2_lo;
+        const volatile double ff = f * f;
+        const volatile double inner = 0.33333333333333333 * f;
+        const volatile double R = ff * (0.5 - inner);
+        if (k == 0) return f - R;
+        const volatile double t = dk * ln2_lo;
+        const volatile double u = R - t;
+        const volatile double hi = dk * ln2_hi;
+        return hi - (u - f);
+    }
+    const volatile double s = f / (2.0 + f);
+    const volatile double z = s * s;
+    int32_t i = hx - 0x6147a;
+    const volatile double w = z * z;
+    const int32_t j = 0x6b851 - hx;
+    volatile double a1 = w * Lg6; a1 = Lg4 + a1; a1 = w * a1; a1 = Lg2 + a1;
+    const volatile double t1 = w * a1;
+    volatile double a2 = w * Lg7; a2 = Lg5 + a2; a2 = w * a2; a2 = Lg3 + a2; a2 = w * a2; a2 = Lg1 + a2;
+    const volatile double t2 = z * a2;
+    i |= j;
+    const volatile double R = t2 + t1;
+    if (i > 0) {
+        volatile double hfsq = 0.5 * f; hfsq = hfsq * f;
+        volatile double v1 = hfsq + R; v1 = s * v1;
+        if (k == 0) { const volatile double d = hfsq - v1; return f - d; }
+        const volatile double t = dk * ln2_lo;
+        volatile double v2 = v1 + t; v2 = hfsq - v2; v2 = v2 - f;
+        const volatile double hi = dk * ln2_hi;
+        return hi - v2;
+    }
+    volatile double v1 = f - R; v1 = s * v1;
+    if (k == 0) return f - v1;
+    const volatile double t = dk * ln2_lo;
+    volatile double v2 = v1 - t; v2 = v2 - f;
+    const volatile double hi = dk * ln2_hi;
+    return hi - v2;
+}

@@ -21,8 +21,6 @@
 
 namespace kmu {
 
-constexpr uint32_t CHUNK_BYTES = 64;
-
 __device__ __forceinline__ uint64_t fmix64(uint64_t h) {
     h ^= h >> 33;
     h *= 0xff51afd7ed558ccdULL;
@@ -135,49 +133,13 @@ __global__ void count_init_kernel(CountTable t, int key64) {
     }
 }
 
-// last sequence s with byte_off[s] <= byte (byte_off ascending, byte_off[0] == 0)
-__device__ __forceinline__ uint64_t seq_of_byte(const uint64_t* __restrict__ byte_off, uint64_t nseq, uint64_t byte) {
-    uint64_t lo = 0, hi = nseq;
-    while (hi - lo > 1) {
-        uint64_t mid = (lo + hi) >> 1;
-        if (__ldg(byte_off + mid) <= byte) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
-// Calls f(compressed canonical-or-forward value) for every k-mer that starts inside chunk `c`.
-template <typename V, typename F>
-__device__ __forceinline__ void for_each_kmer_in_chunk(const SeqView& b, uint64_t total_bytes, uint64_t c, uint32_t k,
-                                                       bool canonical, F&& f) {
-    const uint64_t byte0 = c * CHUNK_BYTES;
-    const uint64_t byte1 = min(byte0 + (uint64_t)CHUNK_BYTES, total_bytes);
-    uint64_t s = seq_of_byte(b.byte_off, b.nseq, byte0);
-    while (s < b.nseq) {
-        const uint64_t sb = __ldg(b.byte_off + s);
-        if (sb >= byte1) break;
-        const uint64_t L = __ldg(b.nbases + s);
-        const uint64_t nk = L >= k ? L - k + 1 : 0;
-        const uint64_t p_lo = byte0 > sb ? (byte0 - sb) * 4 : 0;
-        const uint64_t p_hi = min(nk, (byte1 - sb) * 4);
-        if (p_lo < p_hi) {
-            KmerWalker<V> wk;
-            wk.start((const uint32_t*)(b.packed + sb), p_lo, k);
-            for (uint64_t p = p_lo; p < p_hi; ++p) {
-                wk.roll();
-                f(wk.prekey(canonical));
-            }
-        }
-        ++s;
-    }
-}
-
 template <typename V>
 __global__ void __launch_bounds__(256) count_insert_seqs_kernel(SeqView b, uint64_t total_bytes, uint32_t k, int canonical,
                                                                  CountTable t) {
     const uint64_t nchunks = (total_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES;
     bool ok = true;
     for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < nchunks; c += (uint64_t)gridDim.x * blockDim.x)
-        for_each_kmer_in_chunk<V>(b, total_bytes, c, k, canonical != 0, [&](V key) { ok &= CountOps<V>::insert(t, key, 1u); });
+        for_each_kmer_in_chunk<V, false>(b, total_bytes, c, k, canonical != 0, [&](V key) { ok &= CountOps<V>::insert(t, key, 1u); });
     if (!ok) *t.overflow = 1ULL;
 }
 
@@ -278,7 +240,7 @@ __global__ void __launch_bounds__(256) count_partition_kernel(SeqView b, uint64_
     for (uint64_t tile = blockIdx.x; tile * blockDim.x < nchunks; tile += gridDim.x) {
         const uint64_t c = tile * blockDim.x + threadIdx.x;
         if (c < nchunks)
-            for_each_kmer_in_chunk<V>(b, total_bytes, c, k, canonical != 0, [&](V key) {
+            for_each_kmer_in_chunk<V, false>(b, total_bytes, c, k, canonical != 0, [&](V key) {
                 const uint32_t p = owner_of<V>(key, nparts);
                 const unsigned long long pos = atomicAdd(&cur[p], 1ULL);
                 if (WRITE) out[pos] = key;

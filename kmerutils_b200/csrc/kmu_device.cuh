@@ -427,4 +427,48 @@ struct KmerSource<V, true> {
     using Walker = KmerWalkerAA<V>;
 };
 
+// ----------------------------------------------------------------------------
+//  Chunked traversal of a whole batch: the byte buffer is cut into 64-byte chunks (256 bases or 64
+//  residues); a thread owns the k-mers that START in its chunk, finds the sequence(s) overlapping
+//  it by binary search in the batch's byte offsets and rolls the windows in registers.
+// ----------------------------------------------------------------------------
+constexpr uint32_t CHUNK_BYTES = 64;
+
+// last sequence s with byte_off[s] <= byte (byte_off ascending, byte_off[0] == 0)
+__device__ __forceinline__ uint64_t seq_of_byte(const uint64_t* __restrict__ byte_off, uint64_t nseq, uint64_t byte) {
+    uint64_t lo = 0, hi = nseq;
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (__ldg(byte_off + mid) <= byte) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Calls f(pre-key) for every k-mer that starts inside chunk `c` (pre-key: canonical or forward value)
+template <typename V, bool AA, typename F>
+__device__ __forceinline__ void for_each_kmer_in_chunk(const SeqView& b, uint64_t total_bytes, uint64_t c, uint32_t k,
+                                                       bool canonical, F&& f) {
+    constexpr uint64_t PER_BYTE = AA ? 1 : 4;  // sequence positions per byte
+    const uint64_t byte0 = c * CHUNK_BYTES;
+    const uint64_t byte1 = min(byte0 + (uint64_t)CHUNK_BYTES, total_bytes);
+    uint64_t s = seq_of_byte(b.byte_off, b.nseq, byte0);
+    while (s < b.nseq) {
+        const uint64_t sb = __ldg(b.byte_off + s);
+        if (sb >= byte1) break;
+        const uint64_t L = __ldg(b.nbases + s);
+        const uint64_t nk = L >= k ? L - k + 1 : 0;
+        const uint64_t p_lo = byte0 > sb ? (byte0 - sb) * PER_BYTE : 0;
+        const uint64_t p_hi = min(nk, (byte1 - sb) * PER_BYTE);
+        if (p_lo < p_hi) {
+            typename KmerSource<V, AA>::Walker wk;
+            wk.start((const uint32_t*)(b.packed + sb), p_lo, k);
+            for (uint64_t p = p_lo; p < p_hi; ++p) {
+                wk.roll();
+                f(wk.prekey(canonical));
+            }
+        }
+        ++s;
+    }
+}
+
 }  // namespace kmu

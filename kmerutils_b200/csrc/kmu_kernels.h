@@ -138,6 +138,44 @@ struct SmhParams {
 cudaError_t launch_smh_fast(const SmhParams& P, bool key64, bool f64, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t launch_smh_exact(const SmhParams& P, bool key64, bool f64, int grid, cudaStream_t st);
 
+// ---- SetSketch (kmu_setsketch.cu) ---------------------------------------------------------------
+struct SskConsts {
+    double a, inva, lnb;  // SetSketchParams.a, 1 / a, ln(b) (deterministic log)
+    double ln_term;       // ln(1e4 m)
+    uint32_t m;
+    int iq1;              // q + 1
+};
+struct SskParams {
+    const uint8_t* packed;
+    const uint64_t* byte_off;
+    const uint64_t* nbases;
+    const uint32_t* order;
+    uint64_t first, count;
+    unsigned long long* work_counter;
+    uint32_t k;
+    int kmer_type, hash_kind;
+    SskConsts C;
+    void* sig;      // registers as u16 / u32 / u64 (sig_bytes 2 / 4 / 8)
+    int sig_bytes;
+    uint32_t team_warps, team_smem_bytes;
+    const uint32_t* kspec_in;  // per-sequence level for a redo launch, or nullptr
+    uint32_t* kmin_out;        // smallest register reached by a failed speculation
+    unsigned long long* slow_count;
+    uint32_t* slow_list;
+    unsigned long long* exact_count;
+    uint32_t* exact_list;
+    uint32_t exact_nk_max;
+    uint32_t* whole_regs;  // whole-batch mode: m global registers
+    uint8_t* scratch;      // exact path
+    uint64_t scratch_per_warp;
+    int group;             // exact path: all listed sequences go into ONE sketch
+};
+cudaError_t launch_ssk_team(const SskParams& P, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t launch_ssk_whole(const SskParams& P, const SeqView& b, uint64_t total_bytes, uint32_t kspec, double xcut,
+                             int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_ssk_store(const uint32_t* regs, uint32_t m, void* out, int sig_bytes, cudaStream_t st);
+cudaError_t launch_ssk_exact(const SskParams& P, int grid, cudaStream_t st);
+
 // ---- counting table (kmu_count.cu) ----------------------------------------------------------
 struct CountTable {
     void* slots;                  // u32 keys: u64 slot (key << 32 | count); u64 keys: 16-byte slot {key, count}

@@ -1,0 +1,411 @@
+// kmu_setsketch.cu -- SetSketch (HyperLogLog-like) registers on sm_100a.
+//
+// Replaces HyperLogLogSketch::sketch_compressedkmer (one sketch per sequence,
+// src/sketching/setsketchert.rs:758-802), ::sketch_compressedkmer_seqs(_block) (one sketch for a
+// whole file, :677-724, 811-895; its block split + SetSketcher::merge is an element-wise max) and
+// the amino-acid mirror (src/aautils/setsketchert.rs:790-1011): every k-mer is streamed through
+// probminhash's SetSketcher::sketch (Ertl 2021, SetSketch1).
+//
+// GPU formulation.  Item x draws an increasing sequence x_0 < x_1 < ... (exponential spacings,
+// rand_distr's ziggurat Exp1), turns x_j into the level k_j = clamp(floor(1 - log_b x_j), 0, q + 1)
+// and offers it to register slot_j of an incremental Fisher-Yates shuffle; a register keeps the
+// MAXIMUM.  The sequential algorithm stops an item as soon as k_j <= lower_k, a lower bound of the
+// smallest register: such points cannot raise any register.  Hence
+//   * speculative path: every item is cut at a level K_spec derived from the number of k-mers; the
+//     result is exact iff the smallest register ends >= K_spec, which is verified.  A failed sketch
+//     is redone with K_spec' = the smallest register it reached (a true lower bound), which cannot
+//     fail.  Almost every item stops at j = 0 on a comparison of x_0 with a precomputed cut, before
+//     any logarithm.
+//   * exact path (few k-mers relative to m): one warp per sketch, 32 items per round with a full
+//     lazily-reset permutation per lane in global scratch, lower_k = min register between rounds.
+// log / exp are the deterministic routines of kmu_detmath.cuh (bit-identical to the CPU oracle).
+#include <cstdint>
+
+#include "kmu_detmath.cuh"
+#include "kmu_device.cuh"
+#include "kmu_kernels.h"
+#include "zig_exp_tables.h"
+
+namespace kmu {
+
+__constant__ double c_zig_x[257] = ZIG_EXP_TABLE_X;
+__constant__ double c_zig_f[257] = ZIG_EXP_TABLE_F;
+
+struct ZigTables {
+    const double* x;  // 257 entries each, in shared memory
+    const double* f;
+};
+
+__device__ __forceinline__ void load_zig_tables(double* sx, double* sf) {
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) {
+        sx[i] = c_zig_x[i];
+        sf[i] = c_zig_f[i];
+    }
+}
+
+// rand 0.9 StandardUniform for f64: 53 bits, multiply method
+__device__ __forceinline__ double std_uniform_f64(Xoshiro256pp& rng) {
+    return __dmul_rn((double)(rng.next_u64() >> 11), 1.0 / 9007199254740992.0);
+}
+
+// rand_distr 0.5 Exp1 (ziggurat)
+__device__ __forceinline__ double exp1_sample(Xoshiro256pp& rng, const ZigTables& z) {
+    for (;;) {
+        const uint64_t bits = rng.next_u64();
+        const uint32_t i = (uint32_t)bits & 0xffu;
+        const double u = __dsub_rn(__longlong_as_double((long long)((bits >> 12) | 0x3FF0000000000000ULL)),
+                                   1.0 - 2.220446049250313e-16 / 2.0);
+        const double x = __dmul_rn(u, z.x[i]);
+        if (x < z.x[i + 1]) return x;
+        if (i == 0) return __dsub_rn(ZIG_EXP_R, det_log(std_uniform_f64(rng)));
+        const double f1 = z.f[i + 1];
+        if (__dadd_rn(f1, __dmul_rn(__dsub_rn(z.f[i], f1), std_uniform_f64(rng))) < det_exp(-x)) return x;
+    }
+}
+
+constexpr uint32_t SSK_SPARSE_CAP = 24;  // points an item may place in the speculative kernels
+
+// Points of one item against the registers.  Returns false if the item needed more than
+// SSK_SPARSE_CAP points (the caller redoes the sketch on the exact path).
+__device__ __forceinline__ bool ssk_item_points(Xoshiro256pp& rng, const ZigTables& zt, const SskConsts& C, uint32_t kspec,
+                                                double xcut, uint32_t* regs) {
+    uint32_t idx[SSK_SPARSE_CAP], val[SSK_SPARSE_CAP];
+    uint32_t n = 0;
+    double x = 0.0;
+    const uint32_t m = C.m;
+    for (uint32_t j = 0; j < m; ++j) {
+        const double e = exp1_sample(rng, zt);
+        x = __dadd_rn(x, __dmul_rn(__ddiv_rn(C.inva, (double)(m - j)), e));
+        if (x > xcut) break;  // certainly log_b(x) > -K_spec: the level is <= K_spec
+        const double lb = __ddiv_rn(det_log(x), C.lnb);
+        if (lb > -(double)kspec) break;
+        const int z = __double2int_rd(__dsub_rn(1.0, lb));  // floor, saturating
+        const int kk = max(0, min(C.iq1, z));
+        if ((uint32_t)kk <= kspec) break;
+        if (j >= SSK_SPARSE_CAP) return false;
+        // FYshuffle::next: idx = lastidx + (usize)(U * (m - lastidx)), swap, value at idx is the slot
+        const double xsi = rng.unif01();
+        const uint32_t pi = j + (uint32_t)__double2uint_rz(__dmul_rn(xsi, (double)(m - j)));
+        uint32_t vj = j, vk = pi;
+        int pos_k = -1;
+        for (uint32_t t = 0; t < n; ++t) {
+            if (idx[t] == j) vj = val[t];
+            if (idx[t] == pi) {
+                vk = val[t];
+                pos_k = (int)t;
+            }
+        }
+        uint32_t slot = vj;
+        if (pi != j) {
+            slot = vk;
+            if (pos_k >= 0) {
+                val[pos_k] = vj;
+            } else {
+                idx[n] = pi;
+                val[n] = vj;
+                ++n;
+            }
+        }
+        if ((uint32_t)kk > *(volatile uint32_t*)(regs + slot)) atomicMax(regs + slot, (uint32_t)kk);
+    }
+    return true;
+}
+
+// speculative level for n k-mers: with D >= n / 4 distinct items every register ends >= K_spec except
+// with probability ~1e-4:  K_spec = 1 + floor(log_b(D a / ln(1e4 m)))
+__device__ __forceinline__ uint32_t ssk_kspec(uint64_t nk, const SskConsts& C) {
+    const double ratio = (double)nk * 0.25 * C.a / C.ln_term;
+    if (!(ratio > 1.0)) return 0;
+    const double kf = 1.0 + floor(log(ratio) / C.lnb);
+    const double cap = (double)(C.iq1 - 1);
+    return (uint32_t)(kf < cap ? kf : cap);
+}
+__device__ __forceinline__ double ssk_xcut(uint32_t kspec, const SskConsts& C) {
+    return exp(-(double)kspec * C.lnb) * (1.0 + 1e-6);
+}
+
+__device__ __forceinline__ void ssk_store(void* out, int sig_bytes, size_t i, uint32_t v) {
+    if (sig_bytes == 2) ((uint16_t*)out)[i] = (uint16_t)v;
+    else if (sig_bytes == 4) ((uint32_t*)out)[i] = v;
+    else ((uint64_t*)out)[i] = v;
+}
+
+struct SskTeamShared {
+    uint32_t seq, nbases, valid, flag, minreg;
+    uint32_t pad;
+    uint64_t byte_off;
+};
+
+// ---- one sketch per sequence, one team per sequence ---------------------------------------------
+template <typename V, bool AA>
+__global__ void __launch_bounds__(1024, 1) ssk_team_kernel(const SskParams P) {
+    using TK = typename KmerSource<V, AA>::Task;
+    extern __shared__ __align__(16) uint8_t smem[];
+    double* zx = (double*)smem;
+    double* zf = zx + 264;
+    load_zig_tables(zx, zf);
+    const ZigTables zt{zx, zf};
+    Team team;
+    team.size = P.team_warps * 32;
+    team.id = threadIdx.x / team.size;
+    team.tid = threadIdx.x - team.id * team.size;
+    team.warp = team.tid >> 5;
+    team.lane = threadIdx.x & 31;
+    uint8_t* tbase = smem + 2 * 264 * sizeof(double) + (size_t)team.id * P.team_smem_bytes;
+    uint32_t* regs = (uint32_t*)tbase;
+    SskTeamShared* ts = (SskTeamShared*)(tbase + (((size_t)P.C.m * 4 + 15) & ~(size_t)15));
+    const V header = (V)word_header(P.kmer_type, P.k);
+    const bool canonical = hash_is_canonical(P.hash_kind);
+    const uint32_t k = P.k, m = P.C.m;
+    __syncthreads();
+
+    for (;;) {
+        team.sync();
+        if (team.tid == 0) {
+            const unsigned long long w = atomicAdd(P.work_counter, 1ULL);
+            ts->valid = w < P.count;
+            if (w < P.count) {
+                const uint32_t seq = P.order[P.first + w];
+                ts->seq = seq;
+                ts->nbases = (uint32_t)P.nbases[seq];
+                ts->byte_off = P.byte_off[seq];
+            }
+            ts->flag = 0;
+            ts->minreg = 0xFFFFFFFFu;
+        }
+        team.sync();
+        if (!ts->valid) break;
+        const uint32_t seq = ts->seq, L = ts->nbases;
+        const uint32_t* words = (const uint32_t*)(P.packed + ts->byte_off);
+        const uint32_t nk = L >= k ? L - k + 1 : 0;
+        const uint32_t kspec = P.kspec_in ? P.kspec_in[seq] : ssk_kspec(nk, P.C);
+        if (nk && (kspec == 0 || nk <= P.exact_nk_max)) {  // few k-mers: the exact path is cheaper and always right
+            if (team.tid == 0) P.exact_list[atomicAdd(P.exact_count, 1ULL)] = seq;
+            continue;
+        }
+        const double xcut = ssk_xcut(kspec, P.C);
+        for (uint32_t j = team.tid; j < m; j += team.size) regs[j] = 0;
+        team.sync();
+        const uint32_t ntasks = (nk + 15) >> 4;
+        bool ok = true;
+        for (uint32_t task = team.tid; task < ntasks; task += team.size) {
+            TK tk;
+            uint32_t p = task << 4;
+            tk.init(words, p, k);
+            const uint32_t pend = min(p + 16, nk);
+#pragma unroll 1
+            for (uint32_t t = 0; p < pend; ++t, ++p) {
+                const V key = finalize_key<V>(tk.get(t, canonical), header, P.hash_kind);
+                Xoshiro256pp rng;
+                rng.seed(nohash_seed(key));
+                ok &= ssk_item_points(rng, zt, P.C, kspec, xcut, regs);
+            }
+        }
+        if (!ok) ts->flag = 2;
+        team.sync();
+        uint32_t mn = 0xFFFFFFFFu;
+        for (uint32_t j = team.tid; j < m; j += team.size) {
+            const uint32_t v = regs[j];
+            ssk_store(P.sig, P.sig_bytes, (size_t)seq * m + j, v);
+            mn = v < mn ? v : mn;
+        }
+        mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+        if (team.lane == 0 && nk) atomicMin(&ts->minreg, mn);
+        team.sync();
+        if (team.tid == 0 && nk) {
+            if (ts->flag == 2) {  // an item overflowed the sparse permutation: exact path
+                P.exact_list[atomicAdd(P.exact_count, 1ULL)] = seq;
+            } else if (ts->minreg < kspec) {  // speculation failed: redo with the level reached (a true lower bound)
+                P.kmin_out[seq] = ts->minreg;
+                P.slow_list[atomicAdd(P.slow_count, 1ULL)] = seq;
+            }
+        }
+    }
+}
+
+// ---- one sketch for the whole batch: every CTA keeps partial registers in shared memory ----------
+template <typename V, bool AA>
+__global__ void __launch_bounds__(512, 2) ssk_whole_kernel(const SskParams P, SeqView b, uint64_t total_bytes, uint32_t kspec,
+                                                            double xcut) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    double* zx = (double*)smem;
+    double* zf = zx + 264;
+    uint32_t* regs = (uint32_t*)(zf + 264);
+    load_zig_tables(zx, zf);
+    const ZigTables zt{zx, zf};
+    const uint32_t m = P.C.m;
+    for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) regs[j] = 0;
+    __syncthreads();
+    const V header = (V)word_header(P.kmer_type, P.k);
+    const bool canonical = hash_is_canonical(P.hash_kind);
+    const uint64_t nchunks = (total_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES;
+    bool ok = true;
+    for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < nchunks; c += (uint64_t)gridDim.x * blockDim.x)
+        for_each_kmer_in_chunk<V, AA>(b, total_bytes, c, P.k, canonical, [&](V pk) {
+            const V key = finalize_key<V>(pk, header, P.hash_kind);
+            Xoshiro256pp rng;
+            rng.seed(nohash_seed(key));
+            ok &= ssk_item_points(rng, zt, P.C, kspec, xcut, regs);
+        });
+    if (!ok) *P.slow_count = 1ULL;  // overflow flag of the whole-batch path
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) {
+        const uint32_t v = regs[j];
+        if (v) atomicMax(P.whole_regs + j, v);
+    }
+}
+
+// registers (u32) -> signature type
+__global__ void ssk_store_kernel(const uint32_t* regs, uint32_t m, void* out, int sig_bytes) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x)
+        ssk_store(out, sig_bytes, j, regs[j]);
+}
+
+// ---- exact path: one warp per sketch --------------------------------------------------------------
+// group mode (P.group != 0): one warp sketches ALL sequences order[first .. first+count) into one
+// signature (row 0); otherwise warps pull single sequences.
+template <typename V, bool AA>
+__global__ void __launch_bounds__(32) ssk_exact_kernel(const SskParams P) {
+    using Walker = typename KmerSource<V, AA>::Walker;
+    __shared__ double zx[264], zf[264];
+    load_zig_tables(zx, zf);
+    __syncwarp();
+    const ZigTables zt{zx, zf};
+    const int lane = threadIdx.x;
+    const uint32_t k = P.k, m = P.C.m;
+    const V header = (V)word_header(P.kmer_type, P.k);
+    const bool canonical = hash_is_canonical(P.hash_kind);
+    uint8_t* base = P.scratch + (size_t)blockIdx.x * P.scratch_per_warp;
+    uint32_t* regs = (uint32_t*)base;
+    uint32_t* pl = regs + ((m + 3) & ~3u) + (size_t)lane * 2 * m;
+    uint32_t* ql = pl + m;
+    uint32_t stamp = 0;
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(P.work_counter, 1ULL);
+        w = __shfl_sync(0xFFFFFFFFu, w, 0);
+        const uint64_t nwork = P.group ? 1 : P.count;
+        if (w >= nwork) break;
+        for (uint32_t j = lane; j < m; j += 32) regs[j] = 0;
+        __syncwarp();
+        uint32_t lower = 0;
+        const uint64_t s_begin = P.group ? 0 : w, s_end = P.group ? P.count : w + 1;
+        for (uint64_t si = s_begin; si < s_end; ++si) {
+            const uint32_t seq = P.order[P.first + si];
+            const uint32_t L = (uint32_t)P.nbases[seq];
+            const uint32_t* words = (const uint32_t*)(P.packed + P.byte_off[seq]);
+            const uint32_t nk = L >= k ? L - k + 1 : 0;
+            for (uint32_t p0 = 0; p0 < nk; p0 += 32) {
+                const uint32_t pos = p0 + lane;
+                ++stamp;
+                if (pos < nk) {
+                    Walker wk;
+                    wk.start(words, pos, k);
+                    wk.roll();
+                    const V key = finalize_key<V>(wk.prekey(canonical), header, P.hash_kind);
+                    Xoshiro256pp rng;
+                    rng.seed(nohash_seed(key));
+                    double x = 0.0;
+                    for (uint32_t j = 0; j < m; ++j) {
+                        const double e = exp1_sample(rng, zt);
+                        x = __dadd_rn(x, __dmul_rn(__ddiv_rn(P.C.inva, (double)(m - j)), e));
+                        const double lb = __ddiv_rn(det_log(x), P.C.lnb);
+                        if (lb > -(double)lower) break;
+                        const int z = __double2int_rd(__dsub_rn(1.0, lb));
+                        const int kk = max(0, min(P.C.iq1, z));
+                        if ((uint32_t)kk <= lower) break;
+                        const double xsi = rng.unif01();
+                        const uint32_t pi = j + (uint32_t)__double2uint_rz(__dmul_rn(xsi, (double)(m - j)));
+                        if (ql[j] != stamp) {
+                            ql[j] = stamp;
+                            pl[j] = j;
+                        }
+                        if (ql[pi] != stamp) {
+                            ql[pi] = stamp;
+                            pl[pi] = pi;
+                        }
+                        const uint32_t slot = pl[pi];
+                        pl[pi] = pl[j];
+                        pl[j] = slot;
+                        if ((uint32_t)kk > *(volatile uint32_t*)(regs + slot)) atomicMax(regs + slot, (uint32_t)kk);
+                    }
+                }
+                __syncwarp();
+                uint32_t mn = 0xFFFFFFFFu;
+                for (uint32_t j = lane; j < m; j += 32) {
+                    const uint32_t v = *(volatile uint32_t*)(regs + j);
+                    mn = v < mn ? v : mn;
+                }
+                lower = __reduce_min_sync(0xFFFFFFFFu, mn);
+                __syncwarp();
+            }
+        }
+        const size_t row = P.group ? 0 : (size_t)P.order[P.first + w];
+        for (uint32_t j = lane; j < m; j += 32) ssk_store(P.sig, P.sig_bytes, row * m + j, regs[j]);
+        __syncwarp();
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------
+template <typename V, bool AA>
+static cudaError_t launch_team_t(const SskParams& P, int grid, int block, size_t smem, cudaStream_t st) {
+    auto kern = ssk_team_kernel<V, AA>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kern<<<grid, block, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ssk_team(const SskParams& P, int grid, int block, size_t smem, cudaStream_t st) {
+    switch (P.kmer_type) {
+        case KMU_KMERAA32: return launch_team_t<uint32_t, true>(P, grid, block, smem, st);
+        case KMU_KMERAA64: return launch_team_t<uint64_t, true>(P, grid, block, smem, st);
+        case KMU_KMER64: return launch_team_t<uint64_t, false>(P, grid, block, smem, st);
+        default: return launch_team_t<uint32_t, false>(P, grid, block, smem, st);
+    }
+}
+
+template <typename V, bool AA>
+static cudaError_t launch_whole_t(const SskParams& P, const SeqView& b, uint64_t total_bytes, uint32_t kspec, double xcut,
+                                  int grid, size_t smem, cudaStream_t st) {
+    auto kern = ssk_whole_kernel<V, AA>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kern<<<grid, 512, smem, st>>>(P, b, total_bytes, kspec, xcut);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ssk_whole(const SskParams& P, const SeqView& b, uint64_t total_bytes, uint32_t kspec, double xcut,
+                             int grid, size_t smem, cudaStream_t st) {
+    switch (P.kmer_type) {
+        case KMU_KMERAA32: return launch_whole_t<uint32_t, true>(P, b, total_bytes, kspec, xcut, grid, smem, st);
+        case KMU_KMERAA64: return launch_whole_t<uint64_t, true>(P, b, total_bytes, kspec, xcut, grid, smem, st);
+        case KMU_KMER64: return launch_whole_t<uint64_t, false>(P, b, total_bytes, kspec, xcut, grid, smem, st);
+        default: return launch_whole_t<uint32_t, false>(P, b, total_bytes, kspec, xcut, grid, smem, st);
+    }
+}
+
+cudaError_t launch_ssk_store(const uint32_t* regs, uint32_t m, void* out, int sig_bytes, cudaStream_t st) {
+    ssk_store_kernel<<<(m + 255) / 256, 256, 0, st>>>(regs, m, out, sig_bytes);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ssk_exact(const SskParams& P, int grid, cudaStream_t st) {
+    switch (P.kmer_type) {
+        case KMU_KMERAA32: ssk_exact_kernel<uint32_t, true><<<grid, 32, 0, st>>>(P); break;
+        case KMU_KMERAA64: ssk_exact_kernel<uint64_t, true><<<grid, 32, 0, st>>>(P); break;
+        case KMU_KMER64: ssk_exact_kernel<uint64_t, false><<<grid, 32, 0, st>>>(P); break;
+        default: ssk_exact_kernel<uint32_t, false><<<grid, 32, 0, st>>>(P); break;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace kmu

@@ -235,6 +235,24 @@ class Engine:
                                                dtype.itemsize, _p(out), 0))
         return out
 
+    def sketch_setsketch(self, batch, k, kmer_type, hash_kind=HASH_CANON_INVHASH, params=None, dtype=np.uint16,
+                         whole=False, out_device_ptr=None):
+        """SetSketch registers (HyperLogLogSketch): (nseq, m) array, or (m,) when whole=True (one sketch for the
+        batch, sketch_compressedkmer_seqs).  params = (b, m, a, q) or None for SetSketchParams::default()."""
+        dtype = np.dtype(dtype)
+        if dtype not in (np.dtype(np.uint16), np.dtype(np.uint32), np.dtype(np.uint64)):
+            raise ValueError("SetSketch registers are u16, u32 or u64")
+        prm = _lib.KmuSetSketchParams(*(params if params is not None else (1.001, 4096, 20.0, 65534)))
+        m = int(prm.m)
+        if out_device_ptr is not None:
+            check(self.lib.kmu_sketch_setsketch(self.ctx, batch.handle, k, kmer_type, hash_kind, C.byref(prm),
+                                                dtype.itemsize, int(bool(whole)), C.c_void_p(out_device_ptr), 1))
+            return None
+        out = np.zeros((1 if whole else len(batch), m), dtype=dtype)
+        check(self.lib.kmu_sketch_setsketch(self.ctx, batch.handle, k, kmer_type, hash_kind, C.byref(prm),
+                                            dtype.itemsize, int(bool(whole)), _p(out), 0))
+        return out[0] if whole else out
+
     def sketch_pmh3a_host(self, packed, byte_off, nbases, k, kmer_type, hash_kind, m, out):
         """One-shot: host packed buffer in, host signatures out (H2D + kernels + D2H)."""
         off = _as_u64(byte_off)

@@ -6,6 +6,9 @@
 // ============================================================================
 #include "kmer_oracle.hpp"
 
+#include "det_math.hpp"
+#include "zig_exp_tables.h"
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -566,6 +569,79 @@ void superminhash_seqs(const uint8_t* packed, const uint64_t* byte_off, const ui
     for (uint32_t j = 0; j < m; ++j) out[j] = smh.h[j];
 }
 
+// ---------------------------------------------------------------- SetSketch -------
+// rand_distr 0.5 Exp1 (ziggurat; tables regenerated by scripts/gen_ziggurat_tables.py) on top of
+// rand 0.9's StandardUniform f64 (53 bits, multiply method).
+const double ZIG_X[257] = ZIG_EXP_TABLE_X;
+const double ZIG_F[257] = ZIG_EXP_TABLE_F;
+inline double std_uniform_f64(Xoshiro256pp& rng) { return (double)(rng.next_u64() >> 11) * (1.0 / 9007199254740992.0); }
+inline double exp1_sample(Xoshiro256pp& rng) {
+    for (;;) {
+        const uint64_t bits = rng.next_u64();
+        const unsigned i = (unsigned)(bits & 0xff);
+        const double u = detmath_from_bits((bits >> 12) | 0x3FF0000000000000ULL) - (1.0 - 2.220446049250313e-16 / 2.0);
+        const double x = u * ZIG_X[i];
+        if (x < ZIG_X[i + 1]) return x;
+        if (i == 0) return ZIG_EXP_R - det_log(std_uniform_f64(rng));
+        if (ZIG_F[i + 1] + (ZIG_F[i] - ZIG_F[i + 1]) * std_uniform_f64(rng) < det_exp(-x)) return x;
+    }
+}
+
+// probminhash::setsketcher::SetSketcher (Ertl 2021, SetSketch1) with its FYshuffle
+// (incremental Fisher-Yates driven by Uniform<f64>).  The permutation is reset lazily (stamps) --
+// same values as the crate's O(m) reset.
+struct SetSketchOrc {
+    double b, a, lnb;
+    uint64_t m, q;
+    std::vector<uint64_t> kvec;
+    double lower_k = 0.0;
+    uint64_t nbmin = 0;
+    std::vector<uint32_t> v, stamp;
+    uint32_t cur_stamp = 0;
+    SetSketchOrc(double b_, uint64_t m_, double a_, uint64_t q_)
+        : b(b_), a(a_), lnb(det_log(b_)), m(m_), q(q_), kvec(m_, 0), v(m_, 0), stamp(m_, 0) {}
+    inline uint32_t& perm(uint64_t i) {
+        if (stamp[i] != cur_stamp) {
+            stamp[i] = cur_stamp;
+            v[i] = (uint32_t)i;
+        }
+        return v[i];
+    }
+    void sketch(uint64_t seed) {
+        Xoshiro256pp rng(seed);
+        ++cur_stamp;  // permut_generator.reset()
+        uint64_t lastidx = 0;
+        const int32_t iq1 = (int32_t)q + 1;
+        const double inva = 1.0 / a;
+        double x_pred = 0.0;
+        for (uint64_t j = 0; j < m; ++j) {
+            const double x_j = x_pred + (inva / (double)(m - j)) * exp1_sample(rng);
+            x_pred = x_j;
+            const double lb = det_log(x_j) / lnb;
+            if (lb > -lower_k) break;
+            const double fl = std::floor(1.0 - lb);
+            const int32_t z = fl >= 2147483647.0 ? 2147483647 : (fl <= -2147483648.0 ? (int32_t)(-2147483647 - 1) : (int32_t)fl);
+            const int32_t k = std::max(0, std::min(iq1, z));
+            if ((double)k <= lower_k) break;
+            // FYshuffle::next
+            const double xsi = rng.unif01();
+            const uint64_t idx = lastidx + (uint64_t)(xsi * (double)(m - lastidx));
+            const uint32_t val = perm(idx);
+            perm(idx) = perm(lastidx);
+            perm(lastidx) = val;
+            ++lastidx;
+            if ((double)k > (double)kvec[val]) {
+                kvec[val] = (uint64_t)k;
+                ++nbmin;
+                if (nbmin % m == 0) {
+                    const double flow = (double)*std::min_element(kvec.begin(), kvec.end());
+                    if (flow > lower_k) lower_k = flow;
+                }
+            }
+        }
+    }
+};
+
 }  // namespace
 
 // ================================================================= C API =========
@@ -937,6 +1013,53 @@ uint64_t orc_aa_filter(const uint8_t* ascii, uint64_t n, uint8_t* out) {
     for (uint64_t i = 0; i < n; ++i)
         if (encode_aa(ascii[i]) >= 0) out[kept++] = ascii[i];
     return kept;
+}
+
+// SetSketch of one group of sequences (nseq = 1: HyperLogLogSketch::sketch_compressedkmer per sequence,
+// setsketchert.rs:758-802; nseq > 1: sketch_compressedkmer_seqs(_block), :677-724, 811-895 -- the block split
+// + merge of the reference is an element-wise max and gives the same registers).  Keys are hashed by
+// NoHashHasher (:702-704).  sig_bytes 2 / 4 / 8 = u16 / u32 / u64 registers.
+void orc_sketch_setsketch(const uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases, uint64_t nseq, int k,
+                          int type, int hash_kind, double b, uint64_t m, double a, uint64_t q, int sig_bytes, void* out) {
+    SetSketchOrc ss(b, m, a, q);
+    const int key_bytes = is_u32_type(type) ? 4 : 8;
+    for (uint64_t s = 0; s < nseq; ++s)
+        for_each_kmer(packed + byte_off[s], nbases[s], 0, nbases[s], k, type, [&](uint64_t word) {
+            ss.sketch(nohash_seed(apply_hash(word, k, type, hash_kind), key_bytes));
+        });
+    for (uint64_t j = 0; j < m; ++j) {
+        if (sig_bytes == 2) ((uint16_t*)out)[j] = (uint16_t)ss.kvec[j];
+        else if (sig_bytes == 4) ((uint32_t*)out)[j] = (uint32_t)ss.kvec[j];
+        else ((uint64_t*)out)[j] = ss.kvec[j];
+    }
+}
+
+void orc_sketch_setsketch_batch(const uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases, uint64_t nseq,
+                                int k, int type, int hash_kind, double b, uint64_t m, double a, uint64_t q, int sig_bytes,
+                                void* out, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<uint64_t> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            uint64_t i = next.fetch_add(1);
+            if (i >= nseq) break;
+            orc_sketch_setsketch(packed, byte_off + i, nbases + i, 1, k, type, hash_kind, b, m, a, q, sig_bytes,
+                                 (uint8_t*)out + i * m * (uint64_t)sig_bytes);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+}
+
+double orc_det_log(double x) { return det_log(x); }
+double orc_det_exp(double x) { return det_exp(x); }
+double orc_exp1_from_seed(uint64_t seed, int skip) {
+    Xoshiro256pp rng(seed);
+    double v = 0;
+    for (int i = 0; i <= skip; ++i) v = exp1_sample(rng);
+    return v;
 }
 
 int orc_hardware_threads(void) {

@@ -124,6 +124,18 @@ void orc_sketch_superminhash_batch(const uint8_t* packed, const uint64_t* byte_o
                                    uint64_t nseq, int k, int type, int hash_kind, uint32_t m, int hasher,
                                    int sig_bytes, void* out, int nthreads);
 
+// ---- A13 : SetSketch / HyperLogLogSketch (probminhash::setsketcher, Ertl 2021; PARITY UNPINNED:
+//      rand_distr's ziggurat tables are regenerated, ln/exp are the deterministic det_math.hpp ones) ----
+void orc_sketch_setsketch(const uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases,
+                          uint64_t nseq, int k, int type, int hash_kind, double b, uint64_t m, double a,
+                          uint64_t q, int sig_bytes, void* out);
+void orc_sketch_setsketch_batch(const uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases,
+                                uint64_t nseq, int k, int type, int hash_kind, double b, uint64_t m,
+                                double a, uint64_t q, int sig_bytes, void* out, int nthreads);
+double orc_det_log(double x);
+double orc_det_exp(double x);
+double orc_exp1_from_seed(uint64_t seed, int skip);
+
 // ---- A15 : counting (exact multiset semantics of KmerCounter, kmercount.rs:241-288) -----
 // distinct canonical compressed k-mer values in ascending order with their multiplicities;
 // returns the number of distinct keys (only the first `cap` are written); UINT64_MAX on a bad (k, type)

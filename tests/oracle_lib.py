@@ -24,7 +24,8 @@ f64p = C.POINTER(C.c_double)
 
 
 def build_oracle(force=False):
-    src = [os.path.join(ORACLE_DIR, f) for f in ("kmer_oracle.cpp", "kmer_oracle.hpp", "Makefile")]
+    src = [os.path.join(ORACLE_DIR, f) for f in ("kmer_oracle.cpp", "kmer_oracle.hpp", "Makefile", "det_math.hpp",
+                                                 "zig_exp_tables.h")]
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
     if force or stale:
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
@@ -97,6 +98,16 @@ class Oracle:
                                               C.c_int, C.c_void_p]
         L.orc_sketch_superminhash_batch.argtypes = [u8p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                                     C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_sketch_setsketch.argtypes = [u8p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64,
+                                           C.c_double, C.c_uint64, C.c_int, C.c_void_p]
+        L.orc_sketch_setsketch_batch.argtypes = [u8p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_double,
+                                                 C.c_uint64, C.c_double, C.c_uint64, C.c_int, C.c_void_p, C.c_int]
+        L.orc_det_log.restype = C.c_double
+        L.orc_det_log.argtypes = [C.c_double]
+        L.orc_det_exp.restype = C.c_double
+        L.orc_det_exp.argtypes = [C.c_double]
+        L.orc_exp1_from_seed.restype = C.c_double
+        L.orc_exp1_from_seed.argtypes = [C.c_uint64, C.c_int]
         L.orc_count_kmers.restype = C.c_uint64
         L.orc_count_kmers.argtypes = [u8p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, u64p, u64p, C.c_uint64]
         L.orc_dispatch.restype = C.c_uint64
@@ -234,6 +245,31 @@ class Oracle:
         out = np.zeros(m, dtype=dtype)
         self.L.orc_sketch_superminhash(_ptr(packed, u8p), _ptr(byte_off, u64p), _ptr(nbases, u64p), len(nbases), k, ktype,
                                        kind, m, hasher, out.dtype.itemsize, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def sketch_setsketch_batch(self, packed, byte_off, nbases, k, ktype, kind, params=(1.001, 4096, 20.0, 65534),
+                               dtype=np.uint16, nthreads=0):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        byte_off = np.ascontiguousarray(byte_off, dtype=np.uint64)
+        nbases = np.ascontiguousarray(nbases, dtype=np.uint64)
+        b, m, a, q = params
+        out = np.zeros((len(nbases), m), dtype=dtype)
+        if nthreads <= 0:
+            nthreads = self.hardware_threads()
+        self.L.orc_sketch_setsketch_batch(_ptr(packed, u8p), _ptr(byte_off, u64p), _ptr(nbases, u64p), len(nbases), k,
+                                          ktype, kind, b, m, a, q, out.dtype.itemsize, out.ctypes.data_as(C.c_void_p),
+                                          nthreads)
+        return out
+
+    def sketch_setsketch_seqs(self, packed, byte_off, nbases, k, ktype, kind, params=(1.001, 4096, 20.0, 65534),
+                              dtype=np.uint16):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        byte_off = np.ascontiguousarray(byte_off, dtype=np.uint64)
+        nbases = np.ascontiguousarray(nbases, dtype=np.uint64)
+        b, m, a, q = params
+        out = np.zeros(m, dtype=dtype)
+        self.L.orc_sketch_setsketch(_ptr(packed, u8p), _ptr(byte_off, u64p), _ptr(nbases, u64p), len(nbases), k, ktype,
+                                    kind, b, m, a, q, out.dtype.itemsize, out.ctypes.data_as(C.c_void_p))
         return out
 
     # ---- counting ----------------------------------------------------------------

@@ -337,3 +337,55 @@ def test_aa_superminhash_reference_inequality(oracle, dtype):
         sigs.append(oracle.sketch_superminhash_batch(a, np.zeros(1, np.uint64), np.array([len(a)], np.uint64), 5,
                                                      ol.KMERAA64, ol.HASH_MASKED_VALUE, 800, 0, dtype)[0])
     assert abs(float(np.mean(sigs[0] == sigs[1])) - 0.5) < 0.1
+
+
+# ---- SetSketch building blocks and properties (the reference has no test for HLL) ---------
+def test_det_log_exp_accuracy(oracle):
+    import math
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([np.exp(rng.uniform(-700, 700, 2000)), rng.uniform(0.5, 2.0, 2000), 1 + rng.uniform(-1e-6, 1e-6, 500)])
+    for x in xs:
+        assert abs(oracle.L.orc_det_log(float(x)) - math.log(x)) <= 2.3e-16 * max(abs(math.log(x)), 1e-300) + 1e-320
+    for y in rng.uniform(-30, 30, 2000):
+        assert abs(oracle.L.orc_det_exp(float(y)) - math.exp(y)) <= 2.3e-16 * math.exp(y)
+    assert oracle.L.orc_det_log(1.0) == 0.0 and oracle.L.orc_det_exp(0.0) == 1.0
+
+
+def test_ziggurat_exp1_moments(oracle):
+    v = np.array([oracle.L.orc_exp1_from_seed(s, 0) for s in range(40000)])
+    assert (v > 0).all()
+    assert abs(v.mean() - 1.0) < 0.02 and abs(v.var() - 1.0) < 0.06  # Exp(1)
+    assert abs((v > 1.0).mean() - np.exp(-1.0)) < 0.01
+
+
+def _hll(oracle, seqs, k=12, params=(1.001, 512, 20.0, 65534)):
+    packed = [oracle.pack_2bit(s) for s in seqs]
+    off, cur = [], 0
+    for p in packed:
+        off.append(cur)
+        cur += (len(p) + 15) // 16 * 16
+    buf = np.zeros(cur + 16, np.uint8)
+    for o, p in zip(off, packed):
+        buf[o:o + len(p)] = p
+    nb = np.array([len(s) for s in seqs], np.uint64)
+    off = np.array(off, np.uint64)
+    each = oracle.sketch_setsketch_batch(buf, off, nb, k, ol.KMER32, ol.HASH_CANON_INVHASH, params)
+    both = oracle.sketch_setsketch_seqs(buf, off, nb, k, ol.KMER32, ol.HASH_CANON_INVHASH, params)
+    return each, both
+
+
+def test_setsketch_properties(oracle):
+    a = oracle.synth_ascii(90, 0, 30000)
+    b = oracle.synth_ascii(90, 20000, 30000)  # overlaps the last third of a
+    each, both = _hll(oracle, [a, b])
+    assert np.array_equal(both, each.max(axis=0))  # mergeable by max (SetSketcher::merge)
+    each_rev, both_rev = _hll(oracle, [b, a])
+    assert np.array_equal(both, both_rev)  # order independent
+    dup_each, dup_both = _hll(oracle, [a, a])
+    assert np.array_equal(dup_both, each[0])  # idempotent
+    assert (each > 0).all() and each.max() <= 65535
+    # more distinct k-mers -> larger registers on average; Jaccard by equal registers is about |A n B| / |A u B|
+    small, _ = _hll(oracle, [a[:3000]])
+    assert small.mean() < each[0].mean()
+    j = float(np.mean(each[0] == each[1]))
+    assert 0.1 < j < 0.4  # true Jaccard = 10000 / 50000 = 0.2
