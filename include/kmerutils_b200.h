@@ -103,6 +103,12 @@ int32_t kmu_seqbatch_from_aa(kmu_ctx* ctx, const uint8_t* ascii, const uint64_t*
 int32_t kmu_seqbatch_synth_aa(kmu_ctx* ctx, uint64_t seed, const uint64_t* nres, uint64_t nseq, kmu_seqbatch** batch);
 /* 0 = DNA (2 bits / base), 1 = amino acids (one 5-bit code per byte) */
 int32_t kmu_seqbatch_alphabet(const kmu_seqbatch* batch);
+/* synthetic short reads (bench / tests): reads first_read .. first_read + nreads of length
+ * read_len drawn uniformly from the one sequence of `genome`, random strand, substitution errors at
+ * err_ppm per million bases.  The read index seeds every draw, so shards of one read set can be
+ * generated independently on several GPUs. */
+int32_t kmu_seqbatch_sample_reads(kmu_ctx* ctx, const kmu_seqbatch* genome, uint64_t seed, uint64_t first_read,
+                                  uint64_t nreads, uint32_t read_len, uint32_t err_ppm, kmu_seqbatch** batch);
 void kmu_seqbatch_destroy(kmu_seqbatch* batch);
 uint64_t kmu_seqbatch_nseq(const kmu_seqbatch* batch);
 uint64_t kmu_seqbatch_total_bases(const kmu_seqbatch* batch);

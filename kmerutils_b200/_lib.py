@@ -64,6 +64,8 @@ SIGNATURES = {
     "kmu_seqbatch_from_aa": (C.c_int32, [C.c_void_p, C.c_void_p, u64p, C.c_uint64, C.c_int32, u64p, vpp]),
     "kmu_seqbatch_synth_aa": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, C.c_uint64, vpp]),
     "kmu_seqbatch_alphabet": (C.c_int32, [C.c_void_p]),
+    "kmu_seqbatch_sample_reads": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
+                                              C.c_uint32, vpp]),
     "kmu_seqbatch_destroy": (None, [C.c_void_p]),
     "kmu_seqbatch_nseq": (C.c_uint64, [C.c_void_p]),
     "kmu_seqbatch_total_bases": (C.c_uint64, [C.c_void_p]),

@@ -219,6 +219,54 @@ cudaError_t launch_synth_aa(uint8_t* codes, const uint64_t* byte_off, const uint
     return cudaGetLastError();
 }
 
+// ---- reads sampled from a genome ----------------------------------------
+// read r: start = z(2r) % (G - len + 1), strand = z(2r + 1) & 1 (1: reverse complement),
+// base j substituted when e = z'(r * len + j) has e % 1e6 < err_ppm, by (base + 1 + (e >> 32) % 3) & 3;
+// z = SplitMix64 stream `seed`, z' = stream `seed ^ 0x5bd1e995a5a5a5a5`.
+__device__ __forceinline__ uint32_t genome_base(const uint8_t* __restrict__ g, uint64_t pos) {
+    return (g[pos >> 2] >> (6 - 2 * (pos & 3))) & 3u;
+}
+
+__global__ void sample_reads_kernel(const uint8_t* __restrict__ genome, uint64_t glen, uint64_t seed, uint64_t first_read,
+                                    uint64_t nreads, uint32_t read_len, uint32_t err_ppm, uint32_t words_per_read,
+                                    uint8_t* out) {
+    const uint64_t total_words = nreads * words_per_read;
+    const uint64_t eseed = seed ^ 0x5bd1e995a5a5a5a5ULL;
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < total_words;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = w / words_per_read;
+        const uint32_t wi = (uint32_t)(w - r * words_per_read);
+        const uint64_t gr = first_read + r;
+        const uint64_t start = synth_z(seed, 2 * gr) % (glen - read_len + 1);
+        const bool rev = synth_z(seed, 2 * gr + 1) & 1;
+        uint32_t word = 0;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t j = wi * 16 + i;
+            uint32_t code = 0;
+            if (j < read_len) {
+                code = rev ? 3u - genome_base(genome, start + read_len - 1 - j) : genome_base(genome, start + j);
+                const uint64_t e = synth_z(eseed, gr * read_len + j);
+                if ((uint32_t)(e % 1000000ULL) < err_ppm) code = (code + 1u + (uint32_t)((e >> 32) % 3u)) & 3u;
+            }
+            word |= code << (30 - 2 * i);
+        }
+        ((uint32_t*)out)[w] = __byte_perm(word, 0, 0x0123);
+    }
+}
+
+cudaError_t launch_sample_reads(const uint8_t* genome, uint64_t glen, uint64_t seed, uint64_t first_read, uint64_t nreads,
+                                uint32_t read_len, uint32_t err_ppm, uint32_t words_per_read, uint8_t* out,
+                                cudaStream_t stream) {
+    if (nreads == 0) return cudaSuccess;
+    const uint64_t total_words = nreads * words_per_read;
+    uint64_t want = (total_words + 255) / 256;
+    int grid = (int)(want < 148ull * 16 ? want : 148ull * 16);
+    sample_reads_kernel<<<grid, 256, 0, stream>>>(genome, glen, seed, first_read, nreads, read_len, err_ppm,
+                                                  words_per_read, out);
+    return cudaGetLastError();
+}
+
 // ---- length classes ---------------------------------------------------------------------------
 __device__ __forceinline__ int len_bucket(uint64_t nk) {
     if (nk == 0) return LEN_BUCKETS - 1;

@@ -504,6 +504,33 @@ int32_t kmu_seqbatch_synth_aa(kmu_ctx* ctx, uint64_t seed, const uint64_t* nres,
     return KMU_OK;
 }
 
+int32_t kmu_seqbatch_sample_reads(kmu_ctx* ctx, const kmu_seqbatch* genome, uint64_t seed, uint64_t first_read,
+                                  uint64_t nreads, uint32_t read_len, uint32_t err_ppm, kmu_seqbatch** out) {
+    if (!ctx || !genome || !out) return fail(KMU_EINVAL, "null argument");
+    if (genome->alphabet != 0 || genome->nseq != 1) return fail(KMU_EINVAL, "the genome must be a batch of one DNA sequence");
+    const uint64_t glen = genome->h_nbases[0];
+    if (read_len < 1 || read_len > glen) return fail(KMU_EINVAL, "read length %u does not fit the genome", read_len);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    std::vector<uint64_t> nb(nreads, read_len);
+    kmu_seqbatch* b = nullptr;
+    int32_t rc = batch_alloc(ctx, nb.data(), nreads, &b);
+    if (rc) return rc;
+    rc = batch_upload_meta(ctx, b);
+    const uint32_t words_per_read = (uint32_t)(align_up((read_len + 3) / 4, SEQ_ALIGN) / 4);
+    cudaError_t e = kmu::launch_sample_reads(genome->packed, glen, seed, first_read, nreads, read_len, err_ppm,
+                                             words_per_read, b->packed, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->packed + b->packed_bytes, 0, TAIL_SLACK, ctx->stream);
+    ctx->launches += 1;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess || rc) {
+        kmu_seqbatch_destroy(b);
+        return rc ? rc : fail(KMU_ECUDA, "read sampling failed: %s", cudaGetErrorString(e));
+    }
+    *out = b;
+    return KMU_OK;
+}
+
 int32_t kmu_seqbatch_alphabet(const kmu_seqbatch* b) { return b ? b->alphabet : -1; }
 
 int32_t kmu_seqbatch_download(kmu_ctx* ctx, const kmu_seqbatch* b, uint8_t* packed_out, uint64_t* byte_off_out,

@@ -87,6 +87,10 @@ cudaError_t launch_aa_encode(const uint8_t* ascii, const uint64_t* ascii_off, co
                              uint8_t* codes, cudaStream_t stream);
 cudaError_t launch_synth_aa(uint8_t* codes, const uint64_t* byte_off, const uint64_t* nres, const uint64_t* first_res,
                             uint64_t nseq, uint64_t total_bytes, uint64_t seed, cudaStream_t stream);
+// reads sampled from a packed genome with substitution errors; every read takes words_per_read u32
+cudaError_t launch_sample_reads(const uint8_t* genome, uint64_t glen, uint64_t seed, uint64_t first_read, uint64_t nreads,
+                                uint32_t read_len, uint32_t err_ppm, uint32_t words_per_read, uint8_t* out,
+                                cudaStream_t stream);
 // length classes: bucket = 8 per octave of the k-mer count, bucket 0 = longest
 constexpr int LEN_BUCKETS = 512;
 cudaError_t launch_len_hist(const uint64_t* nbases, uint64_t nseq, uint32_t k, unsigned long long* hist,

@@ -1,0 +1,136 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink on the GPU box, gloo in
+the CPU tests).  Only the steps of the path that really exchange data use a collective:
+
+* per-read / per-genome sketches shard by sequence -- NO collective (`shard_by_bases`, `round_robin`);
+* counting: the reference hands every k-mer to the thread `intNN_hash(kmer) % N`
+  (DispatchableT::dispatch, src/base/kmercount.rs:382-420); here rank = thread, the hand-off is an
+  all-to-all of the buckets `kmu_count_partition` builds (`exchange_kmers`, `count_sharded`);
+* whole-file SetSketch / SuperMinHash registers are mergeable (SetSketcher::merge,
+  src/sketching/setsketchert.rs:876-882): allreduce max / min (`merge_registers`).
+
+The helpers take torch tensors on whatever device the process group's backend needs, so the same code
+runs under gloo on CPU tensors (tests/test_dist_cpu.py) and under NCCL on device tensors.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_by_bases(nbases, world):
+    """Contiguous ranges of sequences with about equal numbers of bases: [(start, end)] * world."""
+    nb = np.asarray(nbases, dtype=np.uint64)
+    cum = np.concatenate([[0], np.cumsum(nb, dtype=np.uint64)]).astype(np.float64)
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        cuts.append(int(np.searchsorted(cum, target, side="left")))
+    cuts.append(len(nb))
+    cuts = np.maximum.accumulate(np.minimum(cuts, len(nb)))
+    return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
+
+
+def round_robin(n, world, rank):
+    """Indices of the units (genomes) rank `rank` owns."""
+    return np.arange(rank, n, world, dtype=np.int64)
+
+
+def _world(group=None):
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def exchange_kmers(keys, part_counts, group=None):
+    """All-to-all of k-mer buckets.  keys: 1-D tensor, bucket p (destined to rank p) at offset
+    sum(part_counts[:p]); part_counts: sequence of world ints.  Returns (received keys, recv_counts):
+    the k-mers this rank owns, grouped by sending rank."""
+    rank, world = _world(group)
+    counts = [int(c) for c in part_counts]
+    assert len(counts) == world and sum(counts) == keys.numel()
+    if world == 1:
+        return keys, counts
+    send_counts = torch.tensor(counts, dtype=torch.int64, device=keys.device)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    recv = [int(c) for c in recv_counts.cpu()]
+    out = torch.empty(sum(recv), dtype=keys.dtype, device=keys.device)
+    dist.all_to_all_single(out, keys, output_split_sizes=recv, input_split_sizes=counts, group=group)
+    return out, recv
+
+
+def allreduce_sum(values, device, group=None):
+    t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=device)
+    if _world(group)[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return [int(v) for v in t.cpu()]
+
+
+_WIDEN = {torch.uint16: torch.int32, torch.uint32: torch.int64, torch.uint64: torch.int64}
+
+
+def merge_registers(regs, op, group=None):
+    """Element-wise max (SetSketch) or min (SuperMinHash) of the per-rank registers, in place semantics:
+    returns a tensor of the input dtype.  NCCL has no unsigned 16/32-bit types: those are widened."""
+    assert op in ("max", "min")
+    if _world(group)[1] == 1:
+        return regs
+    wide = _WIDEN.get(regs.dtype)
+    t = regs.to(wide) if wide is not None else regs.clone()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.MIN, group=group)
+    return t.to(regs.dtype) if wide is not None else t
+
+
+def gather_rows(local_rows, group=None):
+    """Concatenate per-rank row blocks (signatures of contiguous shards) in rank order on every rank."""
+    rank, world = _world(group)
+    if world == 1:
+        return local_rows
+    n = torch.tensor([local_rows.shape[0]], dtype=torch.int64, device=local_rows.device)
+    sizes = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    width = local_rows.shape[1]
+    pad = torch.zeros((max(sizes), width), dtype=local_rows.dtype, device=local_rows.device)
+    pad[: local_rows.shape[0]] = local_rows
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+
+
+def count_sharded(engine, batch, k, kmer_type, capacity_per_rank, count_bits=8, canonical=True, group=None):
+    """count_kmer_threaded_one_to_many across ranks (kmercount.rs:881-974): every rank extracts the
+    canonical k-mers of ITS sequences, buckets them by owner on the GPU, the buckets cross NVLink in
+    one all-to-all and each rank inserts what it owns.  Returns (counter, stats) where stats are the
+    job-wide nb_distinct / nb_unique / nb_inserted (allreduce of the per-rank table statistics)."""
+    import kmerutils_b200 as kb
+
+    rank, world = _world(group)
+    dev = torch.device("cuda", engine.device)
+    tdtype = torch.int64 if kb.val_dtype(kmer_type) == np.uint64 else torch.int32
+    n = batch.kmer_count(k)
+    send = torch.empty(max(n, 1), dtype=tdtype, device=dev)
+    _, counts = engine.count_partition(batch, k, kmer_type, world, canonical, out_device_ptr=send.data_ptr())
+    engine.sync()
+    torch.cuda.current_stream(dev).synchronize()
+    recv, _ = exchange_kmers(send[:n], counts, group)
+    torch.cuda.current_stream(dev).synchronize()
+    counter = engine.counter(k, kmer_type, capacity_per_rank, count_bits)
+    if recv.numel():
+        counter.insert_kmers(device_ptr=recv.data_ptr(), n=recv.numel())
+    st = counter.stats()
+    tot = allreduce_sum([st["nb_distinct"], st["nb_unique"], st["nb_inserted"]], dev, group)
+    return counter, {"nb_distinct": tot[0], "nb_unique": tot[1], "nb_inserted": tot[2], "local": st}
+
+
+def query_sharded(engine, counter, kmers, kmer_type, group=None):
+    """get_count for k-mers held by any rank: every rank asks its own table for the k-mers it owns
+    (dispatch) and the answers are summed (a k-mer lives on exactly one rank)."""
+    rank, world = _world(group)
+    kmers = np.ascontiguousarray(kmers)
+    local = counter.get_count(kmers).astype(np.int64)
+    if world == 1:
+        return local.astype(np.uint32)
+    t = torch.from_numpy(local).to(torch.device("cuda", engine.device))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy().astype(np.uint32)

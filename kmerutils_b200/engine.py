@@ -187,6 +187,13 @@ class Engine:
         check(self.lib.kmu_seqbatch_synth(self.ctx, seed, _p(nb, u64p), len(nb), C.byref(h)))
         return SeqBatch(self, h)
 
+    def batch_sample_reads(self, genome, seed, first_read, nreads, read_len=150, err_ppm=5000):
+        """Short reads drawn from a one-sequence genome batch: random start and strand, substitutions."""
+        h = C.c_void_p()
+        check(self.lib.kmu_seqbatch_sample_reads(self.ctx, genome.handle, seed, first_read, nreads, read_len, err_ppm,
+                                                 C.byref(h)))
+        return SeqBatch(self, h)
+
     # ---- k-mers ---------------------------------------------------------------------------
     def generate_kmers(self, batch, k, kmer_type, hash_kind=_lib.HASH_IDENTITY_RAW):
         """-> (values, out_off): all k-mers of all sequences mapped through the hash closure."""

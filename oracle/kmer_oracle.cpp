@@ -1062,6 +1062,20 @@ double orc_exp1_from_seed(uint64_t seed, int skip) {
     return v;
 }
 
+// read `r` of the synthetic short-read set, as ASCII: see kmu_seqbatch_sample_reads
+void orc_sample_read(const uint8_t* genome_packed, uint64_t glen, uint64_t seed, uint64_t r, uint32_t read_len,
+                     uint32_t err_ppm, uint8_t* ascii_out) {
+    const uint64_t eseed = seed ^ 0x5bd1e995a5a5a5a5ULL;
+    const uint64_t start = synth_z(seed, 2 * r) % (glen - read_len + 1);
+    const bool rev = synth_z(seed, 2 * r + 1) & 1;
+    for (uint32_t j = 0; j < read_len; ++j) {
+        unsigned code = rev ? 3u - base_at(genome_packed, start + read_len - 1 - j) : base_at(genome_packed, start + j);
+        const uint64_t e = synth_z(eseed, r * read_len + j);
+        if ((uint32_t)(e % 1000000ULL) < err_ppm) code = (code + 1u + (unsigned)((e >> 32) % 3u)) & 3u;
+        ascii_out[j] = (uint8_t)DECODE2B[code];
+    }
+}
+
 int orc_hardware_threads(void) {
     unsigned n = std::thread::hardware_concurrency();
     return n ? (int)n : 1;

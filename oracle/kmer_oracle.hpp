@@ -155,6 +155,8 @@ void orc_synth_ascii(uint64_t seed, uint64_t first_base, uint64_t nbases, uint8_
 void orc_synth_aa(uint64_t seed, uint64_t first_res, uint64_t nres, uint8_t* ascii_out);
 uint64_t orc_aa_filter(const uint8_t* ascii, uint64_t n, uint8_t* out);
 
+void orc_sample_read(const uint8_t* genome_packed, uint64_t glen, uint64_t seed, uint64_t r, uint32_t read_len,
+                     uint32_t err_ppm, uint8_t* ascii_out);
 int orc_hardware_threads(void);
 
 #ifdef __cplusplus

@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Multi-GPU check, run under torchrun on N GPUs of one box:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 scripts/dist_check.py
+Counting over NCCL all-to-all (owners = DispatchableT::dispatch) and SetSketch / SuperMinHash register merges, each
+compared on rank 0 with the CPU oracle run on the whole input."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import kmerutils_b200 as kb  # noqa: E402
+from kmerutils_b200 import dist as kd  # noqa: E402
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = kb.Engine(local)
+    glen, nreads, k = 200_000, 40_000, 31
+    genome = eng.batch_synth(3, np.array([glen], dtype=np.uint64))
+    per = nreads // world
+    first = rank * per
+    mine = eng.batch_sample_reads(genome, 3, first, per if rank < world - 1 else nreads - first, 150, 5000)
+    counter, st = kd.count_sharded(eng, mine, k, kb.KMER64, capacity_per_rank=int(nreads * 150 * 1.2 / world) + 1024)
+    hll_local = eng.sketch_setsketch(mine, 21, kb.KMER64, kb.HASH_CANON_INVHASH, (1.001, 256, 20.0, 65534), np.uint16, whole=True)
+    hll = kd.merge_registers(torch.from_numpy(hll_local.astype(np.int32)).cuda(), "max").cpu().numpy().astype(np.uint16)
+    smh_local = eng.sketch_superminhash(mine, 21, kb.KMER64, kb.HASH_CANON_INVHASH, 256).min(axis=0)
+    smh = kd.merge_registers(torch.from_numpy(smh_local).cuda(), "min").cpu().numpy()
+    ok = True
+    if rank == 0:
+        from oracle_lib import get_oracle
+        from test_pmh3a_gpu import oracle_batch
+        orc = get_oracle()
+        gp, _ = oracle_batch(orc, 3, np.array([glen], dtype=np.uint64))
+        reads = orc.sample_reads(gp, glen, 3, 0, nreads, 150, 5000)
+        packed = [orc.pack_2bit(r) for r in reads]
+        buf = np.zeros(48 * nreads + 16, np.uint8)
+        for i, p in enumerate(packed):
+            buf[48 * i: 48 * i + len(p)] = p
+        off = np.arange(nreads, dtype=np.uint64) * 48
+        nb = np.full(nreads, 150, dtype=np.uint64)
+        keys, cnts = orc.count_kmers(buf, off, nb, k, kb.KMER64, True)
+        want = (len(keys), int((cnts == 1).sum()), int(cnts.sum()))
+        got = (st["nb_distinct"], st["nb_unique"], st["nb_inserted"])
+        ok &= got == want
+        print(f"[dist_check] world={world} counting stats {got} want {want}", flush=True)
+        want_hll = orc.sketch_setsketch_seqs(buf, off, nb, 21, kb.KMER64, kb.HASH_CANON_INVHASH, (1.001, 256, 20.0, 65534))
+        ok &= bool(np.array_equal(hll, want_hll))
+        want_smh = orc.sketch_superminhash_seqs(buf, off, nb, 21, kb.KMER64, kb.HASH_CANON_INVHASH, 256)
+        ok &= bool(np.array_equal(smh, want_smh))
+        print(f"[dist_check] setsketch merge ok={np.array_equal(hll, want_hll)} superminhash merge ok={np.array_equal(smh, want_smh)}", flush=True)
+        probe = keys[:: max(1, len(keys) // 5000)]
+        probe_want = np.minimum(cnts[:: max(1, len(keys) // 5000)], 255).astype(np.uint32)
+    else:
+        probe = None
+    # every rank must take part in the query collective with the same probe set
+    obj = [probe]
+    dist.broadcast_object_list(obj, src=0)
+    res = kd.query_sharded(eng, counter, obj[0], kb.KMER64)
+    if rank == 0:
+        ok &= bool(np.array_equal(res, probe_want))
+        print(f"[dist_check] sharded get_count ok={np.array_equal(res, probe_want)}", flush=True)
+        print("[dist_check] PASS" if ok else "[dist_check] FAIL", flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    counter.destroy()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()

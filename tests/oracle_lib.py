@@ -117,6 +117,7 @@ class Oracle:
         L.orc_synth_aa.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, u8p]
         L.orc_aa_filter.restype = C.c_uint64
         L.orc_aa_filter.argtypes = [u8p, C.c_uint64, u8p]
+        L.orc_sample_read.argtypes = [u8p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, u8p]
         L.orc_hardware_threads.restype = C.c_int
 
     # ---- sequences -------------------------------------------------------------
@@ -311,6 +312,15 @@ class Oracle:
         out = np.zeros(len(a) + 1, dtype=np.uint8)
         n = self.L.orc_aa_filter(_ptr(a, u8p), len(a), _ptr(out, u8p))
         return out[:n].tobytes()
+
+    def sample_reads(self, genome_packed, glen, seed, first_read, nreads, read_len=150, err_ppm=5000):
+        g = np.ascontiguousarray(genome_packed, dtype=np.uint8)
+        out = []
+        buf = np.zeros(read_len, dtype=np.uint8)
+        for r in range(first_read, first_read + nreads):
+            self.L.orc_sample_read(_ptr(g, u8p), glen, seed, r, read_len, err_ppm, _ptr(buf, u8p))
+            out.append(buf.tobytes())
+        return out
 
     def hardware_threads(self):
         return int(self.L.orc_hardware_threads())

@@ -141,3 +141,22 @@ def test_partition_by_owner(engine, oracle, k, ktype, nparts):
         ctr.insert_kmers(part.astype(kb.val_dtype(ktype)))
     assert np.array_equal(ctr.get_count(keys), np.minimum(cnts, 255).astype(np.uint32))
     ctr.destroy()
+
+
+def test_sample_reads_and_sharded_count_single_rank(engine, oracle):
+    # the synthetic short reads of config C3 are the same on the device and in the oracle
+    glen = 50_000
+    genome = engine.batch_synth(3, np.array([glen], dtype=np.uint64))
+    gp, _ = oracle_batch(oracle, 3, np.array([glen], dtype=np.uint64))
+    reads = engine.batch_sample_reads(genome, 3, first_read=1000, nreads=400, read_len=150, err_ppm=5000)
+    packed, off, nb = reads.download()
+    want = oracle.sample_reads(gp, glen, 3, 1000, 400, 150, 5000)
+    for i in (0, 1, 2, 57, 399):
+        assert oracle.unpack_2bit(packed[int(off[i]): int(off[i]) + 38], 150) == want[i]
+    # count through the multi-GPU driver with one rank: partition -> (no exchange) -> insert
+    from kmerutils_b200 import dist as kd
+    keys, cnts = oracle.count_kmers(packed, off, nb, 31, kb.KMER64, True)
+    counter, st = kd.count_sharded(engine, reads, 31, kb.KMER64, capacity_per_rank=len(keys))
+    assert (st["nb_distinct"], st["nb_unique"], st["nb_inserted"]) == (len(keys), int((cnts == 1).sum()), int(cnts.sum()))
+    assert np.array_equal(kd.query_sharded(engine, counter, keys, kb.KMER64), np.minimum(cnts, 255).astype(np.uint32))
+    counter.destroy()
