@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <initializer_list>
 #include <mutex>
@@ -785,15 +786,18 @@ std::vector<OctaveClass> kmu_octave_classes(const kmu_seqbatch* b) {
 
 extern "C" {
 
+// phase 0: everything; phase 1: the main launches only (nothing waits on the device); phase 2: wait for
+// them and redo the sequences they flagged.  The host pipeline runs 1 and 2 apart so that it can
+// prepare the next chunk while the device works.
 static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type,
-                                   int32_t hash_kind, uint32_t m, void* d_sig) {
+                                   int32_t hash_kind, uint32_t m, void* d_sig, int phase = 0) {
     const bool key64 = kmer_type_is_u64(kmer_type);
     const bool aa = kmer_type_is_aa(kmer_type);
     const size_t vsz = key64 ? 8 : 4;
     const uint64_t nseq = b->nseq;
     cudaStream_t st = ctx->stream;
     uint64_t launches = 0;
-    ctx->lrec.clear();
+    if (phase != 2) ctx->lrec.clear();
 
     // ---- order sequences longest first (8 buckets per octave of the k-mer count) -------
     // histogram and cursors come from the host copy of the lengths; the processing order is
@@ -804,7 +808,8 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     unsigned long long* d_work = d_cursor + kmu::LEN_BUCKETS;  // 128 work counters
     unsigned long long* d_ovf_count = d_work + 128;
     unsigned long long* d_phase = d_work + 256;  // 8 per launch, profiling only
-    CUDA_TRY(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256 + 8 * 128), st));
+    if (phase != 2)
+        CUDA_TRY(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256 + 8 * 128), st));
     {
         int32_t orc = kmu_ensure_order(ctx, b, k, &launches);
         if (orc) return orc;
@@ -979,13 +984,14 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         return KMU_OK;
     };
 
-    if (classes.size() > 120) return fail(KMU_EINVAL, "too many launch classes");
+    if (classes.size() > 120) return fail(KMU_EINVAL, "too many launch classes");  // work counter 127 is the redo launch's
     int ci = 0;
-    for (const LaunchClass& c : classes) {
-        int32_t rc = run_class(c, d_order, ci++, true);
-        if (rc) return rc;
-    }
-    if (ctx->profiling) {
+    if (phase != 2)
+        for (const LaunchClass& c : classes) {
+            int32_t rc = run_class(c, d_order, ci++, true);
+            if (rc) return rc;
+        }
+    if (ctx->profiling && phase != 2) {
         // bases per launch: class i covers the sequences whose length bucket start lies in its range
         for (uint64_t L : b->h_nbases) {
             uint64_t nk = L >= k ? L - k + 1 : 0;
@@ -999,7 +1005,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     }
     // ---- sequences whose u8 histogram counters wrapped or whose speculative qmax bound failed:
     //      redo them with u32 table counters and without speculation ---------------------------
-    {
+    if (phase != 1) {
         unsigned long long novf = 0;
         CUDA_TRY(cudaMemcpyAsync(&novf, d_ovf_count, sizeof(novf), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -1010,7 +1016,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
             c.nk_max = nk_longest;
             c.mode = 1;
             c.table_global = true;
-            int32_t rc = run_class(c, (const uint32_t*)ctx->overflow.p, ci++, false);
+            int32_t rc = run_class(c, (const uint32_t*)ctx->overflow.p, 127, false);
             if (rc) return rc;
         }
     }
@@ -1107,10 +1113,20 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
     const uint64_t total_bytes = layout_offsets(nbases, nseq, lay);
     bool same_layout = packed_bytes >= total_bytes;
     for (uint64_t i = 0; i < nseq && same_layout; ++i) same_layout = byte_off[i] == lay[i];
-    const uint64_t target = 96ull << 20;
+    // chunk sizes: a small first chunk (the pipeline starts computing early), large middle chunks
+    // (few launch tails), a small last chunk (short drain of the final download)
+    uint64_t big = std::max<uint64_t>(64ull << 20, total_bytes / 4);
+    uint64_t small = std::max<uint64_t>(8ull << 20, total_bytes / 48);
+    if (const char* env = std::getenv("KMU_HOST_CHUNK_BYTES")) {  // tests: force many small chunks
+        const uint64_t v = std::strtoull(env, nullptr, 10);
+        if (v) big = small = v;
+    }
     std::vector<uint64_t> cut{0};
     for (uint64_t i = 0, start = 0; i < nseq; ++i) {
         const uint64_t end = i + 1 < nseq ? lay[i + 1] : total_bytes;
+        const uint64_t left = total_bytes - lay[start];
+        uint64_t target = cut.size() == 1 ? small : big;
+        if (cut.size() > 1 && left > small && left - small < target) target = left - small;  // leave a small tail chunk
         if (end - lay[start] >= target || i + 1 == nseq) {
             cut.push_back(i + 1);
             start = i + 1;
@@ -1182,12 +1198,15 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
     int32_t rc = upload(0);
     for (size_t c = 0; c < nchunks && rc == KMU_OK; ++c) {
         const int sl = (int)(c & 1);
-        if (c + 1 < nchunks) rc = upload(c + 1);
-        if (rc) break;
         CUDA_TRY(cudaStreamWaitEvent(ctx->stream, hp.in_done[sl], 0));
         if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, hp.out_done[sl], 0));  // signature slot free again
         cudaEventRecord(ctx->ev[0], ctx->stream);
-        rc = sketch_pmh3a_locked(ctx, &views[c], k, kmer_type, hash_kind, m, hp.sig[sl].p);
+        rc = sketch_pmh3a_locked(ctx, &views[c], k, kmer_type, hash_kind, m, hp.sig[sl].p, 1);
+        if (rc) break;
+        // the device is busy with chunk c: lay out and upload chunk c + 1 meanwhile
+        if (c + 1 < nchunks) rc = upload(c + 1);
+        if (rc) break;
+        rc = sketch_pmh3a_locked(ctx, &views[c], k, kmer_type, hash_kind, m, hp.sig[sl].p, 2);
         cudaEventRecord(ctx->ev[1], ctx->stream);
         CUDA_TRY(cudaEventRecord(hp.compute_done[sl], ctx->stream));
         if (rc) break;

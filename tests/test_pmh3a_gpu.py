@@ -106,3 +106,28 @@ def test_reference_statistical_tests(engine, oracle):
     # identity hash: reverse complement shares (almost) nothing (<= 0.1)
     sig_id = engine.sketch_pmh3a(batch, 5, kb.KMER32, kb.HASH_IDENTITY_RAW, 4000)
     assert oracle.jaccard(sig_id[0], sig_id[2]) <= 0.1
+
+
+@pytest.mark.parametrize("chunk_bytes", [None, 4096, 100000])
+@pytest.mark.parametrize("ragged", [False, True])
+def test_host_pipeline(engine, oracle, chunk_bytes, ragged, monkeypatch):
+    # kmu_sketch_pmh3a_host: host buffers in, host signatures out, chunked over three streams.  Same
+    # signatures whatever the chunking, for a buffer in the batch layout and for a tightly packed one.
+    rng = np.random.default_rng(17)
+    nb = np.concatenate([[1, 7, 8, 30000], rng.integers(8, 6000, 300)]).astype(np.uint64)
+    packed, off = oracle_batch(oracle, 33, nb)
+    want = oracle.sketch_pmh3a_batch(packed, off, nb, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200)
+    if ragged:  # sequences back to back without the 16-byte alignment: re-laid out through the pinned staging buffer
+        sizes = (nb + np.uint64(3)) // np.uint64(4)
+        roff = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+        tight = np.zeros(int(sizes.sum()) + 16, dtype=np.uint8)
+        for o, r, s_ in zip(off, roff, sizes):
+            tight[int(r): int(r + s_)] = packed[int(o): int(o + s_)]
+        packed, off = tight, roff
+    if chunk_bytes:
+        monkeypatch.setenv("KMU_HOST_CHUNK_BYTES", str(chunk_bytes))
+    out = np.zeros((len(nb), 200), dtype=np.uint32)
+    engine.sketch_pmh3a_host(packed, off, nb, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200, out)
+    assert np.array_equal(out, want)
+    t = engine.last_times()
+    assert t["d2h_bytes"] == out.nbytes and t["h2d_bytes"] > 0 and t["host_ms"] > 0
