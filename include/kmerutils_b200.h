@@ -109,6 +109,12 @@ int32_t kmu_seqbatch_alphabet(const kmu_seqbatch* batch);
  * generated independently on several GPUs. */
 int32_t kmu_seqbatch_sample_reads(kmu_ctx* ctx, const kmu_seqbatch* genome, uint64_t seed, uint64_t first_read,
                                   uint64_t nreads, uint32_t read_len, uint32_t err_ppm, kmu_seqbatch** batch);
+/* sub-ranges [begin[i], end[i]) (in bases / residues, clamped to the sequence) of sequences seq_idx[i] of `src`
+ * as a new batch: KmerSeqIterator::set_range (kmergenerator.rs:56-65), the blocks of BlockSeqSketcher
+ * (seqblocksketch.rs:97-149: block b of a sequence = bases [b*bs, b*bs + bs + k - 1)), the ranges of
+ * sketch_seqrange_superminhash (seqminhash.rs:19-62). */
+int32_t kmu_seqbatch_slices(kmu_ctx* ctx, const kmu_seqbatch* src, const uint64_t* seq_idx, const uint64_t* begin,
+                            const uint64_t* end, uint64_t nslices, kmu_seqbatch** batch);
 void kmu_seqbatch_destroy(kmu_seqbatch* batch);
 uint64_t kmu_seqbatch_nseq(const kmu_seqbatch* batch);
 uint64_t kmu_seqbatch_total_bases(const kmu_seqbatch* batch);
@@ -154,6 +160,16 @@ int32_t kmu_sketch_pmh3a(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, in
 int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t packed_bytes, const uint64_t* byte_off,
                               const uint64_t* nbases, uint64_t nseq, uint32_t k, int32_t kmer_type, int32_t hash_kind,
                               uint32_t m, void* sig);
+
+/* whole-file form: ONE signature for the batch (all contigs of a genome counted into one multiplicity
+ * map), ProbHash3aSketch::sketch_compressedkmer_seqs  src/sketching/setsketchert.rs:160-202.  sig: m values. */
+int32_t kmu_sketch_pmh3a_whole(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, int32_t kmer_type, int32_t hash_kind,
+                               uint32_t m, void* sig, int32_t sig_on_device);
+/* ProbMinHash3a::hash_weigthed_hashmap on an explicit weighted set (host arrays): n distinct keys of key_bytes
+ * (4 or 8) with positive f64 weights -- the f64-weighted maps of BlockSeqSketcher (seqblocksketch.rs:121-138)
+ * or any multiplicity map built elsewhere.  sig: m keys. */
+int32_t kmu_pmh3a_weighted(kmu_ctx* ctx, const void* keys, const double* weights, uint64_t n, int32_t key_bytes,
+                           uint32_t m, void* sig);
 
 /* ---- SuperMinHash per-sequence sketch
  *      SeqSketcher::sketch_superminhash          src/sketching/seqsketchjaccard.rs:328-380  (key_hasher FNV, :346-349)

@@ -66,6 +66,7 @@ SIGNATURES = {
     "kmu_seqbatch_alphabet": (C.c_int32, [C.c_void_p]),
     "kmu_seqbatch_sample_reads": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
                                               C.c_uint32, vpp]),
+    "kmu_seqbatch_slices": (C.c_int32, [C.c_void_p, C.c_void_p, u64p, u64p, u64p, C.c_uint64, vpp]),
     "kmu_seqbatch_destroy": (None, [C.c_void_p]),
     "kmu_seqbatch_nseq": (C.c_uint64, [C.c_void_p]),
     "kmu_seqbatch_total_bases": (C.c_uint64, [C.c_void_p]),
@@ -80,6 +81,9 @@ SIGNATURES = {
                                      C.c_int32]),
     "kmu_sketch_pmh3a_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, u64p, u64p, C.c_uint64, C.c_uint32,
                                           C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
+    "kmu_sketch_pmh3a_whole": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32, C.c_void_p,
+                                           C.c_int32]),
+    "kmu_pmh3a_weighted": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_uint32, C.c_void_p]),
     "kmu_sketch_superminhash": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32,
                                             C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "kmu_sketch_setsketch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32,

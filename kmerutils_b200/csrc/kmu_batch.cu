@@ -267,6 +267,58 @@ cudaError_t launch_sample_reads(const uint8_t* genome, uint64_t glen, uint64_t s
     return cudaGetLastError();
 }
 
+// ---- slices: sub-ranges of sequences as a new batch -------------------------------------------
+// (blocks of BlockSeqSketcher, src/sketching/seqblocksketch.rs:97-149; ranges of
+//  sketch_seqrange_superminhash, src/sketching/seqminhash.rs:19-62; KmerSeqIterator::set_range)
+// one thread per destination 32-bit word (DNA: 16 bases re-aligned with a funnel shift; amino acids: 4 codes)
+__global__ void slice_copy_kernel(const uint8_t* __restrict__ src, const uint64_t* __restrict__ src_byte_off,
+                                  const uint64_t* __restrict__ seq_idx, const uint64_t* __restrict__ begin,
+                                  const uint64_t* __restrict__ dst_byte_off, const uint64_t* __restrict__ dst_len,
+                                  uint64_t nslices, uint64_t total_words, int alphabet, uint8_t* dst) {
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < total_words;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t byte = w * 4;
+        uint64_t lo = 0, hi = nslices;
+        while (hi - lo > 1) {
+            uint64_t mid = (lo + hi) >> 1;
+            if (dst_byte_off[mid] <= byte) lo = mid; else hi = mid;
+        }
+        const uint64_t len = dst_len[lo];
+        const uint8_t* sp = src + src_byte_off[seq_idx[lo]];
+        uint32_t out = 0;
+        if (alphabet) {
+            const uint64_t p0 = byte - dst_byte_off[lo];
+            for (int i = 0; i < 4; ++i)
+                if (p0 + i < len) out |= (uint32_t)sp[begin[lo] + p0 + i] << (8 * i);
+            ((uint32_t*)dst)[w] = out;
+        } else {
+            const uint64_t p0 = (byte - dst_byte_off[lo]) * 4;  // first base of this word inside the slice
+            if (p0 < len) {
+                const uint64_t q = begin[lo] + p0;
+                const uint32_t* sw = (const uint32_t*)sp + (q >> 4);
+                const uint32_t sh = (uint32_t)(q & 15) * 2;
+                uint32_t v = be32(sw[0]);
+                if (sh) v = (v << sh) | (be32(sw[1]) >> (32 - sh));
+                const uint64_t left = len - p0;
+                if (left < 16) v &= ~0u << (32 - 2 * (uint32_t)left);  // pad with 'A' like Sequence::new
+                out = v;
+            }
+            ((uint32_t*)dst)[w] = __byte_perm(out, 0, 0x0123);
+        }
+    }
+}
+
+cudaError_t launch_slice_copy(const uint8_t* src, const uint64_t* src_byte_off, const uint64_t* seq_idx, const uint64_t* begin,
+                              const uint64_t* dst_byte_off, const uint64_t* dst_len, uint64_t nslices, uint64_t total_words,
+                              int alphabet, uint8_t* dst, cudaStream_t stream) {
+    if (total_words == 0 || nslices == 0) return cudaSuccess;
+    uint64_t want = (total_words + 255) / 256;
+    int grid = (int)(want < 148ull * 16 ? want : 148ull * 16);
+    slice_copy_kernel<<<grid, 256, 0, stream>>>(src, src_byte_off, seq_idx, begin, dst_byte_off, dst_len, nslices, total_words,
+                                                alphabet, dst);
+    return cudaGetLastError();
+}
+
 // ---- length classes ---------------------------------------------------------------------------
 __device__ __forceinline__ int len_bucket(uint64_t nk) {
     if (nk == 0) return LEN_BUCKETS - 1;

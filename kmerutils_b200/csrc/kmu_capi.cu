@@ -156,7 +156,8 @@ void kmu_ctx_destroy(kmu_ctx* c) {
     if (!c) return;
     ScopedDevice sd(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (auto* b : {&c->order, &c->counters, &c->table_scratch, &c->slot_scratch, &c->overflow, &c->sig_dev, &c->misc, &c->memo})
+    for (auto* b : {&c->order, &c->counters, &c->table_scratch, &c->slot_scratch, &c->overflow, &c->sig_dev, &c->misc, &c->memo,
+                    &c->whole_table, &c->items_slots})
         b->release();
     c->pinned.release();
     for (int i = 0; i < 2; ++i) {
@@ -527,6 +528,45 @@ int32_t kmu_seqbatch_sample_reads(kmu_ctx* ctx, const kmu_seqbatch* genome, uint
     if (e != cudaSuccess || rc) {
         kmu_seqbatch_destroy(b);
         return rc ? rc : fail(KMU_ECUDA, "read sampling failed: %s", cudaGetErrorString(e));
+    }
+    *out = b;
+    return KMU_OK;
+}
+
+int32_t kmu_seqbatch_slices(kmu_ctx* ctx, const kmu_seqbatch* src, const uint64_t* seq_idx, const uint64_t* begin,
+                            const uint64_t* end, uint64_t nslices, kmu_seqbatch** out) {
+    if (!ctx || !src || !out || (nslices && (!seq_idx || !begin || !end))) return fail(KMU_EINVAL, "null argument");
+    std::vector<uint64_t> len(nslices), beg(nslices);
+    for (uint64_t i = 0; i < nslices; ++i) {
+        if (seq_idx[i] >= src->nseq) return fail(KMU_EINVAL, "slice %llu names sequence %llu of %llu", (unsigned long long)i,
+                                                 (unsigned long long)seq_idx[i], (unsigned long long)src->nseq);
+        const uint64_t L = src->h_nbases[seq_idx[i]];
+        const uint64_t e = std::min(end[i], L), b0 = std::min(begin[i], e);
+        beg[i] = b0;
+        len[i] = e - b0;
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    kmu_seqbatch* b = nullptr;
+    int32_t rc = batch_alloc(ctx, len.data(), nslices, &b, src->alphabet);
+    if (rc) return rc;
+    rc = batch_upload_meta(ctx, b);
+    cudaError_t e = ctx->misc.reserve(2 * sizeof(uint64_t) * (nslices + 1));
+    uint64_t* d_idx = (uint64_t*)ctx->misc.p;
+    uint64_t* d_beg = d_idx + (nslices + 1);
+    if (e == cudaSuccess && nslices) {
+        e = cudaMemcpyAsync(d_idx, seq_idx, sizeof(uint64_t) * nslices, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_beg, beg.data(), sizeof(uint64_t) * nslices, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (e == cudaSuccess)
+        e = kmu::launch_slice_copy(src->packed, src->byte_off, d_idx, d_beg, b->byte_off, b->nbases, nslices, b->packed_bytes / 4,
+                                   src->alphabet, b->packed, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->packed + b->packed_bytes, 0, TAIL_SLACK, ctx->stream);
+    ctx->launches += 1;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // beg / len are host temporaries
+    if (e != cudaSuccess || rc) {
+        kmu_seqbatch_destroy(b);
+        return rc ? rc : fail(KMU_ECUDA, "slicing failed: %s", cudaGetErrorString(e));
     }
     *out = b;
     return KMU_OK;

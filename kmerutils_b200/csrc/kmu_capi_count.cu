@@ -1,6 +1,8 @@
 // kmu_capi_count.cu -- C ABI of the counting table (include/kmerutils_b200.h "k-mer counting").
 // Replaces KmerCounter / KmerCounterPool and the count_kmer* drivers of src/base/kmercount.rs.
 #include <algorithm>
+#include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "kmu_host.h"
@@ -279,6 +281,160 @@ int32_t kmu_count_partition(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
     for (uint32_t p = 0; p < nparts; ++p) part_counts[p] = pt[p];
+    return KMU_OK;
+}
+
+// ---- ProbMinHash3a over a weighted set --------------------------------------------------------
+static void fill_exp01(kmu::Exp01Params& e, uint32_t m) {
+    // ProbMinHash3a::new : lambda = ln(m / (m-1)); ExpRestricted01::new
+    const double lambda = std::log((double)m / (double)(m - 1));
+    e.lambda = lambda;
+    e.c1 = std::expm1(lambda) / lambda;
+    e.c2 = std::log(2.0 / (1.0 + std::exp(-lambda))) / lambda;
+    e.c3 = (1.0 - std::exp(-lambda)) / lambda;
+}
+
+// runs the item kernel with growing bounds until every slot ended below the bound
+static int32_t run_pmh3a_items(kmu_ctx* ctx, kmu::Pmh3aItemsParams P, bool key64, int src, uint64_t distinct, void* d_sig,
+                               uint64_t* launches) {
+    cudaStream_t st = ctx->stream;
+    const uint32_t m = P.m;
+    CUDA_TRY(ctx->items_slots.reserve(sizeof(kmu::Slot) * m + 64));
+    P.global_slots = (kmu::Slot*)ctx->items_slots.p;
+    unsigned long long* d_max = (unsigned long long*)((uint8_t*)ctx->items_slots.p + sizeof(kmu::Slot) * m);
+    const size_t smem = sizeof(kmu::Slot) * (size_t)m;
+    P.slots_in_smem = smem <= SMEM_BUDGET ? 1 : 0;
+    P.slot_thresh = (uint32_t)(0x100000000ULL % m);
+    fill_exp01(P.e, m);
+    const uint64_t work = (P.n + 511) / 512;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(work, (uint64_t)ctx->sm_count));
+    double bound = distinct ? (double)m / (double)distinct * std::log((double)m / 1e-4) : 1.0;
+    for (int attempt = 0; attempt < 200; ++attempt) {
+        P.bound = bound;
+        CUDA_TRY(kmu::launch_pmh3a_items_init(P.global_slots, m, st));
+        CUDA_TRY(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), st));
+        if (P.n) CUDA_TRY(kmu::launch_pmh3a_items(P, key64, src, grid, P.slots_in_smem ? smem : 0, st));
+        CUDA_TRY(kmu::launch_pmh3a_items_finish(P.global_slots, m, key64, d_sig, d_max, st));
+        *launches += 3;
+        unsigned long long mx = 0;
+        CUDA_TRY(cudaMemcpyAsync(&mx, d_max, sizeof(mx), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        double top;
+        std::memcpy(&top, &mx, 8);
+        if (distinct == 0 || top < bound) return KMU_OK;  // every slot filled below the bound: nothing pruned could win
+        bound *= 4.0;
+        if (!(bound < 1e300)) break;
+    }
+    return fail(KMU_ECUDA, "ProbMinHash3a item sketch did not converge");
+}
+
+int32_t kmu_pmh3a_weighted(kmu_ctx* ctx, const void* keys, const double* weights, uint64_t n, int32_t key_bytes, uint32_t m,
+                           void* sig) {
+    if (!ctx || !sig || (n && (!keys || !weights))) return fail(KMU_EINVAL, "null argument");
+    if (key_bytes != 4 && key_bytes != 8) return fail(KMU_EINVAL, "key_bytes must be 4 or 8");
+    if (m < 2) return fail(KMU_EINVAL, "ProbMinHash3a needs at least 2 hash values (m = %u)", m);
+    for (uint64_t i = 0; i < n; ++i)
+        if (!(weights[i] > 0.0)) return fail(KMU_EINVAL, "weight %llu is not positive", (unsigned long long)i);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    cudaStream_t st = ctx->stream;
+    const size_t kb = n * (size_t)key_bytes, wb = n * sizeof(double), sb = (size_t)m * key_bytes;
+    CUDA_TRY(ctx->misc.reserve(align_up(kb, 16) + align_up(wb, 16) + sb + 64));
+    uint8_t* d_keys = (uint8_t*)ctx->misc.p;
+    double* d_w = (double*)(d_keys + align_up(kb, 16));
+    void* d_sig = (uint8_t*)d_w + align_up(wb, 16);
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(d_keys, keys, kb, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_w, weights, wb, cudaMemcpyHostToDevice, st));
+    }
+    kmu::Pmh3aItemsParams P{};
+    P.keys = d_keys;
+    P.weights = d_w;
+    P.n = n;
+    P.m = m;
+    uint64_t launches = 0;
+    cudaEventRecord(ctx->ev[0], st);
+    int32_t rc = run_pmh3a_items(ctx, P, key_bytes == 8, 0, n, d_sig, &launches);
+    cudaEventRecord(ctx->ev[1], st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(sig, d_sig, sb, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    ctx->launches += launches;
+    ctx->last.launches = launches;
+    return KMU_OK;
+}
+
+int32_t kmu_sketch_pmh3a_whole(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t hash_kind,
+                               uint32_t m, void* sig, int32_t sig_on_device) {
+    if (!ctx || !b || !sig) return fail(KMU_EINVAL, "null argument");
+    if (int32_t a = kmu_check_kmer_args(b, k, kmer_type, hash_kind)) return a;
+    if (kmer_type_is_aa(kmer_type)) return fail(KMU_EINVAL, "whole-file ProbMinHash3a takes DNA sequences");
+    if (m < 2) return fail(KMU_EINVAL, "ProbMinHash3a needs at least 2 hash values (m = %u)", m);
+    uint64_t total = 0;
+    for (uint64_t L : b->h_nbases) total += L >= k ? L - k + 1 : 0;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    cudaStream_t st = ctx->stream;
+    const bool key64 = kmer_type == KMU_KMER64;
+    const size_t vsz = key64 ? 8 : 4;
+    void* d_sig = sig;
+    if (!sig_on_device) {
+        CUDA_TRY(ctx->sig_dev.reserve((size_t)m * vsz));
+        d_sig = ctx->sig_dev.p;
+    }
+    // multiplicity table over all sequences (the FnvHashMap of setsketchert.rs:171-189); the hash closures are
+    // injective on the pre-key, so counting pre-keys counts hashed keys
+    uint64_t want = std::max<uint64_t>(1024, total * 2);
+    if (2 * k < 40) want = std::min<uint64_t>(want, std::max<uint64_t>(1024, 2ull << (2 * k)));
+    uint64_t cap = 1024;
+    while (cap < want) cap <<= 1;
+    const size_t slot_bytes = key64 ? 16 : 8;
+    cudaError_t me = ctx->whole_table.reserve(cap * slot_bytes + sizeof(unsigned long long) * AUX_WORDS);
+    if (me != cudaSuccess)
+        return fail(KMU_ENOMEM, "multiplicity table of %llu slots: %s", (unsigned long long)cap, cudaGetErrorString(me));
+    kmu::CountTable t;
+    t.slots = ctx->whole_table.p;
+    t.capmask = cap - 1;
+    unsigned long long* aux = (unsigned long long*)((uint8_t*)ctx->whole_table.p + cap * slot_bytes);
+    t.special = aux;
+    t.overflow = aux + 1;
+    unsigned long long* stats = aux + 8;
+    uint64_t launches = 0;
+    cudaEventRecord(ctx->ev[0], st);
+    CUDA_TRY(cudaMemsetAsync(aux, 0, sizeof(unsigned long long) * AUX_WORDS, st));
+    CUDA_TRY(kmu::launch_count_init(t, key64, ctx->sm_count, st));
+    kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
+    CUDA_TRY(kmu::launch_count_insert_seqs(v, b->packed_bytes, k, key64, kmu::hash_kind_is_canonical_host(hash_kind), t,
+                                           ctx->sm_count, st));
+    CUDA_TRY(kmu::launch_count_stats(t, key64, stats, ctx->sm_count, st));
+    launches += 3;
+    std::vector<unsigned long long> h(3 + 256);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), stats, sizeof(unsigned long long) * (3 + 256), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    uint64_t distinct = 0;
+    for (int i = 1; i < 256; ++i) distinct += h[3 + i];
+    kmu::Pmh3aItemsParams P{};
+    P.table = t.slots;
+    P.special = t.special;
+    P.n = cap;
+    P.k = k;
+    P.kmer_type = kmer_type;
+    P.hash_kind = hash_kind;
+    P.m = m;
+    int32_t rc = run_pmh3a_items(ctx, P, key64, key64 ? 2 : 1, distinct, d_sig, &launches);
+    cudaEventRecord(ctx->ev[1], st);
+    if (rc) return rc;
+    if (!sig_on_device) {
+        CUDA_TRY(cudaMemcpyAsync(sig, d_sig, (size_t)m * vsz, cudaMemcpyDeviceToHost, st));
+        ctx->last.d2h_bytes = (size_t)m * vsz;
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    ctx->launches += launches;
+    ctx->last.launches = launches;
     return KMU_OK;
 }
 

@@ -85,6 +85,7 @@ struct kmu_ctx {
     int sm_count = 148;
     // scratch
     DevBuf order, counters, table_scratch, slot_scratch, overflow, sig_dev, misc;
+    DevBuf whole_table, items_slots;  // whole-file ProbMinHash3a: counting table + global slots
     bool table_scratch_clean = false;
     PinnedBuf pinned;
     // first-point table of the ProbMinHash3a kernels (small key spaces), see kmu_pmh3a.cu

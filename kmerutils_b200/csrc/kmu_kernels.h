@@ -91,6 +91,9 @@ cudaError_t launch_synth_aa(uint8_t* codes, const uint64_t* byte_off, const uint
 cudaError_t launch_sample_reads(const uint8_t* genome, uint64_t glen, uint64_t seed, uint64_t first_read, uint64_t nreads,
                                 uint32_t read_len, uint32_t err_ppm, uint32_t words_per_read, uint8_t* out,
                                 cudaStream_t stream);
+cudaError_t launch_slice_copy(const uint8_t* src, const uint64_t* src_byte_off, const uint64_t* seq_idx, const uint64_t* begin,
+                              const uint64_t* dst_byte_off, const uint64_t* dst_len, uint64_t nslices, uint64_t total_words,
+                              int alphabet, uint8_t* dst, cudaStream_t stream);
 // length classes: bucket = 8 per octave of the k-mer count, bucket 0 = longest
 constexpr int LEN_BUCKETS = 512;
 cudaError_t launch_len_hist(const uint64_t* nbases, uint64_t nseq, uint32_t k, unsigned long long* hist,
@@ -118,6 +121,28 @@ cudaError_t launch_generate_kmers(const SeqView& b, uint32_t k, int kmer_type, i
                                   void* out, cudaStream_t stream);
 cudaError_t launch_nthash(const SeqView& b, uint32_t k, uint32_t n_multi, const uint64_t* out_off, uint64_t* out_hash,
                           uint8_t* out_strand, cudaStream_t stream);
+
+inline bool hash_kind_is_canonical_host(int hash_kind) { return hash_kind == 2 || hash_kind == 3; }  // KMU_HASH_CANON_*
+
+// ---- ProbMinHash3a over a weighted set (kmu_pmh3a_items.cu) -----------------------------------
+struct Pmh3aItemsParams {
+    const void* keys;        // SRC 0: n keys (u32 / u64)
+    const double* weights;   // SRC 0: n weights
+    const void* table;       // SRC 1 / 2: counting table slots, n = number of slots
+    const unsigned long long* special;  // SRC 2: multiplicity of the key ~0
+    uint64_t n;
+    uint32_t k;
+    int kmer_type, hash_kind;  // SRC 1 / 2: table keys are pre-keys, mapped through the hash closure
+    uint32_t m, slot_thresh;
+    Exp01Params e;
+    double bound;
+    int slots_in_smem;
+    Slot* global_slots;
+};
+cudaError_t launch_pmh3a_items(const Pmh3aItemsParams& P, bool key64, int src, int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_pmh3a_items_init(Slot* slots, uint32_t m, cudaStream_t st);
+cudaError_t launch_pmh3a_items_finish(const Slot* slots, uint32_t m, bool key64, void* sig, unsigned long long* max_hbits,
+                                      cudaStream_t st);
 
 // ---- SuperMinHash (kmu_smh.cu) ----------------------------------------------------------------
 struct SmhParams {

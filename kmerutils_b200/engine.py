@@ -63,6 +63,14 @@ class SeqBatch:
                                                     _p(nb, u64p)))
         return packed, off, nb
 
+    def download_meta(self):
+        """-> (None, byte_off[nseq], nbases[nseq]) without copying the packed bytes"""
+        n = len(self)
+        off = np.zeros(n, dtype=np.uint64)
+        nb = np.zeros(n, dtype=np.uint64)
+        check(self.engine.lib.kmu_seqbatch_download(self.engine.ctx, self.handle, None, _p(off, u64p), _p(nb, u64p)))
+        return None, off, nb
+
     def destroy(self):
         if self._h is not None:
             self.engine.lib.kmu_seqbatch_destroy(self._h)
@@ -194,6 +202,31 @@ class Engine:
                                                  C.byref(h)))
         return SeqBatch(self, h)
 
+    def batch_slices(self, src, seq_idx, begin, end):
+        """New batch made of the ranges [begin[i], end[i]) of sequences seq_idx[i] of `src` (copied on the device)."""
+        idx, b, e = _as_u64(seq_idx), _as_u64(begin), _as_u64(end)
+        h = C.c_void_p()
+        check(self.lib.kmu_seqbatch_slices(self.ctx, src.handle, _p(idx, u64p), _p(b, u64p), _p(e, u64p), len(idx),
+                                           C.byref(h)))
+        return SeqBatch(self, h)
+
+    def blocksketch(self, batch, k, m, block_size, hash_kind=HASH_CANON_INVHASH):
+        """BlockSeqSketcher::blocksketch_sequences (seqblocksketch.rs:97-167): every sequence is cut into runs of
+        block_size consecutive k-mers (Kmer32bit), one ProbMinHash3a signature per block.  The number of blocks
+        comes from the BASES (ceil(L / block_size)), so trailing blocks may be empty (all-zero signature).
+        -> (sig[nblocks_total, m], numseq[nblocks_total], numblock[nblocks_total])"""
+        _, _, nb = batch.download_meta()
+        nblocks = (nb + np.uint64(block_size) - np.uint64(1)) // np.uint64(block_size)
+        numseq = np.repeat(np.arange(len(nb), dtype=np.uint64), nblocks.astype(np.int64))
+        first = np.concatenate([[0], np.cumsum(nblocks)[:-1]]).astype(np.uint64) if len(nb) else np.zeros(0, np.uint64)
+        numblock = np.arange(int(nblocks.sum()), dtype=np.uint64) - np.repeat(first, nblocks.astype(np.int64))
+        begin = numblock * np.uint64(block_size)
+        end = begin + np.uint64(block_size + k - 1)
+        blocks = self.batch_slices(batch, numseq, begin, end)
+        sig = self.sketch_pmh3a(blocks, k, KMER32, hash_kind, m)
+        blocks.destroy()
+        return sig, numseq.astype(np.uint32), numblock.astype(np.uint32)
+
     # ---- k-mers ---------------------------------------------------------------------------
     def generate_kmers(self, batch, k, kmer_type, hash_kind=_lib.HASH_IDENTITY_RAW):
         """-> (values, out_off): all k-mers of all sequences mapped through the hash closure."""
@@ -259,6 +292,22 @@ class Engine:
         check(self.lib.kmu_sketch_setsketch(self.ctx, batch.handle, k, kmer_type, hash_kind, C.byref(prm),
                                             dtype.itemsize, int(bool(whole)), _p(out), 0))
         return out[0] if whole else out
+
+    def sketch_pmh3a_whole(self, batch, k, kmer_type, hash_kind=HASH_CANON_INVHASH, m=200):
+        """ONE ProbMinHash3a signature for the whole batch (ProbHash3aSketch::sketch_compressedkmer_seqs)."""
+        out = np.zeros(m, dtype=val_dtype(kmer_type))
+        check(self.lib.kmu_sketch_pmh3a_whole(self.ctx, batch.handle, k, kmer_type, hash_kind, m, _p(out), 0))
+        return out
+
+    def pmh3a_weighted(self, keys, weights, m):
+        """ProbMinHash3a::hash_weigthed_hashmap on explicit (key, weight) arrays; keys u32 or u64."""
+        keys = np.ascontiguousarray(keys)
+        if keys.dtype not in (np.dtype(np.uint32), np.dtype(np.uint64)):
+            raise ValueError("keys must be uint32 or uint64")
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        out = np.zeros(m, dtype=keys.dtype)
+        check(self.lib.kmu_pmh3a_weighted(self.ctx, _p(keys), _p(w), len(keys), keys.dtype.itemsize, m, _p(out)))
+        return out
 
     def sketch_pmh3a_host(self, packed, byte_off, nbases, k, kmer_type, hash_kind, m, out):
         """One-shot: host packed buffer in, host signatures out (H2D + kernels + D2H)."""

@@ -1,0 +1,106 @@
+"""Whole-file ProbMinHash3a (sketch_compressedkmer_seqs), explicit weighted sets, slices and block sketches."""
+import numpy as np
+import pytest
+
+import kmerutils_b200 as kb
+from test_pmh3a_gpu import S80, oracle_batch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("k,ktype,kind,m", [(16, kb.KMER16B32, kb.HASH_CANON_INVHASH, 12000),
+                                            (8, kb.KMER32, kb.HASH_CANON_INVHASH, 200),
+                                            (21, kb.KMER64, kb.HASH_CANON_INVHASH, 1000),
+                                            (31, kb.KMER64, kb.HASH_IDENTITY_RAW, 64),
+                                            (12, kb.KMER32, kb.HASH_MASKED_VALUE, 15000)])
+def test_pmh3a_whole_file(engine, oracle, k, ktype, kind, m):
+    # ProbHash3aSketch::sketch_compressedkmer_seqs (setsketchert.rs:160-202): contigs of one genome -> one signature
+    rng = np.random.default_rng(k + m)
+    nb = np.concatenate([[400000, 90000, 5, k], rng.integers(k, 20000, 30)]).astype(np.uint64)
+    batch = engine.batch_synth(60 + k, nb)
+    packed, off = oracle_batch(oracle, 60 + k, nb)
+    got = engine.sketch_pmh3a_whole(batch, k, ktype, kind, m)
+    want = oracle.sketch_pmh3a_seqs(packed, off, nb, k, ktype, kind, m)
+    assert np.array_equal(got.astype(np.uint64), want)
+
+
+def test_pmh3a_whole_small_inputs(engine, oracle):
+    # fewer distinct k-mers than slots: the bound has to grow until every slot is filled; no k-mer at all: zeros
+    for nb in ([30], [9, 8], [7, 3]):
+        nb = np.array(nb, dtype=np.uint64)
+        batch = engine.batch_synth(5, nb)
+        packed, off = oracle_batch(oracle, 5, nb)
+        got = engine.sketch_pmh3a_whole(batch, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200)
+        want = oracle.sketch_pmh3a_seqs(packed, off, nb, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200)
+        assert np.array_equal(got.astype(np.uint64), want)
+
+
+@pytest.mark.parametrize("dtype", [np.uint32, np.uint64])
+def test_pmh3a_weighted_set(engine, oracle, dtype):
+    # ProbMinHash3a::hash_weigthed_hashmap on explicit (key, weight) pairs, f64 weights (seqblocksketch.rs:121-138)
+    rng = np.random.default_rng(4)
+    for n, m in [(1, 50), (7, 50), (300, 200), (50000, 200), (200000, 12000)]:
+        keys = np.unique(rng.integers(0, np.iinfo(dtype).max, n, dtype=np.uint64).astype(dtype))
+        w = rng.integers(1, 40, len(keys)).astype(np.float64)
+        if n == 300:
+            w = w + 0.5  # non-integer weights
+        got = engine.pmh3a_weighted(keys, w, m)
+        want = oracle.pmh3a_weighted(keys.astype(np.uint64), w, m, np.dtype(dtype).itemsize)
+        assert np.array_equal(got.astype(np.uint64), want)
+    with pytest.raises(kb.KmuInvalid):
+        engine.pmh3a_weighted(np.array([1, 2], dtype=dtype), np.array([1.0, 0.0]), 10)
+
+
+def test_slices(engine, oracle):
+    rng = np.random.default_rng(8)
+    nb = np.array([1000, 37, 5000, 16, 64], dtype=np.uint64)
+    batch = engine.batch_synth(12, nb)
+    packed, off = oracle_batch(oracle, 12, nb)
+    seqs = [oracle.unpack_2bit(packed[int(o): int(o) + (int(n) + 3) // 4], int(n)) for o, n in zip(off, nb)]
+    idx = rng.integers(0, len(nb), 200).astype(np.uint64)
+    begin = np.array([rng.integers(0, int(nb[i]) + 1) for i in idx], dtype=np.uint64)
+    end = np.array([b + rng.integers(0, 300) for b in begin], dtype=np.uint64)  # may overrun: clamped
+    sl = engine.batch_slices(batch, idx, begin, end)
+    sp, so, sn = sl.download()
+    for j in range(len(idx)):
+        want = seqs[int(idx[j])][int(begin[j]): int(end[j])]
+        assert int(sn[j]) == len(want)
+        nbytes = (len(want) + 3) // 4
+        got = sp[int(so[j]): int(so[j]) + nbytes]
+        assert oracle.unpack_2bit(got, len(want)) == want
+        if len(want) % 4:  # the tail is padded with 'A' (00) like Sequence::new (sequence.rs:66-71)
+            assert got[-1] & ((1 << (8 - 2 * (len(want) % 4))) - 1) == 0
+    # amino-acid batches slice too
+    aa = engine.batch_synth_aa(3, np.array([500, 20], dtype=np.uint64))
+    codes, aoff, _ = aa.download()
+    sa = engine.batch_slices(aa, [0, 1, 0], [10, 0, 490], [30, 25, 600])
+    c2, o2, n2 = sa.download()
+    assert n2.tolist() == [20, 20, 10]
+    assert np.array_equal(c2[int(o2[0]): int(o2[0]) + 20], codes[10:30])
+    assert np.array_equal(c2[int(o2[2]): int(o2[2]) + 10], codes[490:500])
+
+
+@pytest.mark.parametrize("block_size", [50, 64, 1000])
+def test_block_sketch(engine, oracle, block_size):
+    # BlockSeqSketcher::blocksketch_sequences (seqblocksketch.rs:97-167), k = 8 Kmer32bit, canonical + int32_hash
+    nb = np.array([1000, 207, 64, 50, 5, 3333], dtype=np.uint64)
+    batch = engine.batch_synth(19, nb)
+    packed, off = oracle_batch(oracle, 19, nb)
+    sig, numseq, numblock = engine.blocksketch(batch, 8, 40, block_size)
+    row = 0
+    for s, L in enumerate(nb):
+        want = oracle.blocksketch_seq(packed[int(off[s]):], int(L), 8, 40, block_size)
+        n = len(want)
+        assert n == (int(L) + block_size - 1) // block_size
+        assert np.array_equal(sig[row:row + n], want)
+        assert (numseq[row:row + n] == s).all() and numblock[row:row + n].tolist() == list(range(n))
+        row += n
+    assert row == len(sig)
+
+
+def test_block_sketch_reference_test(engine):
+    # seqblocksketch.rs:458-496: a sequence compared with itself block by block has distance 1 (all slots equal)
+    batch, _ = engine.batch_from_ascii([S80, S80])
+    sig, numseq, numblock = engine.blocksketch(batch, 3, 10, 20)
+    a, b = sig[numseq == 0], sig[numseq == 1]
+    assert a.shape == b.shape == (4, 10) and np.array_equal(a, b)
