@@ -240,6 +240,36 @@ int32_t kmu_count_export(kmu_ctx* ctx, const kmu_counter* counter, uint32_t min_
 int32_t kmu_count_partition(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, int32_t kmer_type, int32_t canonical,
                             uint32_t nparts, void* kmers_out, uint64_t* part_counts, int32_t out_on_device);
 
+/* ---- host-side feeders and writers (no device work) --------------------------------------------
+ * FASTA / FASTQ reader: packs of ACCEPTED reads as one ASCII buffer + offsets, ready for
+ * kmu_seqbatch_from_ascii.  A record holding any non-ACGT character is dropped and counted, as
+ * parse_with_needletail (src/io.rs:12-72) and readblockseq (src/bin/datasketcher.rs:358-388) do. */
+typedef struct kmu_fastx kmu_fastx;
+int32_t kmu_fastx_open(const char* path, kmu_fastx** reader);
+void kmu_fastx_close(kmu_fastx* reader);
+int32_t kmu_fastx_next_pack(kmu_fastx* reader, uint64_t max_seqs, uint8_t* ascii, uint64_t ascii_cap, uint64_t* ascii_off,
+                            uint64_t* nseq_out);
+void kmu_fastx_stats(const kmu_fastx* reader, uint64_t* nb_read, uint64_t* nb_bad_read, uint64_t* nb_bases,
+                     uint64_t* nb_bad_bases);
+/* signature dump: `u32 0xceabeadd | u32 sig_size = 4 | u32 sketch_size | u32 kmer_size`, then sketch_size u32 per
+ * sequence in input order (SeqSketcher::create_signature_dump, dump_signatures_block_u32,
+ * src/sketching/seqsketchjaccard.rs:390-414, 577-585) */
+typedef struct kmu_sigdump kmu_sigdump;
+int32_t kmu_sigdump_create(const char* path, uint32_t sketch_size, uint32_t kmer_size, kmu_sigdump** dump);
+int32_t kmu_sigdump_write(kmu_sigdump* dump, const uint32_t* sig, uint64_t nseq);
+/* block signature dump: `u32 0xceabbadd | u8 sig_size = 4 | u32 sketch_size | u32 kmer_size | u32 block_size`, then per
+ * sequence `u32 numseq | u32 nbblocks` and per block `u32 numseq | u32 numblock | sketch`
+ * (BlockSeqSketcher::create_signature_dump / dump_blocks, src/sketching/seqblocksketch.rs:59-65, 172-226) */
+int32_t kmu_blockdump_create(const char* path, uint32_t sketch_size, uint32_t kmer_size, uint32_t block_size,
+                             kmu_sigdump** dump);
+int32_t kmu_blockdump_write(kmu_sigdump* dump, const uint32_t* sig, const uint32_t* numseq, const uint32_t* numblock,
+                            uint64_t nblocks);
+int32_t kmu_sigdump_close(kmu_sigdump* dump);
+/* SigSketchFileReader (seqsketchjaccard.rs:588-712): header, number of signatures, and (sig != NULL) signatures
+ * first .. first + count */
+int32_t kmu_sigdump_read(const char* path, uint32_t* sig_size, uint32_t* sketch_size, uint32_t* kmer_size, uint64_t* nsig,
+                         uint32_t* sig, uint64_t first, uint64_t count);
+
 /* ---- timing of the last compute call on the context (CUDA events on its stream) ----- */
 typedef struct kmu_times {
     float kernel_ms;    /* device time of the compute kernels of the last call */

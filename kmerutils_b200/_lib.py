@@ -98,6 +98,17 @@ SIGNATURES = {
     "kmu_count_export": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
     "kmu_count_partition": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32,
                                         C.c_void_p, u64p, C.c_int32]),
+    "kmu_fastx_open": (C.c_int32, [C.c_char_p, vpp]),
+    "kmu_fastx_close": (None, [C.c_void_p]),
+    "kmu_fastx_next_pack": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p, u64p]),
+    "kmu_fastx_stats": (None, [C.c_void_p, u64p, u64p, u64p, u64p]),
+    "kmu_sigdump_create": (C.c_int32, [C.c_char_p, C.c_uint32, C.c_uint32, vpp]),
+    "kmu_sigdump_write": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "kmu_blockdump_create": (C.c_int32, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, vpp]),
+    "kmu_blockdump_write": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "kmu_sigdump_close": (C.c_int32, [C.c_void_p]),
+    "kmu_sigdump_read": (C.c_int32, [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                     u64p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "kmu_last_times": (C.c_int32, [C.c_void_p, C.POINTER(KmuTimes)]),
     "kmu_ctx_set_profiling": (C.c_int32, [C.c_void_p, C.c_int32]),
     "kmu_last_launch_profile": (C.c_uint32, [C.c_void_p, C.POINTER(KmuLaunchRec), C.c_uint32]),

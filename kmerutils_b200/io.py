@@ -1,0 +1,168 @@
+"""Host-side feeders and writers around the GPU path: FASTA/FASTQ packs (src/io.rs, datasketcher's readblockseq),
+signature dumps (seqsketchjaccard.rs:382-414, 572-712), block signature dumps (seqblocksketch.rs:59-65, 172-226),
+sketch parameter JSON (sketcharg.rs:79-138), and the datasketcher loop that ties them to the kernels."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, u64p
+
+
+def _p(a, t=C.c_void_p):
+    return a.ctypes.data_as(t)
+
+
+class FastxReader:
+    """Packs of accepted reads; a record with any non-ACGT character is dropped (io.rs:41-48)."""
+
+    def __init__(self, path, pack_bases=64 << 20):
+        self.lib = _lib.load_library()
+        h = C.c_void_p()
+        check(self.lib.kmu_fastx_open(os.fsencode(path), C.byref(h)))
+        self._h = h
+        self.buf = np.zeros(pack_bases, dtype=np.uint8)
+
+    def next_pack(self, max_seqs=10000):
+        """-> list of bytes (ASCII reads), empty at end of file.  10000 is datasketcher's pack (datasketcher.rs:244)."""
+        buf, off = self.next_pack_raw(max_seqs)
+        return [buf[int(off[i]): int(off[i + 1])].tobytes() for i in range(len(off) - 1)]
+
+    def next_pack_raw(self, max_seqs=10000):
+        """-> (ascii buffer view, offsets[n + 1]) without splitting into Python objects"""
+        off = np.zeros(max_seqs + 1, dtype=np.uint64)
+        n = C.c_uint64()
+        check(self.lib.kmu_fastx_next_pack(self._h, max_seqs, _p(self.buf), self.buf.nbytes, _p(off, u64p), C.byref(n)))
+        return self.buf, off[: n.value + 1]
+
+    def stats(self):
+        v = [C.c_uint64() for _ in range(4)]
+        self.lib.kmu_fastx_stats(self._h, *[C.byref(x) for x in v])
+        return dict(zip(("nb_read", "nb_bad_read", "nb_bases", "nb_bad_bases"), (x.value for x in v)))
+
+    def close(self):
+        if self._h is not None:
+            self.lib.kmu_fastx_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class SignatureDump:
+    """SeqSketcher::create_signature_dump + dump_signatures_block_u32."""
+
+    def __init__(self, path, sketch_size, kmer_size):
+        self.lib = _lib.load_library()
+        h = C.c_void_p()
+        check(self.lib.kmu_sigdump_create(os.fsencode(path), sketch_size, kmer_size, C.byref(h)))
+        self._h = h
+        self.sketch_size = sketch_size
+
+    def write(self, sig):
+        sig = np.ascontiguousarray(sig, dtype=np.uint32)
+        assert sig.ndim == 2 and sig.shape[1] == self.sketch_size
+        check(self.lib.kmu_sigdump_write(self._h, _p(sig), sig.shape[0]))
+
+    def close(self):
+        if self._h is not None:
+            check(self.lib.kmu_sigdump_close(self._h))
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class BlockSignatureDump:
+    """BlockSeqSketcher::create_signature_dump + dump_blocks."""
+
+    def __init__(self, path, sketch_size, kmer_size, block_size):
+        self.lib = _lib.load_library()
+        h = C.c_void_p()
+        check(self.lib.kmu_blockdump_create(os.fsencode(path), sketch_size, kmer_size, block_size, C.byref(h)))
+        self._h = h
+        self.sketch_size = sketch_size
+
+    def write(self, sig, numseq, numblock):
+        sig = np.ascontiguousarray(sig, dtype=np.uint32)
+        ns = np.ascontiguousarray(numseq, dtype=np.uint32)
+        nb = np.ascontiguousarray(numblock, dtype=np.uint32)
+        assert sig.shape == (len(ns), self.sketch_size) and len(nb) == len(ns)
+        check(self.lib.kmu_blockdump_write(self._h, _p(sig), _p(ns), _p(nb), len(ns)))
+
+    def close(self):
+        if self._h is not None:
+            check(self.lib.kmu_sigdump_close(self._h))
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def read_signature_dump(path, first=0, count=None):
+    """SigSketchFileReader: -> (header dict, signatures[count, sketch_size] u32)"""
+    lib = _lib.load_library()
+    ss, sk, ks, n = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
+    check(lib.kmu_sigdump_read(os.fsencode(path), C.byref(ss), C.byref(sk), C.byref(ks), C.byref(n), None, 0, 0))
+    if count is None:
+        count = n.value - first
+    sig = np.zeros((count, sk.value), dtype=np.uint32)
+    if count:
+        check(lib.kmu_sigdump_read(os.fsencode(path), None, None, None, None, _p(sig), first, count))
+    return {"sig_size": ss.value, "sketch_size": sk.value, "kmer_size": ks.value, "nb_signatures": n.value}, sig
+
+
+def dump_sketch_params(dirpath, kmer_size, sketch_size, algo="PROB3A", data_t="DNA"):
+    """SeqSketcherParams::dump_json (sketcharg.rs:79-106): `sketchparams_dump.json` in a directory."""
+    path = os.path.join(dirpath, "sketchparams_dump.json")
+    with open(path, "w") as f:
+        json.dump({"kmer_size": kmer_size, "sketch_size": sketch_size, "algo": algo, "data_t": data_t}, f)
+    return path
+
+
+def reload_sketch_params(dirpath):
+    """SeqSketcherParams::reload_json (sketcharg.rs:109-138)"""
+    with open(os.path.join(dirpath, "sketchparams_dump.json")) as f:
+        d = json.load(f)
+    for key in ("kmer_size", "sketch_size", "algo", "data_t"):
+        if key not in d:
+            raise ValueError(f"SeqSketcherParams reload: missing {key}")
+    return d
+
+
+def datasketcher(engine, fastx_path, dump_path, kmer_size=8, sketch_size=200, pack=10000, block_size=0):
+    """The loop of src/bin/datasketcher.rs:236-300: read packs of `pack` accepted reads, sketch each read with
+    ProbMinHash3a (Kmer32bit, canonical + int32_hash, :222-226) on the GPU, append the signatures to the dump.
+    block_size > 0 sketches blocks of k-mers instead (BlockSeqSketcher, pack 5000).  -> number of reads sketched"""
+    from ._lib import HASH_CANON_INVHASH, KMER32
+    n_done = 0
+    with FastxReader(fastx_path) as rd:
+        if block_size:
+            out = BlockSignatureDump(dump_path, sketch_size, kmer_size, block_size)
+        else:
+            out = SignatureDump(dump_path, sketch_size, kmer_size)
+        with out:
+            while True:
+                reads = rd.next_pack(pack)
+                if not reads:
+                    break
+                batch, _ = engine.batch_from_ascii(reads)
+                if block_size:
+                    sig, numseq, numblock = engine.blocksketch(batch, kmer_size, sketch_size, block_size)
+                    out.write(sig, numseq + np.uint32(n_done), numblock)
+                else:
+                    out.write(engine.sketch_pmh3a(batch, kmer_size, KMER32, HASH_CANON_INVHASH, sketch_size))
+                batch.destroy()
+                n_done += len(reads)
+    return n_done

@@ -1,0 +1,95 @@
+"""Host-side feeders / writers (CPU): FASTA/FASTQ packs with the reference's non-ACGT read rejection
+(src/io.rs:12-72, datasketcher.rs:358-388), signature dump formats, params JSON."""
+import struct
+
+import numpy as np
+import pytest
+
+import kmerutils_b200 as kb
+from kmerutils_b200 import io as kio
+
+
+def write(tmp_path, name, text):
+    p = tmp_path / name
+    p.write_bytes(text)
+    return str(p)
+
+
+def test_fastq_packs_and_rejection(tmp_path):
+    recs = [(b"r1", b"ACGTACGTAC"), (b"r2", b"ACGTNACGT"), (b"r3", b"acgtTTGA"), (b"r4", b"GGGG"), (b"r5", b"ACRT")]
+    text = b"".join(b"@" + n + b" desc\n" + s + b"\n+\n" + b"I" * len(s) + b"\n" for n, s in recs)
+    with kio.FastxReader(write(tmp_path, "a.fastq", text)) as rd:
+        first = rd.next_pack(2)
+        rest = rd.next_pack(10)
+        assert rd.next_pack(10) == []
+        st = rd.stats()
+    assert first == [b"ACGTACGTAC", b"acgtTTGA"] and rest == [b"GGGG"]  # reads with N / R are dropped whole
+    assert st == {"nb_read": 5, "nb_bad_read": 2, "nb_bases": 35, "nb_bad_bases": 2}
+
+
+def test_fasta_multiline_crlf_and_quality_traps(tmp_path):
+    fasta = b">s1 first\r\nACGT\r\nAC\r\n\r\n>s2\nTTTT\n>s3\nNNNN\n>s4\nGATTACA"
+    with kio.FastxReader(write(tmp_path, "b.fa", fasta)) as rd:
+        assert rd.next_pack() == [b"ACGTAC", b"TTTT", b"GATTACA"]
+    # a quality line may start with '@' or '>' : the reader counts quality characters, it does not look for headers
+    fq = b"@q1\nACGT\n+\n@>II\n@q2\nGGCC\n+q2\n>@@@\n"
+    with kio.FastxReader(write(tmp_path, "c.fq", fq)) as rd:
+        assert rd.next_pack() == [b"ACGT", b"GGCC"]
+    with pytest.raises(kb.KmuError):
+        kio.FastxReader(str(tmp_path / "missing.fq"))
+    with kio.FastxReader(write(tmp_path, "d.fq", b"garbage\n")) as rd:
+        with pytest.raises(kb.KmuInvalid):
+            rd.next_pack()
+
+
+def test_pack_buffer_boundary(tmp_path):
+    reads = [b"A" * 30, b"C" * 30, b"G" * 30]
+    text = b"".join(b">x\n" + r + b"\n" for r in reads)
+    rd = kio.FastxReader(write(tmp_path, "e.fa", text), pack_bases=64)
+    assert rd.next_pack() == reads[:2]  # the third read does not fit: it opens the next pack
+    assert rd.next_pack() == reads[2:]
+    assert rd.next_pack() == []
+    assert rd.stats()["nb_read"] == 3
+    rd.close()
+
+
+def test_signature_dump_format(tmp_path):
+    path = str(tmp_path / "sig.bin")
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 2**32, (3, 5), dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 2**32, (2, 5), dtype=np.uint64).astype(np.uint32)
+    with kio.SignatureDump(path, 5, 8) as d:
+        d.write(a)
+        d.write(b)
+    raw = open(path, "rb").read()
+    # u32 0xceabeadd | u32 sig_size = 4 | u32 sketch_size | u32 kmer_size, little endian (seqsketchjaccard.rs:402-409)
+    assert struct.unpack("<4I", raw[:16]) == (0xceabeadd, 4, 5, 8)
+    assert raw[16:] == np.concatenate([a, b]).astype("<u4").tobytes()
+    hdr, sig = kio.read_signature_dump(path)
+    assert hdr == {"sig_size": 4, "sketch_size": 5, "kmer_size": 8, "nb_signatures": 5}
+    assert np.array_equal(sig, np.concatenate([a, b]))
+    _, part = kio.read_signature_dump(path, first=1, count=3)
+    assert np.array_equal(part, np.concatenate([a, b])[1:4])
+    open(path, "r+b").write(b"\0\0\0\0")
+    with pytest.raises(kb.KmuInvalid):  # "file is not a dump of signature"
+        kio.read_signature_dump(path)
+
+
+def test_block_dump_format(tmp_path):
+    path = str(tmp_path / "blocks.bin")
+    sig = np.arange(5 * 3, dtype=np.uint32).reshape(5, 3)
+    numseq = np.array([7, 7, 7, 9, 9], dtype=np.uint32)
+    numblock = np.array([0, 1, 2, 0, 1], dtype=np.uint32)
+    with kio.BlockSignatureDump(path, 3, 8, 100) as d:
+        d.write(sig, numseq, numblock)
+    raw = open(path, "rb").read()
+    # 17-byte header: sig_size is ONE byte in the writer (seqblocksketch.rs:216-224)
+    assert struct.unpack("<IBIII", raw[:17]) == (0xceabbadd, 4, 3, 8, 100)
+    body = np.frombuffer(raw[17:], dtype="<u4")
+    want = [7, 3, 7, 0, 0, 1, 2, 7, 1, 3, 4, 5, 7, 2, 6, 7, 8, 9, 2, 9, 0, 9, 10, 11, 9, 1, 12, 13, 14]
+    assert body.tolist() == want
+
+
+def test_sketch_params_json(tmp_path):
+    kio.dump_sketch_params(str(tmp_path), 8, 200, "PROB3A", "DNA")
+    assert kio.reload_sketch_params(str(tmp_path)) == {"kmer_size": 8, "sketch_size": 200, "algo": "PROB3A", "data_t": "DNA"}
