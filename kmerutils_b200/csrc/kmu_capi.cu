@@ -634,7 +634,7 @@ int32_t kmu_generate_kmers(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int3
     }
     kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    CUDA_TRY(kmu::launch_generate_kmers(v, k, kmer_type, hash_kind, (const uint64_t*)ctx->misc.p, dout, ctx->stream));
+    CUDA_TRY(kmu::launch_generate_kmers(v, b->packed_bytes, k, kmer_type, hash_kind, (const uint64_t*)ctx->misc.p, dout, ctx->stream));
     cudaEventRecord(ctx->ev[1], ctx->stream);
     ctx->launches += 1;
     ctx->last.launches = 1;

@@ -136,10 +136,15 @@ __global__ void count_init_kernel(CountTable t, int key64) {
 template <typename V>
 __global__ void __launch_bounds__(256) count_insert_seqs_kernel(SeqView b, uint64_t total_bytes, uint32_t k, int canonical,
                                                                  CountTable t) {
-    const uint64_t nchunks = (total_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES;
+    const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     bool ok = true;
-    for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < nchunks; c += (uint64_t)gridDim.x * blockDim.x)
-        for_each_kmer_in_chunk<V, false>(b, total_bytes, c, k, canonical != 0, [&](V key) { ok &= CountOps<V>::insert(t, key, 1u); });
+    for (uint64_t g = warp; g < ngroups; g += nwarps)
+        warp_for_each_kmer<V>(b, total_bytes, g, k, canonical != 0, lane, [&](V key, bool active) {
+            if (active) ok &= CountOps<V>::insert(t, key, 1u);
+        });
     if (!ok) *t.overflow = 1ULL;
 }
 
@@ -235,17 +240,21 @@ __global__ void __launch_bounds__(256) count_partition_kernel(SeqView b, uint64_
     for (int p = threadIdx.x; p < MAX_PARTS; p += blockDim.x)
         cur[p] = (WRITE && (uint32_t)p < nparts) ? block_counts[(size_t)p * gridDim.x + blockIdx.x] : 0ULL;
     __syncthreads();
-    const uint64_t nchunks = (total_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES;
-    // a block owns contiguous tiles of blockDim.x chunks so that both walks see the same k-mers
-    for (uint64_t tile = blockIdx.x; tile * blockDim.x < nchunks; tile += gridDim.x) {
-        const uint64_t c = tile * blockDim.x + threadIdx.x;
-        if (c < nchunks)
-            for_each_kmer_in_chunk<V, false>(b, total_bytes, c, k, canonical != 0, [&](V key) {
-                const uint32_t p = owner_of<V>(key, nparts);
-                const unsigned long long pos = atomicAdd(&cur[p], 1ULL);
-                if (WRITE) out[pos] = key;
-            });
-    }
+    const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
+    const int lane = threadIdx.x & 31;
+    const uint32_t wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    // a block owns the groups blockIdx.x * wpb + wib + j * gridDim.x * wpb in both walks: same k-mers, same block
+    for (uint64_t g = (uint64_t)blockIdx.x * wpb + wib; g < ngroups; g += (uint64_t)gridDim.x * wpb)
+        warp_for_each_kmer<V>(b, total_bytes, g, k, canonical != 0, lane, [&](V key, bool active) {
+            // lanes going to the same owner reserve their output positions with one shared-memory atomic
+            const uint32_t p = active ? owner_of<V>(key, nparts) : 0xFFFFFFFFu;
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, p);
+            const int leader = __ffs(peers) - 1;
+            unsigned long long base = 0;
+            if (active && lane == leader) base = atomicAdd(&cur[p], (unsigned long long)__popc(peers));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (WRITE && active) out[base + __popc(peers & ((1u << lane) - 1))] = key;
+        });
     if (!WRITE) {
         __syncthreads();
         for (int p = threadIdx.x; p < (int)nparts; p += blockDim.x) block_counts[(size_t)p * gridDim.x + blockIdx.x] = cur[p];
@@ -291,8 +300,8 @@ cudaError_t launch_count_init(const CountTable& t, bool key64, int sm_count, cud
 cudaError_t launch_count_insert_seqs(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
                                      const CountTable& t, int sm_count, cudaStream_t st) {
     if (b.nseq == 0 || total_bytes == 0) return cudaSuccess;
-    const uint64_t nchunks = (total_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES;
-    const int grid = grid_for(nchunks, 256, sm_count, 8);
+    const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
+    const int grid = grid_for(ngroups * 32, 256, sm_count, 8);
     if (key64) count_insert_seqs_kernel<uint64_t><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, t);
     else count_insert_seqs_kernel<uint32_t><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, t);
     return cudaGetLastError();
@@ -332,8 +341,8 @@ cudaError_t launch_count_export(const CountTable& t, bool key64, uint32_t min_co
 }
 
 int count_partition_grid(uint64_t total_bytes, int sm_count) {
-    const uint64_t nchunks = (total_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES;
-    return grid_for(nchunks, 256, sm_count, 4);
+    const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
+    return grid_for(ngroups * 32, 256, sm_count, 4);
 }
 
 cudaError_t launch_count_partition(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,

@@ -471,4 +471,63 @@ __device__ __forceinline__ void for_each_kmer_in_chunk(const SeqView& b, uint64_
     }
 }
 
+// ----------------------------------------------------------------------------
+//  Direct k-mer read: the forward value of the k-mer starting at base p, straight from the packed
+//  words (two or three big-endian words re-aligned with funnel shifts) -- no rolling state, so the
+//  32 lanes of a warp can take 32 consecutive positions.
+// ----------------------------------------------------------------------------
+template <typename V>
+__device__ __forceinline__ V kmer_at(const uint32_t* __restrict__ words, uint64_t p, uint32_t k);
+template <>
+__device__ __forceinline__ uint32_t kmer_at<uint32_t>(const uint32_t* __restrict__ words, uint64_t p, uint32_t k) {
+    const uint32_t* w = words + (p >> 4);
+    const uint32_t sh = (uint32_t)(p & 15) * 2;
+    const uint32_t x = __funnelshift_l(be32(__ldg(w + 1)), be32(__ldg(w)), sh);  // 16 bases from p (k <= 16)
+    return x >> (32 - 2 * k);
+}
+template <>
+__device__ __forceinline__ uint64_t kmer_at<uint64_t>(const uint32_t* __restrict__ words, uint64_t p, uint32_t k) {
+    const uint32_t* w = words + (p >> 4);
+    const uint32_t sh = (uint32_t)(p & 15) * 2;
+    const uint32_t a = be32(__ldg(w)), b = be32(__ldg(w + 1)), c = be32(__ldg(w + 2));
+    const uint64_t x = ((uint64_t)__funnelshift_l(b, a, sh) << 32) | __funnelshift_l(c, b, sh);  // 32 bases from p
+    return x >> (64 - 2 * k);
+}
+
+// Warp-cooperative traversal of a whole batch: the byte buffer is cut into groups of 2 KB; a warp
+// owns the k-mers that START in its group and hands 32 consecutive positions at a time to its lanes.
+// f(pre-key, active) is called with all 32 lanes converged (inactive lanes: active == false).
+constexpr uint32_t GROUP_BYTES = 2048;
+
+template <typename V, typename F>
+__device__ __forceinline__ void warp_for_each_kmer(const SeqView& b, uint64_t total_bytes, uint64_t group, uint32_t k,
+                                                   bool canonical, int lane, F&& f) {
+    const uint64_t byte0 = group * GROUP_BYTES;
+    const uint64_t byte1 = min(byte0 + (uint64_t)GROUP_BYTES, total_bytes);
+    uint64_t s = seq_of_byte(b.byte_off, b.nseq, byte0);
+    while (s < b.nseq) {
+        const uint64_t sb = __ldg(b.byte_off + s);
+        if (sb >= byte1) break;
+        const uint64_t L = __ldg(b.nbases + s);
+        const uint64_t nk = L >= k ? L - k + 1 : 0;
+        const uint64_t p_lo = byte0 > sb ? (byte0 - sb) * 4 : 0;
+        const uint64_t p_hi = min(nk, (byte1 - sb) * 4);
+        const uint32_t* words = (const uint32_t*)(b.packed + sb);
+        for (uint64_t p0 = p_lo; p0 < p_hi; p0 += 32) {
+            const uint64_t p = p0 + lane;
+            const bool active = p < p_hi;
+            V key = 0;
+            if (active) {
+                key = kmer_at<V>(words, p, k);
+                if (canonical) {
+                    const V rc = revcomp_val(key, k);
+                    key = key < rc ? key : rc;
+                }
+            }
+            f(key, active);
+        }
+        ++s;
+    }
+}
+
 }  // namespace kmu

@@ -84,8 +84,53 @@ __global__ void __launch_bounds__(256) generate_kmers_kernel(SeqView b, uint32_t
     }
 }
 
-cudaError_t launch_generate_kmers(const SeqView& b, uint32_t k, int kmer_type, int hash_kind, const uint64_t* out_off,
-                                  void* out, cudaStream_t stream) {
+// DNA batches: warp-cooperative version.  A warp owns the k-mers starting in one 2 KB group of the packed
+// buffer; lane l takes positions p0 + l, p0 + l + 32, ... read straight from the packed words (kmer_at), so every
+// store instruction of the warp writes one contiguous run of 32 values.
+template <typename V, int U>
+__global__ void __launch_bounds__(256) generate_kmers_warp_kernel(SeqView b, uint64_t total_bytes, uint32_t k, int kmer_type,
+                                                                   int hash_kind, const uint64_t* __restrict__ out_off,
+                                                                   V* __restrict__ out) {
+    const V header = (V)word_header(kmer_type, k);
+    const bool canonical = hash_is_canonical(hash_kind);
+    const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t g = warp; g < ngroups; g += nwarps) {
+        const uint64_t byte0 = g * GROUP_BYTES;
+        const uint64_t byte1 = min(byte0 + (uint64_t)GROUP_BYTES, total_bytes);
+        uint64_t s = seq_of_byte(b.byte_off, b.nseq, byte0);
+        while (s < b.nseq) {
+            const uint64_t sb = __ldg(b.byte_off + s);
+            if (sb >= byte1) break;
+            const uint64_t L = __ldg(b.nbases + s);
+            const uint64_t nk = L >= k ? L - k + 1 : 0;
+            const uint64_t p_lo = byte0 > sb ? (byte0 - sb) * 4 : 0;
+            const uint64_t p_hi = min(nk, (byte1 - sb) * 4);
+            const uint32_t* words = (const uint32_t*)(b.packed + sb);
+            V* o = out + __ldg(out_off + s);
+            for (uint64_t p0 = p_lo; p0 < p_hi; p0 += 32 * U) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint64_t p = p0 + lane + 32 * u;
+                    if (p < p_hi) {
+                        V key = kmer_at<V>(words, p, k);
+                        if (canonical) {
+                            const V rc = revcomp_val(key, k);
+                            key = key < rc ? key : rc;
+                        }
+                        o[p] = finalize_key<V>(key, header, hash_kind);
+                    }
+                }
+            }
+            ++s;
+        }
+    }
+}
+
+cudaError_t launch_generate_kmers(const SeqView& b, uint64_t total_bytes, uint32_t k, int kmer_type, int hash_kind,
+                                  const uint64_t* out_off, void* out, cudaStream_t stream) {
     if (b.nseq == 0) return cudaSuccess;
     const int block = 256;
     const int grid = 148 * 8;
@@ -94,9 +139,9 @@ cudaError_t launch_generate_kmers(const SeqView& b, uint32_t k, int kmer_type, i
     else if (kmer_type == KMU_KMERAA32)
         generate_kmers_kernel<uint32_t, 8, true><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint32_t*)out);
     else if (kmer_type == KMU_KMER64)
-        generate_kmers_kernel<uint64_t, 8, false><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint64_t*)out);
+        generate_kmers_warp_kernel<uint64_t, 4><<<grid, block, 0, stream>>>(b, total_bytes, k, kmer_type, hash_kind, out_off, (uint64_t*)out);
     else
-        generate_kmers_kernel<uint32_t, 8, false><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint32_t*)out);
+        generate_kmers_warp_kernel<uint32_t, 4><<<grid, block, 0, stream>>>(b, total_bytes, k, kmer_type, hash_kind, out_off, (uint32_t*)out);
     return cudaGetLastError();
 }
 

@@ -117,8 +117,8 @@ inline uint64_t len_bucket_min_nk(int bucket) {
 // ---- k-mer generation / ntHash (kmu_extract.cu) -----------------------------------------
 cudaError_t launch_kmer_offsets(const uint64_t* nbases, uint64_t nseq, uint32_t k, uint64_t* out_off,
                                 cudaStream_t stream);
-cudaError_t launch_generate_kmers(const SeqView& b, uint32_t k, int kmer_type, int hash_kind, const uint64_t* out_off,
-                                  void* out, cudaStream_t stream);
+cudaError_t launch_generate_kmers(const SeqView& b, uint64_t total_bytes, uint32_t k, int kmer_type, int hash_kind,
+                                  const uint64_t* out_off, void* out, cudaStream_t stream);
 cudaError_t launch_nthash(const SeqView& b, uint32_t k, uint32_t n_multi, const uint64_t* out_off, uint64_t* out_hash,
                           uint8_t* out_strand, cudaStream_t stream);
 
