@@ -243,8 +243,19 @@ def main():
         # algorithmic bytes of one launch: packed bases in (0.25 B/base) + signatures out (m * 4 B/read)
         alg_bytes = dom["nbases"] * 0.25 + dom["nseq"] * M * 4
         achieved = alg_bytes / (dom["ms"] * 1e-3) / 1e9
+        # DRAM traffic of the same launch from the committed ncu --set full capture (profiles/r1_traffic.json);
+        # only quoted when the capture is of the launch measured here (same reads and bases)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tr = json.load(f)
+            if tr["launch_reads"] == dom["nseq"] and tr["launch_bases"] == dom["nbases"]:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_kind": peak_kind,
+                    "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)",
+                    "algorithmic_bytes": alg_bytes, "peak_kind": peak_kind,
                     "kernel": "pmh3a_sketch_kernel<u32,%s> team_warps=%d" % ("hist" if dom["mode"] == 0 else "table", dom["team_warps"]),
                     "launch_ms": dom["ms"], "launch_bases": dom["nbases"], "launch_reads": dom["nseq"],
                     "share_of_step": dom["ms"] / max(sum(r["ms"] for r in prof), 1e-9),
@@ -282,7 +293,8 @@ def main():
         e2e = {"value": total_bases * world / e2e_s / 1e9, "unit": "Gbases/s",
                "h2d_bytes_per_step": int(tm["h2d_bytes"]), "d2h_bytes_per_step": int(tm["d2h_bytes"]),
                "ms_per_step": e2e_s * 1e3, "steps": n_e2e,
-               "h2d_ms": tm["h2d_ms"], "kernel_ms": tm["kernel_ms"], "d2h_ms": tm["d2h_ms"]}
+               "h2d_ms": tm["h2d_ms"], "kernel_ms": tm["kernel_ms"], "d2h_ms": tm["d2h_ms"], "host_ms": tm["host_ms"],
+               "api": "kmu_sketch_pmh3a_host (pinned host buffers, 3-stream chunked pipeline)"}
         # the signatures the host got must be the ones left in HBM by the device-resident path
         if not torch.equal(pin_out, sig_dev.cpu()):
             raise SystemExit("e2e signatures differ from the device-resident run")
