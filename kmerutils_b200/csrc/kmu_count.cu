@@ -225,20 +225,24 @@ __global__ void __launch_bounds__(256) count_export_kernel(CountTable t, uint32_
 // owner = intNN_hash(compressed canonical value) % nparts.  Two walks: (A) every block counts its
 // k-mers per owner into block_counts[part][block]; an exclusive scan of that matrix (part major)
 // gives every block its private output ranges; (B) the block recomputes the keys and writes them.
-constexpr int MAX_PARTS = 64;
+constexpr int MAX_PARTS = 4096;
 
-template <typename V>
-__device__ __forceinline__ uint32_t owner_of(V key, uint32_t nparts) {
-    return (uint32_t)(inv_hash(key) % (V)nparts);
+// PMODE 0: owner = DispatchableT::dispatch = intNN_hash(value) % nparts (multi-GPU exchange)
+// PMODE 1: bucket = region of the counting table the key hashes to: (fmix64(key) & capmask) >> shift
+//          (two-phase insertion: k-mers are grouped by table region so that the inserts of a region hit L2)
+template <typename V, int PMODE>
+__device__ __forceinline__ uint32_t part_of(V key, uint32_t nparts, uint64_t capmask, uint32_t shift) {
+    if (PMODE == 0) return (uint32_t)(inv_hash(key) % (V)nparts);
+    return (uint32_t)((fmix64((uint64_t)key) & capmask) >> shift);
 }
 
-template <typename V, bool WRITE>
+template <typename V, bool WRITE, int PMODE>
 __global__ void __launch_bounds__(256) count_partition_kernel(SeqView b, uint64_t total_bytes, uint32_t k, int canonical,
-                                                               uint32_t nparts, unsigned long long* block_counts,
-                                                               V* __restrict__ out) {
-    __shared__ unsigned long long cur[MAX_PARTS];
-    for (int p = threadIdx.x; p < MAX_PARTS; p += blockDim.x)
-        cur[p] = (WRITE && (uint32_t)p < nparts) ? block_counts[(size_t)p * gridDim.x + blockIdx.x] : 0ULL;
+                                                               uint32_t nparts, uint64_t capmask, uint32_t shift,
+                                                               unsigned long long* block_counts, V* __restrict__ out) {
+    extern __shared__ unsigned long long cur[];  // nparts cursors
+    for (uint32_t p = threadIdx.x; p < nparts; p += blockDim.x)
+        cur[p] = WRITE ? block_counts[(size_t)p * gridDim.x + blockIdx.x] : 0ULL;
     __syncthreads();
     const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
     const int lane = threadIdx.x & 31;
@@ -246,8 +250,8 @@ __global__ void __launch_bounds__(256) count_partition_kernel(SeqView b, uint64_
     // a block owns the groups blockIdx.x * wpb + wib + j * gridDim.x * wpb in both walks: same k-mers, same block
     for (uint64_t g = (uint64_t)blockIdx.x * wpb + wib; g < ngroups; g += (uint64_t)gridDim.x * wpb)
         warp_for_each_kmer<V>(b, total_bytes, g, k, canonical != 0, lane, [&](V key, bool active) {
-            // lanes going to the same owner reserve their output positions with one shared-memory atomic
-            const uint32_t p = active ? owner_of<V>(key, nparts) : 0xFFFFFFFFu;
+            // lanes going to the same part reserve their output positions with one shared-memory atomic
+            const uint32_t p = active ? part_of<V, PMODE>(key, nparts, capmask, shift) : 0xFFFFFFFFu;
             const uint32_t peers = __match_any_sync(0xFFFFFFFFu, p);
             const int leader = __ffs(peers) - 1;
             unsigned long long base = 0;
@@ -257,31 +261,37 @@ __global__ void __launch_bounds__(256) count_partition_kernel(SeqView b, uint64_
         });
     if (!WRITE) {
         __syncthreads();
-        for (int p = threadIdx.x; p < (int)nparts; p += blockDim.x) block_counts[(size_t)p * gridDim.x + blockIdx.x] = cur[p];
+        for (uint32_t p = threadIdx.x; p < nparts; p += blockDim.x) block_counts[(size_t)p * gridDim.x + blockIdx.x] = cur[p];
     }
 }
 
-// exclusive scan of block_counts (nparts * nblocks entries, part major) in place; part_totals[p] = sum of part p
-__global__ void count_partition_scan_kernel(unsigned long long* block_counts, uint32_t nparts, uint32_t nblocks,
-                                            unsigned long long* part_totals) {
-    // one thread per part computes its row sum, then thread 0 chains the parts (nparts <= 64, nblocks ~ 1e3)
-    __shared__ unsigned long long tot[MAX_PARTS];
-    const uint32_t p = threadIdx.x;
-    if (p < nparts) {
-        unsigned long long s = 0;
-        for (uint32_t j = 0; j < nblocks; ++j) s += block_counts[(size_t)p * nblocks + j];
-        tot[p] = s;
-        part_totals[p] = s;
-    }
-    __syncthreads();
-    if (p < nparts) {
-        unsigned long long base = 0;
-        for (uint32_t q = 0; q < p; ++q) base += tot[q];
-        for (uint32_t j = 0; j < nblocks; ++j) {
-            unsigned long long v = block_counts[(size_t)p * nblocks + j];
-            block_counts[(size_t)p * nblocks + j] = base;
-            base += v;
+// block_counts (nparts * nblocks entries, part major) -> exclusive offsets, in three steps
+__global__ void count_partition_rowsum_kernel(const unsigned long long* block_counts, uint32_t nparts, uint32_t nblocks,
+                                              unsigned long long* part_totals) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nparts) return;
+    unsigned long long s = 0;
+    for (uint32_t j = 0; j < nblocks; ++j) s += block_counts[(size_t)p * nblocks + j];
+    part_totals[p] = s;
+}
+__global__ void count_partition_base_kernel(const unsigned long long* part_totals, uint32_t nparts, unsigned long long* part_base) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (uint32_t p = 0; p < nparts; ++p) {
+            part_base[p] = acc;
+            acc += part_totals[p];
         }
+    }
+}
+__global__ void count_partition_offsets_kernel(unsigned long long* block_counts, uint32_t nparts, uint32_t nblocks,
+                                               const unsigned long long* part_base) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nparts) return;
+    unsigned long long base = part_base[p];
+    for (uint32_t j = 0; j < nblocks; ++j) {
+        const unsigned long long v = block_counts[(size_t)p * nblocks + j];
+        block_counts[(size_t)p * nblocks + j] = base;
+        base += v;
     }
 }
 
@@ -345,19 +355,38 @@ int count_partition_grid(uint64_t total_bytes, int sm_count) {
     return grid_for(ngroups * 32, 256, sm_count, 4);
 }
 
+template <typename V, int PMODE>
+static cudaError_t launch_partition_t(const SeqView& b, uint64_t total_bytes, uint32_t k, bool canonical, uint32_t nparts,
+                                      uint64_t capmask, uint32_t shift, int grid, unsigned long long* block_counts,
+                                      unsigned long long* part_totals, void* out, cudaStream_t st) {
+    const size_t smem = sizeof(unsigned long long) * nparts;
+    unsigned long long* part_base = part_totals + nparts;
+    count_partition_kernel<V, false, PMODE><<<grid, 256, smem, st>>>(b, total_bytes, k, canonical, nparts, capmask, shift,
+                                                                      block_counts, nullptr);
+    count_partition_rowsum_kernel<<<(nparts + 127) / 128, 128, 0, st>>>(block_counts, nparts, (uint32_t)grid, part_totals);
+    count_partition_base_kernel<<<1, 32, 0, st>>>(part_totals, nparts, part_base);
+    count_partition_offsets_kernel<<<(nparts + 127) / 128, 128, 0, st>>>(block_counts, nparts, (uint32_t)grid, part_base);
+    count_partition_kernel<V, true, PMODE><<<grid, 256, smem, st>>>(b, total_bytes, k, canonical, nparts, capmask, shift,
+                                                                     block_counts, (V*)out);
+    return cudaGetLastError();
+}
+
+// block_counts: nparts * grid entries (scratch); part_totals: 2 * nparts entries (totals, then scratch); out: all k-mers, part major
 cudaError_t launch_count_partition(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
                                    uint32_t nparts, int grid, unsigned long long* block_counts,
                                    unsigned long long* part_totals, void* out, cudaStream_t st) {
-    if (key64) {
-        count_partition_kernel<uint64_t, false><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, nparts, block_counts, nullptr);
-        count_partition_scan_kernel<<<1, MAX_PARTS, 0, st>>>(block_counts, nparts, (uint32_t)grid, part_totals);
-        count_partition_kernel<uint64_t, true><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, nparts, block_counts, (uint64_t*)out);
-    } else {
-        count_partition_kernel<uint32_t, false><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, nparts, block_counts, nullptr);
-        count_partition_scan_kernel<<<1, MAX_PARTS, 0, st>>>(block_counts, nparts, (uint32_t)grid, part_totals);
-        count_partition_kernel<uint32_t, true><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, nparts, block_counts, (uint32_t*)out);
-    }
-    return cudaGetLastError();
+    if (key64) return launch_partition_t<uint64_t, 0>(b, total_bytes, k, canonical, nparts, 0, 0, grid, block_counts, part_totals, out, st);
+    return launch_partition_t<uint32_t, 0>(b, total_bytes, k, canonical, nparts, 0, 0, grid, block_counts, part_totals, out, st);
+}
+
+// two-phase insertion: group the k-mers of the batch by table region (nparts = regions, a power of two)
+cudaError_t launch_count_partition_by_region(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
+                                             const CountTable& t, uint32_t nparts, int grid, unsigned long long* block_counts,
+                                             unsigned long long* part_totals, void* out, cudaStream_t st) {
+    uint32_t shift = 0;
+    while (((t.capmask + 1) >> shift) > nparts) ++shift;
+    if (key64) return launch_partition_t<uint64_t, 1>(b, total_bytes, k, canonical, nparts, t.capmask, shift, grid, block_counts, part_totals, out, st);
+    return launch_partition_t<uint32_t, 1>(b, total_bytes, k, canonical, nparts, t.capmask, shift, grid, block_counts, part_totals, out, st);
 }
 
 }  // namespace kmu

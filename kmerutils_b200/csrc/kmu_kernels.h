@@ -224,9 +224,12 @@ cudaError_t launch_count_stats(const CountTable& t, bool key64, unsigned long lo
 cudaError_t launch_count_export(const CountTable& t, bool key64, uint32_t min_count, void* keys, uint32_t* counts,
                                 unsigned long long* cursor, uint64_t cap, int sm_count, cudaStream_t st);
 int count_partition_grid(uint64_t total_bytes, int sm_count);
-// block_counts: nparts * grid entries (scratch); part_totals: nparts entries; out: all k-mers, part major
+// block_counts: nparts * grid entries (scratch); part_totals: 2 * nparts entries; out: all k-mers, part major
 cudaError_t launch_count_partition(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
                                    uint32_t nparts, int grid, unsigned long long* block_counts,
                                    unsigned long long* part_totals, void* out, cudaStream_t st);
+cudaError_t launch_count_partition_by_region(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
+                                             const CountTable& t, uint32_t nparts, int grid, unsigned long long* block_counts,
+                                             unsigned long long* part_totals, void* out, cudaStream_t st);
 
 }  // namespace kmu
