@@ -202,6 +202,14 @@ int32_t kmu_sketch_setsketch(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k
                              const kmu_setsketch_params* params, int32_t sig_bytes, int32_t whole, void* sig,
                              int32_t sig_on_device);
 
+/* ---- Jaccard estimates between signatures: out[i * nb + j] = #{s : a_i[s] == b_j[s]} / m
+ *      compute_probminhash_jaccard / probminhash_get_jaccard_objects (src/sketching/seqsketchjaccard.rs:86-108), the
+ *      comparison step of jaccard_index_probminhash3a (:423-495), SuperMinHash::get_jaccard_index_estimate, and the
+ *      DistHamming of datasketcher (src/bin/datasketcher.rs:179-185) as 1 - out.  slot_bytes 2 / 4 / 8; slots are
+ *      compared as bit patterns. */
+int32_t kmu_signature_jaccard(kmu_ctx* ctx, const void* sig_a, uint64_t na, const void* sig_b, uint64_t nb, uint32_t m,
+                              int32_t slot_bytes, double* out, int32_t on_device);
+
 /* ---- k-mer counting (replaces KmerCounter: cuckoo filter + counting Bloom filter,
  *      src/base/kmercount.rs:70-83) -------------------------------------------------------
  * One exact open-addressing table in HBM keyed by kmer.get_compressed_value().  Semantics are

@@ -674,7 +674,7 @@ int32_t kmu_nthash_canonical(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, ui
     }
     kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    CUDA_TRY(kmu::launch_nthash(v, k, n_multi, (const uint64_t*)ctx->misc.p, dh, ds, ctx->stream));
+    CUDA_TRY(kmu::launch_nthash(v, b->packed_bytes, k, n_multi, (const uint64_t*)ctx->misc.p, dh, ds, ctx->stream));
     cudaEventRecord(ctx->ev[1], ctx->stream);
     ctx->launches += 1;
     ctx->last.launches = 1;

@@ -160,66 +160,70 @@ __device__ __forceinline__ uint64_t nt_seed(uint32_t b) {
     return (b & 2) ? hi : lo;
 }
 
-template <int T>
-__global__ void __launch_bounds__(256) nthash_kernel(SeqView b, uint32_t k, uint32_t n_multi,
-                                                      const uint64_t* __restrict__ out_off, uint64_t* __restrict__ out_hash,
-                                                      uint8_t* __restrict__ out_strand) {
-    const uint64_t total = out_off[b.nseq];
+// warp-cooperative version: a warp owns the k-mers starting in one 2 KB group; every lane takes a run of
+// NT_RUN consecutive positions (one O(k) initialisation, then the O(1) ntHash recurrence)
+constexpr uint32_t NT_RUN = 32;
+__global__ void __launch_bounds__(256) nthash_warp_kernel(SeqView b, uint64_t total_bytes, uint32_t k, uint32_t n_multi,
+                                                           const uint64_t* __restrict__ out_off, uint64_t* __restrict__ out_hash,
+                                                           uint8_t* __restrict__ out_strand) {
     const uint64_t mult = (uint64_t)k * 0x90b45d39fb6da1faULL;  // nthash.rs:13,68 (wrapping)
-    for (uint64_t e0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * T; e0 < total;
-         e0 += (uint64_t)gridDim.x * blockDim.x * T) {
-        uint64_t s = seq_of_element(out_off, b.nseq, e0);
-        uint64_t s_end = out_off[s + 1];
-        KmerWalker<uint64_t> wk;
-        wk.start((const uint32_t*)(b.packed + b.byte_off[s]), e0 - out_off[s], k);
-        bool fresh = true;
-        uint64_t f = 0, r = 0;
-        for (int t = 0; t < T; ++t) {
-            uint64_t e = e0 + t;
-            if (e >= total) break;
-            if (e >= s_end) {
-                do {
-                    ++s;
-                    s_end = out_off[s + 1];
-                } while (e >= s_end);
-                wk.start((const uint32_t*)(b.packed + b.byte_off[s]), 0, k);
-                fresh = true;
-            }
-            uint32_t old_base = (uint32_t)(wk.fwd >> (2 * k - 2)) & 3u;  // leftmost base of the previous k-mer
-            wk.roll();
-            if (fresh) {
+    const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t g = warp; g < ngroups; g += nwarps) {
+        const uint64_t byte0 = g * GROUP_BYTES;
+        const uint64_t byte1 = min(byte0 + (uint64_t)GROUP_BYTES, total_bytes);
+        uint64_t s = seq_of_byte(b.byte_off, b.nseq, byte0);
+        while (s < b.nseq) {
+            const uint64_t sb = __ldg(b.byte_off + s);
+            if (sb >= byte1) break;
+            const uint64_t L = __ldg(b.nbases + s);
+            const uint64_t nk = L >= k ? L - k + 1 : 0;
+            const uint64_t p_lo = byte0 > sb ? (byte0 - sb) * 4 : 0;
+            const uint64_t p_hi = min(nk, (byte1 - sb) * 4);
+            const uint32_t* words = (const uint32_t*)(b.packed + sb);
+            const uint64_t obase = __ldg(out_off + s);
+            for (uint64_t p0 = p_lo + (uint64_t)lane * NT_RUN; p0 < p_hi; p0 += 32 * NT_RUN) {
+                const uint64_t pend = min(p0 + NT_RUN, p_hi);
+                KmerWalker<uint64_t> wk;
+                wk.start(words, p0, k);
+                wk.roll();
                 // nthash_canonical_init (kmer.rs:74-94)
-                f = 0;
-                r = 0;
+                uint64_t f = 0, r = 0;
                 for (uint32_t i = 0; i < k; ++i) {
-                    uint32_t base = (uint32_t)(wk.fwd >> (2 * (k - 1 - i))) & 3u;
+                    const uint32_t base = (uint32_t)(wk.fwd >> (2 * (k - 1 - i))) & 3u;
                     f ^= rotl_var(nt_seed(base), k - 1 - i);
                     r ^= rotl_var(nt_seed(3u - base), i);
                 }
-                fresh = false;
-            } else {
-                // ntHash recurrence: identical values to re-initialising on the new window
-                uint32_t nb = (uint32_t)wk.fwd & 3u;
-                f = rotl_var(f, 1) ^ rotl_var(nt_seed(old_base), k) ^ nt_seed(nb);
-                r = rotl_var(r, 63) ^ rotl_var(nt_seed(3u - old_base), 63) ^ rotl_var(nt_seed(3u - nb), k - 1);
+                for (uint64_t p = p0;;) {
+                    const uint64_t h0 = f <= r ? f : r;
+                    uint64_t* o = out_hash + (obase + p) * n_multi;
+                    o[0] = h0;
+                    for (uint32_t i = 1; i < n_multi; ++i) {
+                        uint64_t tmp = h0 * ((uint64_t)i ^ mult);
+                        tmp ^= tmp >> 27;
+                        o[i] = tmp;
+                    }
+                    if (out_strand) out_strand[obase + p] = f <= r ? 0 : 1;
+                    if (++p >= pend) break;
+                    // ntHash recurrence: identical values to re-initialising on the new window
+                    const uint32_t old_base = (uint32_t)(wk.fwd >> (2 * k - 2)) & 3u;
+                    wk.roll();
+                    const uint32_t nb = (uint32_t)wk.fwd & 3u;
+                    f = rotl_var(f, 1) ^ rotl_var(nt_seed(old_base), k) ^ nt_seed(nb);
+                    r = rotl_var(r, 63) ^ rotl_var(nt_seed(3u - old_base), 63) ^ rotl_var(nt_seed(3u - nb), k - 1);
+                }
             }
-            uint64_t h0 = f <= r ? f : r;
-            uint64_t* o = out_hash + e * n_multi;
-            o[0] = h0;
-            for (uint32_t i = 1; i < n_multi; ++i) {
-                uint64_t tmp = h0 * ((uint64_t)i ^ mult);
-                tmp ^= tmp >> 27;
-                o[i] = tmp;
-            }
-            if (out_strand) out_strand[e] = f <= r ? 0 : 1;
+            ++s;
         }
     }
 }
 
-cudaError_t launch_nthash(const SeqView& b, uint32_t k, uint32_t n_multi, const uint64_t* out_off, uint64_t* out_hash,
-                          uint8_t* out_strand, cudaStream_t stream) {
+cudaError_t launch_nthash(const SeqView& b, uint64_t total_bytes, uint32_t k, uint32_t n_multi, const uint64_t* out_off,
+                          uint64_t* out_hash, uint8_t* out_strand, cudaStream_t stream) {
     if (b.nseq == 0) return cudaSuccess;
-    nthash_kernel<8><<<148 * 8, 256, 0, stream>>>(b, k, n_multi, out_off, out_hash, out_strand);
+    nthash_warp_kernel<<<148 * 8, 256, 0, stream>>>(b, total_bytes, k, n_multi, out_off, out_hash, out_strand);
     return cudaGetLastError();
 }
 

@@ -119,8 +119,8 @@ cudaError_t launch_kmer_offsets(const uint64_t* nbases, uint64_t nseq, uint32_t 
                                 cudaStream_t stream);
 cudaError_t launch_generate_kmers(const SeqView& b, uint64_t total_bytes, uint32_t k, int kmer_type, int hash_kind,
                                   const uint64_t* out_off, void* out, cudaStream_t stream);
-cudaError_t launch_nthash(const SeqView& b, uint32_t k, uint32_t n_multi, const uint64_t* out_off, uint64_t* out_hash,
-                          uint8_t* out_strand, cudaStream_t stream);
+cudaError_t launch_nthash(const SeqView& b, uint64_t total_bytes, uint32_t k, uint32_t n_multi, const uint64_t* out_off,
+                          uint64_t* out_hash, uint8_t* out_strand, cudaStream_t stream);
 
 inline bool hash_kind_is_canonical_host(int hash_kind) { return hash_kind == 2 || hash_kind == 3; }  // KMU_HASH_CANON_*
 

@@ -322,6 +322,24 @@ class Engine:
                                              k, kmer_type, hash_kind, m, C.c_void_p(optr)))
         return out
 
+    def signature_jaccard(self, sig_a, sig_b):
+        """(na, nb) matrix of Jaccard estimates = fraction of equal slots (compute_probminhash_jaccard,
+        seqsketchjaccard.rs:86-108).  sig_a (na, m), sig_b (nb, m), same dtype (any 2 / 4 / 8 byte slot type)."""
+        a = np.ascontiguousarray(sig_a)
+        b = np.ascontiguousarray(sig_b)
+        if a.ndim != 2 or b.ndim != 2 or a.shape[1] != b.shape[1] or a.dtype != b.dtype:
+            raise ValueError("signatures must be 2-D arrays of one dtype and one sketch size")
+        out = np.zeros((a.shape[0], b.shape[0]), dtype=np.float64)
+        check(self.lib.kmu_signature_jaccard(self.ctx, _p(a), a.shape[0], _p(b), b.shape[0], a.shape[1], a.dtype.itemsize,
+                                             _p(out), 0))
+        return out
+
+    def jaccard_index_probminhash3a(self, batch_a, batch_b, k, kmer_type, hash_kind=HASH_CANON_INVHASH, m=200):
+        """SeqSketcher::jaccard_index_probminhash3a (seqsketchjaccard.rs:423-495) generalised to many-vs-many:
+        sketch both batches, compare.  -> (len(batch_a), len(batch_b)) f64"""
+        return self.signature_jaccard(self.sketch_pmh3a(batch_a, k, kmer_type, hash_kind, m),
+                                      self.sketch_pmh3a(batch_b, k, kmer_type, hash_kind, m))
+
     # ---- counting ---------------------------------------------------------------------------
     def counter(self, k, kmer_type, capacity, count_bits=8):
         return KmerCounter(self, k, kmer_type, capacity, count_bits)
