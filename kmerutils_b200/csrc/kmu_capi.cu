@@ -157,15 +157,20 @@ void kmu_ctx_destroy(kmu_ctx* c) {
     ScopedDevice sd(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto* b : {&c->order, &c->counters, &c->table_scratch, &c->slot_scratch, &c->overflow, &c->sig_dev, &c->misc, &c->memo,
-                    &c->whole_table, &c->items_slots})
+                    &c->whole_table, &c->items_slots, &c->counters_alt, &c->overflow_alt})
         b->release();
     c->pinned.release();
+    c->pinned_small.release();
+    for (auto& ev : c->phase_ev)
+        if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
         c->pipe.packed[i].release();
         c->pipe.meta[i].release();
         c->pipe.sig[i].release();
         c->pipe.stage[i].release();
         c->pipe.meta_host[i].release();
+        c->pipe.order[i].release();
+        c->pipe.cursor[i].release();
         for (cudaEvent_t ev : {c->pipe.in_begin[i], c->pipe.in_done[i], c->pipe.compute_done[i], c->pipe.out_begin[i],
                                c->pipe.out_done[i]})
             if (ev) cudaEventDestroy(ev);
@@ -830,7 +835,9 @@ extern "C" {
 // them and redo the sequences they flagged.  The host pipeline runs 1 and 2 apart so that it can
 // prepare the next chunk while the device works.
 static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type,
-                                   int32_t hash_kind, uint32_t m, void* d_sig, int phase = 0) {
+                                   int32_t hash_kind, uint32_t m, void* d_sig, int phase = 0, int scratch_set = 0) {
+    DevBuf& counters = scratch_set ? ctx->counters_alt : ctx->counters;
+    DevBuf& overflow = scratch_set ? ctx->overflow_alt : ctx->overflow;
     const bool key64 = kmer_type_is_u64(kmer_type);
     const bool aa = kmer_type_is_aa(kmer_type);
     const size_t vsz = key64 ? 8 : 4;
@@ -842,14 +849,14 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     // ---- order sequences longest first (8 buckets per octave of the k-mer count) -------
     // histogram and cursors come from the host copy of the lengths; the processing order is
     // built on the device once per (batch, k) and kept with the batch
-    CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256 + 8 * 128)));
-    unsigned long long* d_hist = (unsigned long long*)ctx->counters.p;
+    CUDA_TRY(counters.reserve(sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256 + 8 * 128)));
+    unsigned long long* d_hist = (unsigned long long*)counters.p;
     unsigned long long* d_cursor = d_hist + kmu::LEN_BUCKETS;
     unsigned long long* d_work = d_cursor + kmu::LEN_BUCKETS;  // 128 work counters
     unsigned long long* d_ovf_count = d_work + 128;
     unsigned long long* d_phase = d_work + 256;  // 8 per launch, profiling only
     if (phase != 2)
-        CUDA_TRY(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256 + 8 * 128), st));
+        CUDA_TRY(cudaMemsetAsync(counters.p, 0, sizeof(unsigned long long) * (2 * kmu::LEN_BUCKETS + 256 + 8 * 128), st));
     {
         int32_t orc = kmu_ensure_order(ctx, b, k, &launches);
         if (orc) return orc;
@@ -923,9 +930,9 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         P.e.c3 = (1.0 - std::exp(-lambda)) / lambda;
     }
     P.sig = d_sig;
-    CUDA_TRY(ctx->overflow.reserve(sizeof(uint32_t) * (nseq + 1)));
+    CUDA_TRY(overflow.reserve(sizeof(uint32_t) * (nseq + 1)));
     P.overflow_count = d_ovf_count;
-    P.overflow_list = (uint32_t*)ctx->overflow.p;
+    P.overflow_list = (uint32_t*)overflow.p;
     // first point of every possible pre-key when the key space is small (u32 key types, k <= 10):
     // built once per (k, type, hash, m) and kept in the context (16 B per key, L2 resident)
     P.memo_fast = nullptr;
@@ -1045,10 +1052,24 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     }
     // ---- sequences whose u8 histogram counters wrapped or whose speculative qmax bound failed:
     //      redo them with u32 table counters and without speculation ---------------------------
+    if (phase == 1) {
+        // the redo count travels to pinned host memory right behind the launches: phase 2 only waits for this
+        // chunk's event, not for whatever was enqueued on the stream afterwards
+        CUDA_TRY(ctx->pinned_small.reserve(64));
+        unsigned long long* h_novf = (unsigned long long*)ctx->pinned_small.p + (scratch_set ? 1 : 0);
+        CUDA_TRY(cudaMemcpyAsync(h_novf, d_ovf_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        if (!ctx->phase_ev[scratch_set]) CUDA_TRY(cudaEventCreateWithFlags(&ctx->phase_ev[scratch_set], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(ctx->phase_ev[scratch_set], st));
+    }
     if (phase != 1) {
         unsigned long long novf = 0;
-        CUDA_TRY(cudaMemcpyAsync(&novf, d_ovf_count, sizeof(novf), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        if (phase == 2) {
+            CUDA_TRY(cudaEventSynchronize(ctx->phase_ev[scratch_set]));
+            novf = ((unsigned long long*)ctx->pinned_small.p)[scratch_set ? 1 : 0];
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(&novf, d_ovf_count, sizeof(novf), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
         if (novf) {
             LaunchClass c{};
             c.first = 0;
@@ -1056,7 +1077,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
             c.nk_max = nk_longest;
             c.mode = 1;
             c.table_global = true;
-            int32_t rc = run_class(c, (const uint32_t*)ctx->overflow.p, 127, false);
+            int32_t rc = run_class(c, (const uint32_t*)overflow.p, 127, false);
             if (rc) return rc;
         }
     }
@@ -1134,6 +1155,12 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);
     const auto t_begin = std::chrono::steady_clock::now();
+    const bool trace = std::getenv("KMU_TRACE") != nullptr;
+    auto stamp = [&](const char* what, size_t c) {
+        if (trace)
+            std::fprintf(stderr, "[kmu host pipe] %8.3f ms  %s %zu\n",
+                         std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), what, c);
+    };
     ctx->last = kmu_times{};
     HostPipe& hp = ctx->pipe;
     if (!hp.copy_in) {
@@ -1184,6 +1211,10 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
         if (e == cudaSuccess) e = hp.meta[sl].reserve(2 * sizeof(uint64_t) * (max_seqs + 1));
         if (e == cudaSuccess) e = hp.sig[sl].reserve(max_seqs * m * vsz);
         if (e == cudaSuccess) e = hp.meta_host[sl].reserve(2 * sizeof(uint64_t) * (max_seqs + 1));
+        // the processing order of a chunk lives in pipeline-owned buffers: no cudaMalloc (a device-wide
+        // synchronisation) between chunks
+        if (e == cudaSuccess) e = hp.order[sl].reserve(sizeof(uint32_t) * (max_seqs + 1));
+        if (e == cudaSuccess) e = hp.cursor[sl].reserve(sizeof(unsigned long long) * kmu::LEN_BUCKETS);
         if (e == cudaSuccess && !same_layout) e = hp.stage[sl].reserve(max_bytes);
         if (e != cudaSuccess) return fail(KMU_ENOMEM, "host pipeline buffers: %s", cudaGetErrorString(e));
     }
@@ -1207,6 +1238,8 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
         v.nbases = (uint64_t*)hp.meta[sl].p + (max_seqs + 1);
         v.nseq = n;
         v.packed_bytes = b1 - b0;
+        v.order_cache.order = hp.order[sl];  // borrowed: handed back when the chunk is done
+        v.order_cache.cursor_dev = hp.cursor[sl];
         v.h_nbases.assign(nbases + s0, nbases + s1);
         v.h_byte_off.resize(n);
         for (uint64_t i = 0; i < n; ++i) {
@@ -1215,7 +1248,8 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
         }
         // the slot's previous occupant (chunk c-2) must have been sketched and its copies harvested
         if (c >= 2) {
-            CUDA_TRY(cudaEventSynchronize(hp.compute_done[sl]));
+            // chunk c - 2 (same slot) has been sketched; its redo launch may still be running: the copy waits for it
+            CUDA_TRY(cudaStreamWaitEvent(hp.copy_in, hp.compute_done[sl], 0));
             harvest(sl);
         }
         uint64_t* mh = (uint64_t*)hp.meta_host[sl].p;
@@ -1235,21 +1269,37 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
         ctx->last.h2d_bytes += v.packed_bytes + 2 * sizeof(uint64_t) * n;
         return KMU_OK;
     };
+    stamp("layout done, chunks", nchunks);
     int32_t rc = upload(0);
+    stamp("upload enqueued", 0);
+    // Per chunk c: [phase 1] enqueue its sketch launches; meanwhile lay out + upload chunk c + 1 and build its
+    // processing order (host histogram + one scatter kernel queued behind chunk c); [phase 2] wait for chunk c, redo
+    // the sequences it flagged; start the download.  The gap between two chunks is the launch overhead only.
+    cudaEventRecord(ctx->ev[0], ctx->stream);
     for (size_t c = 0; c < nchunks && rc == KMU_OK; ++c) {
         const int sl = (int)(c & 1);
         CUDA_TRY(cudaStreamWaitEvent(ctx->stream, hp.in_done[sl], 0));
         if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, hp.out_done[sl], 0));  // signature slot free again
-        cudaEventRecord(ctx->ev[0], ctx->stream);
-        rc = sketch_pmh3a_locked(ctx, &views[c], k, kmer_type, hash_kind, m, hp.sig[sl].p, 1);
+        const int sset = sl;  // two sets of counters / redo lists: a chunk's redo launch may still run when the next chunk starts
+        rc = sketch_pmh3a_locked(ctx, &views[c], k, kmer_type, hash_kind, m, hp.sig[sl].p, 1, sset);
         if (rc) break;
-        // the device is busy with chunk c: lay out and upload chunk c + 1 meanwhile
-        if (c + 1 < nchunks) rc = upload(c + 1);
+        stamp("sketch enqueued", c);
+        if (c + 1 < nchunks) {
+            rc = upload(c + 1);
+            if (rc) break;
+            CUDA_TRY(cudaStreamWaitEvent(ctx->stream, hp.in_done[sl ^ 1], 0));
+            rc = kmu_ensure_order(ctx, &views[c + 1], k, nullptr);
+            if (rc) break;
+            stamp("next chunk uploaded + ordered", c + 1);
+        }
+        rc = sketch_pmh3a_locked(ctx, &views[c], k, kmer_type, hash_kind, m, hp.sig[sl].p, 2, sset);
+        stamp("sketch finished", c);
         if (rc) break;
-        rc = sketch_pmh3a_locked(ctx, &views[c], k, kmer_type, hash_kind, m, hp.sig[sl].p, 2);
-        cudaEventRecord(ctx->ev[1], ctx->stream);
+        hp.order[sl] = views[c].order_cache.order;
+        hp.cursor[sl] = views[c].order_cache.cursor_dev;
+        views[c].order_cache.order = DevBuf{};
+        views[c].order_cache.cursor_dev = DevBuf{};
         CUDA_TRY(cudaEventRecord(hp.compute_done[sl], ctx->stream));
-        if (rc) break;
         CUDA_TRY(cudaStreamWaitEvent(hp.copy_out, hp.compute_done[sl], 0));
         const size_t out_bytes = (size_t)views[c].nseq * m * vsz;
         CUDA_TRY(cudaEventRecord(hp.out_begin[sl], hp.copy_out));
@@ -1258,11 +1308,8 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
         CUDA_TRY(cudaEventRecord(hp.out_done[sl], hp.copy_out));
         timed_out[sl] = 1;
         ctx->last.d2h_bytes += out_bytes;
-        CUDA_TRY(cudaEventSynchronize(ctx->ev[1]));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-        ctx->last.kernel_ms += ms;
     }
+    cudaEventRecord(ctx->ev[1], ctx->stream);
     cudaError_t e1 = cudaStreamSynchronize(hp.copy_in);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     cudaError_t e3 = cudaStreamSynchronize(hp.copy_out);
@@ -1274,6 +1321,11 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
     }
     harvest(0);
     harvest(1);
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last.kernel_ms = ms;
+    }
+    stamp("all streams idle", 0);
     ctx->last.host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return KMU_OK;
 }

@@ -70,7 +70,7 @@ struct PinnedBuf {
 struct HostPipe {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t in_begin[2]{}, in_done[2]{}, compute_done[2]{}, out_begin[2]{}, out_done[2]{};
-    DevBuf packed[2], meta[2], sig[2];
+    DevBuf packed[2], meta[2], sig[2], order[2], cursor[2];
     PinnedBuf stage[2], meta_host[2];
 };
 
@@ -86,8 +86,10 @@ struct kmu_ctx {
     // scratch
     DevBuf order, counters, table_scratch, slot_scratch, overflow, sig_dev, misc;
     DevBuf whole_table, items_slots;  // whole-file ProbMinHash3a: counting table + global slots
+    DevBuf counters_alt, overflow_alt;  // second set of sketch counters / redo list (host pipeline: two chunks in flight)
     bool table_scratch_clean = false;
-    PinnedBuf pinned;
+    PinnedBuf pinned, pinned_small;
+    cudaEvent_t phase_ev[2]{};  // end of the main sketch launches of a chunk (host pipeline)
     // first-point table of the ProbMinHash3a kernels (small key spaces), see kmu_pmh3a.cu
     DevBuf memo;
     uint32_t memo_k = 0, memo_m = 0;

@@ -131,3 +131,29 @@ def test_host_pipeline(engine, oracle, chunk_bytes, ragged, monkeypatch):
     assert np.array_equal(out, want)
     t = engine.last_times()
     assert t["d2h_bytes"] == out.nbytes and t["h2d_bytes"] > 0 and t["host_ms"] > 0
+
+
+def test_host_pipeline_with_redo_sequences(engine, oracle, monkeypatch):
+    # sequences whose u8 histogram counters wrap are redone by a second launch per chunk: with several chunks in
+    # flight every chunk parity has its own counters / redo list
+    rng = np.random.default_rng(23)
+    seqs = []
+    for i in range(60):
+        if i % 7 == 3:
+            seqs.append(b"AC" * int(rng.integers(400, 3000)))  # one k-mer seen > 255 times
+        else:
+            seqs.append(oracle.synth_ascii(55, int(rng.integers(0, 1 << 20)), int(rng.integers(50, 4000))))
+    packed = [oracle.pack_2bit(s) for s in seqs]
+    nb = np.array([len(s) for s in seqs], dtype=np.uint64)
+    sizes = np.array([(len(p) + 15) // 16 * 16 for p in packed], dtype=np.uint64)
+    off = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+    buf = np.zeros(int(sizes.sum()) + 64, dtype=np.uint8)
+    for o, p in zip(off, packed):
+        buf[int(o): int(o) + len(p)] = p
+    want = oracle.sketch_pmh3a_batch(buf, off, nb, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200)
+    monkeypatch.setenv("KMU_HOST_CHUNK_BYTES", "3000")
+    out = np.zeros((len(nb), 200), dtype=np.uint32)
+    for _ in range(2):
+        out[:] = 0
+        engine.sketch_pmh3a_host(buf, off, nb, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200, out)
+        assert np.array_equal(out, want)
