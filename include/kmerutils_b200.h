@@ -171,6 +171,23 @@ int32_t kmu_sketch_pmh3a_whole(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t
 int32_t kmu_pmh3a_weighted(kmu_ctx* ctx, const void* keys, const double* weights, uint64_t n, int32_t key_bytes,
                            uint32_t m, void* sig);
 
+/* Peer-to-peer form of the exchange: ONE kernel extracts the canonical k-mers, buckets them by owner and stores
+ * every bucket straight into its owner's receive buffer -- a buffer of another GPU of the box mapped with CUDA IPC,
+ * so the stores cross NVLink from inside the kernel (no staging copy, no separate collective).
+ *   1. kmu_count_partition_counts : per-owner counts of this rank's k-mers;
+ *   2. the ranks share the counts (a few integers) and derive, for every destination, the offset of each sender's
+ *      bucket; receive buffers are allocated with kmu_ipc_alloc and opened on the senders with kmu_ipc_open;
+ *   3. kmu_count_partition_scatter : the same walk writes bucket p at dests[p] + dest_offsets[p] (elements);
+ *   4. after a barrier each rank feeds its receive buffer to kmu_count_insert_kmers. */
+int32_t kmu_count_partition_counts(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, int32_t kmer_type,
+                                   int32_t canonical, uint32_t nparts, uint64_t* part_counts);
+int32_t kmu_count_partition_scatter(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, int32_t kmer_type,
+                                    int32_t canonical, uint32_t nparts, void* const* dests, const uint64_t* dest_offsets);
+int32_t kmu_ipc_alloc(kmu_ctx* ctx, uint64_t bytes, void** dev_ptr, uint8_t handle[64]);
+int32_t kmu_ipc_free(kmu_ctx* ctx, void* dev_ptr);
+int32_t kmu_ipc_open(kmu_ctx* ctx, const uint8_t handle[64], void** peer_ptr);
+int32_t kmu_ipc_close(kmu_ctx* ctx, void* peer_ptr);
+
 /* ---- SuperMinHash per-sequence sketch
  *      SeqSketcher::sketch_superminhash          src/sketching/seqsketchjaccard.rs:328-380  (key_hasher FNV, :346-349)
  *      SuperHashSketch::sketch_compressedkmer    src/sketching/setsketchert.rs:255-296      (key_hasher NOHASH, :267-269)

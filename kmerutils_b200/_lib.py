@@ -111,6 +111,13 @@ SIGNATURES = {
     "kmu_sigdump_close": (C.c_int32, [C.c_void_p]),
     "kmu_sigdump_read": (C.c_int32, [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                      u64p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "kmu_count_partition_counts": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32, u64p]),
+    "kmu_count_partition_scatter": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32,
+                                                C.POINTER(C.c_void_p), u64p]),
+    "kmu_ipc_alloc": (C.c_int32, [C.c_void_p, C.c_uint64, vpp, C.c_void_p]),
+    "kmu_ipc_free": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "kmu_ipc_open": (C.c_int32, [C.c_void_p, C.c_void_p, vpp]),
+    "kmu_ipc_close": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "kmu_last_times": (C.c_int32, [C.c_void_p, C.POINTER(KmuTimes)]),
     "kmu_ctx_set_profiling": (C.c_int32, [C.c_void_p, C.c_int32]),
     "kmu_last_launch_profile": (C.c_uint32, [C.c_void_p, C.POINTER(KmuLaunchRec), C.c_uint32]),

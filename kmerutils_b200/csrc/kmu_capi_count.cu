@@ -311,6 +311,116 @@ int32_t kmu_count_partition(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int
     return KMU_OK;
 }
 
+// ---- peer-to-peer exchange: extraction + bucketing + NVLink stores in one kernel -------------------
+// Step 1: per-owner counts of this rank's k-mers (kept with the context for step 2).
+int32_t kmu_count_partition_counts(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t canonical,
+                                   uint32_t nparts, uint64_t* part_counts) {
+    if (!ctx || !b || !part_counts) return fail(KMU_EINVAL, "null argument");
+    if (kmer_type_is_aa(kmer_type) || b->alphabet != 0) return fail(KMU_EINVAL, "partitioning takes DNA k-mers");
+    if (!kmer_type_accepts(k, kmer_type))
+        return fail(KMU_EINVAL, "kmer size %u is not supported by kmer type %d", k, kmer_type);
+    if (nparts < 1 || nparts > 64) return fail(KMU_EINVAL, "nparts must be in 1..64, got %u", nparts);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    const bool key64 = kmer_type == KMU_KMER64;
+    const int grid = kmu::count_partition_grid(b->packed_bytes, ctx->sm_count);
+    CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * ((size_t)nparts * grid + 2 * nparts + 2 * 64 + 64)));
+    unsigned long long* block_counts = (unsigned long long*)ctx->counters.p;
+    unsigned long long* part_totals = block_counts + (size_t)nparts * grid;
+    kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
+    std::vector<unsigned long long> pt(nparts, 0);
+    if (b->nseq && b->packed_bytes) {
+        cudaEventRecord(ctx->ev[0], ctx->stream);
+        CUDA_TRY(kmu::launch_count_partition_counts(v, b->packed_bytes, k, key64, canonical != 0, nparts, grid, block_counts,
+                                                    part_totals, ctx->stream));
+        cudaEventRecord(ctx->ev[1], ctx->stream);
+        CUDA_TRY(cudaMemcpyAsync(pt.data(), part_totals, sizeof(unsigned long long) * nparts, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+        ctx->launches += 2;
+        ctx->last.launches = 2;
+    }
+    for (uint32_t p = 0; p < nparts; ++p) part_counts[p] = pt[p];
+    ctx->p2p_grid = grid;
+    ctx->p2p_nparts = nparts;
+    ctx->p2p_batch = b;
+    return KMU_OK;
+}
+
+// Step 2: the same walk writes bucket p at dests[p] + dest_offsets[p] (elements).  dests[p] is a device pointer of
+// this process: local memory or a peer GPU's buffer opened with kmu_ipc_open -- the stores then cross NVLink from
+// inside the kernel, no separate collective.  Must follow kmu_count_partition_counts on the same batch / k / nparts.
+int32_t kmu_count_partition_scatter(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t canonical,
+                                    uint32_t nparts, void* const* dests, const uint64_t* dest_offsets) {
+    if (!ctx || !b || !dests || !dest_offsets) return fail(KMU_EINVAL, "null argument");
+    if (ctx->p2p_batch != b || ctx->p2p_nparts != nparts || ctx->p2p_grid <= 0)
+        return fail(KMU_EINVAL, "kmu_count_partition_scatter must follow kmu_count_partition_counts on the same batch");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    const bool key64 = kmer_type == KMU_KMER64;
+    const int grid = ctx->p2p_grid;
+    unsigned long long* block_counts = (unsigned long long*)ctx->counters.p;
+    unsigned long long* part_base = block_counts + (size_t)nparts * grid + 2 * nparts;  // 64 entries
+    void** d_dests = (void**)(part_base + 64);                                          // 64 entries
+    std::vector<unsigned long long> base(dest_offsets, dest_offsets + nparts);
+    CUDA_TRY(cudaMemcpyAsync(part_base, base.data(), sizeof(unsigned long long) * nparts, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_dests, dests, sizeof(void*) * nparts, cudaMemcpyHostToDevice, ctx->stream));
+    kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
+    if (b->nseq && b->packed_bytes) {
+        cudaEventRecord(ctx->ev[0], ctx->stream);
+        CUDA_TRY(kmu::launch_count_partition_scatter(v, b->packed_bytes, k, key64, canonical != 0, nparts, grid, block_counts,
+                                                     part_base, d_dests, ctx->stream));
+        cudaEventRecord(ctx->ev[1], ctx->stream);
+        ctx->launches += 2;
+        ctx->last.launches = 2;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (b->nseq && b->packed_bytes) cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    ctx->p2p_batch = nullptr;
+    return KMU_OK;
+}
+
+// receive buffers shared between the processes of one box (CUDA IPC): export a buffer of this GPU ...
+int32_t kmu_ipc_alloc(kmu_ctx* ctx, uint64_t bytes, void** dev_ptr, uint8_t handle[64]) {
+    if (!ctx || !dev_ptr || !handle) return fail(KMU_EINVAL, "null argument");
+    ScopedDevice sd(ctx->device);
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 256));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(KMU_ECUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(handle, &h, 64);
+    *dev_ptr = p;
+    return KMU_OK;
+}
+int32_t kmu_ipc_free(kmu_ctx* ctx, void* dev_ptr) {
+    if (!ctx) return fail(KMU_EINVAL, "null argument");
+    ScopedDevice sd(ctx->device);
+    if (dev_ptr) CUDA_TRY(cudaFree(dev_ptr));
+    return KMU_OK;
+}
+// ... and map a peer's buffer into this process (the returned pointer is valid in this context's kernels)
+int32_t kmu_ipc_open(kmu_ctx* ctx, const uint8_t handle[64], void** peer_ptr) {
+    if (!ctx || !handle || !peer_ptr) return fail(KMU_EINVAL, "null argument");
+    ScopedDevice sd(ctx->device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return KMU_OK;
+}
+int32_t kmu_ipc_close(kmu_ctx* ctx, void* peer_ptr) {
+    if (!ctx) return fail(KMU_EINVAL, "null argument");
+    ScopedDevice sd(ctx->device);
+    if (peer_ptr) CUDA_TRY(cudaIpcCloseMemHandle(peer_ptr));
+    return KMU_OK;
+}
+
 // ---- ProbMinHash3a over a weighted set --------------------------------------------------------
 static void fill_exp01(kmu::Exp01Params& e, uint32_t m) {
     // ProbMinHash3a::new : lambda = ln(m / (m-1)); ExpRestricted01::new

@@ -236,10 +236,13 @@ __device__ __forceinline__ uint32_t part_of(V key, uint32_t nparts, uint64_t cap
     return (uint32_t)((fmix64((uint64_t)key) & capmask) >> shift);
 }
 
+// WRITE: bucket p is written at dests[p] + (offset kept in block_counts) when `dests` is given -- dests[p] may be
+// peer-GPU memory mapped over NVLink: extraction, bucketing and the exchange are then ONE kernel -- else at out + offset.
 template <typename V, bool WRITE, int PMODE>
 __global__ void __launch_bounds__(256) count_partition_kernel(SeqView b, uint64_t total_bytes, uint32_t k, int canonical,
                                                                uint32_t nparts, uint64_t capmask, uint32_t shift,
-                                                               unsigned long long* block_counts, V* __restrict__ out) {
+                                                               unsigned long long* block_counts, V* __restrict__ out,
+                                                               V* const* __restrict__ dests) {
     extern __shared__ unsigned long long cur[];  // nparts cursors
     for (uint32_t p = threadIdx.x; p < nparts; p += blockDim.x)
         cur[p] = WRITE ? block_counts[(size_t)p * gridDim.x + blockIdx.x] : 0ULL;
@@ -257,7 +260,10 @@ __global__ void __launch_bounds__(256) count_partition_kernel(SeqView b, uint64_
             unsigned long long base = 0;
             if (active && lane == leader) base = atomicAdd(&cur[p], (unsigned long long)__popc(peers));
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (WRITE && active) out[base + __popc(peers & ((1u << lane) - 1))] = key;
+            if (WRITE && active) {
+                V* o = dests ? dests[p] : out;
+                o[base + __popc(peers & ((1u << lane) - 1))] = key;
+            }
         });
     if (!WRITE) {
         __syncthreads();
@@ -362,12 +368,33 @@ static cudaError_t launch_partition_t(const SeqView& b, uint64_t total_bytes, ui
     const size_t smem = sizeof(unsigned long long) * nparts;
     unsigned long long* part_base = part_totals + nparts;
     count_partition_kernel<V, false, PMODE><<<grid, 256, smem, st>>>(b, total_bytes, k, canonical, nparts, capmask, shift,
-                                                                      block_counts, nullptr);
+                                                                      block_counts, nullptr, nullptr);
     count_partition_rowsum_kernel<<<(nparts + 127) / 128, 128, 0, st>>>(block_counts, nparts, (uint32_t)grid, part_totals);
     count_partition_base_kernel<<<1, 32, 0, st>>>(part_totals, nparts, part_base);
     count_partition_offsets_kernel<<<(nparts + 127) / 128, 128, 0, st>>>(block_counts, nparts, (uint32_t)grid, part_base);
     count_partition_kernel<V, true, PMODE><<<grid, 256, smem, st>>>(b, total_bytes, k, canonical, nparts, capmask, shift,
-                                                                     block_counts, (V*)out);
+                                                                     block_counts, (V*)out, nullptr);
+    return cudaGetLastError();
+}
+
+// the two halves apart (peer-to-peer exchange): (1) count per owner; the host turns the job-wide counts into the
+// offset of this rank's bucket inside every destination; (2) write every bucket at dests[p] + part_base[p]
+cudaError_t launch_count_partition_counts(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
+                                          uint32_t nparts, int grid, unsigned long long* block_counts,
+                                          unsigned long long* part_totals, cudaStream_t st) {
+    const size_t smem = sizeof(unsigned long long) * nparts;
+    if (key64) count_partition_kernel<uint64_t, false, 0><<<grid, 256, smem, st>>>(b, total_bytes, k, canonical, nparts, 0, 0, block_counts, nullptr, nullptr);
+    else count_partition_kernel<uint32_t, false, 0><<<grid, 256, smem, st>>>(b, total_bytes, k, canonical, nparts, 0, 0, block_counts, nullptr, nullptr);
+    count_partition_rowsum_kernel<<<(nparts + 127) / 128, 128, 0, st>>>(block_counts, nparts, (uint32_t)grid, part_totals);
+    return cudaGetLastError();
+}
+cudaError_t launch_count_partition_scatter(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
+                                           uint32_t nparts, int grid, unsigned long long* block_counts,
+                                           const unsigned long long* part_base, void* const* dests, cudaStream_t st) {
+    const size_t smem = sizeof(unsigned long long) * nparts;
+    count_partition_offsets_kernel<<<(nparts + 127) / 128, 128, 0, st>>>(block_counts, nparts, (uint32_t)grid, part_base);
+    if (key64) count_partition_kernel<uint64_t, true, 0><<<grid, 256, smem, st>>>(b, total_bytes, k, canonical, nparts, 0, 0, block_counts, nullptr, (uint64_t* const*)dests);
+    else count_partition_kernel<uint32_t, true, 0><<<grid, 256, smem, st>>>(b, total_bytes, k, canonical, nparts, 0, 0, block_counts, nullptr, (uint32_t* const*)dests);
     return cudaGetLastError();
 }
 

@@ -86,6 +86,9 @@ struct kmu_ctx {
     // scratch
     DevBuf order, counters, table_scratch, slot_scratch, overflow, sig_dev, misc;
     DevBuf whole_table, items_slots;  // whole-file ProbMinHash3a: counting table + global slots
+    int p2p_grid = 0;  // kmu_count_partition_counts -> _scatter hand-over
+    uint32_t p2p_nparts = 0;
+    const kmu_seqbatch* p2p_batch = nullptr;
     DevBuf counters_alt, overflow_alt;  // second set of sketch counters / redo list (host pipeline: two chunks in flight)
     bool table_scratch_clean = false;
     PinnedBuf pinned, pinned_small;

@@ -228,6 +228,12 @@ int count_partition_grid(uint64_t total_bytes, int sm_count);
 cudaError_t launch_count_partition(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
                                    uint32_t nparts, int grid, unsigned long long* block_counts,
                                    unsigned long long* part_totals, void* out, cudaStream_t st);
+cudaError_t launch_count_partition_counts(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
+                                          uint32_t nparts, int grid, unsigned long long* block_counts,
+                                          unsigned long long* part_totals, cudaStream_t st);
+cudaError_t launch_count_partition_scatter(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
+                                           uint32_t nparts, int grid, unsigned long long* block_counts,
+                                           const unsigned long long* part_base, void* const* dests, cudaStream_t st);
 cudaError_t launch_count_partition_by_region(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
                                              const CountTable& t, uint32_t nparts, int grid, unsigned long long* block_counts,
                                              unsigned long long* part_totals, void* out, cudaStream_t st);

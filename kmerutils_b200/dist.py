@@ -134,3 +134,91 @@ def query_sharded(engine, counter, kmers, kmer_type, group=None):
     t = torch.from_numpy(local).to(torch.device("cuda", engine.device))
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t.cpu().numpy().astype(np.uint32)
+
+
+class P2PExchange:
+    """Receive buffers of all ranks of one box, mapped into each other with CUDA IPC (grow-only).  The counting
+    exchange then needs no collective on the data path: every rank's partition kernel stores its buckets straight
+    into the owners' buffers over NVLink (`count_sharded_p2p`)."""
+
+    def __init__(self, engine, group=None):
+        self.engine = engine
+        self.group = group
+        self.rank, self.world = _world(group)
+        self.local_ptr, self.local_handle, self.local_bytes, self.generation = None, None, 0, 0
+        self.peer_ptrs = [None] * self.world
+        self.peer_gen = [-1] * self.world
+
+    def ensure(self, recv_bytes):
+        """Collective.  Makes this rank's receive buffer at least recv_bytes large and (re)maps every peer buffer that
+        changed.  -> list of `world` device pointers valid in this process (own buffer at index rank)."""
+        if self.local_ptr is None or recv_bytes > self.local_bytes:
+            if self.local_ptr is not None:
+                # peers still map the old buffer: they drop it below, after the barrier implied by the gather
+                old = self.local_ptr
+            else:
+                old = None
+            size = max(int(recv_bytes * 1.25), 1 << 20)
+            self.local_ptr, self.local_handle = self.engine.ipc_alloc(size)
+            self.local_bytes = size
+            self.generation += 1
+            self._old = old
+        else:
+            self._old = None
+        if self.world == 1:
+            if self._old is not None:
+                self.engine.ipc_free(self._old)
+            return [self.local_ptr]
+        info = [None] * self.world
+        dist.all_gather_object(info, (self.local_handle, self.generation), group=self.group)
+        for r, (handle, gen) in enumerate(info):
+            if r == self.rank:
+                self.peer_ptrs[r] = self.local_ptr
+                continue
+            if gen != self.peer_gen[r]:
+                if self.peer_ptrs[r] is not None:
+                    self.engine.ipc_close(self.peer_ptrs[r])
+                self.peer_ptrs[r] = self.engine.ipc_open(handle)
+                self.peer_gen[r] = gen
+        dist.barrier(group=self.group)  # every peer has dropped its mapping of a replaced buffer
+        if self._old is not None:
+            self.engine.ipc_free(self._old)
+        return list(self.peer_ptrs)
+
+    def close(self):
+        for r, p in enumerate(self.peer_ptrs):
+            if p is not None and r != self.rank:
+                self.engine.ipc_close(p)
+        self.peer_ptrs = [None] * self.world
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        if self.local_ptr is not None:
+            self.engine.ipc_free(self.local_ptr)
+            self.local_ptr = None
+
+
+def count_sharded_p2p(engine, batch, k, kmer_type, counter, xchg, canonical=True, group=None):
+    """One round of the counting exchange without a data-path collective: the partition kernel of every rank writes
+    its buckets directly into the owners' receive buffers (peer memory over NVLink), then every rank inserts what
+    landed in its buffer.  `counter` is this rank's table, `xchg` a P2PExchange.  -> number of k-mers received"""
+    import kmerutils_b200 as kb
+
+    rank, world = _world(group)
+    esz = 8 if kb.val_dtype(kmer_type) == np.uint64 else 4
+    counts = engine.count_partition_counts(batch, k, kmer_type, world, canonical)
+    if world > 1:
+        mat = [None] * world
+        dist.all_gather_object(mat, [int(c) for c in counts], group=group)
+    else:
+        mat = [[int(c) for c in counts]]
+    recv_total = sum(mat[s][rank] for s in range(world))
+    dests = xchg.ensure(recv_total * esz)
+    offsets = [sum(mat[s][p] for s in range(rank)) for p in range(world)]
+    engine.count_partition_scatter(batch, k, kmer_type, world, dests, offsets, canonical)  # returns when the kernel is done
+    if world > 1:
+        dist.barrier(group=group)  # every sender's stores have landed
+    if recv_total:
+        counter.insert_kmers(device_ptr=xchg.local_ptr, n=recv_total)
+    if world > 1:
+        dist.barrier(group=group)  # the buffers may be overwritten by the next round
+    return recv_total

@@ -358,6 +358,40 @@ class Engine:
         return out[: batch.kmer_count(k)], counts
 
 
+    # ---- peer-to-peer exchange (one box, CUDA IPC over NVLink) ----------------------------------
+    def count_partition_counts(self, batch, k, kmer_type, nparts, canonical=True):
+        counts = np.zeros(nparts, dtype=np.uint64)
+        check(self.lib.kmu_count_partition_counts(self.ctx, batch.handle, k, kmer_type, int(bool(canonical)), nparts,
+                                                  _p(counts, u64p)))
+        return counts
+
+    def count_partition_scatter(self, batch, k, kmer_type, nparts, dests, dest_offsets, canonical=True):
+        """dests: nparts device pointers (ints); dest_offsets: element offset of this rank's bucket in each of them"""
+        ptrs = (C.c_void_p * nparts)(*[int(d) for d in dests])
+        offs = _as_u64(dest_offsets)
+        check(self.lib.kmu_count_partition_scatter(self.ctx, batch.handle, k, kmer_type, int(bool(canonical)), nparts,
+                                                   ptrs, _p(offs, u64p)))
+
+    def ipc_alloc(self, nbytes):
+        """-> (device pointer, 64-byte IPC handle) of a buffer other processes of the box can map"""
+        ptr = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        check(self.lib.kmu_ipc_alloc(self.ctx, int(nbytes), C.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def ipc_free(self, ptr):
+        check(self.lib.kmu_ipc_free(self.ctx, C.c_void_p(ptr)))
+
+    def ipc_open(self, handle):
+        ptr = C.c_void_p()
+        buf = (C.c_uint8 * 64)(*handle)
+        check(self.lib.kmu_ipc_open(self.ctx, buf, C.byref(ptr)))
+        return ptr.value
+
+    def ipc_close(self, ptr):
+        check(self.lib.kmu_ipc_close(self.ctx, C.c_void_p(ptr)))
+
+
 class KmerCounter:
     """Exact k-mer multiplicity table in HBM behind the KmerCountT interface
     (src/base/kmercount.rs:48-59): insert_kmer / get_count / get_nb_distinct / get_nb_unique."""

@@ -29,6 +29,18 @@ def main():
     first = rank * per
     mine = eng.batch_sample_reads(genome, 3, first, per if rank < world - 1 else nreads - first, 150, 5000)
     counter, st = kd.count_sharded(eng, mine, k, kb.KMER64, capacity_per_rank=int(nreads * 150 * 1.2 / world) + 1024)
+    # the same exchange without NCCL on the data path: partition kernel stores into peer buffers (CUDA IPC / NVLink)
+    xchg = kd.P2PExchange(eng)
+    counter2 = eng.counter(k, kb.KMER64, int(nreads * 150 * 1.2 / world) + 1024)
+    half = mine  # two rounds over the same reads would double the counts: split the shard in two slices instead
+    nloc = len(mine)
+    idx = np.arange(nloc, dtype=np.uint64)
+    for lo, hi in ((0, nloc // 2), (nloc // 2, nloc)):
+        part = eng.batch_slices(mine, idx[lo:hi], np.zeros(hi - lo, np.uint64), np.full(hi - lo, 150, np.uint64))
+        kd.count_sharded_p2p(eng, part, k, kb.KMER64, counter2, xchg)
+        part.destroy()
+    st2 = counter2.stats()
+    tot2 = kd.allreduce_sum([st2["nb_distinct"], st2["nb_unique"], st2["nb_inserted"]], torch.device("cuda", local))
     hll_local = eng.sketch_setsketch(mine, 21, kb.KMER64, kb.HASH_CANON_INVHASH, (1.001, 256, 20.0, 65534), np.uint16, whole=True)
     hll = kd.merge_registers(torch.from_numpy(hll_local.astype(np.int32)).cuda(), "max").cpu().numpy().astype(np.uint16)
     smh_local = eng.sketch_superminhash(mine, 21, kb.KMER64, kb.HASH_CANON_INVHASH, 256).min(axis=0)
@@ -51,6 +63,8 @@ def main():
         got = (st["nb_distinct"], st["nb_unique"], st["nb_inserted"])
         ok &= got == want
         print(f"[dist_check] world={world} counting stats {got} want {want}", flush=True)
+        ok &= tuple(tot2) == want
+        print(f"[dist_check] peer-to-peer exchange (no data-path collective) stats {tuple(tot2)} ok={tuple(tot2) == want}", flush=True)
         want_hll = orc.sketch_setsketch_seqs(buf, off, nb, 21, kb.KMER64, kb.HASH_CANON_INVHASH, (1.001, 256, 20.0, 65534))
         ok &= bool(np.array_equal(hll, want_hll))
         want_smh = orc.sketch_superminhash_seqs(buf, off, nb, 21, kb.KMER64, kb.HASH_CANON_INVHASH, 256)
@@ -71,6 +85,8 @@ def main():
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     counter.destroy()
+    counter2.destroy()
+    xchg.close()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)
 

@@ -186,3 +186,33 @@ def test_count_two_phase_large_table(engine, oracle, monkeypatch):
     assert np.array_equal(ctr2.get_count(keys[sel]), ctr.get_count(keys[sel]))
     ctr.destroy()
     ctr2.destroy()
+
+
+def test_p2p_exchange_single_rank(engine, oracle):
+    # the peer-to-peer form of the exchange with one rank: the bucket is written through a device pointer table into
+    # an IPC-exportable buffer, then inserted
+    from kmerutils_b200 import dist as kd
+    rng = np.random.default_rng(3)
+    nb = rng.integers(31, 900, 400).astype(np.uint64)
+    batch = engine.batch_synth(88, nb)
+    packed, off = oracle_batch(oracle, 88, nb)
+    keys, cnts = oracle.count_kmers(packed, off, nb, 31, kb.KMER64, True)
+    xchg = kd.P2PExchange(engine)
+    ctr = engine.counter(31, kb.KMER64, capacity=len(keys))
+    for _ in range(2):  # second round reuses the buffer
+        n = kd.count_sharded_p2p(engine, batch, 31, kb.KMER64, ctr, xchg)
+        assert n == batch.kmer_count(31)
+    assert np.array_equal(ctr.get_count(keys), np.minimum(2 * cnts, 255).astype(np.uint32))
+    # four owners on one GPU: buckets land at the right offsets of four buffers
+    counts = engine.count_partition_counts(batch, 31, kb.KMER64, 4)
+    import torch
+    bufs = [torch.zeros(int(c) + 8, dtype=torch.int64, device="cuda:0") for c in counts]
+    engine.count_partition_scatter(batch, 31, kb.KMER64, 4, [b.data_ptr() for b in bufs], [3, 0, 5, 1])
+    for p, (b, o) in enumerate(zip(bufs, [3, 0, 5, 1])):
+        got = b.cpu().numpy().astype(np.uint64)[o:o + int(counts[p])]
+        assert (oracle.dispatch(np.unique(got)[:100], kb.KMER64, 4) == p).all()
+    allk = np.concatenate([b.cpu().numpy().astype(np.uint64)[o:o + int(c)] for b, o, c in zip(bufs, [3, 0, 5, 1], counts)])
+    u, m = np.unique(allk, return_counts=True)
+    assert np.array_equal(u, keys) and np.array_equal(m.astype(np.uint64), cnts)
+    ctr.destroy()
+    xchg.close()
