@@ -258,6 +258,11 @@ int32_t kmu_count_stats(kmu_ctx* ctx, const kmu_counter* counter, uint64_t* nb_d
  * entries; *n_out = number found (KMU_EOVERFLOW if > cap) */
 int32_t kmu_count_export(kmu_ctx* ctx, const kmu_counter* counter, uint32_t min_count, void* kmers, uint32_t* counts,
                          uint64_t cap, uint64_t* n_out);
+/* the multiple k-mer dump of threaded_dump_kmer_counter / dump_in_file_multiple_kmer (kmercount.rs:139-145, 584-791):
+ * `u32 0xcea2bbff | u8 kmer_size | u8 nb_bytes_by_count | u64 nb_kmer`, then `kmer.dump()` + count per k-mer seen at
+ * least twice (each once, unordered).  count_bytes 1 or 2. */
+int32_t kmu_count_dump_multiple(kmu_ctx* ctx, const kmu_counter* counter, const char* path, int32_t count_bytes,
+                                uint64_t* nb_dumped);
 /* DispatchableT::dispatch (kmercount.rs:382-420) for a whole batch: all (canonical) compressed k-mer
  * values bucketed by owner = intNN_hash(value) % nparts.  kmers_out holds kmu_kmer_count() values,
  * bucket p first-to-last at offset sum(part_counts[0..p)).  This is the send side of the multi-GPU

@@ -2,6 +2,7 @@
 // Replaces KmerCounter / KmerCounterPool and the count_kmer* drivers of src/base/kmercount.rs.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -308,6 +309,58 @@ int32_t kmu_count_partition(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
     for (uint32_t p = 0; p < nparts; ++p) part_counts[p] = pt[p];
+    return KMU_OK;
+}
+
+// ---- dump of the multiple k-mers (threaded_dump_kmer_counter / dump_in_file_multiple_kmer,
+//      src/base/kmercount.rs:139-145, 584-791): `u32 0xcea2bbff | u8 kmer_size | u8 nb_bytes_by_count | u64 nb_kmer`,
+//      then per k-mer `kmer.dump()` (4 bytes for the u32 types, kmer32bit.rs / kmer16b32bit.rs:65-68; `u8 k + u64 value`
+//      for Kmer64bit, kmer64bit.rs:98-104) followed by the count on nb_bytes_by_count bytes.  Every k-mer seen at
+//      least twice appears ONCE with its saturated count; nb_kmer is exact (the reference writes an estimate and, in
+//      the threaded writer, u16 counts whatever the header says, SURVEY App. B.8 -- count_bytes = 2 matches it).
+int32_t kmu_count_dump_multiple(kmu_ctx* ctx, const kmu_counter* c, const char* path, int32_t count_bytes, uint64_t* nb_dumped) {
+    if (!ctx || !c || !path) return fail(KMU_EINVAL, "null argument");
+    if (count_bytes != 1 && count_bytes != 2) return fail(KMU_EINVAL, "count_bytes must be 1 or 2");
+    uint64_t distinct = 0, unique = 0;
+    int32_t rc = kmu_count_stats(ctx, c, &distinct, &unique, nullptr, nullptr);
+    if (rc) return rc;
+    const uint64_t n = distinct - unique;
+    const size_t esz = c->key64 ? 8 : 4;
+    std::vector<uint8_t> keys((n + 1) * esz);
+    std::vector<uint32_t> counts(n + 1);
+    uint64_t got = 0;
+    rc = kmu_count_export(ctx, c, 2, keys.data(), counts.data(), n, &got);
+    if (rc) return rc;
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(KMU_EINVAL, "cannot open %s", path);
+    const uint32_t magic = 0xcea2bbffu;
+    const uint8_t ksz = (uint8_t)c->k, cb = (uint8_t)count_bytes;
+    std::fwrite(&magic, 4, 1, f);
+    std::fwrite(&ksz, 1, 1, f);
+    std::fwrite(&cb, 1, 1, f);
+    std::fwrite(&got, 8, 1, f);
+    const uint32_t sat = c->max_count() < (count_bytes == 1 ? 0xFFu : 0xFFFFu) ? c->max_count() : (count_bytes == 1 ? 0xFFu : 0xFFFFu);
+    std::vector<uint8_t> rec;
+    rec.reserve(got * (esz + 3));
+    for (uint64_t i = 0; i < got; ++i) {
+        if (c->key64) {
+            rec.push_back(ksz);
+            const uint8_t* p = keys.data() + i * 8;
+            rec.insert(rec.end(), p, p + 8);
+        } else {
+            uint32_t w;
+            std::memcpy(&w, keys.data() + i * 4, 4);
+            if (c->kmer_type == KMU_KMER32) w |= c->k << 28;  // Kmer32bit.0 carries k in its top four bits (kmer32bit.rs:68-76)
+            const uint8_t* p = (const uint8_t*)&w;
+            rec.insert(rec.end(), p, p + 4);
+        }
+        const uint32_t cnt = counts[i] < sat ? counts[i] : sat;
+        rec.push_back((uint8_t)cnt);
+        if (count_bytes == 2) rec.push_back((uint8_t)(cnt >> 8));
+    }
+    std::fwrite(rec.data(), 1, rec.size(), f);
+    std::fclose(f);
+    if (nb_dumped) *nb_dumped = got;
     return KMU_OK;
 }
 

@@ -455,6 +455,13 @@ class KmerCounter:
                                                C.byref(n)))
         return kmers[: n.value], counts[: n.value]
 
+    def dump_multiple(self, path, count_bytes=2):
+        """threaded_dump_kmer_counter (kmercount.rs:653-791): file of the k-mers seen at least twice with their counts."""
+        import os
+        n = C.c_uint64()
+        check(self.engine.lib.kmu_count_dump_multiple(self.engine.ctx, self._h, os.fsencode(path), count_bytes, C.byref(n)))
+        return n.value
+
     def destroy(self):
         if self._h is not None:
             self.engine.lib.kmu_count_destroy(self._h)

@@ -216,3 +216,37 @@ def test_p2p_exchange_single_rank(engine, oracle):
     assert np.array_equal(u, keys) and np.array_equal(m.astype(np.uint64), cnts)
     ctr.destroy()
     xchg.close()
+
+
+@pytest.mark.parametrize("k,ktype", [(31, kb.KMER64), (16, kb.KMER16B32), (12, kb.KMER32)])
+def test_multiple_kmer_dump_format(engine, oracle, tmp_path, k, ktype):
+    import struct
+    rng = np.random.default_rng(k)
+    reads = genome_reads(oracle, 5, 8000, 600, 150, rng)
+    batch, _ = engine.batch_from_ascii(reads)
+    packed, off, nb = batch.download()
+    keys, cnts = oracle.count_kmers(packed, off, nb, k, ktype, True)
+    ctr = engine.counter(k, ktype, capacity=len(keys), count_bits=8)
+    ctr.insert_seqs(batch)
+    path = str(tmp_path / "x.multi_kmer.bin")
+    n = ctr.dump_multiple(path, count_bytes=2)
+    raw = open(path, "rb").read()
+    magic, ksz, cb, nk = struct.unpack("<IBBQ", raw[:14])  # kmercount.rs:139-145
+    assert (magic, ksz, cb, nk) == (0xcea2bbff, k, 2, n) and n == int((cnts >= 2).sum())
+    recsz = (9 if ktype == kb.KMER64 else 4) + 2
+    assert len(raw) == 14 + n * recsz
+    got = {}
+    for i in range(n):
+        r = raw[14 + i * recsz: 14 + (i + 1) * recsz]
+        if ktype == kb.KMER64:  # Kmer64bit::dump = u8 k + u64 value (kmer64bit.rs:98-104)
+            assert r[0] == k
+            key = struct.unpack("<Q", r[1:9])[0]
+        else:
+            key = struct.unpack("<I", r[:4])[0]
+            if ktype == kb.KMER32:  # the word carries k in its top four bits
+                assert key >> 28 == k
+                key &= 0x0FFFFFFF
+        got[key] = struct.unpack("<H", r[-2:])[0]
+    want = {int(a): min(int(c), 255) for a, c in zip(keys, cnts) if c >= 2}
+    assert got == want
+    ctr.destroy()
