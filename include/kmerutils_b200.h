@@ -227,6 +227,12 @@ int32_t kmu_sketch_setsketch(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k
 int32_t kmu_signature_jaccard(kmu_ctx* ctx, const void* sig_a, uint64_t na, const void* sig_b, uint64_t nb, uint32_t m,
                               int32_t slot_bytes, double* out, int32_t on_device);
 
+/* whole-file form: ONE SuperMinHash signature for the batch (SuperHashSketch::sketch_compressedkmer_seqs,
+ * src/sketching/setsketchert.rs:299-335); equals the element-wise minimum of the per-sequence signatures */
+int32_t kmu_sketch_superminhash_whole(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, int32_t kmer_type,
+                                      int32_t hash_kind, uint32_t m, int32_t key_hasher, int32_t sig_bytes, void* sig,
+                                      int32_t sig_on_device);
+
 /* ---- k-mer counting (replaces KmerCounter: cuckoo filter + counting Bloom filter,
  *      src/base/kmercount.rs:70-83) -------------------------------------------------------
  * One exact open-addressing table in HBM keyed by kmer.get_compressed_value().  Semantics are

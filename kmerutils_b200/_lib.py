@@ -90,6 +90,8 @@ SIGNATURES = {
                                          C.POINTER(KmuSetSketchParams), C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "kmu_signature_jaccard": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32,
                                           C.c_void_p, C.c_int32]),
+    "kmu_sketch_superminhash_whole": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32,
+                                                  C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "kmu_count_create": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint64, vpp]),
     "kmu_count_destroy": (None, [C.c_void_p]),
     "kmu_count_capacity": (C.c_uint64, [C.c_void_p]),

@@ -39,41 +39,13 @@ TeamGeometry team_geometry(uint64_t nk_max, size_t team_bytes, size_t cta_fixed_
 
 }  // namespace
 
-// deterministic natural logarithm, host copy of kmu_detmath.cuh (same operations, same results)
-static double host_det_log(double x);
-
-extern "C" {
-
-int32_t kmu_sketch_superminhash(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t hash_kind,
-                                uint32_t m, int32_t key_hasher, int32_t sig_bytes, void* sig, int32_t sig_on_device) {
-    if (!ctx || !b) return fail(KMU_EINVAL, "null argument");
-    if (int32_t a = kmu_check_kmer_args(b, k, kmer_type, hash_kind)) return a;
-    if (key_hasher != KMU_HASHER_NOHASH && key_hasher != KMU_HASHER_FNV) return fail(KMU_EINVAL, "unknown key hasher %d", key_hasher);
-    if (sig_bytes != 4 && sig_bytes != 8) return fail(KMU_EINVAL, "sig_bytes must be 4 (f32) or 8 (f64)");
-    if (m < 1) return fail(KMU_EINVAL, "SuperMinHash needs a sketch size >= 1");
-    const size_t team_bytes = align_up((size_t)m * sig_bytes, 16) + 32;
-    if (team_bytes > SMEM_BUDGET)
-        return fail(KMU_EINVAL, "sketch size %u does not fit the shared memory of one SM (max %zu slots of %d bytes)", m,
-                    (SMEM_BUDGET - 32) / sig_bytes, sig_bytes);
-    if (b->nseq == 0) return KMU_OK;
-    if (!sig) return fail(KMU_EINVAL, "null signature buffer");
-    if (b->nseq >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "more than 2^32-1 sequences in one batch");
-    for (uint64_t L : b->h_nbases)
-        if (L >= 0xFFFFFF00ull) return fail(KMU_EINVAL, "a single sequence is limited to 2^32 - 256 bases");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    ScopedDevice sd(ctx->device);
-    ctx->last = kmu_times{};
+// per-sequence SuperMinHash into device memory (the context's mutex is held by the caller)
+static int32_t smh_per_sequence_device(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t hash_kind,
+                                       uint32_t m, int32_t key_hasher, int32_t sig_bytes, void* d_sig, uint64_t* launches) {
     cudaStream_t st = ctx->stream;
     const bool key64 = kmer_type_is_u64(kmer_type), f64 = sig_bytes == 8;
-    const size_t out_bytes = (size_t)b->nseq * m * sig_bytes;
-    void* d_sig = sig;
-    if (!sig_on_device) {
-        CUDA_TRY(ctx->sig_dev.reserve(out_bytes));
-        d_sig = ctx->sig_dev.p;
-    }
-    uint64_t launches = 0;
-    cudaEventRecord(ctx->ev[0], st);
-    int32_t rc = kmu_ensure_order(ctx, b, k, &launches);
+    const size_t team_bytes = align_up((size_t)m * sig_bytes, 16) + 32;
+    int32_t rc = kmu_ensure_order(ctx, b, k, launches);
     if (rc) return rc;
     std::vector<OctaveClass> classes = kmu_octave_classes(b);
     if (classes.size() > 120) return fail(KMU_EINVAL, "too many launch classes");
@@ -120,7 +92,7 @@ int32_t kmu_sketch_superminhash(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k,
         per_sm = std::max(1u, std::min(per_sm, 8u));
         const int grid = (int)std::min<uint64_t>(ctas_needed, (uint64_t)ctx->sm_count * per_sm);
         CUDA_TRY(kmu::launch_smh_fast(Q, key64, f64, grid, l.g.block, l.g.smem, st));
-        ++launches;
+        ++*launches;
     }
     // short sequences (relative to m) and failed speculations: exact path
     unsigned long long nslow = 0;
@@ -142,7 +114,48 @@ int32_t kmu_sketch_superminhash(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k,
         Q.scratch = (uint8_t*)ctx->table_scratch.p;
         Q.scratch_per_warp = per_warp;
         CUDA_TRY(kmu::launch_smh_exact(Q, key64, f64, (int)warps, st));
-        ++launches;
+        ++*launches;
+    }
+    return KMU_OK;
+}
+
+// deterministic natural logarithm, host copy of kmu_detmath.cuh (same operations, same results)
+static double host_det_log(double x);
+
+extern "C" {
+
+int32_t kmu_sketch_superminhash(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t hash_kind,
+                                uint32_t m, int32_t key_hasher, int32_t sig_bytes, void* sig, int32_t sig_on_device) {
+    if (!ctx || !b) return fail(KMU_EINVAL, "null argument");
+    if (int32_t a = kmu_check_kmer_args(b, k, kmer_type, hash_kind)) return a;
+    if (key_hasher != KMU_HASHER_NOHASH && key_hasher != KMU_HASHER_FNV) return fail(KMU_EINVAL, "unknown key hasher %d", key_hasher);
+    if (sig_bytes != 4 && sig_bytes != 8) return fail(KMU_EINVAL, "sig_bytes must be 4 (f32) or 8 (f64)");
+    if (m < 1) return fail(KMU_EINVAL, "SuperMinHash needs a sketch size >= 1");
+    const size_t team_bytes = align_up((size_t)m * sig_bytes, 16) + 32;
+    if (team_bytes > SMEM_BUDGET)
+        return fail(KMU_EINVAL, "sketch size %u does not fit the shared memory of one SM (max %zu slots of %d bytes)", m,
+                    (SMEM_BUDGET - 32) / sig_bytes, sig_bytes);
+    if (b->nseq == 0) return KMU_OK;
+    if (!sig) return fail(KMU_EINVAL, "null signature buffer");
+    if (b->nseq >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "more than 2^32-1 sequences in one batch");
+    for (uint64_t L : b->h_nbases)
+        if (L >= 0xFFFFFF00ull) return fail(KMU_EINVAL, "a single sequence is limited to 2^32 - 256 bases");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    cudaStream_t st = ctx->stream;
+    const bool key64 = kmer_type_is_u64(kmer_type), f64 = sig_bytes == 8;
+    const size_t out_bytes = (size_t)b->nseq * m * sig_bytes;
+    void* d_sig = sig;
+    if (!sig_on_device) {
+        CUDA_TRY(ctx->sig_dev.reserve(out_bytes));
+        d_sig = ctx->sig_dev.p;
+    }
+    uint64_t launches = 0;
+    cudaEventRecord(ctx->ev[0], st);
+    {
+        int32_t rc = smh_per_sequence_device(ctx, b, k, kmer_type, hash_kind, m, key_hasher, sig_bytes, d_sig, &launches);
+        if (rc) return rc;
     }
     cudaEventRecord(ctx->ev[1], st);
     if (!sig_on_device) {
@@ -155,6 +168,84 @@ int32_t kmu_sketch_superminhash(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k,
     if (e != cudaSuccess) return fail(KMU_ECUDA, "SuperMinHash sketch kernels failed: %s", cudaGetErrorString(e));
     cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
     if (!sig_on_device) cudaEventElapsedTime(&ctx->last.d2h_ms, ctx->ev[4], ctx->ev[5]);
+    ctx->launches += launches;
+    ctx->last.launches = launches;
+    return KMU_OK;
+}
+
+int32_t kmu_sketch_superminhash_whole(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type, int32_t hash_kind,
+                                      uint32_t m, int32_t key_hasher, int32_t sig_bytes, void* sig, int32_t sig_on_device) {
+    if (!ctx || !b || !sig) return fail(KMU_EINVAL, "null argument");
+    if (int32_t a = kmu_check_kmer_args(b, k, kmer_type, hash_kind)) return a;
+    if (key_hasher != KMU_HASHER_NOHASH && key_hasher != KMU_HASHER_FNV) return fail(KMU_EINVAL, "unknown key hasher %d", key_hasher);
+    if (sig_bytes != 4 && sig_bytes != 8) return fail(KMU_EINVAL, "sig_bytes must be 4 (f32) or 8 (f64)");
+    if (m < 1) return fail(KMU_EINVAL, "SuperMinHash needs a sketch size >= 1");
+    if (align_up((size_t)m * sig_bytes, 16) + 32 > SMEM_BUDGET)
+        return fail(KMU_EINVAL, "sketch size %u does not fit the shared memory of one SM", m);
+    if (b->nseq >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "more than 2^32-1 sequences in one batch");
+    uint64_t total = 0;
+    for (uint64_t L : b->h_nbases) {
+        if (L >= 0xFFFFFF00ull) return fail(KMU_EINVAL, "a single sequence is limited to 2^32 - 256 bases");
+        total += L >= k ? L - k + 1 : 0;
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    cudaStream_t st = ctx->stream;
+    const bool key64 = kmer_type_is_u64(kmer_type), f64 = sig_bytes == 8;
+    const size_t row_bytes = (size_t)m * sig_bytes;
+    CUDA_TRY(ctx->items_slots.reserve(row_bytes + 64));
+    void* d_row = ctx->items_slots.p;  // the merged slots (bit patterns of S)
+    uint64_t launches = 0;
+    cudaEventRecord(ctx->ev[0], st);
+    CUDA_TRY(kmu::launch_smh_fill_large(d_row, m, f64, st));
+    ++launches;
+    bool done = total == 0;
+    // speculative loop bound from the total k-mer count (same rule as the per-sequence kernel)
+    uint32_t a_spec = 0;
+    if (total) {
+        const double need = (double)m / (double)total * std::log(1e4 * (double)m);
+        const uint32_t a1 = need >= (double)m ? m : (uint32_t)std::ceil(need);
+        a_spec = std::max<uint32_t>(a1, 1) - 1;
+    }
+    if (!done && a_spec <= 15) {
+        kmu::SmhParams P{};
+        P.k = k;
+        P.kmer_type = kmer_type;
+        P.hash_kind = hash_kind;
+        P.m = m;
+        P.hasher = key_hasher;
+        kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
+        const uint64_t nchunks = (b->packed_bytes + 63) / 64;
+        const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((nchunks + 511) / 512, (uint64_t)ctx->sm_count * 2));
+        CUDA_TRY(kmu::launch_smh_whole(P, key64, f64, v, b->packed_bytes, a_spec, d_row, grid, align_up(row_bytes, 16), st));
+        ++launches;
+        std::vector<uint8_t> h(row_bytes);
+        CUDA_TRY(cudaMemcpyAsync(h.data(), d_row, row_bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        done = true;
+        const double bound = (double)(a_spec + 1);
+        for (uint32_t j = 0; j < m && done; ++j)
+            done = (f64 ? ((const double*)h.data())[j] : (double)((const float*)h.data())[j]) < bound;
+        if (!done) {
+            CUDA_TRY(kmu::launch_smh_fill_large(d_row, m, f64, st));
+            ++launches;
+        }
+    }
+    if (!done) {
+        // few k-mers relative to m, or the bound failed: per-sequence sketches (exact path inside), merged by minimum
+        CUDA_TRY(ctx->sig_dev.reserve((size_t)b->nseq * row_bytes));
+        int32_t rc = smh_per_sequence_device(ctx, b, k, kmer_type, hash_kind, m, key_hasher, sig_bytes, ctx->sig_dev.p, &launches);
+        if (rc) return rc;
+        CUDA_TRY(kmu::launch_smh_colmin(ctx->sig_dev.p, b->nseq, m, f64, d_row, st));
+        ++launches;
+    }
+    cudaEventRecord(ctx->ev[1], st);
+    CUDA_TRY(cudaMemcpyAsync(sig, d_row, row_bytes, sig_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (!sig_on_device) ctx->last.d2h_bytes = row_bytes;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(KMU_ECUDA, "SuperMinHash whole-file sketch failed: %s", cudaGetErrorString(e));
+    cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
     ctx->launches += launches;
     ctx->last.launches = launches;
     return KMU_OK;

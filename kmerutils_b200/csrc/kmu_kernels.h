@@ -165,6 +165,10 @@ struct SmhParams {
     uint64_t scratch_per_warp;
 };
 cudaError_t launch_smh_fast(const SmhParams& P, bool key64, bool f64, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t launch_smh_whole(const SmhParams& P, bool key64, bool f64, const SeqView& b, uint64_t total_bytes, uint32_t a_spec,
+                             void* gslots, int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_smh_fill_large(void* slots, uint32_t m, bool f64, cudaStream_t st);
+cudaError_t launch_smh_colmin(const void* rows, uint64_t nseq, uint32_t m, bool f64, void* out, cudaStream_t st);
 cudaError_t launch_smh_exact(const SmhParams& P, bool key64, bool f64, int grid, cudaStream_t st);
 
 // ---- SetSketch (kmu_setsketch.cu) ---------------------------------------------------------------

@@ -17,6 +17,7 @@
 //     slots) an item is one seed, two draws and one atomicMin in shared memory.
 //   * exact path (short sequences relative to m): one warp per sequence, 32 items per round with a
 //     full lazily-reset permutation per lane in global scratch, a = floor(max slot) between rounds.
+#include <algorithm>
 #include <cstdint>
 
 #include "kmu_device.cuh"
@@ -264,6 +265,91 @@ __global__ void __launch_bounds__(32) smh_exact_kernel(const SmhParams P) {
         for (uint32_t j = lane; j < m; j += 32) out[j] = F::value(h[j]);
         __syncwarp();
     }
+}
+
+// ---- one sketch for the whole batch (SuperHashSketch::sketch_compressedkmer_seqs, setsketchert.rs:299-335) --------
+// every CTA keeps partial slots in shared memory over its share of the 64-byte chunks of the packed buffer and merges
+// them into the global slots with atomicMin; the host verifies the speculative bound (all slots < a_spec + 1)
+template <typename V, typename S, bool AA>
+__global__ void __launch_bounds__(512, 2) smh_whole_kernel(const SmhParams P, SeqView b, uint64_t total_bytes, uint32_t a_spec,
+                                                            typename FloatOps<S>::B* gslots) {
+    using F = FloatOps<S>;
+    using B = typename F::B;
+    extern __shared__ __align__(16) uint8_t smem[];
+    B* h = (B*)smem;
+    const uint32_t m = P.m;
+    for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) h[j] = F::large();
+    __syncthreads();
+    const V header = (V)word_header(P.kmer_type, P.k);
+    const bool canonical = hash_is_canonical(P.hash_kind);
+    const uint64_t nchunks = (total_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES;
+    for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < nchunks; c += (uint64_t)gridDim.x * blockDim.x)
+        for_each_kmer_in_chunk<V, AA>(b, total_bytes, c, P.k, canonical, [&](V pk) {
+            const V key = finalize_key<V>(pk, header, P.hash_kind);
+            Xoshiro256pp rng;
+            rng.seed(item_seed<V>(key, P.hasher));
+            smh_item_points<S>(rng, m, a_spec, h);
+        });
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < m; j += blockDim.x)
+        if (h[j] != F::large()) atomicMin(gslots + j, h[j]);
+}
+
+template <typename B>
+__global__ void smh_fill_kernel(B* slots, uint32_t m, B v) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) slots[j] = v;
+}
+
+// column minimum of nseq rows of m slots (element-wise merge of per-sequence sketches)
+template <typename B>
+__global__ void smh_colmin_kernel(const B* rows, uint64_t nseq, uint32_t m, B* out) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        B mn = ~(B)0;
+        for (uint64_t r = blockIdx.y; r < nseq; r += gridDim.y) {
+            const B v = rows[r * m + j];
+            mn = v < mn ? v : mn;
+        }
+        atomicMin(out + j, mn);
+    }
+}
+
+template <typename V, typename S, bool AA>
+static cudaError_t launch_whole_t(const SmhParams& P, const SeqView& b, uint64_t total_bytes, uint32_t a_spec, void* gslots,
+                                  int grid, size_t smem, cudaStream_t st) {
+    auto kern = smh_whole_kernel<V, S, AA>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kern<<<grid, 512, smem, st>>>(P, b, total_bytes, a_spec, (typename FloatOps<S>::B*)gslots);
+    return cudaGetLastError();
+}
+template <typename V, bool AA>
+static cudaError_t launch_whole_s(const SmhParams& P, bool f64, const SeqView& b, uint64_t total_bytes, uint32_t a_spec,
+                                  void* gslots, int grid, size_t smem, cudaStream_t st) {
+    return f64 ? launch_whole_t<V, double, AA>(P, b, total_bytes, a_spec, gslots, grid, smem, st)
+               : launch_whole_t<V, float, AA>(P, b, total_bytes, a_spec, gslots, grid, smem, st);
+}
+cudaError_t launch_smh_whole(const SmhParams& P, bool key64, bool f64, const SeqView& b, uint64_t total_bytes, uint32_t a_spec,
+                             void* gslots, int grid, size_t smem, cudaStream_t st) {
+    if (P.kmer_type == KMU_KMERAA32) return launch_whole_s<uint32_t, true>(P, f64, b, total_bytes, a_spec, gslots, grid, smem, st);
+    if (P.kmer_type == KMU_KMERAA64) return launch_whole_s<uint64_t, true>(P, f64, b, total_bytes, a_spec, gslots, grid, smem, st);
+    return key64 ? launch_whole_s<uint64_t, false>(P, f64, b, total_bytes, a_spec, gslots, grid, smem, st)
+                 : launch_whole_s<uint32_t, false>(P, f64, b, total_bytes, a_spec, gslots, grid, smem, st);
+}
+// slots <- F::from(u32::MAX) as bit patterns
+cudaError_t launch_smh_fill_large(void* slots, uint32_t m, bool f64, cudaStream_t st) {
+    if (f64) smh_fill_kernel<unsigned long long><<<(m + 255) / 256, 256, 0, st>>>((unsigned long long*)slots, m, 0x41EFFFFFFFE00000ULL);
+    else smh_fill_kernel<unsigned int><<<(m + 255) / 256, 256, 0, st>>>((unsigned int*)slots, m, 0x4F800000u);
+    return cudaGetLastError();
+}
+cudaError_t launch_smh_colmin(const void* rows, uint64_t nseq, uint32_t m, bool f64, void* out, cudaStream_t st) {
+    dim3 grid((m + 255) / 256, (unsigned)std::min<uint64_t>(nseq ? nseq : 1, 256));
+    if (f64) smh_colmin_kernel<unsigned long long><<<grid, 256, 0, st>>>((const unsigned long long*)rows, nseq, m, (unsigned long long*)out);
+    else smh_colmin_kernel<unsigned int><<<grid, 256, 0, st>>>((const unsigned int*)rows, nseq, m, (unsigned int*)out);
+    return cudaGetLastError();
 }
 
 template <typename V, typename S, bool AA>

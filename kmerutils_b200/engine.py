@@ -275,6 +275,15 @@ class Engine:
                                                dtype.itemsize, _p(out), 0))
         return out
 
+    def sketch_superminhash_whole(self, batch, k, kmer_type, hash_kind=HASH_CANON_INVHASH, m=200,
+                                  key_hasher=_lib.HASHER_NOHASH, dtype=np.float64):
+        """ONE SuperMinHash signature for the whole batch (SuperHashSketch::sketch_compressedkmer_seqs)."""
+        dtype = np.dtype(dtype)
+        out = np.zeros(m, dtype=dtype)
+        check(self.lib.kmu_sketch_superminhash_whole(self.ctx, batch.handle, k, kmer_type, hash_kind, m, key_hasher,
+                                                     dtype.itemsize, _p(out), 0))
+        return out
+
     def sketch_setsketch(self, batch, k, kmer_type, hash_kind=HASH_CANON_INVHASH, params=None, dtype=np.uint16,
                          whole=False, out_device_ptr=None):
         """SetSketch registers (HyperLogLogSketch): (nseq, m) array, or (m,) when whole=True (one sketch for the

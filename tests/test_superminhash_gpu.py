@@ -81,3 +81,25 @@ def test_superminhash_bad_arguments(engine):
         engine.sketch_superminhash(b, 8, kb.KMER32, m=0)
     with pytest.raises(kb.KmuInvalid):
         engine.sketch_superminhash(b, 8, kb.KMER32, m=100000)  # 800 kB of slots: does not fit one SM
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("nb", [[600000, 250000, 10, 3000, 77], [500, 300, 20], [40], [5, 3]])
+def test_superminhash_whole_file(engine, oracle, nb, dtype):
+    # SuperHashSketch::sketch_compressedkmer_seqs (setsketchert.rs:299-335): one sketch over all contigs;
+    # large inputs take the whole-batch kernel, small ones the per-sequence path merged by minimum
+    nb = np.array(nb, dtype=np.uint64)
+    batch = engine.batch_synth(61, nb)
+    packed, off = oracle_batch(oracle, 61, nb)
+    got = engine.sketch_superminhash_whole(batch, 12, kb.KMER32, kb.HASH_CANON_INVHASH, 300, kb.HASHER_NOHASH, dtype)
+    want = oracle.sketch_superminhash_seqs(packed, off, nb, 12, kb.KMER32, kb.HASH_CANON_INVHASH, 300, 0, dtype)
+    assert np.array_equal(got, want)
+
+
+def test_superminhash_whole_genome_m12000(engine, oracle):
+    nb = np.array([900000, 400000, 200000], dtype=np.uint64)  # a 1.5 Mb "genome" in three contigs
+    batch = engine.batch_synth(62, nb)
+    packed, off = oracle_batch(oracle, 62, nb)
+    got = engine.sketch_superminhash_whole(batch, 16, kb.KMER16B32, kb.HASH_CANON_INVHASH, 12000)
+    want = oracle.sketch_superminhash_seqs(packed, off, nb, 16, kb.KMER16B32, kb.HASH_CANON_INVHASH, 12000)
+    assert np.array_equal(got, want)
