@@ -115,6 +115,9 @@ int32_t kmu_seqbatch_sample_reads(kmu_ctx* ctx, const kmu_seqbatch* genome, uint
  * sketch_seqrange_superminhash (seqminhash.rs:19-62). */
 int32_t kmu_seqbatch_slices(kmu_ctx* ctx, const kmu_seqbatch* src, const uint64_t* seq_idx, const uint64_t* begin,
                             const uint64_t* end, uint64_t nslices, kmu_seqbatch** batch);
+/* a view of nseq consecutive sequences of `src` (e.g. the contigs of one genome of a multi-genome batch) that shares the
+ * packed bases of `src`; `src` must outlive the view.  Destroy it with kmu_seqbatch_destroy. */
+int32_t kmu_seqbatch_view(const kmu_seqbatch* src, uint64_t first_seq, uint64_t nseq, kmu_seqbatch** view);
 void kmu_seqbatch_destroy(kmu_seqbatch* batch);
 uint64_t kmu_seqbatch_nseq(const kmu_seqbatch* batch);
 uint64_t kmu_seqbatch_total_bases(const kmu_seqbatch* batch);

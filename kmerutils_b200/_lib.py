@@ -67,6 +67,7 @@ SIGNATURES = {
     "kmu_seqbatch_sample_reads": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
                                               C.c_uint32, vpp]),
     "kmu_seqbatch_slices": (C.c_int32, [C.c_void_p, C.c_void_p, u64p, u64p, u64p, C.c_uint64, vpp]),
+    "kmu_seqbatch_view": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, vpp]),
     "kmu_seqbatch_destroy": (None, [C.c_void_p]),
     "kmu_seqbatch_nseq": (C.c_uint64, [C.c_void_p]),
     "kmu_seqbatch_total_bases": (C.c_uint64, [C.c_void_p]),

@@ -229,6 +229,7 @@ void kmu_seqbatch_destroy(kmu_seqbatch* b) {
     ScopedDevice sd(b->device);
     b->order_cache.order.release();
     b->order_cache.cursor_dev.release();
+    if (!b->owns && b->owns_byte_off && b->byte_off) cudaFree(b->byte_off);
     if (b->owns) {
         if (b->packed) cudaFree(b->packed);
         if (b->byte_off) cudaFree(b->byte_off);
@@ -574,6 +575,43 @@ int32_t kmu_seqbatch_slices(kmu_ctx* ctx, const kmu_seqbatch* src, const uint64_
         return rc ? rc : fail(KMU_ECUDA, "slicing failed: %s", cudaGetErrorString(e));
     }
     *out = b;
+    return KMU_OK;
+}
+
+// a view of `nseq` consecutive sequences of a batch (one genome = its contigs): shares the device buffers of `src`,
+// which must outlive the view
+int32_t kmu_seqbatch_view(const kmu_seqbatch* src, uint64_t first_seq, uint64_t nseq, kmu_seqbatch** out) {
+    if (!src || !out) return fail(KMU_EINVAL, "null argument");
+    if (first_seq > src->nseq || nseq > src->nseq - first_seq)
+        return fail(KMU_EINVAL, "view %llu..%llu exceeds the %llu sequences of the batch", (unsigned long long)first_seq,
+                    (unsigned long long)(first_seq + nseq), (unsigned long long)src->nseq);
+    auto* v = new kmu_seqbatch();
+    v->device = src->device;
+    v->owns = false;
+    v->alphabet = src->alphabet;
+    v->nseq = nseq;
+    // the view starts at its first sequence: byte offsets are rebased into an array of its own
+    const uint64_t base = nseq ? src->h_byte_off[first_seq] : 0;
+    v->packed = src->packed + base;
+    v->nbases = src->nbases + first_seq;
+    v->h_nbases.assign(src->h_nbases.begin() + first_seq, src->h_nbases.begin() + first_seq + nseq);
+    v->h_byte_off.resize(nseq);
+    for (uint64_t i = 0; i < nseq; ++i) v->h_byte_off[i] = src->h_byte_off[first_seq + i] - base;
+    for (uint64_t L : v->h_nbases) v->total_bases += L;
+    if (nseq) {
+        const uint64_t L = v->h_nbases.back();
+        v->packed_bytes = v->h_byte_off.back() + align_up(src->alphabet ? L : (L + 3) / 4, SEQ_ALIGN);
+    }
+    ScopedDevice sd(src->device);
+    cudaError_t e = cudaMalloc((void**)&v->byte_off, sizeof(uint64_t) * (nseq + 1));
+    if (e == cudaSuccess && nseq) e = cudaMemcpy(v->byte_off, v->h_byte_off.data(), sizeof(uint64_t) * nseq, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (v->byte_off) cudaFree(v->byte_off);
+        delete v;
+        return fail(KMU_ECUDA, "view creation failed: %s", cudaGetErrorString(e));
+    }
+    v->owns_byte_off = true;
+    *out = v;
     return KMU_OK;
 }
 

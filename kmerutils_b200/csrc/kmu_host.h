@@ -124,7 +124,8 @@ struct kmu_seqbatch {
     uint64_t nseq = 0;
     uint64_t packed_bytes = 0;  // without the tail slack
     uint64_t total_bases = 0;
-    bool owns = true;           // false: the buffers belong to a context arena
+    bool owns = true;           // false: the buffers belong to a context arena or to a parent batch
+    bool owns_byte_off = false; // a view: byte_off is the view's own (rebased) array
     int alphabet = 0;           // 0: DNA, 2 bits per base packed; 1: amino acids, one 5-bit code per byte
     std::vector<uint64_t> h_nbases;
     std::vector<uint64_t> h_byte_off;

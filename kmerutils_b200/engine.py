@@ -202,6 +202,28 @@ class Engine:
                                                  C.byref(h)))
         return SeqBatch(self, h)
 
+    def batch_view(self, src, first_seq, nseq):
+        """View of nseq consecutive sequences of `src` (shares its packed bases; keep `src` alive)."""
+        h = C.c_void_p()
+        check(self.lib.kmu_seqbatch_view(src.handle, int(first_seq), int(nseq), C.byref(h)))
+        v = SeqBatch(self, h)
+        v._parent = src
+        return v
+
+    def sketch_groups(self, batch, group_sizes, algo, k, kmer_type, hash_kind=HASH_CANON_INVHASH, **kw):
+        """One whole-file signature per group of consecutive sequences (a genome = its contigs), the way gsearch drives
+        the `sketch_compressedkmer_seqs` entry points.  algo: "pmh3a" | "superminhash" | "setsketch"; kw as for the
+        whole-file calls.  -> (ngroups, m) array"""
+        fn = {"pmh3a": self.sketch_pmh3a_whole, "superminhash": self.sketch_superminhash_whole,
+              "setsketch": lambda b, k_, t, h, **kk: self.sketch_setsketch(b, k_, t, h, whole=True, **kk)}[algo]
+        rows, first = [], 0
+        for n in group_sizes:
+            view = self.batch_view(batch, first, int(n))
+            rows.append(fn(view, k, kmer_type, hash_kind, **kw))
+            view.destroy()
+            first += int(n)
+        return np.stack(rows) if rows else np.zeros((0, 0))
+
     def batch_slices(self, src, seq_idx, begin, end):
         """New batch made of the ranges [begin[i], end[i]) of sequences seq_idx[i] of `src` (copied on the device)."""
         idx, b, e = _as_u64(seq_idx), _as_u64(begin), _as_u64(end)

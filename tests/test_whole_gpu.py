@@ -104,3 +104,34 @@ def test_block_sketch_reference_test(engine):
     sig, numseq, numblock = engine.blocksketch(batch, 3, 10, 20)
     a, b = sig[numseq == 0], sig[numseq == 1]
     assert a.shape == b.shape == (4, 10) and np.array_equal(a, b)
+
+
+def test_views_and_groups(engine, oracle):
+    # genomes made of several contigs in one batch: one whole-file signature per genome through views
+    rng = np.random.default_rng(31)
+    groups = [3, 1, 5, 2]
+    nb = np.concatenate([rng.integers(2000, 60000, g) for g in groups]).astype(np.uint64)
+    batch = engine.batch_synth(44, nb)
+    packed, off = oracle_batch(oracle, 44, nb)
+    first = 0
+    sm = engine.sketch_groups(batch, groups, "superminhash", 16, kb.KMER16B32, m=500)
+    pm = engine.sketch_groups(batch, groups, "pmh3a", 16, kb.KMER16B32, m=500)
+    hl = engine.sketch_groups(batch, groups, "setsketch", 16, kb.KMER16B32, params=(1.001, 256, 20.0, 65534))
+    for gi, g in enumerate(groups):
+        sl = slice(first, first + g)
+        o, n = off[sl], nb[sl]
+        assert np.array_equal(sm[gi], oracle.sketch_superminhash_seqs(packed, o, n, 16, kb.KMER16B32, kb.HASH_CANON_INVHASH, 500))
+        assert np.array_equal(pm[gi].astype(np.uint64), oracle.sketch_pmh3a_seqs(packed, o, n, 16, kb.KMER16B32, kb.HASH_CANON_INVHASH, 500))
+        assert np.array_equal(hl[gi], oracle.sketch_setsketch_seqs(packed, o, n, 16, kb.KMER16B32, kb.HASH_CANON_INVHASH,
+                                                                    (1.001, 256, 20.0, 65534)))
+        first += g
+    # a view behaves like a batch for the per-sequence calls too
+    view = engine.batch_view(batch, 4, 5)
+    assert len(view) == 5 and view.total_bases == int(nb[4:9].sum())
+    got = engine.sketch_pmh3a(view, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 64)
+    want = oracle.sketch_pmh3a_batch(packed, off[4:9], nb[4:9], 8, kb.KMER32, kb.HASH_CANON_INVHASH, 64)
+    assert np.array_equal(got, want)
+    kmers, _ = engine.generate_kmers(view, 21, kb.KMER64, kb.HASH_CANON_RAW)
+    assert len(kmers) == int(np.maximum(nb[4:9].astype(np.int64) - 20, 0).sum())
+    with pytest.raises(kb.KmuInvalid):
+        engine.batch_view(batch, 9, 5)
