@@ -324,7 +324,7 @@ int32_t kmu_last_times(const kmu_ctx* ctx, kmu_times* out);
 /* ---- optional per-launch profile of the last sketch call (CUDA events around every launch
  *      of the sketch kernel; switch on with kmu_ctx_set_profiling before the call) ---------- */
 typedef struct kmu_launch_rec {
-    int32_t mode;           /* 0 = direct u16 histogram, 1 = open-addressing table */
+    int32_t mode;           /* 0 = u8 histogram, 1 = open-addressing table, 2 = one-pass kernel for long sequences */
     int32_t table_global;   /* table in global scratch instead of shared memory */
     uint32_t team_warps;    /* warps cooperating on one sequence */
     uint32_t teams_per_cta;

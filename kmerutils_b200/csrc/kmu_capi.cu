@@ -909,8 +909,17 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     // ---- launch classes: one per octave of the k-mer count ------------------------------
     const bool hist_ok = k <= 8 && !aa;
     const size_t entry = kmu::pmh3a_entry_bytes(key64);
+    // long sequences over a small key space go to the one-pass kernel (kmu_pmh3a_direct.cu): they are the prefix
+    // of the processing order made of the octaves >= DIRECT_MIN_OCT
+    constexpr int DIRECT_MIN_OCT = 11;  // at least 2048 k-mers
+    const bool direct_ok = !key64 && !aa && k <= 8 && kmu::pmh3a_direct_smem_bytes(k, m) <= SMEM_BUDGET &&
+                           !std::getenv("KMU_NO_DIRECT");
+    uint64_t direct_count = 0;
+    if (direct_ok)
+        for (int oct = 63; oct >= DIRECT_MIN_OCT; --oct)
+            for (int bb = kmu::LEN_BUCKETS - 1 - (oct * 8 + 7); bb <= kmu::LEN_BUCKETS - 1 - oct * 8; ++bb) direct_count += hist[bb];
     std::vector<LaunchClass> classes;
-    for (int oct = 63; oct >= 0; --oct) {
+    for (int oct = direct_ok ? DIRECT_MIN_OCT - 1 : 63; oct >= 0; --oct) {
         // buckets of this octave: keys oct*8 .. oct*8+7  -> bucket index LEN_BUCKETS-1-key
         int b_hi = kmu::LEN_BUCKETS - 1 - (oct * 8 + 7), b_lo = kmu::LEN_BUCKETS - 1 - oct * 8;
         uint64_t cnt = 0;
@@ -1071,6 +1080,46 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
 
     if (classes.size() > 120) return fail(KMU_EINVAL, "too many launch classes");  // work counter 127 is the redo launch's
     int ci = 0;
+    if (phase != 2 && direct_count) {
+        kmu::Pmh3aParams Q = P;
+        Q.order = d_order;
+        Q.first = 0;
+        Q.count = direct_count;
+        Q.work_counter = d_work + 126;
+        Q.regionA_bytes = (uint32_t)std::max<uint64_t>(16, 1ull << (2 * k));
+        Q.slots_smem_bytes = (uint32_t)align_up((uint64_t)m * 20, 16);
+        int variant = 3;
+        if (const char* env = std::getenv("KMU_DIRECT_VARIANT")) variant = std::atoi(env);
+        const int grid = (int)std::min<uint64_t>(direct_count, (uint64_t)ctx->sm_count * kmu::pmh3a_direct_ctas_per_sm(variant));
+        size_t li = ctx->lrec.size();
+        if (ctx->profiling) {
+            while (ctx->lev.size() < 2 * (li + 1)) {
+                cudaEvent_t ev;
+                CUDA_TRY(cudaEventCreate(&ev));
+                ctx->lev.push_back(ev);
+            }
+            cudaEventRecord(ctx->lev[2 * li], st);
+        }
+        CUDA_TRY(kmu::launch_pmh3a_direct(Q, grid, variant, st));
+        if (ctx->profiling) {
+            cudaEventRecord(ctx->lev[2 * li + 1], st);
+            kmu_launch_rec r{};
+            r.mode = 2;  // one-pass kernel
+            r.team_warps = variant < 2 ? 8 : 16;
+            r.teams_per_cta = 1;
+            r.grid = (uint32_t)grid;
+            r.block = variant < 2 ? 256 : 512;
+            r.smem_bytes = (uint32_t)kmu::pmh3a_direct_smem_bytes(k, m);
+            r.nseq = direct_count;
+            r.nk_max = nk_longest;
+            r.counter_idx = 126;
+            for (uint64_t L : b->h_nbases)
+                if (L >= k && L - k + 1 >= (1ull << DIRECT_MIN_OCT)) r.nbases += L;
+            ctx->lrec.push_back(r);
+        }
+        ++launches;
+    }
+    const size_t lrec_base = ctx->lrec.size();
     if (phase != 2)
         for (const LaunchClass& c : classes) {
             int32_t rc = run_class(c, d_order, ci++, true);
@@ -1081,9 +1130,9 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         for (uint64_t L : b->h_nbases) {
             uint64_t nk = L >= k ? L - k + 1 : 0;
             uint64_t pos = cursor[kmu::len_bucket_host(nk)];
-            for (size_t i = 0; i < classes.size() && i < ctx->lrec.size(); ++i)
+            for (size_t i = 0; i < classes.size() && lrec_base + i < ctx->lrec.size(); ++i)
                 if (pos >= classes[i].first && pos < classes[i].first + classes[i].count) {
-                    ctx->lrec[i].nbases += L;
+                    ctx->lrec[lrec_base + i].nbases += L;
                     break;
                 }
         }

@@ -69,6 +69,12 @@ size_t pmh3a_entry_bytes(bool key64);
 cudaError_t launch_pmh3a(const Pmh3aParams& P, bool key64, int mode, int grid, int block, size_t smem,
                          cudaStream_t stream);
 
+// one-pass kernel for long sequences over a small key space (kmu_pmh3a_direct.cu); P.regionA_bytes = 4^k,
+// P.slots_smem_bytes = 20 m rounded to 16, P.memo_fast set, P.order/first/count = the sequences to sketch
+size_t pmh3a_direct_smem_bytes(uint32_t k, uint32_t m);
+int pmh3a_direct_ctas_per_sm(int variant);
+cudaError_t launch_pmh3a_direct(const Pmh3aParams& P, int grid, int variant, cudaStream_t stream);
+
 // ---- batch utilities (kmu_batch.cu) ------------------------------------------------------
 // synthetic packed bases: base j of sequence i = SplitMix64 stream `seed` output first_base[i] + j
 cudaError_t launch_synth_packed(uint8_t* packed, const uint64_t* byte_off, const uint64_t* nbases,

@@ -157,3 +157,39 @@ def test_host_pipeline_with_redo_sequences(engine, oracle, monkeypatch):
         out[:] = 0
         engine.sketch_pmh3a_host(buf, off, nb, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200, out)
         assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("k,m,kind", [(8, 200, kb.HASH_CANON_INVHASH), (8, 512, kb.HASH_CANON_INVHASH),
+                                      (8, 513, kb.HASH_CANON_INVHASH), (7, 100, kb.HASH_IDENTITY_RAW),
+                                      (6, 31, kb.HASH_CANON_RAW), (4, 16, kb.HASH_INVHASH)])
+def test_one_pass_kernel_long_reads(engine, oracle, k, m, kind):
+    # sequences with >= 2048 k-mers over <= 4^8 keys take the one-pass kernel (kmu_pmh3a_direct.cu); lengths straddle
+    # its lower bound, small k gives counts far above 255 (u8 wrap -> flagged -> general kernel)
+    rng = np.random.default_rng(1000 + k)
+    nb = np.concatenate([[2047 + k - 1, 2048 + k - 1, 2049 + k - 1], rng.integers(2000, 2200, 40),
+                         rng.integers(2200, 12000, 150), rng.integers(12000, 90000, 30), [300000]])
+    check_config(engine, oracle, 300 + k, nb, k, kb.KMER32, kind, m)
+
+
+def test_one_pass_kernel_repeats(engine, oracle, monkeypatch):
+    # tandem repeats inside random context: a few keys with counts 2..300 next to thousands of singletons
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = []
+    for i in range(60):
+        parts = []
+        for _ in range(int(rng.integers(2, 8))):
+            parts.append(acgt[rng.integers(0, 4, int(rng.integers(500, 4000)))].tobytes())
+            unit = acgt[rng.integers(0, 4, int(rng.integers(1, 40)))].tobytes()
+            parts.append(unit * int(rng.integers(2, 120)))
+        seqs.append(b"".join(parts))
+    batch, bad = engine.batch_from_ascii(seqs)
+    assert bad.sum() == 0
+    packed, off, nb = batch.download()
+    want = oracle.sketch_pmh3a_batch(np.concatenate([packed, np.zeros(64, np.uint8)]), off, nb, 8, kb.KMER32,
+                                     kb.HASH_CANON_INVHASH, 200)
+    got = engine.sketch_pmh3a(batch, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200)
+    assert np.array_equal(got, want)
+    monkeypatch.setenv("KMU_NO_DIRECT", "1")  # the general kernel alone gives the same
+    got2 = engine.sketch_pmh3a(batch, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200)
+    assert np.array_equal(got2, want)
