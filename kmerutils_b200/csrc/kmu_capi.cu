@@ -1088,7 +1088,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         Q.work_counter = d_work + 126;
         Q.regionA_bytes = (uint32_t)std::max<uint64_t>(16, 1ull << (2 * k));
         Q.slots_smem_bytes = (uint32_t)align_up((uint64_t)m * 20, 16);
-        int variant = 3;
+        int variant = 5;
         if (const char* env = std::getenv("KMU_DIRECT_VARIANT")) variant = std::atoi(env);
         const int grid = (int)std::min<uint64_t>(direct_count, (uint64_t)ctx->sm_count * kmu::pmh3a_direct_ctas_per_sm(variant));
         size_t li = ctx->lrec.size();
@@ -1105,10 +1105,10 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
             cudaEventRecord(ctx->lev[2 * li + 1], st);
             kmu_launch_rec r{};
             r.mode = 2;  // one-pass kernel
-            r.team_warps = variant < 2 ? 8 : 16;
+            r.team_warps = variant < 2 ? 8 : (variant == 4 || variant >= 6 ? 12 : 16);
             r.teams_per_cta = 1;
             r.grid = (uint32_t)grid;
-            r.block = variant < 2 ? 256 : 512;
+            r.block = variant < 2 ? 256 : (variant == 4 || variant >= 6 ? 384 : 512);
             r.smem_bytes = (uint32_t)kmu::pmh3a_direct_smem_bytes(k, m);
             r.nseq = direct_count;
             r.nk_max = nk_longest;

@@ -53,6 +53,6 @@ for r in rows:
 for fn, (ti, ts) in tot.items():
     print(f"== {fn}: {ti} warp instructions, {ts} samples")
     items = [(k, v) for k, v in agg.items() if k[0] == fn]
-    items.sort(key=lambda kv: -kv[1][0])
+    items.sort(key=lambda kv: -kv[1][2 if "--by-samples" in sys.argv else 0])
     for (f, file, line), (inst, tinst, samp, text) in items[:top]:
         print(f"{100*inst/ti:5.1f}% inst {100*samp/max(ts,1):5.1f}% smp  thr/inst {tinst/max(inst,1):4.1f}  {file}:{line}  {text}")
