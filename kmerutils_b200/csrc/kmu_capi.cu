@@ -909,19 +909,27 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     // ---- launch classes: one per octave of the k-mer count ------------------------------
     const bool hist_ok = k <= 8 && !aa;
     const size_t entry = kmu::pmh3a_entry_bytes(key64);
-    // long sequences over a small key space go to the one-pass kernel (kmu_pmh3a_direct.cu): they are the prefix
-    // of the processing order made of the octaves >= DIRECT_MIN_OCT
-    constexpr int DIRECT_MIN_OCT = 11;  // at least 2048 k-mers
+    // sequences over a small key space go to the one-pass kernel (kmu_pmh3a_direct.cu): the prefix of the
+    // processing order made of the length classes >= key_long takes its long-sequence form (one point per
+    // occurrence), the classes [key_short, key_long) that follow its short-sequence form (two points)
+    // (boundaries in length-class keys, 8 per octave of the k-mer count: key = 8 * octave + next three bits)
+    int key_long = 11 * 8;       // at least 2048 k-mers
+    int key_short = 9 * 8 + 4;   // at least 768 k-mers: below that nearly every item needs a third point
+    if (const char* env = std::getenv("KMU_DIRECT_KEYS")) std::sscanf(env, "%d,%d", &key_long, &key_short);
+    key_short = std::min(key_short, key_long);
     const bool direct_ok = !key64 && !aa && k <= 8 && kmu::pmh3a_direct_smem_bytes(k, m) <= SMEM_BUDGET &&
                            !std::getenv("KMU_NO_DIRECT");
-    uint64_t direct_count = 0;
-    if (direct_ok)
-        for (int oct = 63; oct >= DIRECT_MIN_OCT; --oct)
-            for (int bb = kmu::LEN_BUCKETS - 1 - (oct * 8 + 7); bb <= kmu::LEN_BUCKETS - 1 - oct * 8; ++bb) direct_count += hist[bb];
+    if (!direct_ok) key_long = key_short = kmu::LEN_BUCKETS;
+    uint64_t direct_count = 0, direct_short_count = 0;
+    for (int key = kmu::LEN_BUCKETS - 1; key >= key_short; --key)
+        (key >= key_long ? direct_count : direct_short_count) += hist[kmu::LEN_BUCKETS - 1 - key];
+    const uint64_t nk_long = kmu::len_bucket_min_nk(kmu::LEN_BUCKETS - 1 - std::min(key_long, kmu::LEN_BUCKETS - 1));
+    const uint64_t nk_short = kmu::len_bucket_min_nk(kmu::LEN_BUCKETS - 1 - std::min(key_short, kmu::LEN_BUCKETS - 1));
     std::vector<LaunchClass> classes;
-    for (int oct = direct_ok ? DIRECT_MIN_OCT - 1 : 63; oct >= 0; --oct) {
-        // buckets of this octave: keys oct*8 .. oct*8+7  -> bucket index LEN_BUCKETS-1-key
-        int b_hi = kmu::LEN_BUCKETS - 1 - (oct * 8 + 7), b_lo = kmu::LEN_BUCKETS - 1 - oct * 8;
+    for (int oct = std::min(63, (key_short - 1) / 8); oct >= 0 && key_short > 0; --oct) {
+        // buckets of this octave: keys oct*8 .. oct*8+7 (below key_short)  -> bucket index LEN_BUCKETS-1-key
+        const int top_key = std::min(oct * 8 + 7, key_short - 1);
+        int b_hi = kmu::LEN_BUCKETS - 1 - top_key, b_lo = kmu::LEN_BUCKETS - 1 - oct * 8;
         uint64_t cnt = 0;
         for (int bb = b_hi; bb <= b_lo; ++bb) cnt += hist[bb];
         if (!cnt) continue;
@@ -980,14 +988,14 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     CUDA_TRY(overflow.reserve(sizeof(uint32_t) * (nseq + 1)));
     P.overflow_count = d_ovf_count;
     P.overflow_list = (uint32_t*)overflow.p;
-    // first point of every possible pre-key when the key space is small (u32 key types, k <= 10):
-    // built once per (k, type, hash, m) and kept in the context (16 B per key, L2 resident)
+    // first and second point of every possible pre-key when the key space is small (u32 key types, k <= 10):
+    // built once per (k, type, hash, m) and kept in the context (2 x 16 B per key, L2 resident)
     P.memo_fast = nullptr;
     if (!key64 && !aa && 2 * k <= 20) {
         const uint32_t nkeys = 1u << (2 * k);
         if (!(ctx->memo.p && ctx->memo_k == k && ctx->memo_m == m && ctx->memo_type == kmer_type &&
               ctx->memo_hash == hash_kind)) {
-            CUDA_TRY(ctx->memo.reserve((size_t)nkeys * 16));
+            CUDA_TRY(ctx->memo.reserve((size_t)nkeys * 32));
             CUDA_TRY(kmu::launch_pmh3a_memo(P, ctx->memo.p, nkeys, st));
             ++launches;
             ctx->memo_k = k;
@@ -1078,19 +1086,22 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         return KMU_OK;
     };
 
-    if (classes.size() > 120) return fail(KMU_EINVAL, "too many launch classes");  // work counter 127 is the redo launch's
+    if (classes.size() > 120) return fail(KMU_EINVAL, "too many launch classes");  // work counters 125, 126: one-pass launches, 127: redo launch
     int ci = 0;
-    if (phase != 2 && direct_count) {
+    for (int form = 0; form < 2 && phase != 2; ++form) {  // 0: long sequences, 1: short sequences
+        const uint64_t count = form == 0 ? direct_count : direct_short_count;
+        if (!count) continue;
         kmu::Pmh3aParams Q = P;
         Q.order = d_order;
-        Q.first = 0;
-        Q.count = direct_count;
-        Q.work_counter = d_work + 126;
+        Q.first = form == 0 ? 0 : (uint32_t)direct_count;
+        Q.count = count;
+        Q.work_counter = d_work + 126 - form;
+        Q.phase_clocks = ctx->profiling ? d_phase + 8 * (126 - form) : nullptr;
         Q.regionA_bytes = (uint32_t)std::max<uint64_t>(16, 1ull << (2 * k));
         Q.slots_smem_bytes = (uint32_t)align_up((uint64_t)m * 20, 16);
-        int variant = 5;
-        if (const char* env = std::getenv("KMU_DIRECT_VARIANT")) variant = std::atoi(env);
-        const int grid = (int)std::min<uint64_t>(direct_count, (uint64_t)ctx->sm_count * kmu::pmh3a_direct_ctas_per_sm(variant));
+        int variant = form;
+        if (const char* env = std::getenv(form == 0 ? "KMU_DIRECT_VARIANT" : "KMU_DIRECT_SHORT_VARIANT")) variant = std::atoi(env);
+        const int grid = (int)std::min<uint64_t>(count, (uint64_t)ctx->sm_count * kmu::pmh3a_direct_ctas_per_sm(variant));
         size_t li = ctx->lrec.size();
         if (ctx->profiling) {
             while (ctx->lev.size() < 2 * (li + 1)) {
@@ -1105,16 +1116,19 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
             cudaEventRecord(ctx->lev[2 * li + 1], st);
             kmu_launch_rec r{};
             r.mode = 2;  // one-pass kernel
-            r.team_warps = variant < 2 ? 8 : (variant == 4 || variant >= 6 ? 12 : 16);
+            r.team_warps = (uint32_t)kmu::pmh3a_direct_threads(variant) / 32;
             r.teams_per_cta = 1;
             r.grid = (uint32_t)grid;
-            r.block = variant < 2 ? 256 : (variant == 4 || variant >= 6 ? 384 : 512);
+            r.block = (uint32_t)kmu::pmh3a_direct_threads(variant);
             r.smem_bytes = (uint32_t)kmu::pmh3a_direct_smem_bytes(k, m);
-            r.nseq = direct_count;
-            r.nk_max = nk_longest;
-            r.counter_idx = 126;
-            for (uint64_t L : b->h_nbases)
-                if (L >= k && L - k + 1 >= (1ull << DIRECT_MIN_OCT)) r.nbases += L;
+            r.nseq = count;
+            r.nk_max = form == 0 ? nk_longest : std::min<uint64_t>(nk_longest, nk_long - 1);
+            r.counter_idx = 126 - form;
+            for (uint64_t L : b->h_nbases) {
+                const uint64_t nk = L >= k ? L - k + 1 : 0;
+                const bool is_long = nk >= nk_long;
+                if (form == 0 ? is_long : (!is_long && nk >= nk_short)) r.nbases += L;
+            }
             ctx->lrec.push_back(r);
         }
         ++launches;
@@ -1183,7 +1197,7 @@ int32_t kmu_sketch_pmh3a(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_
     if (!sig) return fail(KMU_EINVAL, "null signature buffer");
     if (b->nseq >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "more than 2^32-1 sequences in one batch");
     for (uint64_t L : b->h_nbases)
-        if (L >= 0xFFFFFF00ull) return fail(KMU_EINVAL, "a single sequence is limited to 2^32 - 256 bases");
+        if (L >= (1ull << 30)) return fail(KMU_EINVAL, "a single sequence is limited to 2^30 bases here (kmu_sketch_pmh3a_whole has no limit)");
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};
@@ -1237,7 +1251,7 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
     for (uint64_t i = 0; i < nseq; ++i) {
         if (byte_off[i] + (nbases[i] + 3) / 4 > packed_bytes)
             return fail(KMU_EINVAL, "sequence %llu overruns the packed buffer", (unsigned long long)i);
-        if (nbases[i] >= 0xFFFFFF00ull) return fail(KMU_EINVAL, "a single sequence is limited to 2^32 - 256 bases");
+        if (nbases[i] >= (1ull << 30)) return fail(KMU_EINVAL, "a single sequence is limited to 2^30 bases here (kmu_sketch_pmh3a_whole has no limit)");
     }
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);

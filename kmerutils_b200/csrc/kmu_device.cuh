@@ -357,8 +357,11 @@ struct TaskKmers<uint32_t> {
     uint32_t mask, sh0, j0;
     __device__ __forceinline__ void init(const uint32_t* words, uint64_t p0, uint32_t k) {
         const uint32_t* w = words + (p0 >> 4);
-        uint32_t w0 = be32(w[0]), w1 = be32(w[1]);
-        W = ((uint64_t)w0 << 32) | w1;
+        init_loaded(w[0], w[1], p0, k);
+    }
+    // the two words words[p0 >> 4], words[(p0 >> 4) + 1] were loaded by the caller (software pipelining)
+    __device__ __forceinline__ void init_loaded(uint32_t w0_le, uint32_t w1_le, uint64_t p0, uint32_t k) {
+        W = ((uint64_t)be32(w0_le) << 32) | be32(w1_le);
         RC = revcomp_word64(W);
         mask = value_mask<uint32_t>(2 * k);
         sh0 = 64 - 2 * k;

@@ -49,7 +49,7 @@ struct Pmh3aParams {
     uint64_t table_scratch_entries;
     unsigned long long* overflow_count;
     uint32_t* overflow_list;
-    // first point of every pre-key {x bits lo, x bits hi, slot, hashed key} (u32 key types with a
+    // first two points of every pre-key, 2 x {x bits lo, x bits hi, slot, hashed key} (u32 key types with a
     // small key space), or nullptr
     const void* memo_fast;
     // speculative qmax start: B = spec_factor / nk with spec_factor = m ln(m / 1e-4); 0 = off
@@ -73,6 +73,7 @@ cudaError_t launch_pmh3a(const Pmh3aParams& P, bool key64, int mode, int grid, i
 // P.slots_smem_bytes = 20 m rounded to 16, P.memo_fast set, P.order/first/count = the sequences to sketch
 size_t pmh3a_direct_smem_bytes(uint32_t k, uint32_t m);
 int pmh3a_direct_ctas_per_sm(int variant);
+int pmh3a_direct_threads(int variant);
 cudaError_t launch_pmh3a_direct(const Pmh3aParams& P, int grid, int variant, cudaStream_t stream);
 
 // ---- batch utilities (kmu_batch.cu) ------------------------------------------------------

@@ -208,6 +208,8 @@ __device__ __forceinline__ bool first_point_alive(V key, double winv, double qma
 }
 
 constexpr uint32_t QFLAG_SKIP_FIRST = 0x80000000u;  // QItem.cnt: the item's first point is already in the sketch
+constexpr uint32_t QFLAG_SKIP_TWO = 0x40000000u;    // QItem.cnt: so are its first two points
+constexpr uint32_t QFLAG_MASK = QFLAG_SKIP_FIRST | QFLAG_SKIP_TWO;
 
 // --------------------------------------------------------------------------------
 // Process up to 32 queued distinct items with one warp: every lane owns one item and
@@ -225,13 +227,18 @@ __device__ __forceinline__ void process_items(const QItem<V>* queue, uint32_t he
     uint32_t i = 1;
     if (act) {
         QItem<V> it = queue[(head + lane) & (QCAP - 1)];
-        winv = 1.0 / (double)(it.cnt & ~QFLAG_SKIP_FIRST);
+        winv = 1.0 / (double)(it.cnt & ~QFLAG_MASK);
         key = it.key;
         rng.seed(nohash_seed(key));
-        if (it.cnt & QFLAG_SKIP_FIRST) {  // first point applied by the caller: keep the stream aligned
+        if (it.cnt & QFLAG_MASK) {  // first point(s) applied by the caller: keep the stream aligned
             (void)exp01_sample(P.e, rng);
             (void)rng.unif_range(0, P.m, P.slot_thresh);
             i = 2;
+            if (it.cnt & QFLAG_SKIP_TWO) {
+                (void)exp01_sample(P.e, rng);
+                (void)rng.unif_range(0, P.m, P.slot_thresh);
+                i = 3;
+            }
         }
     }
     uint32_t iter = 0;
@@ -505,16 +512,21 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
                 V key = 0;
                 if (cnt) {
                     if (MEMO) {
-                        // first point straight from the per-key table; only an item that may need a
-                        // second point (winv < qmax) goes to the queue
-                        const uint4 e = __ldg((const uint4*)P.memo_fast + (uint32_t)pk);
+                        // first and second point straight from the per-key tables; only an item that may
+                        // need a third point (2 winv < qmax) goes to the queue
+                        const uint4 e = __ldg((const uint4*)P.memo_fast + 2 * (uint32_t)pk);
                         const double winv = cnt < 64 ? s_winv[cnt] : 1.0 / (double)cnt;
+                        const bool second = winv < qmax;
+                        uint4 e2 = make_uint4(0, 0, 0, 0);
+                        if (second) e2 = __ldg((const uint4*)P.memo_fast + 2 * (uint32_t)pk + 1);
                         const double h = __dmul_rn(winv, __hiloint2double((int)e.y, (int)e.x));
                         key = (V)e.w;
-                        if (h < qmax) {
-                            sketch_update(S, e.z, h, (uint64_t)e.w);
-                            cnt = winv < qmax ? (cnt | QFLAG_SKIP_FIRST) : 0u;
-                        } else {
+                        if (h < qmax) sketch_update(S, e.z, h, (uint64_t)e.w);
+                        if (second && cnt < QFLAG_SKIP_TWO) {
+                            const double h2 = __dadd_rn(winv, __dmul_rn(winv, __hiloint2double((int)e2.y, (int)e2.x)));
+                            if (h2 < qmax) sketch_update(S, e2.z, h2, (uint64_t)e.w);
+                            cnt = __dmul_rn(winv, 2.0) < qmax ? (cnt | QFLAG_SKIP_TWO) : 0u;
+                        } else if (!second) {
                             cnt = 0;
                         }
                     } else {
@@ -575,7 +587,8 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_sketch_kernel(const Pmh3aParams
     }
 }
 
-// first point of every pre-key: {x bits lo, x bits hi, slot, hashed key}
+// first two points of every pre-key, one 32-byte sector per key: fast[2 pk] = {x1 bits lo, x1 bits hi, slot1, hashed key},
+// fast[2 pk + 1] = {x2 bits lo, x2 bits hi, slot2, hashed key}
 __global__ void pmh3a_memo_kernel(uint4* fast, uint32_t nkeys, Pmh3aParams P) {
     const uint32_t header = word_header(P.kmer_type, P.k);
     for (uint32_t pk = blockIdx.x * blockDim.x + threadIdx.x; pk < nkeys; pk += gridDim.x * blockDim.x) {
@@ -584,7 +597,10 @@ __global__ void pmh3a_memo_kernel(uint4* fast, uint32_t nkeys, Pmh3aParams P) {
         rng.seed(nohash_seed(key));
         const double x = exp01_sample(P.e, rng);
         const uint32_t s = rng.unif_range(0, P.m, P.slot_thresh);
-        fast[pk] = make_uint4((uint32_t)__double2loint(x), (uint32_t)__double2hiint(x), s, key);
+        fast[2 * pk] = make_uint4((uint32_t)__double2loint(x), (uint32_t)__double2hiint(x), s, key);
+        const double x2 = exp01_sample(P.e, rng);
+        const uint32_t s2 = rng.unif_range(0, P.m, P.slot_thresh);
+        fast[2 * pk + 1] = make_uint4((uint32_t)__double2loint(x2), (uint32_t)__double2hiint(x2), s2, key);
     }
 }
 

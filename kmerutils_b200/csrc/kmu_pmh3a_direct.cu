@@ -1,27 +1,28 @@
-// kmu_pmh3a_direct.cu -- ProbMinHash3a for long sequences over a small key space (u32 k-mers, k <= 8), one pass.
+// kmu_pmh3a_direct.cu -- ProbMinHash3a over a small key space (u32 k-mers, k <= 8), one pass over the sequence.
 //
-// Same result as pmh3a_sketch_kernel (kmu_pmh3a.cu); different organisation.  The first point of an item is
-// h = x(key) / count with (x, slot) a function of the key only (per-key memo table).  Every k-mer OCCURRENCE raises
-// the key's counter in the shared-memory histogram and offers x / (new count) to the key's slot: the last occurrence
-// offers the true first point, the earlier offers are larger and harmless.  During the pass a slot is one 64-bit
-// word, the top 48 bits of its smallest offer over the 16-bit index of the key that made it (64-bit CAS, entered
-// only by offers below the current value).  After the pass each slot recomputes x / count of the key it names, which
-// restores the low bits; two offers of different keys with the same top 48 bits are seen as a tie and the sequence
-// is flagged.  A later point of an item is >= 1 / count, so only items with 1 / count < q1 (q1 = largest
-// slot value) can still matter; one scan of the histogram -- the same sweep that wipes it -- lists them and they draw
-// their later points from their own Xoshiro256++ stream with the usual 128-bit slot updates.  There is no second walk
-// over the sequence.  Flagged sequences (tie, race, wrapped u8 counter, too many items) are redone by the general
+// Same result as pmh3a_sketch_kernel (kmu_pmh3a.cu); different organisation.  Point i of an item is
+// h_i = (i - 1 + x_i(key)) / count with (x_i, slot_i) a function of the key only; the per-key memo table holds the
+// first two.  Every k-mer OCCURRENCE raises the key's counter in the shared-memory histogram and offers its first NP
+// points (NP = 1 for long sequences, 2 for short ones) computed with the NEW count to their slots: the last occurrence
+// offers the true points, the earlier offers are larger and harmless.  During the pass a slot is one 64-bit word: the
+// top 47 bits of its smallest offer, the point index, the 16-bit index of the key that made it (64-bit CAS, entered
+// only by offers below the current value).  After the pass each slot recomputes the point it names from the final
+// count, which restores the low bits; two offers with the same top 47 bits are seen as a tie and the sequence is
+// flagged.  Point NP + 1 of an item is >= NP / count, so only items with NP / count < q1 (q1 = largest slot value) can
+// still matter: they are listed -- by one scan of the histogram, the sweep that wipes it (long sequences), or from
+// the keys whose count reached 2 during the pass (short sequences) -- and draw their later points from their own
+// Xoshiro256++ stream with the usual 128-bit slot updates.  There is no second walk over the sequence.  Flagged
+// sequences (tie, wrapped u8 counter, too many items, every item needs later points) are redone by the general
 // kernel.
 #include <cstdint>
-#include <cstdio>
 
 #include "kmu_device.cuh"
 #include "kmu_kernels.h"
 
 namespace kmu {
 
-constexpr uint32_t DIRECT_T = 8;          // positions per task
-constexpr uint32_t DIRECT_ITEMS = 1024;   // items that draw later points
+constexpr uint32_t DIRECT_ITEMS = 1024;  // items that draw later points
+constexpr uint32_t DIRECT_LIST2 = 1024;  // keys whose count reached 2 (short sequences)
 
 struct DirectWork {
     uint64_t byte_off;
@@ -29,12 +30,12 @@ struct DirectWork {
 };
 struct DirectState {
     unsigned long long qbits;  // largest slot value after the pass (bit pattern)
-    uint32_t flag, cmax, nitems, pad;
+    uint32_t flag, cmax, nitems, n2;
 };
 struct DirectShared {
-    DirectWork work[2];   // [parity of the sequence's turn]: fetched one turn ahead
+    DirectWork work[2];  // [parity of the sequence's turn]: fetched one turn ahead
     DirectState st[2];
-    double winv[256];     // 1 / count
+    double winv[256];    // 1 / count
 };
 
 __device__ __forceinline__ bool direct_update(Slot* slots, uint32_t* hi, uint32_t s, double h, uint32_t key) {
@@ -57,19 +58,32 @@ __device__ __forceinline__ void direct_fetch(const Pmh3aParams& P, DirectWork* w
     }
 }
 
-// an offer that may lower its slot (rare): 64-bit CAS; equal top 48 bits with another key -> tie
+// pass slot word: h bits 63..17 | point index (bit 16) | key index
+__device__ __forceinline__ unsigned long long direct_word(double h, uint32_t pt, uint32_t pk) {
+    return ((unsigned long long)__double_as_longlong(h) & ~0x1FFFFULL) | (pt << 16) | pk;
+}
+
+// an offer that may lower its slot (rare): 64-bit CAS; equal top 47 bits with another offer -> tie
 __device__ __forceinline__ bool direct_offer_slow(unsigned long long* slot, unsigned long long mine) {
     unsigned long long cur = *(volatile unsigned long long*)slot;
     while (mine < cur) {
-        if (((mine ^ cur) >> 16) == 0) break;
+        if (((mine ^ cur) >> 17) == 0) break;
         const unsigned long long seen = atomicCAS(slot, cur, mine);
         if (seen == cur) break;
         cur = seen;
     }
-    return ((mine ^ cur) >> 16) == 0 && mine != cur;
+    return ((mine ^ cur) >> 17) == 0 && mine != cur;
 }
 
-template <int NT, int MINB, bool SPLIT>
+// point pt (0, 1) of an item from its memo entry {x lo, x hi, slot, key} and 1 / count
+__device__ __forceinline__ double direct_point(const uint4& e, uint32_t pt, double winv) {
+    const double wx = __dmul_rn(winv, __hiloint2double((int)e.y, (int)e.x));
+    return pt ? __dadd_rn(winv, wx) : wx;  // base of point 2 = winv * 1
+}
+
+// NT threads per sequence, T positions per task, NP memoised points offered per occurrence, LIST: the items that
+// may need later points come from the keys seen twice (else from a scan of the histogram)
+template <int NT, int MINB, int T, int NP, bool LIST>
 __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t m = P.m, k = P.k;
@@ -77,8 +91,9 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
     Slot* slots = (Slot*)(smem + P.regionA_bytes);
     uint32_t* hi = (uint32_t*)(smem + P.regionA_bytes + (size_t)m * 16);
     uint32_t* items = (uint32_t*)(smem + P.regionA_bytes + P.slots_smem_bytes);  // pk | count << 16
-    unsigned long long* best = (unsigned long long*)items;  // during the pass, per slot: top 48 bits of the lowest offer | key index
-    DirectShared* ds = (DirectShared*)(items + DIRECT_ITEMS);
+    unsigned long long* best = (unsigned long long*)items;  // during the pass, per slot: the lowest offer (direct_word)
+    uint16_t* list2 = (uint16_t*)(items + DIRECT_ITEMS);
+    DirectShared* ds = (DirectShared*)(list2 + DIRECT_LIST2);
     const double* s_winv = ds->winv;
     const int tid = threadIdx.x, lane = tid & 31;
     for (uint32_t j = tid; j < 256; j += NT) ds->winv[j] = j ? 1.0 / (double)j : 0.0;
@@ -89,9 +104,19 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
         ds->st[0] = DirectState{0, 0, 0, 0, 0};
     }
     const bool canonical = hash_is_canonical(P.hash_kind);
-    const uint4* memo = (const uint4*)P.memo_fast;
+    const uint4* memo = (const uint4*)P.memo_fast;  // [2 pk] first point, [2 pk + 1] second point
     __syncthreads();
 
+    // optional phase timing (profiling runs only): thread 0 accumulates clock deltas.
+    // 0 pass, 1 wait for the slowest thread of the pass, 2 slots + q1, 3 sweep, 4 later points, 5 output
+    long long t_mark = P.phase_clocks && tid == 0 ? clock64() : 0;
+    auto mark = [&](int phase) {
+        if (P.phase_clocks && tid == 0) {
+            const long long now = clock64();
+            atomicAdd(P.phase_clocks + phase, (unsigned long long)(now - t_mark));
+            t_mark = now;
+        }
+    };
     for (uint32_t turn = 0;; ++turn) {
         const DirectWork* wk = &ds->work[turn & 1];
         DirectState* st = &ds->st[turn & 1];
@@ -103,55 +128,63 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
         unsigned long long ticket = 0;
         if (tid == NT - 1) ticket = atomicAdd(P.work_counter, 1ULL);
 
-        // ---- the pass: count, offer first points.  Tasks of tlen <= 8 consecutive positions, thread-interleaved;
-        //      tlen is chosen so that the last round of tasks is nearly full ----
+        // ---- the pass: count, offer the memoised points.  Tasks of tlen <= T consecutive positions,
+        //      thread-interleaved; tlen is chosen so that the last round of tasks is nearly full ----
         uint32_t mymax = 0;
         bool bad = false;
-        const uint32_t rounds = (nk + NT * DIRECT_T - 1) / (NT * DIRECT_T);
+        const uint32_t rounds = (nk + NT * T - 1) / (NT * T);
         const uint32_t tlen = rounds ? (nk + NT * rounds - 1) / (NT * rounds) : 1;
         for (uint32_t p0 = tid * tlen; p0 < nk; p0 += NT * tlen) {
             const uint32_t nv = min(tlen, nk - p0);
             TaskKmers<uint32_t> tk;
             tk.init(words, p0, k);
-            uint32_t pk[DIRECT_T], old[DIRECT_T], xlo[DIRECT_T], xhi[DIRECT_T], sl[DIRECT_T];
+            uint32_t pk[T];
+            uint4 e1[T], e2[T];
 #pragma unroll
-            for (uint32_t t = 0; t < DIRECT_T; ++t) {
+            for (uint32_t t = 0; t < T; ++t) {
                 pk[t] = tk.get(t, canonical);
-                if (t < nv) {  // eight independent L2 lookups in flight
-                    const uint4 e = __ldg(memo + pk[t]);
-                    xlo[t] = e.x;
-                    xhi[t] = e.y;
-                    sl[t] = e.z;
+                if (t < nv) {  // independent L2 lookups in flight (both points sit in one 32-byte sector)
+                    e1[t] = __ldg(memo + 2 * pk[t]);
+                    if (NP == 2) e2[t] = __ldg(memo + 2 * pk[t] + 1);
                 }
             }
-            if (SPLIT) {
 #pragma unroll
-                for (uint32_t t = 0; t < DIRECT_T; ++t)
-                    if (t < nv) old[t] = atomicAdd((uint32_t*)hist + (pk[t] >> 2), 1u << ((pk[t] & 3u) * 8));
-            }
-#pragma unroll
-            for (uint32_t t = 0; t < DIRECT_T; ++t) {
+            for (uint32_t t = 0; t < T; ++t) {
                 if (t < nv) {
-                    if (!SPLIT) old[t] = atomicAdd((uint32_t*)hist + (pk[t] >> 2), 1u << ((pk[t] & 3u) * 8));
-                    const uint32_t cn = ((old[t] >> ((pk[t] & 3u) * 8)) & 0xFFu) + 1;  // 256: the u8 counter wrapped
+                    const uint32_t sh = (pk[t] & 3u) * 8;
+                    const uint32_t old = atomicAdd((uint32_t*)hist + (pk[t] >> 2), 1u << sh);
+                    const uint32_t cn = ((old >> sh) & 0xFFu) + 1;  // 256: the u8 counter wrapped
                     mymax = cn > mymax ? cn : mymax;
-                    const double h = __dmul_rn(s_winv[cn & 0xFFu], __hiloint2double((int)xhi[t], (int)xlo[t]));
-                    unsigned long long* slot = best + sl[t];
-                    if ((uint32_t)__double2hiint(h) <= ((volatile uint32_t*)slot)[1])
-                        bad |= direct_offer_slow(slot, ((unsigned long long)__double_as_longlong(h) & ~0xFFFFULL) | pk[t]);
+                    if (LIST && cn == 2) {
+                        const uint32_t pos = atomicAdd(&st->n2, 1u);
+                        if (pos < DIRECT_LIST2) list2[pos] = (uint16_t)pk[t];
+                    }
+                    const double winv = s_winv[cn & 0xFFu];
+                    {
+                        const double h = direct_point(e1[t], 0, winv);
+                        unsigned long long* slot = best + e1[t].z;
+                        if ((uint32_t)__double2hiint(h) <= ((volatile uint32_t*)slot)[1]) bad |= direct_offer_slow(slot, direct_word(h, 0, pk[t]));
+                    }
+                    if (NP == 2) {
+                        const double h = direct_point(e2[t], 1, winv);
+                        unsigned long long* slot = best + e2[t].z;
+                        if ((uint32_t)__double2hiint(h) <= ((volatile uint32_t*)slot)[1]) bad |= direct_offer_slow(slot, direct_word(h, 1, pk[t]));
+                    }
                 }
             }
         }
         mymax = __reduce_max_sync(0xFFFFFFFFu, mymax);
         if (lane == 0 && mymax) atomicMax(&st->cmax, mymax);
         if (bad || mymax > 255) st->flag = 1;
+        mark(0);
         __syncthreads();
+        mark(1);
         if (tid == NT - 1) {
             direct_fetch(P, &ds->work[(turn + 1) & 1], ticket);
             ds->st[(turn + 1) & 1] = DirectState{0, 0, 0, 0, 0};
         }
 
-        // ---- slots: recompute the winner's first point (restores the low bits), q1 ----
+        // ---- slots: recompute the winning point (restores the low bits), q1 ----
         {
             unsigned long long mx = 0;
             for (uint32_t j = tid; j < m; j += NT) {
@@ -159,12 +192,11 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
                 unsigned long long hbits = F64_MAX_BITS;
                 uint32_t key = 0;
                 if (b != ~0ULL) {
-                    const uint32_t pkey = (uint32_t)b & 0xFFFFu;
-                    const uint4 ee = __ldg(memo + pkey);
+                    const uint32_t pkey = (uint32_t)b & 0xFFFFu, pt = ((uint32_t)b >> 16) & 1u;
+                    const uint4 ee = __ldg(memo + 2 * pkey + pt);
                     const uint32_t cnt = hist[pkey];
-                    const double h = __dmul_rn(s_winv[cnt], __hiloint2double((int)ee.y, (int)ee.x));
-                    hbits = (unsigned long long)__double_as_longlong(h);
-                    if (cnt == 0 || ee.z != j || ((hbits ^ b) >> 16) != 0) st->flag = 3;
+                    hbits = (unsigned long long)__double_as_longlong(direct_point(ee, pt, s_winv[cnt]));
+                    if (cnt == 0 || ee.z != j || ((hbits ^ b) >> 17) != 0) st->flag = 3;
                     key = ee.w;
                 }
                 hi[j] = (uint32_t)(hbits >> 32);
@@ -178,23 +210,26 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
             }
         }
         __syncthreads();
+        mark(2);
         const double q1 = __longlong_as_double((long long)st->qbits);
         const uint32_t cmax = st->cmax;
-        // smallest count whose items may place a later point: 1 / c < q1
-        uint32_t cneed = q1 > 1.0 ? 1u : (q1 < 1.0 / 256.0 ? 256u : min(256u, (uint32_t)(1.0 / q1)));
-        while (cneed > 1 && s_winv[cneed - 1] < q1) --cneed;
-        while (cneed < 256 && !(s_winv[cneed] < q1)) ++cneed;
+        // smallest count whose items may place point NP + 1: NP / c < q1
+        const double np = (double)NP;
+        uint32_t cneed = q1 > np ? 1u : (q1 < np / 256.0 ? 256u : min(256u, (uint32_t)(np / q1)));
+        while (cneed > 1 && __dmul_rn(s_winv[cneed - 1], np) < q1) --cneed;
+        while (cneed < 256 && !(__dmul_rn(s_winv[cneed], np) < q1)) ++cneed;
         const bool later = st->flag == 0 && nk && cmax >= cneed;
         const bool scan = later && cneed >= 2 && cneed < 256;
         if (later && !scan && tid == 0) st->flag = 2;  // every item needs later points: general kernel
 
-        // ---- one sweep over the histogram: list the items with count >= cneed, wipe ----
-        {
-            const uint32_t need4 = cneed * 0x01010101u;
-            for (uint32_t j = tid; j < P.regionA_bytes / 16; j += NT) {
-                const uint4 v = ((uint4*)hist)[j];
-                ((uint4*)hist)[j] = make_uint4(0, 0, 0, 0);
-                if (scan) {
+        // ---- the items with count >= cneed.  Scan: one sweep over the histogram lists them and wipes it ----
+        if (!LIST) {
+            if (scan) {
+                const uint32_t need4 = cneed * 0x01010101u;
+#pragma unroll 2
+                for (uint32_t j = tid; j < P.regionA_bytes / 16; j += NT) {
+                    const uint4 v = ((uint4*)hist)[j];
+                    ((uint4*)hist)[j] = make_uint4(0, 0, 0, 0);
                     const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (uint32_t w = 0; w < 4; ++w) {
@@ -207,24 +242,43 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
                         }
                     }
                 }
+            } else {
+#pragma unroll 4
+                for (uint32_t j = tid; j < P.regionA_bytes / 16; j += NT) ((uint4*)hist)[j] = make_uint4(0, 0, 0, 0);
             }
+            __syncthreads();
         }
-        __syncthreads();
+        mark(3);
         if (scan) {
-            const uint32_t nitems = st->nitems;
-            if (nitems > DIRECT_ITEMS) {
+            const uint32_t nitems = LIST ? st->n2 : st->nitems;
+            if (nitems > (LIST ? DIRECT_LIST2 : DIRECT_ITEMS)) {
                 if (tid == 0) st->flag = 4;
             } else {
                 for (uint32_t i = tid; i < nitems; i += NT) {
-                    const uint32_t it = items[i];
-                    const uint32_t cnt = it >> 16;
-                    const uint32_t key = __ldg(memo + (it & 0xFFFFu)).w;
+                    uint32_t pkey, cnt;
+                    if (LIST) {
+                        pkey = list2[i];
+                        cnt = hist[pkey];
+                        if (cnt < cneed) continue;
+                    } else {
+                        pkey = items[i] & 0xFFFFu;
+                        cnt = items[i] >> 16;
+                    }
                     const double winv = s_winv[cnt];
-                    Xoshiro256pp rng;
+                    const uint4 ee = __ldg(memo + 2 * pkey + 1);  // the item's second point
+                    const uint32_t key = ee.w;
+                    if (NP == 1) {
+                        const double h2 = direct_point(ee, 1, winv);
+                        if (h2 < q1) direct_update(slots, hi, ee.z, h2, key);
+                        if (!(__dmul_rn(winv, 2.0) < q1)) continue;
+                    }
+                    Xoshiro256pp rng;  // third point on: the key's own stream, aligned past the two memoised points
                     rng.seed(nohash_seed(key));
-                    (void)exp01_sample(P.e, rng);  // the first point was offered from the memo: keep the stream aligned
+                    (void)exp01_sample(P.e, rng);
                     (void)rng.unif_range(0, m, P.slot_thresh);
-                    for (uint32_t ip = 2;; ++ip) {
+                    (void)exp01_sample(P.e, rng);
+                    (void)rng.unif_range(0, m, P.slot_thresh);
+                    for (uint32_t ip = 3;; ++ip) {
                         const double base = __dmul_rn(winv, (double)(ip - 1));
                         if (!(base < q1)) break;
                         const double x = exp01_sample(P.e, rng);
@@ -235,6 +289,11 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
                 }
             }
             __syncthreads();
+            mark(4);
+        }
+        if (LIST) {  // the later points read the counts: wipe afterwards
+#pragma unroll 4
+            for (uint32_t j = tid; j < P.regionA_bytes / 16; j += NT) ((uint4*)hist)[j] = make_uint4(0, 0, 0, 0);
         }
 
         // ---- signature out, or hand the sequence to the general kernel; the pass slots of the next turn ----
@@ -246,6 +305,7 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
         }
         for (uint32_t j = tid; j < m; j += NT) best[j] = ~0ULL;
         __syncthreads();
+        mark(5);
     }
 }
 
@@ -254,12 +314,12 @@ size_t pmh3a_direct_smem_bytes(uint32_t k, uint32_t m) {
     if (hist < 16) hist = 16;
     const size_t slots = (((size_t)m * 20) + 15) & ~(size_t)15;
     if ((size_t)m * 8 > DIRECT_ITEMS * 4) return ~(size_t)0;  // the pass keeps its slots in the item list's space
-    return hist + slots + DIRECT_ITEMS * 4 + sizeof(DirectShared) + 16;
+    return hist + slots + DIRECT_ITEMS * 4 + DIRECT_LIST2 * 2 + sizeof(DirectShared) + 16;
 }
 
-template <int NT, int MINB, bool SPLIT>
+template <int NT, int MINB, int T, int NP, bool LIST>
 static cudaError_t launch_direct_t(const Pmh3aParams& P, int grid, size_t smem, cudaStream_t stream) {
-    auto kern = pmh3a_direct_kernel<NT, MINB, SPLIT>;
+    auto kern = pmh3a_direct_kernel<NT, MINB, T, NP, LIST>;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -270,19 +330,17 @@ static cudaError_t launch_direct_t(const Pmh3aParams& P, int grid, size_t smem, 
     return cudaGetLastError();
 }
 
-// variant: threads x CTAs / SM; 0 = 256 x 3, 1 = 256 x 2, 2 = 512 x 1, 3 = 512 x 2 (64 registers), 4 = 384 x 2, 5 = 3 without the
-// split atomics loop
-int pmh3a_direct_ctas_per_sm(int variant) { return variant == 0 ? 3 : (variant == 2 ? 1 : 2); }
+// variant 0: long sequences (one point per occurrence, histogram scan); 1: short sequences (two points per
+// occurrence, list of the keys seen twice); 2, 3: experiments
+int pmh3a_direct_ctas_per_sm(int variant) { return 2; }
+int pmh3a_direct_threads(int variant) { return variant == 3 ? 256 : 512; }
 cudaError_t launch_pmh3a_direct(const Pmh3aParams& P, int grid, int variant, cudaStream_t stream) {
     const size_t smem = pmh3a_direct_smem_bytes(P.k, P.m);
     switch (variant) {
-        case 0: return launch_direct_t<256, 3, true>(P, grid, smem, stream);
-        case 1: return launch_direct_t<256, 2, true>(P, grid, smem, stream);
-        case 2: return launch_direct_t<512, 1, true>(P, grid, smem, stream);
-        case 3: return launch_direct_t<512, 2, true>(P, grid, smem, stream);
-        case 4: return launch_direct_t<384, 2, true>(P, grid, smem, stream);
-        case 5: return launch_direct_t<512, 2, false>(P, grid, smem, stream);
-        default: return launch_direct_t<384, 2, false>(P, grid, smem, stream);
+        case 0: return launch_direct_t<512, 2, 8, 1, false>(P, grid, smem, stream);
+        case 1: return launch_direct_t<512, 2, 4, 2, true>(P, grid, smem, stream);
+        case 2: return launch_direct_t<512, 2, 4, 2, false>(P, grid, smem, stream);
+        default: return launch_direct_t<256, 2, 8, 2, true>(P, grid, smem, stream);
     }
 }
 
