@@ -36,6 +36,7 @@ struct DirectShared {
     DirectWork work[2];  // [parity of the sequence's turn]: fetched one turn ahead
     DirectState st[2];
     double winv[256];    // 1 / count
+    long long t_mark;    // profiling runs: clock at the last phase mark
 };
 
 __device__ __forceinline__ bool direct_update(Slot* slots, uint32_t* hi, uint32_t s, double h, uint32_t key) {
@@ -109,12 +110,13 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
 
     // optional phase timing (profiling runs only): thread 0 accumulates clock deltas.
     // 0 pass, 1 wait for the slowest thread of the pass, 2 slots + q1, 3 sweep, 4 later points, 5 output
-    long long t_mark = P.phase_clocks && tid == 0 ? clock64() : 0;
+    // (the running mark lives in shared memory: no register is held across the pass for it)
+    if (P.phase_clocks && tid == 0) ds->t_mark = clock64();
     auto mark = [&](int phase) {
         if (P.phase_clocks && tid == 0) {
             const long long now = clock64();
-            atomicAdd(P.phase_clocks + phase, (unsigned long long)(now - t_mark));
-            t_mark = now;
+            atomicAdd(P.phase_clocks + phase, (unsigned long long)(now - ds->t_mark));
+            ds->t_mark = now;
         }
     };
     for (uint32_t turn = 0;; ++turn) {
