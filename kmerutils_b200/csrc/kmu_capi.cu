@@ -1248,11 +1248,17 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
     if (nseq == 0) return KMU_OK;
     if (!sig) return fail(KMU_EINVAL, "null signature buffer");
     if (nseq >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "more than 2^32-1 sequences in one batch");
+    // one pass: bounds, and whether the caller's buffer already is in the batch layout (then its offsets are used as they are)
+    bool same_layout = true;
+    uint64_t total_bytes = 0;
     for (uint64_t i = 0; i < nseq; ++i) {
         if (byte_off[i] + (nbases[i] + 3) / 4 > packed_bytes)
             return fail(KMU_EINVAL, "sequence %llu overruns the packed buffer", (unsigned long long)i);
         if (nbases[i] >= (1ull << 30)) return fail(KMU_EINVAL, "a single sequence is limited to 2^30 bases here (kmu_sketch_pmh3a_whole has no limit)");
+        same_layout &= byte_off[i] == total_bytes;
+        total_bytes += align_up((nbases[i] + 3) / 4, SEQ_ALIGN);
     }
+    same_layout &= packed_bytes >= total_bytes;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);
     const auto t_begin = std::chrono::steady_clock::now();
@@ -1277,27 +1283,34 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
     }
     const size_t vsz = kmer_type == KMU_KMER64 ? 8 : 4;
     // batch layout of the whole input and the chunk boundaries
-    std::vector<uint64_t> lay;
-    const uint64_t total_bytes = layout_offsets(nbases, nseq, lay);
-    bool same_layout = packed_bytes >= total_bytes;
-    for (uint64_t i = 0; i < nseq && same_layout; ++i) same_layout = byte_off[i] == lay[i];
-    // chunk sizes: a small first chunk (the pipeline starts computing early), large middle chunks
-    // (few launch tails), a small last chunk (short drain of the final download)
+    std::vector<uint64_t> lay_own;
+    if (!same_layout) layout_offsets(nbases, nseq, lay_own);
+    const uint64_t* lay = same_layout ? byte_off : lay_own.data();
+    // chunk sizes grow geometrically from a small first chunk: the upload of chunk c + 1 (PCIe, about 1.8 x the
+    // sketching rate) hides behind the sketching of chunk c, so only the first small upload is exposed; large
+    // chunks later (few launch tails); a small last chunk (short drain of the final download)
     uint64_t big = std::max<uint64_t>(64ull << 20, total_bytes / 4);
     uint64_t small = std::max<uint64_t>(8ull << 20, total_bytes / 48);
+    uint64_t first = std::max<uint64_t>(4ull << 20, total_bytes / 128);
+    bool grow = true;
     if (const char* env = std::getenv("KMU_HOST_CHUNK_BYTES")) {  // tests: force many small chunks
         const uint64_t v = std::strtoull(env, nullptr, 10);
-        if (v) big = small = v;
+        if (v) {
+            big = small = first = v;
+            grow = false;
+        }
     }
+    uint64_t next_target = first;
     std::vector<uint64_t> cut{0};
     for (uint64_t i = 0, start = 0; i < nseq; ++i) {
         const uint64_t end = i + 1 < nseq ? lay[i + 1] : total_bytes;
         const uint64_t left = total_bytes - lay[start];
-        uint64_t target = cut.size() == 1 ? small : big;
+        uint64_t target = next_target;
         if (cut.size() > 1 && left > small && left - small < target) target = left - small;  // leave a small tail chunk
         if (end - lay[start] >= target || i + 1 == nseq) {
             cut.push_back(i + 1);
             start = i + 1;
+            if (grow) next_target = std::min<uint64_t>(big, next_target + next_target / 2);
         }
     }
     const size_t nchunks = cut.size() - 1;
