@@ -256,11 +256,11 @@ def main():
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)",
                     "algorithmic_bytes": alg_bytes, "peak_kind": peak_kind,
-                    "kernel": ("pmh3a_direct_kernel (one pass, 512 threads per read)" if dom["mode"] == 2 else
+                    "kernel": ("pmh3a_direct_kernel (one pass, %d threads per read)" % dom["block"] if dom["mode"] == 2 else
                                "pmh3a_sketch_kernel<u32,%s> team_warps=%d" % ("hist" if dom["mode"] == 0 else "table", dom["team_warps"])),
                     "launch_ms": dom["ms"], "launch_bases": dom["nbases"], "launch_reads": dom["nseq"],
                     "share_of_step": dom["ms"] / max(sum(r["ms"] for r in prof), 1e-9),
-                    "note": "instruction-bound (RNG seeding + f64 points per distinct k-mer), see DESIGN.md"}
+                    "note": "latency/instruction-bound shared-memory histogram + per-occurrence offers (two shared atomics and one L2 memo lookup per k-mer), see DESIGN.md"}
     if args.profile:
         for r in prof:
             sys.stderr.write(json.dumps(r) + "\n")

@@ -909,22 +909,26 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     // ---- launch classes: one per octave of the k-mer count ------------------------------
     const bool hist_ok = k <= 8 && !aa;
     const size_t entry = kmu::pmh3a_entry_bytes(key64);
-    // sequences over a small key space go to the one-pass kernel (kmu_pmh3a_direct.cu): the prefix of the
-    // processing order made of the length classes >= key_long takes its long-sequence form (one point per
-    // occurrence), the classes [key_short, key_long) that follow its short-sequence form (two points)
-    // (boundaries in length-class keys, 8 per octave of the k-mer count: key = 8 * octave + next three bits)
-    int key_long = 11 * 8;       // at least 2048 k-mers
-    int key_short = 9 * 8 + 4;   // at least 768 k-mers: below that nearly every item needs a third point
-    if (const char* env = std::getenv("KMU_DIRECT_KEYS")) std::sscanf(env, "%d,%d", &key_long, &key_short);
-    key_short = std::min(key_short, key_long);
+    // sequences over a small key space go to the one-pass kernel (kmu_pmh3a_direct.cu).  Three forms, by length
+    // class (key = 8 * octave of the k-mer count + its next three bits), longest first in the processing order:
+    //   keys >= key_vlong          8-bit counters, one point per occurrence (counts above 15 are likely)
+    //   [key_long, key_vlong)      4-bit counters, one point per occurrence
+    //   [key_short, key_long)      4-bit counters, two points per occurrence
+    int form_key[4] = {kmu::LEN_BUCKETS, 16 * 8 + 4, 11 * 8, 9 * 8 + 4};  // 98304, 2048, 768 k-mers
+    int form_variant[3] = {0, 6, 5};
+    if (const char* env = std::getenv("KMU_DIRECT_KEYS")) std::sscanf(env, "%d,%d,%d", &form_key[1], &form_key[2], &form_key[3]);
+    if (const char* env = std::getenv("KMU_DIRECT_VARIANTS")) std::sscanf(env, "%d,%d,%d", &form_variant[0], &form_variant[1], &form_variant[2]);
+    form_key[2] = std::min(form_key[2], form_key[1]);
+    form_key[3] = std::min(form_key[3], form_key[2]);
     const bool direct_ok = !key64 && !aa && k <= 8 && kmu::pmh3a_direct_smem_bytes(k, m) <= SMEM_BUDGET &&
                            !std::getenv("KMU_NO_DIRECT");
-    if (!direct_ok) key_long = key_short = kmu::LEN_BUCKETS;
-    uint64_t direct_count = 0, direct_short_count = 0;
-    for (int key = kmu::LEN_BUCKETS - 1; key >= key_short; --key)
-        (key >= key_long ? direct_count : direct_short_count) += hist[kmu::LEN_BUCKETS - 1 - key];
-    const uint64_t nk_long = kmu::len_bucket_min_nk(kmu::LEN_BUCKETS - 1 - std::min(key_long, kmu::LEN_BUCKETS - 1));
-    const uint64_t nk_short = kmu::len_bucket_min_nk(kmu::LEN_BUCKETS - 1 - std::min(key_short, kmu::LEN_BUCKETS - 1));
+    if (!direct_ok) form_key[1] = form_key[2] = form_key[3] = kmu::LEN_BUCKETS;
+    const int key_short = form_key[3];
+    uint64_t form_count[3] = {0, 0, 0}, form_nk_min[3];
+    for (int f = 0; f < 3; ++f) {
+        for (int key = form_key[f] - 1; key >= form_key[f + 1]; --key) form_count[f] += hist[kmu::LEN_BUCKETS - 1 - key];
+        form_nk_min[f] = kmu::len_bucket_min_nk(kmu::LEN_BUCKETS - 1 - std::min(form_key[f + 1], kmu::LEN_BUCKETS - 1));
+    }
     std::vector<LaunchClass> classes;
     for (int oct = std::min(63, (key_short - 1) / 8); oct >= 0 && key_short > 0; --oct) {
         // buckets of this octave: keys oct*8 .. oct*8+7 (below key_short)  -> bucket index LEN_BUCKETS-1-key
@@ -1086,21 +1090,21 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         return KMU_OK;
     };
 
-    if (classes.size() > 120) return fail(KMU_EINVAL, "too many launch classes");  // work counters 125, 126: one-pass launches, 127: redo launch
+    if (classes.size() > 120) return fail(KMU_EINVAL, "too many launch classes");  // work counters 124..126: one-pass launches, 127: redo launch
     int ci = 0;
-    for (int form = 0; form < 2 && phase != 2; ++form) {  // 0: long sequences, 1: short sequences
-        const uint64_t count = form == 0 ? direct_count : direct_short_count;
+    uint64_t form_first = 0;
+    for (int form = 0; form < 3 && phase != 2; form_first += form_count[form], ++form) {
+        const uint64_t count = form_count[form];
         if (!count) continue;
         kmu::Pmh3aParams Q = P;
         Q.order = d_order;
-        Q.first = form == 0 ? 0 : (uint32_t)direct_count;
+        Q.first = form_first;
         Q.count = count;
         Q.work_counter = d_work + 126 - form;
         Q.phase_clocks = ctx->profiling ? d_phase + 8 * (126 - form) : nullptr;
-        Q.regionA_bytes = (uint32_t)std::max<uint64_t>(16, 1ull << (2 * k));
+        const int variant = form_variant[form];
+        Q.regionA_bytes = (uint32_t)kmu::pmh3a_direct_hist_bytes(k, variant);
         Q.slots_smem_bytes = (uint32_t)align_up((uint64_t)m * 20, 16);
-        int variant = form;
-        if (const char* env = std::getenv(form == 0 ? "KMU_DIRECT_VARIANT" : "KMU_DIRECT_SHORT_VARIANT")) variant = std::atoi(env);
         const int grid = (int)std::min<uint64_t>(count, (uint64_t)ctx->sm_count * kmu::pmh3a_direct_ctas_per_sm(variant));
         size_t li = ctx->lrec.size();
         if (ctx->profiling) {
@@ -1120,14 +1124,13 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
             r.teams_per_cta = 1;
             r.grid = (uint32_t)grid;
             r.block = (uint32_t)kmu::pmh3a_direct_threads(variant);
-            r.smem_bytes = (uint32_t)kmu::pmh3a_direct_smem_bytes(k, m);
+            r.smem_bytes = (uint32_t)kmu::pmh3a_direct_smem_bytes(k, m, variant);
             r.nseq = count;
-            r.nk_max = form == 0 ? nk_longest : std::min<uint64_t>(nk_longest, nk_long - 1);
+            r.nk_max = form == 0 ? nk_longest : std::min<uint64_t>(nk_longest, form_nk_min[form - 1] - 1);
             r.counter_idx = 126 - form;
             for (uint64_t L : b->h_nbases) {
                 const uint64_t nk = L >= k ? L - k + 1 : 0;
-                const bool is_long = nk >= nk_long;
-                if (form == 0 ? is_long : (!is_long && nk >= nk_short)) r.nbases += L;
+                if (nk >= form_nk_min[form] && (form == 0 || nk < form_nk_min[form - 1])) r.nbases += L;
             }
             ctx->lrec.push_back(r);
         }

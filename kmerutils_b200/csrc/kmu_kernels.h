@@ -71,7 +71,8 @@ cudaError_t launch_pmh3a(const Pmh3aParams& P, bool key64, int mode, int grid, i
 
 // one-pass kernel for long sequences over a small key space (kmu_pmh3a_direct.cu); P.regionA_bytes = 4^k,
 // P.slots_smem_bytes = 20 m rounded to 16, P.memo_fast set, P.order/first/count = the sequences to sketch
-size_t pmh3a_direct_smem_bytes(uint32_t k, uint32_t m);
+size_t pmh3a_direct_smem_bytes(uint32_t k, uint32_t m, int variant = 0);
+size_t pmh3a_direct_hist_bytes(uint32_t k, int variant);
 int pmh3a_direct_ctas_per_sm(int variant);
 int pmh3a_direct_threads(int variant);
 cudaError_t launch_pmh3a_direct(const Pmh3aParams& P, int grid, int variant, cudaStream_t stream);

@@ -84,8 +84,14 @@ __device__ __forceinline__ double direct_point(const uint4& e, uint32_t pt, doub
 
 // NT threads per sequence, T positions per task, NP memoised points offered per occurrence, LIST: the items that
 // may need later points come from the keys seen twice (else from a scan of the histogram)
-template <int NT, int MINB, int T, int NP, bool LIST>
+// HB: bits per histogram counter (8, or 4: half the shared memory, twice the sequences in flight per SM; a
+// count above 15 flags the sequence)
+template <int NT, int MINB, int T, int NP, bool LIST, int HB>
 __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParams P) {
+    constexpr uint32_t CMAX = (1u << HB) - 1;
+    auto hist_count = [](const uint8_t* h, uint32_t pkey) -> uint32_t {
+        return HB == 8 ? (uint32_t)h[pkey] : ((uint32_t)h[pkey >> 1] >> ((pkey & 1u) * 4)) & 15u;
+    };
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t m = P.m, k = P.k;
     uint8_t* hist = smem;
@@ -153,9 +159,9 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
 #pragma unroll
             for (uint32_t t = 0; t < T; ++t) {
                 if (t < nv) {
-                    const uint32_t sh = (pk[t] & 3u) * 8;
-                    const uint32_t old = atomicAdd((uint32_t*)hist + (pk[t] >> 2), 1u << sh);
-                    const uint32_t cn = ((old >> sh) & 0xFFu) + 1;  // 256: the u8 counter wrapped
+                    const uint32_t sh = HB == 8 ? (pk[t] & 3u) * 8 : (pk[t] & 7u) * 4;
+                    const uint32_t old = atomicAdd((uint32_t*)hist + (pk[t] >> (HB == 8 ? 2 : 3)), 1u << sh);
+                    const uint32_t cn = ((old >> sh) & CMAX) + 1;  // CMAX + 1: the counter wrapped
                     mymax = cn > mymax ? cn : mymax;
                     if (LIST && cn == 2) {
                         const uint32_t pos = atomicAdd(&st->n2, 1u);
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
         }
         mymax = __reduce_max_sync(0xFFFFFFFFu, mymax);
         if (lane == 0 && mymax) atomicMax(&st->cmax, mymax);
-        if (bad || mymax > 255) st->flag = 1;
+        if (bad || mymax > CMAX) st->flag = 1;
         mark(0);
         __syncthreads();
         mark(1);
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
                 if (b != ~0ULL) {
                     const uint32_t pkey = (uint32_t)b & 0xFFFFu, pt = ((uint32_t)b >> 16) & 1u;
                     const uint4 ee = __ldg(memo + 2 * pkey + pt);
-                    const uint32_t cnt = hist[pkey];
+                    const uint32_t cnt = hist_count(hist, pkey);
                     hbits = (unsigned long long)__double_as_longlong(direct_point(ee, pt, s_winv[cnt]));
                     if (cnt == 0 || ee.z != j || ((hbits ^ b) >> 17) != 0) st->flag = 3;
                     key = ee.w;
@@ -235,12 +241,26 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
                     const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (uint32_t w = 0; w < 4; ++w) {
-                        uint32_t hit = __vcmpgeu4(wv[w], need4);
-                        while (hit) {
-                            const uint32_t b = (__ffs(hit) - 1) >> 3;
-                            hit &= ~(0xFFu << (b * 8));
-                            const uint32_t pos = atomicAdd(&st->nitems, 1u);
-                            if (pos < DIRECT_ITEMS) items[pos] = (j * 16 + w * 4 + b) | (((wv[w] >> (b * 8)) & 0xFFu) << 16);
+                        if (HB == 8) {
+                            uint32_t hit = __vcmpgeu4(wv[w], need4);
+                            while (hit) {
+                                const uint32_t b = (__ffs(hit) - 1) >> 3;
+                                hit &= ~(0xFFu << (b * 8));
+                                const uint32_t pos = atomicAdd(&st->nitems, 1u);
+                                if (pos < DIRECT_ITEMS) items[pos] = (j * 16 + w * 4 + b) | (((wv[w] >> (b * 8)) & 0xFFu) << 16);
+                            }
+                        } else {
+#pragma unroll
+                            for (uint32_t half = 0; half < 2; ++half) {  // even / odd nibbles as bytes
+                                const uint32_t nib = (wv[w] >> (half * 4)) & 0x0F0F0F0Fu;
+                                uint32_t hit = __vcmpgeu4(nib, need4);
+                                while (hit) {
+                                    const uint32_t b = (__ffs(hit) - 1) >> 3;
+                                    hit &= ~(0xFFu << (b * 8));
+                                    const uint32_t pos = atomicAdd(&st->nitems, 1u);
+                                    if (pos < DIRECT_ITEMS) items[pos] = (j * 32 + w * 8 + b * 2 + half) | (((nib >> (b * 8)) & 0xFFu) << 16);
+                                }
+                            }
                         }
                     }
                 }
@@ -260,7 +280,7 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
                     uint32_t pkey, cnt;
                     if (LIST) {
                         pkey = list2[i];
-                        cnt = hist[pkey];
+                        cnt = hist_count(hist, pkey);
                         if (cnt < cneed) continue;
                     } else {
                         pkey = items[i] & 0xFFFFu;
@@ -311,17 +331,17 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
     }
 }
 
-size_t pmh3a_direct_smem_bytes(uint32_t k, uint32_t m) {
-    size_t hist = (size_t)1 << (2 * k);
-    if (hist < 16) hist = 16;
+size_t pmh3a_direct_hist_bytes(uint32_t k, int variant);
+size_t pmh3a_direct_smem_bytes(uint32_t k, uint32_t m, int variant) {
+    size_t hist = pmh3a_direct_hist_bytes(k, variant);
     const size_t slots = (((size_t)m * 20) + 15) & ~(size_t)15;
     if ((size_t)m * 8 > DIRECT_ITEMS * 4) return ~(size_t)0;  // the pass keeps its slots in the item list's space
     return hist + slots + DIRECT_ITEMS * 4 + DIRECT_LIST2 * 2 + sizeof(DirectShared) + 16;
 }
 
-template <int NT, int MINB, int T, int NP, bool LIST>
+template <int NT, int MINB, int T, int NP, bool LIST, int HB = 8>
 static cudaError_t launch_direct_t(const Pmh3aParams& P, int grid, size_t smem, cudaStream_t stream) {
-    auto kern = pmh3a_direct_kernel<NT, MINB, T, NP, LIST>;
+    auto kern = pmh3a_direct_kernel<NT, MINB, T, NP, LIST, HB>;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -333,16 +353,26 @@ static cudaError_t launch_direct_t(const Pmh3aParams& P, int grid, size_t smem, 
 }
 
 // variant 0: long sequences (one point per occurrence, histogram scan); 1: short sequences (two points per
-// occurrence, list of the keys seen twice); 2, 3: experiments
-int pmh3a_direct_ctas_per_sm(int variant) { return 2; }
-int pmh3a_direct_threads(int variant) { return variant == 3 ? 256 : 512; }
+// occurrence, list of the keys seen twice); 4: as 0 with 4-bit counters, 256 threads, four sequences per SM
+int pmh3a_direct_ctas_per_sm(int variant) { return variant >= 7 ? 5 : (variant >= 4 ? 4 : 2); }
+int pmh3a_direct_threads(int variant) { return variant >= 3 ? 256 : 512; }
+size_t pmh3a_direct_hist_bytes(uint32_t k, int variant) {
+    size_t hist = (size_t)1 << (2 * k);
+    if (variant >= 4) hist /= 2;
+    return hist < 16 ? 16 : hist;
+}
 cudaError_t launch_pmh3a_direct(const Pmh3aParams& P, int grid, int variant, cudaStream_t stream) {
-    const size_t smem = pmh3a_direct_smem_bytes(P.k, P.m);
+    const size_t smem = pmh3a_direct_smem_bytes(P.k, P.m, variant);
     switch (variant) {
         case 0: return launch_direct_t<512, 2, 8, 1, false>(P, grid, smem, stream);
         case 1: return launch_direct_t<512, 2, 4, 2, true>(P, grid, smem, stream);
         case 2: return launch_direct_t<512, 2, 4, 2, false>(P, grid, smem, stream);
-        default: return launch_direct_t<256, 2, 8, 2, true>(P, grid, smem, stream);
+        case 3: return launch_direct_t<256, 2, 8, 2, true>(P, grid, smem, stream);
+        case 4: return launch_direct_t<256, 4, 8, 1, false, 4>(P, grid, smem, stream);
+        case 5: return launch_direct_t<256, 4, 4, 2, true, 4>(P, grid, smem, stream);
+        case 6: return launch_direct_t<256, 4, 4, 1, false, 4>(P, grid, smem, stream);
+        case 7: return launch_direct_t<256, 5, 8, 1, false, 4>(P, grid, smem, stream);
+        default: return launch_direct_t<256, 5, 4, 1, false, 4>(P, grid, smem, stream);
     }
 }
 
