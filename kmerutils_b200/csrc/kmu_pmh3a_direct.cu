@@ -14,6 +14,7 @@
 // Xoshiro256++ stream with the usual 128-bit slot updates.  There is no second walk over the sequence.  Flagged
 // sequences (tie, wrapped u8 counter, too many items, every item needs later points) are redone by the general
 // kernel.
+#include <algorithm>
 #include <cstdint>
 
 #include "kmu_device.cuh"
@@ -21,7 +22,7 @@
 
 namespace kmu {
 
-constexpr uint32_t DIRECT_ITEMS = 1024;  // items that draw later points
+constexpr uint32_t DIRECT_ITEMS = 512;   // items that draw later points (at least; 2 m when that is more: the pass slots live there)
 constexpr uint32_t DIRECT_LIST2 = 1024;  // keys whose count reached 2 (short sequences)
 
 struct DirectWork {
@@ -33,11 +34,12 @@ struct DirectState {
     uint32_t flag, cmax, nitems, n2;
 };
 struct DirectShared {
-    DirectWork work[2];  // [parity of the sequence's turn]: fetched one turn ahead
+    DirectWork work[4];  // [turn & 3]: fetched two turns ahead (the first segment of the next sequence is staged during this one)
     DirectState st[2];
-    double winv[256];    // 1 / count
     long long t_mark;    // profiling runs: clock at the last phase mark
+    long long pad;       // sizeof is a multiple of 16: the reciprocal table and the staging buffers follow
 };
+static_assert(sizeof(DirectShared) % 16 == 0, "staging buffers must be 16-byte aligned");
 
 __device__ __forceinline__ bool direct_update(Slot* slots, uint32_t* hi, uint32_t s, double h, uint32_t key) {
     const uint64_t hbits = (uint64_t)__double_as_longlong(h);
@@ -86,9 +88,13 @@ __device__ __forceinline__ double direct_point(const uint4& e, uint32_t pt, doub
 // may need later points come from the keys seen twice (else from a scan of the histogram)
 // HB: bits per histogram counter (8, or 4: half the shared memory, twice the sequences in flight per SM; a
 // count above 15 flags the sequence)
-template <int NT, int MINB, int T, int NP, bool LIST, int HB>
+// STAGE: bytes per staging buffer (two per CTA): the packed bytes travel global -> shared by TMA bulk copies, one
+// segment of 4 STAGE positions ahead of the pass (0: the pass reads global memory)
+template <int NT, int MINB, int T, int NP, bool LIST, int HB, int STAGE>
 __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParams P) {
     constexpr uint32_t CMAX = (1u << HB) - 1;
+    constexpr uint32_t PS = STAGE * 4;            // positions per segment
+    constexpr uint32_t STAGE_BUF = STAGE + 32;    // segment + halo + the word pair read past the last window
     auto hist_count = [](const uint8_t* h, uint32_t pkey) -> uint32_t {
         return HB == 8 ? (uint32_t)h[pkey] : ((uint32_t)h[pkey >> 1] >> ((pkey & 1u) * 4)) & 15u;
     };
@@ -99,16 +105,34 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
     uint32_t* hi = (uint32_t*)(smem + P.regionA_bytes + (size_t)m * 16);
     uint32_t* items = (uint32_t*)(smem + P.regionA_bytes + P.slots_smem_bytes);  // pk | count << 16
     unsigned long long* best = (unsigned long long*)items;  // during the pass, per slot: the lowest offer (direct_word)
-    uint16_t* list2 = (uint16_t*)(items + DIRECT_ITEMS);
-    DirectShared* ds = (DirectShared*)(list2 + DIRECT_LIST2);
-    const double* s_winv = ds->winv;
+    const uint32_t items_cap = max(DIRECT_ITEMS, 2 * m);
+    uint16_t* list2 = (uint16_t*)(items + items_cap);         // LIST forms only
+    DirectShared* ds = (DirectShared*)(list2 + (LIST ? DIRECT_LIST2 : 0));
+    double* winv_tab = (double*)(ds + 1);                      // [CMAX + 1]: 1 / count
+    uint8_t* stage = (uint8_t*)(winv_tab + CMAX + 1);          // [2][STAGE_BUF]
+    uint64_t* bars = (uint64_t*)(stage + 2 * STAGE_BUF);       // [2] "segment landed"
+    uint32_t buf = 0, parity = 0;                              // staging buffer of the next segment; bit b: phase of bars[b]
+    auto issue = [&](const uint8_t* row, uint32_t nb, uint32_t seg, uint32_t b) {  // one thread
+        const uint32_t row_padded = (((nb + 3) / 4) + 15) & ~15u, off = seg * STAGE;
+        const uint32_t bytes = min((uint32_t)STAGE + 16, row_padded - off);
+        mbar_arrive_expect_tx(&bars[b], bytes);
+        tma_load_bytes(stage + b * STAGE_BUF, row + off, bytes, &bars[b]);
+    };
+    const double* s_winv = winv_tab;
     const int tid = threadIdx.x, lane = tid & 31;
-    for (uint32_t j = tid; j < 256; j += NT) ds->winv[j] = j ? 1.0 / (double)j : 0.0;
+    for (uint32_t j = tid; j <= CMAX; j += NT) winv_tab[j] = j ? 1.0 / (double)j : 0.0;
     for (uint32_t j = tid; j < P.regionA_bytes / 16; j += NT) ((uint4*)hist)[j] = make_uint4(0, 0, 0, 0);
     for (uint32_t j = tid; j < m; j += NT) best[j] = ~0ULL;
     if (tid == 0) {
         direct_fetch(P, &ds->work[0], atomicAdd(P.work_counter, 1ULL));
+        direct_fetch(P, &ds->work[1], atomicAdd(P.work_counter, 1ULL));
         ds->st[0] = DirectState{0, 0, 0, 0, 0};
+        if (STAGE) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            mbar_fence_init();
+            if (ds->work[0].valid && ds->work[0].nbases >= k) issue(P.packed + ds->work[0].byte_off, ds->work[0].nbases, 0, 0);
+        }
     }
     const bool canonical = hash_is_canonical(P.hash_kind);
     const uint4* memo = (const uint4*)P.memo_fast;  // [2 pk] first point, [2 pk + 1] second point
@@ -126,13 +150,13 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
         }
     };
     for (uint32_t turn = 0;; ++turn) {
-        const DirectWork* wk = &ds->work[turn & 1];
+        const DirectWork* wk = &ds->work[turn & 3];
         DirectState* st = &ds->st[turn & 1];
         if (!wk->valid) break;
         const uint32_t seq = wk->seq, L = wk->nbases;
         const uint32_t* words = (const uint32_t*)(P.packed + wk->byte_off);
         const uint32_t nk = L >= k ? L - k + 1 : 0;
-        // next turn's sequence, off the critical path: the ticket is drawn now, its loads wait until after the pass
+        // the sequence after next, off the critical path: the ticket is drawn now, its loads wait until after the pass
         unsigned long long ticket = 0;
         if (tid == NT - 1) ticket = atomicAdd(P.work_counter, 1ULL);
 
@@ -140,20 +164,35 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
         //      thread-interleaved; tlen is chosen so that the last round of tasks is nearly full ----
         uint32_t mymax = 0;
         bool bad = false;
-        const uint32_t rounds = (nk + NT * T - 1) / (NT * T);
-        const uint32_t tlen = rounds ? (nk + NT * rounds - 1) / (NT * rounds) : 1;
-        for (uint32_t p0 = tid * tlen; p0 < nk; p0 += NT * tlen) {
-            const uint32_t nv = min(tlen, nk - p0);
+        const uint32_t nseg = STAGE ? (nk + PS - 1) / PS : 1;
+        for (uint32_t seg = 0; seg < nseg; ++seg) {
+        const uint32_t* seg_words = words;
+        uint32_t seg_nk = nk;
+        if (STAGE) {
+            seg_nk = min(PS, nk - seg * PS);
+            if (tid == NT - 1) {  // the next segment, or the first one of the next sequence, lands while this one is processed
+                const DirectWork* nw = &ds->work[(turn + 1) & 3];
+                if (seg + 1 < nseg) issue((const uint8_t*)words, L, seg + 1, buf ^ 1);
+                else if (nw->valid && nw->nbases >= k) issue(P.packed + nw->byte_off, nw->nbases, 0, buf ^ 1);
+            }
+            mbar_wait(&bars[buf], (parity >> buf) & 1u);
+            parity ^= 1u << buf;
+            seg_words = (const uint32_t*)(stage + buf * STAGE_BUF);
+        }
+        const uint32_t rounds = (seg_nk + NT * T - 1) / (NT * T);
+        const uint32_t tlen = rounds ? (seg_nk + NT * rounds - 1) / (NT * rounds) : 1;
+        for (uint32_t p0 = tid * tlen; p0 < seg_nk; p0 += NT * tlen) {
+            const uint32_t nv = min(tlen, seg_nk - p0);
             TaskKmers<uint32_t> tk;
-            tk.init(words, p0, k);
+            tk.init(seg_words, p0, k);
             uint32_t pk[T];
             uint4 e1[T], e2[T];
 #pragma unroll
             for (uint32_t t = 0; t < T; ++t) {
                 pk[t] = tk.get(t, canonical);
                 if (t < nv) {  // independent L2 lookups in flight (both points sit in one 32-byte sector)
-                    e1[t] = __ldg(memo + 2 * pk[t]);
-                    if (NP == 2) e2[t] = __ldg(memo + 2 * pk[t] + 1);
+                    e1[t] = __ldcg(memo + 2 * pk[t]);  // L2 only: L1 keeps the sequence bytes
+                    if (NP == 2) e2[t] = __ldcg(memo + 2 * pk[t] + 1);
                 }
             }
 #pragma unroll
@@ -167,7 +206,7 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
                         const uint32_t pos = atomicAdd(&st->n2, 1u);
                         if (pos < DIRECT_LIST2) list2[pos] = (uint16_t)pk[t];
                     }
-                    const double winv = s_winv[cn & 0xFFu];
+                    const double winv = s_winv[cn & CMAX];
                     {
                         const double h = direct_point(e1[t], 0, winv);
                         unsigned long long* slot = best + e1[t].z;
@@ -181,6 +220,11 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
                 }
             }
         }
+        if (STAGE) {
+            if (seg + 1 < nseg) __syncthreads();  // everybody is done with this buffer before the segment after next lands in it
+            buf ^= 1;
+        }
+        }
         mymax = __reduce_max_sync(0xFFFFFFFFu, mymax);
         if (lane == 0 && mymax) atomicMax(&st->cmax, mymax);
         if (bad || mymax > CMAX) st->flag = 1;
@@ -188,8 +232,12 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
         __syncthreads();
         mark(1);
         if (tid == NT - 1) {
-            direct_fetch(P, &ds->work[(turn + 1) & 1], ticket);
+            direct_fetch(P, &ds->work[(turn + 2) & 3], ticket);
             ds->st[(turn + 1) & 1] = DirectState{0, 0, 0, 0, 0};
+            if (STAGE && nseg == 0) {  // nothing was staged behind this (empty) sequence: the next one's first segment
+                const DirectWork* nw = &ds->work[(turn + 1) & 3];
+                if (nw->valid && nw->nbases >= k) issue(P.packed + nw->byte_off, nw->nbases, 0, buf);
+            }
         }
 
         // ---- slots: recompute the winning point (restores the low bits), q1 ----
@@ -223,11 +271,12 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
         const uint32_t cmax = st->cmax;
         // smallest count whose items may place point NP + 1: NP / c < q1
         const double np = (double)NP;
-        uint32_t cneed = q1 > np ? 1u : (q1 < np / 256.0 ? 256u : min(256u, (uint32_t)(np / q1)));
+        constexpr uint32_t CNONE = CMAX + 1;  // no count qualifies
+        uint32_t cneed = q1 > np ? 1u : (q1 < np / (double)CNONE ? CNONE : min(CNONE, (uint32_t)(np / q1)));
         while (cneed > 1 && __dmul_rn(s_winv[cneed - 1], np) < q1) --cneed;
-        while (cneed < 256 && !(__dmul_rn(s_winv[cneed], np) < q1)) ++cneed;
+        while (cneed < CNONE && !(__dmul_rn(s_winv[cneed], np) < q1)) ++cneed;
         const bool later = st->flag == 0 && nk && cmax >= cneed;
-        const bool scan = later && cneed >= 2 && cneed < 256;
+        const bool scan = later && cneed >= 2 && cneed < CNONE;
         if (later && !scan && tid == 0) st->flag = 2;  // every item needs later points: general kernel
 
         // ---- the items with count >= cneed.  Scan: one sweep over the histogram lists them and wipes it ----
@@ -247,7 +296,7 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
                                 const uint32_t b = (__ffs(hit) - 1) >> 3;
                                 hit &= ~(0xFFu << (b * 8));
                                 const uint32_t pos = atomicAdd(&st->nitems, 1u);
-                                if (pos < DIRECT_ITEMS) items[pos] = (j * 16 + w * 4 + b) | (((wv[w] >> (b * 8)) & 0xFFu) << 16);
+                                if (pos < items_cap) items[pos] = (j * 16 + w * 4 + b) | (((wv[w] >> (b * 8)) & 0xFFu) << 16);
                             }
                         } else {
 #pragma unroll
@@ -258,7 +307,7 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
                                     const uint32_t b = (__ffs(hit) - 1) >> 3;
                                     hit &= ~(0xFFu << (b * 8));
                                     const uint32_t pos = atomicAdd(&st->nitems, 1u);
-                                    if (pos < DIRECT_ITEMS) items[pos] = (j * 32 + w * 8 + b * 2 + half) | (((nib >> (b * 8)) & 0xFFu) << 16);
+                                    if (pos < items_cap) items[pos] = (j * 32 + w * 8 + b * 2 + half) | (((nib >> (b * 8)) & 0xFFu) << 16);
                                 }
                             }
                         }
@@ -273,7 +322,7 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
         mark(3);
         if (scan) {
             const uint32_t nitems = LIST ? st->n2 : st->nitems;
-            if (nitems > (LIST ? DIRECT_LIST2 : DIRECT_ITEMS)) {
+            if (nitems > (LIST ? DIRECT_LIST2 : items_cap)) {
                 if (tid == 0) st->flag = 4;
             } else {
                 for (uint32_t i = tid; i < nitems; i += NT) {
@@ -332,19 +381,30 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
 }
 
 size_t pmh3a_direct_hist_bytes(uint32_t k, int variant);
+size_t pmh3a_direct_stage_bytes(int variant);
+bool pmh3a_direct_lists(int variant);
+static size_t hist_full(uint32_t k) { return std::max<size_t>(16, (size_t)1 << (2 * k)); }
 size_t pmh3a_direct_smem_bytes(uint32_t k, uint32_t m, int variant) {
     size_t hist = pmh3a_direct_hist_bytes(k, variant);
     const size_t slots = (((size_t)m * 20) + 15) & ~(size_t)15;
-    if ((size_t)m * 8 > DIRECT_ITEMS * 4) return ~(size_t)0;  // the pass keeps its slots in the item list's space
-    return hist + slots + DIRECT_ITEMS * 4 + DIRECT_LIST2 * 2 + sizeof(DirectShared) + 16;
+    const size_t items = (size_t)std::max<uint32_t>(DIRECT_ITEMS, 2 * m) * 4;
+    const size_t list2 = pmh3a_direct_lists(variant) ? DIRECT_LIST2 * 2 : 0;
+    const size_t winv = (pmh3a_direct_hist_bytes(k, variant) < hist_full(k) ? 16 : 256) * sizeof(double);
+    const size_t stage = pmh3a_direct_stage_bytes(variant) ? 2 * (pmh3a_direct_stage_bytes(variant) + 32) + 16 : 0;
+    return hist + slots + items + list2 + sizeof(DirectShared) + winv + stage + 16;
 }
 
-template <int NT, int MINB, int T, int NP, bool LIST, int HB = 8>
+template <int NT, int MINB, int T, int NP, bool LIST, int HB = 8, int STAGE = 0>
 static cudaError_t launch_direct_t(const Pmh3aParams& P, int grid, size_t smem, cudaStream_t stream) {
-    auto kern = pmh3a_direct_kernel<NT, MINB, T, NP, LIST, HB>;
+    auto kern = pmh3a_direct_kernel<NT, MINB, T, NP, LIST, HB, STAGE>;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        // the smallest shared-memory carve-out that holds MINB CTAs: what is left is L1, and L1 is where loads in
+        // flight wait -- the kernel's memory-level parallelism
+        const int pct = (int)std::min<size_t>(100, ((smem + 1024) * MINB * 100 + 233471) / 233472);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
@@ -352,13 +412,16 @@ static cudaError_t launch_direct_t(const Pmh3aParams& P, int grid, size_t smem, 
     return cudaGetLastError();
 }
 
-// variant 0: long sequences (one point per occurrence, histogram scan); 1: short sequences (two points per
-// occurrence, list of the keys seen twice); 4: as 0 with 4-bit counters, 256 threads, four sequences per SM
-int pmh3a_direct_ctas_per_sm(int variant) { return variant >= 7 ? 5 : (variant >= 4 ? 4 : 2); }
-int pmh3a_direct_threads(int variant) { return variant >= 3 ? 256 : 512; }
+// variant 0: 8-bit counters, 512 threads, two sequences per SM, one point per occurrence (very long sequences);
+// 5: 4-bit counters, 256 threads, four sequences per SM, two points per occurrence (short sequences); 6: the same
+// with one point per occurrence (long sequences); 9, 10, 11: 0, 5, 6 with TMA staging; the others: experiments
+int pmh3a_direct_ctas_per_sm(int variant) { return variant == 7 || variant == 8 ? 5 : (variant >= 4 && variant != 9 ? 4 : 2); }
+int pmh3a_direct_threads(int variant) { return variant >= 3 && variant != 9 ? 256 : 512; }
+bool pmh3a_direct_lists(int variant) { return variant == 1 || variant == 5 || variant == 10; }
+size_t pmh3a_direct_stage_bytes(int variant) { return variant == 9 ? 8192 : (variant == 10 || variant == 11 ? 4096 : 0); }
 size_t pmh3a_direct_hist_bytes(uint32_t k, int variant) {
     size_t hist = (size_t)1 << (2 * k);
-    if (variant >= 4) hist /= 2;
+    if (variant >= 4 && variant != 9) hist /= 2;
     return hist < 16 ? 16 : hist;
 }
 cudaError_t launch_pmh3a_direct(const Pmh3aParams& P, int grid, int variant, cudaStream_t stream) {
@@ -366,13 +429,12 @@ cudaError_t launch_pmh3a_direct(const Pmh3aParams& P, int grid, int variant, cud
     switch (variant) {
         case 0: return launch_direct_t<512, 2, 8, 1, false>(P, grid, smem, stream);
         case 1: return launch_direct_t<512, 2, 4, 2, true>(P, grid, smem, stream);
-        case 2: return launch_direct_t<512, 2, 4, 2, false>(P, grid, smem, stream);
-        case 3: return launch_direct_t<256, 2, 8, 2, true>(P, grid, smem, stream);
         case 4: return launch_direct_t<256, 4, 8, 1, false, 4>(P, grid, smem, stream);
         case 5: return launch_direct_t<256, 4, 4, 2, true, 4>(P, grid, smem, stream);
         case 6: return launch_direct_t<256, 4, 4, 1, false, 4>(P, grid, smem, stream);
-        case 7: return launch_direct_t<256, 5, 8, 1, false, 4>(P, grid, smem, stream);
-        default: return launch_direct_t<256, 5, 4, 1, false, 4>(P, grid, smem, stream);
+        case 9: return launch_direct_t<512, 2, 8, 1, false, 8, 8192>(P, grid, smem, stream);
+        case 10: return launch_direct_t<256, 4, 4, 2, true, 4, 4096>(P, grid, smem, stream);
+        default: return launch_direct_t<256, 4, 4, 1, false, 4, 4096>(P, grid, smem, stream);
     }
 }
 
