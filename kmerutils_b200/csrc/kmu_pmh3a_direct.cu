@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
     uint32_t* hi = (uint32_t*)(smem + P.regionA_bytes + (size_t)m * 16);
     uint32_t* items = (uint32_t*)(smem + P.regionA_bytes + P.slots_smem_bytes);  // pk | count << 16
     unsigned long long* best = (unsigned long long*)items;  // during the pass, per slot: the lowest offer (direct_word)
-    const uint32_t items_cap = max(DIRECT_ITEMS, 2 * m);
+    const uint32_t items_cap = (max(DIRECT_ITEMS, 2 * m) + 3) & ~3u;  // what follows stays 16-byte aligned
     uint16_t* list2 = (uint16_t*)(items + items_cap);         // LIST forms only
     DirectShared* ds = (DirectShared*)(list2 + (LIST ? DIRECT_LIST2 : 0));
     double* winv_tab = (double*)(ds + 1);                      // [CMAX + 1]: 1 / count
@@ -387,7 +387,7 @@ static size_t hist_full(uint32_t k) { return std::max<size_t>(16, (size_t)1 << (
 size_t pmh3a_direct_smem_bytes(uint32_t k, uint32_t m, int variant) {
     size_t hist = pmh3a_direct_hist_bytes(k, variant);
     const size_t slots = (((size_t)m * 20) + 15) & ~(size_t)15;
-    const size_t items = (size_t)std::max<uint32_t>(DIRECT_ITEMS, 2 * m) * 4;
+    const size_t items = (size_t)((std::max<uint32_t>(DIRECT_ITEMS, 2 * m) + 3) & ~3u) * 4;
     const size_t list2 = pmh3a_direct_lists(variant) ? DIRECT_LIST2 * 2 : 0;
     const size_t winv = (pmh3a_direct_hist_bytes(k, variant) < hist_full(k) ? 16 : 256) * sizeof(double);
     const size_t stage = pmh3a_direct_stage_bytes(variant) ? 2 * (pmh3a_direct_stage_bytes(variant) + 32) + 16 : 0;
