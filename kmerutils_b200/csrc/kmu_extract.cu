@@ -160,15 +160,35 @@ __device__ __forceinline__ uint64_t nt_seed(uint32_t b) {
     return (b & 2) ? hi : lo;
 }
 
-// warp-cooperative version: a warp owns the k-mers starting in one 2 KB group; every lane takes a run of
-// NT_RUN consecutive positions (one O(k) initialisation, then the O(1) ntHash recurrence)
+// warp-cooperative version: a warp owns the k-mers starting in one 2 KB group and takes them in tiles of
+// 32 x NT_RUN positions; every lane computes a run of NT_RUN consecutive positions (one O(k) initialisation,
+// then the O(1) ntHash recurrence) into the warp's shared-memory tile, and the tile goes out with every store
+// instruction writing 32 consecutive values
 constexpr uint32_t NT_RUN = 32;
+constexpr uint32_t NT_PITCH = NT_RUN + 1;                                          // u64 elements per run: lanes 2 banks apart
+constexpr uint32_t NT_TILE_BYTES = 32 * NT_PITCH * 8 + ((32 * NT_PITCH + 15) & ~15u);  // hashes + strand bytes
 __global__ void __launch_bounds__(256) nthash_warp_kernel(SeqView b, uint64_t total_bytes, uint32_t k, uint32_t n_multi,
                                                            const uint64_t* __restrict__ out_off, uint64_t* __restrict__ out_hash,
                                                            uint8_t* __restrict__ out_strand) {
+    extern __shared__ __align__(16) uint8_t nt_smem[];
+    // per-launch tables: the seeds, their complements, and the recurrence's two XOR terms for every (outgoing base,
+    // incoming base) pair:  f' = rotl(f, 1) ^ FD[out][in],  r' = rotl(r, 63) ^ RD[out][in]
+    __shared__ uint64_t SEED[4], SEEDC[4], FD[16], RD[16];
+    if (threadIdx.x < 16) {
+        const uint32_t ob = threadIdx.x >> 2, nb = threadIdx.x & 3;
+        FD[threadIdx.x] = rotl_var(nt_seed(ob), k) ^ nt_seed(nb);
+        RD[threadIdx.x] = rotl_var(nt_seed(3u - ob), 63) ^ rotl_var(nt_seed(3u - nb), k - 1);
+        if (threadIdx.x < 4) {
+            SEED[threadIdx.x] = nt_seed(threadIdx.x);
+            SEEDC[threadIdx.x] = nt_seed(3u - threadIdx.x);
+        }
+    }
+    __syncthreads();
     const uint64_t mult = (uint64_t)k * 0x90b45d39fb6da1faULL;  // nthash.rs:13,68 (wrapping)
     const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
     const int lane = threadIdx.x & 31;
+    uint64_t* tile_h = (uint64_t*)(nt_smem + (threadIdx.x >> 5) * NT_TILE_BYTES);
+    uint8_t* tile_s = (uint8_t*)(tile_h + 32 * NT_PITCH);
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t g = warp; g < ngroups; g += nwarps) {
@@ -184,36 +204,53 @@ __global__ void __launch_bounds__(256) nthash_warp_kernel(SeqView b, uint64_t to
             const uint64_t p_hi = min(nk, (byte1 - sb) * 4);
             const uint32_t* words = (const uint32_t*)(b.packed + sb);
             const uint64_t obase = __ldg(out_off + s);
-            for (uint64_t p0 = p_lo + (uint64_t)lane * NT_RUN; p0 < p_hi; p0 += 32 * NT_RUN) {
-                const uint64_t pend = min(p0 + NT_RUN, p_hi);
-                KmerWalker<uint64_t> wk;
-                wk.start(words, p0, k);
-                wk.roll();
-                // nthash_canonical_init (kmer.rs:74-94)
-                uint64_t f = 0, r = 0;
-                for (uint32_t i = 0; i < k; ++i) {
-                    const uint32_t base = (uint32_t)(wk.fwd >> (2 * (k - 1 - i))) & 3u;
-                    f ^= rotl_var(nt_seed(base), k - 1 - i);
-                    r ^= rotl_var(nt_seed(3u - base), i);
-                }
-                for (uint64_t p = p0;;) {
-                    const uint64_t h0 = f <= r ? f : r;
-                    uint64_t* o = out_hash + (obase + p) * n_multi;
-                    o[0] = h0;
-                    for (uint32_t i = 1; i < n_multi; ++i) {
-                        uint64_t tmp = h0 * ((uint64_t)i ^ mult);
-                        tmp ^= tmp >> 27;
-                        o[i] = tmp;
-                    }
-                    if (out_strand) out_strand[obase + p] = f <= r ? 0 : 1;
-                    if (++p >= pend) break;
-                    // ntHash recurrence: identical values to re-initialising on the new window
-                    const uint32_t old_base = (uint32_t)(wk.fwd >> (2 * k - 2)) & 3u;
+            for (uint64_t t0 = p_lo; t0 < p_hi; t0 += 32 * NT_RUN) {  // one tile
+                const uint64_t p0 = t0 + (uint64_t)lane * NT_RUN;
+                if (p0 < p_hi) {
+                    const uint32_t n = (uint32_t)min((uint64_t)NT_RUN, p_hi - p0);
+                    KmerWalker<uint64_t> wk;
+                    wk.start(words, p0, k);
                     wk.roll();
-                    const uint32_t nb = (uint32_t)wk.fwd & 3u;
-                    f = rotl_var(f, 1) ^ rotl_var(nt_seed(old_base), k) ^ nt_seed(nb);
-                    r = rotl_var(r, 63) ^ rotl_var(nt_seed(3u - old_base), 63) ^ rotl_var(nt_seed(3u - nb), k - 1);
+                    // nthash_canonical_init (kmer.rs:74-94), Horner form: f = XOR_i rotl(seed[b_i], k-1-i),
+                    // r = XOR_i rotl(seed[3 - b_i], i)
+                    uint64_t f = 0, r = 0;
+                    for (uint32_t i = 0; i < k; ++i) {
+                        f = ((f << 1) | (f >> 63)) ^ SEED[(uint32_t)(wk.fwd >> (2 * (k - 1 - i))) & 3u];
+                        r = ((r << 1) | (r >> 63)) ^ SEEDC[(uint32_t)(wk.fwd >> (2 * i)) & 3u];
+                    }
+                    uint64_t* th = tile_h + lane * NT_PITCH;
+                    uint8_t* ts = tile_s + lane * NT_PITCH;
+                    for (uint32_t j = 0;;) {
+                        th[j] = f <= r ? f : r;
+                        ts[j] = f <= r ? 0 : 1;
+                        if (++j >= n) break;
+                        // ntHash recurrence: identical values to re-initialising on the new window
+                        const uint32_t old_base = (uint32_t)(wk.fwd >> (2 * k - 2)) & 3u;
+                        wk.roll();
+                        const uint32_t nb = (uint32_t)wk.fwd & 3u;
+                        f = ((f << 1) | (f >> 63)) ^ FD[old_base * 4 + nb];
+                        r = ((r >> 1) | (r << 63)) ^ RD[old_base * 4 + nb];
+                    }
                 }
+                __syncwarp();
+                // tile out: run j of the tile = positions t0 + 32 j .. + 31, one per lane
+                const uint32_t tile_n = (uint32_t)min((uint64_t)32 * NT_RUN, p_hi - t0);
+                for (uint32_t j = 0; j * NT_RUN < tile_n; ++j) {
+                    const uint32_t q = j * NT_RUN + lane;
+                    if (q < tile_n) {
+                        const uint64_t h0 = tile_h[j * NT_PITCH + lane];
+                        const uint64_t p = t0 + q;
+                        uint64_t* o = out_hash + (obase + p) * n_multi;
+                        o[0] = h0;
+                        for (uint32_t i = 1; i < n_multi; ++i) {
+                            uint64_t tmp = h0 * ((uint64_t)i ^ mult);
+                            tmp ^= tmp >> 27;
+                            o[i] = tmp;
+                        }
+                        if (out_strand) out_strand[obase + p] = tile_s[j * NT_PITCH + lane];
+                    }
+                }
+                __syncwarp();
             }
             ++s;
         }
@@ -223,7 +260,14 @@ __global__ void __launch_bounds__(256) nthash_warp_kernel(SeqView b, uint64_t to
 cudaError_t launch_nthash(const SeqView& b, uint64_t total_bytes, uint32_t k, uint32_t n_multi, const uint64_t* out_off,
                           uint64_t* out_hash, uint8_t* out_strand, cudaStream_t stream) {
     if (b.nseq == 0) return cudaSuccess;
-    nthash_warp_kernel<<<148 * 8, 256, 0, stream>>>(b, total_bytes, k, n_multi, out_off, out_hash, out_strand);
+    const size_t smem = 8 * (size_t)NT_TILE_BYTES;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(nthash_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    nthash_warp_kernel<<<148 * 2, 256, smem, stream>>>(b, total_bytes, k, n_multi, out_off, out_hash, out_strand);
     return cudaGetLastError();
 }
 
