@@ -3,6 +3,7 @@
 // KmerSeqIterator::next :75-106), and canonical ntHash (src/base/kmer.rs:74-94,
 // src/base/nthash.rs:63-72).  Both are streaming kernels bounded by their HBM writes.
 #include <cstdint>
+#include <cstdlib>
 
 #include "kmu_device.cuh"
 #include "kmu_kernels.h"
@@ -167,7 +168,7 @@ __device__ __forceinline__ uint64_t nt_seed(uint32_t b) {
 constexpr uint32_t NT_RUN = 32;
 constexpr uint32_t NT_PITCH = NT_RUN + 1;                                          // u64 elements per run: lanes 2 banks apart
 constexpr uint32_t NT_TILE_BYTES = 32 * NT_PITCH * 8 + ((32 * NT_PITCH + 15) & ~15u);  // hashes + strand bytes
-__global__ void __launch_bounds__(256) nthash_warp_kernel(SeqView b, uint64_t total_bytes, uint32_t k, uint32_t n_multi,
+__global__ void __launch_bounds__(128) nthash_warp_kernel(SeqView b, uint64_t total_bytes, uint32_t k, uint32_t n_multi,
                                                            const uint64_t* __restrict__ out_off, uint64_t* __restrict__ out_hash,
                                                            uint8_t* __restrict__ out_strand) {
     extern __shared__ __align__(16) uint8_t nt_smem[];
@@ -260,14 +261,15 @@ __global__ void __launch_bounds__(256) nthash_warp_kernel(SeqView b, uint64_t to
 cudaError_t launch_nthash(const SeqView& b, uint64_t total_bytes, uint32_t k, uint32_t n_multi, const uint64_t* out_off,
                           uint64_t* out_hash, uint8_t* out_strand, cudaStream_t stream) {
     if (b.nseq == 0) return cudaSuccess;
-    const size_t smem = 8 * (size_t)NT_TILE_BYTES;
+    const int wpb = 4, cps = 5;  // warps per CTA (one 9.3 KB tile each), CTAs per SM
+    const size_t smem = wpb * (size_t)NT_TILE_BYTES;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(nthash_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    nthash_warp_kernel<<<148 * 2, 256, smem, stream>>>(b, total_bytes, k, n_multi, out_off, out_hash, out_strand);
+    nthash_warp_kernel<<<148 * cps, 32 * wpb, smem, stream>>>(b, total_bytes, k, n_multi, out_off, out_hash, out_strand);
     return cudaGetLastError();
 }
 
