@@ -93,6 +93,8 @@ struct kmu_ctx {
     bool table_scratch_clean = false;
     PinnedBuf pinned, pinned_small;
     cudaEvent_t phase_ev[2]{};  // end of the main sketch launches of a chunk (host pipeline)
+    cudaStream_t aux_stream = nullptr;  // the few-CTA launch of the very long sequences runs beside the main launches
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     // first-point table of the ProbMinHash3a kernels (small key spaces), see kmu_pmh3a.cu
     DevBuf memo;
     uint32_t memo_k = 0, memo_m = 0;
