@@ -168,6 +168,11 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
  * map), ProbHash3aSketch::sketch_compressedkmer_seqs  src/sketching/setsketchert.rs:160-202.  sig: m values. */
 int32_t kmu_sketch_pmh3a_whole(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, int32_t kmer_type, int32_t hash_kind,
                                uint32_t m, void* sig, int32_t sig_on_device);
+/* the same for many genomes in one call: group g = the next group_sizes[g] sequences of the batch (the groups cover the
+ * batch), one signature per group, no host round trip between groups.  This is the loop gsearch runs over
+ * sketch_compressedkmer_seqs, one genome after the other.  sig: ngroups rows of m values. */
+int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* batch, const uint64_t* group_sizes, uint64_t ngroups,
+                                uint32_t k, int32_t kmer_type, int32_t hash_kind, uint32_t m, void* sig, int32_t sig_on_device);
 /* ProbMinHash3a::hash_weigthed_hashmap on an explicit weighted set (host arrays): n distinct keys of key_bytes
  * (4 or 8) with positive f64 weights -- the f64-weighted maps of BlockSeqSketcher (seqblocksketch.rs:121-138)
  * or any multiplicity map built elsewhere.  sig: m keys. */

@@ -628,4 +628,130 @@ int32_t kmu_sketch_pmh3a_whole(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, 
     return KMU_OK;
 }
 
+// One whole-file signature per group of consecutive sequences (a genome = its contigs): what gsearch does with
+// ProbHash3aSketch::sketch_compressedkmer_seqs (src/sketching/setsketchert.rs:160-202) genome after genome.  The groups
+// run back to back on the stream with no host round trip in between: the multiplicity table of a group is reused
+// for the next one (it stays L2 resident: 2 x k-mers x 8 bytes), the item bound comes from the k-mer count instead of
+// the distinct count (1.5 m ln(m / 1e-4) / k-mers: exact whenever at least two thirds of the k-mers are distinct),
+// and all verifications are read back once at the end; a group that failed its check is redone by
+// kmu_sketch_pmh3a_whole.  sig: ngroups rows of m values.
+int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint64_t* group_sizes, uint64_t ngroups, uint32_t k,
+                                int32_t kmer_type, int32_t hash_kind, uint32_t m, void* sig, int32_t sig_on_device) {
+    if (!ctx || !b || (ngroups && (!group_sizes || !sig))) return fail(KMU_EINVAL, "null argument");
+    if (int32_t a = kmu_check_kmer_args(b, k, kmer_type, hash_kind)) return a;
+    if (kmer_type_is_aa(kmer_type)) return fail(KMU_EINVAL, "whole-file ProbMinHash3a takes DNA sequences");
+    if (m < 2) return fail(KMU_EINVAL, "ProbMinHash3a needs at least 2 hash values (m = %u)", m);
+    uint64_t covered = 0;
+    for (uint64_t g = 0; g < ngroups; ++g) covered += group_sizes[g];
+    if (covered != b->nseq) return fail(KMU_EINVAL, "the groups cover %llu sequences, the batch has %llu", (unsigned long long)covered,
+                                        (unsigned long long)b->nseq);
+    if (ngroups == 0) return KMU_OK;
+    const bool key64 = kmer_type == KMU_KMER64;
+    const size_t vsz = key64 ? 8 : 4, slot_bytes = key64 ? 16 : 8;
+    // per group: first sequence, k-mers, bytes; byte offsets rebased to the group's first sequence
+    std::vector<uint64_t> first(ngroups + 1, 0), nk(ngroups, 0), rebased(b->nseq);
+    uint64_t cap_max = 1024;
+    for (uint64_t g = 0; g < ngroups; ++g) {
+        first[g + 1] = first[g] + group_sizes[g];
+        const uint64_t base = group_sizes[g] ? b->h_byte_off[first[g]] : 0;
+        for (uint64_t i = first[g]; i < first[g + 1]; ++i) {
+            rebased[i] = b->h_byte_off[i] - base;
+            nk[g] += b->h_nbases[i] >= k ? b->h_nbases[i] - k + 1 : 0;
+        }
+        uint64_t want = std::max<uint64_t>(1024, nk[g] * 2);
+        if (2 * k < 40) want = std::min<uint64_t>(want, std::max<uint64_t>(1024, 2ull << (2 * k)));
+        uint64_t cap = 1024;
+        while (cap < want) cap <<= 1;
+        cap_max = std::max(cap_max, cap);
+    }
+    std::vector<unsigned long long> tops(ngroups, 0);
+    std::vector<double> bounds(ngroups, 0.0);
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ScopedDevice sd(ctx->device);
+        ctx->last = kmu_times{};
+        cudaStream_t st = ctx->stream;
+        cudaError_t me = ctx->whole_table.reserve(cap_max * slot_bytes + sizeof(unsigned long long) * AUX_WORDS);
+        if (me == cudaSuccess) me = ctx->items_slots.reserve(sizeof(kmu::Slot) * m + 64);
+        if (me == cudaSuccess) me = ctx->misc.reserve(sizeof(uint64_t) * (b->nseq + 1) + sizeof(unsigned long long) * ngroups + 64);
+        if (me == cudaSuccess && !sig_on_device) me = ctx->sig_dev.reserve((size_t)ngroups * m * vsz);
+        if (me != cudaSuccess) return fail(KMU_ENOMEM, "group sketch buffers: %s", cudaGetErrorString(me));
+        uint64_t* d_rebased = (uint64_t*)ctx->misc.p;
+        unsigned long long* d_tops = (unsigned long long*)(d_rebased + b->nseq + 1);
+        uint8_t* d_sig = sig_on_device ? (uint8_t*)sig : (uint8_t*)ctx->sig_dev.p;
+        CUDA_TRY(cudaMemcpyAsync(d_rebased, rebased.data(), sizeof(uint64_t) * b->nseq, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(d_tops, 0, sizeof(unsigned long long) * ngroups, st));
+        kmu::Pmh3aItemsParams P{};
+        P.k = k;
+        P.kmer_type = kmer_type;
+        P.hash_kind = hash_kind;
+        P.m = m;
+        P.global_slots = (kmu::Slot*)ctx->items_slots.p;
+        const size_t smem = sizeof(kmu::Slot) * (size_t)m;
+        P.slots_in_smem = smem <= SMEM_BUDGET ? 1 : 0;
+        P.slot_thresh = (uint32_t)(0x100000000ULL % m);
+        fill_exp01(P.e, m);
+        uint64_t launches = 0;
+        cudaEventRecord(ctx->ev[0], st);
+        for (uint64_t g = 0; g < ngroups; ++g) {
+            if (nk[g] == 0) {  // no k-mer: the all-zero signature of an empty sketch
+                CUDA_TRY(cudaMemsetAsync(d_sig + g * (size_t)m * vsz, 0, (size_t)m * vsz, st));
+                continue;
+            }
+            uint64_t want = std::max<uint64_t>(1024, nk[g] * 2);
+            if (2 * k < 40) want = std::min<uint64_t>(want, std::max<uint64_t>(1024, 2ull << (2 * k)));
+            uint64_t cap = 1024;
+            while (cap < want) cap <<= 1;
+            kmu::CountTable t;
+            t.slots = ctx->whole_table.p;
+            t.capmask = cap - 1;
+            unsigned long long* aux = (unsigned long long*)((uint8_t*)ctx->whole_table.p + cap_max * slot_bytes);
+            t.special = aux;
+            t.overflow = aux + 1;
+            CUDA_TRY(cudaMemsetAsync(aux, 0, sizeof(unsigned long long) * 8, st));
+            CUDA_TRY(kmu::launch_count_init(t, key64, ctx->sm_count, st));
+            const uint64_t s0 = first[g], ns = group_sizes[g];
+            const uint64_t Llast = b->h_nbases[s0 + ns - 1];
+            const uint64_t bytes = rebased[s0 + ns - 1] + align_up((Llast + 3) / 4, SEQ_ALIGN);
+            kmu::SeqView v{b->packed + b->h_byte_off[s0], d_rebased + s0, b->nbases + s0, ns};
+            CUDA_TRY(kmu::launch_count_insert_seqs(v, bytes, k, key64, kmu::hash_kind_is_canonical_host(hash_kind), t, ctx->sm_count, st));
+            P.table = t.slots;
+            P.special = t.special;
+            P.n = cap;
+            bounds[g] = 1.5 * (double)m / (double)nk[g] * std::log((double)m / 1e-4);
+            P.bound = bounds[g];
+            const uint64_t work = (P.n + 511) / 512;
+            const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(work, (uint64_t)ctx->sm_count));
+            CUDA_TRY(kmu::launch_pmh3a_items_init(P.global_slots, m, st));
+            CUDA_TRY(kmu::launch_pmh3a_items(P, key64, key64 ? 2 : 1, grid, P.slots_in_smem ? smem : 0, st));
+            CUDA_TRY(kmu::launch_pmh3a_items_finish(P.global_slots, m, key64, d_sig + g * (size_t)m * vsz, d_tops + g, st));
+            launches += 5;
+        }
+        cudaEventRecord(ctx->ev[1], st);
+        CUDA_TRY(cudaMemcpyAsync(tops.data(), d_tops, sizeof(unsigned long long) * ngroups, cudaMemcpyDeviceToHost, st));
+        if (!sig_on_device) {
+            CUDA_TRY(cudaMemcpyAsync(sig, d_sig, (size_t)ngroups * m * vsz, cudaMemcpyDeviceToHost, st));
+            ctx->last.d2h_bytes = (size_t)ngroups * m * vsz;
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+        ctx->launches += launches;
+        ctx->last.launches = launches;
+    }
+    // groups whose largest slot value did not stay below their bound: the full procedure (distinct count, growing bound)
+    for (uint64_t g = 0; g < ngroups; ++g) {
+        if (nk[g] == 0) continue;
+        double top;
+        std::memcpy(&top, &tops[g], 8);
+        if (top < bounds[g]) continue;
+        kmu_seqbatch* view = nullptr;
+        int32_t rc = kmu_seqbatch_view(b, first[g], group_sizes[g], &view);
+        if (rc) return rc;
+        rc = kmu_sketch_pmh3a_whole(ctx, view, k, kmer_type, hash_kind, m, (uint8_t*)sig + g * (size_t)m * vsz, sig_on_device);
+        kmu_seqbatch_destroy(view);
+        if (rc) return rc;
+    }
+    return KMU_OK;
+}
+
 }  // extern "C"

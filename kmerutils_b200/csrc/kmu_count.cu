@@ -135,16 +135,19 @@ __global__ void count_init_kernel(CountTable t, int key64) {
 
 template <typename V>
 __global__ void __launch_bounds__(256) count_insert_seqs_kernel(SeqView b, uint64_t total_bytes, uint32_t k, int canonical,
-                                                                 CountTable t) {
-    const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
+                                                                 CountTable t, uint32_t group_bytes) {
+    const uint64_t ngroups = (total_bytes + group_bytes - 1) / group_bytes;
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     bool ok = true;
     for (uint64_t g = warp; g < ngroups; g += nwarps)
-        warp_for_each_kmer<V>(b, total_bytes, g, k, canonical != 0, lane, [&](V key, bool active) {
-            if (active) ok &= CountOps<V>::insert(t, key, 1u);
-        });
+        warp_for_each_kmer<V>(
+            b, total_bytes, g, k, canonical != 0, lane,
+            [&](V key, bool active) {
+                if (active) ok &= CountOps<V>::insert(t, key, 1u);
+            },
+            group_bytes);
     if (!ok) *t.overflow = 1ULL;
 }
 
@@ -316,10 +319,15 @@ cudaError_t launch_count_init(const CountTable& t, bool key64, int sm_count, cud
 cudaError_t launch_count_insert_seqs(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
                                      const CountTable& t, int sm_count, cudaStream_t st) {
     if (b.nseq == 0 || total_bytes == 0) return cudaSuccess;
-    const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
+    // a warp takes one slice of the packed buffer; small inputs (one genome) get smaller slices so that every SM has
+    // its eight CTAs of work: the kernel lives on memory-level parallelism
+    uint32_t group_bytes = GROUP_BYTES;
+    const uint64_t want_warps = (uint64_t)sm_count * 8 * 8;
+    while (group_bytes > 64 && (total_bytes + group_bytes - 1) / group_bytes < want_warps) group_bytes /= 2;
+    const uint64_t ngroups = (total_bytes + group_bytes - 1) / group_bytes;
     const int grid = grid_for(ngroups * 32, 256, sm_count, 8);
-    if (key64) count_insert_seqs_kernel<uint64_t><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, t);
-    else count_insert_seqs_kernel<uint32_t><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, t);
+    if (key64) count_insert_seqs_kernel<uint64_t><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, t, group_bytes);
+    else count_insert_seqs_kernel<uint32_t><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, t, group_bytes);
     return cudaGetLastError();
 }
 

@@ -219,6 +219,26 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
 }
 __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) { return ~warp_max_u64(~v); }
 
+// Is an item still alive after its first point, i.e. winv * x1 < qmax ?  x1 = c1 * U where U comes
+// from the first output of the key's Xoshiro256++, which needs only the state words s0 and s3
+// (SplitMix64 outputs 1 and 4 of the seed): half a seeding, no memory.  Items on the rare
+// rejection branch of ExpRestricted01 (c1 * U >= 1) are left to the full path.
+template <typename V>
+__device__ __forceinline__ bool first_point_alive(V key, double winv, double qmax, double c1) {
+    const uint64_t seed = nohash_seed(key);
+    uint64_t z0 = seed + 0x9E3779B97F4A7C15ULL;
+    uint64_t z3 = seed + 4ULL * 0x9E3779B97F4A7C15ULL;
+    z0 = (z0 ^ (z0 >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z3 = (z3 ^ (z3 >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z0 = (z0 ^ (z0 >> 27)) * 0x94D049BB133111EBULL;
+    z3 = (z3 ^ (z3 >> 27)) * 0x94D049BB133111EBULL;
+    const uint64_t s0 = z0 ^ (z0 >> 31), s3 = z3 ^ (z3 >> 31);
+    const uint64_t r = rotl64(s0 + s3, 23) + s0;
+    const double u = __longlong_as_double((long long)((r >> 12) | 0x3FF0000000000000ULL)) - 1.0;
+    const double x = __dmul_rn(c1, u);
+    return !(x < 1.0) || __dmul_rn(winv, x) < qmax;
+}
+
 // ----------------------------------------------------------------------------
 //  TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier: stages the packed bytes of
 //  the next sequence into shared memory while the current one is processed.
@@ -502,11 +522,13 @@ __device__ __forceinline__ uint64_t kmer_at<uint64_t>(const uint32_t* __restrict
 // f(pre-key, active) is called with all 32 lanes converged (inactive lanes: active == false).
 constexpr uint32_t GROUP_BYTES = 2048;
 
+// group_bytes: the slice of the packed buffer one warp takes (a multiple of 16; GROUP_BYTES unless the input is so
+// small that slices of that size would leave most of the GPU idle)
 template <typename V, typename F>
 __device__ __forceinline__ void warp_for_each_kmer(const SeqView& b, uint64_t total_bytes, uint64_t group, uint32_t k,
-                                                   bool canonical, int lane, F&& f) {
-    const uint64_t byte0 = group * GROUP_BYTES;
-    const uint64_t byte1 = min(byte0 + (uint64_t)GROUP_BYTES, total_bytes);
+                                                   bool canonical, int lane, F&& f, uint32_t group_bytes = GROUP_BYTES) {
+    const uint64_t byte0 = group * group_bytes;
+    const uint64_t byte1 = min(byte0 + (uint64_t)group_bytes, total_bytes);
     uint64_t s = seq_of_byte(b.byte_off, b.nseq, byte0);
     while (s < b.nseq) {
         const uint64_t sb = __ldg(b.byte_off + s);

@@ -187,26 +187,6 @@ __device__ __forceinline__ void sketch_update(const SlotArray& S, uint32_t s, do
     if (slot_update_min(&S.slots[s], hbits, key)) *(volatile uint32_t*)(S.hi + s) = (uint32_t)(hbits >> 32);
 }
 
-// Is an item still alive after its first point, i.e. winv * x1 < qmax ?  x1 = c1 * U where U comes
-// from the first output of the key's Xoshiro256++, which needs only the state words s0 and s3
-// (SplitMix64 outputs 1 and 4 of the seed): half a seeding, no memory.  Items on the rare
-// rejection branch of ExpRestricted01 (c1 * U >= 1) are left to the full path.
-template <typename V>
-__device__ __forceinline__ bool first_point_alive(V key, double winv, double qmax, double c1) {
-    const uint64_t seed = nohash_seed(key);
-    uint64_t z0 = seed + 0x9E3779B97F4A7C15ULL;
-    uint64_t z3 = seed + 4ULL * 0x9E3779B97F4A7C15ULL;
-    z0 = (z0 ^ (z0 >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z3 = (z3 ^ (z3 >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z0 = (z0 ^ (z0 >> 27)) * 0x94D049BB133111EBULL;
-    z3 = (z3 ^ (z3 >> 27)) * 0x94D049BB133111EBULL;
-    const uint64_t s0 = z0 ^ (z0 >> 31), s3 = z3 ^ (z3 >> 31);
-    const uint64_t r = rotl64(s0 + s3, 23) + s0;
-    const double u = __longlong_as_double((long long)((r >> 12) | 0x3FF0000000000000ULL)) - 1.0;
-    const double x = __dmul_rn(c1, u);
-    return !(x < 1.0) || __dmul_rn(winv, x) < qmax;
-}
-
 constexpr uint32_t QFLAG_SKIP_FIRST = 0x80000000u;  // QItem.cnt: the item's first point is already in the sketch
 constexpr uint32_t QFLAG_SKIP_TWO = 0x40000000u;    // QItem.cnt: so are its first two points
 constexpr uint32_t QFLAG_MASK = QFLAG_SKIP_FIRST | QFLAG_SKIP_TWO;

@@ -20,6 +20,8 @@ namespace kmu {
 
 template <typename V>
 __device__ __forceinline__ void pmh3a_item(V key, double winv, double bound, const Pmh3aItemsParams& P, Slot* slots) {
+    // most items of a large set die on their first point: half a seeding tells (first_point_alive, kmu_device.cuh)
+    if (!first_point_alive<V>(key, winv, bound, P.e.c1)) return;
     Xoshiro256pp rng;
     rng.seed(nohash_seed(key));
     for (uint32_t i = 1;; ++i) {
@@ -35,7 +37,7 @@ __device__ __forceinline__ void pmh3a_item(V key, double winv, double bound, con
 // SRC 0: explicit lists keys[n] (V), weights[n] (f64); SRC 1: u32-key counting table (8-byte slots);
 // SRC 2: u64-key counting table (16-byte slots, empty key ~0)
 template <typename V, int SRC>
-__global__ void __launch_bounds__(512, 1) pmh3a_items_kernel(const Pmh3aItemsParams P) {
+__global__ void __launch_bounds__(1024, 1) pmh3a_items_kernel(const Pmh3aItemsParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
     Slot* slots = P.slots_in_smem ? (Slot*)smem : P.global_slots;
     const bool partial = P.slots_in_smem != 0;
@@ -107,7 +109,7 @@ static cudaError_t launch_items_t(const Pmh3aItemsParams& P, int grid, size_t sm
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    kern<<<grid, 512, smem, st>>>(P);
+    kern<<<grid, 1024, smem, st>>>(P);
     return cudaGetLastError();
 }
 

@@ -214,6 +214,8 @@ class Engine:
         """One whole-file signature per group of consecutive sequences (a genome = its contigs), the way gsearch drives
         the `sketch_compressedkmer_seqs` entry points.  algo: "pmh3a" | "superminhash" | "setsketch"; kw as for the
         whole-file calls.  -> (ngroups, m) array"""
+        if algo == "pmh3a":
+            return self.sketch_pmh3a_groups(batch, group_sizes, k, kmer_type, hash_kind, **kw)
         fn = {"pmh3a": self.sketch_pmh3a_whole, "superminhash": self.sketch_superminhash_whole,
               "setsketch": lambda b, k_, t, h, **kk: self.sketch_setsketch(b, k_, t, h, whole=True, **kk)}[algo]
         rows, first = [], 0
@@ -328,6 +330,15 @@ class Engine:
         """ONE ProbMinHash3a signature for the whole batch (ProbHash3aSketch::sketch_compressedkmer_seqs)."""
         out = np.zeros(m, dtype=val_dtype(kmer_type))
         check(self.lib.kmu_sketch_pmh3a_whole(self.ctx, batch.handle, k, kmer_type, hash_kind, m, _p(out), 0))
+        return out
+
+    def sketch_pmh3a_groups(self, batch, group_sizes, k, kmer_type, hash_kind=HASH_CANON_INVHASH, m=200):
+        """One whole-file ProbMinHash3a signature per group of consecutive sequences, all groups in one call
+        (kmu_sketch_pmh3a_groups).  -> (ngroups, m)"""
+        gs = _as_u64(group_sizes)
+        out = np.zeros((len(gs), m), dtype=val_dtype(kmer_type))
+        check(self.lib.kmu_sketch_pmh3a_groups(self.ctx, batch.handle, _p(gs, u64p), len(gs), k, kmer_type, hash_kind, m,
+                                               _p(out), 0))
         return out
 
     def pmh3a_weighted(self, keys, weights, m):

@@ -105,6 +105,8 @@ def main():
     one = eng.batch_synth(4, gnb[:1])
     ms = timed(eng, lambda: eng.sketch_pmh3a_whole(one, 16, kb.KMER16B32, kb.HASH_CANON_INVHASH, 12000), 2)
     line("probminhash3a whole-file (table + item kernel), one 5 Mb genome", 5_000_000, ms, 0.25 + 48000.0 / 5e6)
+    ms = timed(eng, lambda: eng.sketch_pmh3a_groups(gb_, np.ones(ng, dtype=np.uint64), 16, kb.KMER16B32, kb.HASH_CANON_INVHASH, 12000), 2)
+    line("probminhash3a whole-file, 32 genomes of 5 Mb in one call (kmu_sketch_pmh3a_groups)", gbases, ms, 0.25 + 48000.0 / 5e6)
     hll = torch.empty((ng, 4096), dtype=torch.int16, device=dev)
     ms = timed(eng, lambda: eng.sketch_setsketch(gb_, 16, kb.KMER16B32, kb.HASH_CANON_INVHASH, None, np.uint16, out_device_ptr=hll.data_ptr()), 2)
     line("setsketch per genome k=16 m=4096 u16", gbases, ms, 0.25 + 8192.0 / 5e6)

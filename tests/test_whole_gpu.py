@@ -135,3 +135,34 @@ def test_views_and_groups(engine, oracle):
     assert len(kmers) == int(np.maximum(nb[4:9].astype(np.int64) - 20, 0).sum())
     with pytest.raises(kb.KmuInvalid):
         engine.batch_view(batch, 9, 5)
+
+
+@pytest.mark.parametrize("k,ktype", [(16, kb.KMER16B32), (21, kb.KMER64), (8, kb.KMER32)])
+def test_pmh3a_groups_one_call(engine, oracle, k, ktype):
+    # kmu_sketch_pmh3a_groups == one kmu_sketch_pmh3a_whole per group; includes a group too short for a k-mer (zero
+    # signature), a one-contig genome and a highly repetitive genome (few distinct k-mers: its item bound fails and the
+    # group goes through the full procedure)
+    rng = np.random.default_rng(77 + k)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    unit = acgt[rng.integers(0, 4, 300)].tobytes()
+    seqs = [acgt[rng.integers(0, 4, int(n))].tobytes() for n in (5000, 800, 12000)]          # genome 0
+    seqs += [b"ACG"]                                                                          # genome 1: no k-mer (k > 3)
+    seqs += [acgt[rng.integers(0, 4, 40000)].tobytes()]                                       # genome 2
+    seqs += [unit * 60, unit * 45]                                                            # genome 3: tandem repeats
+    groups = [3, 1, 1, 2]
+    batch, bad = engine.batch_from_ascii(seqs)
+    assert bad.sum() == 0
+    packed, off, nb = batch.download()
+    packed = np.concatenate([packed, np.zeros(64, np.uint8)])
+    got = engine.sketch_pmh3a_groups(batch, groups, k, ktype, kb.HASH_CANON_INVHASH, 300)
+    first = 0
+    for gi, g in enumerate(groups):
+        sl = slice(first, first + g)
+        if k > 3 and gi == 1:
+            assert not got[gi].any()
+        else:
+            want = oracle.sketch_pmh3a_seqs(packed, off[sl], nb[sl], k, ktype, kb.HASH_CANON_INVHASH, 300)
+            assert np.array_equal(got[gi].astype(np.uint64), want), f"group {gi}"
+        first += g
+    with pytest.raises(kb.KmuInvalid):
+        engine.sketch_pmh3a_groups(batch, [3, 1], k, ktype, kb.HASH_CANON_INVHASH, 300)
