@@ -67,6 +67,24 @@ static int32_t smh_per_sequence_device(kmu_ctx* ctx, const kmu_seqbatch* b, uint
     P.ln_term = std::log(1e4 * (double)m);
     P.slow_count = d_work + 128;
     P.slow_list = (uint32_t*)ctx->overflow.p;
+    // small key spaces: point 0 of every possible pre-key, built once per parameter set and kept in the context
+    P.memo = nullptr;
+    if (!key64 && !kmer_type_is_aa(kmer_type) && k <= 8) {
+        const uint32_t nkeys = 1u << (2 * k);
+        if (!(ctx->smh_memo.p && ctx->smh_memo_k == k && ctx->smh_memo_m == m && ctx->smh_memo_type == kmer_type &&
+              ctx->smh_memo_hash == hash_kind && ctx->smh_memo_hasher == key_hasher && ctx->smh_memo_bytes == sig_bytes)) {
+            CUDA_TRY(ctx->smh_memo.reserve((size_t)nkeys * 16));
+            CUDA_TRY(kmu::launch_smh_memo(P, f64, ctx->smh_memo.p, nkeys, st));
+            ++*launches;
+            ctx->smh_memo_k = k;
+            ctx->smh_memo_m = m;
+            ctx->smh_memo_type = kmer_type;
+            ctx->smh_memo_hash = hash_kind;
+            ctx->smh_memo_hasher = key_hasher;
+            ctx->smh_memo_bytes = sig_bytes;
+        }
+        P.memo = ctx->smh_memo.p;
+    }
     // merge neighbouring octave classes that get the same team geometry: one launch each
     struct Launch { uint64_t first, count; TeamGeometry g; };
     std::vector<Launch> ls;

@@ -93,6 +93,9 @@ struct kmu_ctx {
     bool table_scratch_clean = false;
     PinnedBuf pinned, pinned_small;
     cudaEvent_t phase_ev[2]{};  // end of the main sketch launches of a chunk (host pipeline)
+    DevBuf smh_memo;  // SuperMinHash point 0 per pre-key (small key spaces), valid for the parameters below
+    uint32_t smh_memo_k = 0, smh_memo_m = 0;
+    int smh_memo_type = -1, smh_memo_hash = -1, smh_memo_hasher = -1, smh_memo_bytes = 0;
     cudaStream_t aux_stream = nullptr;  // the few-CTA launch of the very long sequences runs beside the main launches
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     // first-point table of the ProbMinHash3a kernels (small key spaces), see kmu_pmh3a.cu

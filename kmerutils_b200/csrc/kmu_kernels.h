@@ -171,7 +171,10 @@ struct SmhParams {
     uint32_t* slow_list;
     uint8_t* scratch;  // exact path
     uint64_t scratch_per_warp;
+    // small key spaces (u32 DNA k-mers, k <= 8): point 0 of every pre-key, {value bits lo, value bits hi, slot, 0}; or nullptr
+    const void* memo;
 };
+cudaError_t launch_smh_memo(const SmhParams& P, bool f64, void* memo, uint32_t nkeys, cudaStream_t st);
 cudaError_t launch_smh_fast(const SmhParams& P, bool key64, bool f64, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t launch_smh_whole(const SmhParams& P, bool key64, bool f64, const SeqView& b, uint64_t total_bytes, uint32_t a_spec,
                              void* gslots, int grid, size_t smem, cudaStream_t st);

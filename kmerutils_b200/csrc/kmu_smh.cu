@@ -158,6 +158,27 @@ __global__ void __launch_bounds__(1024, 1) smh_fast_kernel(const SmhParams P) {
         }
         for (uint32_t j = team.tid; j < m; j += team.size) h[j] = F::large();
         team.sync();
+        if (!AA && sizeof(V) == 4 && P.memo && a_spec == 0) {
+            // one point per item, straight from the per-key table: eight L2 lookups in flight per thread
+            const uint4* memo = (const uint4*)P.memo;
+            const uint32_t ntasks8 = (nk + 7) >> 3;
+            for (uint32_t task = team.tid; task < ntasks8; task += team.size) {
+                const uint32_t p0 = task << 3, nv = min(8u, nk - p0);
+                TaskKmers<uint32_t> tk8;
+                tk8.init(words, p0, k);
+                uint4 e[8];
+#pragma unroll
+                for (uint32_t t = 0; t < 8; ++t)
+                    if (t < nv) e[t] = __ldcg(memo + tk8.get(t, canonical));
+#pragma unroll
+                for (uint32_t t = 0; t < 8; ++t) {
+                    if (t < nv) {
+                        const B vb = sizeof(B) == 8 ? (B)(((unsigned long long)e[t].y << 32) | e[t].x) : (B)e[t].x;
+                        if (vb < *(volatile B*)(h + e[t].z)) atomicMin(h + e[t].z, vb);
+                    }
+                }
+            }
+        } else {
         const uint32_t ntasks = (nk + 15) >> 4;
         for (uint32_t task = team.tid; task < ntasks; task += team.size) {
             TK tk;
@@ -171,6 +192,7 @@ __global__ void __launch_bounds__(1024, 1) smh_fast_kernel(const SmhParams P) {
                 rng.seed(item_seed<V>(key, P.hasher));
                 smh_item_points<S>(rng, m, a_spec, h);
             }
+        }
         }
         team.sync();
         S* out = (S*)P.sig + (size_t)seq * m;
@@ -368,6 +390,29 @@ static cudaError_t launch_fast(const SmhParams& P, int grid, int block, size_t s
 template <typename V, bool AA>
 static cudaError_t launch_fast_s(const SmhParams& P, bool f64, int grid, int block, size_t smem, cudaStream_t st) {
     return f64 ? launch_fast<V, double, AA>(P, grid, block, smem, st) : launch_fast<V, float, AA>(P, grid, block, smem, st);
+}
+
+// point 0 of every pre-key of a small key space: what smh_item_points does for a_spec == 0, once per key
+template <typename S>
+__global__ void smh_memo_kernel(uint4* memo, uint32_t nkeys, SmhParams P) {
+    using F = FloatOps<S>;
+    const uint32_t header = word_header(P.kmer_type, P.k);
+    for (uint32_t pk = blockIdx.x * blockDim.x + threadIdx.x; pk < nkeys; pk += gridDim.x * blockDim.x) {
+        const uint32_t key = finalize_key<uint32_t>(pk, header, P.hash_kind);
+        Xoshiro256pp rng;
+        rng.seed(item_seed<uint32_t>(key, P.hasher));
+        const S r = F::draw(rng);
+        const uint32_t slot = unif_from(rng, 0, P.m);
+        const unsigned long long vb = (unsigned long long)F::bits(r);
+        memo[pk] = make_uint4((uint32_t)vb, (uint32_t)(vb >> 32), slot, 0u);
+    }
+}
+
+cudaError_t launch_smh_memo(const SmhParams& P, bool f64, void* memo, uint32_t nkeys, cudaStream_t st) {
+    const int grid = (int)std::min<uint32_t>((nkeys + 255) / 256, 148 * 8);
+    if (f64) smh_memo_kernel<double><<<grid, 256, 0, st>>>((uint4*)memo, nkeys, P);
+    else smh_memo_kernel<float><<<grid, 256, 0, st>>>((uint4*)memo, nkeys, P);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_smh_fast(const SmhParams& P, bool key64, bool f64, int grid, int block, size_t smem, cudaStream_t st) {
