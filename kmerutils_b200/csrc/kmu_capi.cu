@@ -181,6 +181,7 @@ void kmu_ctx_destroy(kmu_ctx* c) {
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->lev) cudaEventDestroy(ev);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->redo_stream) cudaStreamDestroy(c->redo_stream);
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     if (c->join_ev) cudaEventDestroy(c->join_ev);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -876,7 +877,8 @@ extern "C" {
 // them and redo the sequences they flagged.  The host pipeline runs 1 and 2 apart so that it can
 // prepare the next chunk while the device works.
 static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_t kmer_type,
-                                   int32_t hash_kind, uint32_t m, void* d_sig, int phase = 0, int scratch_set = 0) {
+                                   int32_t hash_kind, uint32_t m, void* d_sig, int phase = 0, int scratch_set = 0,
+                                   bool redo_aside = false) {
     DevBuf& counters = scratch_set ? ctx->counters_alt : ctx->counters;
     DevBuf& overflow = scratch_set ? ctx->overflow_alt : ctx->overflow;
     const bool key64 = kmer_type_is_u64(kmer_type);
@@ -1013,7 +1015,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         P.memo_fast = ctx->memo.p;
     }
 
-    auto run_class = [&](const LaunchClass& c, const uint32_t* order, int counter_idx, bool speculate) -> int32_t {
+    auto run_class = [&](const LaunchClass& c, const uint32_t* order, int counter_idx, bool speculate, cudaStream_t st) -> int32_t {
         Geometry g = make_geometry(c.nk_max, c.mode, k, m, key64, c.table_global, aa);
         uint64_t teams_needed = c.count;
         uint64_t ctas_needed = (teams_needed + g.teams_per_cta - 1) / g.teams_per_cta;
@@ -1097,6 +1099,12 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     int ci = 0;
     uint64_t form_first = 0;
     bool join_aux = false;
+    const bool use_side = !ctx->profiling && phase != 2 && form_count[1] > 0;
+    if (use_side && !ctx->aux_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
+    }
     for (int form = 0; form < 3 && phase != 2; form_first += form_count[form], ++form) {
         const uint64_t count = form_count[form];
         if (!count) continue;
@@ -1120,19 +1128,16 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
             cudaEventRecord(ctx->lev[2 * li], st);
         }
         // the very long sequences are few (a handful of CTAs, each busy for a long time): their launch runs on a
-        // side stream next to the other forms instead of in front of them (profiling runs time it alone)
-        const bool aside = form == 0 && !ctx->profiling && count < (uint64_t)grid + 1 && count < 2 * (uint64_t)ctx->sm_count;
+        // side stream next to the other forms instead of in front of them (profiling runs time it alone).  Putting
+        // the short form and the team-kernel classes there as well was measured: slower (the kernels compete).
+        const bool aside = use_side && form == 0 && count < (uint64_t)grid + 1 && count < 2 * (uint64_t)ctx->sm_count;
         if (aside) {
-            if (!ctx->aux_stream) {
-                CUDA_TRY(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
-                CUDA_TRY(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
-                CUDA_TRY(cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
+            if (!join_aux) {
+                CUDA_TRY(cudaEventRecord(ctx->fork_ev, st));
+                CUDA_TRY(cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_ev, 0));
+                join_aux = true;
             }
-            CUDA_TRY(cudaEventRecord(ctx->fork_ev, st));
-            CUDA_TRY(cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_ev, 0));
             CUDA_TRY(kmu::launch_pmh3a_direct(Q, grid, variant, ctx->aux_stream));
-            CUDA_TRY(cudaEventRecord(ctx->join_ev, ctx->aux_stream));
-            join_aux = true;
         } else {
             CUDA_TRY(kmu::launch_pmh3a_direct(Q, grid, variant, st));
         }
@@ -1159,9 +1164,13 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     const size_t lrec_base = ctx->lrec.size();
     if (phase != 2)
         for (const LaunchClass& c : classes) {
-            int32_t rc = run_class(c, d_order, ci++, true);
+            int32_t rc = run_class(c, d_order, ci++, true, st);
             if (rc) return rc;
         }
+    if (join_aux) {
+        CUDA_TRY(cudaEventRecord(ctx->join_ev, ctx->aux_stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, ctx->join_ev, 0));
+    }
     if (ctx->profiling && phase != 2) {
         // bases per launch: class i covers the sequences whose length bucket start lies in its range
         for (uint64_t L : b->h_nbases) {
@@ -1174,7 +1183,6 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
                 }
         }
     }
-    if (join_aux) CUDA_TRY(cudaStreamWaitEvent(st, ctx->join_ev, 0));
     // ---- sequences whose u8 histogram counters wrapped or whose speculative qmax bound failed:
     //      redo them with u32 table counters and without speculation ---------------------------
     if (phase == 1) {
@@ -1202,7 +1210,22 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
             c.nk_max = nk_longest;
             c.mode = 1;
             c.table_global = true;
-            int32_t rc = run_class(c, (const uint32_t*)overflow.p, 127, false);
+            // host pipeline: the redo launch of this chunk runs on a side stream while the next chunk's main launches
+            // (already queued on the main stream) proceed, unless those share the global scratch (slots / tables) with it
+            bool aside = redo_aside && phase == 2;
+            for (const LaunchClass& mc : classes) {
+                Geometry mg = make_geometry(mc.nk_max, mc.mode, k, m, key64, mc.table_global, aa);
+                if (mg.slots_smem_bytes == 0 || mg.table_entries_global) aside = false;
+            }
+            cudaStream_t rs = st;
+            if (aside) {
+                if (!ctx->redo_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->redo_stream, cudaStreamNonBlocking));
+                rs = ctx->redo_stream;  // the host has waited for this chunk's main launches: no event needed
+                ctx->redo_on_side = true;
+            } else {
+                ctx->redo_on_main = true;
+            }
+            int32_t rc = run_class(c, (const uint32_t*)overflow.p, 127, false, rs);
             if (rc) return rc;
         }
     }
@@ -1408,36 +1431,47 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
         return KMU_OK;
     };
     stamp("layout done, chunks", nchunks);
-    int32_t rc = upload(0);
-    stamp("upload enqueued", 0);
-    // Per chunk c: [phase 1] enqueue its sketch launches; meanwhile lay out + upload chunk c + 1 and build its
-    // processing order (host histogram + one scatter kernel queued behind chunk c); [phase 2] wait for chunk c, redo
-    // the sequences it flagged; start the download.  The gap between two chunks is the launch overhead only.
+    // Per chunk c: upload chunk c + 1, build its processing order and queue its sketch launches [phase 1] behind
+    // chunk c's on the main stream -- the GPU goes from one chunk to the next without waiting for the host; then wait
+    // for chunk c's launches, redo the sequences it flagged [phase 2] on a side stream beside chunk c + 1, and start
+    // the download.
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    for (size_t c = 0; c < nchunks && rc == KMU_OK; ++c) {
+    // main launches of chunk c: chunk-local order + phase 1; compute_done[slot] marks their end (phase 2 moves it
+    // behind the redo launch when there is one)
+    auto enqueue_main = [&](size_t c) -> int32_t {
         const int sl = (int)(c & 1);
         CUDA_TRY(cudaStreamWaitEvent(ctx->stream, hp.in_done[sl], 0));
-        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, hp.out_done[sl], 0));  // signature slot free again
-        const int sset = sl;  // two sets of counters / redo lists: a chunk's redo launch may still run when the next chunk starts
-        rc = sketch_pmh3a_locked(ctx, &views[c], k, kmer_type, hash_kind, m, hp.sig[sl].p, 1, sset);
-        if (rc) break;
+        if (c >= 2) {
+            CUDA_TRY(cudaStreamWaitEvent(ctx->stream, hp.out_done[sl], 0));      // signature slot free again
+            CUDA_TRY(cudaStreamWaitEvent(ctx->stream, hp.compute_done[sl], 0));  // and the redo launch that used this scratch set
+        }
+        int32_t r = kmu_ensure_order(ctx, &views[c], k, nullptr);
+        // two sets of counters / redo lists: the redo launch of chunk c runs while chunk c + 1 is sketched
+        if (!r) r = sketch_pmh3a_locked(ctx, &views[c], k, kmer_type, hash_kind, m, hp.sig[sl].p, 1, sl);
+        if (!r) CUDA_TRY(cudaEventRecord(hp.compute_done[sl], ctx->stream));
         stamp("sketch enqueued", c);
+        return r;
+    };
+    int32_t rc = upload(0);
+    stamp("upload enqueued", 0);
+    if (!rc) rc = enqueue_main(0);
+    for (size_t c = 0; c < nchunks && rc == KMU_OK; ++c) {
+        const int sl = (int)(c & 1);
         if (c + 1 < nchunks) {
             rc = upload(c + 1);
+            if (!rc) rc = enqueue_main(c + 1);
             if (rc) break;
-            CUDA_TRY(cudaStreamWaitEvent(ctx->stream, hp.in_done[sl ^ 1], 0));
-            rc = kmu_ensure_order(ctx, &views[c + 1], k, nullptr);
-            if (rc) break;
-            stamp("next chunk uploaded + ordered", c + 1);
         }
-        rc = sketch_pmh3a_locked(ctx, &views[c], k, kmer_type, hash_kind, m, hp.sig[sl].p, 2, sset);
+        ctx->redo_on_side = ctx->redo_on_main = false;
+        rc = sketch_pmh3a_locked(ctx, &views[c], k, kmer_type, hash_kind, m, hp.sig[sl].p, 2, sl, true);
         stamp("sketch finished", c);
         if (rc) break;
         hp.order[sl] = views[c].order_cache.order;
         hp.cursor[sl] = views[c].order_cache.cursor_dev;
         views[c].order_cache.order = DevBuf{};
         views[c].order_cache.cursor_dev = DevBuf{};
-        CUDA_TRY(cudaEventRecord(hp.compute_done[sl], ctx->stream));
+        if (ctx->redo_on_side) CUDA_TRY(cudaEventRecord(hp.compute_done[sl], ctx->redo_stream));
+        else if (ctx->redo_on_main) CUDA_TRY(cudaEventRecord(hp.compute_done[sl], ctx->stream));  // behind the next chunk's launches
         CUDA_TRY(cudaStreamWaitEvent(hp.copy_out, hp.compute_done[sl], 0));
         const size_t out_bytes = (size_t)views[c].nseq * m * vsz;
         CUDA_TRY(cudaEventRecord(hp.out_begin[sl], hp.copy_out));
@@ -1446,6 +1480,11 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
         CUDA_TRY(cudaEventRecord(hp.out_done[sl], hp.copy_out));
         timed_out[sl] = 1;
         ctx->last.d2h_bytes += out_bytes;
+    }
+    if (ctx->redo_stream) {  // the last redo launch belongs to the timed region
+        if (!ctx->join_ev) cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming);
+        cudaEventRecord(ctx->join_ev, ctx->redo_stream);
+        cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0);
     }
     cudaEventRecord(ctx->ev[1], ctx->stream);
     cudaError_t e1 = cudaStreamSynchronize(hp.copy_in);

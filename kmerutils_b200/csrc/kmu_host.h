@@ -98,6 +98,8 @@ struct kmu_ctx {
     int smh_memo_type = -1, smh_memo_hash = -1, smh_memo_hasher = -1, smh_memo_bytes = 0;
     cudaStream_t aux_stream = nullptr;  // the few-CTA launch of the very long sequences runs beside the main launches
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    cudaStream_t redo_stream = nullptr;  // host pipeline: the redo launch of a chunk runs beside the next chunk
+    bool redo_on_side = false, redo_on_main = false;  // ... where the last phase-2 call put its redo launch, if any
     // first-point table of the ProbMinHash3a kernels (small key spaces), see kmu_pmh3a.cu
     DevBuf memo;
     uint32_t memo_k = 0, memo_m = 0;
