@@ -920,7 +920,7 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
     //   [key_long, key_vlong)      4-bit counters, one point per occurrence
     //   [key_short, key_long)      4-bit counters, two points per occurrence
     int form_key[4] = {kmu::LEN_BUCKETS, 16 * 8 + 4, 11 * 8, 9 * 8 + 4};  // 98304, 2048, 768 k-mers
-    int form_variant[3] = {0, 11, 5};
+    int form_variant[3] = {0, 1, 2};
     if (const char* env = std::getenv("KMU_DIRECT_KEYS")) std::sscanf(env, "%d,%d,%d", &form_key[1], &form_key[2], &form_key[3]);
     if (const char* env = std::getenv("KMU_DIRECT_VARIANTS")) std::sscanf(env, "%d,%d,%d", &form_variant[0], &form_variant[1], &form_variant[2]);
     form_key[2] = std::min(form_key[2], form_key[1]);

@@ -412,28 +412,37 @@ static cudaError_t launch_direct_t(const Pmh3aParams& P, int grid, size_t smem, 
     return cudaGetLastError();
 }
 
-// variant 0: 8-bit counters, 512 threads, two sequences per SM, one point per occurrence (very long sequences);
-// 5: 4-bit counters, 256 threads, four sequences per SM, two points per occurrence (short sequences); 6: the same
-// with one point per occurrence (long sequences); 9, 10, 11: 0, 5, 6 with TMA staging; the others: experiments
-int pmh3a_direct_ctas_per_sm(int variant) { return variant == 7 || variant == 8 ? 5 : (variant >= 4 && variant != 9 ? 4 : 2); }
-int pmh3a_direct_threads(int variant) { return variant >= 3 && variant != 9 ? 256 : 512; }
-bool pmh3a_direct_lists(int variant) { return variant == 1 || variant == 5 || variant == 10; }
-size_t pmh3a_direct_stage_bytes(int variant) { return variant == 9 ? 8192 : (variant == 10 || variant == 11 ? 4096 : 0); }
+// The forms of the kernel (kmu_capi.cu picks one per length class):
+//   0  very long sequences: 8-bit counters, 512 threads, two sequences per SM, one point per occurrence
+//   1  long sequences: 4-bit counters, 256 threads, four sequences per SM, one point per occurrence, TMA staging
+//   2  short sequences: as 1 without staging, two points per occurrence, items from the keys seen twice
+//   3  as 1 without staging (measurements)
+struct DirectForm {
+    int threads, ctas_per_sm, hist_bits, stage_bytes;
+    bool lists;
+};
+static DirectForm direct_form(int variant) {
+    switch (variant) {
+        case 0: return {512, 2, 8, 0, false};
+        case 2: return {256, 4, 4, 0, true};
+        case 3: return {256, 4, 4, 0, false};
+        default: return {256, 4, 4, 4096, false};
+    }
+}
+int pmh3a_direct_ctas_per_sm(int variant) { return direct_form(variant).ctas_per_sm; }
+int pmh3a_direct_threads(int variant) { return direct_form(variant).threads; }
+bool pmh3a_direct_lists(int variant) { return direct_form(variant).lists; }
+size_t pmh3a_direct_stage_bytes(int variant) { return (size_t)direct_form(variant).stage_bytes; }
 size_t pmh3a_direct_hist_bytes(uint32_t k, int variant) {
-    size_t hist = (size_t)1 << (2 * k);
-    if (variant >= 4 && variant != 9) hist /= 2;
+    const size_t hist = ((size_t)1 << (2 * k)) * direct_form(variant).hist_bits / 8;
     return hist < 16 ? 16 : hist;
 }
 cudaError_t launch_pmh3a_direct(const Pmh3aParams& P, int grid, int variant, cudaStream_t stream) {
     const size_t smem = pmh3a_direct_smem_bytes(P.k, P.m, variant);
     switch (variant) {
         case 0: return launch_direct_t<512, 2, 8, 1, false>(P, grid, smem, stream);
-        case 1: return launch_direct_t<512, 2, 4, 2, true>(P, grid, smem, stream);
-        case 4: return launch_direct_t<256, 4, 8, 1, false, 4>(P, grid, smem, stream);
-        case 5: return launch_direct_t<256, 4, 4, 2, true, 4>(P, grid, smem, stream);
-        case 6: return launch_direct_t<256, 4, 4, 1, false, 4>(P, grid, smem, stream);
-        case 9: return launch_direct_t<512, 2, 8, 1, false, 8, 8192>(P, grid, smem, stream);
-        case 10: return launch_direct_t<256, 4, 4, 2, true, 4, 4096>(P, grid, smem, stream);
+        case 2: return launch_direct_t<256, 4, 4, 2, true, 4>(P, grid, smem, stream);
+        case 3: return launch_direct_t<256, 4, 4, 1, false, 4>(P, grid, smem, stream);
         default: return launch_direct_t<256, 4, 4, 1, false, 4, 4096>(P, grid, smem, stream);
     }
 }
