@@ -394,6 +394,21 @@ struct TaskKmers<uint32_t> {
         uint32_t r = (uint32_t)(RC >> (2 * j)) & mask;
         return f < r ? f : r;
     }
+    // Tasks of NT positions with 2 (NT - 1) + 2 k <= 32: all windows of the task sit in one 32-bit word per strand, so
+    // that get_narrow(t) with a compile-time t is a constant shift and a mask.  Call narrow<NT>() once after init.
+    uint32_t w32, rc32;
+    template <int NT>
+    __device__ __forceinline__ void narrow() {
+        w32 = (uint32_t)(W >> (sh0 - 2 * (j0 + NT - 1)));
+        rc32 = (uint32_t)(RC >> (2 * j0));
+    }
+    template <int NT>
+    __device__ __forceinline__ uint32_t get_narrow(uint32_t t, bool canonical) const {
+        const uint32_t f = (w32 >> (2 * (NT - 1 - t))) & mask;
+        if (!canonical) return f;
+        const uint32_t r = (rc32 >> (2 * t)) & mask;
+        return f < r ? f : r;
+    }
 };
 
 template <>

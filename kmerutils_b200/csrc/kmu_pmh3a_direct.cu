@@ -185,11 +185,12 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
             const uint32_t nv = min(tlen, seg_nk - p0);
             TaskKmers<uint32_t> tk;
             tk.init(seg_words, p0, k);
+            tk.template narrow<T>();  // k <= 8, T <= 8: 2 (T - 1) + 2 k <= 30 bits
             uint32_t pk[T];
             uint4 e1[T], e2[T];
 #pragma unroll
             for (uint32_t t = 0; t < T; ++t) {
-                pk[t] = tk.get(t, canonical);
+                pk[t] = tk.template get_narrow<T>(t, canonical);
                 if (t < nv) {  // independent L2 lookups in flight (both points sit in one 32-byte sector)
                     e1[t] = __ldcg(memo + 2 * pk[t]);  // L2 only: L1 keeps the sequence bytes
                     if (NP == 2) e2[t] = __ldcg(memo + 2 * pk[t] + 1);
