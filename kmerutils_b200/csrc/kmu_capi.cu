@@ -960,6 +960,12 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
         // structure does not depend on the length (histogram, or table in global memory): one launch
         if (!classes.empty()) {
             LaunchClass& p = classes.back();
+            // a handful of sequences is not worth a launch of its own (0.1 ms whatever its size): they join the
+            // class above, whose histogram / table is large enough for anything shorter
+            if (c.count <= 2 * (uint64_t)ctx->sm_count && p.first + p.count == c.first) {
+                p.count += c.count;
+                continue;
+            }
             if (p.mode == c.mode && p.table_global == c.table_global && (c.mode == 0 || c.table_global)) {
                 Geometry gp = make_geometry(p.nk_max, p.mode, k, m, key64, p.table_global, aa);
                 Geometry gc = make_geometry(c.nk_max, c.mode, k, m, key64, c.table_global, aa);
