@@ -277,6 +277,12 @@ int32_t kmu_count_export(kmu_ctx* ctx, const kmu_counter* counter, uint32_t min_
  * least twice (each once, unordered).  count_bytes 1 or 2. */
 int32_t kmu_count_dump_multiple(kmu_ctx* ctx, const kmu_counter* counter, const char* path, int32_t count_bytes,
                                 uint64_t* nb_dumped);
+
+/* partial registers of a counting table, for the multi-GPU whole-file sketch (every rank counts the keys it owns,
+ * sketches them; the ranks merge with an allreduce-min on h and a key select): slots = m records {u64 h bits, u64 key},
+ * h = largest f64 where no point fell below `bound`.  The table's keys are pre-keys (as inserted); hash_kind maps them. */
+int32_t kmu_pmh3a_counter_slots(kmu_ctx* ctx, const kmu_counter* counter, int32_t hash_kind, uint32_t m, double bound,
+                                void* slots, int32_t slots_on_device);
 /* DispatchableT::dispatch (kmercount.rs:382-420) for a whole batch: all (canonical) compressed k-mer
  * values bucketed by owner = intNN_hash(value) % nparts.  kmers_out holds kmu_kmer_count() values,
  * bucket p first-to-last at offset sum(part_counts[0..p)).  This is the send side of the multi-GPU

@@ -86,6 +86,7 @@ SIGNATURES = {
                                            C.c_int32]),
     "kmu_sketch_pmh3a_groups": (C.c_int32, [C.c_void_p, C.c_void_p, u64p, C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32,
                                             C.c_void_p, C.c_int32]),
+    "kmu_pmh3a_counter_slots": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint32, C.c_double, C.c_void_p, C.c_int32]),
     "kmu_pmh3a_weighted": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_uint32, C.c_void_p]),
     "kmu_sketch_superminhash": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32,
                                             C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),

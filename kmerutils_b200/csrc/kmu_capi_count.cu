@@ -485,8 +485,10 @@ static void fill_exp01(kmu::Exp01Params& e, uint32_t m) {
 }
 
 // runs the item kernel with growing bounds until every slot ended below the bound
+// wmax: a lower bound of the largest weight in the set (1 for multiplicity tables).  The heaviest item alone fills every
+// slot below m (ln m + 40) / wmax with probability 1 - e^-40: the bound never has to grow beyond that.
 static int32_t run_pmh3a_items(kmu_ctx* ctx, kmu::Pmh3aItemsParams P, bool key64, int src, uint64_t distinct, void* d_sig,
-                               uint64_t* launches) {
+                               uint64_t* launches, double wmax = 1.0) {
     cudaStream_t st = ctx->stream;
     const uint32_t m = P.m;
     CUDA_TRY(ctx->items_slots.reserve(sizeof(kmu::Slot) * m + 64));
@@ -498,7 +500,8 @@ static int32_t run_pmh3a_items(kmu_ctx* ctx, kmu::Pmh3aItemsParams P, bool key64
     fill_exp01(P.e, m);
     const uint64_t work = (P.n + 511) / 512;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(work, (uint64_t)ctx->sm_count));
-    double bound = distinct ? (double)m / (double)distinct * std::log((double)m / 1e-4) : 1.0;
+    const double bound_max = (double)m * (std::log((double)m) + 40.0) / wmax;
+    double bound = distinct ? std::min(bound_max, (double)m / (double)distinct * std::log((double)m / 1e-4)) : 1.0;
     for (int attempt = 0; attempt < 200; ++attempt) {
         P.bound = bound;
         CUDA_TRY(kmu::launch_pmh3a_items_init(P.global_slots, m, st));
@@ -512,8 +515,8 @@ static int32_t run_pmh3a_items(kmu_ctx* ctx, kmu::Pmh3aItemsParams P, bool key64
         double top;
         std::memcpy(&top, &mx, 8);
         if (distinct == 0 || top < bound) return KMU_OK;  // every slot filled below the bound: nothing pruned could win
-        bound *= 4.0;
-        if (!(bound < 1e300)) break;
+        if (bound >= bound_max) break;
+        bound = std::min(bound_max, bound * 4.0);
     }
     return fail(KMU_ECUDA, "ProbMinHash3a item sketch did not converge");
 }
@@ -545,7 +548,9 @@ int32_t kmu_pmh3a_weighted(kmu_ctx* ctx, const void* keys, const double* weights
     P.m = m;
     uint64_t launches = 0;
     cudaEventRecord(ctx->ev[0], st);
-    int32_t rc = run_pmh3a_items(ctx, P, key_bytes == 8, 0, n, d_sig, &launches);
+    double wmax = 0.0;
+    for (uint64_t i = 0; i < n; ++i) wmax = std::max(wmax, weights[i]);
+    int32_t rc = run_pmh3a_items(ctx, P, key_bytes == 8, 0, n, d_sig, &launches, n ? wmax : 1.0);
     cudaEventRecord(ctx->ev[1], st);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(sig, d_sig, sb, cudaMemcpyDeviceToHost, st));
@@ -625,6 +630,50 @@ int32_t kmu_sketch_pmh3a_whole(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, 
     cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
     ctx->launches += launches;
     ctx->last.launches = launches;
+    return KMU_OK;
+}
+
+// Partial ProbMinHash3a registers of a counting table (the multi-GPU whole-file sketch: every rank owns the complete
+// counts of the keys that hash to it, sketches them, and the ranks merge their registers with an allreduce-min on h
+// and a key select).  slots: m records {h bits (u64; F64 max when the slot saw no point below `bound`),
+// key (u64)}; items are cut at `bound` as in kmu_sketch_pmh3a_whole -- the caller checks the MERGED maximum against it.
+int32_t kmu_pmh3a_counter_slots(kmu_ctx* ctx, const kmu_counter* c, int32_t hash_kind, uint32_t m, double bound, void* slots,
+                                int32_t slots_on_device) {
+    if (!ctx || !c || !slots) return fail(KMU_EINVAL, "null argument");
+    if (m < 2) return fail(KMU_EINVAL, "ProbMinHash3a needs at least 2 hash values (m = %u)", m);
+    if (hash_kind < KMU_HASH_IDENTITY_RAW || hash_kind > KMU_HASH_INVHASH) return fail(KMU_EINVAL, "unknown hash kind %d", hash_kind);
+    if (!(bound > 0.0)) return fail(KMU_EINVAL, "the item bound must be positive");
+    // an item emits (bound x count) points: one key alone fills all m slots below m (ln m + 40) with probability
+    // 1 - e^-40, so nothing larger is ever needed -- and a much larger bound would keep the GPU busy for hours
+    if (bound > (double)m * (std::log((double)m) + 40.0))
+        return fail(KMU_EINVAL, "item bound %g is beyond m (ln m + 40) = %g", bound, (double)m * (std::log((double)m) + 40.0));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx->items_slots.reserve(sizeof(kmu::Slot) * m + 64));
+    kmu::Pmh3aItemsParams P{};
+    const kmu::CountTable t = c->view();
+    P.table = t.slots;
+    P.special = t.special;
+    P.n = c->capacity;
+    P.k = c->k;
+    P.kmer_type = c->kmer_type;
+    P.hash_kind = hash_kind;
+    P.m = m;
+    P.global_slots = (kmu::Slot*)ctx->items_slots.p;
+    const size_t smem = sizeof(kmu::Slot) * (size_t)m;
+    P.slots_in_smem = smem <= SMEM_BUDGET ? 1 : 0;
+    P.slot_thresh = (uint32_t)(0x100000000ULL % m);
+    fill_exp01(P.e, m);
+    P.bound = bound;
+    const uint64_t work = (P.n + 511) / 512;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(work, (uint64_t)ctx->sm_count));
+    CUDA_TRY(kmu::launch_pmh3a_items_init(P.global_slots, m, st));
+    CUDA_TRY(kmu::launch_pmh3a_items(P, c->key64, c->key64 ? 2 : 1, grid, P.slots_in_smem ? smem : 0, st));
+    CUDA_TRY(cudaMemcpyAsync(slots, P.global_slots, sizeof(kmu::Slot) * m, slots_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ctx->launches += 2;
+    ctx->last.launches = 2;
     return KMU_OK;
 }
 

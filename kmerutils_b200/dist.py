@@ -222,3 +222,60 @@ def count_sharded_p2p(engine, batch, k, kmer_type, counter, xchg, canonical=True
     if world > 1:
         dist.barrier(group=group)  # the buffers may be overwritten by the next round
     return recv_total
+
+
+def merge_pmh3a_registers(hbits, keys, device, group=None):
+    """ProbMinHash3a registers are per-slot minima of (h, key): across ranks an allreduce-min on h (positive doubles
+    order like their bit patterns) and, among the ranks that hold that minimum, the smallest key.  hbits, keys: u64
+    arrays of m entries (numpy).  -> (hbits, keys) of the merged sketch, identical on every rank."""
+    h = np.ascontiguousarray(hbits, dtype=np.uint64)
+    kk = np.ascontiguousarray(keys, dtype=np.uint64)
+    if _world(group)[1] == 1:
+        return h, kk
+    th = torch.from_numpy(h.view(np.int64).copy()).to(device)  # h > 0: the sign bit is clear
+    tmin = th.clone()
+    dist.all_reduce(tmin, op=dist.ReduceOp.MIN, group=group)
+    # keys as signed integers that order like the unsigned ones; ranks without the minimum stay out of the way
+    flipped = torch.from_numpy((kk ^ np.uint64(1 << 63)).view(np.int64).copy()).to(device)
+    cand = torch.where(th == tmin, flipped, torch.full_like(flipped, torch.iinfo(torch.int64).max))
+    dist.all_reduce(cand, op=dist.ReduceOp.MIN, group=group)
+    out_h = tmin.cpu().numpy().view(np.uint64)
+    out_k = cand.cpu().numpy().view(np.uint64) ^ np.uint64(1 << 63)
+    return out_h, out_k
+
+
+def pmh3a_whole_sharded(engine, batch, k, kmer_type, hash_kind, m, group=None):
+    """ProbHash3aSketch::sketch_compressedkmer_seqs (setsketchert.rs:160-202) for a file spread over the ranks: the
+    k-mers go to the rank that owns them (count_sharded: every key's multiplicity is complete on one GPU), every rank
+    sketches its keys into partial registers, the registers are merged (merge_pmh3a_registers).  Items are cut at a
+    bound; the merged maximum must stay below it, else the bound grows and the registers are rebuilt -- the same
+    verification as on one GPU.  -> signature (m values), identical on every rank"""
+    import math
+
+    import kmerutils_b200 as kb
+
+    rank, world = _world(group)
+    dev = torch.device("cuda", engine.device)
+    canonical = hash_kind in (kb.HASH_CANON_INVHASH, kb.HASH_CANON_RAW)
+    nk_local = batch.kmer_count(k)
+    nk_total = allreduce_sum([nk_local], dev, group)[0]
+    cap = max(1024, int(nk_total * 1.5 / world) + 1024)
+    counter, stats = count_sharded(engine, batch, k, kmer_type, cap, count_bits=32, canonical=canonical, group=group)
+    distinct = stats["nb_distinct"]
+    sig_dtype = kb.val_dtype(kmer_type)
+    if distinct == 0:
+        counter.destroy()
+        return np.zeros(m, dtype=sig_dtype)
+    bound_max = m * (math.log(m) + 40.0)  # one key alone fills every slot below this (kmu_pmh3a_counter_slots refuses more)
+    bound = min(bound_max, m / distinct * math.log(m / 1e-4))
+    while True:
+        h, keys = engine.pmh3a_counter_slots(counter, hash_kind, m, bound)
+        h, keys = merge_pmh3a_registers(h, keys, dev, group)
+        top = float(h.view(np.float64).max())
+        if top < bound:
+            counter.destroy()
+            return keys.astype(sig_dtype)
+        if bound >= bound_max:
+            counter.destroy()
+            raise RuntimeError("ProbMinHash3a sharded sketch did not converge")
+        bound = min(bound_max, bound * 4.0)

@@ -341,6 +341,13 @@ class Engine:
                                                _p(out), 0))
         return out
 
+    def pmh3a_counter_slots(self, counter, hash_kind, m, bound):
+        """Partial ProbMinHash3a registers of a counting table (kmu_pmh3a_counter_slots): -> (h bits u64[m], key u64[m]);
+        h bits == the largest f64 where no point fell below `bound`."""
+        out = np.zeros((m, 2), dtype=np.uint64)
+        check(self.lib.kmu_pmh3a_counter_slots(self.ctx, counter._h, hash_kind, m, float(bound), _p(out), 0))
+        return out[:, 0].copy(), out[:, 1].copy()
+
     def pmh3a_weighted(self, keys, weights, m):
         """ProbMinHash3a::hash_weigthed_hashmap on explicit (key, weight) arrays; keys u32 or u64."""
         keys = np.ascontiguousarray(keys)

@@ -45,6 +45,9 @@ def main():
     hll = kd.merge_registers(torch.from_numpy(hll_local.astype(np.int32)).cuda(), "max").cpu().numpy().astype(np.uint16)
     smh_local = eng.sketch_superminhash(mine, 21, kb.KMER64, kb.HASH_CANON_INVHASH, 256).min(axis=0)
     smh = kd.merge_registers(torch.from_numpy(smh_local).cuda(), "min").cpu().numpy()
+    # whole-file ProbMinHash3a over the shards: owners count, sketch their keys, registers merge (min h, then key)
+    pmh = {kk: kd.pmh3a_whole_sharded(eng, mine, kk, kt, kb.HASH_CANON_INVHASH, 500)
+           for kk, kt in ((21, kb.KMER64), (16, kb.KMER16B32))}
     ok = True
     if rank == 0:
         from oracle_lib import get_oracle
@@ -70,6 +73,11 @@ def main():
         want_smh = orc.sketch_superminhash_seqs(buf, off, nb, 21, kb.KMER64, kb.HASH_CANON_INVHASH, 256)
         ok &= bool(np.array_equal(smh, want_smh))
         print(f"[dist_check] setsketch merge ok={np.array_equal(hll, want_hll)} superminhash merge ok={np.array_equal(smh, want_smh)}", flush=True)
+        for kk, kt in ((21, kb.KMER64), (16, kb.KMER16B32)):
+            want_pmh = orc.sketch_pmh3a_seqs(buf, off, nb, kk, kt, kb.HASH_CANON_INVHASH, 500)
+            same = bool(np.array_equal(pmh[kk].astype(np.uint64), want_pmh))
+            ok &= same
+            print(f"[dist_check] whole-file probminhash3a over {world} ranks, k={kk}: ok={same}", flush=True)
         probe = keys[:: max(1, len(keys) // 5000)]
         probe_want = np.minimum(cnts[:: max(1, len(keys) // 5000)], 255).astype(np.uint32)
     else:

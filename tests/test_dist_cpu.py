@@ -102,6 +102,16 @@ def _worker(rank, world, port, tmp):
         rows = kd.gather_rows(torch.from_numpy(sig.astype(np.int64)))
         want_sig = oracle.sketch_pmh3a_batch(buf, off, nb_all, 8, ol.KMER32, ol.HASH_CANON_INVHASH, 32, 1)
         assert np.array_equal(rows.numpy().astype(np.uint32), want_sig)
+        # ---- ProbMinHash3a registers: per-slot minimum of (h, key) over the ranks ----
+        rng = np.random.default_rng(99)  # same stream on every rank: all ranks' registers are known everywhere
+        hs = rng.random((world, 64)) + 1e-9
+        ks = rng.integers(0, 2**64, (world, 64), dtype=np.uint64)  # keys beyond 2^63 too
+        hs[1, :8] = hs[0, :8]  # equal h on both ranks: the smaller key wins
+        hs[0, 8:12] = np.finfo(np.float64).max  # slots one rank never filled
+        mh, mk = kd.merge_pmh3a_registers(hs[rank].view(np.uint64), ks[rank], "cpu")
+        for j in range(64):
+            best = min(range(world), key=lambda r: (hs[r, j], int(ks[r, j])))
+            assert mh[j] == hs[best, j].view(np.uint64) and mk[j] == ks[best, j], j
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -166,3 +166,25 @@ def test_pmh3a_groups_one_call(engine, oracle, k, ktype):
         first += g
     with pytest.raises(kb.KmuInvalid):
         engine.sketch_pmh3a_groups(batch, [3, 1], k, ktype, kb.HASH_CANON_INVHASH, 300)
+
+
+def test_pmh3a_counter_slots_match_whole_file(engine, oracle):
+    # the building block of the multi-GPU whole-file sketch: registers (h, key) of a counting table == the whole-file
+    # signature once the bound covers every slot; a bound that is too small leaves slots at the f64 maximum
+    nb = np.array([30000, 12000, 700], dtype=np.uint64)
+    batch = engine.batch_synth(91, nb)
+    k, ktype, m = 21, kb.KMER64, 300
+    want = engine.sketch_pmh3a_whole(batch, k, ktype, kb.HASH_CANON_INVHASH, m)
+    counter = engine.counter(k, ktype, int(nb.sum()), 32)
+    counter.insert_seqs(batch, canonical=True)
+    h, keys = engine.pmh3a_counter_slots(counter, kb.HASH_CANON_INVHASH, m, 1.0)  # every item: all its points below 1
+    assert np.array_equal(keys, want.astype(np.uint64))
+    hv = h.view(np.float64)
+    assert (hv > 0).all() and hv.max() < 1.0
+    h2, _ = engine.pmh3a_counter_slots(counter, kb.HASH_CANON_INVHASH, m, hv.min() * 0.5)
+    assert (h2.view(np.float64) == np.finfo(np.float64).max).all()
+    with pytest.raises(kb.KmuInvalid):
+        engine.pmh3a_counter_slots(counter, kb.HASH_CANON_INVHASH, 1, 1.0)
+    with pytest.raises(kb.KmuInvalid):  # a bound no sketch can need (it would emit 1e300 points per key)
+        engine.pmh3a_counter_slots(counter, kb.HASH_CANON_INVHASH, m, 1e300)
+    counter.destroy()
