@@ -12,8 +12,19 @@
 // still matter: they are listed -- by one scan of the histogram, the sweep that wipes it (long sequences), or from
 // the keys whose count reached 2 during the pass (short sequences) -- and draw their later points from their own
 // Xoshiro256++ stream with the usual 128-bit slot updates.  There is no second walk over the sequence.  Flagged
-// sequences (tie, wrapped u8 counter, too many items, every item needs later points) are redone by the general
+// sequences (tie, wrapped counter, too many items, every item needs later points) are redone by the general
 // kernel.
+//
+// Why the result is the reference's: the sketch is, slot by slot, the minimum of (h, key) over ALL points of ALL
+// items; the sequential algorithm only skips points that cannot be that minimum.  Here every point below q1 is
+// offered (the memoised ones during the pass, the later ones from the item list), and a point that is not offered is
+// >= NP / count >= q1 >= the value its slot ends with.
+//
+// One CTA per sequence, several sequences per SM (4-bit counters: 32 KB of histogram, four CTAs of 256 threads;
+// 8-bit counters for the few sequences long enough to push a count past 15: two CTAs of 512 threads).  The packed
+// bytes arrive by TMA bulk copies in segments of 4 STAGE positions, the next segment -- or the first one of the next
+// sequence -- in flight while the current one is processed; work descriptors are fetched two turns ahead.  The
+// kernel asks for the smallest shared-memory carve-out that holds its CTAs: L1 is where loads in flight wait.
 #include <algorithm>
 #include <cstdint>
 
