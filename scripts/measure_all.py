@@ -69,6 +69,11 @@ def main():
     sig32 = torch.empty((len(nb), 200), dtype=torch.int32, device=dev)
     ms = timed(eng, lambda: eng.sketch_pmh3a(batch, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200, out_device_ptr=sig32.data_ptr()))
     line("probminhash3a per read k=8 m=200", bases, ms, 0.25 + 800.0 * len(nb) / bases)
+    hll = torch.empty((len(nb), 256), dtype=torch.int16, device=dev)
+    ms = timed(eng, lambda: eng.sketch_setsketch(batch, 8, kb.KMER32, kb.HASH_CANON_INVHASH, (1.001, 256, 20.0, 65534), np.uint16,
+                                                 out_device_ptr=hll.data_ptr()))
+    line("setsketch per read k=8 m=256 u16", bases, ms, 0.25 + 512.0 * len(nb) / bases)
+    del hll
     batch.destroy()
     del sig, sig32
     # ---- C3: counting, 150-base reads from a 100 Mb genome, k = 31 ----
