@@ -1,0 +1,312 @@
+// Parity tests of the C++ host layer (include/kmerutils_b200.hpp), written the way the reference's own unit tests
+// read (same inputs, same assertions), plus bit-exact comparison with the CPU oracle (test infrastructure).
+// Needs a GPU: run by tests/test_host_api_cpp.py under `-m gpu`; the CPU suite only compiles and links it.
+//
+// Reference tests mirrored:
+//   src/base/kmergenerator.rs:596-621   test_gen_kmer16b32bit_80bases (+ the first three words)
+//   src/base/kmergenerator.rs:661-700   test_gen_kmer16b32bit_50bases_range_iterator
+//   src/base/kmer32bit.rs:228-312       reverse complement / ordering of Kmer32bit
+//   src/base/kmercount.rs:1524-1565     test_kmer_counter
+//   src/sketching/seqsketchjaccard.rs:742-791   test_pminhasha_kmer_smallb
+//   src/sketching/seqsketchjaccard.rs:947-1004  test_superminhash_kmer_16b32bit_serial
+//   src/sketching/seqsketchjaccard.rs:1015-...  test_reload_sketch_file
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../include/kmerutils_b200.hpp"
+#include "../../oracle/kmer_oracle.hpp"
+
+using namespace kmerutils;
+using namespace kmerutils::base;
+using namespace kmerutils::sketching;
+
+static int failures = 0;
+#define EXPECT(cond)                                                          \
+    do {                                                                      \
+        if (!(cond)) {                                                        \
+            std::fprintf(stderr, "FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); \
+            ++failures;                                                       \
+        }                                                                     \
+    } while (0)
+
+static const std::string S80 = "TCAAAGGGAAACATTCAAAATCAGTATGCGCCCGTTCAGTTACGTATTGCTCTCGCTAATGAGATGGGCTGGGTACAGAG";
+
+static std::string synth(uint64_t seed, size_t n) {
+    std::string s(n, 'A');
+    orc_synth_ascii(seed, 0, n, (uint8_t*)s.data());
+    return s;
+}
+
+static void test_gen_kmer16b32bit_80bases() {
+    Sequence seq(S80, 2);
+    EXPECT(seq.size() == 80);
+    const std::vector<Kmer16b32bit> v = KmerGenerator<Kmer16b32bit>(16).generate_kmer(seq);
+    EXPECT(v.size() == 80 - 16 + 1);
+    for (size_t i = 0; i < v.size(); ++i) {
+        const auto u = v[i].get_uncompressed_kmer();
+        EXPECT(std::string(u.begin(), u.end()) == S80.substr(i, 16));
+    }
+    EXPECT(v[0].v == 0xd02a013du && v[1].v == 0x40a804f4u && v[2].v == 0x02a013d0u);  // kmergenerator.rs:612-621
+}
+
+static void test_gen_kmer_range_and_types() {
+    Sequence seq(S80.substr(0, 50), 2);
+    // range iterator: k-mers starting in [3, 25 - 16] (kmergenerator.rs:661-700)
+    const auto r = KmerGenerator<Kmer16b32bit>(16).generate_kmer_in_range(seq, 3, 25);
+    EXPECT(r.size() == 25 - 3 - 16 + 1);
+    for (size_t i = 0; i < r.size(); ++i) {
+        const auto u = r[i].get_uncompressed_kmer();
+        EXPECT(std::string(u.begin(), u.end()) == S80.substr(3 + i, 16));
+    }
+    const auto k11 = KmerGenerator<Kmer32bit>(11).generate_kmer(seq);
+    EXPECT(k11.size() == 40);
+    for (size_t i = 0; i < k11.size(); ++i) {
+        EXPECT(k11[i].get_nb_base() == 11);
+        const auto u = k11[i].get_uncompressed_kmer();
+        EXPECT(std::string(u.begin(), u.end()) == S80.substr(i, 11));
+    }
+    const auto k31 = KmerGenerator<Kmer64bit>(31).generate_kmer(seq);
+    EXPECT(k31.size() == 20);
+    for (size_t i = 0; i < k31.size(); ++i) {
+        const auto u = k31[i].get_uncompressed_kmer();
+        EXPECT(std::string(u.begin(), u.end()) == S80.substr(i, 31));
+        // the host value type agrees with the oracle's word arithmetic
+        EXPECT(k31[i].reverse_complement().v == orc_kmer_revcomp(k31[i].v, 31, ORC_KMER64));
+        EXPECT(k31[i].push(2).v == orc_kmer_push(k31[i].v, 31, ORC_KMER64, 2));
+    }
+    for (const Kmer32bit& km : k11) {
+        EXPECT(km.reverse_complement().v == (uint32_t)orc_kmer_revcomp(km.v, 11, ORC_KMER32));
+        EXPECT(km.push(3).v == (uint32_t)orc_kmer_push(km.v, 11, ORC_KMER32, 3));
+    }
+    // bad k for the type: the reference panics (kmergenerator.rs:311)
+    bool threw = false;
+    try {
+        KmerGenerator<Kmer32bit>(15).generate_kmer(seq);
+    } catch (const Panic&) {
+        threw = true;
+    }
+    EXPECT(threw);
+    // non-ACGT character: Sequence::new panics (alphabet.rs:125)
+    threw = false;
+    try {
+        Sequence bad(std::string("ACGTNACGT"), 2);
+    } catch (const Panic&) {
+        threw = true;
+    }
+    EXPECT(threw);
+}
+
+static void test_kmer32bit_revcomp_order() {
+    Sequence a(std::string("TACGAGTAGGAT"), 2), b(std::string("ACTTGGAACGTT"), 2);
+    const Kmer32bit ka = KmerGenerator<Kmer32bit>(12).generate_kmer(a)[0];
+    const Kmer32bit kb = KmerGenerator<Kmer32bit>(12).generate_kmer(b)[0];
+    auto str = [](const Kmer32bit& k) {
+        const auto u = k.get_uncompressed_kmer();
+        return std::string(u.begin(), u.end());
+    };
+    EXPECT(str(ka.reverse_complement()) == "ATCCTACTCGTA");  // kmer32bit.rs:228-259
+    EXPECT(str(kb.reverse_complement()) == "AACGTTCCAAGT");
+    EXPECT(kb < ka);                                           // kmer32bit.rs:294-312
+    const auto d = a.get_reverse_complement().decompress();
+    EXPECT(std::string(d.begin(), d.end()) == "ATCCTACTCGTA");  // sequence.rs:947-961
+}
+
+static void test_kmer_counter() {
+    KmerCounter<Kmer16b32bit> kmer_counter(0.03f, 10000000, 8, 16);
+    Sequence seq(S80, 2);
+    const std::vector<Kmer16b32bit> vkmer = KmerGenerator<Kmer16b32bit>(16).generate_kmer(seq);
+    kmer_counter.insert_kmer(vkmer[0]);
+    kmer_counter.insert_kmer(vkmer[1]);
+    uint64_t x = 12345;
+    std::vector<uint32_t> want(vkmer.size(), 0);
+    want[0] = 1;
+    want[1] = 2;
+    for (int i = 0; i < 1000000; ++i) {
+        x = x * 6364136223846793005ull + 1442695040888963407ull;
+        const size_t xsi = 2 + (size_t)((x >> 33) % (vkmer.size() - 2));
+        kmer_counter.insert_kmer(vkmer[xsi]);
+        ++want[xsi];
+    }
+    kmer_counter.insert_kmer(vkmer[1]);
+    EXPECT(kmer_counter.get_count(vkmer[0]) == 1);  // kmercount.rs:1558
+    EXPECT(kmer_counter.get_count(vkmer[1]) == 2);  // kmercount.rs:1559
+    const auto got = kmer_counter.get_counts(vkmer);
+    for (size_t i = 0; i < vkmer.size(); ++i) EXPECT(got[i] == (want[i] > 255 ? 255u : want[i]));  // saturation :1615
+    EXPECT(kmer_counter.get_count(Kmer16b32bit::from_word(0x12345678u, 16)) == 0);                // never inserted :1612
+    EXPECT(kmer_counter.get_nb_distinct() == vkmer.size());
+    EXPECT(kmer_counter.get_nb_unique() == 1);
+
+    // count_kmer_threaded_one_to_many against the oracle's exact multiset
+    std::vector<std::string> reads;
+    for (int i = 0; i < 300; ++i) reads.push_back(synth(77, 20000).substr((size_t)i * 50, 400));
+    const std::vector<Sequence> seqvec = Sequence::new_batch(reads, 2);
+    auto pool = count_kmer_threaded_one_to_many<Kmer64bit>(seqvec, 4, 200000, 31);
+    std::vector<uint8_t> packed;
+    std::vector<uint64_t> off, nb;
+    for (const Sequence& s : seqvec) {
+        off.push_back(packed.size());
+        nb.push_back(s.size());
+        packed.insert(packed.end(), s.packed().begin(), s.packed().end());
+    }
+    std::vector<uint64_t> keys(200000), cnts(200000);
+    const uint64_t nd = orc_count_kmers(packed.data(), off.data(), nb.data(), seqvec.size(), 31, ORC_KMER64, 1, keys.data(), cnts.data(), keys.size());
+    EXPECT(nd <= keys.size());
+    uint64_t nu = 0;
+    std::vector<Kmer64bit> probes;
+    for (uint64_t i = 0; i < nd; ++i) {
+        nu += cnts[i] == 1;
+        probes.push_back(Kmer64bit::from_word(keys[i], 31));
+    }
+    EXPECT(pool->get_nb_distinct() == nd);
+    EXPECT(pool->get_nb_unique() == nu);
+    const auto pc = pool->get_counts(probes);
+    for (uint64_t i = 0; i < nd; ++i) EXPECT(pc[i] == (cnts[i] > 255 ? 255 : cnts[i]));
+}
+
+static void test_pminhasha_kmer_smallb() {
+    const size_t kmer_size = 5, sketch_size = 4000;
+    Sequence seqa(S80, 2);
+    std::vector<Sequence> vecseqb;
+    vecseqb.push_back(Sequence(S80.substr(0, 40), 2));
+    vecseqb.push_back(seqa.get_reverse_complement());
+    const double jac_theo_0 = double(40 - kmer_size) / double(80 - kmer_size);
+    auto vecsig = jaccard_index_probminhash3a<Kmer32bit>(seqa, vecseqb, sketch_size, kmer_size, KmerHash::canonical_invhash());
+    EXPECT(vecsig[0] >= 0.75 * jac_theo_0);  // seqsketchjaccard.rs:784
+    EXPECT(vecsig[1] >= 1.);                 // :785
+    vecsig = jaccard_index_probminhash3a<Kmer32bit>(seqa, vecseqb, sketch_size, kmer_size, KmerHash::identity());
+    EXPECT(vecsig[0] >= 0.75 * jac_theo_0);  // :791
+
+    // bit-exact signatures against the oracle, ragged lengths (shorter than k included), three k-mer types
+    const std::string big = synth(11, 60000);
+    std::vector<std::string> reads = {big.substr(0, 1000), big.substr(1000, 37), big.substr(2000, 7), big.substr(3000, 5000),
+                                      big.substr(9000, 8), big.substr(10000, 20000), big.substr(30000, 999), S80};
+    const std::vector<Sequence> seqs = Sequence::new_batch(reads, 2);
+    struct Case { int k, type, hash; };
+    for (const Case c : {Case{8, ORC_KMER32, ORC_HASH_CANON_INVHASH}, Case{16, ORC_KMER16B32, ORC_HASH_CANON_INVHASH}, Case{21, ORC_KMER64, ORC_HASH_CANON_INVHASH}}) {
+        const uint32_t m = 200;
+        SeqSketcher sk(c.k, m);
+        for (size_t i = 0; i < seqs.size(); ++i) {
+            std::vector<uint64_t> want(m);
+            orc_sketch_pmh3a_seq(seqs[i].packed().data(), seqs[i].size(), c.k, c.type, c.hash, m, want.data());
+            std::vector<uint64_t> got(m);
+            if (c.type == ORC_KMER32) {
+                auto s = sk.sketch_probminhash3a<Kmer32bit>({&seqs[i]}, KmerHash::canonical_invhash())[0];
+                got.assign(s.begin(), s.end());
+            } else if (c.type == ORC_KMER16B32) {
+                auto s = sk.sketch_probminhash3a<Kmer16b32bit>({&seqs[i]}, KmerHash::canonical_invhash())[0];
+                got.assign(s.begin(), s.end());
+            } else {
+                got = sk.sketch_probminhash3a<Kmer64bit>({&seqs[i]}, KmerHash::canonical_invhash())[0];
+            }
+            EXPECT(got == want);
+        }
+    }
+    // whole-file form through the trait object
+    ProbHash3aSketch<Kmer32bit> ph({8, 200});
+    const SeqSketcherT<Kmer32bit, uint32_t>& tr = ph;
+    const auto whole = tr.sketch_compressedkmer_seqs(as_refs(seqs), KmerHash::canonical_invhash());
+    std::vector<uint8_t> packed;
+    std::vector<uint64_t> off, nb;
+    for (const Sequence& s : seqs) {
+        while (packed.size() % 16) packed.push_back(0);
+        off.push_back(packed.size());
+        nb.push_back(s.size());
+        packed.insert(packed.end(), s.packed().begin(), s.packed().end());
+    }
+    std::vector<uint64_t> want(200);
+    orc_sketch_pmh3a_seqs(packed.data(), off.data(), nb.data(), seqs.size(), 8, ORC_KMER32, ORC_HASH_CANON_INVHASH, 200, want.data());
+    EXPECT(whole.size() == 1 && std::vector<uint64_t>(whole[0].begin(), whole[0].end()) == want);
+    // an empty sequence panics in the reference (set_range(..).unwrap(), seqsketchjaccard.rs:230)
+    bool threw = false;
+    try {
+        Sequence empty = Sequence::from_packed({}, 0);
+        SeqSketcher(8, 200).sketch_probminhash3a<Kmer32bit>({&empty}, KmerHash::identity());
+    } catch (const Panic&) {
+        threw = true;
+    }
+    EXPECT(threw);
+}
+
+static void test_superminhash_and_hll() {
+    // test_superminhash_kmer_16b32bit_serial (seqsketchjaccard.rs:947-1004): J(a, first half of a) and J(a, a)
+    const std::string a = synth(21, 4000);
+    const std::vector<Sequence> seqs = Sequence::new_batch({a, a.substr(0, 2000), a}, 2);
+    const size_t m = 800;
+    SeqSketcher sk(16, m);
+    const auto sig = sk.sketch_superminhash<Kmer16b32bit, double>(as_refs(seqs), KmerHash::canonical_invhash());
+    const double j_half = compute_probminhash_jaccard(sig[0], sig[1]), j_same = compute_probminhash_jaccard(sig[0], sig[2]);
+    const double theo = double(2000 - 16 + 1) / double(4000 - 16 + 1);
+    EXPECT(j_same == 1.0);
+    EXPECT(j_half > 0.75 * theo && j_half < 1.25 * theo);
+    // bit-exact against the oracle (FNV key hasher here, NoHashHasher through SuperHashSketch)
+    std::vector<uint8_t> packed;
+    std::vector<uint64_t> off, nb;
+    for (const Sequence& s : seqs) {
+        while (packed.size() % 16) packed.push_back(0);
+        off.push_back(packed.size());
+        nb.push_back(s.size());
+        packed.insert(packed.end(), s.packed().begin(), s.packed().end());
+    }
+    std::vector<double> want(seqs.size() * m);
+    orc_sketch_superminhash_batch(packed.data(), off.data(), nb.data(), seqs.size(), 16, ORC_KMER16B32, ORC_HASH_CANON_INVHASH, m, 1, 8, want.data(), 2);
+    for (size_t i = 0; i < seqs.size(); ++i) EXPECT(std::vector<double>(want.begin() + i * m, want.begin() + (i + 1) * m) == sig[i]);
+    SuperHashSketch<Kmer16b32bit, float> sh({16, m});
+    const auto sigf = sh.sketch_compressedkmer(as_refs(seqs), KmerHash::canonical_invhash());
+    std::vector<float> wantf(seqs.size() * m);
+    orc_sketch_superminhash_batch(packed.data(), off.data(), nb.data(), seqs.size(), 16, ORC_KMER16B32, ORC_HASH_CANON_INVHASH, m, 0, 4, wantf.data(), 2);
+    for (size_t i = 0; i < seqs.size(); ++i) EXPECT(std::vector<float>(wantf.begin() + i * m, wantf.begin() + (i + 1) * m) == sigf[i]);
+    // HyperLogLogSketch: per sequence and whole-file registers
+    SetSketchParams prm;
+    HyperLogLogSketch<Kmer32bit, uint16_t> hll({12, 256}, prm);
+    const auto regs = hll.sketch_compressedkmer(as_refs(seqs), KmerHash::canonical_invhash());
+    std::vector<uint16_t> wr(seqs.size() * 256);
+    orc_sketch_setsketch_batch(packed.data(), off.data(), nb.data(), seqs.size(), 12, ORC_KMER32, ORC_HASH_CANON_INVHASH, prm.b, 256, prm.a, prm.q, 2, wr.data(), 2);
+    for (size_t i = 0; i < seqs.size(); ++i) EXPECT(std::vector<uint16_t>(wr.begin() + i * 256, wr.begin() + (i + 1) * 256) == regs[i]);
+    const auto whole = hll.sketch_compressedkmer_seqs(as_refs(seqs), KmerHash::canonical_invhash());
+    std::vector<uint16_t> ww(256);
+    orc_sketch_setsketch(packed.data(), off.data(), nb.data(), seqs.size(), 12, ORC_KMER32, ORC_HASH_CANON_INVHASH, prm.b, 256, prm.a, prm.q, 2, ww.data());
+    EXPECT(whole.size() == 1 && whole[0] == ww);
+}
+
+static void test_reload_sketch_file(const std::string& dir) {
+    const std::string big = synth(31, 12000);
+    const std::vector<Sequence> seqs = Sequence::new_batch({big.substr(0, 3000), big.substr(3000, 4000), big.substr(7000, 5000)}, 2);
+    SeqSketcher sk(8, 200);
+    const auto sigs = sk.sketch_probminhash3a<Kmer32bit>(as_refs(seqs), KmerHash::canonical_invhash());
+    const std::string fname = dir + "/sigs.bin";
+    kmu_sigdump* out = sk.create_signature_dump(fname);
+    dump_signatures_block_u32(sigs, out);
+    check(kmu_sigdump_close(out), "close");
+    SigSketchFileReader reader(fname);
+    EXPECT(reader.get_kmer_size() == 8 && reader.get_signature_length() == 200 && reader.get_signature_size() == 4);
+    size_t n = 0;
+    while (auto s = reader.next()) {
+        EXPECT(n < sigs.size() && *s == sigs[n]);
+        ++n;
+    }
+    EXPECT(n == sigs.size());
+}
+
+int main(int argc, char** argv) {
+    const std::string dir = argc > 1 ? argv[1] : "/tmp";
+    try {
+        test_gen_kmer16b32bit_80bases();
+        test_gen_kmer_range_and_types();
+        test_kmer32bit_revcomp_order();
+        test_kmer_counter();
+        test_pminhasha_kmer_smallb();
+        test_superminhash_and_hll();
+        test_reload_sketch_file(dir);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "exception: %s\n", e.what());
+        return 2;
+    }
+    if (failures) {
+        std::fprintf(stderr, "%d expectation(s) failed\n", failures);
+        return 1;
+    }
+    std::printf("host api ok: %llu kernel launches\n", (unsigned long long)Context::global().launch_count());
+    return 0;
+}
