@@ -2,7 +2,9 @@
 // (probminhash::compute_probminhash_jaccard, its local restatement probminhash_get_jaccard_objects,
 // src/sketching/seqsketchjaccard.rs:86-108, and the comparison step of jaccard_index_probminhash3a, :423-495;
 // SuperMinHash::get_jaccard_index_estimate is the same count on f32 / f64 slots).
-// One CTA keeps 8 rows of A in shared memory; its warps stream rows of B once each and compare them against all 8.
+// One CTA keeps up to 8 rows of A in shared memory (fewer when the signatures are long: gsearch's 12 000 slots of u32
+// are 48 KB a row; rows too long for even one to fit are read through L1 / L2 instead); its warps stream rows of B once
+// each and compare them against all of them.
 #include <cstdint>
 
 #include "kmu_host.h"
@@ -13,13 +15,18 @@ constexpr int JA_ROWS = 8;
 
 template <typename T>
 __global__ void __launch_bounds__(256) jaccard_kernel(const T* __restrict__ a, uint64_t na, const T* __restrict__ b,
-                                                       uint64_t nb, uint32_t m, double* __restrict__ out) {
+                                                       uint64_t nb, uint32_t m, double* __restrict__ out, int rows_cap,
+                                                       int a_in_smem) {
     extern __shared__ __align__(16) uint8_t smem[];
-    T* sa = (T*)smem;  // JA_ROWS * m
-    const uint64_t a0 = (uint64_t)blockIdx.x * JA_ROWS;
-    const int rows = (int)min((uint64_t)JA_ROWS, na - a0);
-    for (uint32_t i = threadIdx.x; i < (uint32_t)rows * m; i += blockDim.x) sa[i] = a[a0 * m + i];
-    __syncthreads();
+    const uint64_t a0 = (uint64_t)blockIdx.x * rows_cap;
+    const int rows = (int)min((uint64_t)rows_cap, na - a0);
+    const T* sa = a + a0 * m;  // rows * m
+    if (a_in_smem) {
+        T* s = (T*)smem;
+        for (uint32_t i = threadIdx.x; i < (uint32_t)rows * m; i += blockDim.x) s[i] = a[a0 * m + i];
+        sa = s;
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (uint64_t j = (uint64_t)blockIdx.y * nwarps + warp; j < nb; j += (uint64_t)gridDim.y * nwarps) {
         uint32_t eq[JA_ROWS];
@@ -44,19 +51,22 @@ template <typename T>
 static cudaError_t launch_jaccard_t(const void* a, uint64_t na, const void* b, uint64_t nb, uint32_t m, double* out,
                                     int sm_count, cudaStream_t st) {
     auto kern = jaccard_kernel<T>;
-    const size_t smem = (size_t)JA_ROWS * m * sizeof(T);
+    int rows_cap = (int)std::min<size_t>(JA_ROWS, SMEM_BUDGET / ((size_t)m * sizeof(T)));
+    const int a_in_smem = rows_cap >= 1;
+    if (!a_in_smem) rows_cap = JA_ROWS;
+    const size_t smem = a_in_smem ? (size_t)rows_cap * m * sizeof(T) : 0;
     static size_t configured = 0;
     if (smem > configured && smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    const uint64_t gx = (na + JA_ROWS - 1) / JA_ROWS;
+    const uint64_t gx = (na + rows_cap - 1) / rows_cap;
     uint64_t gy = (nb + 7) / 8;
     const uint64_t want_y = std::max<uint64_t>(1, (uint64_t)sm_count * 4 / std::max<uint64_t>(gx, 1));
     if (gy > want_y) gy = want_y;
     dim3 grid((unsigned)std::min<uint64_t>(gx, 0x7FFFFFFF), (unsigned)std::min<uint64_t>(gy, 65535));
-    kern<<<grid, 256, smem, st>>>((const T*)a, na, (const T*)b, nb, m, out);
+    kern<<<grid, 256, smem, st>>>((const T*)a, na, (const T*)b, nb, m, out, rows_cap, a_in_smem);
     return cudaGetLastError();
 }
 
@@ -67,8 +77,7 @@ extern "C" int32_t kmu_signature_jaccard(kmu_ctx* ctx, const void* sig_a, uint64
     if (!ctx || (na && nb && (!sig_a || !sig_b || !out))) return fail(KMU_EINVAL, "null argument");
     if (slot_bytes != 2 && slot_bytes != 4 && slot_bytes != 8) return fail(KMU_EINVAL, "slot_bytes must be 2, 4 or 8");
     if (m < 1) return fail(KMU_EINVAL, "empty signatures");
-    if ((size_t)kmu::JA_ROWS * m * slot_bytes > SMEM_BUDGET) return fail(KMU_EINVAL, "signatures of %u slots are too long", m);
-    if (na > 0x7FFFFFFFull * kmu::JA_ROWS) return fail(KMU_EINVAL, "too many signatures");
+    if (na > 0x7FFFFFFFull) return fail(KMU_EINVAL, "too many signatures");
     if (na == 0 || nb == 0) return KMU_OK;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);

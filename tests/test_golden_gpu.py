@@ -23,7 +23,7 @@ def rows(hexrows, dtype):
 
 
 def test_s80_kmers_and_nthash(engine, fx):
-    b = engine.batch_from_ascii([fx["s80"].encode()])
+    b, _ = engine.batch_from_ascii([fx["s80"].encode()])
     v, _ = engine.generate_kmers(b, 8, kb.KMER32, kb.HASH_CANON_INVHASH)
     assert v.tobytes().hex() == fx["s80_kmers"]["k8_kmer32_canon_invhash"]
     v, _ = engine.generate_kmers(b, 16, kb.KMER16B32)

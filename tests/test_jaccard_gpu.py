@@ -8,7 +8,10 @@ from test_pmh3a_gpu import S80
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("dtype,m", [(np.uint32, 200), (np.uint64, 64), (np.uint16, 4096), (np.float64, 333), (np.float32, 7)])
+# 12 000 slots: gsearch's sketch size (4 rows of u32 / 2 rows of u64 per CTA in shared memory); 40 000 slots of u64 do
+# not fit shared memory at all and are read through the caches
+@pytest.mark.parametrize("dtype,m", [(np.uint32, 200), (np.uint64, 64), (np.uint16, 4096), (np.float64, 333), (np.float32, 7),
+                                     (np.uint32, 12000), (np.float64, 12000), (np.uint64, 40000)])
 def test_signature_jaccard_matrix(engine, oracle, dtype, m):
     rng = np.random.default_rng(m)
     na, nb = 37, 101
