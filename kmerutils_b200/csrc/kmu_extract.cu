@@ -130,6 +130,95 @@ __global__ void __launch_bounds__(256) generate_kmers_warp_kernel(SeqView b, uin
     }
 }
 
+// Vector form of the warp kernel: a lane takes Q = 16 / sizeof(V) consecutive k-mers (one 64-bit window of 32 bases
+// read from three packed words serves all of them, forward and reverse strand) and writes them with ONE 16-byte store,
+// so every store instruction of the warp writes 512 contiguous bytes.  Quads are aligned on the OUTPUT element index
+// (out must be 16-byte aligned); the ragged quads at the ends of a sequence / group fall back to scalar stores.
+template <typename V, int U>
+__global__ void __launch_bounds__(256) generate_kmers_vec_kernel(SeqView b, uint64_t total_bytes, uint32_t k, int kmer_type,
+                                                                  int hash_kind, const uint64_t* __restrict__ out_off,
+                                                                  V* __restrict__ out) {
+    constexpr int Q = 16 / (int)sizeof(V);
+    const V header = (V)word_header(kmer_type, k);
+    const bool canonical = hash_is_canonical(hash_kind);
+    const V mask = value_mask<V>(2 * k);
+    const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t g = warp; g < ngroups; g += nwarps) {
+        const uint64_t byte0 = g * GROUP_BYTES;
+        const uint64_t byte1 = min(byte0 + (uint64_t)GROUP_BYTES, total_bytes);
+        uint64_t s = seq_of_byte(b.byte_off, b.nseq, byte0);
+        while (s < b.nseq) {
+            const uint64_t sb = __ldg(b.byte_off + s);
+            if (sb >= byte1) break;
+            const uint64_t L = __ldg(b.nbases + s);
+            const uint64_t nk = L >= k ? L - k + 1 : 0;
+            const uint64_t p_lo = byte0 > sb ? (byte0 - sb) * 4 : 0;
+            const uint64_t p_hi = min(nk, (byte1 - sb) * 4);
+            const uint32_t* words = (const uint32_t*)(b.packed + sb);
+            const uint64_t ob = __ldg(out_off + s);
+            const uint64_t e_lo = ob + p_lo, e_hi = ob + p_hi;
+            for (uint64_t e0 = e_lo & ~(uint64_t)(Q - 1); e0 < e_hi; e0 += 32 * Q * U) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint64_t e = e0 + (uint64_t)(u * 32 + lane) * Q;
+                    if (e < e_hi) {
+                        const uint32_t t_lo = e < e_lo ? (uint32_t)(e_lo - e) : 0u;
+                        const uint32_t t_hi = (uint32_t)min((uint64_t)Q, e_hi - e);
+                        const uint64_t p = e + t_lo - ob;  // first position this lane produces
+                        const uint32_t* w = words + (p >> 4);
+                        const uint32_t sh = (uint32_t)(p & 15) * 2;
+                        const uint32_t wa = be32(__ldg(w)), wb = be32(__ldg(w + 1)), wc = be32(__ldg(w + 2));
+                        V vals[Q];
+                        if (sizeof(V) == 4) {
+                            // 32 bases from p; k-mer t = bases t .. t + k - 1 of the window, its reverse complement sits
+                            // 2 t bits above the bottom of the window's reverse complement
+                            const uint64_t x = ((uint64_t)__funnelshift_l(wb, wa, sh) << 32) | __funnelshift_l(wc, wb, sh);
+                            const uint64_t rc = revcomp_word64(x);
+#pragma unroll
+                            for (int t = 0; t < Q; ++t) {
+                                V key = (V)(x >> (64 - 2 * k - 2 * t)) & mask;
+                                if (canonical) {
+                                    const V r = (V)(rc >> (2 * t)) & mask;
+                                    key = key < r ? key : r;
+                                }
+                                vals[t] = finalize_key<V>(key, header, hash_kind);
+                            }
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < Q; ++t) {
+                                const uint32_t st = sh + 2 * t;  // <= 32: the clamping funnel shift
+                                const uint64_t x = ((uint64_t)__funnelshift_lc(wb, wa, st) << 32) | __funnelshift_lc(wc, wb, st);
+                                V key = (V)(x >> (64 - 2 * k));
+                                if (canonical) {
+                                    const V r = (V)revcomp_val((uint64_t)key, k);
+                                    key = key < r ? key : r;
+                                }
+                                vals[t] = finalize_key<V>(key, header, hash_kind);
+                            }
+                        }
+                        if (t_lo == 0 && t_hi == Q) {
+                            uint4 v;
+                            if (sizeof(V) == 4) {
+                                v = make_uint4((uint32_t)vals[0], (uint32_t)vals[1], (uint32_t)vals[Q > 2 ? 2 : 0], (uint32_t)vals[Q > 2 ? 3 : 0]);
+                            } else {
+                                const uint64_t a0 = (uint64_t)vals[0], a1 = (uint64_t)vals[1];
+                                v = make_uint4((uint32_t)a0, (uint32_t)(a0 >> 32), (uint32_t)a1, (uint32_t)(a1 >> 32));
+                            }
+                            __stcs((uint4*)(out + e), v);  // streaming: the output is not read again by this kernel
+                        } else {
+                            for (uint32_t t = 0; t + t_lo < t_hi; ++t) out[e + t_lo + t] = vals[t];
+                        }
+                    }
+                }
+            }
+            ++s;
+        }
+    }
+}
+
 cudaError_t launch_generate_kmers(const SeqView& b, uint64_t total_bytes, uint32_t k, int kmer_type, int hash_kind,
                                   const uint64_t* out_off, void* out, cudaStream_t stream) {
     if (b.nseq == 0) return cudaSuccess;
@@ -139,6 +228,10 @@ cudaError_t launch_generate_kmers(const SeqView& b, uint64_t total_bytes, uint32
         generate_kmers_kernel<uint64_t, 8, true><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint64_t*)out);
     else if (kmer_type == KMU_KMERAA32)
         generate_kmers_kernel<uint32_t, 8, true><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint32_t*)out);
+    else if (kmer_type == KMU_KMER64 && ((uintptr_t)out & 15) == 0)
+        generate_kmers_vec_kernel<uint64_t, 2><<<grid, block, 0, stream>>>(b, total_bytes, k, kmer_type, hash_kind, out_off, (uint64_t*)out);
+    else if (kmer_type != KMU_KMER64 && ((uintptr_t)out & 15) == 0)
+        generate_kmers_vec_kernel<uint32_t, 2><<<grid, block, 0, stream>>>(b, total_bytes, k, kmer_type, hash_kind, out_off, (uint32_t*)out);
     else if (kmer_type == KMU_KMER64)
         generate_kmers_warp_kernel<uint64_t, 4><<<grid, block, 0, stream>>>(b, total_bytes, k, kmer_type, hash_kind, out_off, (uint64_t*)out);
     else

@@ -62,6 +62,8 @@ def main():
     ms = timed(eng, lambda: kb._lib.check(eng.lib.kmu_nthash_canonical(eng.ctx, batch.handle, 31, 1, out64.data_ptr(), None, 1)))
     line("nthash_canonical k=31", bases, ms, 0.25 + 8.0 * nk31 / bases)
     del out32, out64
+    if "--extract-only" in sys.argv:
+        return
     # ---- C2 per-read sketches: SuperMinHash / SetSketch beside ProbMinHash3a ----
     sig = torch.empty((len(nb), 200), dtype=torch.float64, device=dev)
     ms = timed(eng, lambda: eng.sketch_superminhash(batch, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200, out_device_ptr=sig.data_ptr()))
