@@ -283,7 +283,7 @@ int32_t kmu_sketch_setsketch(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, in
     const uint32_t m = (uint32_t)P0.m;
     const size_t table_bytes = 2 * 264 * sizeof(double);
     const size_t team_bytes = align_up((size_t)m * 4, 16) + 32;
-    if (P0.m > 0xFFFFFFull || team_bytes + table_bytes > SMEM_BUDGET)
+    if (P0.m > 0xFFFFFFull || team_bytes + table_bytes + kmu::SSK_QUEUE_BYTES > SMEM_BUDGET)
         return fail(KMU_EINVAL, "m = %llu registers do not fit the shared memory of one SM", (unsigned long long)P0.m);
     if (b->nseq == 0 && !whole) return KMU_OK;
     if (!sig) return fail(KMU_EINVAL, "null signature buffer");
@@ -328,6 +328,7 @@ int32_t kmu_sketch_setsketch(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, in
     P.hash_kind = hash_kind;
     P.C.a = P0.a;
     P.C.inva = 1.0 / P0.a;
+    P.C.inva_m0 = P.C.inva / (double)m;  // IEEE division, as __ddiv_rn on the device
     P.C.lnb = host_det_log(P0.b);
     P.C.ln_term = std::log(1e4 * (double)m);
     P.C.m = m;
@@ -339,7 +340,17 @@ int32_t kmu_sketch_setsketch(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, in
     P.slow_list = d_slow;
     P.exact_count = d_work + 129;
     P.exact_list = d_exact;
-    P.exact_nk_max = 16 * m;
+    // per-sequence sketches speculate less cautiously than the whole-file one (a redo costs one sequence, not the file):
+    // one sketch in ~20 is redone, every item places 4-5 times fewer points
+    P.C.spec_ln = std::log(8.0 * (double)m);
+    P.C.spec_dfrac = 0.85;
+    {
+        const double bits = (b->alphabet == 0 ? 2.0 : std::log2(20.0)) * (double)k;  // keys the sequence can hold
+        P.C.spec_keyspace = bits < 40.0 ? std::exp2(bits) * (kmu::hash_kind_is_canonical_host(hash_kind) ? 0.5 : 1.0) : 0.0;
+    }
+    // below this many k-mers an item places too many points for the sparse permutation of the speculative kernels
+    // (on average m spec_ln / (spec_dfrac nk) of them, capped at SSK_SPARSE_CAP = 24): the exact path takes the sequence
+    P.exact_nk_max = (uint64_t)std::ceil((double)m * P.C.spec_ln / (P.C.spec_dfrac * 7.5));
     P.whole_regs = d_whole;
     int ci = 0;
     auto run_exact = [&](const uint32_t* list, uint64_t count, bool group) -> int32_t {
@@ -372,7 +383,8 @@ int32_t kmu_sketch_setsketch(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, in
             kspec = (uint32_t)std::min(kf, (double)(P.C.iq1 - 1));
         }
         bool done = false;
-        if (total_kmers > P.exact_nk_max && kspec > 0) {
+        // (the whole-file cut keeps the cautious bound: an item places ~4 m ln(1e4 m) / nk points below it)
+        if ((double)total_kmers > 4.0 * (double)m * P.C.ln_term / 7.5 && kspec > 0) {
             kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
             const size_t smem = table_bytes + (size_t)m * 4;
             std::vector<uint32_t> regs(m);
@@ -412,7 +424,7 @@ int32_t kmu_sketch_setsketch(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, in
         struct Launch { uint64_t first, count; TeamGeometry g; };
         std::vector<Launch> ls;
         for (const OctaveClass& c : classes) {
-            TeamGeometry g = team_geometry(c.nk_max, team_bytes, table_bytes);
+            TeamGeometry g = team_geometry(c.nk_max, team_bytes, table_bytes + kmu::SSK_QUEUE_BYTES);
             if (!ls.empty() && ls.back().g.team_warps == g.team_warps && ls.back().g.teams_per_cta == g.teams_per_cta &&
                 ls.back().first + ls.back().count == c.first) {
                 ls.back().count += c.count;
@@ -447,7 +459,7 @@ int32_t kmu_sketch_setsketch(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, in
             Q.kspec_in = d_kmin;
             Q.slow_count = P.exact_count;
             Q.slow_list = P.exact_list;
-            rc = run_team(Q, d_slow, 0, cnt[0], team_geometry(b->order_cache.nk_longest, team_bytes, table_bytes));
+            rc = run_team(Q, d_slow, 0, cnt[0], team_geometry(b->order_cache.nk_longest, team_bytes, table_bytes + kmu::SSK_QUEUE_BYTES));
             if (rc) return rc;
             CUDA_TRY(cudaMemcpyAsync(cnt, P.slow_count, sizeof(cnt), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));

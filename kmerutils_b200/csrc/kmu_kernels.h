@@ -183,9 +183,14 @@ cudaError_t launch_smh_colmin(const void* rows, uint64_t nseq, uint32_t m, bool 
 cudaError_t launch_smh_exact(const SmhParams& P, bool key64, bool f64, int grid, cudaStream_t st);
 
 // ---- SetSketch (kmu_setsketch.cu) ---------------------------------------------------------------
+constexpr size_t SSK_QUEUE_BYTES = 32 * 64 * 8;  // team kernel: one queue of 64 keys per warp, after the ziggurat tables
 struct SskConsts {
     double a, inva, lnb;  // SetSketchParams.a, 1 / a, ln(b) (deterministic log)
     double ln_term;       // ln(1e4 m)
+    double inva_m0;       // inva / m: the spacing of an item's first point (what the loop computes for j = 0)
+    // per-sequence speculation (a failed sketch is redone from the level it reached, so this only trades the cost of the
+    // points below the cut against the cost of the redo): D = spec_dfrac * distinct(nk), failure odds ~ m e^-spec_ln
+    double spec_ln, spec_dfrac, spec_keyspace;  // spec_keyspace: number of possible keys, 0 = far more than any nk
     uint32_t m;
     int iq1;              // q + 1
 };

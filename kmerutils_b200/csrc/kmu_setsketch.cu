@@ -63,6 +63,7 @@ __device__ __forceinline__ double exp1_sample(Xoshiro256pp& rng, const ZigTables
     }
 }
 
+constexpr uint32_t SSK_QUEUE = 64;  // keys per warp queue of the team kernel (SSK_QUEUE_BYTES for 32 warps, kmu_kernels.h)
 constexpr uint32_t SSK_SPARSE_CAP = 24;  // points an item may place in the speculative kernels
 
 // Points of one item against the registers.  Returns false if the item needed more than
@@ -75,7 +76,8 @@ __device__ __forceinline__ bool ssk_item_points(Xoshiro256pp& rng, const ZigTabl
     const uint32_t m = C.m;
     for (uint32_t j = 0; j < m; ++j) {
         const double e = exp1_sample(rng, zt);
-        x = __dadd_rn(x, __dmul_rn(__ddiv_rn(C.inva, (double)(m - j)), e));
+        // almost every item stops at j = 0: its spacing is a constant, no division
+        x = __dadd_rn(x, __dmul_rn(j == 0 ? C.inva_m0 : __ddiv_rn(C.inva, (double)(m - j)), e));
         if (x > xcut) break;  // certainly log_b(x) > -K_spec: the level is <= K_spec
         const double lb = __ddiv_rn(det_log(x), C.lnb);
         if (lb > -(double)kspec) break;
@@ -111,10 +113,15 @@ __device__ __forceinline__ bool ssk_item_points(Xoshiro256pp& rng, const ZigTabl
     return true;
 }
 
-// speculative level for n k-mers: with D >= n / 4 distinct items every register ends >= K_spec except
-// with probability ~1e-4:  K_spec = 1 + floor(log_b(D a / ln(1e4 m)))
+// speculative level for a sequence of nk k-mers: with D distinct items every register ends >= K_spec except with
+// probability ~m e^-spec_ln:  K_spec = 1 + floor(log_b(D a / spec_ln)),  D = spec_dfrac * (expected distinct keys among nk
+// draws from the key space).  An item then places about m spec_ln / D points below the cut; a sketch that ends with a
+// register below K_spec (a few percent of them, more for repetitive sequences) is redone from the level
+// it reached.  Any K_spec gives the exact result; this one minimises the work.
 __device__ __forceinline__ uint32_t ssk_kspec(uint64_t nk, const SskConsts& C) {
-    const double ratio = (double)nk * 0.25 * C.a / C.ln_term;
+    double d = (double)nk;
+    if (C.spec_keyspace > 0.0) d = C.spec_keyspace * (1.0 - exp(-d / C.spec_keyspace));
+    const double ratio = d * C.spec_dfrac * C.a / C.spec_ln;
     if (!(ratio > 1.0)) return 0;
     const double kf = 1.0 + floor(log(ratio) / C.lnb);
     const double cap = (double)(C.iq1 - 1);
@@ -151,7 +158,8 @@ __global__ void __launch_bounds__(1024, 1) ssk_team_kernel(const SskParams P) {
     team.tid = threadIdx.x - team.id * team.size;
     team.warp = team.tid >> 5;
     team.lane = threadIdx.x & 31;
-    uint8_t* tbase = smem + 2 * 264 * sizeof(double) + (size_t)team.id * P.team_smem_bytes;
+    V* wq = (V*)(smem + 2 * 264 * sizeof(double)) + (threadIdx.x >> 5) * SSK_QUEUE;  // this warp's queue of keys
+    uint8_t* tbase = smem + 2 * 264 * sizeof(double) + SSK_QUEUE_BYTES + (size_t)team.id * P.team_smem_bytes;
     uint32_t* regs = (uint32_t*)tbase;
     SskTeamShared* ts = (SskTeamShared*)(tbase + (((size_t)P.C.m * 4 + 15) & ~(size_t)15));
     const V header = (V)word_header(P.kmer_type, P.k);
@@ -188,19 +196,49 @@ __global__ void __launch_bounds__(1024, 1) ssk_team_kernel(const SskParams P) {
         team.sync();
         const uint32_t ntasks = (nk + 15) >> 4;
         bool ok = true;
-        for (uint32_t task = team.tid; task < ntasks; task += team.size) {
+        // Two phases, so that the lanes of a warp stay together: (1) every lane seeds its item and draws the first
+        // point -- the same work for all; the items whose first point falls below the cut (a minority) go to the
+        // warp's queue; (2) whenever 32 are queued, every lane takes one and places all its points.  Without the queue
+        // a warp waits at every item for its unluckiest lane (9.8 of 32 lanes active, profiles/r1m_ncu_ssk_team.txt).
+        uint32_t qn = 0;  // warp-uniform
+        for (uint32_t task0 = 0; task0 < ntasks; task0 += team.size) {  // the same trip count for every lane of a warp
+            const uint32_t task = task0 + team.tid;
             TK tk;
-            uint32_t p = task << 4;
-            tk.init(words, p, k);
-            const uint32_t pend = min(p + 16, nk);
+            uint32_t p = task << 4, pend = p;
+            if (task < ntasks) {
+                tk.init(words, p, k);
+                pend = min(p + 16, nk);
+            }
 #pragma unroll 1
-            for (uint32_t t = 0; p < pend; ++t, ++p) {
-                const V key = finalize_key<V>(tk.get(t, canonical), header, P.hash_kind);
-                Xoshiro256pp rng;
-                rng.seed(nohash_seed(key));
-                ok &= ssk_item_points(rng, zt, P.C, kspec, xcut, regs);
+            for (uint32_t t = 0; t < 16; ++t, ++p) {
+                bool surv = false;
+                V key = 0;
+                if (p < pend) {
+                    key = finalize_key<V>(tk.get(t, canonical), header, P.hash_kind);
+                    Xoshiro256pp rng;
+                    rng.seed(nohash_seed(key));
+                    surv = !(__dmul_rn(P.C.inva_m0, exp1_sample(rng, zt)) > xcut);
+                }
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, surv);
+                if (surv) wq[qn + __popc(bal & ((1u << team.lane) - 1u))] = key;
+                qn += __popc(bal);
+                __syncwarp();
+                if (qn >= 32) {
+                    qn -= 32;
+                    const V kq = wq[qn + team.lane];
+                    __syncwarp();
+                    Xoshiro256pp rng;
+                    rng.seed(nohash_seed(kq));
+                    ok &= ssk_item_points(rng, zt, P.C, kspec, xcut, regs);
+                }
             }
         }
+        if ((uint32_t)team.lane < qn) {
+            Xoshiro256pp rng;
+            rng.seed(nohash_seed(wq[team.lane]));
+            ok &= ssk_item_points(rng, zt, P.C, kspec, xcut, regs);
+        }
+        __syncwarp();
         if (!ok) ts->flag = 2;
         team.sync();
         uint32_t mn = 0xFFFFFFFFu;
