@@ -127,6 +127,15 @@ __device__ __forceinline__ uint32_t ssk_kspec(uint64_t nk, const SskConsts& C) {
     const double cap = (double)(C.iq1 - 1);
     return (uint32_t)(kf < cap ? kf : cap);
 }
+// the cautious level (D >= nk / 4, failure odds ~1e-4 per sketch): what a failed speculation is redone with when it
+// left a register below it -- the redo pass must not fail in its turn, the path after it is one warp per sequence
+__device__ __forceinline__ uint32_t ssk_kspec_cautious(uint64_t nk, const SskConsts& C) {
+    const double ratio = (double)nk * 0.25 * C.a / C.ln_term;
+    if (!(ratio > 1.0)) return 0;
+    const double kf = 1.0 + floor(log(ratio) / C.lnb);
+    const double cap = (double)(C.iq1 - 1);
+    return (uint32_t)(kf < cap ? kf : cap);
+}
 __device__ __forceinline__ double ssk_xcut(uint32_t kspec, const SskConsts& C) {
     return exp(-(double)kspec * C.lnb) * (1.0 + 1e-6);
 }
@@ -253,8 +262,10 @@ __global__ void __launch_bounds__(1024, 1) ssk_team_kernel(const SskParams P) {
         if (team.tid == 0 && nk) {
             if (ts->flag == 2) {  // an item overflowed the sparse permutation: exact path
                 P.exact_list[atomicAdd(P.exact_count, 1ULL)] = seq;
-            } else if (ts->minreg < kspec) {  // speculation failed: redo with the level reached (a true lower bound)
-                P.kmin_out[seq] = ts->minreg;
+            } else if (ts->minreg < kspec) {
+                // speculation failed: redo with the level reached (a true lower bound of every final register, cannot
+                // fail) or, when that is lower than the cautious level, with the cautious one
+                P.kmin_out[seq] = max(ts->minreg, ssk_kspec_cautious(nk, P.C));
                 P.slow_list[atomicAdd(P.slow_count, 1ULL)] = seq;
             }
         }

@@ -134,6 +134,14 @@ def main():
     ms = timed(eng, lambda: eng.sketch_pmh3a(pb, 12, kb.KMERAA64, kb.HASH_MASKED_VALUE, 400, out_device_ptr=psig.data_ptr()), 2)
     line("probminhash3a proteome AA k=12 m=400 (residues)", int(pl.sum()), ms, 1.0 + 3200.0 * len(pl) / int(pl.sum()))
     pb.destroy()
+    # SetSketch per protein, default parameters (m = 4096 registers for ~270 12-mers: every item places every point,
+    # the exact path; 2 000 proteins)
+    pl2 = pl[:2000]
+    pb2 = eng.batch_synth_aa(5, pl2)
+    phll = torch.empty((len(pl2), 4096), dtype=torch.int16, device=dev)
+    ms = timed(eng, lambda: eng.sketch_setsketch(pb2, 12, kb.KMERAA64, kb.HASH_MASKED_VALUE, None, np.uint16, out_device_ptr=phll.data_ptr()), 1)
+    line("setsketch proteome AA k=12 m=4096 u16 (residues)", int(pl2.sum()), ms, 1.0 + 8192.0 * len(pl2) / int(pl2.sum()))
+    pb2.destroy()
     eng.close()
 
 

@@ -26,10 +26,28 @@ def check_batch(engine, oracle, seed, nb, k, ktype, kind, params, dtype):
 @pytest.mark.parametrize("dtype", [np.uint16, np.uint32, np.uint64])
 def test_setsketch_per_sequence_small_m(engine, oracle, dtype):
     rng = np.random.default_rng(3)
-    # exact path (<= 16 m = 4096 k-mers), speculative path, multi-warp teams
+    # exact path (few k-mers relative to m), speculative path, multi-warp teams
     nb = np.concatenate([[1, 20, 21, 22, 100, 1000, 4000, 4200, 5000, 9000, 30000, 100000, 400000],
                          rng.integers(21, 20000, 40)])
     check_batch(engine, oracle, 5, nb, 21, kb.KMER64, kb.HASH_CANON_INVHASH, SMALL, dtype)
+
+
+def test_setsketch_failed_speculation_paths(engine, oracle):
+    """Sequences whose distinct k-mer count is far below what the speculative level assumes: tandem repeats (the
+    speculation fails, the redo at the cautious level fails too, the exact path finishes), a half-repetitive read (the
+    redo succeeds) and small-key-space reads (k = 6: 2080 canonical keys whatever the length)."""
+    rng = np.random.default_rng(17)
+    unit = bytes(rng.choice(list(b"ACGT"), 53).astype(np.uint8))
+    rnd = bytes(rng.choice(list(b"ACGT"), 60000).astype(np.uint8))
+    seqs = [unit * 2000, unit * 300, rnd[:30000] + unit * 600, rnd, (unit * 40 + rnd[:500]) * 20]
+    batch, _ = engine.batch_from_ascii(seqs)
+    packed, off, nb = batch.download()
+    packed = np.concatenate([packed, np.zeros(64, np.uint8)])
+    for k, ktype, prm in [(21, kb.KMER64, SMALL), (6, kb.KMER32, SMALL), (12, kb.KMER32, (1.001, 64, 20.0, 65534))]:
+        got = engine.sketch_setsketch(batch, k, ktype, kb.HASH_CANON_INVHASH, prm, np.uint16)
+        want = oracle.sketch_setsketch_batch(packed, off, nb, k, ktype, kb.HASH_CANON_INVHASH, prm, np.uint16)
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        assert len(bad) == 0, f"k={k}: sequences {bad} differ"
 
 
 def test_setsketch_default_params(engine, oracle):
