@@ -1251,6 +1251,17 @@ int32_t kmu_sketch_pmh3a(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_
     if (b->nseq >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "more than 2^32-1 sequences in one batch");
     for (uint64_t L : b->h_nbases)
         if (L >= (1ull << 30)) return fail(KMU_EINVAL, "a single sequence is limited to 2^30 bases here (kmu_sketch_pmh3a_whole has no limit)");
+    // Genome-sized sequences over a large key space: the team kernel keeps one sequence on one SM (a 5 Mb genome is
+    // ~70 ms of one SM), the whole-file procedure (counting table in HBM + item kernel, the whole GPU on one sequence,
+    // ~0.4 ms per 5 Mb) gives the same signature.  Taken when every sequence is long enough for its fixed ~0.1 ms.
+    if (!kmer_type_is_aa(kmer_type) && k > 8 && !std::getenv("KMU_PMH3A_TEAM_ONLY")) {  // (tests compare the two paths)
+        uint64_t min_nk = ~0ull;
+        for (uint64_t L : b->h_nbases) min_nk = std::min<uint64_t>(min_nk, L >= k ? L - k + 1 : 0);
+        if (min_nk >= 2000000 || (b->nseq * 2 <= (uint64_t)ctx->sm_count && min_nk >= 250000)) {
+            std::vector<uint64_t> ones(b->nseq, 1);
+            return kmu_sketch_pmh3a_groups(ctx, b, ones.data(), b->nseq, k, kmer_type, hash_kind, m, sig, sig_on_device);
+        }
+    }
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};

@@ -108,7 +108,11 @@ def main():
     line("superminhash per genome k=16 m=12000 f64", gbases, ms, 0.25 + 96000.0 / 5e6)
     sig32 = torch.empty((ng, 12000), dtype=torch.int32, device=dev)
     ms = timed(eng, lambda: eng.sketch_pmh3a(gb_, 16, kb.KMER16B32, kb.HASH_CANON_INVHASH, 12000, out_device_ptr=sig32.data_ptr()), 1)
-    line("probminhash3a per genome (team kernel) k=16 m=12000", gbases, ms, 0.25 + 48000.0 / 5e6)
+    line("probminhash3a per genome k=16 m=12000 (per-sequence entry point, routed to the whole-file procedure)", gbases, ms, 0.25 + 48000.0 / 5e6)
+    os.environ["KMU_PMH3A_TEAM_ONLY"] = "1"
+    ms = timed(eng, lambda: eng.sketch_pmh3a(gb_, 16, kb.KMER16B32, kb.HASH_CANON_INVHASH, 12000, out_device_ptr=sig32.data_ptr()), 1)
+    del os.environ["KMU_PMH3A_TEAM_ONLY"]
+    line("probminhash3a per genome (team kernel, 32 of 148 SMs busy) k=16 m=12000", gbases, ms, 0.25 + 48000.0 / 5e6)
     one = eng.batch_synth(4, gnb[:1])
     ms = timed(eng, lambda: eng.sketch_pmh3a_whole(one, 16, kb.KMER16B32, kb.HASH_CANON_INVHASH, 12000), 2)
     line("probminhash3a whole-file (table + item kernel), one 5 Mb genome", 5_000_000, ms, 0.25 + 48000.0 / 5e6)

@@ -81,7 +81,7 @@ def test_c3_strand_symmetry(engine, oracle):
 
 
 # ---- C4: 5 Mb genomes, k = 16 Kmer16b32bit, ProbMinHash3a and SuperMinHash with 12 000 slots -------------------------
-def test_c4_genome_sketches_strand_symmetric_and_consistent(engine, oracle):
+def test_c4_genome_sketches_strand_symmetric_and_consistent(engine, oracle, monkeypatch):
     ngen, glen, k, m = 6, 5_000_000, 16, 12_000
     genomes = engine.batch_synth(4, np.full(ngen, glen, dtype=np.uint64))
     rc = revcomp_batch(engine, oracle, genomes)
@@ -92,7 +92,11 @@ def test_c4_genome_sketches_strand_symmetric_and_consistent(engine, oracle):
     # the per-sequence entry point and the whole-file one agree on a one-contig genome
     view = engine.batch_view(genomes, 2, 1)
     assert np.array_equal(engine.sketch_pmh3a_whole(view, k, kb.KMER16B32, kb.HASH_CANON_INVHASH, m).astype(np.uint32), sig[2])
+    per_seq = engine.sketch_pmh3a(view, k, kb.KMER16B32, kb.HASH_CANON_INVHASH, m)  # routed to the whole-file procedure
+    assert np.array_equal(per_seq[0], sig[2])
+    monkeypatch.setenv("KMU_PMH3A_TEAM_ONLY", "1")  # the team kernel (one SM per genome) gives the same
     per_seq = engine.sketch_pmh3a(view, k, kb.KMER16B32, kb.HASH_CANON_INVHASH, m)
+    monkeypatch.delenv("KMU_PMH3A_TEAM_ONLY")
     assert np.array_equal(per_seq[0], sig[2])
     # every slot names a k-mer of its genome
     kmers, _ = engine.generate_kmers(view, k, kb.KMER16B32, kb.HASH_CANON_INVHASH)
