@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Multi-GPU check, run under torchrun on N GPUs of one box:
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 scripts/dist_check.py
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py
 Counting over NCCL all-to-all (owners = DispatchableT::dispatch) and SetSketch / SuperMinHash register merges, each
 compared on rank 0 with the CPU oracle run on the whole input."""
 import os
