@@ -495,7 +495,7 @@ static int32_t run_pmh3a_items(kmu_ctx* ctx, kmu::Pmh3aItemsParams P, bool key64
     P.global_slots = (kmu::Slot*)ctx->items_slots.p;
     unsigned long long* d_max = (unsigned long long*)((uint8_t*)ctx->items_slots.p + sizeof(kmu::Slot) * m);
     const size_t smem = sizeof(kmu::Slot) * (size_t)m;
-    P.slots_in_smem = smem <= SMEM_BUDGET ? 1 : 0;
+    P.slots_in_smem = smem + kmu::PMH3A_ITEMS_QUEUE_BYTES <= SMEM_BUDGET ? 1 : 0;
     P.slot_thresh = (uint32_t)(0x100000000ULL % m);
     fill_exp01(P.e, m);
     const uint64_t work = (P.n + 511) / 512;
@@ -662,7 +662,7 @@ int32_t kmu_pmh3a_counter_slots(kmu_ctx* ctx, const kmu_counter* c, int32_t hash
     P.m = m;
     P.global_slots = (kmu::Slot*)ctx->items_slots.p;
     const size_t smem = sizeof(kmu::Slot) * (size_t)m;
-    P.slots_in_smem = smem <= SMEM_BUDGET ? 1 : 0;
+    P.slots_in_smem = smem + kmu::PMH3A_ITEMS_QUEUE_BYTES <= SMEM_BUDGET ? 1 : 0;
     P.slot_thresh = (uint32_t)(0x100000000ULL % m);
     fill_exp01(P.e, m);
     P.bound = bound;
@@ -707,7 +707,7 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
             rebased[i] = b->h_byte_off[i] - base;
             nk[g] += b->h_nbases[i] >= k ? b->h_nbases[i] - k + 1 : 0;
         }
-        uint64_t want = std::max<uint64_t>(1024, nk[g] * 2);
+        uint64_t want = std::max<uint64_t>(1024, nk[g] + nk[g] / 2 + nk[g] / 16);  // load <= 0.64: a 5 Mb genome's table (64 MB) stays in L2
         if (2 * k < 40) want = std::min<uint64_t>(want, std::max<uint64_t>(1024, 2ull << (2 * k)));
         uint64_t cap = 1024;
         while (cap < want) cap <<= 1;
@@ -737,7 +737,7 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
         P.m = m;
         P.global_slots = (kmu::Slot*)ctx->items_slots.p;
         const size_t smem = sizeof(kmu::Slot) * (size_t)m;
-        P.slots_in_smem = smem <= SMEM_BUDGET ? 1 : 0;
+        P.slots_in_smem = smem + kmu::PMH3A_ITEMS_QUEUE_BYTES <= SMEM_BUDGET ? 1 : 0;
         P.slot_thresh = (uint32_t)(0x100000000ULL % m);
         fill_exp01(P.e, m);
         uint64_t launches = 0;
@@ -747,7 +747,7 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
                 CUDA_TRY(cudaMemsetAsync(d_sig + g * (size_t)m * vsz, 0, (size_t)m * vsz, st));
                 continue;
             }
-            uint64_t want = std::max<uint64_t>(1024, nk[g] * 2);
+            uint64_t want = std::max<uint64_t>(1024, nk[g] + nk[g] / 2 + nk[g] / 16);  // load <= 0.64: a 5 Mb genome's table (64 MB) stays in L2
             if (2 * k < 40) want = std::min<uint64_t>(want, std::max<uint64_t>(1024, 2ull << (2 * k)));
             uint64_t cap = 1024;
             while (cap < want) cap <<= 1;

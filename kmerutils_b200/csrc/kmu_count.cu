@@ -35,11 +35,17 @@ struct CountOps;
 
 template <>
 struct CountOps<uint32_t> {
-    static __device__ __forceinline__ bool insert(const CountTable& t, uint32_t key, uint32_t add) {
+    // The home slot is claimed without looking first (one L2 round trip instead of two when it is free -- the common
+    // case of a genome's mostly distinct k-mers); home() returns what the slot held (0: claimed, done) and rest()
+    // finishes from there, looking before it claims.  (Four claims in flight per lane were slower: 10.4 -> 16.6 ms for 32 genomes.)
+    static __device__ __forceinline__ unsigned long long home(const CountTable& t, uint32_t key, uint32_t add, uint64_t& i) {
+        i = fmix64(key) & t.capmask;
+        return atomicCAS((unsigned long long*)t.slots + i, 0ULL, ((unsigned long long)key << 32) | add);
+    }
+    static __device__ __forceinline__ bool rest(const CountTable& t, uint32_t key, uint32_t add, uint64_t i, unsigned long long e) {
         unsigned long long* tab = (unsigned long long*)t.slots;
-        uint64_t i = fmix64(key) & t.capmask;
         for (uint64_t probe = 0; probe <= t.capmask; ++probe) {
-            unsigned long long e = *(volatile unsigned long long*)(tab + i);
+            if (probe) e = *(volatile unsigned long long*)(tab + i);
             if (e == 0) {
                 unsigned long long old = atomicCAS(tab + i, 0ULL, ((unsigned long long)key << 32) | add);
                 if (old == 0) return true;
@@ -53,6 +59,11 @@ struct CountOps<uint32_t> {
             i = (i + 1) & t.capmask;
         }
         return false;
+    }
+    static __device__ __forceinline__ bool insert(const CountTable& t, uint32_t key, uint32_t add) {
+        uint64_t i;
+        const unsigned long long e = home(t, key, add, i);
+        return e == 0 ? true : rest(t, key, add, i, e);
     }
     static __device__ __forceinline__ uint32_t lookup(const CountTable& t, uint32_t key) {
         const unsigned long long* tab = (const unsigned long long*)t.slots;

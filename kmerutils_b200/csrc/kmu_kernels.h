@@ -147,6 +147,9 @@ struct Pmh3aItemsParams {
     int slots_in_smem;
     Slot* global_slots;
 };
+// shared memory of the item kernel beside the slots: one queue of 64 (key, 1 / weight) items per warp; the slots live in
+// shared memory when 16 m + this fits (callers decide with P.slots_in_smem and pass the slot bytes only)
+constexpr size_t PMH3A_ITEMS_QUEUE_BYTES = 32 * 64 * 16;
 cudaError_t launch_pmh3a_items(const Pmh3aItemsParams& P, bool key64, int src, int grid, size_t smem, cudaStream_t st);
 cudaError_t launch_pmh3a_items_init(Slot* slots, uint32_t m, cudaStream_t st);
 cudaError_t launch_pmh3a_items_finish(const Slot* slots, uint32_t m, bool key64, void* sig, unsigned long long* max_hbits,

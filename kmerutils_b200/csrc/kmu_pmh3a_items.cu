@@ -18,10 +18,9 @@
 
 namespace kmu {
 
+// all points of one item below the bound
 template <typename V>
-__device__ __forceinline__ void pmh3a_item(V key, double winv, double bound, const Pmh3aItemsParams& P, Slot* slots) {
-    // most items of a large set die on their first point: half a seeding tells (first_point_alive, kmu_device.cuh)
-    if (!first_point_alive<V>(key, winv, bound, P.e.c1)) return;
+__device__ __forceinline__ void pmh3a_item_points(V key, double winv, double bound, const Pmh3aItemsParams& P, Slot* slots) {
     Xoshiro256pp rng;
     rng.seed(nohash_seed(key));
     for (uint32_t i = 1;; ++i) {
@@ -33,6 +32,17 @@ __device__ __forceinline__ void pmh3a_item(V key, double winv, double bound, con
         if (h < bound) slot_update_min(&slots[s], (uint64_t)__double_as_longlong(h), (uint64_t)key);
     }
 }
+template <typename V>
+__device__ __forceinline__ void pmh3a_item(V key, double winv, double bound, const Pmh3aItemsParams& P, Slot* slots) {
+    // most items of a large set die on their first point: half a seeding tells (first_point_alive, kmu_device.cuh)
+    if (first_point_alive<V>(key, winv, bound, P.e.c1)) pmh3a_item_points<V>(key, winv, bound, P, slots);
+}
+
+struct ItemQ {
+    unsigned long long key;
+    double winv;
+};
+static_assert(sizeof(ItemQ) * 64 * 32 == PMH3A_ITEMS_QUEUE_BYTES, "one queue of 64 items per warp");
 
 // SRC 0: explicit lists keys[n] (V), weights[n] (f64); SRC 1: u32-key counting table (8-byte slots);
 // SRC 2: u64-key counting table (16-byte slots, empty key ~0)
@@ -49,26 +59,54 @@ __global__ void __launch_bounds__(1024, 1) pmh3a_items_kernel(const Pmh3aItemsPa
         __syncthreads();
     }
     const V header = (V)word_header(P.kmer_type, P.k);
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < P.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    // Two phases, so that the lanes of a warp stay together: every lane reads its entry and tests the item's first point
+    // (half a seeding); the few items that survive go to the warp's queue and are finished 32 at a time.  Without the
+    // queue a warp runs the whole item loop for one or two lanes at a time (8 of 32 lanes active under ncu).
+    const int lane = threadIdx.x & 31;
+    ItemQ* wq = (ItemQ*)(smem + (P.slots_in_smem ? (size_t)P.m * sizeof(Slot) : 0)) + (threadIdx.x >> 5) * 64;
+    uint32_t qn = 0;  // warp-uniform
+    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); i0 < P.n; i0 += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = i0 + lane;
         V key = 0;
         double w = 0.0;
-        if (SRC == 0) {
-            key = ((const V*)P.keys)[i];
-            w = P.weights[i];
-        } else if (SRC == 1) {
-            const unsigned long long e = ((const unsigned long long*)P.table)[i];
-            if (e != 0) {
-                key = finalize_key<V>((V)(e >> 32), header, P.hash_kind);
-                w = (double)(uint32_t)e;
-            }
-        } else {
-            const ulonglong2 e = ((const ulonglong2*)P.table)[i];
-            if (e.x != ~0ULL) {
-                key = finalize_key<V>((V)e.x, header, P.hash_kind);
-                w = (double)e.y;
+        if (i < P.n) {
+            if (SRC == 0) {
+                key = ((const V*)P.keys)[i];
+                w = P.weights[i];
+            } else if (SRC == 1) {
+                const unsigned long long e = ((const unsigned long long*)P.table)[i];
+                if (e != 0) {
+                    key = finalize_key<V>((V)(e >> 32), header, P.hash_kind);
+                    w = (double)(uint32_t)e;
+                }
+            } else {
+                const ulonglong2 e = ((const ulonglong2*)P.table)[i];
+                if (e.x != ~0ULL) {
+                    key = finalize_key<V>((V)e.x, header, P.hash_kind);
+                    w = (double)e.y;
+                }
             }
         }
-        if (w > 0.0) pmh3a_item<V>(key, 1.0 / w, P.bound, P, slots);
+        double winv = 0.0;
+        bool alive = false;
+        if (w > 0.0) {
+            winv = 1.0 / w;
+            alive = first_point_alive<V>(key, winv, P.bound, P.e.c1);
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, alive);
+        if (alive) wq[qn + __popc(bal & ((1u << lane) - 1u))] = ItemQ{(unsigned long long)key, winv};
+        qn += __popc(bal);
+        __syncwarp();
+        if (qn >= 32) {
+            qn -= 32;
+            const ItemQ it = wq[qn + lane];
+            __syncwarp();
+            pmh3a_item_points<V>((V)it.key, it.winv, P.bound, P, slots);
+        }
+    }
+    if ((uint32_t)lane < qn) {
+        const ItemQ it = wq[lane];
+        pmh3a_item_points<V>((V)it.key, it.winv, P.bound, P, slots);
     }
     if (SRC == 2 && blockIdx.x == 0 && threadIdx.x == 0) {  // the u64 key equal to the table's empty mark
         const unsigned long long c = *P.special;
@@ -103,6 +141,7 @@ __global__ void pmh3a_items_finish_kernel(const Slot* slots, uint32_t m, V* sig,
 template <typename V, int SRC>
 static cudaError_t launch_items_t(const Pmh3aItemsParams& P, int grid, size_t smem, cudaStream_t st) {
     auto kern = pmh3a_items_kernel<V, SRC>;
+    smem += PMH3A_ITEMS_QUEUE_BYTES;  // the warps' queues follow the slots
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
