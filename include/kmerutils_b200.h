@@ -291,7 +291,7 @@ int32_t kmu_count_partition(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k,
                             uint32_t nparts, void* kmers_out, uint64_t* part_counts, int32_t out_on_device);
 
 /* ---- host-side feeders and writers (no device work) --------------------------------------------
- * FASTA / FASTQ reader: packs of ACCEPTED reads as one ASCII buffer + offsets, ready for
+ * FASTA / FASTQ reader (plain or gzip-compressed, as needletail reads them): packs of ACCEPTED reads as one ASCII buffer + offsets, ready for
  * kmu_seqbatch_from_ascii.  A record holding any non-ACGT character is dropped and counted, as
  * parse_with_needletail (src/io.rs:12-72) and readblockseq (src/bin/datasketcher.rs:358-388) do. */
 typedef struct kmu_fastx kmu_fastx;

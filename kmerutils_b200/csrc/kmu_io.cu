@@ -7,6 +7,9 @@
 //   * block signature dump: BlockSeqSketcher::create_signature_dump / dump_blocks
 //     (src/sketching/seqblocksketch.rs:59-65, 172-226).
 // All integers are little-endian as written by the reference's to_le_bytes().
+#include <zlib.h>
+
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -39,10 +42,10 @@ struct kmu_sigdump {
 };
 
 struct kmu_fastx {
-    FILE* f = nullptr;
+    gzFile f = nullptr;  // zlib reads plain and gzip-compressed files alike (needletail does the same, io.rs:20-24)
     std::vector<char> buf;
     size_t pos = 0, len = 0;
-    bool eof = false;
+    bool eof = false, bad_stream = false;
     std::string pending;  // an accepted record that did not fit the previous pack
     bool has_pending = false;
     uint64_t nb_read = 0, nb_bad_read = 0, nb_bases = 0, nb_bad_bases = 0;
@@ -52,7 +55,9 @@ struct kmu_fastx {
         len -= pos;
         pos = 0;
         if (len == buf.size()) buf.resize(buf.size() * 2);
-        size_t n = std::fread(buf.data() + len, 1, buf.size() - len, f);
+        const int got = gzread(f, buf.data() + len, (unsigned)std::min<size_t>(buf.size() - len, 1u << 30));
+        const size_t n = got > 0 ? (size_t)got : 0;
+        if (got < 0) bad_stream = true;
         if (n == 0) eof = true;
         len += n;
         return n > 0;
@@ -87,8 +92,9 @@ extern "C" {
 // ---- FASTA / FASTQ ---------------------------------------------------------------------------
 int32_t kmu_fastx_open(const char* path, kmu_fastx** out) {
     if (!path || !out) return fail(KMU_EINVAL, "null argument");
-    FILE* f = std::fopen(path, "rb");
+    gzFile f = gzopen(path, "rb");
     if (!f) return fail(KMU_EINVAL, "file does not exist: %s", path);
+    gzbuffer(f, 1u << 20);
     auto* h = new kmu_fastx();
     h->f = f;
     h->buf.resize(1 << 22);
@@ -98,7 +104,7 @@ int32_t kmu_fastx_open(const char* path, kmu_fastx** out) {
 
 void kmu_fastx_close(kmu_fastx* h) {
     if (!h) return;
-    if (h->f) std::fclose(h->f);
+    if (h->f) gzclose(h->f);
     delete h;
 }
 
@@ -171,6 +177,7 @@ int32_t kmu_fastx_next_pack(kmu_fastx* h, uint64_t max_seqs, uint8_t* ascii, uin
         ascii_off[++n] = used;
     }
     *nseq_out = n;
+    if (h->bad_stream) return fail(KMU_EINVAL, "corrupt or truncated compressed stream");
     return KMU_OK;
 }
 

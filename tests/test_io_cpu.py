@@ -27,6 +27,37 @@ def test_fastq_packs_and_rejection(tmp_path):
     assert st == {"nb_read": 5, "nb_bad_read": 2, "nb_bases": 35, "nb_bad_bases": 2}
 
 
+def test_gzip_input(tmp_path):
+    """needletail (src/io.rs:20-24) reads .gz transparently: so does the feeder (zlib), with the same packs and counts"""
+    import gzip
+    rng = np.random.default_rng(4)
+    recs = [bytes(rng.choice(list(b"ACGT"), int(n)).astype(np.uint8)) for n in rng.integers(50, 3000, 400)]
+    recs[7] = recs[7][:20] + b"N" + recs[7][21:]
+    text = b"".join(b"@r%d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n" for i, s in enumerate(recs))
+    plain = write(tmp_path, "reads.fastq", text)
+    gz = str(tmp_path / "reads.fastq.gz")
+    with gzip.open(gz, "wb") as f:
+        f.write(text)
+    out = []
+    for path in (plain, gz):
+        with kio.FastxReader(path) as rd:
+            got = []
+            while True:
+                pack = rd.next_pack(64)
+                if not pack:
+                    break
+                got += pack
+            out.append((got, rd.stats()))
+    assert out[0] == out[1]
+    assert out[1][0] == recs[:7] + recs[8:] and out[1][1]["nb_bad_read"] == 1
+    # a truncated gzip stream is an error, not a short file
+    bad = write(tmp_path, "cut.fastq.gz", open(gz, "rb").read()[:-200])
+    with pytest.raises(kb.KmuError):
+        with kio.FastxReader(bad) as rd:
+            while rd.next_pack(64):
+                pass
+
+
 def test_fasta_multiline_crlf_and_quality_traps(tmp_path):
     fasta = b">s1 first\r\nACGT\r\nAC\r\n\r\n>s2\nTTTT\n>s3\nNNNN\n>s4\nGATTACA"
     with kio.FastxReader(write(tmp_path, "b.fa", fasta)) as rd:
