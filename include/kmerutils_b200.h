@@ -278,6 +278,12 @@ int32_t kmu_count_export(kmu_ctx* ctx, const kmu_counter* counter, uint32_t min_
 int32_t kmu_count_dump_multiple(kmu_ctx* ctx, const kmu_counter* counter, const char* path, int32_t count_bytes,
                                 uint64_t* nb_dumped);
 
+/* KmerCountReload::load_multiple_kmers_from_file (kmercount.rs:1209-1351): header fields, the number of records in the file
+ * (*n_read; the reference also reads to the end of file rather than trusting nb_declared) and, when kmers / counts are
+ * given (cap entries each), the records: kmers[i] = the dumped word (`.0`; for Kmer32bit it carries k in its top four bits). */
+int32_t kmu_count_reload_multiple(const char* path, uint32_t* kmer_size, uint32_t* count_bytes, uint64_t* nb_declared,
+                                  uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n_read);
+
 /* partial registers of a counting table, for the multi-GPU whole-file sketch (every rank counts the keys it owns,
  * sketches them; the ranks merge with an allreduce-min on h and a key select): slots = m records {u64 h bits, u64 key},
  * h = largest f64 where no point fell below `bound`.  The table's keys are pre-keys (as inserted); hash_kind maps them. */

@@ -105,6 +105,8 @@ SIGNATURES = {
     "kmu_count_stats": (C.c_int32, [C.c_void_p, C.c_void_p, u64p, u64p, u64p, u64p]),
     "kmu_count_export": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
     "kmu_count_dump_multiple": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int32, u64p]),
+    "kmu_count_reload_multiple": (C.c_int32, [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), u64p, u64p,
+                                              C.POINTER(C.c_uint32), C.c_uint64, u64p]),
     "kmu_count_partition": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32,
                                         C.c_void_p, u64p, C.c_int32]),
     "kmu_fastx_open": (C.c_int32, [C.c_char_p, vpp]),

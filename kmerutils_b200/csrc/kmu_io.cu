@@ -311,4 +311,57 @@ int32_t kmu_sigdump_read(const char* path, uint32_t* sig_size, uint32_t* sketch_
     return rc;
 }
 
+// KmerCountReload::load_multiple_kmers_from_file (src/base/kmercount.rs:1209-1351): header `u32 0xcea2bbff | u8 kmer_size |
+// u8 nb_bytes_by_count | u64 nb_kmer`, then records `kmer.dump() | count` until end of file (the reference does not trust
+// the declared number either).  kmer.dump() is the 4-byte word for the u32 types (kmer_size <= 16) and `u8 k | u64 value`
+// for Kmer64bit (kmer64bit.rs:98-104) -- the reference's reader only knows the 4-byte form.
+int32_t kmu_count_reload_multiple(const char* path, uint32_t* kmer_size, uint32_t* count_bytes, uint64_t* nb_declared,
+                                  uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n_read) {
+    if (!path) return fail(KMU_EINVAL, "null argument");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(KMU_EINVAL, "KmerCountReload::load_multiple_kmers_from_file cannot open file %s", path);
+    uint8_t hdr[14];
+    if (std::fread(hdr, 1, 14, f) != 14) {
+        std::fclose(f);
+        return fail(KMU_EINVAL, "KmerCountReload::load_multiple_kmers_from_file could no read magic");
+    }
+    if (get_u32(hdr) != 0xcea2bbffu) {
+        std::fclose(f);
+        return fail(KMU_EINVAL, "KmerCountReload::load_multiple_kmers_from_file unknow magic %x", get_u32(hdr));
+    }
+    const uint32_t ksz = hdr[4], cb = hdr[5];
+    uint64_t declared;
+    std::memcpy(&declared, hdr + 6, 8);
+    if (cb != 1 && cb != 2) {
+        std::fclose(f);
+        return fail(KMU_EINVAL, "load_multiple_kmers, kmer count on more than 2 bytes not yet implemented");
+    }
+    const size_t ksize = ksz > 16 ? 9 : 4, rec = ksize + cb;
+    std::fseek(f, 0, SEEK_END);
+    const uint64_t nrec = ((uint64_t)std::ftell(f) - 14) / rec;
+    if (kmer_size) *kmer_size = ksz;
+    if (count_bytes) *count_bytes = cb;
+    if (nb_declared) *nb_declared = declared;
+    if (n_read) *n_read = nrec;
+    int32_t rc = KMU_OK;
+    if (kmers && counts) {
+        if (nrec > cap) rc = fail(KMU_EOVERFLOW, "the dump holds %llu k-mers, the buffers %llu", (unsigned long long)nrec, (unsigned long long)cap);
+        else {
+            std::fseek(f, 14, SEEK_SET);
+            std::vector<uint8_t> buf(nrec * rec);
+            if (nrec && std::fread(buf.data(), rec, nrec, f) != nrec) rc = fail(KMU_EINVAL, "short read");
+            for (uint64_t i = 0; rc == KMU_OK && i < nrec; ++i) {
+                const uint8_t* r = buf.data() + i * rec;
+                uint64_t v = 0;
+                if (ksize == 9) std::memcpy(&v, r + 1, 8);
+                else v = get_u32(r);
+                kmers[i] = v;
+                counts[i] = cb == 1 ? r[ksize] : (uint32_t)r[ksize] | ((uint32_t)r[ksize + 1] << 8);
+            }
+        }
+    }
+    std::fclose(f);
+    return rc;
+}
+
 }  // extern "C"

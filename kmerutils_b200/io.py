@@ -123,6 +123,20 @@ def read_signature_dump(path, first=0, count=None):
     return {"sig_size": ss.value, "sketch_size": sk.value, "kmer_size": ks.value, "nb_signatures": n.value}, sig
 
 
+def reload_multiple_kmers(path):
+    """KmerCountReload::load_multiple_kmers_from_file (kmercount.rs:1209-1351) -> dict(kmer_size, count_bytes,
+    nb_declared, kmers (u64 words), counts (u32))"""
+    lib = _lib.load_library()
+    ks, cb, nd, n = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+    check(lib.kmu_count_reload_multiple(os.fsencode(path), C.byref(ks), C.byref(cb), C.byref(nd), None, None, 0, C.byref(n)))
+    kmers = np.zeros(max(n.value, 1), dtype=np.uint64)
+    counts = np.zeros(max(n.value, 1), dtype=np.uint32)
+    check(lib.kmu_count_reload_multiple(os.fsencode(path), None, None, None, _p(kmers, C.POINTER(C.c_uint64)),
+                                        _p(counts, C.POINTER(C.c_uint32)), n.value, C.byref(n)))
+    return {"kmer_size": ks.value, "count_bytes": cb.value, "nb_declared": nd.value, "kmers": kmers[: n.value],
+            "counts": counts[: n.value]}
+
+
 def dump_sketch_params(dirpath, kmer_size, sketch_size, algo="PROB3A", data_t="DNA"):
     """SeqSketcherParams::dump_json (sketcharg.rs:79-106): `sketchparams_dump.json` in a directory."""
     path = os.path.join(dirpath, "sketchparams_dump.json")

@@ -249,4 +249,10 @@ def test_multiple_kmer_dump_format(engine, oracle, tmp_path, k, ktype):
         got[key] = struct.unpack("<H", r[-2:])[0]
     want = {int(a): min(int(c), 255) for a, c in zip(keys, cnts) if c >= 2}
     assert got == want
+    # and back through the reloader (KmerCountReload::load_multiple_kmers_from_file)
+    from kmerutils_b200 import io as kio
+    d = kio.reload_multiple_kmers(path)
+    assert (d["kmer_size"], d["count_bytes"], d["nb_declared"]) == (k, 2, n)
+    mask = 0x0FFFFFFF if ktype == kb.KMER32 else 0xFFFFFFFFFFFFFFFF
+    assert {int(a) & mask: int(c) for a, c in zip(d["kmers"], d["counts"])} == want
     ctr.destroy()

@@ -27,6 +27,27 @@ def test_fastq_packs_and_rejection(tmp_path):
     assert st == {"nb_read": 5, "nb_bad_read": 2, "nb_bases": 35, "nb_bad_bases": 2}
 
 
+def test_reload_multiple_kmer_dump(tmp_path):
+    """KmerCountReload::load_multiple_kmers_from_file (kmercount.rs:1209-1351) on hand-written dumps: 4-byte k-mer words
+    with 1- or 2-byte counts, and the Kmer64bit form (u8 k + u64 value)."""
+    recs = [(0xd02a013d, 2), (0x40a804f4, 300), (0x02a013d0, 7)]
+    body = b"".join(struct.pack("<IH", k, c) for k, c in recs)
+    p = write(tmp_path, "a.multi_kmer.bin", struct.pack("<IBBQ", 0xcea2bbff, 16, 2, 3) + body)
+    d = kio.reload_multiple_kmers(p)
+    assert (d["kmer_size"], d["count_bytes"], d["nb_declared"]) == (16, 2, 3)
+    assert d["kmers"].tolist() == [k for k, _ in recs] and d["counts"].tolist() == [c for _, c in recs]
+    body = b"".join(struct.pack("<IB", k, min(c, 255)) for k, c in recs)
+    d = kio.reload_multiple_kmers(write(tmp_path, "b.bin", struct.pack("<IBBQ", 0xcea2bbff, 16, 1, 99) + body))
+    assert d["counts"].tolist() == [2, 255, 7] and d["nb_declared"] == 99  # the records count, not the header
+    body = b"".join(struct.pack("<BQH", 31, v, c) for v, c in [(0x123456789abcdef, 5), (42, 2)])
+    d = kio.reload_multiple_kmers(write(tmp_path, "c.bin", struct.pack("<IBBQ", 0xcea2bbff, 31, 2, 2) + body))
+    assert d["kmers"].tolist() == [0x123456789abcdef, 42] and d["counts"].tolist() == [5, 2]
+    with pytest.raises(kb.KmuError):
+        kio.reload_multiple_kmers(write(tmp_path, "d.bin", struct.pack("<IBBQ", 0xceabeadd, 16, 2, 0)))
+    with pytest.raises(kb.KmuError):
+        kio.reload_multiple_kmers(str(tmp_path / "missing.bin"))
+
+
 def test_gzip_input(tmp_path):
     """needletail (src/io.rs:20-24) reads .gz transparently: so does the feeder (zlib), with the same packs and counts"""
     import gzip
