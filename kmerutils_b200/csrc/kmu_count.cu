@@ -95,9 +95,9 @@ struct CountOps<uint64_t> {
         unsigned long long* tab = (unsigned long long*)t.slots;
         uint64_t i = fmix64(key) & t.capmask;
         for (uint64_t probe = 0; probe <= t.capmask; ++probe) {
-            // the home slot is claimed without looking first: the CAS returns the key that is there
-            unsigned long long cur = ~0ULL;  // EMPTY
-            if (probe) cur = *(volatile unsigned long long*)(tab + 2 * i);
+            // (looking first is the faster order here: claiming the home slot blind, as the u32 table does, made the
+            // insertion of 960 M 31-mers 8 % slower -- most k-mers of a read set are repeats and the CAS is wasted)
+            unsigned long long cur = *(volatile unsigned long long*)(tab + 2 * i);
             if (cur == EMPTY) {
                 cur = atomicCAS(tab + 2 * i, EMPTY, (unsigned long long)key);
                 if (cur == EMPTY) cur = key;
