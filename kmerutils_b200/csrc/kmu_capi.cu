@@ -962,7 +962,8 @@ static int32_t sketch_pmh3a_locked(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t
             LaunchClass& p = classes.back();
             // a handful of sequences is not worth a launch of its own (0.1 ms whatever its size): they join the
             // class above, whose histogram / table is large enough for anything shorter
-            if (c.count <= 2 * (uint64_t)ctx->sm_count && p.first + p.count == c.first) {
+            // (so does a class with less than ~0.1 ms of work in it: the short reads of one chunk of the host pipeline)
+            if ((c.count <= 2 * (uint64_t)ctx->sm_count || c.count * c.nk_max <= 2000000) && p.first + p.count == c.first) {
                 p.count += c.count;
                 continue;
             }
@@ -1350,12 +1351,14 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
     std::vector<uint64_t> lay_own;
     if (!same_layout) layout_offsets(nbases, nseq, lay_own);
     const uint64_t* lay = same_layout ? byte_off : lay_own.data();
-    // chunk sizes grow geometrically from a small first chunk: the upload of chunk c + 1 (PCIe, about 1.8 x the
-    // sketching rate) hides behind the sketching of chunk c, so only the first small upload is exposed; large
-    // chunks later (few launch tails); a small last chunk (short drain of the final download)
+    // chunk sizes grow geometrically from a small first chunk: the upload of chunk c + 1 must hide behind the sketching
+    // of chunk c, and PCIe moves packed bases only ~1.3 x as fast as the kernels consume them (50 GB/s against 39 GB/s
+    // on C2), so a chunk may be at most ~1.3 x its predecessor: 25 % growth from 1/48 of the input (measured: 32.4 ms per
+    // call; 50 % from 1/128 stalls on every upload of the growth phase, 34.0 ms; scripts/e2e_sweep.sh); large chunks
+    // later (few launch tails); a small last chunk (short drain of the final download)
     uint64_t big = std::max<uint64_t>(64ull << 20, total_bytes / 4);
     uint64_t small = std::max<uint64_t>(8ull << 20, total_bytes / 48);
-    uint64_t first = std::max<uint64_t>(4ull << 20, total_bytes / 128);
+    uint64_t first = std::max<uint64_t>(4ull << 20, total_bytes / 48);
     bool grow = true;
     if (const char* env = std::getenv("KMU_HOST_CHUNK_BYTES")) {  // tests: force many small chunks
         const uint64_t v = std::strtoull(env, nullptr, 10);
@@ -1363,6 +1366,12 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
             big = small = first = v;
             grow = false;
         }
+    }
+    uint32_t grow_pct = 25;  // experiments: KMU_HOST_GROW_PCT, KMU_HOST_FIRST_DIV
+    if (const char* env = std::getenv("KMU_HOST_GROW_PCT")) grow_pct = (uint32_t)std::strtoul(env, nullptr, 10);
+    if (const char* env = std::getenv("KMU_HOST_FIRST_DIV")) {
+        const uint64_t d = std::strtoull(env, nullptr, 10);
+        if (d) first = std::max<uint64_t>(4ull << 20, total_bytes / d);
     }
     uint64_t next_target = first;
     std::vector<uint64_t> cut{0};
@@ -1374,7 +1383,7 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
         if (end - lay[start] >= target || i + 1 == nseq) {
             cut.push_back(i + 1);
             start = i + 1;
-            if (grow) next_target = std::min<uint64_t>(big, next_target + next_target / 2);
+            if (grow) next_target = std::min<uint64_t>(big, next_target + next_target * grow_pct / 100);
         }
     }
     const size_t nchunks = cut.size() - 1;

@@ -19,4 +19,6 @@ pin_in[: len(packed)] = torch.from_numpy(packed)
 out = torch.empty((len(nb), 200), dtype=torch.int32).pin_memory()
 for _ in range(int(os.environ.get("CALLS", "1"))):
     eng.sketch_pmh3a_host((pin_in.data_ptr(), pin_in.numel()), off, nb, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200, out.data_ptr())
+    print("host_ms %.2f" % eng.last_times()["host_ms"], end="  ")
+print()
 print(eng.last_times())
