@@ -22,11 +22,14 @@
 //        HyperLogLogSketch}          src/sketching/setsketchert.rs:54-896 same names
 //  jaccard_index_probminhash3a       seqsketchjaccard.rs:423-495          same name
 //  dump_signatures_block_u32 / SigSketchFileReader  :577-712              same names
+//  aautils::kmeraa::{Alphabet,KmerAA32bit,KmerAA64bit,SequenceAA,KmerGenerator},
+//  aautils::setsketchert::{SeqSketcher,SeqSketcherAAT,ProbHash3aSketch,HyperLogLogSketch}   kmerutils::aautils::*
 //
 //  The Rust closure `fhash: Fn(&Kmer) -> Kmer::Val` cannot cross into CUDA: the five closures the
 //  reference actually passes are the constants of kmerutils::KmerHash.
 // ============================================================================
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -677,4 +680,223 @@ class HyperLogLogSketch : public SeqSketcherT<Kmer, S> {
 };
 
 }  // namespace sketching
+// ================================================================== amino acids (src/aautils)
+namespace aautils {
+
+/// Alphabet (src/aautils/kmeraa.rs:29-130): 20 residues on 5 bits, codes 1..21 in the order of "ACDEFGHIKLMNPQRSTVWY"
+/// (code 14 is skipped: Q = 15)
+struct Alphabet {
+    static constexpr const char* bases = "ACDEFGHIKLMNPQRSTVWY";
+    uint8_t len() const { return 20; }
+    uint8_t get_nb_bits() const { return 5; }
+    bool is_valid_base(uint8_t c) const { return c && std::strchr(bases, (char)c) != nullptr; }
+    uint8_t encode(uint8_t c) const {
+        const char* p = c ? std::strchr(bases, (char)c) : nullptr;
+        if (!p) throw Panic(KMU_EINVAL, "encode: not a code in alpahabet for amino acid");
+        const uint8_t i = (uint8_t)(p - bases) + 1;
+        return i >= 14 ? i + 1 : i;
+    }
+    uint8_t decode(uint8_t code) const {
+        const uint8_t i = code > 14 ? code - 1 : code;
+        if (code == 0 || code == 14 || i > 20) throw Panic(KMU_EINVAL, "decode: not a code in alpahabet for amino acid");
+        return (uint8_t)bases[i - 1];
+    }
+};
+
+/// KmerAA32bit / KmerAA64bit (kmeraa.rs:147-400): k residues of 5 bits, first residue in the most significant bits
+template <typename W, int32_t TYPE>
+struct KmerAAbits {
+    using Val = W;
+    static constexpr int32_t kmu_type = TYPE;
+    W aa = 0;
+    uint8_t nb_base = 0;
+    KmerAAbits() = default;
+    explicit KmerAAbits(uint8_t nb) : aa(0), nb_base(nb) {  // ::new panics from sizeof(W) * 8 / 5 residues on (kmeraa.rs:153-161)
+        if (nb >= sizeof(W) * 8 / 5) throw Panic(KMU_EINVAL, "KmerAA: nb_base too large for the word");
+    }
+    static KmerAAbits build(Val val, uint8_t kmer_size) { return from_word(val, kmer_size); }
+    static KmerAAbits from_word(Val word, uint8_t kmer_size) {
+        KmerAAbits k;
+        k.aa = word;
+        k.nb_base = kmer_size;
+        return k;
+    }
+    static size_t get_nb_base_max() { return sizeof(W) * 8 / 5; }
+    uint8_t get_nb_base() const { return nb_base; }
+    Val get_compressed_value() const { return aa; }
+    size_t get_bitsize() const { return sizeof(W) * 8; }
+    /// push takes the residue as its ASCII letter and encodes it (kmeraa.rs:171-182)
+    KmerAAbits push(uint8_t c) const {
+        const W mask = ((W)1 << (5 * nb_base)) - 1;
+        return from_word((W)(((aa << 5) & mask) | (W)(Alphabet().encode(c) & 31)), nb_base);
+    }
+    KmerAAbits reverse_complement() const { throw Panic(KMU_EINVAL, "KmerAA reverse_complement not yet implemented"); }
+    std::vector<uint8_t> get_uncompressed_kmer() const {
+        std::vector<uint8_t> s(nb_base);
+        for (int i = 0; i < nb_base; ++i) s[i] = Alphabet().decode((uint8_t)((aa >> (5 * (nb_base - 1 - i))) & 31));
+        return s;
+    }
+    friend bool operator==(KmerAAbits a, KmerAAbits b) { return a.aa == b.aa && a.nb_base == b.nb_base; }
+    friend bool operator<(KmerAAbits a, KmerAAbits b) { return a.nb_base != b.nb_base ? a.nb_base < b.nb_base : a.aa < b.aa; }
+};
+using KmerAA32bit = KmerAAbits<uint32_t, KMU_KMERAA32>;
+using KmerAA64bit = KmerAAbits<uint64_t, KMU_KMERAA64>;
+
+/// SequenceAA (kmeraa.rs:404-456): the residues as ASCII letters
+class SequenceAA {
+  public:
+    SequenceAA() = default;
+    explicit SequenceAA(const std::string& str) : seq_(str.begin(), str.end()) {}  // SequenceAA::new / from_str
+    static SequenceAA new_filtered(const std::string& buf, const Alphabet& alphabet) {  // :447-456
+        SequenceAA s;
+        for (char c : buf)
+            if (alphabet.is_valid_base((uint8_t)c)) s.seq_.push_back((uint8_t)c);
+        return s;
+    }
+    size_t len() const { return seq_.size(); }
+    size_t size() const { return seq_.size(); }
+    bool is_empty() const { return seq_.empty(); }
+    uint8_t get_base(size_t pos) const {
+        if (pos >= seq_.size()) throw Panic(KMU_EINVAL, "SequenceAA::get_base: position beyond the end");
+        return seq_[pos];
+    }
+    std::string to_string() const { return std::string(seq_.begin(), seq_.end()); }
+    const std::vector<uint8_t>& residues() const { return seq_; }
+
+  private:
+    std::vector<uint8_t> seq_;
+};
+
+/// RAII device batch of proteins (5-bit codes in HBM; an invalid residue panics as Alphabet::encode does)
+class DeviceBatchAA {
+  public:
+    explicit DeviceBatchAA(const std::vector<const SequenceAA*>& vseq, size_t begin = 0, size_t end = ~(size_t)0) {
+        std::vector<uint64_t> off(vseq.size() + 1, 0);
+        std::vector<uint8_t> ascii;
+        for (size_t i = 0; i < vseq.size(); ++i) {
+            const auto& r = vseq[i]->residues();
+            const size_t b = std::min(begin, r.size()), e = std::min(end, r.size());
+            ascii.insert(ascii.end(), r.begin() + b, r.begin() + std::max(b, e));
+            off[i + 1] = ascii.size();
+        }
+        ascii.push_back(0);
+        check(kmu_seqbatch_from_aa(Context::global().get(), ascii.data(), off.data(), vseq.size(), 0, nullptr, &b_), "SequenceAA");
+    }
+    ~DeviceBatchAA() { kmu_seqbatch_destroy(b_); }
+    DeviceBatchAA(const DeviceBatchAA&) = delete;
+    DeviceBatchAA& operator=(const DeviceBatchAA&) = delete;
+    kmu_seqbatch* get() const { return b_; }
+
+  private:
+    kmu_seqbatch* b_ = nullptr;
+};
+
+/// KmerGenerator<KmerAA..> (kmeraa.rs:646-684)
+template <typename T>
+class KmerGenerator {
+  public:
+    explicit KmerGenerator(uint8_t ksize) : kmer_size_(ksize) {}
+    size_t get_kmer_size() const { return kmer_size_; }
+    std::vector<T> generate_kmer(const SequenceAA& seq) const { return run(DeviceBatchAA({&seq})); }
+    /// KmerSeqIterator::set_range(first, last) (kmeraa.rs:540-557): k-mers inside residues [begin, end)
+    std::vector<T> generate_kmer_in_range(const SequenceAA& seq, size_t begin, size_t end) const {
+        if (begin >= end || end > seq.size()) throw Panic(KMU_EINVAL, "KmerSeqIterator::set_range failed");
+        return run(DeviceBatchAA({&seq}, begin, end));
+    }
+
+  private:
+    std::vector<T> run(const DeviceBatchAA& b) const {
+        std::vector<typename T::Val> words(kmu_kmer_count(b.get(), kmer_size_));
+        check(kmu_generate_kmers(Context::global().get(), b.get(), kmer_size_, T::kmu_type, KMU_HASH_IDENTITY_RAW, words.data(), nullptr, 0),
+              "KmerGenerator::generate_kmer");
+        std::vector<T> out;
+        out.reserve(words.size());
+        for (auto w : words) out.push_back(T::from_word(w, kmer_size_));
+        return out;
+    }
+    uint8_t kmer_size_;
+};
+
+/// SeqSketcher of the amino-acid module (src/aautils/setsketchert.rs:1020-1200)
+class SeqSketcher {
+  public:
+    SeqSketcher(size_t kmer_size, size_t sketch_size) : kmer_size_(kmer_size), sketch_size_(sketch_size) {}
+    size_t get_kmer_size() const { return kmer_size_; }
+    size_t get_sketch_size() const { return sketch_size_; }
+    template <typename Kmer>
+    std::vector<std::vector<typename Kmer::Val>> sketch_probminhash3a(const std::vector<const SequenceAA*>& vseq, KmerHash fhash) const {
+        DeviceBatchAA b(vseq);
+        std::vector<typename Kmer::Val> flat(vseq.size() * sketch_size_);
+        check(kmu_sketch_pmh3a(Context::global().get(), b.get(), (uint32_t)kmer_size_, Kmer::kmu_type, fhash.kind, (uint32_t)sketch_size_,
+                               flat.data(), 0),
+              "sketch_probminhash3a");
+        return sketching::rows_of(flat, vseq.size(), sketch_size_);
+    }
+    template <typename Kmer, typename S = double>
+    std::vector<std::vector<S>> sketch_superminhash(const std::vector<const SequenceAA*>& vseq, KmerHash fhash) const {
+        DeviceBatchAA b(vseq);
+        std::vector<S> flat(vseq.size() * sketch_size_);
+        check(kmu_sketch_superminhash(Context::global().get(), b.get(), (uint32_t)kmer_size_, Kmer::kmu_type, fhash.kind,
+                                      (uint32_t)sketch_size_, KMU_HASHER_FNV, (int32_t)sizeof(S), flat.data(), 0),
+              "sketch_superminhash");
+        return sketching::rows_of(flat, vseq.size(), sketch_size_);
+    }
+
+  private:
+    size_t kmer_size_, sketch_size_;
+};
+
+/// SeqSketcherAAT (src/aautils/setsketchert.rs:42-72) and two of its implementations
+template <typename Kmer, typename SigT>
+struct SeqSketcherAAT {
+    using Sig = SigT;
+    virtual ~SeqSketcherAAT() = default;
+    virtual size_t get_kmer_size() const = 0;
+    virtual size_t get_sketch_size() const = 0;
+    virtual std::vector<std::vector<Sig>> sketch_compressedkmeraa(const std::vector<const SequenceAA*>& vseq, KmerHash fhash) const = 0;
+};
+template <typename Kmer>
+class ProbHash3aSketch : public SeqSketcherAAT<Kmer, typename Kmer::Val> {
+  public:
+    explicit ProbHash3aSketch(const sketching::SeqSketcherParams& p) : p_(p) {}
+    size_t get_kmer_size() const override { return p_.kmer_size; }
+    size_t get_sketch_size() const override { return p_.sketch_size; }
+    std::vector<std::vector<typename Kmer::Val>> sketch_compressedkmeraa(const std::vector<const SequenceAA*>& vseq,
+                                                                         KmerHash fhash) const override {
+        return SeqSketcher(p_.kmer_size, p_.sketch_size).template sketch_probminhash3a<Kmer>(vseq, fhash);
+    }
+
+  private:
+    sketching::SeqSketcherParams p_;
+};
+template <typename Kmer, typename S>
+class HyperLogLogSketch : public SeqSketcherAAT<Kmer, S> {
+  public:
+    HyperLogLogSketch(const sketching::SeqSketcherParams& p, const sketching::SetSketchParams& hll) : p_(p), hll_(hll) { hll_.m = p.sketch_size; }
+    size_t get_kmer_size() const override { return p_.kmer_size; }
+    size_t get_sketch_size() const override { return p_.sketch_size; }
+    std::vector<std::vector<S>> sketch_compressedkmeraa(const std::vector<const SequenceAA*>& vseq, KmerHash fhash) const override {
+        return run(vseq, fhash, 0);
+    }
+    /// ONE sketch for the whole collection (sketch_compressedkmeraa_seqs)
+    std::vector<std::vector<S>> sketch_compressedkmeraa_seqs(const std::vector<const SequenceAA*>& vseq, KmerHash fhash) const {
+        return run(vseq, fhash, 1);
+    }
+
+  private:
+    std::vector<std::vector<S>> run(const std::vector<const SequenceAA*>& vseq, KmerHash fhash, int whole) const {
+        DeviceBatchAA b(vseq);
+        const size_t nrows = whole ? 1 : vseq.size();
+        std::vector<S> flat(nrows * hll_.m);
+        const kmu_setsketch_params prm{hll_.b, hll_.m, hll_.a, hll_.q};
+        check(kmu_sketch_setsketch(Context::global().get(), b.get(), (uint32_t)p_.kmer_size, Kmer::kmu_type, fhash.kind, &prm,
+                                   (int32_t)sizeof(S), whole, flat.data(), 0),
+              "HyperLogLogSketch");
+        return sketching::rows_of(flat, nrows, hll_.m);
+    }
+    sketching::SeqSketcherParams p_;
+    sketching::SetSketchParams hll_;
+};
+
+}  // namespace aautils
 }  // namespace kmerutils

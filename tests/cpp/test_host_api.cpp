@@ -10,6 +10,9 @@
 //   src/sketching/seqsketchjaccard.rs:742-791   test_pminhasha_kmer_smallb
 //   src/sketching/seqsketchjaccard.rs:947-1004  test_superminhash_kmer_16b32bit_serial
 //   src/sketching/seqsketchjaccard.rs:1015-...  test_reload_sketch_file
+//   src/aautils/kmeraa.rs:920-1021              test_seqaa_32bit_iterator_range, test_seqaa_iterator_end
+//   src/aautils/setsketchert.rs:1218-1266       test_seqaa_probminhash_64bit
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -289,6 +292,70 @@ static void test_reload_sketch_file(const std::string& dir) {
     EXPECT(n == sigs.size());
 }
 
+static void test_amino_acids() {
+    using namespace kmerutils::aautils;
+    const std::string prot =
+        "MTEQIELIKLYSTRILALAAQMPHVGSLDNPDASAMKRSPLCGSKVTVDVIMQNGKITEFAQNVKACALGQAAASVAAQNIIGRTAEEVVRARDELAAMLKSGGPPPGPPFDGFEVLAPASEYKNRHASILLSLDATAEACASIAAQNSA";
+    SequenceAA seqaa(prot);
+    // test_seqaa_32bit_iterator_range (kmeraa.rs:920-956): 4-mers of the range 3..10 are QIEL IELI ELIK LIKL
+    const auto k4 = aautils::KmerGenerator<KmerAA32bit>(4).generate_kmer_in_range(seqaa, 3, 10);
+    EXPECT(k4.size() == 4);
+    const char* want4[4] = {"QIEL", "IELI", "ELIK", "LIKL"};
+    for (size_t i = 0; i < k4.size() && i < 4; ++i) {
+        const auto u = k4[i].get_uncompressed_kmer();
+        EXPECT(std::string(u.begin(), u.end()) == want4[i]);
+    }
+    // test_seqaa_iterator_end (kmeraa.rs:997-1021): the last 8-mer of the first 32 residues is VGSLDNPD
+    SequenceAA head(prot.substr(0, 32));
+    const auto k8 = aautils::KmerGenerator<KmerAA64bit>(8).generate_kmer(head);
+    EXPECT(k8.size() == 25);
+    const auto last = k8.back().get_uncompressed_kmer();
+    EXPECT(std::string(last.begin(), last.end()) == "VGSLDNPD");
+    // the value type agrees with the generated words: push the next residue by hand
+    KmerAA64bit km = k8[0];
+    for (size_t i = 1; i < k8.size(); ++i) {
+        km = km.push((uint8_t)prot[7 + i]);
+        EXPECT(km == k8[i]);
+    }
+    // an invalid residue panics (Alphabet::encode, kmeraa.rs:106); new_filtered drops it (:447-456)
+    bool threw = false;
+    try {
+        SequenceAA bad(std::string("MTEQXIELIK"));
+        aautils::KmerGenerator<KmerAA32bit>(4).generate_kmer(bad);
+    } catch (const Panic&) {
+        threw = true;
+    }
+    EXPECT(threw);
+    EXPECT(SequenceAA::new_filtered("MTxEQ*IBLKZ", Alphabet()).to_string() == "MTEQILK");
+    // test_seqaa_probminhash_64bit (setsketchert.rs:1218-1266): the second string is the first half of the first, twice
+    const std::string str1 = "MTEQIELIKLYSTRILALAAQMPHVGSLDNPDASAMKRSPLCGSKVTVDVIMQNGKITFDGFEVLAPASEYKNRHASILLSLDATAEACASIAAQNSA";
+    const std::string str2 = "MTEQIELIKLYSTRILALAAQMPHVGSLDNPDASAMKRSPLCGSKVMTEQIELIKLYSTRILALAAQMPHVGSLDNPDASAMKRSPLCGSKV";
+    SequenceAA seq1(str1), seq2(str2);
+    aautils::SeqSketcher sketcher(5, 400);
+    const auto sig = sketcher.sketch_probminhash3a<KmerAA64bit>({&seq1, &seq2}, KmerHash::masked_value());
+    const double dist = sketching::compute_probminhash_jaccard(sig[0], sig[1]);
+    EXPECT(std::abs(dist - 0.5) < 1. / 10.);  // setsketchert.rs:1264
+    // bit-exact against the oracle (the oracle takes the residues as ASCII), trait object, 32-bit k-mers, SetSketch
+    for (const SequenceAA* sq : {&seq1, &seq2, &seqaa}) {
+        std::vector<uint64_t> want(400);
+        orc_sketch_pmh3a_seq(sq->residues().data(), sq->size(), 5, ORC_KMERAA64, ORC_HASH_MASKED_VALUE, 400, want.data());
+        aautils::ProbHash3aSketch<KmerAA64bit> ph({5, 400});
+        const aautils::SeqSketcherAAT<KmerAA64bit, uint64_t>& tr = ph;
+        EXPECT(tr.sketch_compressedkmeraa({sq}, KmerHash::masked_value())[0] == want);
+        std::vector<uint64_t> want32(100);
+        orc_sketch_pmh3a_seq(sq->residues().data(), sq->size(), 6, ORC_KMERAA32, ORC_HASH_MASKED_VALUE, 100, want32.data());
+        const auto got32 = aautils::SeqSketcher(6, 100).sketch_probminhash3a<KmerAA32bit>({sq}, KmerHash::masked_value())[0];
+        EXPECT(std::vector<uint64_t>(got32.begin(), got32.end()) == want32);
+    }
+    sketching::SetSketchParams prm;
+    aautils::HyperLogLogSketch<KmerAA64bit, uint16_t> hll({12, 128}, prm);
+    const auto regs = hll.sketch_compressedkmeraa({&seqaa}, KmerHash::masked_value());
+    const uint64_t off0 = 0, nres = seqaa.size();
+    std::vector<uint16_t> wr(128);
+    orc_sketch_setsketch_batch(seqaa.residues().data(), &off0, &nres, 1, 12, ORC_KMERAA64, ORC_HASH_MASKED_VALUE, prm.b, 128, prm.a, prm.q, 2, wr.data(), 1);
+    EXPECT(regs[0] == wr);
+}
+
 int main(int argc, char** argv) {
     const std::string dir = argc > 1 ? argv[1] : "/tmp";
     try {
@@ -299,6 +366,7 @@ int main(int argc, char** argv) {
         test_pminhasha_kmer_smallb();
         test_superminhash_and_hll();
         test_reload_sketch_file(dir);
+        test_amino_acids();
     } catch (const std::exception& e) {
         std::fprintf(stderr, "exception: %s\n", e.what());
         return 2;
