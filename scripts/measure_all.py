@@ -137,6 +137,9 @@ def main():
     psig = torch.empty((len(pl), 400), dtype=torch.int64, device=dev)
     ms = timed(eng, lambda: eng.sketch_pmh3a(pb, 12, kb.KMERAA64, kb.HASH_MASKED_VALUE, 400, out_device_ptr=psig.data_ptr()), 2)
     line("probminhash3a proteome AA k=12 m=400 (residues)", int(pl.sum()), ms, 1.0 + 3200.0 * len(pl) / int(pl.sum()))
+    # one SetSketch for the whole proteome (sketch_compressedkmeraa_seqs: what a proteome comparison uses), default parameters
+    ms = timed(eng, lambda: eng.sketch_setsketch(pb, 12, kb.KMERAA64, kb.HASH_MASKED_VALUE, None, np.uint16, whole=True), 2)
+    line("setsketch whole proteome AA k=12 m=4096 u16 (residues)", int(pl.sum()), ms, 1.0)
     pb.destroy()
     # SetSketch per protein, default parameters (m = 4096 registers for ~270 12-mers: every item places every point,
     # the exact path; 2 000 proteins)
