@@ -361,7 +361,8 @@ int32_t kmu_sketch_setsketch(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, in
         Q.group = group ? 1 : 0;
         Q.work_counter = d_work + ci++;
         const uint64_t per_warp = align_up((uint64_t)m * 4, 16) + 32ull * 2 * m * sizeof(uint32_t);
-        uint64_t warps = group ? 1 : std::min<uint64_t>(count, (uint64_t)ctx->sm_count * 8);
+        // one-warp CTAs waiting on chains of f64 operations (0.24 IPC with 8 per SM): as many as an SM holds
+        uint64_t warps = group ? 1 : std::min<uint64_t>(count, (uint64_t)ctx->sm_count * 24);
         const uint64_t budget = 8ull << 30;
         if (warps * per_warp > budget) warps = std::max<uint64_t>(1, budget / per_warp);
         CUDA_TRY(ctx->table_scratch.reserve(warps * per_warp));
