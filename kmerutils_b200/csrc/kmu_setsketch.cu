@@ -19,6 +19,7 @@
 //   * exact path (few k-mers relative to m): one warp per sketch, 32 items per round with a full
 //     lazily-reset permutation per lane in global scratch, lower_k = min register between rounds.
 // log / exp are the deterministic routines of kmu_detmath.cuh (bit-identical to the CPU oracle).
+#include <algorithm>
 #include <cstdint>
 
 #include "kmu_detmath.cuh"
@@ -304,6 +305,75 @@ __global__ void __launch_bounds__(512, 2) ssk_whole_kernel(const SskParams P, Se
     }
 }
 
+// DNA form of the whole-batch kernel, warp-cooperative: the lanes of a warp take 32 consecutive positions of the warp's
+// slice at a time and stay together, which allows two phases -- (1) half a seeding per item: the first output of
+// Xoshiro256++ needs only s0 and s3 (SplitMix64 outputs 1 and 4 of the seed), and almost every item of a long input stops
+// on that draw; (2) the items whose ziggurat draw is not accepted at once, or whose first point falls below the cut
+// (about one in 90), are queued per warp and finished 32 at a time with the full generator.  (In the per-thread-chunk
+// form above the lanes that take the rare path never reconverge with the others before the end of their chunk.)
+constexpr uint32_t SSK_WHOLE_WARPS = 16;
+template <typename V>
+__global__ void __launch_bounds__(32 * SSK_WHOLE_WARPS, 2) ssk_whole_warp_kernel(const SskParams P, SeqView b, uint64_t total_bytes,
+                                                                                   uint32_t kspec, double xcut) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    double* zx = (double*)smem;
+    double* zf = zx + 264;
+    V* wq = (V*)(zf + 264) + (threadIdx.x >> 5) * SSK_QUEUE;
+    uint32_t* regs = (uint32_t*)((V*)(zf + 264) + SSK_WHOLE_WARPS * SSK_QUEUE);
+    load_zig_tables(zx, zf);
+    const ZigTables zt{zx, zf};
+    const uint32_t m = P.C.m;
+    for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) regs[j] = 0;
+    __syncthreads();
+    const V header = (V)word_header(P.kmer_type, P.k);
+    const bool canonical = hash_is_canonical(P.hash_kind);
+    const int lane = threadIdx.x & 31;
+    const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    bool ok = true;
+    uint32_t qn = 0;  // warp-uniform
+    for (uint64_t g = warp; g < ngroups; g += nwarps)
+        warp_for_each_kmer<V>(b, total_bytes, g, P.k, canonical, lane, [&](V pk, bool active) {
+            const V key = finalize_key<V>(pk, header, P.hash_kind);
+            bool full = false;
+            if (active) {
+                const uint64_t sd = nohash_seed(key);
+                uint64_t x0 = sd, x3 = sd + 3ULL * 0x9E3779B97F4A7C15ULL;
+                const uint64_t s0 = Xoshiro256pp::splitmix(x0), s3 = Xoshiro256pp::splitmix(x3);
+                const uint64_t bits = rotl64(s0 + s3, 23) + s0;
+                const uint32_t zi = (uint32_t)bits & 0xffu;
+                const double e0 = __dmul_rn(__dsub_rn(__longlong_as_double((long long)((bits >> 12) | 0x3FF0000000000000ULL)),
+                                                      1.0 - 2.220446049250313e-16 / 2.0),
+                                            zx[zi]);
+                full = !(e0 < zx[zi + 1] && __dmul_rn(P.C.inva_m0, e0) > xcut);
+            }
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, full);
+            if (full) wq[qn + __popc(bal & ((1u << lane) - 1u))] = key;
+            qn += __popc(bal);
+            __syncwarp();
+            if (qn >= 32) {
+                qn -= 32;
+                const V kq = wq[qn + lane];
+                __syncwarp();
+                Xoshiro256pp rng;
+                rng.seed(nohash_seed(kq));
+                ok &= ssk_item_points(rng, zt, P.C, kspec, xcut, regs);
+            }
+        });
+    if ((uint32_t)lane < qn) {
+        Xoshiro256pp rng;
+        rng.seed(nohash_seed(wq[lane]));
+        ok &= ssk_item_points(rng, zt, P.C, kspec, xcut, regs);
+    }
+    if (!ok) *P.slow_count = 1ULL;  // overflow flag of the whole-batch path
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) {
+        const uint32_t v = regs[j];
+        if (v) atomicMax(P.whole_regs + j, v);
+    }
+}
+
 // registers (u32) -> signature type
 __global__ void ssk_store_kernel(const uint32_t* regs, uint32_t m, void* out, int sig_bytes) {
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x)
@@ -421,6 +491,22 @@ cudaError_t launch_ssk_team(const SskParams& P, int grid, int block, size_t smem
 template <typename V, bool AA>
 static cudaError_t launch_whole_t(const SskParams& P, const SeqView& b, uint64_t total_bytes, uint32_t kspec, double xcut,
                                   int grid, size_t smem, cudaStream_t st) {
+    if constexpr (!AA) {  // DNA: the warp-cooperative form (queues of SSK_QUEUE keys per warp in front of the registers)
+        auto kern = ssk_whole_warp_kernel<V>;
+        smem += SSK_WHOLE_WARPS * SSK_QUEUE * sizeof(V);
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = smem;
+        }
+        const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
+        const uint64_t want = (ngroups + SSK_WHOLE_WARPS - 1) / SSK_WHOLE_WARPS;
+        // `grid` is sized for 512 chunks of 64 bytes per CTA: at most two CTAs per SM
+        const int g2 = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)std::max(grid, 1) >= want ? want : (uint64_t)grid));
+        kern<<<g2, 32 * SSK_WHOLE_WARPS, smem, st>>>(P, b, total_bytes, kspec, xcut);
+        return cudaGetLastError();
+    }
     auto kern = ssk_whole_kernel<V, AA>;
     static size_t configured = 0;
     if (smem > configured) {
