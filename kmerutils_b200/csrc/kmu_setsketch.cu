@@ -225,9 +225,17 @@ __global__ void __launch_bounds__(1024, 1) ssk_team_kernel(const SskParams P) {
                 V key = 0;
                 if (p < pend) {
                     key = finalize_key<V>(tk.get(t, canonical), header, P.hash_kind);
-                    Xoshiro256pp rng;
-                    rng.seed(nohash_seed(key));
-                    surv = !(__dmul_rn(P.C.inva_m0, exp1_sample(rng, zt)) > xcut);
+                    // the first draw from half a seeding (s0 and s3 of Xoshiro256++, as in ssk_whole_warp_kernel); an item
+                    // whose ziggurat draw is not accepted at once is queued like a survivor
+                    const uint64_t sd = nohash_seed(key);
+                    uint64_t x0 = sd, x3 = sd + 3ULL * 0x9E3779B97F4A7C15ULL;
+                    const uint64_t s0 = Xoshiro256pp::splitmix(x0), s3 = Xoshiro256pp::splitmix(x3);
+                    const uint64_t bits = rotl64(s0 + s3, 23) + s0;
+                    const uint32_t zi = (uint32_t)bits & 0xffu;
+                    const double e0 = __dmul_rn(__dsub_rn(__longlong_as_double((long long)((bits >> 12) | 0x3FF0000000000000ULL)),
+                                                          1.0 - 2.220446049250313e-16 / 2.0),
+                                                zx[zi]);
+                    surv = !(e0 < zx[zi + 1] && __dmul_rn(P.C.inva_m0, e0) > xcut);
                 }
                 const uint32_t bal = __ballot_sync(0xFFFFFFFFu, surv);
                 if (surv) wq[qn + __popc(bal & ((1u << team.lane) - 1u))] = key;
