@@ -85,11 +85,14 @@ static int32_t smh_per_sequence_device(kmu_ctx* ctx, const kmu_seqbatch* b, uint
         }
         P.memo = ctx->smh_memo.p;
     }
+    // the warps' key queues of the value-cut path follow the teams in shared memory, when there is room
+    const size_t smh_queue = team_bytes + kmu::SMH_QUEUE_BYTES <= SMEM_BUDGET ? kmu::SMH_QUEUE_BYTES : 0;
+    P.value_cut = smh_queue ? 1u : 0u;
     // merge neighbouring octave classes that get the same team geometry: one launch each
     struct Launch { uint64_t first, count; TeamGeometry g; };
     std::vector<Launch> ls;
     for (const OctaveClass& c : classes) {
-        TeamGeometry g = team_geometry(c.nk_max, team_bytes);
+        TeamGeometry g = team_geometry(c.nk_max, team_bytes, smh_queue);
         if (!ls.empty() && ls.back().g.team_warps == g.team_warps && ls.back().g.teams_per_cta == g.teams_per_cta &&
             ls.back().first + ls.back().count == c.first) {
             ls.back().count += c.count;

@@ -156,6 +156,7 @@ cudaError_t launch_pmh3a_items_finish(const Slot* slots, uint32_t m, bool key64,
                                       cudaStream_t st);
 
 // ---- SuperMinHash (kmu_smh.cu) ----------------------------------------------------------------
+constexpr size_t SMH_QUEUE_BYTES = 32 * 64 * 8;
 struct SmhParams {
     const uint8_t* packed;
     const uint64_t* byte_off;
@@ -170,6 +171,7 @@ struct SmhParams {
     void* sig;       // nseq * m values of S
     uint32_t team_warps, team_smem_bytes;
     double ln_term;  // ln(1e4 m)
+    uint32_t value_cut;  // 1: the CTA's shared memory ends with one queue of 64 keys per warp (SMH_QUEUE_BYTES): long sequences use the value cut
     unsigned long long* slow_count;
     uint32_t* slow_list;
     uint8_t* scratch;  // exact path

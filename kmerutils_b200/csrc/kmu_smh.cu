@@ -152,6 +152,14 @@ __global__ void __launch_bounds__(1024, 1) smh_fast_kernel(const SmhParams P) {
             const uint32_t a1 = need >= (double)m ? m : (uint32_t)ceil(need);
             a_spec = (a1 < 1 ? 1 : a1) - 1;
         }
+        // value cut of the one-point path: with D >= nk / 4 distinct items every slot ends below 4 m ln(1e4 m) / nk except
+        // with probability ~1e-4 (1 when the sequence is too short for it to help)
+        S cut = (S)1;
+        bool bound_cut = false;
+        if (nk && P.value_cut) {
+            const double c = 4.0 * (double)m / (double)nk * P.ln_term;
+            if (c < 0.9) cut = (S)c;
+        }
         if (a_spec > SMH_FAST_MAX) {  // short sequence: exact path
             if (team.tid == 0) P.slow_list[atomicAdd(P.slow_count, 1ULL)] = seq;
             continue;
@@ -178,6 +186,58 @@ __global__ void __launch_bounds__(1024, 1) smh_fast_kernel(const SmhParams P) {
                     }
                 }
             }
+        } else if (a_spec == 0 && cut < (S)1) {
+            // Long sequence, one point per item, value = the FIRST output of the item's generator -- which needs only s0
+            // and s3 (SplitMix64 outputs 1 and 4 of the seed).  Every slot ends below `cut` (verified below, like the
+            // a_spec bound), so an item whose value is not below it is dropped after half a seeding; the others are
+            // queued per warp and finished 32 at a time with the full generator.
+            const uint32_t ntasks = (nk + 15) >> 4;
+            V* wq = (V*)(smem + (size_t)P.team_smem_bytes * (blockDim.x / team.size)) + (threadIdx.x >> 5) * 64;
+            uint32_t qn = 0;  // warp-uniform
+            for (uint32_t task0 = 0; task0 < ntasks; task0 += team.size) {  // the same trip count for every lane of a warp
+                const uint32_t task = task0 + team.tid;
+                TK tk;
+                uint32_t p = task << 4, pend = p;
+                if (task < ntasks) {
+                    tk.init(words, p, k);
+                    pend = min(p + 16, nk);
+                }
+#pragma unroll 1
+                for (uint32_t t = 0; t < 16; ++t, ++p) {
+                    bool alive = false;
+                    V key = 0;
+                    if (p < pend) {
+                        key = finalize_key<V>(tk.get(t, canonical), header, P.hash_kind);
+                        const uint64_t sd = item_seed<V>(key, P.hasher);
+                        uint64_t x0 = sd, x3 = sd + 3ULL * 0x9E3779B97F4A7C15ULL;
+                        const uint64_t s0 = Xoshiro256pp::splitmix(x0), s3 = Xoshiro256pp::splitmix(x3);
+                        const uint64_t r0 = rotl64(s0 + s3, 23) + s0;
+                        S r;
+                        if (sizeof(S) == 8) r = (S)(__longlong_as_double((long long)((r0 >> 12) | 0x3FF0000000000000ULL)) - 1.0);
+                        else r = (S)(__uint_as_float(((uint32_t)(r0 >> 32) >> 9) | 0x3F800000u) - 1.0f);
+                        alive = r < cut;
+                    }
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, alive);
+                    if (alive) wq[qn + __popc(bal & ((1u << team.lane) - 1u))] = key;
+                    qn += __popc(bal);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        qn -= 32;
+                        const V kq = wq[qn + team.lane];
+                        __syncwarp();
+                        Xoshiro256pp rng;
+                        rng.seed(item_seed<V>(kq, P.hasher));
+                        smh_item_points<S>(rng, m, 0, h);
+                    }
+                }
+            }
+            if ((uint32_t)team.lane < qn) {
+                Xoshiro256pp rng;
+                rng.seed(item_seed<V>(wq[team.lane], P.hasher));
+                smh_item_points<S>(rng, m, 0, h);
+            }
+            __syncwarp();
+            bound_cut = true;
         } else {
         const uint32_t ntasks = (nk + 15) >> 4;
         for (uint32_t task = team.tid; task < ntasks; task += team.size) {
@@ -196,7 +256,7 @@ __global__ void __launch_bounds__(1024, 1) smh_fast_kernel(const SmhParams P) {
         }
         team.sync();
         S* out = (S*)P.sig + (size_t)seq * m;
-        const S bound = (S)(a_spec + 1);
+        const S bound = bound_cut ? cut : (S)(a_spec + 1);
         bool bad = false;
         for (uint32_t j = team.tid; j < m; j += team.size) {
             const S v = F::value(h[j]);

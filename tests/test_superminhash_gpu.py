@@ -73,6 +73,25 @@ def test_superminhash_merge_is_min(engine, oracle):
     assert np.array_equal(per_seq.min(axis=0), whole)
 
 
+def test_superminhash_value_cut_paths(engine, oracle):
+    """Long sequences take the value cut (an item whose first value is not below 4 m ln(1e4 m) / nk is dropped after half
+    a seeding): random ones pass its verification, tandem repeats and half-repetitive reads (far fewer distinct k-mers than
+    the cut assumes) fail it and are redone on the exact path; f32 and f64, both key hashers."""
+    rng = np.random.default_rng(19)
+    unit = bytes(rng.choice(list(b"ACGT"), 53).astype(np.uint8))
+    rnd = bytes(rng.choice(list(b"ACGT"), 120000).astype(np.uint8))
+    seqs = [rnd, unit * 2000, rnd[:40000] + unit * 1000, rnd[:20000], (unit * 40 + rnd[:500]) * 30]
+    batch, _ = engine.batch_from_ascii(seqs)
+    packed, off, nb = batch.download()
+    packed = np.concatenate([packed, np.zeros(64, np.uint8)])
+    for k, ktype, m, dtype, hasher in [(21, kb.KMER64, 64, np.float64, kb.HASHER_NOHASH), (16, kb.KMER16B32, 100, np.float32, kb.HASHER_FNV),
+                                       (12, kb.KMER32, 37, np.float64, kb.HASHER_FNV)]:
+        got = engine.sketch_superminhash(batch, k, ktype, kb.HASH_CANON_INVHASH, m, hasher, dtype)
+        want = oracle.sketch_superminhash_batch(packed, off, nb, k, ktype, kb.HASH_CANON_INVHASH, m, hasher, dtype)
+        bad = np.nonzero((got.view(np.uint8).reshape(len(seqs), -1) != want.view(np.uint8).reshape(len(seqs), -1)).any(axis=1))[0]
+        assert len(bad) == 0, f"k={k}: sequences {bad} differ"
+
+
 def test_superminhash_bad_arguments(engine):
     b = engine.batch_synth(1, np.array([100], dtype=np.uint64))
     with pytest.raises(kb.KmuInvalid):
