@@ -229,6 +229,34 @@ int32_t kmu_sketch_superminhash_whole(kmu_ctx* ctx, const kmu_seqbatch* b, uint3
         const uint32_t a1 = need >= (double)m ? m : (uint32_t)std::ceil(need);
         a_spec = std::max<uint32_t>(a1, 1) - 1;
     }
+    // long DNA inputs: the value cut (an item whose value is not below 4 m ln(1e4 m) / n is dropped after half a seeding);
+    // exact iff every merged slot ends below the cut, which is checked here -- otherwise the general kernel below
+    if (!done && a_spec == 0 && !kmer_type_is_aa(kmer_type) && !std::getenv("KMU_SMH_NO_CUT") &&
+        align_up(row_bytes, 16) + 16 * 64 * (key64 ? 8 : 4) <= SMEM_BUDGET) {
+        double cut = 4.0 * (double)m / (double)total * std::log(1e4 * (double)m);
+        if (!f64) cut = (double)(float)cut;
+        if (cut < 0.9) {
+            kmu::SmhParams P{};
+            P.k = k;
+            P.kmer_type = kmer_type;
+            P.hash_kind = hash_kind;
+            P.m = m;
+            P.hasher = key_hasher;
+            kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
+            CUDA_TRY(kmu::launch_smh_whole_cut(P, key64, f64, v, b->packed_bytes, cut, d_row, ctx->sm_count, st));
+            ++launches;
+            std::vector<uint8_t> h(row_bytes);
+            CUDA_TRY(cudaMemcpyAsync(h.data(), d_row, row_bytes, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            done = true;
+            for (uint32_t j = 0; j < m && done; ++j)
+                done = (f64 ? ((const double*)h.data())[j] : (double)((const float*)h.data())[j]) < cut;
+            if (!done) {
+                CUDA_TRY(kmu::launch_smh_fill_large(d_row, m, f64, st));
+                ++launches;
+            }
+        }
+    }
     if (!done && a_spec <= 15) {
         kmu::SmhParams P{};
         P.k = k;

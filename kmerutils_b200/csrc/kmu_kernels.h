@@ -181,6 +181,8 @@ struct SmhParams {
 };
 cudaError_t launch_smh_memo(const SmhParams& P, bool f64, void* memo, uint32_t nkeys, cudaStream_t st);
 cudaError_t launch_smh_fast(const SmhParams& P, bool key64, bool f64, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t launch_smh_whole_cut(const SmhParams& P, bool key64, bool f64, const SeqView& b, uint64_t total_bytes, double cut,
+                                 void* gslots, int sm_count, cudaStream_t st);
 cudaError_t launch_smh_whole(const SmhParams& P, bool key64, bool f64, const SeqView& b, uint64_t total_bytes, uint32_t a_spec,
                              void* gslots, int grid, size_t smem, cudaStream_t st);
 cudaError_t launch_smh_fill_large(void* slots, uint32_t m, bool f64, cudaStream_t st);

@@ -377,6 +377,91 @@ __global__ void __launch_bounds__(512, 2) smh_whole_kernel(const SmhParams P, Se
         if (h[j] != F::large()) atomicMin(gslots + j, h[j]);
 }
 
+// DNA, long inputs (one point per item): warp-cooperative form of the whole-batch kernel with the value cut of
+// smh_fast_kernel -- the lanes take 32 consecutive positions of the warp's slice at a time, half a seeding gives an item's
+// value, an item not below `cut` is dropped there, the others are queued per warp and finished 32 at a time.  The host
+// verifies that every merged slot ends below the cut.
+constexpr uint32_t SMH_WHOLE_WARPS = 16;
+template <typename V, typename S>
+__global__ void __launch_bounds__(32 * SMH_WHOLE_WARPS, 2) smh_whole_warp_kernel(const SmhParams P, SeqView b, uint64_t total_bytes, S cut,
+                                                                                   typename FloatOps<S>::B* gslots) {
+    using F = FloatOps<S>;
+    using B = typename F::B;
+    extern __shared__ __align__(16) uint8_t smem[];
+    B* h = (B*)smem;
+    const uint32_t m = P.m;
+    V* wq = (V*)(smem + (((size_t)m * sizeof(B) + 15) & ~(size_t)15)) + (threadIdx.x >> 5) * 64;
+    for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) h[j] = F::large();
+    __syncthreads();
+    const V header = (V)word_header(P.kmer_type, P.k);
+    const bool canonical = hash_is_canonical(P.hash_kind);
+    const int lane = threadIdx.x & 31;
+    const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t qn = 0;  // warp-uniform
+    for (uint64_t g = warp; g < ngroups; g += nwarps)
+        warp_for_each_kmer<V>(b, total_bytes, g, P.k, canonical, lane, [&](V pk, bool active) {
+            const V key = finalize_key<V>(pk, header, P.hash_kind);
+            bool alive = false;
+            if (active) {
+                const uint64_t sd = item_seed<V>(key, P.hasher);
+                uint64_t x0 = sd, x3 = sd + 3ULL * 0x9E3779B97F4A7C15ULL;
+                const uint64_t s0 = Xoshiro256pp::splitmix(x0), s3 = Xoshiro256pp::splitmix(x3);
+                const uint64_t r0 = rotl64(s0 + s3, 23) + s0;
+                S r;
+                if (sizeof(S) == 8) r = (S)(__longlong_as_double((long long)((r0 >> 12) | 0x3FF0000000000000ULL)) - 1.0);
+                else r = (S)(__uint_as_float(((uint32_t)(r0 >> 32) >> 9) | 0x3F800000u) - 1.0f);
+                alive = r < cut;
+            }
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, alive);
+            if (alive) wq[qn + __popc(bal & ((1u << lane) - 1u))] = key;
+            qn += __popc(bal);
+            __syncwarp();
+            if (qn >= 32) {
+                qn -= 32;
+                const V kq = wq[qn + lane];
+                __syncwarp();
+                Xoshiro256pp rng;
+                rng.seed(item_seed<V>(kq, P.hasher));
+                smh_item_points<S>(rng, m, 0, h);
+            }
+        });
+    if ((uint32_t)lane < qn) {
+        Xoshiro256pp rng;
+        rng.seed(item_seed<V>(wq[lane], P.hasher));
+        smh_item_points<S>(rng, m, 0, h);
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < m; j += blockDim.x)
+        if (h[j] != F::large()) atomicMin(gslots + j, h[j]);
+}
+
+template <typename V, typename S>
+static cudaError_t launch_whole_cut_t(const SmhParams& P, const SeqView& b, uint64_t total_bytes, double cut, void* gslots, int sm_count,
+                                      cudaStream_t st) {
+    auto kern = smh_whole_warp_kernel<V, S>;
+    const size_t smem = (((size_t)P.m * sizeof(S) + 15) & ~(size_t)15) + SMH_WHOLE_WARPS * 64 * sizeof(V);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((ngroups + SMH_WHOLE_WARPS - 1) / SMH_WHOLE_WARPS, (uint64_t)sm_count * 2));
+    kern<<<grid, 32 * SMH_WHOLE_WARPS, smem, st>>>(P, b, total_bytes, (S)cut, (typename FloatOps<S>::B*)gslots);
+    return cudaGetLastError();
+}
+// DNA batches only; `cut` as the kernel will compare it (already rounded to S by the caller for the verification)
+cudaError_t launch_smh_whole_cut(const SmhParams& P, bool key64, bool f64, const SeqView& b, uint64_t total_bytes, double cut,
+                                 void* gslots, int sm_count, cudaStream_t st) {
+    if (key64) return f64 ? launch_whole_cut_t<uint64_t, double>(P, b, total_bytes, cut, gslots, sm_count, st)
+                          : launch_whole_cut_t<uint64_t, float>(P, b, total_bytes, cut, gslots, sm_count, st);
+    return f64 ? launch_whole_cut_t<uint32_t, double>(P, b, total_bytes, cut, gslots, sm_count, st)
+               : launch_whole_cut_t<uint32_t, float>(P, b, total_bytes, cut, gslots, sm_count, st);
+}
+
 template <typename B>
 __global__ void smh_fill_kernel(B* slots, uint32_t m, B v) {
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) slots[j] = v;

@@ -129,6 +129,12 @@ def main():
     cb = eng.batch_synth(5, cnb)
     ms = timed(eng, lambda: eng.sketch_setsketch(cb, 21, kb.KMER64, kb.HASH_CANON_INVHASH, None, np.uint16, whole=True), 2)
     line("setsketch whole-file k=21 m=4096 (1 Gbase)", int(cnb.sum()), ms, 0.25)
+    ms = timed(eng, lambda: eng.sketch_superminhash_whole(cb, 21, kb.KMER64, kb.HASH_CANON_INVHASH, 4096), 2)
+    line("superminhash whole-file k=21 m=4096 f64 (1 Gbase)", int(cnb.sum()), ms, 0.25)
+    os.environ["KMU_SMH_NO_CUT"] = "1"
+    ms = timed(eng, lambda: eng.sketch_superminhash_whole(cb, 21, kb.KMER64, kb.HASH_CANON_INVHASH, 4096), 2)
+    del os.environ["KMU_SMH_NO_CUT"]
+    line("superminhash whole-file k=21 m=4096 f64 (1 Gbase), per-thread-chunk kernel without the value cut", int(cnb.sum()), ms, 0.25)
     cb.destroy()
     # ---- C5b: proteome, AA k = 12, ProbMinHash3a m = 400 ----
     rng = np.random.default_rng(5)
