@@ -267,9 +267,13 @@ __global__ void __launch_bounds__(128) nthash_warp_kernel(SeqView b, uint64_t to
     extern __shared__ __align__(16) uint8_t nt_smem[];
     // per-launch tables: the seeds, their complements, and the recurrence's two XOR terms for every (outgoing base,
     // incoming base) pair:  f' = rotl(f, 1) ^ FD[out][in],  r' = rotl(r, 63) ^ RD[out][in]
-    __shared__ uint64_t SEED[4], SEEDC[4], FD[16], RD[16];
+    __shared__ uint64_t SEED[4], SEEDC[4], FD[16], RD[16], F2[16], R2[16];
     if (threadIdx.x < 16) {
         const uint32_t ob = threadIdx.x >> 2, nb = threadIdx.x & 3;
+        // initialisation two bases at a time: F2[(x << 2) | y] for consecutive bases x, y (forward strand, x first),
+        // R2[(b << 2) | a] for the reverse strand taken from the last base backwards (a first)
+        F2[threadIdx.x] = rotl_var(nt_seed(ob), 1) ^ nt_seed(nb);
+        R2[threadIdx.x] = rotl_var(nt_seed(3u - nb), 1) ^ nt_seed(3u - ob);
         FD[threadIdx.x] = rotl_var(nt_seed(ob), k) ^ nt_seed(nb);
         RD[threadIdx.x] = rotl_var(nt_seed(3u - ob), 63) ^ rotl_var(nt_seed(3u - nb), k - 1);
         if (threadIdx.x < 4) {
@@ -302,28 +306,44 @@ __global__ void __launch_bounds__(128) nthash_warp_kernel(SeqView b, uint64_t to
                 const uint64_t p0 = t0 + (uint64_t)lane * NT_RUN;
                 if (p0 < p_hi) {
                     const uint32_t n = (uint32_t)min((uint64_t)NT_RUN, p_hi - p0);
-                    KmerWalker<uint64_t> wk;
-                    wk.start(words, p0, k);
-                    wk.roll();
+                    // the run needs its first k-mer and, per step, the outgoing base (position p0 + j) and the incoming one
+                    // (position p0 + j + k): two 64-bit windows of 32 bases, read once -- no rolling k-mer value
+                    const uint32_t* wo = words + (p0 >> 4);
+                    const uint32_t sho = (uint32_t)(p0 & 15) * 2;
+                    const uint32_t o0 = be32(__ldg(wo)), o1 = be32(__ldg(wo + 1)), o2 = be32(__ldg(wo + 2));
+                    const uint64_t OUT = ((uint64_t)__funnelshift_l(o1, o0, sho) << 32) | __funnelshift_l(o2, o1, sho);
+                    const uint64_t q0 = p0 + k;
+                    const uint32_t* wi = words + (q0 >> 4);
+                    const uint32_t shi = (uint32_t)(q0 & 15) * 2;
+                    const uint32_t i0 = be32(__ldg(wi)), i1 = be32(__ldg(wi + 1)), i2 = be32(__ldg(wi + 2));
+                    const uint64_t IN = ((uint64_t)__funnelshift_l(i1, i0, shi) << 32) | __funnelshift_l(i2, i1, shi);
+                    const uint64_t kv = OUT >> (64 - 2 * k);  // the k-mer at p0
                     // nthash_canonical_init (kmer.rs:74-94), Horner form: f = XOR_i rotl(seed[b_i], k-1-i),
                     // r = XOR_i rotl(seed[3 - b_i], i)
                     uint64_t f = 0, r = 0;
-                    for (uint32_t i = 0; i < k; ++i) {
-                        f = ((f << 1) | (f >> 63)) ^ SEED[(uint32_t)(wk.fwd >> (2 * (k - 1 - i))) & 3u];
-                        r = ((r << 1) | (r >> 63)) ^ SEEDC[(uint32_t)(wk.fwd >> (2 * i)) & 3u];
+                    uint32_t i = 0;
+                    if (k & 1) {  // odd k: the first base of each direction alone, then pairs
+                        f = SEED[(uint32_t)(kv >> (2 * (k - 1))) & 3u];
+                        r = SEEDC[(uint32_t)kv & 3u];
+                        i = 1;
+                    }
+                    for (; i < k; i += 2) {
+                        f = ((f << 2) | (f >> 62)) ^ F2[(uint32_t)(kv >> (2 * (k - 2 - i))) & 15u];
+                        r = ((r << 2) | (r >> 62)) ^ R2[(uint32_t)(kv >> (2 * i)) & 15u];
                     }
                     uint64_t* th = tile_h + lane * NT_PITCH;
                     uint8_t* ts = tile_s + lane * NT_PITCH;
-                    for (uint32_t j = 0;;) {
-                        th[j] = f <= r ? f : r;
-                        ts[j] = f <= r ? 0 : 1;
-                        if (++j >= n) break;
-                        // ntHash recurrence: identical values to re-initialising on the new window
-                        const uint32_t old_base = (uint32_t)(wk.fwd >> (2 * k - 2)) & 3u;
-                        wk.roll();
-                        const uint32_t nb = (uint32_t)wk.fwd & 3u;
-                        f = ((f << 1) | (f >> 63)) ^ FD[old_base * 4 + nb];
-                        r = ((r >> 1) | (r << 63)) ^ RD[old_base * 4 + nb];
+                    static_assert(NT_RUN == 32, "one 64-bit window per run");
+#pragma unroll
+                    for (uint32_t j = 0; j < NT_RUN; ++j) {
+                        if (j < n) {
+                            th[j] = f <= r ? f : r;
+                            ts[j] = f <= r ? 0 : 1;
+                            // ntHash recurrence: identical values to re-initialising on the new window
+                            const uint32_t t = ((uint32_t)(OUT >> (62 - 2 * j)) & 3u) * 4 + ((uint32_t)(IN >> (62 - 2 * j)) & 3u);
+                            f = ((f << 1) | (f >> 63)) ^ FD[t];
+                            r = ((r >> 1) | (r << 63)) ^ RD[t];
+                        }
                     }
                 }
                 __syncwarp();
