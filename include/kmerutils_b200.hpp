@@ -38,6 +38,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "kmerutils_b200.h"
@@ -574,6 +575,78 @@ std::vector<double> jaccard_index_probminhash3a(const Sequence& seqa, const std:
               "jaccard_index_probminhash3a");
     return j;
 }
+
+/// BlockSketched / BlockSketchedSeq / BlockSeqSketcher / DistBlockSketched (src/sketching/seqblocksketch.rs:36-167, 419-440):
+/// every sequence is cut into runs of block_size consecutive k-mers (Kmer32bit), one ProbMinHash3a signature per block.
+/// The number of blocks comes from the BASES (ceil(size / block_size)), so trailing blocks may hold no k-mer at all.
+struct BlockSketched {
+    uint32_t numseq = 0, numblock = 0;
+    std::vector<uint32_t> sketch;
+    const std::vector<uint32_t>& get_skech_slice() const { return sketch; }
+};
+struct BlockSketchedSeq {
+    size_t numseq = 0;
+    std::vector<std::vector<BlockSketched>> sketch;  // one vector of length 1 per block, as the reference keeps them for hnsw_rs
+};
+class BlockSeqSketcher {
+  public:
+    BlockSeqSketcher(size_t block_size, size_t kmer_size, size_t sketch_size) : block_size_(block_size), kmer_size_(kmer_size), sketch_size_(sketch_size) {}
+    /// a pack of (numseq, sequence): all blocks of all sequences in one upload and one sketch call
+    std::vector<BlockSketchedSeq> blocksketch_sequences(const std::vector<std::pair<uint32_t, const Sequence*>>& pack_seq, KmerHash fhash) const {
+        std::vector<const Sequence*> vseq;
+        std::vector<uint64_t> idx, begin, end;
+        std::vector<size_t> nblocks;
+        for (size_t s = 0; s < pack_seq.size(); ++s) {
+            const Sequence* seq = pack_seq[s].second;
+            if (seq->size() == 0) throw Panic(KMU_EINVAL, "assertion failed: seq.size() > 0");  // seqblocksketch.rs:108
+            vseq.push_back(seq);
+            const size_t nb = (seq->size() + block_size_ - 1) / block_size_;
+            nblocks.push_back(nb);
+            for (size_t b = 0; b < nb; ++b) {
+                idx.push_back(s);
+                begin.push_back(b * block_size_);
+                end.push_back(b * block_size_ + block_size_ + kmer_size_ - 1);  // block_size k-mers: clamped to the sequence
+            }
+        }
+        DeviceBatch whole(vseq);
+        kmu_seqbatch* blocks = nullptr;
+        check(kmu_seqbatch_slices(Context::global().get(), whole.get(), idx.data(), begin.data(), end.data(), idx.size(), &blocks),
+              "BlockSeqSketcher");
+        std::vector<uint32_t> flat(idx.size() * sketch_size_);
+        const int32_t rc = kmu_sketch_pmh3a(Context::global().get(), blocks, (uint32_t)kmer_size_, KMU_KMER32, fhash.kind,
+                                            (uint32_t)sketch_size_, flat.data(), 0);
+        kmu_seqbatch_destroy(blocks);
+        check(rc, "BlockSeqSketcher");
+        std::vector<BlockSketchedSeq> out(pack_seq.size());
+        size_t row = 0;
+        for (size_t s = 0; s < pack_seq.size(); ++s) {
+            out[s].numseq = pack_seq[s].first;
+            for (size_t b = 0; b < nblocks[s]; ++b, ++row) {
+                BlockSketched bs;
+                bs.numseq = pack_seq[s].first;
+                bs.numblock = (uint32_t)b;
+                bs.sketch.assign(flat.begin() + row * sketch_size_, flat.begin() + (row + 1) * sketch_size_);
+                out[s].sketch.push_back({std::move(bs)});
+            }
+        }
+        return out;
+    }
+    BlockSketchedSeq blocksketch_sequence(size_t numseq, const Sequence& seq, KmerHash fhash) const {
+        return blocksketch_sequences({{(uint32_t)numseq, &seq}}, fhash)[0];
+    }
+
+  private:
+    size_t block_size_, kmer_size_, sketch_size_;
+};
+/// 1 inside a sequence (reads are to be paired across sequences), else the fraction of differing slots (:419-433)
+struct DistBlockSketched {
+    float eval(const std::vector<BlockSketched>& va, const std::vector<BlockSketched>& vb) const {
+        if (va.size() != 1 || vb.size() != 1) throw Panic(KMU_EINVAL, "assertion failed: va.len() == 1 && vb.len() == 1");
+        if (va[0].numseq == vb[0].numseq) return 1.f;
+        if (va[0].sketch.size() != vb[0].sketch.size()) throw Panic(KMU_EINVAL, "assertion failed: va.len() == vb.len()");
+        return (float)(1.0 - compute_probminhash_jaccard(va[0].sketch, vb[0].sketch));
+    }
+};
 
 /// SeqSketcherT (src/sketching/setsketchert.rs:54-79): sketch_compressedkmer = one signature per sequence,
 /// sketch_compressedkmer_seqs = ONE signature for the whole vector (a genome in several contigs)

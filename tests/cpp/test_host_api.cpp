@@ -10,6 +10,7 @@
 //   src/sketching/seqsketchjaccard.rs:742-791   test_pminhasha_kmer_smallb
 //   src/sketching/seqsketchjaccard.rs:947-1004  test_superminhash_kmer_16b32bit_serial
 //   src/sketching/seqsketchjaccard.rs:1015-...  test_reload_sketch_file
+//   src/sketching/seqblocksketch.rs:458-496     test_block_32bit_sketch
 //   src/aautils/kmeraa.rs:920-1021              test_seqaa_32bit_iterator_range, test_seqaa_iterator_end
 //   src/aautils/setsketchert.rs:1218-1266       test_seqaa_probminhash_64bit
 #include <cmath>
@@ -292,6 +293,33 @@ static void test_reload_sketch_file(const std::string& dir) {
     EXPECT(n == sigs.size());
 }
 
+static void test_block_32bit_sketch() {
+    // seqblocksketch.rs:458-496
+    Sequence seqa(std::string("TCAAAGGGAAACATTCAAAATCAGTATGCGCCCGTTCAGTTACGTATTGCTCTCGCCGTAGGCCTAATGAGATGGGCTGGGTACAGAG"), 2);
+    Sequence seqb(std::string("TCAAAGGGAAATTTTTTTCATTCAAAATCAGTATGCGCCCGTTCAGTTACGTATTGCTCTCGCCGTAGGCCTAATGATTTTTTTGATGGGCTGGGTACAGAG"), 2);
+    const size_t block_size = 10, kmer_size = 3, sketch_size = 6;
+    BlockSeqSketcher sketcher(block_size, kmer_size, sketch_size);
+    const BlockSketchedSeq sketcha = sketcher.blocksketch_sequence(1, seqa, KmerHash::canonical_invhash());
+    const BlockSketchedSeq sketchb = sketcher.blocksketch_sequence(2, seqb, KmerHash::canonical_invhash());
+    EXPECT(sketcha.sketch.size() == (seqa.size() + 9) / 10 && sketchb.sketch.size() == (seqb.size() + 9) / 10);
+    DistBlockSketched mydist;
+    EXPECT(mydist.eval(sketcha.sketch[0], sketcha.sketch[0]) == 1.f);  // same sequence: 1 (:487)
+    const float dist_1 = mydist.eval(sketcha.sketch[0], sketchb.sketch[0]);  // the reference prints these two
+    const float dist_2 = mydist.eval(sketcha.sketch[1], sketchb.sketch[1]);
+    EXPECT(dist_1 >= 0.f && dist_1 <= 1.f && dist_2 >= 0.f && dist_2 <= 1.f);
+    // blocks 3 and 4 of seqa (bases 30..49) are blocks 4 and 5 of seqb shifted by the 7 inserted T's: not aligned, so no
+    // equality is expected there; the last full blocks before the first insertion agree only up to position 9's k-mer
+    // every block against the oracle (blocks of block_size k-mers; the oracle takes the packed sequence)
+    std::vector<uint32_t> want(sketcha.sketch.size() * sketch_size);
+    const uint64_t nb = orc_blocksketch_seq(seqa.packed().data(), seqa.size(), (int)kmer_size, (uint32_t)sketch_size, block_size, want.data(),
+                                            sketcha.sketch.size());
+    EXPECT(nb == sketcha.sketch.size());
+    for (size_t b = 0; b < sketcha.sketch.size() && b < nb; ++b) {
+        EXPECT(sketcha.sketch[b].size() == 1 && sketcha.sketch[b][0].numblock == b && sketcha.sketch[b][0].numseq == 1);
+        EXPECT(std::vector<uint32_t>(want.begin() + b * sketch_size, want.begin() + (b + 1) * sketch_size) == sketcha.sketch[b][0].get_skech_slice());
+    }
+}
+
 static void test_amino_acids() {
     using namespace kmerutils::aautils;
     const std::string prot =
@@ -367,6 +395,7 @@ int main(int argc, char** argv) {
         test_superminhash_and_hll();
         test_reload_sketch_file(dir);
         test_amino_acids();
+        test_block_32bit_sketch();
     } catch (const std::exception& e) {
         std::fprintf(stderr, "exception: %s\n", e.what());
         return 2;
