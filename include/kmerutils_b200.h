@@ -52,6 +52,7 @@ extern "C" {
 
 typedef struct kmu_ctx kmu_ctx;
 typedef struct kmu_seqbatch kmu_seqbatch;
+typedef struct kmu_counter kmu_counter;
 
 /* ---- context ------------------------------------------------------------------ */
 int32_t kmu_ctx_create(int32_t device, kmu_ctx** ctx);
@@ -191,6 +192,24 @@ int32_t kmu_count_partition_counts(kmu_ctx* ctx, const kmu_seqbatch* batch, uint
                                    int32_t canonical, uint32_t nparts, uint64_t* part_counts);
 int32_t kmu_count_partition_scatter(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, int32_t kmer_type,
                                     int32_t canonical, uint32_t nparts, void* const* dests, const uint64_t* dest_offsets);
+/* Fused exchange, one walk (replaces the one-producer / N-consumer hand-off of count_kmer_threaded_one_to_many,
+ * kmercount.rs:881-974, owner = DispatchableT::dispatch :382-420): ONE kernel extracts the canonical k-mers of the batch,
+ * buckets them by (owner, region of the owner's table) and appends every bucket to its slab inside the owner's receive
+ * buffer -- dests[o], local memory for o == self, a peer GPU's buffer opened with kmu_ipc_open otherwise: the stores
+ * cross NVLink from inside the kernel.  Every rank creates its counter with the same arguments (same capacity); a
+ * receive buffer holds nregions * nowners slabs of slab_cap keys, slab (r, s) = what sender s found for region r.
+ *   kmu_count_exchange_geometry : nregions for this table and this number of owners;
+ *   kmu_count_exchange_scatter  : the kernel; sent_counts[o * nregions + r] = keys this rank appended for (o, r);
+ *                                 *overflowed != 0 when a slab was too small (nothing may be inserted from this round);
+ *   kmu_count_insert_slabs      : after the ranks have shared their sent_counts (and a barrier), each rank inserts its
+ *                                 buffer region after region -- the updates of a region hit L2;
+ *                                 counts[s * nregions + r] = sender s's sent_counts[self * nregions + r]. */
+int32_t kmu_count_exchange_geometry(const kmu_counter* counter, uint32_t nowners, uint32_t* nregions);
+int32_t kmu_count_exchange_scatter(kmu_ctx* ctx, const kmu_seqbatch* batch, const kmu_counter* counter, int32_t canonical,
+                                   uint32_t nowners, uint32_t self, uint64_t slab_cap, void* const* dests,
+                                   uint64_t* sent_counts, int32_t* overflowed);
+int32_t kmu_count_insert_slabs(kmu_ctx* ctx, kmu_counter* counter, const void* slabs, uint64_t slab_cap, uint32_t nsend,
+                               const uint64_t* counts);
 int32_t kmu_ipc_alloc(kmu_ctx* ctx, uint64_t bytes, void** dev_ptr, uint8_t handle[64]);
 int32_t kmu_ipc_free(kmu_ctx* ctx, void* dev_ptr);
 int32_t kmu_ipc_open(kmu_ctx* ctx, const uint8_t handle[64], void** peer_ptr);
@@ -250,7 +269,6 @@ int32_t kmu_sketch_superminhash_whole(kmu_ctx* ctx, const kmu_seqbatch* batch, u
  * exactly once (KmerCountT, kmercount.rs:48-59).  `capacity` is the number of distinct k-mers
  * the table must hold (KmerCounter::new(fpr, capacity, nb_bits), :88-98); inserting more fails
  * with KMU_EOVERFLOW instead of degrading. */
-typedef struct kmu_counter kmu_counter;
 int32_t kmu_count_create(kmu_ctx* ctx, uint32_t k, int32_t kmer_type, uint32_t count_bits, uint64_t capacity,
                          kmu_counter** counter);
 void kmu_count_destroy(kmu_counter* counter);

@@ -15,6 +15,9 @@
 //  base::sequence::Sequence          src/base/sequence.rs:14-106          kmerutils::base::Sequence
 //  base::kmertraits::{KmerT,CompressedKmerT,KmerBuilder} kmertraits.rs    the three k-mer structs below
 //  base::kmergenerator::KmerGenerator src/base/kmergenerator.rs:148-186   kmerutils::base::KmerGenerator<T>
+//  base::kmergenerator::KmerSeqIterator src/base/kmergenerator.rs:30-107  kmerutils::base::KmerSeqIterator<T> (streams from the GPU)
+//  base::nthash::NtHash              src/base/nthash.rs:76-120, kmer.rs:45-145  methods of Kmer32bit / Kmer16b32bit
+//  base::kmercount::DispatchableT    src/base/kmercount.rs:382-420        dispatch() of the three k-mer types
 //  base::kmercount::{KmerCountT,KmerCounter,KmerCounterPool,
 //        count_kmer_threaded_one_to_many} src/base/kmercount.rs:48-98,881 kmerutils::base::KmerCounter<T> ...
 //  sketching::seqsketchjaccard::SeqSketcher  seqsketchjaccard.rs:117-414  kmerutils::sketching::SeqSketcher
@@ -38,6 +41,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -104,8 +108,108 @@ inline uint32_t bitrev32(uint32_t v) {
 }
 inline uint64_t bitrev64(uint64_t v) { return ((uint64_t)bitrev32((uint32_t)v) << 32) | bitrev32((uint32_t)(v >> 32)); }
 
+/// probminhash::invhash::int32_hash / int64_hash (Thomas Wang's invertible mixes), used by DispatchableT::dispatch
+inline uint32_t int32_hash(uint32_t key) {
+    key += ~(key << 15);
+    key ^= (key >> 10);
+    key += (key << 3);
+    key ^= (key >> 6);
+    key += ~(key << 11);
+    key ^= (key >> 16);
+    return key;
+}
+inline uint64_t int64_hash(uint64_t key) {
+    key = (~key) + (key << 21);
+    key = key ^ (key >> 24);
+    key = (key + (key << 3)) + (key << 8);
+    key = key ^ (key >> 14);
+    key = (key + (key << 2)) + (key << 4);
+    key = key ^ (key >> 28);
+    key = key + (key << 31);
+    return key;
+}
+
+/// ntHash on 2-bit k-mers: seeds and multi-hash expansion (src/base/nthash.rs:10-30, 63-72)
+namespace nthash {
+constexpr uint64_t MULTISEED = 0x90b45d39fb6da1faull;
+constexpr unsigned MULTISHIFT = 27;
+// BASE_MAPPING_2B: A C G T, then the complements T G C A (offset OFFSET_COMP_2B = 4)
+constexpr uint64_t BASE_MAPPING_2B[8] = {0x3c8bfbb395c60474ull, 0x3193c18562a02b4cull, 0x20323ed082572324ull, 0x295549f54be24456ull,
+                                         0x295549f54be24456ull, 0x20323ed082572324ull, 0x3193c18562a02b4cull, 0x3c8bfbb395c60474ull};
+inline uint64_t rotl(uint64_t x, unsigned r) { return (r &= 63) ? (x << r) | (x >> (64 - r)) : x; }
+inline uint64_t rotr(uint64_t x, unsigned r) { return (r &= 63) ? (x >> r) | (x << (64 - r)) : x; }
+/// from_one_hash_val_to_mult_hash (nthash.rs:63-72; release builds wrap on overflow)
+inline void from_one_hash_val_to_mult_hash(uint64_t ksize, std::vector<uint64_t>& hashed) {
+    for (size_t i = 1; i < hashed.size(); ++i) {
+        uint64_t t = hashed[0] * ((uint64_t)i ^ (ksize * MULTISEED));
+        t ^= t >> MULTISHIFT;
+        hashed[i] = t;
+    }
+}
+}  // namespace nthash
+
+/// The NtHash trait (src/base/nthash.rs:76-120) as the macro implement_nthash_for! writes it for the two u32 k-mer types
+/// (src/base/kmer.rs:45-145), bug for bug: the *_cycle methods call `self.push(new_base)` and drop the result, so `self`
+/// never advances (:69, :109), and nthash_canonical_cycle zeroes fhash / rhash before rolling (:97-98).  Only the *_init
+/// methods are meaningful; the batch form on the GPU (kmu_nthash_canonical) is defined against them.
+template <typename Derived>
+struct NtHashMethods {
+    uint64_t nthash_init() const {
+        uint64_t f = 0, r = 0;
+        init(f, r);
+        return f;
+    }
+    uint64_t nthash_cycle(uint64_t hashval, uint8_t new_base) {
+        const uint32_t ksize = self().get_nb_base();
+        return nthash::rotl(hashval, 1) ^ nthash::rotl(nthash::BASE_MAPPING_2B[old_base()], ksize) ^ nthash::BASE_MAPPING_2B[new_base & 3];
+    }
+    std::pair<uint64_t, uint8_t> nthash_canonical_init(uint64_t& fhash, uint64_t& rhash) const {
+        init(fhash, rhash);
+        return fhash <= rhash ? std::make_pair(fhash, (uint8_t)0) : std::make_pair(rhash, (uint8_t)1);
+    }
+    std::pair<uint64_t, uint8_t> nthash_canonical_cycle(uint8_t new_base, uint64_t& fhash, uint64_t& rhash) {
+        fhash = 0;
+        rhash = 0;
+        const uint32_t ksize = self().get_nb_base();
+        const uint8_t ob = old_base();
+        fhash = nthash::rotl(fhash, 1) ^ nthash::rotl(nthash::BASE_MAPPING_2B[ob], ksize) ^ nthash::BASE_MAPPING_2B[new_base & 3];
+        rhash = nthash::rotr(rhash, 1) ^ nthash::rotl(nthash::BASE_MAPPING_2B[4 + ob], ksize) ^
+                nthash::rotl(nthash::BASE_MAPPING_2B[4 + (new_base & 3)], ksize - 1);
+        return fhash <= rhash ? std::make_pair(fhash, (uint8_t)0) : std::make_pair(rhash, (uint8_t)1);
+    }
+    uint8_t nthash_mult_canonical_init(uint64_t& fhash, uint64_t& rhash, std::vector<uint64_t>& hashed) const {
+        const auto res = nthash_canonical_init(fhash, rhash);
+        hashed[0] = res.first;
+        nthash::from_one_hash_val_to_mult_hash(self().get_nb_base(), hashed);
+        return res.second;
+    }
+    uint8_t nthash_mult_canonical_cycle(uint8_t new_base, uint64_t& fhash, uint64_t& rhash, std::vector<uint64_t>& hashed) {
+        const auto res = nthash_canonical_cycle(new_base, fhash, rhash);
+        hashed[0] = res.first;
+        nthash::from_one_hash_val_to_mult_hash(self().get_nb_base(), hashed);
+        return res.second;
+    }
+
+  private:
+    const Derived& self() const { return *static_cast<const Derived*>(this); }
+    uint8_t old_base() const {  // leftmost base of the k-mer
+        const uint32_t k = self().get_nb_base();
+        return (uint8_t)((self().v >> (2 * (k - 1))) & 3u);
+    }
+    void init(uint64_t& fhash, uint64_t& rhash) const {
+        fhash = 0;
+        rhash = 0;
+        const uint32_t k = self().get_nb_base();
+        for (uint32_t i = 0; i < k; ++i) {
+            const uint32_t base = (self().v >> (2 * (k - 1 - i))) & 3u;
+            fhash ^= nthash::rotl(nthash::BASE_MAPPING_2B[base], k - i - 1);
+            rhash ^= nthash::rotl(nthash::BASE_MAPPING_2B[4 + base], i);
+        }
+    }
+};
+
 /// Kmer32bit (src/base/kmer32bit.rs:22): up to 14 bases, the number of bases in the top 4 bits
-struct Kmer32bit {
+struct Kmer32bit : NtHashMethods<Kmer32bit> {
     using Val = uint32_t;
     static constexpr int32_t kmu_type = KMU_KMER32;
     uint32_t v = 0;  // the reference's `.0`
@@ -126,8 +230,11 @@ struct Kmer32bit {
     }
     static size_t get_nb_base_max() { return 14; }
     uint8_t get_nb_base() const { return (uint8_t)(v >> 28); }
-    Val get_compressed_value() const { return v; }
+    /// the value field without the length header (kmer32bit.rs:173-178)
+    Val get_compressed_value() const { return v & 0x0FFFFFFFu; }
     size_t get_bitsize() const { return 32; }
+    /// DispatchableT::dispatch (kmercount.rs:399-408)
+    size_t dispatch(size_t nb_receiver) const { return int32_hash(get_compressed_value()) % (uint32_t)nb_receiver; }
     Kmer32bit push(uint8_t b) const {
         const uint32_t mask = (1u << (2 * get_nb_base())) - 1;
         Kmer32bit r;
@@ -157,7 +264,7 @@ struct Kmer32bit {
 };
 
 /// Kmer16b32bit (src/base/kmer16b32bit.rs:21): exactly 16 bases in a u32
-struct Kmer16b32bit {
+struct Kmer16b32bit : NtHashMethods<Kmer16b32bit> {
     using Val = uint32_t;
     static constexpr int32_t kmu_type = KMU_KMER16B32;
     uint32_t v = 0;
@@ -174,6 +281,8 @@ struct Kmer16b32bit {
     uint8_t get_nb_base() const { return 16; }
     Val get_compressed_value() const { return v; }
     size_t get_bitsize() const { return 32; }
+    /// DispatchableT::dispatch (kmercount.rs:388-397)
+    size_t dispatch(size_t nb_receiver) const { return int32_hash(v) % (uint32_t)nb_receiver; }
     Kmer16b32bit push(uint8_t b) const { return from_word((v << 2) | (b & 3u), 16); }
     Kmer16b32bit reverse_complement() const { return from_word(swap_pairs32(bitrev32(~v)), 16); }
     std::vector<uint8_t> get_uncompressed_kmer() const {
@@ -203,6 +312,8 @@ struct Kmer64bit {
     uint8_t get_nb_base() const { return nb_base; }
     Val get_compressed_value() const { return v; }
     size_t get_bitsize() const { return 64; }
+    /// DispatchableT::dispatch (kmercount.rs:410-419)
+    size_t dispatch(size_t nb_receiver) const { return (size_t)(int64_hash(v) % (uint64_t)nb_receiver); }
     Kmer64bit push(uint8_t b) const {
         const uint64_t mask = nb_base >= 32 ? ~0ull : ((1ull << (2 * nb_base)) - 1);
         return from_word(((v << 2) & mask) | (b & 3u), nb_base);
@@ -322,6 +433,74 @@ inline std::vector<const Sequence*> as_refs(const std::vector<Sequence>& v) {
     return r;
 }
 
+// ---------------------------------------------------------------- KmerSeqIterator
+/// hash functor so that the k-mer value types key std::unordered_map (the reference derives Hash on them)
+struct KmerStdHash {
+    template <typename K>
+    size_t operator()(const K& k) const {
+        return (size_t)int64_hash((uint64_t)k.v ^ ((uint64_t)k.get_nb_base() << 58));
+    }
+};
+/// FnvHashMap<T, u32> of generate_kmer_distribution
+template <typename T>
+using KmerDistribution = std::unordered_map<T, uint32_t, KmerStdHash>;
+
+/// hashmap_count_to_vec_count (kmergenerator.rs:189-203)
+template <typename T>
+std::vector<std::pair<T, uint32_t>> hashmap_count_to_vec_count(const KmerDistribution<T>& kmer_distribution) {
+    return std::vector<std::pair<T, uint32_t>>(kmer_distribution.begin(), kmer_distribution.end());
+}
+
+/// KmerSeqIterator<T> (src/base/kmergenerator.rs:30-107): `new(ksize, &sequence)`, `set_range(begin, end)`, `next()`.
+/// The sequence is uploaded once; next() hands out k-mers from a window of FETCH k-mers generated on the GPU
+/// (kmu_seqbatch_slices + kmu_generate_kmers), refilled when it runs dry -- a streaming consumer never holds more.
+template <typename T>
+class KmerSeqIterator {
+  public:
+    static constexpr size_t FETCH = 1u << 20;
+    KmerSeqIterator(uint8_t ksize, const Sequence& sequence)
+        : nb_base_(ksize), batch_(std::vector<const Sequence*>{&sequence}), seq_size_(sequence.size()), begin_(0), end_(sequence.size()) {
+        if ((size_t)ksize > T::get_nb_base_max())  // kmergenerator.rs:48-53
+            throw Panic(KMU_EINVAL, "KmerSeqIterator cannot support so many bases for given kmer type");
+        if (seq_size_ == 0) throw Panic(KMU_EINVAL, "attempt to subtract with overflow: IterSequence::new on an empty sequence");  // sequence.rs:531
+    }
+    /// Result<(), ()> of IterSequence::set_range (sequence.rs:562-585): false = Err(())
+    bool set_range(size_t begin, size_t end) {
+        if (end <= begin || end > seq_size_) return false;
+        begin_ = begin;
+        end_ = end;
+        pos_ = begin;
+        window_.clear();
+        wpos_ = 0;
+        return true;
+    }
+    std::optional<T> next() {
+        if (wpos_ >= window_.size() && !refill()) return std::nullopt;
+        return T::from_word(window_[wpos_++], nb_base_);
+    }
+
+  private:
+    bool refill() {
+        // k-mers starting at pos_ .. : the window covers bases [pos_, pos_ + FETCH + k - 1) clamped to the range
+        if (pos_ + nb_base_ > end_) return false;
+        const uint64_t idx = 0, b = pos_, e = std::min<uint64_t>(end_, pos_ + FETCH + nb_base_ - 1);
+        kmu_ctx* ctx = Context::global().get();
+        kmu_seqbatch* part = nullptr;
+        check(kmu_seqbatch_slices(ctx, batch_.get(), &idx, &b, &e, 1, &part), "KmerSeqIterator::next");
+        window_.assign(kmu_kmer_count(part, nb_base_), 0);
+        const int32_t rc = kmu_generate_kmers(ctx, part, nb_base_, T::kmu_type, KMU_HASH_IDENTITY_RAW, window_.data(), nullptr, 0);
+        kmu_seqbatch_destroy(part);
+        check(rc, "KmerSeqIterator::next");
+        wpos_ = 0;
+        pos_ += window_.size();
+        return !window_.empty();
+    }
+    uint8_t nb_base_;
+    DeviceBatch batch_;
+    size_t seq_size_, begin_, end_, pos_ = 0, wpos_ = 0;
+    std::vector<typename T::Val> window_;
+};
+
 // ---------------------------------------------------------------- KmerGenerator
 /// KmerGenerator<T> (src/base/kmergenerator.rs:148-186).  `KmerGenerator::new(ksize)` panics on a size the type
 /// cannot hold (:48-53, 218, 311, 415) -- here the first generate call throws.
@@ -338,6 +517,28 @@ class KmerGenerator {
         if (begin >= end || end > seq.size()) throw Panic(KMU_EINVAL, "KmerSeqIterator::set_range failed");
         DeviceBatch b(seq, begin, end);
         return run(b);
+    }
+    /// generate_weighted_kmer = generate_kmer_distribution (kmergenerator.rs:177-186, per type :262-303, 343-408, 459-526):
+    /// the distinct (forward) k-mers of the sequence with their multiplicities -- counted in an exact table on the GPU
+    /// (kmu_count_insert_seqs, canonical off) and read back; iteration order of a hash map is unspecified in the reference too.
+    KmerDistribution<T> generate_weighted_kmer(const Sequence& seq) const { return generate_kmer_distribution(seq); }
+    KmerDistribution<T> generate_kmer_distribution(const Sequence& seq) const {
+        DeviceBatch b(std::vector<const Sequence*>{&seq});
+        const uint64_t nk = kmu_kmer_count(b.get(), kmer_size_);
+        KmerDistribution<T> map;
+        kmu_ctx* ctx = Context::global().get();
+        kmu_counter* c = nullptr;
+        check(kmu_count_create(ctx, kmer_size_, T::kmu_type, 32, std::max<uint64_t>(nk, 16), &c), "generate_kmer_distribution");
+        std::vector<typename T::Val> keys(nk + 1);
+        std::vector<uint32_t> counts(nk + 1);
+        uint64_t n = 0;
+        int32_t rc = kmu_count_insert_seqs(ctx, c, b.get(), 0);
+        if (rc == KMU_OK) rc = kmu_count_export(ctx, c, 1, keys.data(), counts.data(), nk + 1, &n);
+        kmu_count_destroy(c);
+        check(rc, "generate_kmer_distribution");
+        map.reserve(n);
+        for (uint64_t i = 0; i < n; ++i) map.emplace(T::build(keys[i], kmer_size_), counts[i]);
+        return map;
     }
     /// all sequences with one upload and one launch (what a caller looping over generate_kmer wants on a GPU)
     std::vector<std::vector<T>> generate_kmer_batch(const std::vector<const Sequence*>& vseq) const {

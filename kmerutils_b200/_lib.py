@@ -123,6 +123,10 @@ SIGNATURES = {
     "kmu_count_partition_counts": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32, u64p]),
     "kmu_count_partition_scatter": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32,
                                                 C.POINTER(C.c_void_p), u64p]),
+    "kmu_count_exchange_geometry": (C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "kmu_count_exchange_scatter": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32,
+                                               C.c_uint64, C.POINTER(C.c_void_p), u64p, C.POINTER(C.c_int32)]),
+    "kmu_count_insert_slabs": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, u64p]),
     "kmu_ipc_alloc": (C.c_int32, [C.c_void_p, C.c_uint64, vpp, C.c_void_p]),
     "kmu_ipc_free": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "kmu_ipc_open": (C.c_int32, [C.c_void_p, C.c_void_p, vpp]),

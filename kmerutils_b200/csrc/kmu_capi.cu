@@ -637,9 +637,7 @@ int32_t kmu_seqbatch_download(kmu_ctx* ctx, const kmu_seqbatch* b, uint8_t* pack
 // ---- k-mer generation / ntHash ----------------------------------------------------------
 uint64_t kmu_kmer_count(const kmu_seqbatch* b, uint32_t k) {
     if (!b) return 0;
-    uint64_t n = 0;
-    for (uint64_t L : b->h_nbases) n += L >= k ? L - k + 1 : 0;
-    return n;
+    return b->kmer_count(k);
 }
 
 static int32_t upload_kmer_offsets(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, uint64_t* out_off_host,

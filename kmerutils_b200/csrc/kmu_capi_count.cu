@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <vector>
 
 #include "kmu_host.h"
@@ -40,6 +41,164 @@ int32_t check_overflow(kmu_ctx* ctx, kmu_counter* c) {
     if (ovf)
         return fail(KMU_EOVERFLOW, "counting table of %llu slots is full: create the counter with a larger capacity",
                     (unsigned long long)c->capacity);
+    return KMU_OK;
+}
+
+
+// ---- two-phase insertion (kmu_count_part.cu) -----------------------------------------------------------------
+// The table is cut into regions of REGION_BYTES (32 MB: load + RED updates of a region that sits in L2 run at 64 G/s
+// against 15.5 G/s on the whole table, profiles/r1d_micro_atomics.txt); more than max_buckets regions -> larger regions.
+constexpr uint32_t MAX_BUCKETS = 4096;
+
+double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+// KMU_COUNT_REGION_KB / KMU_COUNT_TWO_PHASE_MIN_KEYS: test knobs (small tables through the regioned path)
+uint64_t region_bytes_setting() {
+    if (const char* e = std::getenv("KMU_COUNT_REGION_KB")) {
+        const uint64_t kb = (uint64_t)std::atoll(e);
+        if (kb >= 1) return kb << 10;
+    }
+    return 32ull << 20;
+}
+
+struct RegionGeom {
+    uint32_t nregions = 1;
+    uint32_t shift = 0;  // log2(slots per region)
+};
+
+RegionGeom region_geometry(uint64_t capacity, bool key64, uint32_t nowners) {
+    const uint64_t slot_bytes = key64 ? 16 : 8;
+    uint64_t region_slots = 1;
+    while (region_slots * 2 * slot_bytes <= region_bytes_setting()) region_slots <<= 1;
+    const uint32_t max_regions = MAX_BUCKETS / (nowners ? nowners : 1);
+    while (capacity / region_slots > max_regions) region_slots <<= 1;
+    RegionGeom g;
+    g.nregions = capacity > region_slots ? (uint32_t)(capacity / region_slots) : 1u;
+    if (g.nregions > 1)
+        while ((1ull << g.shift) < region_slots) ++g.shift;
+    return g;
+}
+
+// slab capacity for `n` keys spread over `nbuckets` by a hash: the expected share + 8 sigma + slack
+uint64_t slab_capacity(uint64_t n, uint64_t nbuckets) {
+    const double mean = (double)n / (double)nbuckets;
+    return (uint64_t)(mean + 8.0 * std::sqrt(mean) + 1024.0);
+}
+
+bool two_phase_wanted(const kmu_counter* c, uint64_t nkeys) {
+    if (std::getenv("KMU_COUNT_DIRECT")) return false;
+    const uint64_t table_bytes = c->capacity * (c->key64 ? 16 : 8);
+    uint64_t min_keys = 1ull << 20;
+    if (const char* e = std::getenv("KMU_COUNT_TWO_PHASE_MIN_KEYS")) min_keys = (uint64_t)std::atoll(e);
+    return table_bytes >= 4 * region_bytes_setting() && nkeys >= min_keys;
+}
+
+// bytes the partition slabs of one chunk may take: 32 GB, at most half of the free memory (the buffer already held counts as free)
+uint64_t slab_budget_bytes(uint64_t held) {
+    uint64_t budget = 32ull << 30;
+    if (const char* e = std::getenv("KMU_COUNT_SLAB_MB")) return (uint64_t)std::atoll(e) << 20;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    return std::min<uint64_t>(budget, ((uint64_t)free_b + held) / 2);
+}
+
+// scratch in ctx->counters: [0 .. MAX_BUCKETS) cursors, [MAX_BUCKETS .. +64) chunk flags, then one device pointer
+constexpr size_t PART_SCRATCH_WORDS = MAX_BUCKETS + 64 + 8 + 64 + MAX_BUCKETS / 2;  // ... 64 pointers, MAX_BUCKETS u32 `done` counters
+
+// insert the k-mers of the batch (src == nullptr) or the device key array `src` through partition + regioned insertion.
+// *launches is increased by the kernels launched.  Chunks whose partition overflowed a slab are redone directly.
+int32_t insert_two_phase(kmu_ctx* ctx, kmu_counter* c, const kmu_seqbatch* b, bool canonical, const void* src, uint64_t nsrc,
+                         uint64_t* launches) {
+    const double t_in = now_ms();
+    const size_t esz = c->key64 ? 8 : 4;
+    const RegionGeom rg = region_geometry(c->capacity, c->key64, 1);
+    const bool prefetch = std::getenv("KMU_COUNT_NO_PREFETCH") == nullptr;
+    // chunks: a bound of the k-mers of a chunk = 4 per packed byte (sequences) or the keys themselves
+    const uint64_t unit_total = b ? b->packed_bytes : nsrc;          // bytes or keys
+    const uint64_t keys_per_unit = b ? 4 : 1;
+    // one chunk if its slabs fit the buffer already held (no query of the free memory on the hot path)
+    uint64_t chunk_units = unit_total;
+    if (std::getenv("KMU_COUNT_SLAB_MB") || slab_capacity(unit_total * keys_per_unit, rg.nregions) * rg.nregions * esz > ctx->sig_dev.cap) {
+        const uint64_t budget = slab_budget_bytes(ctx->sig_dev.cap);
+        chunk_units = std::max<uint64_t>(1, budget / (esz * keys_per_unit) * 9 / 10);
+        if (b) chunk_units = std::max<uint64_t>(2048, chunk_units / 2048 * 2048);  // GROUP_BYTES of kmu_device.cuh
+        chunk_units = std::min(chunk_units, unit_total);
+    }
+    const uint64_t nchunks = (unit_total + chunk_units - 1) / chunk_units;
+    if (nchunks > 64) return fail(KMU_ENOMEM, "not enough free device memory for the partition slabs (%llu chunks)", (unsigned long long)nchunks);
+    const uint64_t bound = chunk_units * keys_per_unit;
+    const uint64_t slab_cap = slab_capacity(bound, rg.nregions);
+    if (slab_cap >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "partition slab too large");
+    CUDA_TRY(ctx->sig_dev.reserve(slab_cap * rg.nregions * esz));
+    CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * PART_SCRATCH_WORDS));
+    unsigned long long* cursors = (unsigned long long*)ctx->counters.p;
+    unsigned long long* flags = cursors + MAX_BUCKETS;
+    void** d_dest = (void**)(flags + 64);
+    unsigned int* done = std::getenv("KMU_COUNT_FREE_RUNNING") ? nullptr : (unsigned int*)(flags + 64 + 8 + 64);
+    void* slab_ptr = ctx->sig_dev.p;
+    CUDA_TRY(cudaMemcpyAsync(d_dest, &slab_ptr, sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(unsigned long long) * 64, ctx->stream));
+    kmu::PartGeom g{};
+    g.nowners = 1;
+    g.nregions = rg.nregions;
+    g.capmask = c->capacity - 1;
+    g.shift = rg.shift;
+    g.nsend = 1;
+    g.self = 0;
+    g.slab_cap = slab_cap;
+    kmu::SeqView v{};
+    if (b) v = kmu::SeqView{b->packed, b->byte_off, b->nbases, b->nseq};
+    const bool timing = std::getenv("KMU_COUNT_TIMING") != nullptr;
+    cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
+    if (timing)
+        for (auto& e : tev) cudaEventCreate(&e);
+    for (uint64_t ch = 0; ch < nchunks; ++ch) {
+        const uint64_t u0 = ch * chunk_units, u1 = std::min(unit_total, u0 + chunk_units);
+        CUDA_TRY(cudaMemsetAsync(cursors, 0, sizeof(unsigned long long) * rg.nregions, ctx->stream));
+        if (done) CUDA_TRY(cudaMemsetAsync(done, 0, sizeof(unsigned int) * rg.nregions, ctx->stream));
+        if (timing) {
+            cudaEventRecord(tev[0], ctx->stream);
+            std::fprintf(stderr, "[kmu count] chunk %llu: %.2f ms of host time before the first launch\n", (unsigned long long)ch, now_ms() - t_in);
+        }
+        if (b)
+            CUDA_TRY(kmu::launch_count_part_seqs(v, u0, u1, b->packed_bytes, c->k, c->key64, canonical, g, d_dest, cursors, flags + ch,
+                                                 ctx->sm_count, ctx->stream));
+        else
+            CUDA_TRY(kmu::launch_count_part_keys((const uint8_t*)src + u0 * esz, u1 - u0, c->key64, g, d_dest, cursors, flags + ch,
+                                                 ctx->sm_count, ctx->stream));
+        if (timing) cudaEventRecord(tev[1], ctx->stream);
+        CUDA_TRY(kmu::launch_count_insert_slabs(slab_ptr, slab_cap, rg.nregions, 1, cursors, c->view(), c->key64, rg.shift, flags + ch,
+                                                prefetch, done, ctx->sm_count, ctx->stream));
+        *launches += 2;
+        if (timing) {
+            cudaEventRecord(tev[2], ctx->stream);
+            cudaEventSynchronize(tev[2]);
+            float a = 0, bms = 0;
+            cudaEventElapsedTime(&a, tev[0], tev[1]);
+            cudaEventElapsedTime(&bms, tev[1], tev[2]);
+            std::fprintf(stderr, "[kmu count] chunk %llu/%llu: %u regions of %llu KB, slab_cap %llu, partition %.2f ms, insert %.2f ms\n",
+                         (unsigned long long)ch, (unsigned long long)nchunks, rg.nregions,
+                         (unsigned long long)(((c->key64 ? 16ull : 8ull) << rg.shift) >> 10), (unsigned long long)slab_cap, a, bms);
+        }
+    }
+    if (timing)
+        for (auto& e : tev) cudaEventDestroy(e);
+    unsigned long long hflags[64];
+    CUDA_TRY(cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t ch = 0; ch < nchunks; ++ch) {
+        if (!hflags[ch]) continue;
+        const uint64_t u0 = ch * chunk_units, u1 = std::min(unit_total, u0 + chunk_units);
+        if (b)
+            CUDA_TRY(kmu::launch_count_insert_seqs(v, u1, c->k, c->key64, canonical, c->view(), ctx->sm_count, ctx->stream, u0));
+        else
+            CUDA_TRY(kmu::launch_count_insert_keys((const uint8_t*)src + u0 * esz, u1 - u0, c->key64, c->view(), ctx->sm_count, ctx->stream));
+        *launches += 1;
+    }
     return KMU_OK;
 }
 
@@ -104,6 +263,7 @@ void kmu_count_destroy(kmu_counter* c) {
 uint64_t kmu_count_capacity(const kmu_counter* c) { return c ? c->capacity : 0; }
 
 int32_t kmu_count_insert_seqs(kmu_ctx* ctx, kmu_counter* c, const kmu_seqbatch* b, int32_t canonical) {
+    const double t_enter = now_ms();
     if (!ctx || !c || !b) return fail(KMU_EINVAL, "null argument");
     if (b->alphabet != 0) return fail(KMU_EINVAL, "the counter takes DNA sequences");
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -111,31 +271,16 @@ int32_t kmu_count_insert_seqs(kmu_ctx* ctx, kmu_counter* c, const kmu_seqbatch* 
     ctx->last = kmu_times{};
     if (b->nseq == 0) return KMU_OK;
     kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
-    uint64_t total = 0;
-    for (uint64_t L : b->h_nbases) total += L >= c->k ? L - c->k + 1 : 0;
-    const size_t esz = c->key64 ? 8 : 4, slot_bytes = c->key64 ? 16 : 8;
-    const uint64_t table_bytes = c->capacity * slot_bytes;
-    // Optional two-phase insertion (KMU_COUNT_TWO_PHASE=1): (1) the k-mers are grouped by the 32 MB region of the
-    // table they hash to (streaming writes), (2) they are inserted region after region.  Measured on B200 it is
-    // SLOWER than direct insertion (123 ms vs 66 ms for 960 M 31-mers into a 17 GB table): every slot is touched only
-    // a few times, so the cold sector fetches of each region dominate and the partition pass comes on top
-    // (scripts/micro/atomics_region.cu: 21 G region-ordered updates/s vs 15.5 G fully random).  Kept for experiments.
-    const bool two_phase = std::getenv("KMU_COUNT_TWO_PHASE") != nullptr && table_bytes >= (256ull << 20) &&
-                           total >= (1ull << 22) && total * esz <= (24ull << 30);
+    const uint64_t total = b->kmer_count(c->k);
+    // Tables far larger than L2 take the batch in two phases (partition by table region, then region after region with
+    // the updates hitting L2, kmu_count_part.cu); small tables and small batches are inserted directly.
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    if (two_phase) {
-        uint32_t nparts = 1;
-        while (nparts < 4096 && table_bytes / nparts > (32ull << 20)) nparts <<= 1;
-        const int grid = kmu::count_partition_grid(b->packed_bytes, ctx->sm_count);
-        CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * ((size_t)nparts * grid + 2 * nparts + 64)));
-        unsigned long long* block_counts = (unsigned long long*)ctx->counters.p;
-        unsigned long long* part_totals = block_counts + (size_t)nparts * grid;
-        CUDA_TRY(ctx->sig_dev.reserve(total * esz));
-        CUDA_TRY(kmu::launch_count_partition_by_region(v, b->packed_bytes, c->k, c->key64, canonical != 0, c->view(), nparts,
-                                                       grid, block_counts, part_totals, ctx->sig_dev.p, ctx->stream));
-        CUDA_TRY(kmu::launch_count_insert_keys(ctx->sig_dev.p, total, c->key64, c->view(), ctx->sm_count, ctx->stream));
-        ctx->launches += 6;
-        ctx->last.launches = 6;
+    if (two_phase_wanted(c, total)) {
+        uint64_t nl = 0;
+        int32_t rc2 = insert_two_phase(ctx, c, b, canonical != 0, nullptr, 0, &nl);
+        if (rc2) return rc2;
+        ctx->launches += nl;
+        ctx->last.launches = nl;
     } else {
         CUDA_TRY(kmu::launch_count_insert_seqs(v, b->packed_bytes, c->k, c->key64, canonical != 0, c->view(), ctx->sm_count,
                                                ctx->stream));
@@ -143,10 +288,14 @@ int32_t kmu_count_insert_seqs(kmu_ctx* ctx, kmu_counter* c, const kmu_seqbatch* 
         ctx->last.launches = 1;
     }
     cudaEventRecord(ctx->ev[1], ctx->stream);
+    const double t_q = now_ms();
     int32_t rc = check_overflow(ctx, c);
     cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    if (std::getenv("KMU_COUNT_TIMING"))
+        std::fprintf(stderr, "[kmu count] insert_seqs: host %.2f ms until queued, %.2f ms in all; events %.2f ms\n", t_q - t_enter,
+                     now_ms() - t_enter, ctx->last.kernel_ms);
     if (rc) return rc;
-    for (uint64_t L : b->h_nbases) c->inserted += L >= c->k ? L - c->k + 1 : 0;
+    c->inserted += total;
     return KMU_OK;
 }
 
@@ -167,10 +316,18 @@ int32_t kmu_count_insert_kmers(kmu_ctx* ctx, kmu_counter* c, const void* kmers, 
         d = ctx->misc.p;
     }
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    CUDA_TRY(kmu::launch_count_insert_keys(d, n, c->key64, c->view(), ctx->sm_count, ctx->stream));
+    if (two_phase_wanted(c, n)) {
+        uint64_t nl = 0;
+        int32_t rc2 = insert_two_phase(ctx, c, nullptr, false, d, n, &nl);
+        if (rc2) return rc2;
+        ctx->launches += nl;
+        ctx->last.launches = nl;
+    } else {
+        CUDA_TRY(kmu::launch_count_insert_keys(d, n, c->key64, c->view(), ctx->sm_count, ctx->stream));
+        ctx->launches += 1;
+        ctx->last.launches = 1;
+    }
     cudaEventRecord(ctx->ev[1], ctx->stream);
-    ctx->launches += 1;
-    ctx->last.launches = 1;
     int32_t rc = check_overflow(ctx, c);
     cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
     if (!on_device) cudaEventElapsedTime(&ctx->last.h2d_ms, ctx->ev[2], ctx->ev[3]);
@@ -278,8 +435,7 @@ int32_t kmu_count_partition(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};
     for (uint32_t p = 0; p < nparts; ++p) part_counts[p] = 0;
-    uint64_t total = 0;
-    for (uint64_t L : b->h_nbases) total += L >= k ? L - k + 1 : 0;
+    const uint64_t total = b->kmer_count(k);
     if (total == 0) return KMU_OK;
     if (!kmers_out) return fail(KMU_EINVAL, "null output buffer");
     const bool key64 = kmer_type == KMU_KMER64;
@@ -435,6 +591,92 @@ int32_t kmu_count_partition_scatter(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_
     return KMU_OK;
 }
 
+// ---- fused exchange: extraction + (owner, region) bucketing + NVLink stores in ONE kernel and ONE walk -----------------
+// Every rank holds a table of the same capacity (kmu_count_create with the same arguments).  The receive buffer of a
+// rank is nregions * nowners slabs of slab_cap keys: slab (r, s) holds what sender s found for region r of the table.
+int32_t kmu_count_exchange_geometry(const kmu_counter* c, uint32_t nowners, uint32_t* nregions) {
+    if (!c || !nregions || nowners < 1 || nowners > 64) return fail(KMU_EINVAL, "bad argument");
+    *nregions = region_geometry(c->capacity, c->key64, nowners).nregions;
+    return KMU_OK;
+}
+
+int32_t kmu_count_exchange_scatter(kmu_ctx* ctx, const kmu_seqbatch* b, const kmu_counter* c, int32_t canonical, uint32_t nowners,
+                                   uint32_t self, uint64_t slab_cap, void* const* dests, uint64_t* sent_counts,
+                                   int32_t* overflowed) {
+    if (!ctx || !b || !c || !dests || !sent_counts || !overflowed) return fail(KMU_EINVAL, "null argument");
+    if (b->alphabet != 0) return fail(KMU_EINVAL, "the counter takes DNA sequences");
+    if (nowners < 1 || nowners > 64 || self >= nowners) return fail(KMU_EINVAL, "nowners must be in 1..64 and self below it");
+    if (slab_cap == 0 || slab_cap >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "slab_cap out of range");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    const RegionGeom rg = region_geometry(c->capacity, c->key64, nowners);
+    const uint32_t nb = nowners * rg.nregions;
+    CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * PART_SCRATCH_WORDS));
+    unsigned long long* cursors = (unsigned long long*)ctx->counters.p;
+    unsigned long long* flags = cursors + MAX_BUCKETS;
+    void** d_dests = (void**)(flags + 64 + 8);
+    CUDA_TRY(cudaMemcpyAsync(d_dests, dests, sizeof(void*) * nowners, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(cursors, 0, sizeof(unsigned long long) * (MAX_BUCKETS + 64), ctx->stream));
+    kmu::PartGeom g{};
+    g.nowners = nowners;
+    g.nregions = rg.nregions;
+    g.capmask = c->capacity - 1;
+    g.shift = rg.shift;
+    g.nsend = nowners;
+    g.self = self;
+    g.slab_cap = slab_cap;
+    kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    if (b->nseq && b->packed_bytes) {
+        CUDA_TRY(kmu::launch_count_part_seqs(v, 0, b->packed_bytes, b->packed_bytes, c->k, c->key64, canonical != 0, g, d_dests, cursors,
+                                             flags, ctx->sm_count, ctx->stream));
+        ctx->launches += 1;
+        ctx->last.launches = 1;
+    }
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    std::vector<unsigned long long> h(nb + 1);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), cursors, sizeof(unsigned long long) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h.data() + nb, flags, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    for (uint32_t i = 0; i < nb; ++i) sent_counts[i] = h[i];
+    *overflowed = h[nb] ? 1 : 0;
+    return KMU_OK;
+}
+
+int32_t kmu_count_insert_slabs(kmu_ctx* ctx, kmu_counter* c, const void* slabs, uint64_t slab_cap, uint32_t nsend,
+                               const uint64_t* counts) {
+    if (!ctx || !c || !slabs || !counts) return fail(KMU_EINVAL, "null argument");
+    if (nsend < 1 || nsend > 64) return fail(KMU_EINVAL, "nsend must be in 1..64");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ScopedDevice sd(ctx->device);
+    ctx->last = kmu_times{};
+    const RegionGeom rg = region_geometry(c->capacity, c->key64, nsend);
+    const size_t n = (size_t)nsend * rg.nregions;
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (counts[i] > slab_cap) return fail(KMU_EOVERFLOW, "a slab holds %llu keys, capacity %llu", (unsigned long long)counts[i], (unsigned long long)slab_cap);
+        total += counts[i];
+    }
+    CUDA_TRY(ctx->misc.reserve(sizeof(unsigned long long) * n + sizeof(unsigned int) * rg.nregions));
+    CUDA_TRY(cudaMemcpyAsync(ctx->misc.p, counts, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned int* done = (unsigned int*)((unsigned long long*)ctx->misc.p + n);
+    CUDA_TRY(cudaMemsetAsync(done, 0, sizeof(unsigned int) * rg.nregions, ctx->stream));
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    CUDA_TRY(kmu::launch_count_insert_slabs(slabs, slab_cap, rg.nregions, nsend, (const unsigned long long*)ctx->misc.p, c->view(),
+                                            c->key64, rg.shift, nullptr, std::getenv("KMU_COUNT_NO_PREFETCH") == nullptr, done,
+                                            ctx->sm_count, ctx->stream));
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    ctx->launches += 1;
+    ctx->last.launches = 1;
+    int32_t rc = check_overflow(ctx, c);
+    cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
+    if (rc) return rc;
+    c->inserted += total;
+    return KMU_OK;
+}
+
 // receive buffers shared between the processes of one box (CUDA IPC): export a buffer of this GPU ...
 int32_t kmu_ipc_alloc(kmu_ctx* ctx, uint64_t bytes, void** dev_ptr, uint8_t handle[64]) {
     if (!ctx || !dev_ptr || !handle) return fail(KMU_EINVAL, "null argument");
@@ -567,8 +809,7 @@ int32_t kmu_sketch_pmh3a_whole(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, 
     if (int32_t a = kmu_check_kmer_args(b, k, kmer_type, hash_kind)) return a;
     if (kmer_type_is_aa(kmer_type)) return fail(KMU_EINVAL, "whole-file ProbMinHash3a takes DNA sequences");
     if (m < 2) return fail(KMU_EINVAL, "ProbMinHash3a needs at least 2 hash values (m = %u)", m);
-    uint64_t total = 0;
-    for (uint64_t L : b->h_nbases) total += L >= k ? L - k + 1 : 0;
+    const uint64_t total = b->kmer_count(k);
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};

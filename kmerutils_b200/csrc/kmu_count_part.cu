@@ -1,0 +1,339 @@
+// kmu_count_part.cu -- two-phase insertion into the exact counting table, and the fused multi-GPU exchange.
+//
+// Why: a k-mer inserted straight into a table far larger than L2 costs one random DRAM read-modify-write of a
+// 32-byte sector per k-mer -- measured 163 B of DRAM traffic per 31-mer against 32 B algorithmic, 15.5 G updates/s
+// whatever the kernel does (profiles/r1d_micro_atomics.txt).  The same updates on a table region that sits in L2
+// run at 60-70 G/s.  So the batch is first PARTITIONED by the region of the table each k-mer hashes to (phase 1,
+// streaming), then inserted region after region by the whole grid (phase 2): the region is streamed into L2 once
+// (prefetch, coalesced), takes all its updates there, and is written back once.
+//
+//   phase 1  count_part_kernel      one walk over the packed reads (or over a key array): canonical k-mer ->
+//                                   bucket = owner * nregions + region; a CTA collects a tile of 4096 k-mers in
+//                                   shared memory, sorts it by bucket there (histogram, scan, scatter) and appends
+//                                   every bucket's run to that bucket's slab with ONE global atomic per (tile,
+//                                   bucket) and coalesced stores.  Slabs have a fixed capacity (expected share +
+//                                   8 sigma): an overflow (pathological input: one k-mer repeated millions of
+//                                   times) raises a flag and the caller falls back to direct insertion.
+//   phase 2  count_insert_slabs_kernel   for r in regions: prefetch region r + 1 of the table into L2; all CTAs
+//                                   insert the keys of region r (look, atomicCAS claim, RED add) -- L2 hits.
+//
+// Multi-GPU (reference: DispatchableT::dispatch, kmercount.rs:382-420, and the one-producer / N-consumer hand-off of
+// count_kmer_threaded_one_to_many, :881-974): owner = intNN_hash(key) % nowners.  dests[o] is the receive buffer of
+// rank o -- for o != self a peer GPU's memory mapped with CUDA IPC -- so extraction, canonicalisation, bucketing
+// by (owner, region) and the all-to-all over NVLink are ONE kernel and one walk: no staging buffer, no separate
+// collective on the data path.  Cursors are sender-local; the receive buffer of every rank is cut into
+// [region][sender] slabs, so the receiver's phase 2 needs only the senders' final cursor values (a few KB).
+#include <cstdint>
+
+#include "kmu_count_ops.cuh"
+#include "kmu_device.cuh"
+#include "kmu_kernels.h"
+
+namespace kmu {
+
+constexpr int PART_THREADS = 512;
+constexpr uint32_t PART_TILE_BYTES = 1024;               // packed bytes per tile
+constexpr uint32_t PART_TILE_KEYS = PART_TILE_BYTES * 4;  // k-mers per tile (at most one per base)
+constexpr uint32_t PART_WARP_BYTES = PART_TILE_BYTES / (PART_THREADS / 32);
+
+template <typename V>
+__device__ __forceinline__ uint32_t part_bucket(V key, const PartGeom& g) {
+    uint32_t b = g.nregions > 1 ? (uint32_t)((fmix64((uint64_t)key) & g.capmask) >> g.shift) : 0u;
+    if (g.nowners > 1) b += (uint32_t)(inv_hash(key) % (V)g.nowners) * g.nregions;
+    return b;
+}
+
+// last sequence s >= s_hint with byte_off[s] <= byte (byte_off ascending): the warp looks at 32 entries at a time
+__device__ __forceinline__ uint64_t seq_forward(const uint64_t* __restrict__ byte_off, uint64_t nseq, uint64_t s, uint64_t byte,
+                                                int lane) {
+    for (;;) {
+        const uint64_t idx = s + 1 + lane;
+        const bool ok = idx < nseq && __ldg(byte_off + idx) <= byte;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
+        s += __popc(bal);
+        if (bal != 0xFFFFFFFFu) return s;
+    }
+}
+
+template <typename V, bool FROM_SEQ>
+__global__ void __launch_bounds__(PART_THREADS, 2)
+    count_part_kernel(SeqView b, uint64_t byte_begin, uint64_t byte_end, uint64_t total_bytes, uint32_t k, int canonical,
+                      const V* __restrict__ keys, uint64_t nkeys, PartGeom g, V* const* __restrict__ dests,
+                      unsigned long long* __restrict__ cursors, unsigned long long* __restrict__ flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t NB = g.nowners * g.nregions;
+    V* tkeys = (V*)smem_raw;
+    V* sorted = tkeys + PART_TILE_KEYS;
+    uint16_t* tb = (uint16_t*)(sorted + PART_TILE_KEYS);
+    uint16_t* sb = tb + PART_TILE_KEYS;
+    uint32_t* hist = (uint32_t*)(sb + PART_TILE_KEYS);  // counts, then the fill cursor of the bucket inside `sorted`
+    uint32_t* boff = hist + NB;
+    uint32_t* gpos = boff + NB;
+    __shared__ uint32_t tile_n, warp_sums[PART_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+
+    const uint64_t ntiles = FROM_SEQ ? (byte_end - byte_begin + PART_TILE_BYTES - 1) / PART_TILE_BYTES
+                                     : (nkeys + PART_TILE_KEYS - 1) / PART_TILE_KEYS;
+    // a CTA owns a contiguous range of tiles: the sequence index only moves forward
+    const uint64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const uint64_t t0 = (uint64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
+    for (uint32_t p = tid; p < NB; p += PART_THREADS) hist[p] = 0;
+    if (tid == 0) tile_n = 0;
+    uint64_t s = 0;
+    if (FROM_SEQ && t0 < t1) s = seq_of_byte(b.byte_off, b.nseq, byte_begin + t0 * PART_TILE_BYTES + (uint64_t)wib * PART_WARP_BYTES);
+    __syncthreads();
+    bool lost = false;
+
+    for (uint64_t t = t0; t < t1; ++t) {
+        // ---- phase 1: the tile's keys and bucket ids into shared memory, histogram of the buckets
+        if (FROM_SEQ) {
+            const uint64_t byte0 = byte_begin + t * PART_TILE_BYTES + (uint64_t)wib * PART_WARP_BYTES;
+            const uint64_t byte1 = min(min(byte0 + (uint64_t)PART_WARP_BYTES, byte_end), total_bytes);
+            if (byte0 < byte1) {
+                s = seq_forward(b.byte_off, b.nseq, s, byte0, lane);
+                uint64_t q = s;
+                while (q < b.nseq) {
+                    const uint64_t sbyte = __ldg(b.byte_off + q);
+                    if (sbyte >= byte1) break;
+                    const uint64_t L = __ldg(b.nbases + q);
+                    const uint64_t nk = L >= k ? L - k + 1 : 0;
+                    const uint64_t p_lo = byte0 > sbyte ? (byte0 - sbyte) * 4 : 0;
+                    const uint64_t p_hi = min(nk, (byte1 - sbyte) * 4);
+                    const uint32_t* words = (const uint32_t*)(b.packed + sbyte);
+                    for (uint64_t p0 = p_lo; p0 < p_hi; p0 += 32) {
+                        const uint64_t p = p0 + lane;
+                        const bool active = p < p_hi;
+                        V key = 0;
+                        uint32_t bk = 0;
+                        if (active) {
+                            key = kmer_at<V>(words, p, k);
+                            if (canonical) {
+                                const V rc = revcomp_val(key, k);
+                                key = key < rc ? key : rc;
+                            }
+                            bk = part_bucket<V>(key, g);
+                        }
+                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, active);
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&tile_n, (uint32_t)__popc(bal));
+                        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                        if (active) {
+                            const uint32_t pos = base + __popc(bal & ((1u << lane) - 1));
+                            tkeys[pos] = key;
+                            tb[pos] = (uint16_t)bk;
+                            atomicAdd(&hist[bk], 1u);
+                        }
+                    }
+                    ++q;
+                }
+            }
+        } else {
+            const uint64_t i0 = t * PART_TILE_KEYS;
+            const uint32_t n = (uint32_t)min((uint64_t)PART_TILE_KEYS, nkeys - i0);
+            for (uint32_t i = tid; i < n; i += PART_THREADS) {
+                const V key = keys[i0 + i];
+                const uint32_t bk = part_bucket<V>(key, g);
+                tkeys[i] = key;
+                tb[i] = (uint16_t)bk;
+                atomicAdd(&hist[bk], 1u);
+            }
+            if (tid == 0) tile_n = n;
+        }
+        __syncthreads();
+        const uint32_t n = tile_n;
+        // ---- phase 2: exclusive scan of the histogram; one global atomic per non-empty bucket reserves its run
+        {
+            const uint32_t per_t = (NB + PART_THREADS - 1) / PART_THREADS;  // <= 8
+            const uint32_t first = tid * per_t;
+            uint32_t c[8], sum = 0;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) {
+                c[j] = (j < per_t && first + j < NB) ? hist[first + j] : 0u;
+                sum += c[j];
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (lane == 31) warp_sums[wib] = incl;
+            __syncthreads();
+            uint32_t wbase = 0;
+            for (int w = 0; w < wib; ++w) wbase += warp_sums[w];
+            uint32_t off = wbase + incl - sum;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) {
+                if (j < per_t && first + j < NB) {
+                    const uint32_t bk = first + j;
+                    boff[bk] = off;
+                    hist[bk] = off;
+                    uint32_t gp = 0;
+                    if (c[j]) {
+                        const unsigned long long at = atomicAdd(&cursors[bk], (unsigned long long)c[j]);
+                        if (at + c[j] > g.slab_cap) lost = true;
+                        gp = at > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)at;
+                    }
+                    gpos[bk] = gp;
+                    off += c[j];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: the tile sorted by bucket
+        for (uint32_t i = tid; i < n; i += PART_THREADS) {
+            const uint32_t bk = tb[i];
+            const uint32_t r = atomicAdd(&hist[bk], 1u);
+            sorted[r] = tkeys[i];
+            sb[r] = (uint16_t)bk;
+        }
+        __syncthreads();
+        // ---- phase 4: every bucket's run goes to its slab (consecutive threads, consecutive addresses)
+        for (uint32_t j = tid; j < n; j += PART_THREADS) {
+            const uint32_t bk = sb[j];
+            const uint64_t pos = (uint64_t)gpos[bk] + (j - boff[bk]);
+            if (pos < g.slab_cap) {
+                const uint32_t o = bk / g.nregions, r = bk - o * g.nregions;
+                V* dst = dests[o] + ((uint64_t)r * g.nsend + g.self) * g.slab_cap;
+                dst[pos] = sorted[j];
+            }
+        }
+        __syncthreads();
+        for (uint32_t p = tid; p < NB; p += PART_THREADS) hist[p] = 0;
+        if (tid == 0) tile_n = 0;
+        __syncthreads();
+    }
+    if (lost) *flag = 1ULL;
+}
+
+// phase 2: counts[s * nregions + r] keys of sender s for region r sit at slabs + (r * nsend + s) * slab_cap.
+// All CTAs take the regions in the same order and are kept within two regions of each other: a CTA may start region r
+// only when every CTA has finished region r - 2 (done[] counters; cooperative launch, so that all CTAs are resident).
+// Without the coupling the CTAs drift apart by tens of regions and the working set leaves L2 (measured: no faster than
+// random insertion).
+template <typename V>
+__global__ void __launch_bounds__(256) count_insert_slabs_kernel(const V* __restrict__ slabs, uint64_t slab_cap, uint32_t nregions,
+                                                                 uint32_t nsend, const unsigned long long* __restrict__ counts,
+                                                                 CountTable t, uint32_t shift,
+                                                                 const unsigned long long* __restrict__ skip_flag, int prefetch,
+                                                                 unsigned int* __restrict__ done) {
+    if (skip_flag && *skip_flag) return;  // phase 1 overflowed a slab: the caller inserts this chunk directly
+    const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, gsize = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t slot_bytes = sizeof(V) == 8 ? 16 : 8;
+    const uint64_t region_bytes = nregions > 1 ? (slot_bytes << shift) : (t.capmask + 1) * slot_bytes;
+    const uint64_t lines = region_bytes / 128;
+    bool ok = true;
+    for (uint32_t r = 0; r < nregions; ++r) {
+        if (done && r >= 2) {
+            if (threadIdx.x == 0) {
+                while (*(volatile unsigned int*)(done + r - 2) < gridDim.x) __nanosleep(200);
+                __threadfence();
+            }
+            __syncthreads();
+        }
+        if (prefetch) {
+            // stream the next region of the table into L2 (region 0: the region itself as well): coalesced lines
+            // instead of the cold random sector fetches of the updates
+            const uint32_t first = r == 0 ? 0 : r + 1, last = r + 1;
+            for (uint32_t pr = first; pr <= last && pr < nregions; ++pr) {
+                const char* base = (const char*)t.slots + (uint64_t)pr * region_bytes;
+                for (uint64_t l = gtid; l < lines; l += gsize)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + l * 128));
+            }
+        }
+        for (uint32_t s = 0; s < nsend; ++s) {
+            const unsigned long long cnt0 = counts[(uint64_t)s * nregions + r];
+            const uint64_t cnt = cnt0 < slab_cap ? cnt0 : slab_cap;
+            const V* seg = slabs + ((uint64_t)r * nsend + s) * slab_cap;
+            for (uint64_t i = gtid; i < cnt; i += gsize) ok &= CountOps<V>::insert(t, seg[i], 1u);
+        }
+        if (done) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(done + r, 1u);
+            }
+        }
+    }
+    if (!ok) *t.overflow = 1ULL;
+}
+
+size_t count_part_smem_bytes(bool key64, uint32_t nbuckets) {
+    const size_t esz = key64 ? 8 : 4;
+    return (size_t)PART_TILE_KEYS * (2 * esz + 4) + (size_t)nbuckets * 12;
+}
+
+int count_part_grid(int sm_count) { return sm_count * 2; }
+
+cudaError_t launch_count_part_seqs(const SeqView& b, uint64_t byte_begin, uint64_t byte_end, uint64_t total_bytes, uint32_t k,
+                                   bool key64, bool canonical, const PartGeom& g, void* const* dests,
+                                   unsigned long long* cursors, unsigned long long* flag, int sm_count, cudaStream_t st) {
+    if (byte_end <= byte_begin) return cudaSuccess;
+    const size_t smem = count_part_smem_bytes(key64, g.nowners * g.nregions);
+    const int grid = count_part_grid(sm_count);
+    if (key64) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(count_part_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024);
+            attr = true;
+        }
+        count_part_kernel<uint64_t, true><<<grid, PART_THREADS, smem, st>>>(b, byte_begin, byte_end, total_bytes, k, canonical, nullptr, 0,
+                                                                             g, (uint64_t* const*)dests, cursors, flag);
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(count_part_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024);
+            attr = true;
+        }
+        count_part_kernel<uint32_t, true><<<grid, PART_THREADS, smem, st>>>(b, byte_begin, byte_end, total_bytes, k, canonical, nullptr, 0,
+                                                                             g, (uint32_t* const*)dests, cursors, flag);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count_part_keys(const void* keys, uint64_t nkeys, bool key64, const PartGeom& g, void* const* dests,
+                                   unsigned long long* cursors, unsigned long long* flag, int sm_count, cudaStream_t st) {
+    if (nkeys == 0) return cudaSuccess;
+    const size_t smem = count_part_smem_bytes(key64, g.nowners * g.nregions);
+    const int grid = count_part_grid(sm_count);
+    SeqView none{nullptr, nullptr, nullptr, 0};
+    if (key64) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(count_part_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024);
+            attr = true;
+        }
+        count_part_kernel<uint64_t, false><<<grid, PART_THREADS, smem, st>>>(none, 0, 0, 0, 0, 0, (const uint64_t*)keys, nkeys, g,
+                                                                              (uint64_t* const*)dests, cursors, flag);
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(count_part_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024);
+            attr = true;
+        }
+        count_part_kernel<uint32_t, false><<<grid, PART_THREADS, smem, st>>>(none, 0, 0, 0, 0, 0, (const uint32_t*)keys, nkeys, g,
+                                                                              (uint32_t* const*)dests, cursors, flag);
+    }
+    return cudaGetLastError();
+}
+
+// done: nregions zeroed counters (the coupling of the CTAs), or nullptr for free-running CTAs
+cudaError_t launch_count_insert_slabs(const void* slabs, uint64_t slab_cap, uint32_t nregions, uint32_t nsend,
+                                      const unsigned long long* counts, const CountTable& t, bool key64, uint32_t shift,
+                                      const unsigned long long* skip_flag, bool prefetch, unsigned int* done, int sm_count,
+                                      cudaStream_t st) {
+    const void* fn = key64 ? (const void*)count_insert_slabs_kernel<uint64_t> : (const void*)count_insert_slabs_kernel<uint32_t>;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    const int grid = sm_count * per_sm;
+    int pf = prefetch ? 1 : 0;
+    void* args[] = {(void*)&slabs, (void*)&slab_cap, (void*)&nregions, (void*)&nsend, (void*)&counts, (void*)&t,
+                    (void*)&shift,  (void*)&skip_flag, (void*)&pf,      (void*)&done};
+    if (done) return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, 0, st);
+    return cudaLaunchKernel(fn, dim3(grid), dim3(256), args, 0, st);
+}
+
+}  // namespace kmu

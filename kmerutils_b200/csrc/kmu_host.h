@@ -136,6 +136,26 @@ struct kmu_seqbatch {
     int alphabet = 0;           // 0: DNA, 2 bits per base packed; 1: amino acids, one 5-bit code per byte
     std::vector<uint64_t> h_nbases;
     std::vector<uint64_t> h_byte_off;
+    // sum over the sequences of max(0, L - k + 1), cached for the last k asked (the batch is immutable)
+    mutable uint32_t kmer_total_k = 0;
+    mutable uint64_t kmer_total = 0;
+    mutable uint64_t min_nbases = ~0ull;  // shortest sequence (computed on first use)
+    uint64_t kmer_count(uint32_t k) const {
+        if (k == 0) return 0;
+        if (min_nbases == ~0ull) {
+            uint64_t m = ~0ull - 1;
+            for (uint64_t L : h_nbases) m = L < m ? L : m;
+            min_nbases = m;
+        }
+        if (nseq && min_nbases >= k) return total_bases - nseq * (uint64_t)(k - 1);  // every sequence holds a k-mer
+        if (kmer_total_k != k) {
+            uint64_t n = 0;
+            for (uint64_t L : h_nbases) n += L >= k ? L - k + 1 : 0;
+            kmer_total = n;
+            kmer_total_k = k;
+        }
+        return kmer_total;
+    }
 };
 
 struct ScopedDevice {

@@ -241,7 +241,7 @@ struct CountTable {
 };
 cudaError_t launch_count_init(const CountTable& t, bool key64, int sm_count, cudaStream_t st);
 cudaError_t launch_count_insert_seqs(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
-                                     const CountTable& t, int sm_count, cudaStream_t st);
+                                     const CountTable& t, int sm_count, cudaStream_t st, uint64_t byte_begin = 0);
 cudaError_t launch_count_insert_keys(const void* keys, uint64_t n, bool key64, const CountTable& t, int sm_count,
                                      cudaStream_t st);
 cudaError_t launch_count_query(const void* keys, uint64_t n, bool key64, const CountTable& t, uint32_t max_count,
@@ -264,5 +264,29 @@ cudaError_t launch_count_partition_scatter(const SeqView& b, uint64_t total_byte
 cudaError_t launch_count_partition_by_region(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
                                              const CountTable& t, uint32_t nparts, int grid, unsigned long long* block_counts,
                                              unsigned long long* part_totals, void* out, cudaStream_t st);
+
+
+// ---- two-phase insertion / fused exchange (kmu_count_part.cu) ---------------------------------
+// bucket of a key = owner * nregions + region; owner = intNN_hash(key) % nowners (DispatchableT::dispatch,
+// kmercount.rs:382-420), region = (fmix64(key) & capmask) >> shift = the slice of the owner's table the key hashes to.
+// Bucket (o, r) is appended to the slab at dests[o] + (r * nsend + self) * slab_cap (elements).
+struct PartGeom {
+    uint32_t nowners;   // >= 1
+    uint32_t nregions;  // power of two; nowners * nregions <= 4096
+    uint64_t capmask;   // capacity - 1 of an owner's table (all owners use the same capacity)
+    uint32_t shift;     // log2(slots per region)
+    uint32_t nsend, self;
+    uint64_t slab_cap;  // keys per slab (< 2^32)
+};
+size_t count_part_smem_bytes(bool key64, uint32_t nbuckets);
+cudaError_t launch_count_part_seqs(const SeqView& b, uint64_t byte_begin, uint64_t byte_end, uint64_t total_bytes, uint32_t k,
+                                   bool key64, bool canonical, const PartGeom& g, void* const* dests,
+                                   unsigned long long* cursors, unsigned long long* flag, int sm_count, cudaStream_t st);
+cudaError_t launch_count_part_keys(const void* keys, uint64_t nkeys, bool key64, const PartGeom& g, void* const* dests,
+                                   unsigned long long* cursors, unsigned long long* flag, int sm_count, cudaStream_t st);
+cudaError_t launch_count_insert_slabs(const void* slabs, uint64_t slab_cap, uint32_t nregions, uint32_t nsend,
+                                      const unsigned long long* counts, const CountTable& t, bool key64, uint32_t shift,
+                                      const unsigned long long* skip_flag, bool prefetch, unsigned int* done, int sm_count,
+                                      cudaStream_t st);
 
 }  // namespace kmu

@@ -149,16 +149,21 @@ class P2PExchange:
         self.peer_ptrs = [None] * self.world
         self.peer_gen = [-1] * self.world
 
-    def ensure(self, recv_bytes):
+    def ensure(self, recv_bytes, symmetric=False):
         """Collective.  Makes this rank's receive buffer at least recv_bytes large and (re)maps every peer buffer that
-        changed.  -> list of `world` device pointers valid in this process (own buffer at index rank)."""
+        changed.  -> list of `world` device pointers valid in this process (own buffer at index rank).
+        symmetric=True: every rank asks for the same size in the same call, so a rank whose buffer is large enough
+        knows that all are and returns without any collective."""
+        if symmetric and self.local_ptr is not None and recv_bytes <= self.local_bytes and all(
+                p is not None for p in self.peer_ptrs):
+            return list(self.peer_ptrs)
         if self.local_ptr is None or recv_bytes > self.local_bytes:
             if self.local_ptr is not None:
                 # peers still map the old buffer: they drop it below, after the barrier implied by the gather
                 old = self.local_ptr
             else:
                 old = None
-            size = max(int(recv_bytes * 1.25), 1 << 20)
+            size = max(int(recv_bytes) if symmetric else int(recv_bytes * 1.25), 1 << 20)
             self.local_ptr, self.local_handle = self.engine.ipc_alloc(size)
             self.local_bytes = size
             self.generation += 1
@@ -222,6 +227,48 @@ def count_sharded_p2p(engine, batch, k, kmer_type, counter, xchg, canonical=True
     if world > 1:
         dist.barrier(group=group)  # the buffers may be overwritten by the next round
     return recv_total
+
+
+def exchange_slab_cap(nk_max_per_rank, world, nregions):
+    """Keys per slab for a round in which no rank sends more than nk_max_per_rank k-mers: the expected share of a
+    (sender, owner, region) bucket + 8 sigma + slack."""
+    mean = nk_max_per_rank / float(world * nregions)
+    return int(mean + 8.0 * mean ** 0.5 + 1024)
+
+
+def count_round_fused(engine, batch, counter, xchg, nk_bound, canonical=True, group=None):
+    """One round of multi-GPU counting with the fused exchange (kmu_count_exchange_scatter): a single kernel per rank
+    extracts the canonical k-mers, buckets them by (owner = intNN_hash % world, region of the owner's table) and stores
+    them into the owners' receive buffers over NVLink; the ranks then share their bucket counts (a few KB) and every rank
+    inserts its buffer region after region (kmu_count_insert_slabs).  `nk_bound`: no rank sends more k-mers than this in
+    a round (fixes the slab size; the same on every rank).  Every rank's `counter` was created with the same arguments.
+    -> (keys received, bytes sent to peers)"""
+    import kmerutils_b200 as kb
+
+    rank, world = _world(group)
+    esz = 8 if kb.val_dtype(counter.kmer_type) == np.uint64 else 4
+    nreg = counter.exchange_regions(world)
+    slab_cap = exchange_slab_cap(nk_bound, world, nreg)
+    dests = xchg.ensure(nreg * world * slab_cap * esz, symmetric=True)
+    sent, overflowed = counter.exchange_scatter(batch, world, rank, slab_cap, dests, canonical)  # returns when the kernel is done
+    if world > 1:
+        dev = torch.device("cuda", engine.device)
+        mine = torch.from_numpy(np.append(sent.reshape(-1).astype(np.int64), int(overflowed))).to(dev)
+        allc = torch.empty((world, mine.numel()), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine, group=group)  # also the barrier: every sender's stores have landed
+        allc = allc.cpu().numpy()
+        bad = bool(allc[:, -1].any())
+        counts = allc[:, :-1].reshape(world, world, nreg)[:, rank, :]
+    else:
+        bad = overflowed
+        counts = sent.reshape(1, 1, nreg)[:, 0, :]
+    if bad:
+        raise RuntimeError("count_round_fused: a slab overflowed (one k-mer repeated millions of times?); use count_sharded")
+    counter.insert_slabs(xchg.local_ptr, slab_cap, counts.astype(np.uint64))
+    if world > 1:
+        dist.barrier(group=group)  # the buffers may be overwritten by the next round
+    sent_peer = int(sent.sum() - sent[rank].sum()) * esz
+    return int(counts.sum()), sent_peer
 
 
 def merge_pmh3a_registers(hbits, keys, device, group=None):

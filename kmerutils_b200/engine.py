@@ -473,6 +473,29 @@ class KmerCounter:
         a = np.ascontiguousarray(kmers, dtype=self.dtype)
         check(self.engine.lib.kmu_count_insert_kmers(self.engine.ctx, self._h, _p(a), len(a), 0))
 
+    def exchange_regions(self, nowners):
+        """Regions this table is cut into for an exchange among `nowners` ranks (kmu_count_exchange_geometry)."""
+        n = C.c_uint32()
+        check(self.engine.lib.kmu_count_exchange_geometry(self._h, int(nowners), C.byref(n)))
+        return int(n.value)
+
+    def exchange_scatter(self, batch, nowners, self_rank, slab_cap, dests, canonical=True):
+        """ONE kernel: canonical k-mers of `batch` bucketed by (owner, table region) and stored straight into the owners'
+        receive buffers `dests` (device pointers, peers over NVLink).  -> (sent_counts[nowners, nregions], overflowed)"""
+        nreg = self.exchange_regions(nowners)
+        ptrs = (C.c_void_p * nowners)(*[int(d) for d in dests])
+        sent = np.zeros(nowners * nreg, dtype=np.uint64)
+        ovf = C.c_int32()
+        check(self.engine.lib.kmu_count_exchange_scatter(self.engine.ctx, batch.handle, self._h, int(bool(canonical)), int(nowners),
+                                                         int(self_rank), int(slab_cap), ptrs, _p(sent, u64p), C.byref(ovf)))
+        return sent.reshape(nowners, nreg), bool(ovf.value)
+
+    def insert_slabs(self, slabs_ptr, slab_cap, counts):
+        """Insert a receive buffer of [region][sender] slabs; counts[sender, region] keys each (kmu_count_insert_slabs)."""
+        cnt = np.ascontiguousarray(counts, dtype=np.uint64)
+        check(self.engine.lib.kmu_count_insert_slabs(self.engine.ctx, self._h, C.c_void_p(int(slabs_ptr)), int(slab_cap),
+                                                     int(cnt.shape[0]), _p(cnt.reshape(-1), u64p)))
+
     def get_count(self, kmers):
         a = np.ascontiguousarray(kmers, dtype=self.dtype)
         out = np.zeros(len(a), dtype=np.uint32)

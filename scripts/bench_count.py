@@ -23,7 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads", type=int, default=8_000_000)
     ap.add_argument("--rounds", type=int, default=3)
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--exchange", default="fused", choices=["fused", "p2p", "nccl"])
     ap.add_argument("--genome", type=int, default=100_000_000)
     args = ap.parse_args()
     import torch
@@ -40,7 +40,7 @@ def main():
     # distinct k-mers this rank will own over all rounds: genome k-mers / world + the error k-mers it receives
     cap = int(args.genome / world * 1.1 + args.rounds * nk_round * 0.22)
     counter = eng.counter(k, kb.KMER64, capacity=cap)
-    xchg = kd.P2PExchange(eng) if args.exchange == "p2p" else None
+    xchg = kd.P2PExchange(eng) if args.exchange in ("p2p", "fused") else None
     send = torch.empty(nk_round, dtype=torch.int64, device=dev) if args.exchange == "nccl" else None
     t_part = t_xchg = t_ins = 0.0
     sent_bytes = 0
@@ -67,6 +67,11 @@ def main():
             a = time.perf_counter()
             counter.insert_seqs(reads, canonical=True)
             t_ins += time.perf_counter() - a
+        elif args.exchange == "fused":
+            a = time.perf_counter()
+            _, sent = kd.count_round_fused(eng, reads, counter, xchg, nk_round)
+            t_ins += time.perf_counter() - a
+            sent_bytes += sent
         elif args.exchange == "p2p":
             a = time.perf_counter()
             counts = eng.count_partition_counts(reads, k, kb.KMER64, world, True)

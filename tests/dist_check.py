@@ -41,6 +41,18 @@ def main():
         part.destroy()
     st2 = counter2.stats()
     tot2 = kd.allreduce_sum([st2["nb_distinct"], st2["nb_unique"], st2["nb_inserted"]], torch.device("cuda", local))
+    # fused exchange, one walk: (owner, table region) buckets stored into the peers' slabs, regioned insertion
+    # (small regions so that this small table is cut into many)
+    os.environ["KMU_COUNT_REGION_KB"] = "64"
+    counter3 = eng.counter(k, kb.KMER64, int(nreads * 150 * 1.2 / world) + 1024)
+    nk_bound = (nreads - (world - 1) * per) * (150 - k + 1)
+    for lo, hi in ((0, nloc // 2), (nloc // 2, nloc)):
+        part = eng.batch_slices(mine, idx[lo:hi], np.zeros(hi - lo, np.uint64), np.full(hi - lo, 150, np.uint64))
+        kd.count_round_fused(eng, part, counter3, xchg, nk_bound)
+        part.destroy()
+    os.environ.pop("KMU_COUNT_REGION_KB")
+    st3 = counter3.stats()
+    tot3 = kd.allreduce_sum([st3["nb_distinct"], st3["nb_unique"], st3["nb_inserted"]], torch.device("cuda", local))
     hll_local = eng.sketch_setsketch(mine, 21, kb.KMER64, kb.HASH_CANON_INVHASH, (1.001, 256, 20.0, 65534), np.uint16, whole=True)
     hll = kd.merge_registers(torch.from_numpy(hll_local.astype(np.int32)).cuda(), "max").cpu().numpy().astype(np.uint16)
     smh_local = eng.sketch_superminhash(mine, 21, kb.KMER64, kb.HASH_CANON_INVHASH, 256).min(axis=0)
@@ -68,6 +80,8 @@ def main():
         print(f"[dist_check] world={world} counting stats {got} want {want}", flush=True)
         ok &= tuple(tot2) == want
         print(f"[dist_check] peer-to-peer exchange (no data-path collective) stats {tuple(tot2)} ok={tuple(tot2) == want}", flush=True)
+        ok &= tuple(tot3) == want
+        print(f"[dist_check] fused one-walk exchange + regioned insertion stats {tuple(tot3)} ok={tuple(tot3) == want}", flush=True)
         want_hll = orc.sketch_setsketch_seqs(buf, off, nb, 21, kb.KMER64, kb.HASH_CANON_INVHASH, (1.001, 256, 20.0, 65534))
         ok &= bool(np.array_equal(hll, want_hll))
         want_smh = orc.sketch_superminhash_seqs(buf, off, nb, 21, kb.KMER64, kb.HASH_CANON_INVHASH, 256)
@@ -94,6 +108,7 @@ def main():
     dist.broadcast(flag, src=0)
     counter.destroy()
     counter2.destroy()
+    counter3.destroy()
     xchg.close()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)

@@ -163,26 +163,26 @@ def test_sample_reads_and_sharded_count_single_rank(engine, oracle):
 
 
 def test_count_two_phase_large_table(engine, oracle, monkeypatch):
-    # optional two-phase insertion into a table far larger than L2 (k-mers grouped by table region first):
-    # same table as the direct path
+    # a table far larger than L2 takes a large batch in two phases by default (k-mers grouped by table region first,
+    # kmu_count_part.cu); KMU_COUNT_DIRECT=1 forces direct insertion: same table either way
     glen = 300_000
     genome = engine.batch_synth(9, np.array([glen], dtype=np.uint64))
     reads = engine.batch_sample_reads(genome, 9, 0, 40_000, 150, 5000)
     packed, off, nb = reads.download()
     keys, cnts = oracle.count_kmers(packed, off, nb, 31, kb.KMER64, True)
     sel = slice(None, None, 7)
-    ctr2 = engine.counter(31, kb.KMER64, capacity=9_000_000)
-    ctr2.insert_seqs(reads, canonical=True)
-    assert engine.last_times()["launches"] == 1  # direct path (default)
-    assert ctr2.stats()["nb_distinct"] == len(keys)
-    monkeypatch.setenv("KMU_COUNT_TWO_PHASE", "1")
     ctr = engine.counter(31, kb.KMER64, capacity=9_000_000)
     assert ctr.capacity() * 16 >= 256 << 20
     ctr.insert_seqs(reads, canonical=True)
-    assert engine.last_times()["launches"] == 6  # two-phase path
+    assert engine.last_times()["launches"] == 2  # partition + regioned insertion
     st = ctr.stats()
     assert (st["nb_distinct"], st["nb_unique"], st["nb_inserted"]) == (len(keys), int((cnts == 1).sum()), int(cnts.sum()))
     assert np.array_equal(ctr.get_count(keys[sel]), np.minimum(cnts[sel], 255).astype(np.uint32))
+    monkeypatch.setenv("KMU_COUNT_DIRECT", "1")
+    ctr2 = engine.counter(31, kb.KMER64, capacity=9_000_000)
+    ctr2.insert_seqs(reads, canonical=True)
+    assert engine.last_times()["launches"] == 1  # direct path
+    assert ctr2.stats()["nb_distinct"] == len(keys)
     assert np.array_equal(ctr2.get_count(keys[sel]), ctr.get_count(keys[sel]))
     ctr.destroy()
     ctr2.destroy()

@@ -1,0 +1,140 @@
+"""Two-phase insertion (partition by table region + regioned insertion, kmu_count_part.cu) against the oracle's exact
+multiset counts and against direct insertion: same table contents whatever the path.  The environment knobs
+KMU_COUNT_REGION_KB / KMU_COUNT_TWO_PHASE_MIN_KEYS push small tables through the regioned path (many regions, several
+chunks, the slab-overflow fallback)."""
+import os
+
+import numpy as np
+import pytest
+
+import kmerutils_b200 as kb
+from test_count_gpu import genome_reads
+
+pytestmark = pytest.mark.gpu
+
+
+class knobs:
+    def __init__(self, **kw):
+        self.kw = {k: str(v) for k, v in kw.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kw}
+        os.environ.update(self.kw)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def table_contents(ctr):
+    k, c = ctr.export(min_count=1)
+    o = np.argsort(k, kind="stable")
+    return k[o], c[o]
+
+
+@pytest.mark.parametrize("k,ktype,region_kb", [(31, kb.KMER64, 64), (21, kb.KMER64, 16), (16, kb.KMER16B32, 32),
+                                               (12, kb.KMER32, 16), (32, kb.KMER64, 64)])
+def test_two_phase_matches_oracle_and_direct(engine, oracle, k, ktype, region_kb):
+    rng = np.random.default_rng(100 + k)
+    reads = genome_reads(oracle, 60 + k, 30000, 3000, 150, rng)
+    reads += [b"ACGT" * 3, b"ACGTTGCA" * 40, b"C", oracle.synth_ascii(9, 0, 70000)]  # short, periodic, one long sequence
+    batch, _ = engine.batch_from_ascii(reads)
+    packed, off, nb = batch.download()
+    keys, cnts = oracle.count_kmers(packed, off, nb, k, ktype, True)
+    with knobs(KMU_COUNT_REGION_KB=region_kb, KMU_COUNT_TWO_PHASE_MIN_KEYS=1):
+        ctr = engine.counter(k, ktype, capacity=max(len(keys), 1 << 16), count_bits=8)
+        l0 = engine.launch_count()
+        ctr.insert_seqs(batch, canonical=True)
+        assert engine.launch_count() - l0 >= 2  # partition + regioned insertion, not the direct kernel
+        st = ctr.stats()
+        assert st["nb_distinct"] == len(keys)
+        assert st["nb_unique"] == int((cnts == 1).sum())
+        assert st["nb_inserted"] == int(cnts.sum()) == batch.kmer_count(k)
+        assert np.array_equal(ctr.get_count(keys), np.minimum(cnts, 255).astype(np.uint32))
+        # a second batch on top (key array form): every count doubles
+        allk, _ = engine.generate_kmers(batch, k, ktype, kb.HASH_CANON_RAW)
+        if ktype == kb.KMER32:
+            allk = allk & np.uint32(0x0FFFFFFF)  # the table is keyed by get_compressed_value() (kmer32bit.rs:173-178)
+        ctr.insert_kmers(allk)
+        assert np.array_equal(ctr.get_count(keys), np.minimum(2 * cnts, 255).astype(np.uint32))
+        two = table_contents(ctr)
+        ctr.destroy()
+    with knobs(KMU_COUNT_DIRECT=1):
+        ctr = engine.counter(k, ktype, capacity=max(len(keys), 1 << 16), count_bits=8)
+        l0 = engine.launch_count()
+        ctr.insert_seqs(batch, canonical=True)
+        assert engine.launch_count() - l0 == 1
+        ctr.insert_kmers(allk)
+        direct = table_contents(ctr)
+        ctr.destroy()
+    assert np.array_equal(two[0], direct[0]) and np.array_equal(two[1], direct[1])
+    batch.destroy()
+
+
+def test_two_phase_chunks_and_overflow_fallback(engine, oracle):
+    """Several chunks (tiny slab budget) and a batch whose k-mers all fall into one bucket (a homopolymer run): the
+    slab of that bucket overflows, the chunk is redone by direct insertion, the counts stay exact."""
+    k, ktype = 31, kb.KMER64
+    rng = np.random.default_rng(7)
+    reads = genome_reads(oracle, 77, 50000, 4000, 150, rng) + [b"A" * 300000, b"ACGT" * 20000]
+    batch, _ = engine.batch_from_ascii(reads)
+    packed, off, nb = batch.download()
+    keys, cnts = oracle.count_kmers(packed, off, nb, k, ktype, True)
+    for slab_mb in (2, 64):
+        with knobs(KMU_COUNT_REGION_KB=64, KMU_COUNT_TWO_PHASE_MIN_KEYS=1, KMU_COUNT_SLAB_MB=slab_mb):
+            ctr = engine.counter(k, ktype, capacity=1 << 17, count_bits=32)
+            ctr.insert_seqs(batch, canonical=True)
+            st = ctr.stats()
+            assert st["nb_distinct"] == len(keys) and st["nb_inserted"] == int(cnts.sum())
+            assert np.array_equal(ctr.get_count(keys).astype(np.uint64), cnts.astype(np.uint64))
+            ctr.destroy()
+    batch.destroy()
+
+
+def test_two_phase_default_geometry(engine):
+    """The default geometry (32 MB regions) on a table of 256 MB: 2 M reads-worth of random 31-mers, conservation of the
+    inserted k-mers and agreement with direct insertion on the table statistics."""
+    nb = np.full(20000, 150, dtype=np.uint64)
+    batch = engine.batch_synth(41, nb)
+    res = []
+    for direct in (False, True):
+        with knobs(**({"KMU_COUNT_DIRECT": 1} if direct else {})):
+            ctr = engine.counter(31, kb.KMER64, capacity=8_000_000, count_bits=8)  # 2^24 slots * 16 B = 256 MB
+            for _ in range(2):
+                ctr.insert_seqs(batch, canonical=True)
+            st = ctr.stats()
+            res.append((st["nb_distinct"], st["nb_unique"], st["nb_inserted"], st["hist"].tolist()))
+            ctr.destroy()
+    assert res[0] == res[1]
+    assert res[0][2] == 2 * batch.kmer_count(31)
+    batch.destroy()
+
+
+def test_exchange_scatter_single_rank(engine, oracle):
+    """The fused exchange kernel with one owner writing into its own buffer, then the slab insertion: the path every
+    rank runs in a multi-GPU round (tests/dist_check.py covers two ranks)."""
+    import torch
+    k, ktype = 31, kb.KMER64
+    rng = np.random.default_rng(3)
+    reads = genome_reads(oracle, 12, 40000, 5000, 150, rng)
+    batch, _ = engine.batch_from_ascii(reads)
+    packed, off, nb = batch.download()
+    keys, cnts = oracle.count_kmers(packed, off, nb, k, ktype, True)
+    with knobs(KMU_COUNT_REGION_KB=64):
+        ctr = engine.counter(k, ktype, capacity=1 << 18, count_bits=8)
+        nreg = ctr.exchange_regions(1)
+        assert nreg > 1
+        from kmerutils_b200.dist import exchange_slab_cap
+        slab_cap = exchange_slab_cap(batch.kmer_count(k), 1, nreg)
+        buf = torch.empty(nreg * slab_cap, dtype=torch.int64, device="cuda:0")
+        sent, ovf = ctr.exchange_scatter(batch, 1, 0, slab_cap, [buf.data_ptr()], True)
+        assert not ovf and int(sent.sum()) == batch.kmer_count(k)
+        ctr.insert_slabs(buf.data_ptr(), slab_cap, sent.reshape(1, nreg))
+        st = ctr.stats()
+        assert st["nb_distinct"] == len(keys) and st["nb_unique"] == int((cnts == 1).sum())
+        assert np.array_equal(ctr.get_count(keys), np.minimum(cnts, 255).astype(np.uint32))
+        ctr.destroy()
+    batch.destroy()
