@@ -165,6 +165,12 @@ def main():
     ap.add_argument("--profile", action="store_true", help="print the per-launch profile to stderr")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--configs", default="all",
+                    help="the other BASELINE shapes reported in `configs`: all | none | comma list of "
+                         "extract,c2strong,c1,c3,c4,c5a,c5b")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="C3 at N > 1: fused = one kernel buckets and stores into the peers over NVLink; nccl = partition + all-to-all")
+    ap.add_argument("--c3-reads", type=int, default=26_666_667, help="C3: reads of 150 b per GPU per step (default 4 Gbases)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -255,18 +261,21 @@ def main():
         # algorithmic bytes of one launch: packed bases in (0.25 B/base) + signatures out (m * 4 B/read)
         alg_bytes = dom["nbases"] * 0.25 + dom["nseq"] * M * 4
         achieved = alg_bytes / (dom["ms"] * 1e-3) / 1e9
-        # DRAM traffic of the same launch from the committed ncu --set full capture (profiles/r1_traffic.json);
-        # only quoted when the capture is of the launch measured here (same reads and bases)
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-                tr = json.load(f)
-            if tr["launch_reads"] == dom["nseq"] and tr["launch_bases"] == dom["nbases"]:
-                traffic = tr["dram_bytes_per_launch"]
-        except Exception:
-            pass
+        # DRAM traffic is NOT measured in this run (ncu is not running): `traffic` stays null; the figure of the committed
+        # ncu --set full capture of the same launch (same reads and bases) is quoted apart, labelled as such
+        precaptured = None
+        for name in ("r2_traffic.json", "r1_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", name)) as f:
+                    tr = json.load(f)
+                if tr["launch_reads"] == dom["nseq"] and tr["launch_bases"] == dom["nbases"]:
+                    precaptured = {"dram_bytes_per_launch": tr["dram_bytes_per_launch"], "source": "profiles/" + name,
+                                   "note": "ncu --set full capture committed with the repo, not measured in this run"}
+                    break
+            except Exception:
+                pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)",
+                    "traffic": None, "traffic_precaptured": precaptured,
                     "algorithmic_bytes": alg_bytes, "peak_kind": peak_kind,
                     "kernel": ("pmh3a_direct_kernel (one pass, %d threads per read)" % dom["block"] if dom["mode"] == 2 else
                                "pmh3a_sketch_kernel<u32,%s> team_warps=%d" % ("hist" if dom["mode"] == 0 else "table", dom["team_warps"])),
@@ -293,7 +302,7 @@ def main():
         e2e_step()
         barrier()
         t0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 3))
+        n_e2e = max(1, args.steps)
         for _ in range(n_e2e):
             e2e_step()
         barrier()
@@ -311,6 +320,52 @@ def main():
         # the signatures the host got must be the ones left in HBM by the device-resident path
         if not torch.equal(pin_out, sig_dev.cpu()):
             raise SystemExit("e2e signatures differ from the device-resident run")
+
+    # ---- a step on a FRESH batch: includes the per-batch build of the processing order that later steps reuse ------
+    eng.sync()
+    fresh = eng.batch_synth(seed, nbases)
+    ev0.record(ext)
+    eng.sketch_pmh3a(fresh, K, KMER_TYPE, HASH_KIND, M, out_device_ptr=sig_dev.data_ptr())
+    ev1.record(ext)
+    barrier()
+    fresh_ms = ev0.elapsed_time(ev1)
+    fresh.destroy()
+
+    # ---- the other BASELINE shapes -----------------------------------------------------------------------------
+    configs = []
+    want = set(("extract,c2strong,c1,c3,c4,c5a,c5b" if args.configs == "all" else args.configs).split(",")) - {"none", ""}
+    if want:
+        from kmerutils_b200 import benchcfg
+        T = benchcfg.Timer(eng, local_rank, world)
+
+        def guarded(name, fn):
+            try:
+                r = fn()
+                configs.extend(r if isinstance(r, list) else [r])
+            except Exception as exc:  # a failed shape must not take the headline line with it
+                configs.append({"workload": name, "error": f"{type(exc).__name__}: {exc}"})
+                if world > 1:
+                    raise
+            torch.cuda.empty_cache()
+
+        if "extract" in want:
+            guarded("extract", lambda: benchcfg.run_extract(kb, eng, T, rank, world, args.steps, args.warmup, peak, batch, total_bases))
+    batch.destroy()
+    del sig_dev
+    torch.cuda.empty_cache()
+    if want:
+        if "c2strong" in want and world > 1:
+            guarded("c2strong", lambda: benchcfg.run_c2_strong(kb, eng, T, rank, world, args.steps, args.warmup, peak))
+        if "c1" in want:
+            guarded("c1", lambda: benchcfg.run_c1(kb, eng, T, rank, world, args.steps, args.warmup, peak))
+        if "c3" in want:
+            guarded("c3", lambda: benchcfg.run_c3(kb, eng, T, rank, world, args.steps, args.warmup, peak, args.c3_reads, args.exchange))
+        if "c4" in want:
+            guarded("c4", lambda: benchcfg.run_c4(kb, eng, T, rank, world, args.steps, args.warmup, peak))
+        if "c5a" in want:
+            guarded("c5a", lambda: benchcfg.run_c5a(kb, eng, T, rank, world, args.steps, args.warmup, peak))
+        if "c5b" in want:
+            guarded("c5b", lambda: benchcfg.run_c5b(kb, eng, T, rank, world, args.steps, args.warmup, peak))
 
     # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample ----------------------
     cpu = None
@@ -331,6 +386,8 @@ def main():
                        "bases_per_gpu": total_bases, "l2": "inputs (1.1 GB packed) larger than L2, no flush needed",
                        "parallelism": f"reads sharded, {world} independent shard(s), no collective"},
             "kernel_ms_per_step": float(np.mean(kernel_ms)),
+            "fresh_batch_step_ms": fresh_ms,
+            "configs": configs,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "published_reference": {"value": 0.0859, "unit": "Gbases/s", "hardware": "8-core i7 laptop",
                                     "source": "README.md:45"},
@@ -338,7 +395,6 @@ def main():
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
-    batch.destroy()
     eng.close()
 
 

@@ -83,10 +83,12 @@ RegionGeom region_geometry(uint64_t capacity, bool key64, uint32_t nowners) {
     return g;
 }
 
-// slab capacity for `n` keys spread over `nbuckets` by a hash: the expected share + 8 sigma + slack
+// slab capacity for `n` keys spread over `nbuckets` by a hash: the expected share + 64 sqrt(share) + slack.  The keys
+// are k-mer OCCURRENCES: a key seen c times puts c entries into one bucket, so the spread of a bucket is sqrt(c) times
+// that of distinct keys -- 64 sqrt(share) is 8 sigma at a mean multiplicity of 64 (the C3 shape has 10-40).
 uint64_t slab_capacity(uint64_t n, uint64_t nbuckets) {
     const double mean = (double)n / (double)nbuckets;
-    return (uint64_t)(mean + 8.0 * std::sqrt(mean) + 1024.0);
+    return (uint64_t)(mean + 64.0 * std::sqrt(mean) + 1024.0);
 }
 
 bool two_phase_wanted(const kmu_counter* c, uint64_t nkeys) {

@@ -231,12 +231,13 @@ def count_sharded_p2p(engine, batch, k, kmer_type, counter, xchg, canonical=True
 
 def exchange_slab_cap(nk_max_per_rank, world, nregions):
     """Keys per slab for a round in which no rank sends more than nk_max_per_rank k-mers: the expected share of a
-    (sender, owner, region) bucket + 8 sigma + slack."""
+    (sender, owner, region) bucket + 64 sqrt(share) + slack (8 sigma for k-mers repeated 64 times on average: a key seen
+    c times puts c entries into one bucket)."""
     mean = nk_max_per_rank / float(world * nregions)
-    return int(mean + 8.0 * mean ** 0.5 + 1024)
+    return int(mean + 64.0 * mean ** 0.5 + 1024)
 
 
-def count_round_fused(engine, batch, counter, xchg, nk_bound, canonical=True, group=None):
+def count_round_fused(engine, batch, counter, xchg, nk_bound, canonical=True, group=None, phases=None):
     """One round of multi-GPU counting with the fused exchange (kmu_count_exchange_scatter): a single kernel per rank
     extracts the canonical k-mers, buckets them by (owner = intNN_hash % world, region of the owner's table) and stores
     them into the owners' receive buffers over NVLink; the ranks then share their bucket counts (a few KB) and every rank
@@ -250,7 +251,11 @@ def count_round_fused(engine, batch, counter, xchg, nk_bound, canonical=True, gr
     nreg = counter.exchange_regions(world)
     slab_cap = exchange_slab_cap(nk_bound, world, nreg)
     dests = xchg.ensure(nreg * world * slab_cap * esz, symmetric=True)
+    import time as _time
     sent, overflowed = counter.exchange_scatter(batch, world, rank, slab_cap, dests, canonical)  # returns when the kernel is done
+    if phases is not None:
+        phases["scatter_ms"] = phases.get("scatter_ms", 0.0) + engine.last_times()["kernel_ms"]
+    t_share = _time.perf_counter()
     if world > 1:
         dev = torch.device("cuda", engine.device)
         mine = torch.from_numpy(np.append(sent.reshape(-1).astype(np.int64), int(overflowed))).to(dev)
@@ -264,7 +269,11 @@ def count_round_fused(engine, batch, counter, xchg, nk_bound, canonical=True, gr
         counts = sent.reshape(1, 1, nreg)[:, 0, :]
     if bad:
         raise RuntimeError("count_round_fused: a slab overflowed (one k-mer repeated millions of times?); use count_sharded")
+    if phases is not None:
+        phases["share_counts_ms"] = phases.get("share_counts_ms", 0.0) + (_time.perf_counter() - t_share) * 1e3
     counter.insert_slabs(xchg.local_ptr, slab_cap, counts.astype(np.uint64))
+    if phases is not None:
+        phases["insert_ms"] = phases.get("insert_ms", 0.0) + engine.last_times()["kernel_ms"]
     if world > 1:
         dist.barrier(group=group)  # the buffers may be overwritten by the next round
     sent_peer = int(sent.sum() - sent[rank].sum()) * esz
