@@ -157,7 +157,7 @@ void kmu_ctx_destroy(kmu_ctx* c) {
     ScopedDevice sd(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto* b : {&c->order, &c->counters, &c->table_scratch, &c->slot_scratch, &c->overflow, &c->sig_dev, &c->misc, &c->memo,
-                    &c->whole_table, &c->items_slots, &c->counters_alt, &c->overflow_alt, &c->smh_memo})
+                    &c->whole_table, &c->items_slots, &c->part_fine, &c->counters_alt, &c->overflow_alt, &c->smh_memo})
         b->release();
     c->pinned.release();
     c->pinned_small.release();

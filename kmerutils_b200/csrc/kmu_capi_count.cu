@@ -65,21 +65,53 @@ uint64_t region_bytes_setting() {
     return 32ull << 20;
 }
 
+// The table is cut into `nfine_total` regions of region_bytes_setting() (32 MB: they sit in L2 while they take their
+// updates).  The partition kernel is efficient up to a few hundred buckets per pass (a tile of 4096 k-mers sorted in shared
+// memory: with thousands of buckets every bucket gets one key per tile, i.e. one global atomic and one 8-byte store per
+// key -- measured 14.7 G keys/s at 4096 buckets against 77 G at 512), so large tables are partitioned in TWO levels:
+// level 1 (from the reads; across GPUs: owner x coarse region) makes ncoarse coarse regions per owner, level 2 cuts
+// each coarse slab into nfine fine regions just before they are inserted.
 struct RegionGeom {
-    uint32_t nregions = 1;
-    uint32_t shift = 0;  // log2(slots per region)
+    uint32_t ncoarse = 1;       // level-1 regions of an owner's table (== regions when nfine == 1)
+    uint32_t nfine = 1;         // level-2 regions per coarse region
+    uint32_t coarse_shift = 0;  // log2(slots per coarse region)
+    uint32_t fine_shift = 0;    // log2(slots per fine region)
+    uint32_t regions() const { return ncoarse * nfine; }
 };
+
+uint32_t level1_bucket_target() {
+    if (const char* e = std::getenv("KMU_COUNT_LEVEL1_BUCKETS")) {
+        const long v = std::atol(e);
+        if (v >= 1) return (uint32_t)v;
+    }
+    return 512;
+}
 
 RegionGeom region_geometry(uint64_t capacity, bool key64, uint32_t nowners) {
     const uint64_t slot_bytes = key64 ? 16 : 8;
     uint64_t region_slots = 1;
     while (region_slots * 2 * slot_bytes <= region_bytes_setting()) region_slots <<= 1;
-    const uint32_t max_regions = MAX_BUCKETS / (nowners ? nowners : 1);
-    while (capacity / region_slots > max_regions) region_slots <<= 1;
+    if (nowners < 1) nowners = 1;
+    uint64_t total = capacity > region_slots ? capacity / region_slots : 1;  // a power of two
+    while (total > 65536) {  // never more than 64 K regions: larger regions instead
+        total >>= 1;
+        region_slots <<= 1;
+    }
     RegionGeom g;
-    g.nregions = capacity > region_slots ? (uint32_t)(capacity / region_slots) : 1u;
-    if (g.nregions > 1)
-        while ((1ull << g.shift) < region_slots) ++g.shift;
+    uint64_t ncoarse = total, nfine = 1;
+    while (ncoarse > 1 && ncoarse * nowners > level1_bucket_target()) {
+        ncoarse >>= 1;
+        nfine <<= 1;
+    }
+    while (nfine > 1024) {  // level 2 too wide: give level 1 more buckets (MAX_BUCKETS bounds it)
+        nfine >>= 1;
+        ncoarse <<= 1;
+    }
+    g.ncoarse = (uint32_t)ncoarse;
+    g.nfine = (uint32_t)nfine;
+    while ((1ull << g.fine_shift) < region_slots) ++g.fine_shift;
+    g.coarse_shift = g.fine_shift;
+    while ((1ull << g.coarse_shift) < region_slots * nfine) ++g.coarse_shift;
     return g;
 }
 
@@ -108,8 +140,83 @@ uint64_t slab_budget_bytes(uint64_t held) {
     return std::min<uint64_t>(budget, ((uint64_t)free_b + held) / 2);
 }
 
-// scratch in ctx->counters: [0 .. MAX_BUCKETS) cursors, [MAX_BUCKETS .. +64) chunk flags, then one device pointer
-constexpr size_t PART_SCRATCH_WORDS = MAX_BUCKETS + 64 + 8 + 64 + MAX_BUCKETS / 2;  // ... 64 pointers, MAX_BUCKETS u32 `done` counters
+// scratch in ctx->counters (u64 words): [0, MAX_BUCKETS) level-1 cursors | 64 chunk flags | 8 (one device pointer) | 64 pointers
+// (exchange destinations) | 65536 level-2 cursors | 4096 level-2 flags (one per coarse region) | 65536 u32 `done` counters
+constexpr size_t OFF_FLAGS = MAX_BUCKETS, OFF_PTR = OFF_FLAGS + 64, OFF_DESTS = OFF_PTR + 8, OFF_CUR2 = OFF_DESTS + 64,
+                 OFF_FLAGS2 = OFF_CUR2 + 65536, OFF_DONE = OFF_FLAGS2 + 4096, PART_SCRATCH_WORDS = OFF_DONE + 65536 / 2 + 8;
+
+// Regioned insertion of level-1 slabs: slab (c, s) = keys of sender s for coarse region c at slabs + (c * nsend + s) * slab_cap,
+// counts_dev[s * ncoarse + c] keys each (device array).  nfine == 1: one launch over all regions.  Otherwise, per coarse
+// region: partition its slabs into nfine fine slabs (ctx->part_fine), insert those.  skip_flag (device, may be null): the
+// whole call does nothing when set.  A fine slab that overflows (flags2[c]) makes the host redo that coarse region directly.
+int32_t insert_level1_slabs(kmu_ctx* ctx, kmu_counter* c, const void* slabs, uint64_t slab_cap, uint32_t nsend,
+                            const unsigned long long* counts_dev, const RegionGeom& rg, const unsigned long long* skip_flag,
+                            uint64_t* launches) {
+    const size_t esz = c->key64 ? 8 : 4;
+    const bool prefetch = std::getenv("KMU_COUNT_NO_PREFETCH") == nullptr;
+    unsigned long long* scratch = (unsigned long long*)ctx->counters.p;
+    unsigned int* done = std::getenv("KMU_COUNT_FREE_RUNNING") ? nullptr : (unsigned int*)(scratch + OFF_DONE);
+    if (done) CUDA_TRY(cudaMemsetAsync(done, 0, sizeof(unsigned int) * rg.regions(), ctx->stream));
+    if (rg.nfine == 1) {
+        CUDA_TRY(kmu::launch_count_insert_slabs(slabs, slab_cap, rg.ncoarse, nsend, counts_dev, c->view(), c->key64, rg.fine_shift,
+                                                skip_flag, prefetch, done, ctx->sm_count, ctx->stream));
+        *launches += 1;
+        return KMU_OK;
+    }
+    unsigned long long* cur2 = scratch + OFF_CUR2;
+    unsigned long long* flags2 = scratch + OFF_FLAGS2;
+    void** d_fine = (void**)(scratch + OFF_PTR);
+    const uint64_t fine_cap = slab_capacity((uint64_t)nsend * slab_cap, rg.nfine);
+    if (fine_cap >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "partition slab too large");
+    CUDA_TRY(ctx->part_fine.reserve(fine_cap * rg.nfine * esz));
+    void* fine_ptr = ctx->part_fine.p;
+    CUDA_TRY(cudaMemcpyAsync(d_fine, &fine_ptr, sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(cur2, 0, sizeof(unsigned long long) * (65536 + 4096), ctx->stream));
+    kmu::PartGeom g{};
+    g.nowners = 1;
+    g.nregions = rg.nfine;
+    g.capmask = ((1ull << rg.coarse_shift) - 1);  // the fine region inside the coarse one
+    g.shift = rg.fine_shift;
+    g.nsend = 1;
+    g.self = 0;
+    g.slab_cap = fine_cap;
+    for (uint32_t cr = 0; cr < rg.ncoarse; ++cr) {
+        kmu::KeySegs segs;
+        segs.stride = slab_cap;
+        segs.nseg = nsend;
+        segs.counts = counts_dev + cr;
+        segs.count_stride = rg.ncoarse;
+        segs.skip_flag = skip_flag;
+        const uint8_t* base = (const uint8_t*)slabs + (uint64_t)cr * nsend * slab_cap * esz;
+        CUDA_TRY(kmu::launch_count_part_keys(base, slab_cap, segs, c->key64, g, d_fine, cur2 + (uint64_t)cr * rg.nfine, flags2 + cr,
+                                             ctx->sm_count, ctx->stream));
+        CUDA_TRY(kmu::launch_count_insert_slabs(fine_ptr, fine_cap, rg.nfine, 1, cur2 + (uint64_t)cr * rg.nfine, c->view(), c->key64,
+                                                rg.fine_shift, flags2 + cr, prefetch, done ? done + (uint64_t)cr * rg.nfine : nullptr,
+                                                ctx->sm_count, ctx->stream, cr * rg.nfine, rg.nfine));
+        *launches += 2;
+    }
+    // level-2 overflows (a key repeated millions of times inside one coarse region): those coarse regions go in directly
+    std::vector<unsigned long long> f2(rg.ncoarse), skip(1, 0);
+    CUDA_TRY(cudaMemcpyAsync(f2.data(), flags2, sizeof(unsigned long long) * rg.ncoarse, cudaMemcpyDeviceToHost, ctx->stream));
+    if (skip_flag) CUDA_TRY(cudaMemcpyAsync(skip.data(), skip_flag, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (skip[0]) return KMU_OK;
+    std::vector<unsigned long long> hc;
+    for (uint32_t cr = 0; cr < rg.ncoarse; ++cr) {
+        if (!f2[cr]) continue;
+        if (hc.empty()) {
+            hc.resize((size_t)nsend * rg.ncoarse);
+            CUDA_TRY(cudaMemcpy(hc.data(), counts_dev, sizeof(unsigned long long) * hc.size(), cudaMemcpyDeviceToHost));
+        }
+        for (uint32_t sd = 0; sd < nsend; ++sd) {
+            const uint64_t n = std::min<uint64_t>(hc[(size_t)sd * rg.ncoarse + cr], slab_cap);
+            const uint8_t* seg = (const uint8_t*)slabs + ((uint64_t)cr * nsend + sd) * slab_cap * esz;
+            CUDA_TRY(kmu::launch_count_insert_keys(seg, n, c->key64, c->view(), ctx->sm_count, ctx->stream));
+            *launches += 1;
+        }
+    }
+    return KMU_OK;
+}
 
 // insert the k-mers of the batch (src == nullptr) or the device key array `src` through partition + regioned insertion.
 // *launches is increased by the kernels launched.  Chunks whose partition overflowed a slab are redone directly.
@@ -118,13 +225,12 @@ int32_t insert_two_phase(kmu_ctx* ctx, kmu_counter* c, const kmu_seqbatch* b, bo
     const double t_in = now_ms();
     const size_t esz = c->key64 ? 8 : 4;
     const RegionGeom rg = region_geometry(c->capacity, c->key64, 1);
-    const bool prefetch = std::getenv("KMU_COUNT_NO_PREFETCH") == nullptr;
     // chunks: a bound of the k-mers of a chunk = 4 per packed byte (sequences) or the keys themselves
     const uint64_t unit_total = b ? b->packed_bytes : nsrc;          // bytes or keys
     const uint64_t keys_per_unit = b ? 4 : 1;
     // one chunk if its slabs fit the buffer already held (no query of the free memory on the hot path)
     uint64_t chunk_units = unit_total;
-    if (std::getenv("KMU_COUNT_SLAB_MB") || slab_capacity(unit_total * keys_per_unit, rg.nregions) * rg.nregions * esz > ctx->sig_dev.cap) {
+    if (std::getenv("KMU_COUNT_SLAB_MB") || slab_capacity(unit_total * keys_per_unit, rg.ncoarse) * rg.ncoarse * esz > ctx->sig_dev.cap) {
         const uint64_t budget = slab_budget_bytes(ctx->sig_dev.cap);
         chunk_units = std::max<uint64_t>(1, budget / (esz * keys_per_unit) * 9 / 10);
         if (b) chunk_units = std::max<uint64_t>(2048, chunk_units / 2048 * 2048);  // GROUP_BYTES of kmu_device.cuh
@@ -133,22 +239,21 @@ int32_t insert_two_phase(kmu_ctx* ctx, kmu_counter* c, const kmu_seqbatch* b, bo
     const uint64_t nchunks = (unit_total + chunk_units - 1) / chunk_units;
     if (nchunks > 64) return fail(KMU_ENOMEM, "not enough free device memory for the partition slabs (%llu chunks)", (unsigned long long)nchunks);
     const uint64_t bound = chunk_units * keys_per_unit;
-    const uint64_t slab_cap = slab_capacity(bound, rg.nregions);
+    const uint64_t slab_cap = slab_capacity(bound, rg.ncoarse);
     if (slab_cap >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "partition slab too large");
-    CUDA_TRY(ctx->sig_dev.reserve(slab_cap * rg.nregions * esz));
+    CUDA_TRY(ctx->sig_dev.reserve(slab_cap * rg.ncoarse * esz));
     CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * PART_SCRATCH_WORDS));
     unsigned long long* cursors = (unsigned long long*)ctx->counters.p;
-    unsigned long long* flags = cursors + MAX_BUCKETS;
-    void** d_dest = (void**)(flags + 64);
-    unsigned int* done = std::getenv("KMU_COUNT_FREE_RUNNING") ? nullptr : (unsigned int*)(flags + 64 + 8 + 64);
+    unsigned long long* flags = cursors + OFF_FLAGS;
+    void** d_dest = (void**)(cursors + OFF_DESTS);
     void* slab_ptr = ctx->sig_dev.p;
     CUDA_TRY(cudaMemcpyAsync(d_dest, &slab_ptr, sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(unsigned long long) * 64, ctx->stream));
     kmu::PartGeom g{};
     g.nowners = 1;
-    g.nregions = rg.nregions;
+    g.nregions = rg.ncoarse;
     g.capmask = c->capacity - 1;
-    g.shift = rg.shift;
+    g.shift = rg.coarse_shift;
     g.nsend = 1;
     g.self = 0;
     g.slab_cap = slab_cap;
@@ -160,31 +265,29 @@ int32_t insert_two_phase(kmu_ctx* ctx, kmu_counter* c, const kmu_seqbatch* b, bo
         for (auto& e : tev) cudaEventCreate(&e);
     for (uint64_t ch = 0; ch < nchunks; ++ch) {
         const uint64_t u0 = ch * chunk_units, u1 = std::min(unit_total, u0 + chunk_units);
-        CUDA_TRY(cudaMemsetAsync(cursors, 0, sizeof(unsigned long long) * rg.nregions, ctx->stream));
-        if (done) CUDA_TRY(cudaMemsetAsync(done, 0, sizeof(unsigned int) * rg.nregions, ctx->stream));
-        if (timing) {
-            cudaEventRecord(tev[0], ctx->stream);
-            std::fprintf(stderr, "[kmu count] chunk %llu: %.2f ms of host time before the first launch\n", (unsigned long long)ch, now_ms() - t_in);
-        }
+        CUDA_TRY(cudaMemsetAsync(cursors, 0, sizeof(unsigned long long) * rg.ncoarse, ctx->stream));
+        if (timing) cudaEventRecord(tev[0], ctx->stream);
         if (b)
             CUDA_TRY(kmu::launch_count_part_seqs(v, u0, u1, b->packed_bytes, c->k, c->key64, canonical, g, d_dest, cursors, flags + ch,
                                                  ctx->sm_count, ctx->stream));
         else
-            CUDA_TRY(kmu::launch_count_part_keys((const uint8_t*)src + u0 * esz, u1 - u0, c->key64, g, d_dest, cursors, flags + ch,
-                                                 ctx->sm_count, ctx->stream));
+            CUDA_TRY(kmu::launch_count_part_keys((const uint8_t*)src + u0 * esz, u1 - u0, kmu::KeySegs{}, c->key64, g, d_dest, cursors,
+                                                 flags + ch, ctx->sm_count, ctx->stream));
+        *launches += 1;
         if (timing) cudaEventRecord(tev[1], ctx->stream);
-        CUDA_TRY(kmu::launch_count_insert_slabs(slab_ptr, slab_cap, rg.nregions, 1, cursors, c->view(), c->key64, rg.shift, flags + ch,
-                                                prefetch, done, ctx->sm_count, ctx->stream));
-        *launches += 2;
+        int32_t rc = insert_level1_slabs(ctx, c, slab_ptr, slab_cap, 1, cursors, rg, flags + ch, launches);
+        if (rc) return rc;
         if (timing) {
             cudaEventRecord(tev[2], ctx->stream);
             cudaEventSynchronize(tev[2]);
             float a = 0, bms = 0;
             cudaEventElapsedTime(&a, tev[0], tev[1]);
             cudaEventElapsedTime(&bms, tev[1], tev[2]);
-            std::fprintf(stderr, "[kmu count] chunk %llu/%llu: %u regions of %llu KB, slab_cap %llu, partition %.2f ms, insert %.2f ms\n",
-                         (unsigned long long)ch, (unsigned long long)nchunks, rg.nregions,
-                         (unsigned long long)(((c->key64 ? 16ull : 8ull) << rg.shift) >> 10), (unsigned long long)slab_cap, a, bms);
+            std::fprintf(stderr, "[kmu count] chunk %llu/%llu: %u x %u regions of %llu KB, slab_cap %llu, level-1 partition %.2f ms, "
+                                 "level-2 partition + insertion %.2f ms (host %.2f ms so far)\n",
+                         (unsigned long long)ch, (unsigned long long)nchunks, rg.ncoarse, rg.nfine,
+                         (unsigned long long)(((c->key64 ? 16ull : 8ull) << rg.fine_shift) >> 10), (unsigned long long)slab_cap, a, bms,
+                         now_ms() - t_in);
         }
     }
     if (timing)
@@ -598,7 +701,7 @@ int32_t kmu_count_partition_scatter(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_
 // rank is nregions * nowners slabs of slab_cap keys: slab (r, s) holds what sender s found for region r of the table.
 int32_t kmu_count_exchange_geometry(const kmu_counter* c, uint32_t nowners, uint32_t* nregions) {
     if (!c || !nregions || nowners < 1 || nowners > 64) return fail(KMU_EINVAL, "bad argument");
-    *nregions = region_geometry(c->capacity, c->key64, nowners).nregions;
+    *nregions = region_geometry(c->capacity, c->key64, nowners).ncoarse;
     return KMU_OK;
 }
 
@@ -613,18 +716,19 @@ int32_t kmu_count_exchange_scatter(kmu_ctx* ctx, const kmu_seqbatch* b, const km
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};
     const RegionGeom rg = region_geometry(c->capacity, c->key64, nowners);
-    const uint32_t nb = nowners * rg.nregions;
+    const uint32_t nb = nowners * rg.ncoarse;
+    if (nb > MAX_BUCKETS) return fail(KMU_EINVAL, "too many (owner, region) buckets: %u", nb);
     CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * PART_SCRATCH_WORDS));
     unsigned long long* cursors = (unsigned long long*)ctx->counters.p;
-    unsigned long long* flags = cursors + MAX_BUCKETS;
-    void** d_dests = (void**)(flags + 64 + 8);
+    unsigned long long* flags = cursors + OFF_FLAGS;
+    void** d_dests = (void**)(cursors + OFF_DESTS);
     CUDA_TRY(cudaMemcpyAsync(d_dests, dests, sizeof(void*) * nowners, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(cursors, 0, sizeof(unsigned long long) * (MAX_BUCKETS + 64), ctx->stream));
     kmu::PartGeom g{};
     g.nowners = nowners;
-    g.nregions = rg.nregions;
+    g.nregions = rg.ncoarse;
     g.capmask = c->capacity - 1;
-    g.shift = rg.shift;
+    g.shift = rg.coarse_shift;
     g.nsend = nowners;
     g.self = self;
     g.slab_cap = slab_cap;
@@ -655,23 +759,22 @@ int32_t kmu_count_insert_slabs(kmu_ctx* ctx, kmu_counter* c, const void* slabs, 
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};
     const RegionGeom rg = region_geometry(c->capacity, c->key64, nsend);
-    const size_t n = (size_t)nsend * rg.nregions;
+    const size_t n = (size_t)nsend * rg.ncoarse;
     uint64_t total = 0;
     for (size_t i = 0; i < n; ++i) {
         if (counts[i] > slab_cap) return fail(KMU_EOVERFLOW, "a slab holds %llu keys, capacity %llu", (unsigned long long)counts[i], (unsigned long long)slab_cap);
         total += counts[i];
     }
-    CUDA_TRY(ctx->misc.reserve(sizeof(unsigned long long) * n + sizeof(unsigned int) * rg.nregions));
+    CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * PART_SCRATCH_WORDS));
+    CUDA_TRY(ctx->misc.reserve(sizeof(unsigned long long) * n));
     CUDA_TRY(cudaMemcpyAsync(ctx->misc.p, counts, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, ctx->stream));
-    unsigned int* done = (unsigned int*)((unsigned long long*)ctx->misc.p + n);
-    CUDA_TRY(cudaMemsetAsync(done, 0, sizeof(unsigned int) * rg.nregions, ctx->stream));
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    CUDA_TRY(kmu::launch_count_insert_slabs(slabs, slab_cap, rg.nregions, nsend, (const unsigned long long*)ctx->misc.p, c->view(),
-                                            c->key64, rg.shift, nullptr, std::getenv("KMU_COUNT_NO_PREFETCH") == nullptr, done,
-                                            ctx->sm_count, ctx->stream));
+    uint64_t nl = 0;
+    int32_t rc0 = insert_level1_slabs(ctx, c, slabs, slab_cap, nsend, (const unsigned long long*)ctx->misc.p, rg, nullptr, &nl);
+    if (rc0) return rc0;
     cudaEventRecord(ctx->ev[1], ctx->stream);
-    ctx->launches += 1;
-    ctx->last.launches = 1;
+    ctx->launches += nl;
+    ctx->last.launches = nl;
     int32_t rc = check_overflow(ctx, c);
     cudaEventElapsedTime(&ctx->last.kernel_ms, ctx->ev[0], ctx->ev[1]);
     if (rc) return rc;

@@ -58,8 +58,9 @@ __device__ __forceinline__ uint64_t seq_forward(const uint64_t* __restrict__ byt
 template <typename V, bool FROM_SEQ>
 __global__ void __launch_bounds__(PART_THREADS, 2)
     count_part_kernel(SeqView b, uint64_t byte_begin, uint64_t byte_end, uint64_t total_bytes, uint32_t k, int canonical,
-                      const V* __restrict__ keys, uint64_t nkeys, PartGeom g, V* const* __restrict__ dests,
+                      const V* __restrict__ keys, uint64_t nkeys, KeySegs segs, PartGeom g, V* const* __restrict__ dests,
                       unsigned long long* __restrict__ cursors, unsigned long long* __restrict__ flag) {
+    if (segs.skip_flag && *segs.skip_flag) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t NB = g.nowners * g.nregions;
     V* tkeys = (V*)smem_raw;
@@ -70,10 +71,32 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
     uint32_t* boff = hist + NB;
     uint32_t* gpos = boff + NB;
     __shared__ uint32_t tile_n, warp_sums[PART_THREADS / 32];
+    __shared__ unsigned long long seg_pref[65], seg_n[64];  // key-array form: tiles before segment s, keys of segment s
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 
-    const uint64_t ntiles = FROM_SEQ ? (byte_end - byte_begin + PART_TILE_BYTES - 1) / PART_TILE_BYTES
-                                     : (nkeys + PART_TILE_KEYS - 1) / PART_TILE_KEYS;
+    if (!FROM_SEQ) {
+        // the keys are one array of nkeys, or segs.nseg segments `segs.stride` keys apart holding
+        // min(segs.counts[s * segs.count_stride], nkeys) keys each (the slabs a coarse region received from its senders)
+        if (tid == 0) {
+            unsigned long long acc = 0;
+            const uint32_t ns = segs.counts ? segs.nseg : 1u;
+            for (uint32_t q = 0; q < ns; ++q) {
+                unsigned long long nq = nkeys;
+                if (segs.counts) {
+                    nq = segs.counts[(uint64_t)q * segs.count_stride];
+                    if (nq > nkeys) nq = nkeys;
+                }
+                seg_pref[q] = acc;
+                seg_n[q] = nq;
+                acc += (nq + PART_TILE_KEYS - 1) / PART_TILE_KEYS;
+            }
+            seg_pref[ns] = acc;
+            for (uint32_t q = ns + 1; q < 65; ++q) seg_pref[q] = ~0ULL;
+        }
+        __syncthreads();
+    }
+    const uint32_t nsegs = (!FROM_SEQ && segs.counts) ? segs.nseg : 1u;
+    const uint64_t ntiles = FROM_SEQ ? (byte_end - byte_begin + PART_TILE_BYTES - 1) / PART_TILE_BYTES : seg_pref[nsegs];
     // a CTA owns a contiguous range of tiles: the sequence index only moves forward
     const uint64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
     const uint64_t t0 = (uint64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
@@ -128,10 +151,13 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
                 }
             }
         } else {
-            const uint64_t i0 = t * PART_TILE_KEYS;
-            const uint32_t n = (uint32_t)min((uint64_t)PART_TILE_KEYS, nkeys - i0);
+            uint32_t sg = 0;
+            while (sg + 1 < nsegs && seg_pref[sg + 1] <= t) ++sg;
+            const uint64_t i0 = (t - seg_pref[sg]) * PART_TILE_KEYS;
+            const uint32_t n = (uint32_t)min((uint64_t)PART_TILE_KEYS, (uint64_t)seg_n[sg] - i0);
+            const V* src = keys + (uint64_t)sg * segs.stride + i0;
             for (uint32_t i = tid; i < n; i += PART_THREADS) {
-                const V key = keys[i0 + i];
+                const V key = src[i];
                 const uint32_t bk = part_bucket<V>(key, g);
                 tkeys[i] = key;
                 tb[i] = (uint16_t)bk;
@@ -206,7 +232,8 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
     if (lost) *flag = 1ULL;
 }
 
-// phase 2: counts[s * nregions + r] keys of sender s for region r sit at slabs + (r * nsend + s) * slab_cap.
+// phase 2: counts[s * count_stride + r] keys of sender s for region r sit at slabs + (r * nsend + s) * slab_cap; the
+// regions are regions region0 .. region0 + nregions of the table (region0 only matters for the prefetch addresses).
 // All CTAs take the regions in the same order and are kept within two regions of each other: a CTA may start region r
 // only when every CTA has finished region r - 2 (done[] counters; cooperative launch, so that all CTAs are resident).
 // Without the coupling the CTAs drift apart by tens of regions and the working set leaves L2 (measured: no faster than
@@ -216,7 +243,8 @@ __global__ void __launch_bounds__(256) count_insert_slabs_kernel(const V* __rest
                                                                  uint32_t nsend, const unsigned long long* __restrict__ counts,
                                                                  CountTable t, uint32_t shift,
                                                                  const unsigned long long* __restrict__ skip_flag, int prefetch,
-                                                                 unsigned int* __restrict__ done) {
+                                                                 unsigned int* __restrict__ done, uint32_t region0,
+                                                                 uint64_t count_stride) {
     if (skip_flag && *skip_flag) return;  // phase 1 overflowed a slab: the caller inserts this chunk directly
     const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, gsize = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t slot_bytes = sizeof(V) == 8 ? 16 : 8;
@@ -236,13 +264,13 @@ __global__ void __launch_bounds__(256) count_insert_slabs_kernel(const V* __rest
             // instead of the cold random sector fetches of the updates
             const uint32_t first = r == 0 ? 0 : r + 1, last = r + 1;
             for (uint32_t pr = first; pr <= last && pr < nregions; ++pr) {
-                const char* base = (const char*)t.slots + (uint64_t)pr * region_bytes;
+                const char* base = (const char*)t.slots + (uint64_t)(region0 + pr) * region_bytes;
                 for (uint64_t l = gtid; l < lines; l += gsize)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(base + l * 128));
             }
         }
         for (uint32_t s = 0; s < nsend; ++s) {
-            const unsigned long long cnt0 = counts[(uint64_t)s * nregions + r];
+            const unsigned long long cnt0 = counts[(uint64_t)s * count_stride + r];
             const uint64_t cnt = cnt0 < slab_cap ? cnt0 : slab_cap;
             const V* seg = slabs + ((uint64_t)r * nsend + s) * slab_cap;
             for (uint64_t i = gtid; i < cnt; i += gsize) ok &= CountOps<V>::insert(t, seg[i], 1u);
@@ -278,7 +306,7 @@ cudaError_t launch_count_part_seqs(const SeqView& b, uint64_t byte_begin, uint64
             attr = true;
         }
         count_part_kernel<uint64_t, true><<<grid, PART_THREADS, smem, st>>>(b, byte_begin, byte_end, total_bytes, k, canonical, nullptr, 0,
-                                                                             g, (uint64_t* const*)dests, cursors, flag);
+                                                                             KeySegs{}, g, (uint64_t* const*)dests, cursors, flag);
     } else {
         static bool attr = false;
         if (!attr) {
@@ -286,13 +314,14 @@ cudaError_t launch_count_part_seqs(const SeqView& b, uint64_t byte_begin, uint64
             attr = true;
         }
         count_part_kernel<uint32_t, true><<<grid, PART_THREADS, smem, st>>>(b, byte_begin, byte_end, total_bytes, k, canonical, nullptr, 0,
-                                                                             g, (uint32_t* const*)dests, cursors, flag);
+                                                                             KeySegs{}, g, (uint32_t* const*)dests, cursors, flag);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_count_part_keys(const void* keys, uint64_t nkeys, bool key64, const PartGeom& g, void* const* dests,
-                                   unsigned long long* cursors, unsigned long long* flag, int sm_count, cudaStream_t st) {
+cudaError_t launch_count_part_keys(const void* keys, uint64_t nkeys, const KeySegs& segs, bool key64, const PartGeom& g,
+                                   void* const* dests, unsigned long long* cursors, unsigned long long* flag, int sm_count,
+                                   cudaStream_t st) {
     if (nkeys == 0) return cudaSuccess;
     const size_t smem = count_part_smem_bytes(key64, g.nowners * g.nregions);
     const int grid = count_part_grid(sm_count);
@@ -303,7 +332,7 @@ cudaError_t launch_count_part_keys(const void* keys, uint64_t nkeys, bool key64,
             cudaFuncSetAttribute(count_part_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024);
             attr = true;
         }
-        count_part_kernel<uint64_t, false><<<grid, PART_THREADS, smem, st>>>(none, 0, 0, 0, 0, 0, (const uint64_t*)keys, nkeys, g,
+        count_part_kernel<uint64_t, false><<<grid, PART_THREADS, smem, st>>>(none, 0, 0, 0, 0, 0, (const uint64_t*)keys, nkeys, segs, g,
                                                                               (uint64_t* const*)dests, cursors, flag);
     } else {
         static bool attr = false;
@@ -311,7 +340,7 @@ cudaError_t launch_count_part_keys(const void* keys, uint64_t nkeys, bool key64,
             cudaFuncSetAttribute(count_part_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024);
             attr = true;
         }
-        count_part_kernel<uint32_t, false><<<grid, PART_THREADS, smem, st>>>(none, 0, 0, 0, 0, 0, (const uint32_t*)keys, nkeys, g,
+        count_part_kernel<uint32_t, false><<<grid, PART_THREADS, smem, st>>>(none, 0, 0, 0, 0, 0, (const uint32_t*)keys, nkeys, segs, g,
                                                                               (uint32_t* const*)dests, cursors, flag);
     }
     return cudaGetLastError();
@@ -321,7 +350,8 @@ cudaError_t launch_count_part_keys(const void* keys, uint64_t nkeys, bool key64,
 cudaError_t launch_count_insert_slabs(const void* slabs, uint64_t slab_cap, uint32_t nregions, uint32_t nsend,
                                       const unsigned long long* counts, const CountTable& t, bool key64, uint32_t shift,
                                       const unsigned long long* skip_flag, bool prefetch, unsigned int* done, int sm_count,
-                                      cudaStream_t st) {
+                                      cudaStream_t st, uint32_t region0, uint64_t count_stride) {
+    if (count_stride == 0) count_stride = nregions;
     const void* fn = key64 ? (const void*)count_insert_slabs_kernel<uint64_t> : (const void*)count_insert_slabs_kernel<uint32_t>;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0);
@@ -331,7 +361,7 @@ cudaError_t launch_count_insert_slabs(const void* slabs, uint64_t slab_cap, uint
     const int grid = sm_count * per_sm;
     int pf = prefetch ? 1 : 0;
     void* args[] = {(void*)&slabs, (void*)&slab_cap, (void*)&nregions, (void*)&nsend, (void*)&counts, (void*)&t,
-                    (void*)&shift,  (void*)&skip_flag, (void*)&pf,      (void*)&done};
+                    (void*)&shift,  (void*)&skip_flag, (void*)&pf,      (void*)&done,     (void*)&region0,  (void*)&count_stride};
     if (done) return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, 0, st);
     return cudaLaunchKernel(fn, dim3(grid), dim3(256), args, 0, st);
 }

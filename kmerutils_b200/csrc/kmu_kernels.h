@@ -278,15 +278,25 @@ struct PartGeom {
     uint32_t nsend, self;
     uint64_t slab_cap;  // keys per slab (< 2^32)
 };
+// key-array form of the partition: nseg segments `stride` keys apart, segment s holding min(counts[s * count_stride], nkeys)
+// keys (counts == nullptr: one array of nkeys keys); skip_flag != 0 -> the kernel does nothing
+struct KeySegs {
+    uint64_t stride = 0;
+    uint32_t nseg = 1;
+    const unsigned long long* counts = nullptr;
+    uint64_t count_stride = 0;
+    const unsigned long long* skip_flag = nullptr;
+};
 size_t count_part_smem_bytes(bool key64, uint32_t nbuckets);
 cudaError_t launch_count_part_seqs(const SeqView& b, uint64_t byte_begin, uint64_t byte_end, uint64_t total_bytes, uint32_t k,
                                    bool key64, bool canonical, const PartGeom& g, void* const* dests,
                                    unsigned long long* cursors, unsigned long long* flag, int sm_count, cudaStream_t st);
-cudaError_t launch_count_part_keys(const void* keys, uint64_t nkeys, bool key64, const PartGeom& g, void* const* dests,
-                                   unsigned long long* cursors, unsigned long long* flag, int sm_count, cudaStream_t st);
+cudaError_t launch_count_part_keys(const void* keys, uint64_t nkeys, const KeySegs& segs, bool key64, const PartGeom& g,
+                                   void* const* dests, unsigned long long* cursors, unsigned long long* flag, int sm_count,
+                                   cudaStream_t st);
 cudaError_t launch_count_insert_slabs(const void* slabs, uint64_t slab_cap, uint32_t nregions, uint32_t nsend,
                                       const unsigned long long* counts, const CountTable& t, bool key64, uint32_t shift,
                                       const unsigned long long* skip_flag, bool prefetch, unsigned int* done, int sm_count,
-                                      cudaStream_t st);
+                                      cudaStream_t st, uint32_t region0 = 0, uint64_t count_stride = 0);
 
 }  // namespace kmu

@@ -35,20 +35,22 @@ def table_contents(ctr):
     return k[o], c[o]
 
 
-@pytest.mark.parametrize("k,ktype,region_kb", [(31, kb.KMER64, 64), (21, kb.KMER64, 16), (16, kb.KMER16B32, 32),
-                                               (12, kb.KMER32, 16), (32, kb.KMER64, 64)])
-def test_two_phase_matches_oracle_and_direct(engine, oracle, k, ktype, region_kb):
+@pytest.mark.parametrize("k,ktype,region_kb,level1", [(31, kb.KMER64, 64, 512), (21, kb.KMER64, 16, 512), (16, kb.KMER16B32, 32, 512),
+                                                      (12, kb.KMER32, 16, 512), (32, kb.KMER64, 64, 512),
+                                                      # two levels: 4 coarse regions cut into fine ones before the insertion
+                                                      (31, kb.KMER64, 16, 4), (16, kb.KMER16B32, 16, 2), (21, kb.KMER64, 32, 1)])
+def test_two_phase_matches_oracle_and_direct(engine, oracle, k, ktype, region_kb, level1):
     rng = np.random.default_rng(100 + k)
     reads = genome_reads(oracle, 60 + k, 30000, 3000, 150, rng)
     reads += [b"ACGT" * 3, b"ACGTTGCA" * 40, b"C", oracle.synth_ascii(9, 0, 70000)]  # short, periodic, one long sequence
     batch, _ = engine.batch_from_ascii(reads)
     packed, off, nb = batch.download()
     keys, cnts = oracle.count_kmers(packed, off, nb, k, ktype, True)
-    with knobs(KMU_COUNT_REGION_KB=region_kb, KMU_COUNT_TWO_PHASE_MIN_KEYS=1):
+    with knobs(KMU_COUNT_REGION_KB=region_kb, KMU_COUNT_TWO_PHASE_MIN_KEYS=1, KMU_COUNT_LEVEL1_BUCKETS=level1):
         ctr = engine.counter(k, ktype, capacity=max(len(keys), 1 << 16), count_bits=8)
         l0 = engine.launch_count()
         ctr.insert_seqs(batch, canonical=True)
-        assert engine.launch_count() - l0 >= 2  # partition + regioned insertion, not the direct kernel
+        assert engine.launch_count() - l0 >= (2 if level1 >= 512 else 3)  # partition(s) + regioned insertion, not the direct kernel
         st = ctr.stats()
         assert st["nb_distinct"] == len(keys)
         assert st["nb_unique"] == int((cnts == 1).sum())
@@ -83,8 +85,9 @@ def test_two_phase_chunks_and_overflow_fallback(engine, oracle):
     batch, _ = engine.batch_from_ascii(reads)
     packed, off, nb = batch.download()
     keys, cnts = oracle.count_kmers(packed, off, nb, k, ktype, True)
-    for slab_mb in (2, 64):
-        with knobs(KMU_COUNT_REGION_KB=64, KMU_COUNT_TWO_PHASE_MIN_KEYS=1, KMU_COUNT_SLAB_MB=slab_mb):
+    # level1 = 1: the level-1 partition cannot overflow (one slab), the homopolymer overflows a FINE slab of level 2
+    for slab_mb, level1 in ((2, 512), (64, 512), (64, 4), (64, 1)):
+        with knobs(KMU_COUNT_REGION_KB=64, KMU_COUNT_TWO_PHASE_MIN_KEYS=1, KMU_COUNT_SLAB_MB=slab_mb, KMU_COUNT_LEVEL1_BUCKETS=level1):
             ctr = engine.counter(k, ktype, capacity=1 << 17, count_bits=32)
             ctr.insert_seqs(batch, canonical=True)
             st = ctr.stats()
