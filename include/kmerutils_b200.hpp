@@ -26,7 +26,8 @@
 //  jaccard_index_probminhash3a       seqsketchjaccard.rs:423-495          same name
 //  dump_signatures_block_u32 / SigSketchFileReader  :577-712              same names
 //  aautils::kmeraa::{Alphabet,KmerAA32bit,KmerAA64bit,SequenceAA,KmerGenerator},
-//  aautils::setsketchert::{SeqSketcher,SeqSketcherAAT,ProbHash3aSketch,HyperLogLogSketch}   kmerutils::aautils::*
+//  aautils::setsketchert::{SeqSketcher,SeqSketcherAAT,ProbHash3aSketch,SuperHashSketch,HyperLogLogSketch}   kmerutils::aautils::*
+//  sketching::seqminhash::sketch_seqrange_superminhash  src/sketching/seqminhash.rs:19-62   same name
 //
 //  The Rust closure `fhash: Fn(&Kmer) -> Kmer::Val` cannot cross into CUDA: the five closures the
 //  reference actually passes are the constants of kmerutils::KmerHash.
@@ -639,18 +640,91 @@ class KmerCounter {
     std::vector<typename Kmer::Val> pending_;
 };
 
-/// KmerCounterPool (kmercount.rs:424-460): the reference shards by DispatchableT over threads; one GPU holds one table
+/// KmerCounterPool (kmercount.rs:424-565): one counter per "thread", a k-mer lives in counter `kmer.dispatch(n)`
+/// (DispatchableT, :382-420).  Here every counter is a table in HBM; the pool keeps the reference's layout so that code
+/// written against `pool.counters[i]` / `get_above2_count` / `get_count_nb_bits` keeps working.
 template <typename Kmer>
-using KmerCounterPool = KmerCounter<Kmer>;
+class KmerCounterPool {
+  public:
+    std::vector<std::unique_ptr<KmerCounter<Kmer>>> counters;
+    explicit KmerCounterPool(std::vector<std::unique_ptr<KmerCounter<Kmer>>> c) : counters(std::move(c)) {}
+    uint32_t get_above2_count(Kmer kmer) { return counters[kmer.dispatch(counters.size())]->get_above2_count(kmer); }
+    uint8_t get_count_nb_bits() const { return counters.empty() ? 0 : counters[0]->get_count_nb_bits(); }
+    // KmerCountT for the pool (:533-563)
+    void insert_kmer(Kmer kmer) { counters[kmer.dispatch(counters.size())]->insert_kmer(kmer); }
+    uint32_t get_count(Kmer kmer) { return counters[kmer.dispatch(counters.size())]->get_count(kmer); }
+    /// many k-mers with one query per counter (what a caller looping over get_count wants on a GPU)
+    std::vector<uint32_t> get_counts(const std::vector<Kmer>& kmers) {
+        std::vector<std::vector<Kmer>> per(counters.size());
+        std::vector<std::vector<size_t>> idx(counters.size());
+        for (size_t i = 0; i < kmers.size(); ++i) {
+            const size_t loc = kmers[i].dispatch(counters.size());
+            per[loc].push_back(kmers[i]);
+            idx[loc].push_back(i);
+        }
+        std::vector<uint32_t> out(kmers.size(), 0);
+        for (size_t loc = 0; loc < counters.size(); ++loc) {
+            if (per[loc].empty()) continue;
+            const auto c = counters[loc]->get_counts(per[loc]);
+            for (size_t j = 0; j < c.size(); ++j) out[idx[loc][j]] = c[j];
+        }
+        return out;
+    }
+    uint64_t get_nb_distinct() {
+        uint64_t n = 0;
+        for (auto& c : counters) n += c->get_nb_distinct();
+        return n;
+    }
+    uint64_t get_nb_unique() {
+        uint64_t n = 0;
+        for (auto& c : counters) n += c->get_nb_unique();
+        return n;
+    }
+};
 
-/// count_kmer_threaded_one_to_many (kmercount.rs:881-974): canonical k-mers of all sequences, 8-bit counters.
-/// nb_threads is accepted for source compatibility (the GPU is the thread pool).
+/// the common body of the two threaded drivers: the canonical k-mers of all sequences are bucketed by
+/// DispatchableT::dispatch on the GPU (kmu_count_partition) and bucket i is inserted into counter i
 template <typename Kmer>
-std::unique_ptr<KmerCounterPool<Kmer>> count_kmer_threaded_one_to_many(const std::vector<Sequence>& seqvec, size_t /*nb_threads*/,
+std::unique_ptr<KmerCounterPool<Kmer>> count_kmer_into_pool(const std::vector<Sequence>& seqvec, size_t nb_threads, size_t nb_bits,
+                                                            size_t kmer_size) {
+    if (nb_threads < 1 || nb_threads > 64) throw Panic(KMU_EINVAL, "nb_threads must be in 1..64");
+    kmu_ctx* ctx = Context::global().get();
+    DeviceBatch b(as_refs(seqvec));
+    const uint64_t nk = kmu_kmer_count(b.get(), (uint32_t)kmer_size);
+    std::vector<std::unique_ptr<KmerCounter<Kmer>>> counters;
+    for (size_t i = 0; i < nb_threads; ++i)  // the reference sizes every filter for 1e9 / 3e9 keys (:888-892); a table is sized by its input
+        counters.emplace_back(new KmerCounter<Kmer>(0.03f, (size_t)(nk / nb_threads * 1.3) + 1024, nb_bits, (uint8_t)kmer_size));
+    if (nk) {
+        void* dev = nullptr;
+        uint8_t handle[64];
+        check(kmu_ipc_alloc(ctx, nk * sizeof(typename Kmer::Val), &dev, handle), "count_kmer: device buffer");
+        std::vector<uint64_t> part(nb_threads, 0);
+        int32_t rc = kmu_count_partition(ctx, b.get(), (uint32_t)kmer_size, Kmer::kmu_type, 1, (uint32_t)nb_threads, dev, part.data(), 1);
+        uint64_t off = 0;
+        for (size_t i = 0; i < nb_threads && rc == KMU_OK; ++i) {
+            rc = kmu_count_insert_kmers(ctx, counters[i]->handle(), (const uint8_t*)dev + off * sizeof(typename Kmer::Val), part[i], 1);
+            off += part[i];
+        }
+        kmu_ipc_free(ctx, dev);
+        check(rc, "count_kmer");
+    }
+    return std::make_unique<KmerCounterPool<Kmer>>(std::move(counters));
+}
+
+/// count_kmer_threaded_one_to_many (kmercount.rs:881-974): one producer, nb_threads counters, `count_size` BITS per count
+/// (:893), canonical k-mers (:938), counter = dispatch (:941)
+template <typename Kmer>
+std::unique_ptr<KmerCounterPool<Kmer>> count_kmer_threaded_one_to_many(const std::vector<Sequence>& seqvec, size_t nb_threads,
                                                                        size_t count_size, size_t kmer_size) {
-    auto pool = std::make_unique<KmerCounterPool<Kmer>>(0.03f, count_size, 8, (uint8_t)kmer_size);
-    pool->insert_sequences(as_refs(seqvec), true);
-    return pool;
+    return count_kmer_into_pool<Kmer>(seqvec, nb_threads, count_size, kmer_size);
+}
+
+/// count_kmer_thread_independant (kmercount.rs:797-867): every thread walks all k-mers and keeps those it owns; 8-bit counts
+/// (:802).  Same pool as the one-to-many driver.
+template <typename Kmer>
+std::unique_ptr<KmerCounterPool<Kmer>> count_kmer_thread_independant(const std::vector<Sequence>& seqvec, size_t nb_threads,
+                                                                     size_t kmer_size) {
+    return count_kmer_into_pool<Kmer>(seqvec, nb_threads, 8, kmer_size);
 }
 
 }  // namespace base
@@ -915,6 +989,22 @@ class SuperHashSketch : public SeqSketcherT<Kmer, S> {
     SeqSketcherParams p_;
 };
 
+/// sketch_seqrange_superminhash (src/sketching/seqminhash.rs:19-62): SuperMinHash (f64, NoHashHasher) of the k-mers inside
+/// `range` of one sequence, canonical + int32_hash hard-coded (:37-38, 48-49); k = 16 -> Kmer16b32bit, 9..=15 -> Kmer32bit,
+/// anything else panics (:55-60).  (k = 15 panics one step later in the reference, inside KmerSeqIterator::<Kmer32bit>::new.)
+inline std::vector<double> sketch_seqrange_superminhash(const Sequence& seq, size_t range_start, size_t range_end, size_t kmer_size,
+                                                        size_t sketch_size) {
+    if (kmer_size != 16 && (kmer_size < 9 || kmer_size > 15)) throw Panic(KMU_EINVAL, "sketch_sequence_superminhash , unimplemented kmer_size");
+    if (range_end <= range_start || range_end > seq.size())  // set_range(..).unwrap() (:33, :44)
+        throw Panic(KMU_EINVAL, "called `Result::unwrap()` on an `Err` value: set_range");
+    DeviceBatch b(seq, range_start, range_end);
+    std::vector<double> sig(sketch_size);
+    check(kmu_sketch_superminhash(Context::global().get(), b.get(), (uint32_t)kmer_size, kmer_size == 16 ? KMU_KMER16B32 : KMU_KMER32,
+                                  KMU_HASH_CANON_INVHASH, (uint32_t)sketch_size, KMU_HASHER_NOHASH, 8, sig.data(), 0),
+          "sketch_seqrange_superminhash");
+    return sig;
+}
+
 /// SetSketchParams of probminhash (default b 1.001, m 4096, a 20, q 2^16 - 2)
 struct SetSketchParams {
     double b = 1.001;
@@ -1138,6 +1228,37 @@ class ProbHash3aSketch : public SeqSketcherAAT<Kmer, typename Kmer::Val> {
     std::vector<std::vector<typename Kmer::Val>> sketch_compressedkmeraa(const std::vector<const SequenceAA*>& vseq,
                                                                          KmerHash fhash) const override {
         return SeqSketcher(p_.kmer_size, p_.sketch_size).template sketch_probminhash3a<Kmer>(vseq, fhash);
+    }
+
+  private:
+    sketching::SeqSketcherParams p_;
+};
+/// SuperHashSketch of the amino-acid module (src/aautils/setsketchert.rs:203-329): NoHashHasher keys (:250-252, 302-304)
+template <typename Kmer, typename S>
+class SuperHashSketch : public SeqSketcherAAT<Kmer, S> {
+  public:
+    static_assert(std::is_same<S, float>::value || std::is_same<S, double>::value, "S is f32 or f64");
+    explicit SuperHashSketch(const sketching::SeqSketcherParams& p) : p_(p) {}
+    size_t get_kmer_size() const override { return p_.kmer_size; }
+    size_t get_sketch_size() const override { return p_.sketch_size; }
+    std::vector<std::vector<S>> sketch_compressedkmeraa(const std::vector<const SequenceAA*>& vseq, KmerHash fhash) const override {
+        for (const SequenceAA* q : vseq)  // set_range(0, seqb.size()).unwrap() (:255): an empty sequence panics
+            if (q->size() == 0) throw Panic(KMU_EINVAL, "called `Result::unwrap()` on an `Err` value: set_range on an empty sequence");
+        DeviceBatchAA b(vseq);
+        std::vector<S> flat(vseq.size() * p_.sketch_size);
+        check(kmu_sketch_superminhash(Context::global().get(), b.get(), (uint32_t)p_.kmer_size, Kmer::kmu_type, fhash.kind,
+                                      (uint32_t)p_.sketch_size, KMU_HASHER_NOHASH, (int32_t)sizeof(S), flat.data(), 0),
+              "SuperHashSketch::sketch_compressedkmeraa");
+        return sketching::rows_of(flat, vseq.size(), p_.sketch_size);
+    }
+    /// ONE signature for the whole collection (sketch_compressedkmeraa_seqs, :291-328)
+    std::vector<std::vector<S>> sketch_compressedkmeraa_seqs(const std::vector<const SequenceAA*>& vseq, KmerHash fhash) const {
+        DeviceBatchAA b(vseq);
+        std::vector<S> sig(p_.sketch_size);
+        check(kmu_sketch_superminhash_whole(Context::global().get(), b.get(), (uint32_t)p_.kmer_size, Kmer::kmu_type, fhash.kind,
+                                            (uint32_t)p_.sketch_size, KMU_HASHER_NOHASH, (int32_t)sizeof(S), sig.data(), 0),
+              "SuperHashSketch::sketch_compressedkmeraa_seqs");
+        return {sig};
     }
 
   private:

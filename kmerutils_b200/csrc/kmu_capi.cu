@@ -1494,14 +1494,25 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
         hp.cursor[sl] = views[c].order_cache.cursor_dev;
         views[c].order_cache.order = DevBuf{};
         views[c].order_cache.cursor_dev = DevBuf{};
-        if (ctx->redo_on_side) CUDA_TRY(cudaEventRecord(hp.compute_done[sl], ctx->redo_stream));
-        else if (ctx->redo_on_main) CUDA_TRY(cudaEventRecord(hp.compute_done[sl], ctx->stream));  // behind the next chunk's launches
-        CUDA_TRY(cudaStreamWaitEvent(hp.copy_out, hp.compute_done[sl], 0));
+        // a CUDA failure here must not return before the three streams are idle: copies into the caller's `sig` and the
+        // pinned staging buffers may still be in flight (every exit goes through the synchronisation below)
+#define CUDA_BRK(expr)                                                                           \
+    {                                                                                            \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            rc = fail(KMU_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));               \
+            break;                                                                               \
+        }                                                                                        \
+    }
+        if (ctx->redo_on_side) CUDA_BRK(cudaEventRecord(hp.compute_done[sl], ctx->redo_stream))
+        else if (ctx->redo_on_main) CUDA_BRK(cudaEventRecord(hp.compute_done[sl], ctx->stream))  // behind the next chunk's launches
+        CUDA_BRK(cudaStreamWaitEvent(hp.copy_out, hp.compute_done[sl], 0))
         const size_t out_bytes = (size_t)views[c].nseq * m * vsz;
-        CUDA_TRY(cudaEventRecord(hp.out_begin[sl], hp.copy_out));
-        CUDA_TRY(cudaMemcpyAsync((uint8_t*)sig + (size_t)cut[c] * m * vsz, hp.sig[sl].p, out_bytes, cudaMemcpyDeviceToHost,
-                                 hp.copy_out));
-        CUDA_TRY(cudaEventRecord(hp.out_done[sl], hp.copy_out));
+        CUDA_BRK(cudaEventRecord(hp.out_begin[sl], hp.copy_out))
+        CUDA_BRK(cudaMemcpyAsync((uint8_t*)sig + (size_t)cut[c] * m * vsz, hp.sig[sl].p, out_bytes, cudaMemcpyDeviceToHost,
+                                 hp.copy_out))
+        CUDA_BRK(cudaEventRecord(hp.out_done[sl], hp.copy_out))
+#undef CUDA_BRK
         timed_out[sl] = 1;
         ctx->last.d2h_bytes += out_bytes;
     }

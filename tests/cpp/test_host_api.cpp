@@ -7,6 +7,8 @@
 //   src/base/kmergenerator.rs:661-700   test_gen_kmer16b32bit_50bases_range_iterator
 //   src/base/kmer32bit.rs:228-312       reverse complement / ordering of Kmer32bit
 //   src/base/kmercount.rs:1524-1565     test_kmer_counter
+//   src/base/kmergenerator.rs:776-850   test_generate_weighted_kmer32bit
+//   src/base/kmer.rs:45-145, nthash.rs:76-120   NtHash methods of the two u32 k-mer types
 //   src/sketching/seqsketchjaccard.rs:742-791   test_pminhasha_kmer_smallb
 //   src/sketching/seqsketchjaccard.rs:947-1004  test_superminhash_kmer_16b32bit_serial
 //   src/sketching/seqsketchjaccard.rs:1015-...  test_reload_sketch_file
@@ -146,7 +148,8 @@ static void test_kmer_counter() {
     std::vector<std::string> reads;
     for (int i = 0; i < 300; ++i) reads.push_back(synth(77, 20000).substr((size_t)i * 50, 400));
     const std::vector<Sequence> seqvec = Sequence::new_batch(reads, 2);
-    auto pool = count_kmer_threaded_one_to_many<Kmer64bit>(seqvec, 4, 200000, 31);
+    auto pool = count_kmer_threaded_one_to_many<Kmer64bit>(seqvec, 4, 8, 31);  // 4 counters, 8 bits per count (:881-893)
+    EXPECT(pool->counters.size() == 4 && pool->get_count_nb_bits() == 8);
     std::vector<uint8_t> packed;
     std::vector<uint64_t> off, nb;
     for (const Sequence& s : seqvec) {
@@ -167,6 +170,208 @@ static void test_kmer_counter() {
     EXPECT(pool->get_nb_unique() == nu);
     const auto pc = pool->get_counts(probes);
     for (uint64_t i = 0; i < nd; ++i) EXPECT(pc[i] == (cnts[i] > 255 ? 255 : cnts[i]));
+    // every k-mer sits in the counter its dispatch names (DispatchableT, kmercount.rs:382-420), nowhere else
+    for (uint64_t i = 0; i < nd; i += 97) {
+        const size_t loc = probes[i].dispatch(4);
+        EXPECT(loc == (size_t)(orc_int64_hash(keys[i]) % 4));
+        for (size_t c = 0; c < 4; ++c) EXPECT(pool->counters[c]->get_count(probes[i]) == (c == loc ? pc[i] : 0u));
+        EXPECT(pool->get_above2_count(probes[i]) == (pc[i] >= 2 ? pc[i] : 0u));
+    }
+    // count_kmer_thread_independant (kmercount.rs:797-867): the same pool, 8-bit counts
+    auto pool2 = count_kmer_thread_independant<Kmer64bit>(seqvec, 3, 31);
+    EXPECT(pool2->counters.size() == 3 && pool2->get_nb_distinct() == nd && pool2->get_nb_unique() == nu);
+}
+
+// the advisor's round-1 finding: Kmer32bit::get_compressed_value() is the value WITHOUT the length header
+// (kmer32bit.rs:173-178); insert_kmer / get_count and insert_sequences must key the table the same way
+static void test_kmer32bit_counter_keys() {
+    Sequence seq(S80, 2);
+    const std::vector<Kmer32bit> v = KmerGenerator<Kmer32bit>(11).generate_kmer(seq);
+    for (const Kmer32bit& km : v) {
+        EXPECT(km.get_compressed_value() == (km.v & 0x0FFFFFFFu));
+        EXPECT((km.v >> 28) == 11);
+        EXPECT(km.get_compressed_value() == (uint32_t)orc_kmer_compressed_value(km.v, 11, ORC_KMER32));
+        EXPECT(Kmer32bit::build(km.get_compressed_value(), 11) == km);
+    }
+    std::vector<std::string> reads;
+    for (int i = 0; i < 200; ++i) reads.push_back(synth(91, 30000).substr((size_t)i * 70, 300));
+    const std::vector<Sequence> seqvec = Sequence::new_batch(reads, 2);
+    std::vector<uint8_t> packed;
+    std::vector<uint64_t> off, nb;
+    for (const Sequence& s : seqvec) {
+        off.push_back(packed.size());
+        nb.push_back(s.size());
+        packed.insert(packed.end(), s.packed().begin(), s.packed().end());
+    }
+    {
+        std::vector<uint64_t> keys(100000), cnts(100000);
+        const uint64_t nd = orc_count_kmers(packed.data(), off.data(), nb.data(), seqvec.size(), 11, ORC_KMER32, 1, keys.data(), cnts.data(), keys.size());
+        KmerCounter<Kmer32bit> counter(0.03f, 100000, 8, 11);
+        counter.insert_sequences(as_refs(seqvec), true);
+        std::vector<Kmer32bit> probes;
+        for (uint64_t i = 0; i < nd; ++i) probes.push_back(Kmer32bit::build((uint32_t)keys[i], 11));
+        auto got = counter.get_counts(probes);
+        for (uint64_t i = 0; i < nd; ++i) EXPECT(got[i] == (cnts[i] > 255 ? 255 : cnts[i]));
+        EXPECT(counter.get_count(probes[0]) == got[0]);
+        // the same k-mers once more one by one: every count grows by one, no new distinct key appears
+        for (const Kmer32bit& km : probes) counter.insert_kmer(km);
+        got = counter.get_counts(probes);
+        for (uint64_t i = 0; i < nd; ++i) EXPECT(got[i] == (cnts[i] + 1 > 255 ? 255 : cnts[i] + 1));
+        EXPECT(counter.get_nb_distinct() == nd);
+    }
+    {
+        std::vector<uint64_t> keys(100000), cnts(100000);
+        const uint64_t nd = orc_count_kmers(packed.data(), off.data(), nb.data(), seqvec.size(), 23, ORC_KMER64, 1, keys.data(), cnts.data(), keys.size());
+        KmerCounter<Kmer64bit> counter(0.03f, 100000, 8, 23);
+        std::vector<Kmer64bit> probes;
+        for (uint64_t i = 0; i < nd; ++i) probes.push_back(Kmer64bit::build(keys[i], 23));
+        for (const Kmer64bit& km : probes) counter.insert_kmer(km);
+        counter.insert_sequences(as_refs(seqvec), true);
+        const auto got = counter.get_counts(probes);
+        for (uint64_t i = 0; i < nd; ++i) EXPECT(got[i] == (cnts[i] + 1 > 255 ? 255 : cnts[i] + 1));
+        EXPECT(counter.get_nb_distinct() == nd && counter.get_nb_unique() == 0);
+    }
+}
+
+// NtHash trait (nthash.rs:76-120, kmer.rs:45-145) on the host value types against the batch kernel and the oracle
+static void test_nthash_trait() {
+    Sequence seq(S80, 2);
+    const std::vector<Kmer16b32bit> v16 = KmerGenerator<Kmer16b32bit>(16).generate_kmer(seq);
+    DeviceBatch b(std::vector<const Sequence*>{&seq});
+    std::vector<uint64_t> h(v16.size() * 4);
+    std::vector<uint8_t> strand(v16.size());
+    check(kmu_nthash_canonical(Context::global().get(), b.get(), 16, 4, h.data(), strand.data(), 0), "kmu_nthash_canonical");
+    for (size_t i = 0; i < v16.size(); ++i) {
+        uint64_t f = 0, r = 0;
+        const auto res = v16[i].nthash_canonical_init(f, r);
+        EXPECT(res.first == h[4 * i] && res.second == strand[i]);
+        EXPECT(v16[i].nthash_init() == f && f == orc_nthash_init(v16[i].v, 16, ORC_KMER16B32));
+        std::vector<uint64_t> multi(4);
+        EXPECT(v16[i].nthash_mult_canonical_init(f, r, multi) == strand[i]);
+        for (int j = 0; j < 4; ++j) EXPECT(multi[j] == h[4 * i + j]);
+    }
+    // SURVEY Appendix C (derived from kmer.rs:74-94): window 0 of the 80-base string
+    uint64_t f = 0, r = 0;
+    EXPECT(v16[0].nthash_canonical_init(f, r).first == 0x684a2ec1114d51c5ull && f == 0x9840eab169670ddfull && r == 0x684a2ec1114d51c5ull);
+    const std::vector<Kmer32bit> v8 = KmerGenerator<Kmer32bit>(8).generate_kmer(seq);
+    EXPECT(v8[0].nthash_init() == 0x935533199c1dfb81ull && v8[1].nthash_init() == 0x4f6868cb4fb9a55eull);
+    // the *_cycle methods are the reference's single-step shims, bug for bug: same values as the oracle's restatement
+    for (size_t i = 0; i + 1 < v8.size(); i += 7) {
+        Kmer32bit km = v8[i];
+        const uint8_t nbase = (uint8_t)(v8[i + 1].v & 3);
+        EXPECT(km.nthash_cycle(km.nthash_init(), nbase) == orc_nthash_cycle(km.v, 8, ORC_KMER32, orc_nthash_init(km.v, 8, ORC_KMER32), nbase));
+        EXPECT(km == v8[i]);  // push(new_base) is dropped: self does not advance (kmer.rs:69)
+        uint64_t f1 = 1, r1 = 2, f2 = 1, r2 = 2, canon = 0;
+        const auto got = km.nthash_canonical_cycle(nbase, f1, r1);
+        const int st = orc_nthash_canonical_cycle(km.v, 8, ORC_KMER32, nbase, &f2, &r2, &canon);
+        EXPECT(f1 == f2 && r1 == r2 && got.first == canon && got.second == st);
+    }
+}
+
+// KmerSeqIterator (kmergenerator.rs:30-107) and generate_weighted_kmer (:155-186) on the host layer
+static void test_kmer_seq_iterator_and_distribution() {
+    Sequence seq(S80, 2);
+    const std::vector<Kmer16b32bit> all = KmerGenerator<Kmer16b32bit>(16).generate_kmer(seq);
+    KmerSeqIterator<Kmer16b32bit> it(16, seq);
+    size_t n = 0;
+    while (auto km = it.next()) {
+        EXPECT(n < all.size() && *km == all[n]);
+        ++n;
+    }
+    EXPECT(n == all.size() && !it.next());
+    // test_gen_kmer16b32bit_50bases_range_iterator (kmergenerator.rs:661-700): range 3..25
+    EXPECT(it.set_range(3, 25));
+    n = 0;
+    while (auto km = it.next()) {
+        const auto u = km->get_uncompressed_kmer();
+        EXPECT(std::string(u.begin(), u.end()) == S80.substr(3 + n, 16));
+        ++n;
+    }
+    EXPECT(n == 25 - 3 - 16 + 1);
+    EXPECT(!it.set_range(10, 10) && !it.set_range(5, 81));  // Err(()) (sequence.rs:563-565)
+    bool threw = false;
+    try {
+        KmerSeqIterator<Kmer32bit> bad(15, seq);  // kmergenerator.rs:48-53
+    } catch (const Panic&) {
+        threw = true;
+    }
+    EXPECT(threw);
+    // a sequence longer than the iterator's window: every k-mer, in order, across the refills
+    const std::string big = synth(5, (1u << 20) + 5000);
+    Sequence sbig(big, 2);
+    KmerSeqIterator<Kmer32bit> itb(11, sbig);
+    const std::vector<Kmer32bit> wantb = KmerGenerator<Kmer32bit>(11).generate_kmer(sbig);
+    n = 0;
+    bool same = true;
+    while (auto km = itb.next()) {
+        same &= n < wantb.size() && *km == wantb[n];
+        ++n;
+    }
+    EXPECT(same && n == wantb.size() && n == big.size() - 10);
+    // test_generate_weighted_kmer32bit (kmergenerator.rs:776-850): 3-mers of the first 48 bases with their multiplicities
+    Sequence s48(S80.substr(0, 48), 2);
+    const auto dist = KmerGenerator<Kmer32bit>(3).generate_weighted_kmer(s48);
+    const std::pair<const char*, uint32_t> want[] = {
+        {"TCA", 4}, {"CAA", 2}, {"AAA", 4}, {"AAG", 1}, {"AGG", 1}, {"GGG", 1}, {"GGA", 1}, {"GAA", 1}, {"AAC", 1}, {"ACA", 1}, {"CAT", 1},
+        {"ATT", 2}, {"TTC", 2}, {"AAT", 1}, {"ATC", 1}, {"CAG", 2}, {"AGT", 2}, {"GTA", 2}, {"TAT", 2}, {"ATG", 1}, {"TGC", 1}, {"GCG", 1},
+        {"CGC", 1}, {"GCC", 1}, {"CCC", 1}, {"CCG", 1}, {"CGT", 2}, {"GTT", 2}, {"TTA", 1}, {"TAC", 1}, {"ACG", 1}};
+    EXPECT(dist.size() == sizeof(want) / sizeof(want[0]));
+    uint32_t total = 0;
+    for (const auto& w : want) {
+        Sequence one(std::string(w.first), 2);
+        const Kmer32bit km = KmerGenerator<Kmer32bit>(3).generate_kmer(one)[0];
+        const auto f = dist.find(km);
+        EXPECT(f != dist.end() && f->second == w.second);
+        total += w.second;
+    }
+    EXPECT(total == 46);
+    EXPECT(hashmap_count_to_vec_count(dist).size() == dist.size());
+    // the other two types: multiplicities sum to the number of k-mers
+    uint64_t t16 = 0, t64 = 0;
+    for (const auto& kv : KmerGenerator<Kmer16b32bit>(16).generate_weighted_kmer(seq)) t16 += kv.second;
+    for (const auto& kv : KmerGenerator<Kmer64bit>(21).generate_kmer_distribution(seq)) t64 += kv.second;
+    EXPECT(t16 == 65 && t64 == 60);
+}
+
+// sketch_seqrange_superminhash (seqminhash.rs:19-62) and the amino-acid SuperHashSketch (aautils/setsketchert.rs:203-329)
+static void test_seqrange_and_aa_superminhash() {
+    const std::string a = synth(17, 6000);
+    Sequence seq(a, 2);
+    for (const int k : {12, 16}) {
+        const size_t lo = 500, hi = 4100, m = 300;
+        const std::vector<double> got = sketch_seqrange_superminhash(seq, lo, hi, k, m);
+        Sequence sub(a.substr(lo, hi - lo), 2);
+        const uint64_t off0 = 0, nb0 = hi - lo;
+        std::vector<double> want(m);
+        orc_sketch_superminhash_batch(sub.packed().data(), &off0, &nb0, 1, k, k == 16 ? ORC_KMER16B32 : ORC_KMER32, ORC_HASH_CANON_INVHASH, m, 0, 8,
+                                      want.data(), 1);
+        EXPECT(got == want);
+    }
+    bool threw = false;
+    try {
+        sketch_seqrange_superminhash(seq, 0, 100, 8, 100);  // "unimplemented kmer_size" (seqminhash.rs:55-60)
+    } catch (const Panic&) {
+        threw = true;
+    }
+    EXPECT(threw);
+    using namespace kmerutils::aautils;
+    const std::string p1 = "MTEQIELIKLYSTRILALAAQMPHVGSLDNPDASAMKRSPLCGSKVTVDVIMQNGKITFDGFEVLAPASEYKNRHASILLSLDATAEACASIAAQNSA";
+    const std::string p2 = "MTEQIELIKLYSTRILALAAQMPHVGSLDNPDASAMKRSPLCGSKVMTEQIELIKLYSTRILALAAQMPHVGSLDNPDASAMKRSPLCGSKV";
+    SequenceAA s1(p1), s2(p2);
+    aautils::SuperHashSketch<KmerAA64bit, double> sh({5, 200});
+    const SeqSketcherAAT<KmerAA64bit, double>& tr = sh;
+    const auto sig = tr.sketch_compressedkmeraa({&s1, &s2}, KmerHash::masked_value());
+    const SequenceAA* both[2] = {&s1, &s2};
+    for (int i = 0; i < 2; ++i) {
+        const uint64_t off0 = 0, n0 = both[i]->size();
+        std::vector<double> want(200);
+        orc_sketch_superminhash_batch(both[i]->residues().data(), &off0, &n0, 1, 5, ORC_KMERAA64, ORC_HASH_MASKED_VALUE, 200, 0, 8, want.data(), 1);
+        EXPECT(sig[i] == want);
+    }
+    // one signature for the collection = element-wise minimum of the per-sequence ones
+    const auto whole = sh.sketch_compressedkmeraa_seqs({&s1, &s2}, KmerHash::masked_value());
+    EXPECT(whole.size() == 1);
+    for (size_t j = 0; j < 200 && whole.size() == 1; ++j) EXPECT(whole[0][j] == std::min(sig[0][j], sig[1][j]));
 }
 
 static void test_pminhasha_kmer_smallb() {
@@ -391,6 +596,10 @@ int main(int argc, char** argv) {
         test_gen_kmer_range_and_types();
         test_kmer32bit_revcomp_order();
         test_kmer_counter();
+        test_kmer32bit_counter_keys();
+        test_nthash_trait();
+        test_kmer_seq_iterator_and_distribution();
+        test_seqrange_and_aa_superminhash();
         test_pminhasha_kmer_smallb();
         test_superminhash_and_hll();
         test_reload_sketch_file(dir);
