@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/kmerutils_b200.h"
+#include "kmu_detmath.cuh"
 #include "kmu_kernels.h"
 
 namespace kmu {
@@ -171,7 +172,9 @@ __device__ __forceinline__ double exp01_sample(const Exp01Params& p, Xoshiro256p
         }
         if (x <= __dmul_rn(p.c3, __dsub_rn(1.0, y))) return x;
         if (__dmul_rn(p.c1, y) <= __dsub_rn(1.0, x)) return x;
-        if (__dmul_rn(__dmul_rn(y, p.c1), p.lambda) <= expm1(__dmul_rn(p.lambda, __dsub_rn(1.0, x)))) return x;
+        // deterministic expm1 shared with the CPU oracle (kmu_detmath.cuh == oracle/det_math.hpp): CUDA's expm1 and glibc's
+        // may differ by one ulp
+        if (__dmul_rn(__dmul_rn(y, p.c1), p.lambda) <= det_expm1(__dmul_rn(p.lambda, __dsub_rn(1.0, x)))) return x;
     }
 }
 

@@ -92,3 +92,32 @@ DETMATH_FN double det_exp(double x) {
     const double y = 1.0 - ((lo - (x * c) / (2.0 - c)) - hi);
     return detmath_from_bits(detmath_bits(y) + ((uint64_t)(int64_t)k << 52));  // y * 2^k (no over/underflow in range)
 }
+
+// expm1(x) for 0 <= x < 1.5 ln2 (the only range ExpRestricted01 asks for: lambda (1 - x) with lambda = ln(m / (m - 1)) <= ln 2):
+// the k = 0 and k = 1 branches of the classic scheme (fdlibm s_expm1.c), explicit IEEE double operations only.  Used by BOTH
+// the CPU oracle and the kernels for the last rejection test of ExpRestricted01, so that the two sides cannot differ by the
+// one ulp that separates CUDA's expm1 from glibc's; agreement with a platform libm is < 1 ulp, not bit-for-bit.
+DETMATH_FN double det_expm1(double x) {
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+                 Q1 = -3.33333333333331316428e-02, Q2 = 1.58730158725481460165e-03, Q3 = -7.93650757867487942473e-05,
+                 Q4 = 4.00821782732936239552e-06, Q5 = -2.01099218183624371326e-07;
+    int k = 0;
+    double c = 0.0;
+    if (x > 0.34657359027997264) {  // x > 0.5 ln2: x = hi - lo + ln2
+        const double hi = x - ln2_hi, lo = ln2_lo;
+        k = 1;
+        x = hi - lo;
+        c = (hi - x) - lo;
+    } else if (x < 5.551115123125783e-17) {  // x < 2**-54
+        return x;
+    }
+    const double hfx = 0.5 * x, hxs = x * hfx;
+    const double r1 = 1.0 + hxs * (Q1 + hxs * (Q2 + hxs * (Q3 + hxs * (Q4 + hxs * Q5))));
+    const double t = 3.0 - r1 * hfx;
+    double e = hxs * ((r1 - t) / (6.0 - x * t));
+    if (k == 0) return x - (x * e - hxs);
+    e = (x * (e - c) - c);
+    e -= hxs;
+    if (x < -0.25) return -2.0 * (e - (x + 0.5));
+    return 1.0 + 2.0 * (x - e);
+}

@@ -10,6 +10,7 @@
 #include "zig_exp_tables.h"
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstring>
@@ -336,7 +337,7 @@ struct ExpRestricted01 {
             }
             if (x <= c3 * (1.0 - y)) return x;
             if (c1 * y <= 1.0 - x) return x;
-            if (y * c1 * lambda <= std::expm1(lambda * (1.0 - x))) return x;
+            if (y * c1 * lambda <= det_expm1(lambda * (1.0 - x))) return x;  // the same expm1 as the kernels (det_math.hpp)
         }
     }
 };
@@ -1055,6 +1056,122 @@ void orc_sketch_setsketch_batch(const uint8_t* packed, const uint64_t* byte_off,
 
 double orc_det_log(double x) { return det_log(x); }
 double orc_det_exp(double x) { return det_exp(x); }
+double orc_det_expm1(double x) { return det_expm1(x); }
+
+// How often does the deterministic ln / exp / expm1 of det_math.hpp lead to a DIFFERENT RESULT than the platform libm
+// the Rust reference calls (f64::ln / exp / exp_m1 -> glibc on Linux)?  Draws the arguments exactly as the sketchers
+// draw them and evaluates both at every call:
+//   SetSketch (setsketcher.rs: lb = ln(x_j) / ln(b), k = floor(1 - lb)): `points` points of `nkeys` keys with NoHash seeds
+//   synth(seed, i); the ziggurat's rare paths (ln(U) in the tail, exp(-x) in the wedge test) are counted too;
+//   ExpRestricted01 (ProbMinHash3a, lambda = ln(m / (m - 1))): its last rejection test, y c1 lambda <= expm1(lambda (1 - x)).
+// out[0] ln evaluations            out[1] bit patterns differ   out[2] KEYS whose register values k_1 .. k_points differ between an
+//                                                                all-deterministic and an all-libm evaluation of the key
+// out[3] ziggurat ln/exp evaluations out[4] bit patterns differ out[5] wedge accept decisions that differ
+// out[6] expm1 evaluations         out[7] bit patterns differ   out[8] accept decision differs
+void orc_libm_divergence(uint64_t nkeys, uint64_t seed, double b, uint64_t m, double a, uint64_t q, uint32_t points, uint32_t m_pmh,
+                         int nthreads, uint64_t* out) {
+    if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::vector<std::array<uint64_t, 9>> acc((size_t)nthreads);
+    const double lnb_det = det_log(b), lnb_std = std::log(b), inva = 1.0 / a;
+    const int32_t iq1 = (int32_t)q + 1;
+    const ExpRestricted01 e01(std::log((double)m_pmh / (double)(m_pmh - 1)));
+    auto regval = [&](double lb) {
+        const double fl = std::floor(1.0 - lb);
+        const int32_t z = fl >= 2147483647.0 ? 2147483647 : (fl <= -2147483648.0 ? (int32_t)(-2147483647 - 1) : (int32_t)fl);
+        return std::max(0, std::min(iq1, z));
+    };
+    auto work = [&](int t) {
+        std::array<uint64_t, 9>& c = acc[(size_t)t];
+        c.fill(0);
+        for (uint64_t i = (uint64_t)t; i < nkeys; i += (uint64_t)nthreads) {
+            const uint64_t key = synth_z(seed, i);
+            {  // SetSketch points: the same key through an all-deterministic and an all-libm pipeline
+                int32_t kd[64], ks[64];
+                const uint32_t np_ = std::min<uint32_t>(std::min<uint64_t>(points, m), 64);
+                for (int pass = 0; pass < 2; ++pass) {
+                    const bool det = pass == 0;
+                    Xoshiro256pp rng(key);
+                    double x_pred = 0.0;
+                    for (uint32_t j = 0; j < np_; ++j) {
+                        double e;
+                        for (;;) {  // Exp1 (ziggurat)
+                            const uint64_t bits = rng.next_u64();
+                            const unsigned zi = (unsigned)(bits & 0xff);
+                            const double u = detmath_from_bits((bits >> 12) | 0x3FF0000000000000ULL) - (1.0 - 2.220446049250313e-16 / 2.0);
+                            const double x = u * ZIG_X[zi];
+                            if (x < ZIG_X[zi + 1]) {
+                                e = x;
+                                break;
+                            }
+                            if (zi == 0) {
+                                const double uu = std_uniform_f64(rng);
+                                if (det) {
+                                    ++c[3];
+                                    c[4] += detmath_bits(det_log(uu)) != detmath_bits(std::log(uu));
+                                }
+                                e = ZIG_EXP_R - (det ? det_log(uu) : std::log(uu));
+                                break;
+                            }
+                            const double lhs = ZIG_F[zi + 1] + (ZIG_F[zi] - ZIG_F[zi + 1]) * std_uniform_f64(rng);
+                            const double ex = det ? det_exp(-x) : std::exp(-x);
+                            if (det) {
+                                ++c[3];
+                                c[4] += detmath_bits(ex) != detmath_bits(std::exp(-x));
+                                c[5] += (lhs < ex) != (lhs < std::exp(-x));
+                            }
+                            if (lhs < ex) {
+                                e = x;
+                                break;
+                            }
+                        }
+                        const double x_j = x_pred + (inva / (double)(m - j)) * e;
+                        x_pred = x_j;
+                        if (det) {
+                            ++c[0];
+                            c[1] += detmath_bits(det_log(x_j)) != detmath_bits(std::log(x_j));
+                        }
+                        (det ? kd : ks)[j] = regval(det ? det_log(x_j) / lnb_det : std::log(x_j) / lnb_std);
+                        (void)rng.unif01();  // the FYshuffle draw between two points
+                    }
+                }
+                bool same = true;
+                for (uint32_t j = 0; j < np_; ++j) same &= kd[j] == ks[j];
+                c[2] += !same;
+            }
+            {  // ExpRestricted01, rejection branch entered with probability 1 - 1/c1
+                Xoshiro256pp rng(key ^ 0x5DEECE66DULL);
+                for (uint32_t rep = 0; rep < points; ++rep) {
+                    double x = e01.c1 * rng.unif01();
+                    if (x < 1.0) continue;
+                    for (;;) {
+                        x = rng.unif01();
+                        if (x < e01.c2) break;
+                        double y = 0.5 * rng.unif01();
+                        if (y > 1.0 - x) {
+                            x = 1.0 - x;
+                            y = 1.0 - y;
+                        }
+                        if (x <= e01.c3 * (1.0 - y)) break;
+                        if (e01.c1 * y <= 1.0 - x) break;
+                        const double arg = e01.lambda * (1.0 - x), lhs = y * e01.c1 * e01.lambda;
+                        const double m1 = det_expm1(arg), m2 = std::expm1(arg);
+                        ++c[6];
+                        c[7] += detmath_bits(m1) != detmath_bits(m2);
+                        c[8] += (lhs <= m1) != (lhs <= m2);
+                        if (lhs <= m1) break;
+                    }
+                }
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) th.emplace_back(work, t);
+    for (auto& t : th) t.join();
+    for (int j = 0; j < 9; ++j) {
+        out[j] = 0;
+        for (int t = 0; t < nthreads; ++t) out[j] += acc[(size_t)t][(size_t)j];
+    }
+}
 double orc_exp1_from_seed(uint64_t seed, int skip) {
     Xoshiro256pp rng(seed);
     double v = 0;

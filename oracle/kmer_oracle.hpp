@@ -134,6 +134,11 @@ void orc_sketch_setsketch_batch(const uint8_t* packed, const uint64_t* byte_off,
                                 double a, uint64_t q, int sig_bytes, void* out, int nthreads);
 double orc_det_log(double x);
 double orc_det_exp(double x);
+double orc_det_expm1(double x);
+// statistics of the deviations of det_log / det_exp / det_expm1 from the platform libm on arguments drawn as the sketchers
+// draw them (see kmer_oracle.cpp); out: 9 counters
+void orc_libm_divergence(uint64_t nkeys, uint64_t seed, double b, uint64_t m, double a, uint64_t q, uint32_t points, uint32_t m_pmh,
+                         int nthreads, uint64_t* out);
 double orc_exp1_from_seed(uint64_t seed, int skip);
 
 // ---- A15 : counting (exact multiset semantics of KmerCounter, kmercount.rs:241-288) -----

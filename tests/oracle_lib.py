@@ -106,6 +106,10 @@ class Oracle:
         L.orc_det_log.argtypes = [C.c_double]
         L.orc_det_exp.restype = C.c_double
         L.orc_det_exp.argtypes = [C.c_double]
+        L.orc_det_expm1.restype = C.c_double
+        L.orc_det_expm1.argtypes = [C.c_double]
+        L.orc_libm_divergence.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, C.c_double, C.c_uint64, C.c_uint32,
+                                          C.c_uint32, C.c_int, u64p]
         L.orc_exp1_from_seed.restype = C.c_double
         L.orc_exp1_from_seed.argtypes = [C.c_uint64, C.c_int]
         L.orc_count_kmers.restype = C.c_uint64
@@ -321,6 +325,17 @@ class Oracle:
             self.L.orc_sample_read(_ptr(g, u8p), glen, seed, r, read_len, err_ppm, _ptr(buf, u8p))
             out.append(buf.tobytes())
         return out
+
+    def libm_divergence(self, nkeys, seed=1, params=(1.001, 4096, 20.0, 65534), points=4, m_pmh=2, nthreads=0):
+        """Deviations of the deterministic ln / exp / expm1 from the platform libm on arguments drawn as the sketchers draw
+        them -> dict of the 9 counters of orc_libm_divergence."""
+        out = np.zeros(9, dtype=np.uint64)
+        b, m, a, q = params
+        self.L.orc_libm_divergence(int(nkeys), int(seed), float(b), int(m), float(a), int(q), int(points), int(m_pmh), int(nthreads),
+                                   _ptr(out, u64p))
+        names = ["ln_evals", "ln_bits_differ", "keys_with_different_registers", "zig_evals", "zig_bits_differ", "zig_wedge_decision_differs",
+                 "expm1_evals", "expm1_bits_differ", "expm1_decision_differs"]
+        return {n: int(v) for n, v in zip(names, out)}
 
     def hardware_threads(self):
         return int(self.L.orc_hardware_threads())

@@ -51,6 +51,24 @@ def test_pmh3a_weighted_set(engine, oracle, dtype):
         engine.pmh3a_weighted(np.array([1, 2], dtype=dtype), np.array([1.0, 0.0]), 10)
 
 
+@pytest.mark.parametrize("m", [2, 3])
+def test_pmh3a_tiny_sketch_stress(engine, oracle, m):
+    """m = 2 and 3 (lambda = ln 2, ln 1.5): the sketch sizes that send the most draws through the rejection branch of
+    ExpRestricted01, down to its last test `y c1 lambda <= expm1(lambda (1 - x))` -- evaluated with the SAME deterministic
+    expm1 on the device and in the oracle (kmu_detmath.cuh == oracle/det_math.hpp).  1.2e7 weighted items."""
+    rng = np.random.default_rng(100 + m)
+    keys = np.unique(rng.integers(0, np.iinfo(np.uint64).max, 12_000_000, dtype=np.uint64))
+    w = rng.integers(1, 6, len(keys)).astype(np.float64)
+    got = engine.pmh3a_weighted(keys, w, m)
+    want = oracle.pmh3a_weighted(keys, w, m, 8)
+    assert np.array_equal(got.astype(np.uint64), want)
+    # many small sets as well: every one of them decides its slots among a handful of items
+    for rep in range(200):
+        kk = np.unique(rng.integers(0, 1 << 32, rng.integers(1, 40), dtype=np.uint64).astype(np.uint32))
+        ww = rng.integers(1, 4, len(kk)).astype(np.float64)
+        assert np.array_equal(engine.pmh3a_weighted(kk, ww, m).astype(np.uint64), oracle.pmh3a_weighted(kk.astype(np.uint64), ww, m, 4))
+
+
 def test_slices(engine, oracle):
     rng = np.random.default_rng(8)
     nb = np.array([1000, 37, 5000, 16, 64], dtype=np.uint64)
