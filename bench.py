@@ -98,6 +98,31 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned memory is allocated: pinned pages
+    are then first-touched on that node and the H2D copies do not cross the socket interconnect.  -> description (or why not)"""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (dom, bus, dev)
+        node = int(open(path + "/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": node, "bound": False, "why": "the platform reports no NUMA node for the GPU"}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"numa_node": node, "bound": False, "why": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as exc:  # containers without /sys: run unbound
+        return {"bound": False, "why": f"{type(exc).__name__}: {exc}"}
+
+
 def cpu_sample_rate(orc, nbases, seed, target_s, nthreads):
     """Time the oracle port (one task per read over nthreads, like rayon in the reference) on a
     bounded prefix of the workload sized for about target_s seconds."""
@@ -186,6 +211,8 @@ def main():
 
     assert args.warmup >= 0 and args.steps >= 1
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -293,33 +320,84 @@ def main():
         pin_in = torch.empty(len(packed_host) + 64, dtype=torch.uint8).pin_memory()
         pin_in[: len(packed_host)] = torch.from_numpy(packed_host)
         pin_out = torch.empty((nseq, M), dtype=torch.int32).pin_memory()
-        del packed_host
 
         def e2e_step():
             eng.sketch_pmh3a_host((pin_in.data_ptr(), pin_in.numel()), off_host, nbases, K, KMER_TYPE, HASH_KIND, M,
                                   pin_out.data_ptr())
 
+        def timed_calls(fn, n):
+            """n calls between two barriers -> (seconds per call of this rank, max over ranks)"""
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            mine = (time.perf_counter() - t0) / n
+            barrier()
+            worst = mine
+            if world > 1:
+                t = torch.tensor([mine], dtype=torch.float64, device=f"cuda:{local_rank}")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                worst = float(t.item())
+            return mine, worst
+
         e2e_step()
-        barrier()
-        t0 = time.perf_counter()
         n_e2e = max(1, args.steps)
-        for _ in range(n_e2e):
-            e2e_step()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / n_e2e
-        if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+        mine_s, e2e_s = timed_calls(e2e_step, n_e2e)
         tm = eng.last_times()
         e2e = {"value": total_bases * world / e2e_s / 1e9, "unit": "Gbases/s",
                "h2d_bytes_per_step": int(tm["h2d_bytes"]), "d2h_bytes_per_step": int(tm["d2h_bytes"]),
-               "ms_per_step": e2e_s * 1e3, "steps": n_e2e,
+               "ms_per_step": e2e_s * 1e3, "ms_per_step_this_rank": mine_s * 1e3, "steps": n_e2e,
                "h2d_ms": tm["h2d_ms"], "kernel_ms": tm["kernel_ms"], "d2h_ms": tm["d2h_ms"], "host_ms": tm["host_ms"],
-               "api": "kmu_sketch_pmh3a_host (pinned host buffers, 3-stream chunked pipeline)"}
+               "numa": numa,
+               "api": "kmu_sketch_pmh3a_host (pinned host buffers in the batch layout, 3-stream chunked pipeline)"}
         # the signatures the host got must be the ones left in HBM by the device-resident path
         if not torch.equal(pin_out, sig_dev.cpu()):
             raise SystemExit("e2e signatures differ from the device-resident run")
+
+        # the host ceiling: the same bytes with NOTHING but the copies, all ranks at once -- what the box's PCIe / host
+        # memory gives N GPUs together; e2e cannot beat max(copy time, kernel time)
+        cs, cs2 = torch.cuda.Stream(device=f"cuda:{local_rank}"), torch.cuda.Stream(device=f"cuda:{local_rank}")
+        dbuf = torch.empty(pin_in.numel(), dtype=torch.uint8, device=f"cuda:{local_rank}")
+
+        def copies():  # the two directions at the same time, as the pipeline runs them
+            with torch.cuda.stream(cs):
+                dbuf.copy_(pin_in, non_blocking=True)
+            with torch.cuda.stream(cs2):
+                pin_out.copy_(sig_dev, non_blocking=True)
+            cs.synchronize()
+            cs2.synchronize()
+
+        copies()
+        _, copy_s = timed_calls(copies, 3)
+        bytes_moved = pin_in.numel() + pin_out.numel() * 4
+        e2e["host_ceiling"] = {"copies_only_ms": copy_s * 1e3, "gbs_per_gpu_both_directions": bytes_moved / copy_s / 1e9,
+                               "gbs_all_gpus": bytes_moved * world / copy_s / 1e9,
+                               "bound_ms": max(copy_s * 1e3, ms_per_step),
+                               "e2e_over_bound": e2e_s * 1e3 / max(copy_s * 1e3, ms_per_step),
+                               "note": "H2D of the packed reads and D2H of the signatures alone, the two directions on two streams, "
+                                       "every rank at the same time (max over ranks); bound_ms = max(copies, device-resident step)"}
+        del dbuf
+
+        # the same call from SEPARATE per-sequence host allocations (the `&[&Sequence]` the Rust entry points get): one numpy
+        # array per read, gathered into pinned staging memory by the library while the previous chunk is sketched
+        sizes = (nbases + np.uint64(3)) // np.uint64(4)
+        seqs = [packed_host[int(o): int(o) + int(sz)].copy() for o, sz in zip(off_host, sizes)]
+        addrs = np.array([a.ctypes.data for a in seqs], dtype=np.uint64)
+        del packed_host
+        pin_out.zero_()
+
+        def e2e_ptrs_step():
+            eng.sketch_pmh3a_host_ptrs(addrs, nbases, K, KMER_TYPE, HASH_KIND, M, pin_out.data_ptr())
+
+        e2e_ptrs_step()
+        _, ptrs_s = timed_calls(e2e_ptrs_step, min(n_e2e, 3))
+        if not torch.equal(pin_out, sig_dev.cpu()):
+            raise SystemExit("e2e (separate sequences) signatures differ from the device-resident run")
+        tm = eng.last_times()
+        e2e["from_separate_sequences"] = {"value": total_bases * world / ptrs_s / 1e9, "unit": "Gbases/s", "ms_per_step": ptrs_s * 1e3,
+                                          "host_ms": tm["host_ms"], "api": "kmu_sketch_pmh3a_host_ptrs (one host allocation per read, "
+                                          "gathered by up to 16 host threads into pinned staging memory, chunk by chunk)"}
+        del seqs, addrs
 
     # ---- a step on a FRESH batch: includes the per-batch build of the processing order that later steps reuse ------
     eng.sync()
@@ -370,6 +448,7 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample ----------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, all_cpus)  # the CPU arm uses every host core, not only the GPU's NUMA node
         from oracle_lib import get_oracle
         orc = get_oracle()
         nthreads = orc.hardware_threads()

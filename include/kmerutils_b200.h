@@ -165,6 +165,13 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
                               const uint64_t* nbases, uint64_t nseq, uint32_t k, int32_t kmer_type, int32_t hash_kind,
                               uint32_t m, void* sig);
 
+/* the same with the sequences as nseq SEPARATE host allocations -- what `sketch_compressedkmer(&self, vseq: &[&Sequence], ..)`
+ * (setsketchert.rs:70-79) and `SeqSketcher::sketch_probminhash3a(&self, vseq: &[&Sequence], ..)` (seqsketchjaccard.rs:211-220)
+ * receive: seq_ptrs[i] = Sequence::seq of sequence i, ceil(nbases[i] / 4) bytes.  The sequences are gathered chunk by
+ * chunk into pinned staging memory by several host threads while the previous chunk is being sketched. */
+int32_t kmu_sketch_pmh3a_host_ptrs(kmu_ctx* ctx, const uint8_t* const* seq_ptrs, const uint64_t* nbases, uint64_t nseq,
+                                   uint32_t k, int32_t kmer_type, int32_t hash_kind, uint32_t m, void* sig);
+
 /* whole-file form: ONE signature for the batch (all contigs of a genome counted into one multiplicity
  * map), ProbHash3aSketch::sketch_compressedkmer_seqs  src/sketching/setsketchert.rs:160-202.  sig: m values. */
 int32_t kmu_sketch_pmh3a_whole(kmu_ctx* ctx, const kmu_seqbatch* batch, uint32_t k, int32_t kmer_type, int32_t hash_kind,

@@ -82,6 +82,8 @@ SIGNATURES = {
                                      C.c_int32]),
     "kmu_sketch_pmh3a_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, u64p, u64p, C.c_uint64, C.c_uint32,
                                           C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
+    "kmu_sketch_pmh3a_host_ptrs": (C.c_int32, [C.c_void_p, C.c_void_p, u64p, C.c_uint64, C.c_uint32, C.c_int32, C.c_int32,
+                                               C.c_uint32, C.c_void_p]),
     "kmu_sketch_pmh3a_whole": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32, C.c_void_p,
                                            C.c_int32]),
     "kmu_sketch_pmh3a_groups": (C.c_int32, [C.c_void_p, C.c_void_p, u64p, C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32,

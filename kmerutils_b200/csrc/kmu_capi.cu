@@ -1301,10 +1301,12 @@ int32_t kmu_sketch_pmh3a(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_
 // the batch layout (every sequence on a 16-byte boundary, back to back) is copied straight from
 // the caller's memory -- pin it for full PCIe speed; any other layout is re-laid out through a
 // pinned staging buffer first.
-int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t packed_bytes, const uint64_t* byte_off,
-                              const uint64_t* nbases, uint64_t nseq, uint32_t k, int32_t kmer_type, int32_t hash_kind,
-                              uint32_t m, void* sig) {
-    if (!ctx || (nseq && (!packed || !byte_off || !nbases))) return fail(KMU_EINVAL, "null argument");
+// ptrs != nullptr: the sequences are nseq separate host allocations (the `&[&Sequence]` of the Rust entry points); they are
+// gathered chunk by chunk into the pinned staging buffer by up to 16 host threads while the previous chunk is sketched.
+static int32_t sketch_pmh3a_host_impl(kmu_ctx* ctx, const uint8_t* packed, uint64_t packed_bytes, const uint64_t* byte_off,
+                                      const uint8_t* const* ptrs, const uint64_t* nbases, uint64_t nseq, uint32_t k,
+                                      int32_t kmer_type, int32_t hash_kind, uint32_t m, void* sig) {
+    if (!ctx || (nseq && (!nbases || (!ptrs && (!packed || !byte_off))))) return fail(KMU_EINVAL, "null argument");
     if (kmer_type_is_aa(kmer_type)) return fail(KMU_EINVAL, "the one-shot host form takes 2-bit DNA sequences");
     if (int32_t a = kmu_check_kmer_args(nullptr, k, kmer_type, hash_kind)) return a;
     if (m < 2) return fail(KMU_EINVAL, "ProbMinHash3a needs at least 2 hash values (m = %u)", m);
@@ -1312,16 +1314,17 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
     if (!sig) return fail(KMU_EINVAL, "null signature buffer");
     if (nseq >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "more than 2^32-1 sequences in one batch");
     // one pass: bounds, and whether the caller's buffer already is in the batch layout (then its offsets are used as they are)
-    bool same_layout = true;
+    bool same_layout = ptrs == nullptr;
     uint64_t total_bytes = 0;
     for (uint64_t i = 0; i < nseq; ++i) {
-        if (byte_off[i] + (nbases[i] + 3) / 4 > packed_bytes)
+        if (!ptrs && byte_off[i] + (nbases[i] + 3) / 4 > packed_bytes)
             return fail(KMU_EINVAL, "sequence %llu overruns the packed buffer", (unsigned long long)i);
+        if (ptrs && nbases[i] && !ptrs[i]) return fail(KMU_EINVAL, "sequence %llu: null pointer", (unsigned long long)i);
         if (nbases[i] >= (1ull << 30)) return fail(KMU_EINVAL, "a single sequence is limited to 2^30 bases here (kmu_sketch_pmh3a_whole has no limit)");
-        same_layout &= byte_off[i] == total_bytes;
+        if (!ptrs) same_layout &= byte_off[i] == total_bytes;
         total_bytes += align_up((nbases[i] + 3) / 4, SEQ_ALIGN);
     }
-    same_layout &= packed_bytes >= total_bytes;
+    if (!ptrs) same_layout &= packed_bytes >= total_bytes;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);
     const auto t_begin = std::chrono::steady_clock::now();
@@ -1440,9 +1443,14 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
         uint64_t* mh = (uint64_t*)hp.meta_host[sl].p;
         std::memcpy(mh, v.h_byte_off.data(), sizeof(uint64_t) * n);
         std::memcpy(mh + (max_seqs + 1), v.h_nbases.data(), sizeof(uint64_t) * n);
-        const uint8_t* src = packed + b0;
+        const uint8_t* src = same_layout ? packed + b0 : nullptr;
         if (!same_layout) {
-            parallel_copy((uint8_t*)hp.stage[sl].p, v.h_byte_off, nullptr, packed, byte_off + s0, nbases + s0, n);
+            if (c >= 2) {
+                // the staging buffer of this slot fed the upload of chunk c - 2: that copy must be over before it is refilled
+                CUDA_TRY(cudaEventSynchronize(hp.in_done[sl]));
+            }
+            if (ptrs) parallel_copy((uint8_t*)hp.stage[sl].p, v.h_byte_off, ptrs + s0, nullptr, nullptr, nbases + s0, n);
+            else parallel_copy((uint8_t*)hp.stage[sl].p, v.h_byte_off, nullptr, packed, byte_off + s0, nbases + s0, n);
             src = (const uint8_t*)hp.stage[sl].p;
         }
         CUDA_TRY(cudaEventRecord(hp.in_begin[sl], hp.copy_in));
@@ -1540,6 +1548,18 @@ int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t pack
     stamp("all streams idle", 0);
     ctx->last.host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return KMU_OK;
+}
+
+int32_t kmu_sketch_pmh3a_host(kmu_ctx* ctx, const uint8_t* packed, uint64_t packed_bytes, const uint64_t* byte_off,
+                              const uint64_t* nbases, uint64_t nseq, uint32_t k, int32_t kmer_type, int32_t hash_kind,
+                              uint32_t m, void* sig) {
+    return sketch_pmh3a_host_impl(ctx, packed, packed_bytes, byte_off, nullptr, nbases, nseq, k, kmer_type, hash_kind, m, sig);
+}
+
+int32_t kmu_sketch_pmh3a_host_ptrs(kmu_ctx* ctx, const uint8_t* const* seq_ptrs, const uint64_t* nbases, uint64_t nseq, uint32_t k,
+                                   int32_t kmer_type, int32_t hash_kind, uint32_t m, void* sig) {
+    if (nseq && !seq_ptrs) return fail(KMU_EINVAL, "null argument");
+    return sketch_pmh3a_host_impl(ctx, nullptr, 0, nullptr, seq_ptrs, nbases, nseq, k, kmer_type, hash_kind, m, sig);
 }
 
 }  // extern "C"

@@ -77,16 +77,11 @@ __device__ __forceinline__ unsigned long long direct_word(double h, uint32_t pt,
     return ((unsigned long long)__double_as_longlong(h) & ~0x1FFFFULL) | (pt << 16) | pk;
 }
 
-// an offer that may lower its slot (rare): 64-bit CAS; equal top 47 bits with another offer -> tie
+// an offer that may lower its slot (rare): 64-bit minimum; equal top 47 bits with the value it met -> tie (the
+// sequence is flagged and redone by the general kernel, so what the slot holds after a tie does not matter)
 __device__ __forceinline__ bool direct_offer_slow(unsigned long long* slot, unsigned long long mine) {
-    unsigned long long cur = *(volatile unsigned long long*)slot;
-    while (mine < cur) {
-        if (((mine ^ cur) >> 17) == 0) break;
-        const unsigned long long seen = atomicCAS(slot, cur, mine);
-        if (seen == cur) break;
-        cur = seen;
-    }
-    return ((mine ^ cur) >> 17) == 0 && mine != cur;
+    const unsigned long long old = atomicMin(slot, mine);
+    return ((mine ^ old) >> 17) == 0 && mine != old;
 }
 
 // point pt (0, 1) of an item from its memo entry {x lo, x hi, slot, key} and 1 / count
@@ -300,9 +295,9 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
                     const uint4 v = ((uint4*)hist)[j];
                     ((uint4*)hist)[j] = make_uint4(0, 0, 0, 0);
                     const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+                    if (HB == 8) {
 #pragma unroll
-                    for (uint32_t w = 0; w < 4; ++w) {
-                        if (HB == 8) {
+                        for (uint32_t w = 0; w < 4; ++w) {
                             uint32_t hit = __vcmpgeu4(wv[w], need4);
                             while (hit) {
                                 const uint32_t b = (__ffs(hit) - 1) >> 3;
@@ -310,16 +305,30 @@ __global__ void __launch_bounds__(NT, MINB) pmh3a_direct_kernel(const Pmh3aParam
                                 const uint32_t pos = atomicAdd(&st->nitems, 1u);
                                 if (pos < items_cap) items[pos] = (j * 16 + w * 4 + b) | (((wv[w] >> (b * 8)) & 0xFFu) << 16);
                             }
-                        } else {
+                        }
+                    } else {
+                        // even / odd nibbles as bytes; one test for the whole 16 bytes (32 counters), the listing loop only
+                        // where a counter qualifies -- almost never
+                        uint32_t he[4], ho[4], any = 0;
 #pragma unroll
-                            for (uint32_t half = 0; half < 2; ++half) {  // even / odd nibbles as bytes
-                                const uint32_t nib = (wv[w] >> (half * 4)) & 0x0F0F0F0Fu;
-                                uint32_t hit = __vcmpgeu4(nib, need4);
-                                while (hit) {
-                                    const uint32_t b = (__ffs(hit) - 1) >> 3;
-                                    hit &= ~(0xFFu << (b * 8));
-                                    const uint32_t pos = atomicAdd(&st->nitems, 1u);
-                                    if (pos < items_cap) items[pos] = (j * 32 + w * 8 + b * 2 + half) | (((nib >> (b * 8)) & 0xFFu) << 16);
+                        for (uint32_t w = 0; w < 4; ++w) {
+                            he[w] = __vcmpgeu4(wv[w] & 0x0F0F0F0Fu, need4);
+                            ho[w] = __vcmpgeu4((wv[w] >> 4) & 0x0F0F0F0Fu, need4);
+                            any |= he[w] | ho[w];
+                        }
+                        if (any) {
+#pragma unroll
+                            for (uint32_t w = 0; w < 4; ++w) {
+#pragma unroll
+                                for (uint32_t half = 0; half < 2; ++half) {
+                                    const uint32_t nib = (wv[w] >> (half * 4)) & 0x0F0F0F0Fu;
+                                    uint32_t hit = half ? ho[w] : he[w];
+                                    while (hit) {
+                                        const uint32_t b = (__ffs(hit) - 1) >> 3;
+                                        hit &= ~(0xFFu << (b * 8));
+                                        const uint32_t pos = atomicAdd(&st->nitems, 1u);
+                                        if (pos < items_cap) items[pos] = (j * 32 + w * 8 + b * 2 + half) | (((nib >> (b * 8)) & 0xFFu) << 16);
+                                    }
                                 }
                             }
                         }

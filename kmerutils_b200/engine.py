@@ -371,6 +371,15 @@ class Engine:
                                              k, kmer_type, hash_kind, m, C.c_void_p(optr)))
         return out
 
+    def sketch_pmh3a_host_ptrs(self, seq_addrs, nbases, k, kmer_type, hash_kind, m, out):
+        """One-shot from nseq SEPARATE host allocations (the `&[&Sequence]` form): seq_addrs = uint64 array of addresses."""
+        addrs = np.ascontiguousarray(seq_addrs, dtype=np.uint64)
+        nb = _as_u64(nbases)
+        optr = out.ctypes.data if isinstance(out, np.ndarray) else out
+        check(self.lib.kmu_sketch_pmh3a_host_ptrs(self.ctx, _p(addrs), _p(nb, u64p), len(nb), k, kmer_type, hash_kind, m,
+                                                  C.c_void_p(optr)))
+        return out
+
     def signature_jaccard(self, sig_a, sig_b):
         """(na, nb) matrix of Jaccard estimates = fraction of equal slots (compute_probminhash_jaccard,
         seqsketchjaccard.rs:86-108).  sig_a (na, m), sig_b (nb, m), same dtype (any 2 / 4 / 8 byte slot type)."""

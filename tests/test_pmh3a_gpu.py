@@ -133,6 +133,27 @@ def test_host_pipeline(engine, oracle, chunk_bytes, ragged, monkeypatch):
     assert t["d2h_bytes"] == out.nbytes and t["h2d_bytes"] > 0 and t["host_ms"] > 0
 
 
+@pytest.mark.parametrize("chunk_bytes", [None, 4096])
+def test_host_pipeline_from_separate_sequences(engine, oracle, chunk_bytes, monkeypatch):
+    # kmu_sketch_pmh3a_host_ptrs: every sequence its own host allocation (the `&[&Sequence]` of the Rust entry points,
+    # setsketchert.rs:70-79), gathered into pinned staging memory chunk by chunk.  Same signatures.
+    rng = np.random.default_rng(19)
+    nb = np.concatenate([[1, 7, 8, 40000], rng.integers(8, 7000, 6000)]).astype(np.uint64)
+    packed, off = oracle_batch(oracle, 35, nb)
+    want = oracle.sketch_pmh3a_batch(packed, off, nb, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200)
+    seqs = [np.array(packed[int(o): int(o) + (int(n) + 3) // 4], dtype=np.uint8, copy=True) for o, n in zip(off, nb)]
+    addrs = np.array([a.ctypes.data for a in seqs], dtype=np.uint64)
+    if chunk_bytes:
+        monkeypatch.setenv("KMU_HOST_CHUNK_BYTES", str(chunk_bytes))
+    out = np.zeros((len(nb), 200), dtype=np.uint32)
+    engine.sketch_pmh3a_host_ptrs(addrs, nb, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200, out)
+    assert np.array_equal(out, want)
+    with pytest.raises(kb.KmuInvalid):
+        bad = addrs.copy()
+        bad[3] = 0
+        engine.sketch_pmh3a_host_ptrs(bad, nb, 8, kb.KMER32, kb.HASH_CANON_INVHASH, 200, out)
+
+
 def test_host_pipeline_with_redo_sequences(engine, oracle, monkeypatch):
     # sequences whose u8 histogram counters wrap are redone by a second launch per chunk: with several chunks in
     # flight every chunk parity has its own counters / redo list
