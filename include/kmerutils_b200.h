@@ -332,6 +332,20 @@ int32_t kmu_fastx_next_pack(kmu_fastx* reader, uint64_t max_seqs, uint8_t* ascii
                             uint64_t* nseq_out);
 void kmu_fastx_stats(const kmu_fastx* reader, uint64_t* nb_read, uint64_t* nb_bad_read, uint64_t* nb_bases,
                      uint64_t* nb_bad_bases);
+/* Multi-threaded form of the feeder (kmu_ingest.cu): a reader thread cuts the file into blocks at record boundaries, `nthreads`
+ * parser threads (0 = all host cores) check and copy the accepted reads of a block into a pinned pack buffer, and the packs come
+ * out in file order while the parsers work ahead -- the loop of src/bin/datasketcher.rs:236-300 with the sketch of pack i
+ * overlapping the parsing of packs i + 1 ...  FASTA (sequences on any number of lines) and 4-line FASTQ, plain or gzip-compressed
+ * (the inflation of a gzip stream stays serial); a FASTQ with sequences on several lines is refused (use kmu_fastx_open).
+ *   kmu_ingest_next    : *ascii / *ascii_off / *nseq = the next pack (for kmu_seqbatch_from_ascii), valid until
+ *                        kmu_ingest_release(token); *nseq == 0 at end of file. */
+typedef struct kmu_ingest kmu_ingest;
+int32_t kmu_ingest_open(const char* path, uint32_t nthreads, uint64_t block_bytes, kmu_ingest** reader);
+int32_t kmu_ingest_next(kmu_ingest* reader, const uint8_t** ascii, const uint64_t** ascii_off, uint64_t* nseq, void** token);
+int32_t kmu_ingest_release(kmu_ingest* reader, void* token);
+void kmu_ingest_stats(const kmu_ingest* reader, uint64_t* nb_read, uint64_t* nb_bad_read, uint64_t* nb_bases,
+                      uint64_t* nb_bad_bases);
+void kmu_ingest_close(kmu_ingest* reader);
 /* signature dump: `u32 0xceabeadd | u32 sig_size = 4 | u32 sketch_size | u32 kmer_size`, then sketch_size u32 per
  * sequence in input order (SeqSketcher::create_signature_dump, dump_signatures_block_u32,
  * src/sketching/seqsketchjaccard.rs:390-414, 577-585) */

@@ -115,6 +115,11 @@ SIGNATURES = {
     "kmu_fastx_close": (None, [C.c_void_p]),
     "kmu_fastx_next_pack": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p, u64p]),
     "kmu_fastx_stats": (None, [C.c_void_p, u64p, u64p, u64p, u64p]),
+    "kmu_ingest_open": (C.c_int32, [C.c_char_p, C.c_uint32, C.c_uint64, vpp]),
+    "kmu_ingest_next": (C.c_int32, [C.c_void_p, vpp, vpp, u64p, vpp]),
+    "kmu_ingest_release": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "kmu_ingest_stats": (None, [C.c_void_p, u64p, u64p, u64p, u64p]),
+    "kmu_ingest_close": (None, [C.c_void_p]),
     "kmu_sigdump_create": (C.c_int32, [C.c_char_p, C.c_uint32, C.c_uint32, vpp]),
     "kmu_sigdump_write": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "kmu_blockdump_create": (C.c_int32, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, vpp]),

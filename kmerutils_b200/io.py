@@ -54,6 +54,83 @@ class FastxReader:
         self.close()
 
 
+class IngestReader:
+    """Multi-threaded feeder (kmu_ingest_*): packs of accepted reads in file order, parsed by `nthreads` host threads into
+    pinned buffers while the caller works on the previous pack."""
+
+    def __init__(self, path, nthreads=0, block_bytes=64 << 20):
+        self.lib = _lib.load_library()
+        h = C.c_void_p()
+        check(self.lib.kmu_ingest_open(os.fsencode(path), int(nthreads), int(block_bytes), C.byref(h)))
+        self._h = h
+
+    def next(self):
+        """-> (ascii address, offsets array view [n + 1], n, token) or None at end of file; call release(token) when the
+        pack has been uploaded"""
+        a, o, tok = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n = C.c_uint64()
+        check(self.lib.kmu_ingest_next(self._h, C.byref(a), C.byref(o), C.byref(n), C.byref(tok)))
+        if n.value == 0:
+            return None
+        off = np.ctypeslib.as_array(C.cast(o, C.POINTER(C.c_uint64)), shape=(n.value + 1,))
+        return a.value, off, int(n.value), tok
+
+    def release(self, token):
+        check(self.lib.kmu_ingest_release(self._h, token))
+
+    def stats(self):
+        v = [C.c_uint64() for _ in range(4)]
+        self.lib.kmu_ingest_stats(self._h, *[C.byref(x) for x in v])
+        return dict(zip(("nb_read", "nb_bad_read", "nb_bases", "nb_bad_bases"), (x.value for x in v)))
+
+    def close(self):
+        if self._h is not None:
+            self.lib.kmu_ingest_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def datasketcher_mt(engine, fastx_path, dump_path=None, kmer_size=8, sketch_size=200, nthreads=0, block_bytes=64 << 20,
+                    sink=None):
+    """The datasketcher loop (src/bin/datasketcher.rs:236-300) on the multi-threaded feeder: the host threads parse the
+    following packs while the GPU packs (kmu_seqbatch_from_ascii from pinned memory) and sketches the current one.
+    Signatures go to the dump file and / or to sink(sig) in file order.  -> dict(reads, bases, seconds, stats)"""
+    import time
+
+    from ._lib import HASH_CANON_INVHASH, KMER32
+    t0 = time.perf_counter()
+    n_done = bases = 0
+    out = SignatureDump(dump_path, sketch_size, kmer_size) if dump_path else None
+    with IngestReader(fastx_path, nthreads, block_bytes) as rd:
+        while True:
+            pack = rd.next()
+            if pack is None:
+                break
+            addr, off, n, tok = pack
+            h = C.c_void_p()
+            check(engine.lib.kmu_seqbatch_from_ascii(engine.ctx, C.c_void_p(addr), _p(off, u64p), n, 0, None, C.byref(h)))
+            rd.release(tok)  # the pack is on the device: its buffer goes back to the parsers
+            from .engine import SeqBatch
+            batch = SeqBatch(engine, h)
+            sig = engine.sketch_pmh3a(batch, kmer_size, KMER32, HASH_CANON_INVHASH, sketch_size)
+            bases += batch.total_bases
+            batch.destroy()
+            if out:
+                out.write(sig)
+            if sink:
+                sink(sig)
+            n_done += n
+        stats = rd.stats()
+    if out:
+        out.close()
+    return {"reads": n_done, "bases": bases, "seconds": time.perf_counter() - t0, "stats": stats}
+
+
 class SignatureDump:
     """SeqSketcher::create_signature_dump + dump_signatures_block_u32."""
 

@@ -145,3 +145,83 @@ def test_block_dump_format(tmp_path):
 def test_sketch_params_json(tmp_path):
     kio.dump_sketch_params(str(tmp_path), 8, 200, "PROB3A", "DNA")
     assert kio.reload_sketch_params(str(tmp_path)) == {"kmer_size": 8, "sketch_size": 200, "algo": "PROB3A", "data_t": "DNA"}
+
+
+def _all_reads_single(path):
+    out = []
+    with kio.FastxReader(path) as rd:
+        while True:
+            pack = rd.next_pack(1000)
+            if not pack:
+                break
+            out += pack
+        return out, rd.stats()
+
+
+def _all_reads_mt(path, nthreads, block_bytes):
+    import ctypes as C
+    out = []
+    with kio.IngestReader(path, nthreads, block_bytes) as rd:
+        while True:
+            pack = rd.next()
+            if pack is None:
+                break
+            addr, off, n, tok = pack
+            buf = (C.c_uint8 * int(off[n])).from_address(addr)
+            raw = bytes(buf)
+            out += [raw[int(off[i]): int(off[i + 1])] for i in range(n)]
+            rd.release(tok)
+        return out, rd.stats()
+
+
+@pytest.mark.parametrize("fmt", ["fastq", "fasta", "fastq.gz"])
+def test_multithreaded_feeder_matches_the_serial_reader(tmp_path, fmt):
+    """kmu_ingest_* (reader thread + parser threads + ordered packs) against kmu_fastx_*: the same accepted reads in the same
+    order and the same statistics, for blocks far smaller than the file (boundaries fall everywhere: inside headers,
+    sequences, quality lines that start with '@')."""
+    import gzip
+    rng = np.random.default_rng(11)
+    recs = []
+    for i in range(3000):
+        n = int(rng.integers(1, 400))
+        s = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), n).tobytes()
+        if i % 17 == 0:
+            s = s[: n // 2] + b"N" + s[n // 2:]       # dropped read
+        if i % 23 == 0:
+            s = s.lower()
+        recs.append((b"read%d some description" % i, s))
+    if fmt.startswith("fastq"):
+        quals = [rng.choice(np.frombuffer(b"@>+IIIIFF#", dtype=np.uint8), len(s)).tobytes() for _, s in recs]
+        text = b"".join(b"@" + h + b"\n" + s + b"\n+" + (h if i % 5 == 0 else b"") + b"\n" + q + b"\n"
+                        for i, ((h, s), q) in enumerate(zip(recs, quals)))
+    else:
+        text = b"".join(b">" + h + b"\n" + b"\n".join(s[j: j + 60] for j in range(0, len(s), 60)) + b"\n" for h, s in recs)
+    path = str(tmp_path / ("x." + fmt))
+    if fmt.endswith(".gz"):
+        with gzip.open(path, "wb") as f:
+            f.write(text)
+    else:
+        (tmp_path / ("x." + fmt)).write_bytes(text)
+    want, want_st = _all_reads_single(path)
+    assert len(want) == sum(1 for _, s in recs if b"N" not in s.upper())
+    for nthreads, block in ((1, 1 << 16), (4, 1 << 16), (8, 1 << 20)):
+        got, st = _all_reads_mt(path, nthreads, block)
+        assert got == want
+        assert st == want_st
+
+
+def test_multithreaded_feeder_long_records_and_errors(tmp_path):
+    # one FASTA record larger than several blocks, then short ones; a FASTQ whose sequence spans two lines is refused
+    rng = np.random.default_rng(12)
+    big = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 700_000).tobytes()
+    text = b">big\n" + b"\n".join(big[j: j + 80] for j in range(0, len(big), 80)) + b"\n>s2\nACGT\n>s3\nGGNA\n>s4\nTT\n"
+    (tmp_path / "big.fa").write_bytes(text)
+    got, st = _all_reads_mt(str(tmp_path / "big.fa"), 3, 1 << 16)
+    assert got == [big, b"ACGT", b"TT"] and st["nb_bad_read"] == 1 and st["nb_read"] == 4
+    (tmp_path / "ml.fq").write_bytes(b"@r1\nACGT\nACGT\n+\nIIIIIIII\n" * 50)
+    with pytest.raises(kb.KmuError):
+        _all_reads_mt(str(tmp_path / "ml.fq"), 2, 1 << 16)
+    with pytest.raises(kb.KmuError):
+        kio.IngestReader(str(tmp_path / "missing.fq"))
+    (tmp_path / "empty.fq").write_bytes(b"")
+    assert _all_reads_mt(str(tmp_path / "empty.fq"), 2, 1 << 16)[0] == []
