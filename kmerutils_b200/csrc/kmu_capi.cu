@@ -157,7 +157,7 @@ void kmu_ctx_destroy(kmu_ctx* c) {
     ScopedDevice sd(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto* b : {&c->order, &c->counters, &c->table_scratch, &c->slot_scratch, &c->overflow, &c->sig_dev, &c->misc, &c->memo,
-                    &c->whole_table, &c->items_slots, &c->part_fine, &c->counters_alt, &c->overflow_alt, &c->smh_memo})
+                    &c->whole_table, &c->items_slots, &c->part_fine, &c->ascii_dev, &c->ascii_off_dev, &c->ascii_bad_dev, &c->counters_alt, &c->overflow_alt, &c->smh_memo})
         b->release();
     c->pinned.release();
     c->pinned_small.release();
@@ -344,12 +344,12 @@ int32_t kmu_seqbatch_from_ascii(kmu_ctx* ctx, const uint8_t* ascii, const uint64
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};
     const uint64_t total_ascii = nseq ? ascii_off[nseq] : 0;
-    DevBuf d_ascii, d_off, d_bad;
-    auto cleanup = [&]() {
-        d_ascii.release();
-        d_off.release();
-        d_bad.release();
-    };
+    // staging buffers owned by the context (grow-only): a feeder calls this once per pack, and cudaMalloc / cudaFree per
+    // call cost more than the upload itself
+    DevBuf& d_ascii = ctx->ascii_dev;
+    DevBuf& d_off = ctx->ascii_off_dev;
+    DevBuf& d_bad = ctx->ascii_bad_dev;
+    auto cleanup = [&]() {};
     cudaError_t e = d_ascii.reserve(total_ascii + 16);
     if (e == cudaSuccess) e = d_off.reserve(sizeof(uint64_t) * (nseq + 1));
     if (e == cudaSuccess) e = d_bad.reserve(sizeof(uint64_t) * (nseq + 1));

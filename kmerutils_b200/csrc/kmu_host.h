@@ -85,6 +85,7 @@ struct kmu_ctx {
     int sm_count = 148;
     // scratch
     DevBuf order, counters, table_scratch, slot_scratch, overflow, sig_dev, misc;
+    DevBuf ascii_dev, ascii_off_dev, ascii_bad_dev;  // staging of kmu_seqbatch_from_ascii / _from_aa (grow-only: no cudaMalloc per pack)
     DevBuf part_fine;  // level-2 slabs of the two-phase counting insertion (kmu_capi_count.cu)
     DevBuf whole_table, items_slots;  // whole-file ProbMinHash3a: counting table + global slots
     int p2p_grid = 0;  // kmu_count_partition_counts -> _scatter hand-over

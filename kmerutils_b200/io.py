@@ -103,32 +103,42 @@ def datasketcher_mt(engine, fastx_path, dump_path=None, kmer_size=8, sketch_size
     import time
 
     from ._lib import HASH_CANON_INVHASH, KMER32
+    from .engine import SeqBatch
     t0 = time.perf_counter()
-    n_done = bases = 0
+    n_done = bases = npacks = 0
+    t_wait = t_upload = t_sketch = 0.0
     out = SignatureDump(dump_path, sketch_size, kmer_size) if dump_path else None
     with IngestReader(fastx_path, nthreads, block_bytes) as rd:
+        t_open = time.perf_counter() - t0
         while True:
+            ta = time.perf_counter()
             pack = rd.next()
+            tb = time.perf_counter()
+            t_wait += tb - ta
             if pack is None:
                 break
             addr, off, n, tok = pack
             h = C.c_void_p()
             check(engine.lib.kmu_seqbatch_from_ascii(engine.ctx, C.c_void_p(addr), _p(off, u64p), n, 0, None, C.byref(h)))
             rd.release(tok)  # the pack is on the device: its buffer goes back to the parsers
-            from .engine import SeqBatch
+            tc = time.perf_counter()
+            t_upload += tc - tb
             batch = SeqBatch(engine, h)
             sig = engine.sketch_pmh3a(batch, kmer_size, KMER32, HASH_CANON_INVHASH, sketch_size)
             bases += batch.total_bases
             batch.destroy()
+            t_sketch += time.perf_counter() - tc
             if out:
                 out.write(sig)
             if sink:
                 sink(sig)
             n_done += n
+            npacks += 1
         stats = rd.stats()
     if out:
         out.close()
-    return {"reads": n_done, "bases": bases, "seconds": time.perf_counter() - t0, "stats": stats}
+    return {"reads": n_done, "bases": bases, "seconds": time.perf_counter() - t0, "stats": stats, "packs": npacks,
+            "open_s": t_open, "wait_for_parser_s": t_wait, "upload_and_pack_s": t_upload, "sketch_s": t_sketch}
 
 
 class SignatureDump:
