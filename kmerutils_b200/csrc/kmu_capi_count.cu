@@ -1066,8 +1066,18 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
         ScopedDevice sd(ctx->device);
         ctx->last = kmu_times{};
         cudaStream_t st = ctx->stream;
-        cudaError_t me = ctx->whole_table.reserve(cap_max * slot_bytes + sizeof(unsigned long long) * AUX_WORDS);
-        if (me == cudaSuccess) me = ctx->items_slots.reserve(sizeof(kmu::Slot) * m + 64);
+        // the genomes are independent: NS of them are in flight at once, each on its own stream with its own table and
+        // slots (one 5 Mb genome fills half of the GPU: its 64 MB table sits in L2, its launches are short)
+        const int NS = (int)std::min<uint64_t>(kmu_ctx::GROUP_STREAMS, ngroups);
+        cudaError_t me = cudaSuccess;
+        for (int q = 0; q < NS && me == cudaSuccess; ++q) {
+            if (!ctx->group_stream[q]) me = cudaStreamCreateWithFlags(&ctx->group_stream[q], cudaStreamNonBlocking);
+            if (me == cudaSuccess && !ctx->group_ev[q]) me = cudaEventCreateWithFlags(&ctx->group_ev[q], cudaEventDisableTiming);
+            if (me == cudaSuccess) me = ctx->group_table[q].reserve(cap_max * slot_bytes + sizeof(unsigned long long) * AUX_WORDS);
+            if (me == cudaSuccess) me = ctx->group_slots[q].reserve(sizeof(kmu::Slot) * m + 64);
+        }
+        if (me == cudaSuccess && !ctx->group_ev[kmu_ctx::GROUP_STREAMS])
+            me = cudaEventCreateWithFlags(&ctx->group_ev[kmu_ctx::GROUP_STREAMS], cudaEventDisableTiming);
         if (me == cudaSuccess) me = ctx->misc.reserve(sizeof(uint64_t) * (b->nseq + 1) + sizeof(unsigned long long) * ngroups + 64);
         if (me == cudaSuccess && !sig_on_device) me = ctx->sig_dev.reserve((size_t)ngroups * m * vsz);
         if (me != cudaSuccess) return fail(KMU_ENOMEM, "group sketch buffers: %s", cudaGetErrorString(me));
@@ -1081,16 +1091,19 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
         P.kmer_type = kmer_type;
         P.hash_kind = hash_kind;
         P.m = m;
-        P.global_slots = (kmu::Slot*)ctx->items_slots.p;
         const size_t smem = sizeof(kmu::Slot) * (size_t)m;
         P.slots_in_smem = smem + kmu::PMH3A_ITEMS_QUEUE_BYTES <= SMEM_BUDGET ? 1 : 0;
         P.slot_thresh = (uint32_t)(0x100000000ULL % m);
         fill_exp01(P.e, m);
         uint64_t launches = 0;
         cudaEventRecord(ctx->ev[0], st);
+        CUDA_TRY(cudaEventRecord(ctx->group_ev[kmu_ctx::GROUP_STREAMS], st));
+        for (int q = 0; q < NS; ++q) CUDA_TRY(cudaStreamWaitEvent(ctx->group_stream[q], ctx->group_ev[kmu_ctx::GROUP_STREAMS], 0));
         for (uint64_t g = 0; g < ngroups; ++g) {
+            const int q = (int)(g % (uint64_t)NS);
+            cudaStream_t gs = ctx->group_stream[q];
             if (nk[g] == 0) {  // no k-mer: the all-zero signature of an empty sketch
-                CUDA_TRY(cudaMemsetAsync(d_sig + g * (size_t)m * vsz, 0, (size_t)m * vsz, st));
+                CUDA_TRY(cudaMemsetAsync(d_sig + g * (size_t)m * vsz, 0, (size_t)m * vsz, gs));
                 continue;
             }
             uint64_t want = std::max<uint64_t>(1024, nk[g] + nk[g] / 2 + nk[g] / 16);  // load <= 0.64: a 5 Mb genome's table (64 MB) stays in L2
@@ -1098,18 +1111,19 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
             uint64_t cap = 1024;
             while (cap < want) cap <<= 1;
             kmu::CountTable t;
-            t.slots = ctx->whole_table.p;
+            t.slots = ctx->group_table[q].p;
             t.capmask = cap - 1;
-            unsigned long long* aux = (unsigned long long*)((uint8_t*)ctx->whole_table.p + cap_max * slot_bytes);
+            unsigned long long* aux = (unsigned long long*)((uint8_t*)ctx->group_table[q].p + cap_max * slot_bytes);
             t.special = aux;
             t.overflow = aux + 1;
-            CUDA_TRY(cudaMemsetAsync(aux, 0, sizeof(unsigned long long) * 8, st));
-            CUDA_TRY(kmu::launch_count_init(t, key64, ctx->sm_count, st));
+            CUDA_TRY(cudaMemsetAsync(aux, 0, sizeof(unsigned long long) * 8, gs));
+            CUDA_TRY(kmu::launch_count_init(t, key64, ctx->sm_count, gs));
             const uint64_t s0 = first[g], ns = group_sizes[g];
             const uint64_t Llast = b->h_nbases[s0 + ns - 1];
             const uint64_t bytes = rebased[s0 + ns - 1] + align_up((Llast + 3) / 4, SEQ_ALIGN);
             kmu::SeqView v{b->packed + b->h_byte_off[s0], d_rebased + s0, b->nbases + s0, ns};
-            CUDA_TRY(kmu::launch_count_insert_seqs(v, bytes, k, key64, kmu::hash_kind_is_canonical_host(hash_kind), t, ctx->sm_count, st));
+            CUDA_TRY(kmu::launch_count_insert_seqs(v, bytes, k, key64, kmu::hash_kind_is_canonical_host(hash_kind), t, ctx->sm_count, gs));
+            P.global_slots = (kmu::Slot*)ctx->group_slots[q].p;
             P.table = t.slots;
             P.special = t.special;
             P.n = cap;
@@ -1117,10 +1131,14 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
             P.bound = bounds[g];
             const uint64_t work = (P.n + 511) / 512;
             const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(work, (uint64_t)ctx->sm_count));
-            CUDA_TRY(kmu::launch_pmh3a_items_init(P.global_slots, m, st));
-            CUDA_TRY(kmu::launch_pmh3a_items(P, key64, key64 ? 2 : 1, grid, P.slots_in_smem ? smem : 0, st));
-            CUDA_TRY(kmu::launch_pmh3a_items_finish(P.global_slots, m, key64, d_sig + g * (size_t)m * vsz, d_tops + g, st));
+            CUDA_TRY(kmu::launch_pmh3a_items_init(P.global_slots, m, gs));
+            CUDA_TRY(kmu::launch_pmh3a_items(P, key64, key64 ? 2 : 1, grid, P.slots_in_smem ? smem : 0, gs));
+            CUDA_TRY(kmu::launch_pmh3a_items_finish(P.global_slots, m, key64, d_sig + g * (size_t)m * vsz, d_tops + g, gs));
             launches += 5;
+        }
+        for (int q = 0; q < NS; ++q) {
+            CUDA_TRY(cudaEventRecord(ctx->group_ev[q], ctx->group_stream[q]));
+            CUDA_TRY(cudaStreamWaitEvent(st, ctx->group_ev[q], 0));
         }
         cudaEventRecord(ctx->ev[1], st);
         CUDA_TRY(cudaMemcpyAsync(tops.data(), d_tops, sizeof(unsigned long long) * ngroups, cudaMemcpyDeviceToHost, st));

@@ -86,6 +86,11 @@ struct kmu_ctx {
     // scratch
     DevBuf order, counters, table_scratch, slot_scratch, overflow, sig_dev, misc;
     DevBuf ascii_dev, ascii_off_dev, ascii_bad_dev;  // staging of kmu_seqbatch_from_ascii / _from_aa (grow-only: no cudaMalloc per pack)
+    // kmu_sketch_pmh3a_groups: genomes are sketched on several streams at once, each with its own table and slots
+    static constexpr int GROUP_STREAMS = 4;
+    cudaStream_t group_stream[GROUP_STREAMS]{};
+    cudaEvent_t group_ev[GROUP_STREAMS + 1]{};
+    DevBuf group_table[GROUP_STREAMS], group_slots[GROUP_STREAMS];
     DevBuf part_fine;  // level-2 slabs of the two-phase counting insertion (kmu_capi_count.cu)
     DevBuf whole_table, items_slots;  // whole-file ProbMinHash3a: counting table + global slots
     int p2p_grid = 0;  // kmu_count_partition_counts -> _scatter hand-over

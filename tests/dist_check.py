@@ -57,6 +57,16 @@ def main():
     hll = kd.merge_registers(torch.from_numpy(hll_local.astype(np.int32)).cuda(), "max").cpu().numpy().astype(np.uint16)
     smh_local = eng.sketch_superminhash(mine, 21, kb.KMER64, kb.HASH_CANON_INVHASH, 256).min(axis=0)
     smh = kd.merge_registers(torch.from_numpy(smh_local).cuda(), "min").cpu().numpy()
+    # one long sequence cut into `world` chunks with a k - 1 halo (bench.py C5a at N > 1): rank r sketches chunk r, the
+    # registers merge with the allreduce
+    hl = np.array([3_000_000], dtype=np.uint64)
+    hfull = eng.batch_synth(21, hl)
+    hb = (hl * np.uint64(rank)) // np.uint64(world)
+    he = np.minimum(hl, (hl * np.uint64(rank + 1)) // np.uint64(world) + np.uint64(20))
+    hmine = eng.batch_slices(hfull, np.zeros(1, np.uint64), hb, he)
+    halo_local = eng.sketch_setsketch(hmine, 21, kb.KMER64, kb.HASH_CANON_INVHASH, (1.001, 256, 20.0, 65534), np.uint16, whole=True)
+    halo_hll = kd.merge_registers(torch.from_numpy(halo_local.astype(np.int32)).cuda(), "max").cpu().numpy().astype(np.uint16)
+    halo_whole = eng.sketch_setsketch(hfull, 21, kb.KMER64, kb.HASH_CANON_INVHASH, (1.001, 256, 20.0, 65534), np.uint16, whole=True)
     # whole-file ProbMinHash3a over the shards: owners count, sketch their keys, registers merge (min h, then key)
     pmh = {kk: kd.pmh3a_whole_sharded(eng, mine, kk, kt, kb.HASH_CANON_INVHASH, 500)
            for kk, kt in ((21, kb.KMER64), (16, kb.KMER16B32))}
@@ -87,6 +97,11 @@ def main():
         want_smh = orc.sketch_superminhash_seqs(buf, off, nb, 21, kb.KMER64, kb.HASH_CANON_INVHASH, 256)
         ok &= bool(np.array_equal(smh, want_smh))
         print(f"[dist_check] setsketch merge ok={np.array_equal(hll, want_hll)} superminhash merge ok={np.array_equal(smh, want_smh)}", flush=True)
+        hp_, ho_ = oracle_batch(orc, 21, hl)
+        want_halo = orc.sketch_setsketch_seqs(hp_, ho_, hl, 21, kb.KMER64, kb.HASH_CANON_INVHASH, (1.001, 256, 20.0, 65534))
+        halo_ok = bool(np.array_equal(halo_hll, want_halo) and np.array_equal(halo_whole, want_halo))
+        ok &= halo_ok
+        print(f"[dist_check] one 3 Mb sequence in {world} chunks with a k-1 halo, allreduce-max vs the oracle's single-sequence sketch: ok={halo_ok}", flush=True)
         for kk, kt in ((21, kb.KMER64), (16, kb.KMER16B32)):
             want_pmh = orc.sketch_pmh3a_seqs(buf, off, nb, kk, kt, kb.HASH_CANON_INVHASH, 500)
             same = bool(np.array_equal(pmh[kk].astype(np.uint64), want_pmh))
