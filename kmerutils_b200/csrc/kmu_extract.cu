@@ -130,20 +130,55 @@ __global__ void __launch_bounds__(256) generate_kmers_warp_kernel(SeqView b, uin
     }
 }
 
-// Vector form of the warp kernel: a lane takes Q = 16 / sizeof(V) consecutive k-mers (one 64-bit window of 32 bases
-// read from three packed words serves all of them, forward and reverse strand) and writes them with ONE 16-byte store,
-// so every store instruction of the warp writes 512 contiguous bytes.  Quads are aligned on the OUTPUT element index
-// (out must be 16-byte aligned); the ragged quads at the ends of a sequence / group fall back to scalar stores.
-template <typename V, int U>
-__global__ void __launch_bounds__(256) generate_kmers_vec_kernel(SeqView b, uint64_t total_bytes, uint32_t k, int kmer_type,
-                                                                  int hash_kind, const uint64_t* __restrict__ out_off,
-                                                                  V* __restrict__ out) {
-    constexpr int Q = 16 / (int)sizeof(V);
-    const V header = (V)word_header(kmer_type, k);
-    const bool canonical = hash_is_canonical(hash_kind);
+// Run form of the warp kernel: a lane takes R = 32 / sizeof(V) CONSECUTIVE k-mers (8 u32 / 4 u64) and writes them with ONE
+// 256-bit store (st.global.v8.b32, SASS STG.E.ENL2.256), so every store instruction of the warp writes 1 KB of contiguous
+// output.  The lane reads the window of packed words its run needs once; ONE reverse complement of the window serves all
+// k-mers of the run on both strands, there is no rolling state.  Everything inside a (group, sequence) segment is 32-bit
+// arithmetic relative to the segment; runs are aligned on the OUTPUT index (out must be 32-byte aligned), the < 2 R ragged
+// elements at the two ends of a segment go through the scalar form.  The issue budget is what bounds this kernel (the
+// alu pipe takes shifts / logic / compares at one warp instruction per two cycles per SM sub-partition, the fma pipe the
+// multiply-adds at the same rate), hence:
+//   * the two `key += ~(key << n)` steps of int32_hash are one multiply-add each (key * (1 - 2^n) - 1, fma pipe) and the
+//     header OR is folded into the first one's constant;
+//   * PACK16 (2 k <= 16 bits): k-mers t and t + 4 of a run sit exactly one byte apart in the window, one shift + one byte
+//     permute packs both into the two halves of a register, and the strand minimum is one 16-bit SIMD instruction.
+__device__ __forceinline__ void st256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
+                                      uint32_t a6, uint32_t a7) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5),
+                 "r"(a6), "r"(a7)
+                 : "memory");
+}
+// reverse complement of 16 bases: one BREV, the complement folded into the pair swap (one three-input logic op)
+__device__ __forceinline__ uint32_t revcomp16(uint32_t w) {
+    const uint32_t r = __brev(w);
+    uint32_t d;  // ~(((r << 1) & 0xAAAAAAAA) | ((r >> 1) & 0x55555555)): lut 0x27 of (a, b, c) = ~(c ? b : a)
+    asm("lop3.b32 %0, %1, %2, 0x55555555, 0x27;" : "=r"(d) : "r"(r << 1), "r"(r >> 1));
+    return d;
+}
+// int32_hash(v | header) with c0 = header * 0xFFFF8001 - 1 (v and header share no bit)
+__device__ __forceinline__ uint32_t int32_hash_folded(uint32_t v, uint32_t c0) {
+    uint32_t key = v * 0xFFFF8001u + c0;  // key + ~(key << 15) = key * (1 - 2^15) - 1
+    key ^= key >> 10;
+    key *= 9u;
+    key ^= key >> 6;
+    key = key * 0xFFFFF801u - 1u;  // key + ~(key << 11)
+    key ^= key >> 16;
+    return key;
+}
+template <typename V, bool HASH>
+__device__ __forceinline__ V finish_key(V v, V header, uint32_t c0) {
+    if (sizeof(V) == 4) return HASH ? (V)int32_hash_folded((uint32_t)v, c0) : (V)(v | header);
+    return HASH ? (V)int64_hash((uint64_t)(v | header)) : (V)(v | header);
+}
+
+template <typename V, bool CANON, bool HASH, int PACK16>  // PACK16: 0 no, 1 for 2 k < 16, 2 for 2 k == 16 (no mask)
+__global__ void __launch_bounds__(256) generate_kmers_run_kernel(SeqView b, uint64_t total_bytes, uint32_t k, V header,
+                                                                  const uint64_t* __restrict__ out_off, V* __restrict__ out) {
+    constexpr uint32_t R = 32 / (uint32_t)sizeof(V);
     const V mask = value_mask<V>(2 * k);
+    const uint32_t c0 = (uint32_t)header * 0xFFFF8001u - 1u;
     const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
-    const int lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t g = warp; g < ngroups; g += nwarps) {
@@ -157,81 +192,144 @@ __global__ void __launch_bounds__(256) generate_kmers_vec_kernel(SeqView b, uint
             const uint64_t nk = L >= k ? L - k + 1 : 0;
             const uint64_t p_lo = byte0 > sb ? (byte0 - sb) * 4 : 0;
             const uint64_t p_hi = min(nk, (byte1 - sb) * 4);
-            const uint32_t* words = (const uint32_t*)(b.packed + sb);
-            const uint64_t ob = __ldg(out_off + s);
-            const uint64_t e_lo = ob + p_lo, e_hi = ob + p_hi;
-            for (uint64_t e0 = e_lo & ~(uint64_t)(Q - 1); e0 < e_hi; e0 += 32 * Q * U) {
+            ++s;
+            if (p_lo >= p_hi) continue;
+            // the segment: n k-mers from position p_lo of the sequence, output o[0 .. n)
+            const uint32_t n = (uint32_t)(p_hi - p_lo);
+            const uint64_t e0 = __ldg(out_off + s - 1) + p_lo;
+            V* o = out + e0;
+            const uint32_t* wbase = (const uint32_t*)(b.packed + sb) + (p_lo >> 4);
+            const uint32_t q0 = (uint32_t)p_lo & 15;
+            const uint32_t head = min(n, (R - (uint32_t)(e0 & (R - 1))) & (R - 1));
+            const uint32_t nruns = (n - head) / R;
+            const uint32_t nscalar = n - nruns * R;  // < 2 R <= 16: the ragged ends, one lane each
+            if (lane < nscalar) {
+                const uint32_t r = lane < head ? lane : lane + nruns * R;
+                V key = kmer_at<V>(wbase, q0 + r, k);
+                if (CANON) {
+                    const V rc = revcomp_val(key, k);
+                    key = key < rc ? key : rc;
+                }
+                o[r] = finish_key<V, HASH>(key, header, c0);
+            }
+#pragma unroll 2
+            for (uint32_t j = lane; j < nruns; j += 32) {
+                const uint32_t r = head + j * R;
+                const uint32_t q = q0 + r;
+                const uint32_t* w = wbase + (q >> 4);
+                const uint32_t sh = (q & 15) * 2;
+                if (sizeof(V) == 4) {
+                    // 32 bases from position p_lo + r: the 8 k-mers of the run start at bases 0 .. 7 of the window
+                    const uint32_t wa = be32(__ldg(w)), wb = be32(__ldg(w + 1)), wc = be32(__ldg(w + 2));
+                    const uint32_t xh = __funnelshift_l(wb, wa, sh), xl = __funnelshift_l(wc, wb, sh);
+                    const uint64_t x = ((uint64_t)xh << 32) | xl;
+                    const uint64_t rc = CANON ? (((uint64_t)revcomp16(xl) << 32) | revcomp16(xh)) : 0;
+                    uint32_t vals[8];
+                    if (PACK16) {
+                        const uint32_t mask2 = (uint32_t)mask * 0x10001u;
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const uint64_t e = e0 + (uint64_t)(u * 32 + lane) * Q;
-                    if (e < e_hi) {
-                        const uint32_t t_lo = e < e_lo ? (uint32_t)(e_lo - e) : 0u;
-                        const uint32_t t_hi = (uint32_t)min((uint64_t)Q, e_hi - e);
-                        const uint64_t p = e + t_lo - ob;  // first position this lane produces
-                        const uint32_t* w = words + (p >> 4);
-                        const uint32_t sh = (uint32_t)(p & 15) * 2;
-                        const uint32_t wa = be32(__ldg(w)), wb = be32(__ldg(w + 1)), wc = be32(__ldg(w + 2));
-                        V vals[Q];
-                        if (sizeof(V) == 4) {
-                            // 32 bases from p; k-mer t = bases t .. t + k - 1 of the window, its reverse complement sits
-                            // 2 t bits above the bottom of the window's reverse complement
-                            const uint64_t x = ((uint64_t)__funnelshift_l(wb, wa, sh) << 32) | __funnelshift_l(wc, wb, sh);
-                            const uint64_t rc = revcomp_word64(x);
-#pragma unroll
-                            for (int t = 0; t < Q; ++t) {
-                                V key = (V)(x >> (64 - 2 * k - 2 * t)) & mask;
-                                if (canonical) {
-                                    const V r = (V)(rc >> (2 * t)) & mask;
-                                    key = key < r ? key : r;
-                                }
-                                vals[t] = finalize_key<V>(key, header, hash_kind);
+                        for (uint32_t t = 0; t < 4; ++t) {
+                            // k-mer t + 4 in bits 0 .. 2k of z, k-mer t in bits 8 .. 8 + 2k: packed as (t | t + 4)
+                            const uint32_t z = (uint32_t)(x >> (56 - 2 * k - 2 * t));
+                            uint32_t pk = __byte_perm(z, 0, 0x2110);
+                            if (PACK16 == 1) pk &= mask2;
+                            if (CANON) {
+                                const uint32_t y = (uint32_t)(rc >> (2 * t));  // strand -: k-mer t at bit 0, t + 4 at bit 8
+                                uint32_t pr = __byte_perm(y, 0, 0x1021);
+                                if (PACK16 == 1) pr &= mask2;
+                                pk = __vminu2(pk, pr);
                             }
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < Q; ++t) {
-                                const uint32_t st = sh + 2 * t;  // <= 32: the clamping funnel shift
-                                const uint64_t x = ((uint64_t)__funnelshift_lc(wb, wa, st) << 32) | __funnelshift_lc(wc, wb, st);
-                                V key = (V)(x >> (64 - 2 * k));
-                                if (canonical) {
-                                    const V r = (V)revcomp_val((uint64_t)key, k);
-                                    key = key < r ? key : r;
-                                }
-                                vals[t] = finalize_key<V>(key, header, hash_kind);
-                            }
+                            vals[t] = (uint32_t)finish_key<V, HASH>((V)(pk >> 16), header, c0);
+                            vals[t + 4] = (uint32_t)finish_key<V, HASH>((V)(pk & 0xFFFFu), header, c0);
                         }
-                        if (t_lo == 0 && t_hi == Q) {
-                            uint4 v;
-                            if (sizeof(V) == 4) {
-                                v = make_uint4((uint32_t)vals[0], (uint32_t)vals[1], (uint32_t)vals[Q > 2 ? 2 : 0], (uint32_t)vals[Q > 2 ? 3 : 0]);
-                            } else {
-                                const uint64_t a0 = (uint64_t)vals[0], a1 = (uint64_t)vals[1];
-                                v = make_uint4((uint32_t)a0, (uint32_t)(a0 >> 32), (uint32_t)a1, (uint32_t)(a1 >> 32));
-                            }
-                            __stcs((uint4*)(out + e), v);  // streaming: the output is not read again by this kernel
-                        } else {
-                            for (uint32_t t = 0; t + t_lo < t_hi; ++t) out[e + t_lo + t] = vals[t];
+                    } else {
+#pragma unroll
+                        for (uint32_t t = 0; t < 8; ++t) {
+                            uint32_t key = (uint32_t)(x >> (64 - 2 * k - 2 * t)) & (uint32_t)mask;
+                            if (CANON) key = min(key, (uint32_t)(rc >> (2 * t)) & (uint32_t)mask);
+                            vals[t] = (uint32_t)finish_key<V, HASH>((V)key, header, c0);
                         }
                     }
+                    st256(o + r, vals[0], vals[1], vals[2], vals[3], vals[4], vals[5], vals[6], vals[7]);
+                } else {
+                    // 48 bases from position p_lo + r in (a0, a1, a2); the window's reverse complement is (r2, r1, r0) read
+                    // from the top, so strand - of k-mer t is the window's reverse complement shifted right by 2 t
+                    const uint32_t w0 = be32(__ldg(w)), w1 = be32(__ldg(w + 1)), w2 = be32(__ldg(w + 2)), w3 = be32(__ldg(w + 3));
+                    const uint32_t a0 = __funnelshift_l(w1, w0, sh), a1 = __funnelshift_l(w2, w1, sh), a2 = __funnelshift_l(w3, w2, sh);
+                    const uint32_t r0 = CANON ? revcomp16(a0) : 0, r1 = CANON ? revcomp16(a1) : 0, r2 = CANON ? revcomp16(a2) : 0;
+                    uint32_t vals[8];
+#pragma unroll
+                    for (uint32_t t = 0; t < 4; ++t) {
+                        const uint64_t x = ((uint64_t)__funnelshift_l(a1, a0, 2 * t) << 32) | __funnelshift_l(a2, a1, 2 * t);
+                        uint64_t key = x >> (64 - 2 * k);
+                        if (CANON) {
+                            const uint64_t y = (((uint64_t)__funnelshift_r(r1, r2, 2 * t) << 32) | __funnelshift_r(r0, r1, 2 * t)) & (uint64_t)mask;
+                            key = key < y ? key : y;
+                        }
+                        key = (uint64_t)finish_key<V, HASH>((V)key, header, c0);
+                        vals[2 * t] = (uint32_t)key;
+                        vals[2 * t + 1] = (uint32_t)(key >> 32);
+                    }
+                    st256(o + r, vals[0], vals[1], vals[2], vals[3], vals[4], vals[5], vals[6], vals[7]);
                 }
             }
-            ++s;
         }
     }
+}
+
+// grid of a grid-stride kernel: exactly the CTAs that are resident at once (a grid of 8 CTAs per SM with 40 registers per
+// thread runs as one full wave of 6 per SM plus a second wave at a third of the occupancy: every CTA has the same share
+// of the groups, so the second wave costs as much time as the first)
+template <typename K>
+static int resident_grid(K kernel, int block) {
+    int per_sm = 0, dev = 0, sms = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return per_sm * sms;
+}
+
+template <typename V>
+static void launch_run_kernel(const SeqView& b, uint64_t total_bytes, uint32_t k, int kmer_type, int hash_kind,
+                              const uint64_t* out_off, V* out, cudaStream_t stream) {
+    const int block = 256;
+    const bool canon = hash_is_canonical(hash_kind);
+    const bool hashed = hash_kind == KMU_HASH_CANON_INVHASH || hash_kind == KMU_HASH_INVHASH;
+    const V header = hash_kind == KMU_HASH_MASKED_VALUE ? (V)0 : (V)word_header(kmer_type, k);
+#define KMU_RUN(C, H, P)                                                                                              \
+    generate_kmers_run_kernel<V, C, H, P><<<resident_grid(generate_kmers_run_kernel<V, C, H, P>, block), block, 0, stream>>>( \
+        b, total_bytes, k, header, out_off, out)
+    if constexpr (sizeof(V) == 4) {
+        if (k == 8) {
+            if (canon) { if (hashed) KMU_RUN(true, true, 2); else KMU_RUN(true, false, 2); }
+            else { if (hashed) KMU_RUN(false, true, 2); else KMU_RUN(false, false, 2); }
+            return;
+        }
+        if (k < 8) {
+            if (canon) { if (hashed) KMU_RUN(true, true, 1); else KMU_RUN(true, false, 1); }
+            else { if (hashed) KMU_RUN(false, true, 1); else KMU_RUN(false, false, 1); }
+            return;
+        }
+    }
+    {
+        if (canon) { if (hashed) KMU_RUN(true, true, 0); else KMU_RUN(true, false, 0); }
+        else { if (hashed) KMU_RUN(false, true, 0); else KMU_RUN(false, false, 0); }
+    }
+#undef KMU_RUN
 }
 
 cudaError_t launch_generate_kmers(const SeqView& b, uint64_t total_bytes, uint32_t k, int kmer_type, int hash_kind,
                                   const uint64_t* out_off, void* out, cudaStream_t stream) {
     if (b.nseq == 0) return cudaSuccess;
     const int block = 256;
-    const int grid = 148 * 8;
+    const int grid = 148 * 6;  // 40 registers per thread: 6 CTAs of 256 threads per SM
     if (kmer_type == KMU_KMERAA64)
         generate_kmers_kernel<uint64_t, 8, true><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint64_t*)out);
     else if (kmer_type == KMU_KMERAA32)
         generate_kmers_kernel<uint32_t, 8, true><<<grid, block, 0, stream>>>(b, k, kmer_type, hash_kind, out_off, (uint32_t*)out);
-    else if (kmer_type == KMU_KMER64 && ((uintptr_t)out & 15) == 0)
-        generate_kmers_vec_kernel<uint64_t, 2><<<grid, block, 0, stream>>>(b, total_bytes, k, kmer_type, hash_kind, out_off, (uint64_t*)out);
-    else if (kmer_type != KMU_KMER64 && ((uintptr_t)out & 15) == 0)
-        generate_kmers_vec_kernel<uint32_t, 2><<<grid, block, 0, stream>>>(b, total_bytes, k, kmer_type, hash_kind, out_off, (uint32_t*)out);
+    else if (kmer_type == KMU_KMER64 && ((uintptr_t)out & 31) == 0)
+        launch_run_kernel<uint64_t>(b, total_bytes, k, kmer_type, hash_kind, out_off, (uint64_t*)out, stream);
+    else if (kmer_type != KMU_KMER64 && ((uintptr_t)out & 31) == 0)
+        launch_run_kernel<uint32_t>(b, total_bytes, k, kmer_type, hash_kind, out_off, (uint32_t*)out, stream);
     else if (kmer_type == KMU_KMER64)
         generate_kmers_warp_kernel<uint64_t, 4><<<grid, block, 0, stream>>>(b, total_bytes, k, kmer_type, hash_kind, out_off, (uint64_t*)out);
     else
@@ -371,9 +469,146 @@ __global__ void __launch_bounds__(128) nthash_warp_kernel(SeqView b, uint64_t to
     }
 }
 
+// Run form of ntHash (one hash per k-mer, 32-byte aligned outputs): the k-mers of a (group, sequence) segment are cut
+// into 32 contiguous stretches, one per lane, each a multiple of 32 positions that starts on a multiple of 32 of the
+// OUTPUT index.  A lane initialises once (O(k)) and then only rolls; every 4 steps it writes its 4 hashes with one 256-bit
+// store (a full 32-byte sector: no shared-memory transposition, no partial sectors), every 16 steps the 16 strand bytes
+// with one 128-bit store.  The elements before the first aligned index of a segment (< 32) are computed one per lane by
+// initialisation alone; the last, partial run of a segment rolls with scalar stores.
+struct NtTables {
+    uint64_t SEED[4], SEEDC[4], FD[16], RD[16], F2[16], R2[16];
+};
+__device__ __forceinline__ void nt_tables_fill(NtTables& T, uint32_t k) {
+    if (threadIdx.x < 16) {
+        const uint32_t ob = threadIdx.x >> 2, nb = threadIdx.x & 3;
+        T.F2[threadIdx.x] = rotl_var(nt_seed(ob), 1) ^ nt_seed(nb);
+        T.R2[threadIdx.x] = rotl_var(nt_seed(3u - nb), 1) ^ nt_seed(3u - ob);
+        T.FD[threadIdx.x] = rotl_var(nt_seed(ob), k) ^ nt_seed(nb);
+        T.RD[threadIdx.x] = rotl_var(nt_seed(3u - ob), 63) ^ rotl_var(nt_seed(3u - nb), k - 1);
+        if (threadIdx.x < 4) {
+            T.SEED[threadIdx.x] = nt_seed(threadIdx.x);
+            T.SEEDC[threadIdx.x] = nt_seed(3u - threadIdx.x);
+        }
+    }
+}
+// 32 bases from position q of the word stream w
+__device__ __forceinline__ uint64_t window32(const uint32_t* __restrict__ w, uint32_t q) {
+    const uint32_t* a = w + (q >> 4);
+    const uint32_t sh = (q & 15) * 2;
+    const uint32_t x0 = be32(__ldg(a)), x1 = be32(__ldg(a + 1)), x2 = be32(__ldg(a + 2));
+    return ((uint64_t)__funnelshift_l(x1, x0, sh) << 32) | __funnelshift_l(x2, x1, sh);
+}
+// nthash_canonical_init (kmer.rs:74-94), Horner form, two bases per step
+__device__ __forceinline__ void nt_init(const NtTables& T, uint64_t kv, uint32_t k, uint64_t& f, uint64_t& r) {
+    f = 0;
+    r = 0;
+    uint32_t i = 0;
+    if (k & 1) {
+        f = T.SEED[(uint32_t)(kv >> (2 * (k - 1))) & 3u];
+        r = T.SEEDC[(uint32_t)kv & 3u];
+        i = 1;
+    }
+    for (; i < k; i += 2) {
+        f = ((f << 2) | (f >> 62)) ^ T.F2[(uint32_t)(kv >> (2 * (k - 2 - i))) & 15u];
+        r = ((r << 2) | (r >> 62)) ^ T.R2[(uint32_t)(kv >> (2 * i)) & 15u];
+    }
+}
+__device__ __forceinline__ void st128(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3) {
+    asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
+}
+
+template <bool STRAND>
+__global__ void __launch_bounds__(128) nthash_run_kernel(SeqView b, uint64_t total_bytes, uint32_t k,
+                                                          const uint64_t* __restrict__ out_off, uint64_t* __restrict__ out_hash,
+                                                          uint8_t* __restrict__ out_strand) {
+    __shared__ NtTables T;
+    nt_tables_fill(T, k);
+    __syncthreads();
+    const uint64_t ngroups = (total_bytes + GROUP_BYTES - 1) / GROUP_BYTES;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t g = warp; g < ngroups; g += nwarps) {
+        const uint64_t byte0 = g * GROUP_BYTES;
+        const uint64_t byte1 = min(byte0 + (uint64_t)GROUP_BYTES, total_bytes);
+        uint64_t s = seq_of_byte(b.byte_off, b.nseq, byte0);
+        while (s < b.nseq) {
+            const uint64_t sb = __ldg(b.byte_off + s);
+            if (sb >= byte1) break;
+            const uint64_t L = __ldg(b.nbases + s);
+            const uint64_t nk = L >= k ? L - k + 1 : 0;
+            const uint64_t p_lo = byte0 > sb ? (byte0 - sb) * 4 : 0;
+            const uint64_t p_hi = min(nk, (byte1 - sb) * 4);
+            ++s;
+            if (p_lo >= p_hi) continue;
+            const uint32_t n = (uint32_t)(p_hi - p_lo);
+            const uint64_t e0 = __ldg(out_off + s - 1) + p_lo;
+            uint64_t* oh = out_hash + e0;
+            uint8_t* os = out_strand + e0;
+            const uint32_t* wbase = (const uint32_t*)(b.packed + sb) + (p_lo >> 4);
+            const uint32_t q0 = (uint32_t)p_lo & 15;
+            const uint32_t head = min(n, (32u - (uint32_t)(e0 & 31)) & 31u);
+            if (lane < head) {
+                uint64_t f, r;
+                nt_init(T, window32(wbase, q0 + lane) >> (64 - 2 * k), k, f, r);
+                const bool rev = r < f;
+                oh[lane] = rev ? r : f;
+                if (STRAND) os[lane] = rev ? 1 : 0;
+            }
+            const uint32_t body = n - head;
+            const uint32_t stretch = (((body + 31) >> 5) + 31) & ~31u;
+            uint32_t q = head + lane * stretch;
+            const uint32_t q_end = min(q + stretch, n);
+            if (q >= q_end) continue;
+            uint64_t f, r;
+            nt_init(T, window32(wbase, q0 + q) >> (64 - 2 * k), k, f, r);
+            for (; q < q_end; q += 32) {
+                // outgoing bases (positions q + j) and incoming ones (q + j + k): two windows of 32 bases per run
+                const uint64_t OUT = window32(wbase, q0 + q), IN = window32(wbase, q0 + q + k);
+                if (q + 32 <= q_end) {
+                    uint32_t hv[8], sv[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; ++j) {
+                        const bool rev = r < f;
+                        const uint64_t h = rev ? r : f;
+                        hv[2 * (j & 3)] = (uint32_t)h;
+                        hv[2 * (j & 3) + 1] = (uint32_t)(h >> 32);
+                        if (STRAND && rev) sv[(j & 15) >> 2] |= 1u << (8 * (j & 3));
+                        if ((j & 3) == 3) st256(oh + q + j - 3, hv[0], hv[1], hv[2], hv[3], hv[4], hv[5], hv[6], hv[7]);
+                        if (STRAND && (j & 15) == 15) {
+                            st128(os + q + j - 15, sv[0], sv[1], sv[2], sv[3]);
+                            sv[0] = sv[1] = sv[2] = sv[3] = 0;
+                        }
+                        const uint32_t t = ((uint32_t)(OUT >> (62 - 2 * j)) & 3u) * 4 + ((uint32_t)(IN >> (62 - 2 * j)) & 3u);
+                        f = ((f << 1) | (f >> 63)) ^ T.FD[t];
+                        r = ((r >> 1) | (r << 63)) ^ T.RD[t];
+                    }
+                } else {
+                    const uint32_t cnt = q_end - q;
+                    for (uint32_t j = 0; j < cnt; ++j) {
+                        const bool rev = r < f;
+                        oh[q + j] = rev ? r : f;
+                        if (STRAND) os[q + j] = rev ? 1 : 0;
+                        const uint32_t t = ((uint32_t)(OUT >> (62 - 2 * j)) & 3u) * 4 + ((uint32_t)(IN >> (62 - 2 * j)) & 3u);
+                        f = ((f << 1) | (f >> 63)) ^ T.FD[t];
+                        r = ((r >> 1) | (r << 63)) ^ T.RD[t];
+                    }
+                }
+            }
+        }
+    }
+}
+
 cudaError_t launch_nthash(const SeqView& b, uint64_t total_bytes, uint32_t k, uint32_t n_multi, const uint64_t* out_off,
                           uint64_t* out_hash, uint8_t* out_strand, cudaStream_t stream) {
     if (b.nseq == 0) return cudaSuccess;
+    if (n_multi == 1 && ((uintptr_t)out_hash & 31) == 0 && ((uintptr_t)out_strand & 15) == 0) {
+        if (out_strand)
+            nthash_run_kernel<true><<<resident_grid(nthash_run_kernel<true>, 128), 128, 0, stream>>>(b, total_bytes, k, out_off, out_hash, out_strand);
+        else
+            nthash_run_kernel<false><<<resident_grid(nthash_run_kernel<false>, 128), 128, 0, stream>>>(b, total_bytes, k, out_off, out_hash, out_strand);
+        return cudaGetLastError();
+    }
     const int wpb = 4, cps = 5;  // warps per CTA (one 9.3 KB tile each), CTAs per SM
     const size_t smem = wpb * (size_t)NT_TILE_BYTES;
     static bool configured = false;

@@ -47,6 +47,26 @@ def test_generate_kmers_hash_kinds(engine, oracle, kind, k, ktype):
     assert np.array_equal(got.astype(np.uint64), want)
 
 
+RUN_CASES = [(3, kb.KMER32), (7, kb.KMER32), (8, kb.KMER32), (9, kb.KMER32), (14, kb.KMER32), (16, kb.KMER16B32),
+             (5, kb.KMER64), (21, kb.KMER64), (31, kb.KMER64), (32, kb.KMER64)]
+
+
+@pytest.mark.parametrize("kind", [kb.HASH_IDENTITY_RAW, kb.HASH_MASKED_VALUE, kb.HASH_CANON_INVHASH, kb.HASH_CANON_RAW,
+                                  kb.HASH_INVHASH])
+@pytest.mark.parametrize("k,ktype", RUN_CASES)
+def test_generate_kmers_run_form(engine, oracle, kind, k, ktype):
+    """The run form (8 u32 / 4 u64 consecutive k-mers per lane, one 256-bit store): sequences that cross several 2 KB
+    groups, segments that start at every output alignment, ragged heads and tails, sequences shorter than a run."""
+    nb = np.array([9000, 5, 20011, 8191, 8193, 33, 33002, 1, 70000, 8200, 17, 4099], dtype=np.uint64)
+    batch = engine.batch_synth(31 + k, nb)
+    packed, off = oracle_batch(oracle, 31 + k, nb)
+    got, _ = engine.generate_kmers(batch, k, ktype, kind)
+    want = oracle_kmers(oracle, packed, off, nb, k, ktype, kind)
+    assert len(got) == len(want)
+    bad = np.flatnonzero(got.astype(np.uint64) != want)
+    assert len(bad) == 0, f"first mismatch at k-mer {bad[0]}: {int(got[bad[0]]):#x} != {int(want[bad[0]]):#x}"
+
+
 def test_reference_kmer_vectors(engine, oracle):
     # kmergenerator.rs:596-699 : 16-mers of the 80-base test string; first three words are in the source comments
     batch, bad = engine.batch_from_ascii([S80])
@@ -92,6 +112,26 @@ def test_nthash(engine, oracle, k, n_multi):
     first = int(np.maximum(nb[0] - k + 1, 0))
     for i in range(first):
         assert int(h[i, 0]) == oracle.nthash_canonical(words[i], k, kb.KMER64)[2]
+
+
+@pytest.mark.parametrize("k", [1, 8, 15, 16, 17, 31, 32])
+def test_nthash_run_form(engine, oracle, k):
+    """n_multi = 1 takes the run form (per-lane stretches, 256-bit stores): long and ragged sequences, sampled against the
+    oracle, and every value against the tile kernel (n_multi = 2, same first hash)."""
+    nb = np.array([9000, 5, 20011, 8191, 8193, 33, 33002, 1, 70000, 8200, 17, 4099, 64, 95], dtype=np.uint64)
+    batch = engine.batch_synth(77 + k, nb)
+    packed, off = oracle_batch(oracle, 77 + k, nb)
+    h1, s1 = engine.nthash_canonical(batch, k, 1)
+    h2, s2 = engine.nthash_canonical(batch, k, 2)
+    assert np.array_equal(h1[:, 0], h2[:, 0]) and np.array_equal(s1, s2)
+    h0, _ = engine.nthash_canonical(batch, k, 1, want_strand=False)
+    assert np.array_equal(h0, h1)
+    words = oracle_kmers(oracle, packed, off, nb, k, kb.KMER64, kb.HASH_IDENTITY_RAW)
+    assert len(words) == len(h1)
+    rng = np.random.default_rng(k)
+    for i in np.concatenate([rng.integers(0, len(words), 600), np.arange(40), np.arange(len(words) - 40, len(words))]):
+        f, r, c, s = oracle.nthash_canonical(words[i], k, kb.KMER64)
+        assert int(h1[i, 0]) == c and int(s1[i]) == s
 
 
 def test_nthash_survey_vectors(engine):
