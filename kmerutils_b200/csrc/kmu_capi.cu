@@ -70,7 +70,12 @@ int32_t batch_alloc(kmu_ctx* ctx, const uint64_t* nbases, uint64_t nseq, kmu_seq
     b->alphabet = alphabet;
     b->h_nbases.assign(nbases, nbases + nseq);
     b->packed_bytes = layout_offsets(nbases, nseq, b->h_byte_off, alphabet);
-    for (uint64_t i = 0; i < nseq; ++i) b->total_bases += nbases[i];
+    uint64_t shortest = ~0ull - 1;  // kept with the batch: kmer_count(k) is then O(1) whenever every sequence holds a k-mer
+    for (uint64_t i = 0; i < nseq; ++i) {
+        b->total_bases += nbases[i];
+        shortest = nbases[i] < shortest ? nbases[i] : shortest;
+    }
+    b->min_nbases = shortest;
     cudaError_t e = cudaMalloc((void**)&b->packed, b->packed_bytes + TAIL_SLACK);
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->byte_off, sizeof(uint64_t) * (nseq + 1));
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->nbases, sizeof(uint64_t) * (nseq + 1));

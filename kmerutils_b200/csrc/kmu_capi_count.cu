@@ -46,7 +46,7 @@ int32_t check_overflow(kmu_ctx* ctx, kmu_counter* c) {
 
 
 // ---- two-phase insertion (kmu_count_part.cu) -----------------------------------------------------------------
-// The table is cut into regions of REGION_BYTES (32 MB: load + RED updates of a region that sits in L2 run at 64 G/s
+// The table is cut into regions of REGION_BYTES (64 MB: load + RED updates of a region that sits in L2 run at 64 G/s
 // against 15.5 G/s on the whole table, profiles/r1d_micro_atomics.txt); more than max_buckets regions -> larger regions.
 constexpr uint32_t MAX_BUCKETS = 4096;
 
@@ -62,10 +62,10 @@ uint64_t region_bytes_setting() {
         const uint64_t kb = (uint64_t)std::atoll(e);
         if (kb >= 1) return kb << 10;
     }
-    return 32ull << 20;
+    return 64ull << 20;
 }
 
-// The table is cut into `nfine_total` regions of region_bytes_setting() (32 MB: they sit in L2 while they take their
+// The table is cut into `nfine_total` regions of region_bytes_setting() (64 MB, half of the L2: they sit there while they take their
 // updates).  The partition kernel is efficient up to a few hundred buckets per pass (a tile of 4096 k-mers sorted in shared
 // memory: with thousands of buckets every bucket gets one key per tile, i.e. one global atomic and one 8-byte store per
 // key -- measured 14.7 G keys/s at 4096 buckets against 77 G at 512), so large tables are partitioned in TWO levels:
@@ -84,7 +84,7 @@ uint32_t level1_bucket_target() {
         const long v = std::atol(e);
         if (v >= 1) return (uint32_t)v;
     }
-    return 512;
+    return 1024;
 }
 
 RegionGeom region_geometry(uint64_t capacity, bool key64, uint32_t nowners) {
@@ -228,17 +228,22 @@ int32_t insert_two_phase(kmu_ctx* ctx, kmu_counter* c, const kmu_seqbatch* b, bo
     // chunks: a bound of the k-mers of a chunk = 4 per packed byte (sequences) or the keys themselves
     const uint64_t unit_total = b ? b->packed_bytes : nsrc;          // bytes or keys
     const uint64_t keys_per_unit = b ? 4 : 1;
+    // the exact number of k-mers (known on the host from the lengths): 150-base reads hold 120 31-mers, not 150 -- sizing
+    // the slabs by it lets a 4 Gbase step go through in ONE chunk, and every chunk costs a full sweep of the table
+    const uint64_t keys_total = b ? b->kmer_count(c->k) : nsrc;
     // one chunk if its slabs fit the buffer already held (no query of the free memory on the hot path)
     uint64_t chunk_units = unit_total;
-    if (std::getenv("KMU_COUNT_SLAB_MB") || slab_capacity(unit_total * keys_per_unit, rg.ncoarse) * rg.ncoarse * esz > ctx->sig_dev.cap) {
+    if (std::getenv("KMU_COUNT_SLAB_MB") || slab_capacity(keys_total, rg.ncoarse) * rg.ncoarse * esz > ctx->sig_dev.cap) {
         const uint64_t budget = slab_budget_bytes(ctx->sig_dev.cap);
-        chunk_units = std::max<uint64_t>(1, budget / (esz * keys_per_unit) * 9 / 10);
-        if (b) chunk_units = std::max<uint64_t>(2048, chunk_units / 2048 * 2048);  // GROUP_BYTES of kmu_device.cuh
-        chunk_units = std::min(chunk_units, unit_total);
+        if (slab_capacity(keys_total, rg.ncoarse) * rg.ncoarse * esz > budget) {
+            chunk_units = std::max<uint64_t>(1, budget / (esz * keys_per_unit) * 9 / 10);
+            if (b) chunk_units = std::max<uint64_t>(2048, chunk_units / 2048 * 2048);  // GROUP_BYTES of kmu_device.cuh
+            chunk_units = std::min(chunk_units, unit_total);
+        }
     }
     const uint64_t nchunks = (unit_total + chunk_units - 1) / chunk_units;
     if (nchunks > 64) return fail(KMU_ENOMEM, "not enough free device memory for the partition slabs (%llu chunks)", (unsigned long long)nchunks);
-    const uint64_t bound = chunk_units * keys_per_unit;
+    const uint64_t bound = std::min(chunk_units * keys_per_unit, keys_total);
     const uint64_t slab_cap = slab_capacity(bound, rg.ncoarse);
     if (slab_cap >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "partition slab too large");
     CUDA_TRY(ctx->sig_dev.reserve(slab_cap * rg.ncoarse * esz));

@@ -155,6 +155,8 @@ __device__ __forceinline__ uint32_t revcomp16(uint32_t w) {
     asm("lop3.b32 %0, %1, %2, 0x55555555, 0x27;" : "=r"(d) : "r"(r << 1), "r"(r >> 1));
     return d;
 }
+// x >> n (0 <= n < 32, n a compile-time constant after unrolling) as a high multiply: the fma pipe's shift
+__device__ __forceinline__ uint32_t shr_fma(uint32_t x, uint32_t n) { return n == 0 ? x : __umulhi(x, 1u << (32 - n)); }
 // int32_hash(v | header) with c0 = header * 0xFFFF8001 - 1 (v and header share no bit)
 __device__ __forceinline__ uint32_t int32_hash_folded(uint32_t v, uint32_t c0) {
     uint32_t key = v * 0xFFFF8001u + c0;  // key + ~(key << 15) = key * (1 - 2^15) - 1
@@ -218,31 +220,38 @@ __global__ void __launch_bounds__(256) generate_kmers_run_kernel(SeqView b, uint
                 const uint32_t q = q0 + r;
                 const uint32_t* w = wbase + (q >> 4);
                 const uint32_t sh = (q & 15) * 2;
-                if (sizeof(V) == 4) {
+                if (sizeof(V) == 4 && PACK16) {
+                    // 2 k <= 16: the run's 8 k-mers lie in the 16 bases from position p_lo + r (two words).  k-mer t + 4 sits
+                    // in bits 0 .. 2k of z = xh >> (24 - 2k - 2t), k-mer t in bits 8 .. 8 + 2k: one byte permute packs them
+                    // as (t | t + 4); on strand - (reverse complement of the 16 bases) k-mer t is at bit 2t, t + 4 at bit
+                    // 2t + 8.  The right shifts by constants are high multiplies (fma pipe): the alu pipe is the bound.
+                    const uint32_t xh = __funnelshift_l(be32(__ldg(w + 1)), be32(__ldg(w)), sh);
+                    const uint32_t rl = CANON ? revcomp16(xh) : 0;
+                    const uint32_t mask2 = (uint32_t)mask * 0x10001u;
+                    uint32_t vals[8];
+#pragma unroll
+                    for (uint32_t t = 0; t < 4; ++t) {
+                        const uint32_t z = PACK16 == 2 ? shr_fma(xh, 8 - 2 * t) : xh >> (24 - 2 * k - 2 * t);
+                        uint32_t pk = __byte_perm(z, 0, 0x2110);
+                        if (PACK16 == 1) pk &= mask2;
+                        if (CANON) {
+                            uint32_t pr = __byte_perm(shr_fma(rl, 2 * t), 0, 0x1021);
+                            if (PACK16 == 1) pr &= mask2;
+                            pk = __vminu2(pk, pr);
+                        }
+                        const uint32_t hi = shr_fma(pk, 16), lo = pk - (hi << 16);
+                        vals[t] = (uint32_t)finish_key<V, HASH>((V)hi, header, c0);
+                        vals[t + 4] = (uint32_t)finish_key<V, HASH>((V)lo, header, c0);
+                    }
+                    st256(o + r, vals[0], vals[1], vals[2], vals[3], vals[4], vals[5], vals[6], vals[7]);
+                } else if (sizeof(V) == 4) {
                     // 32 bases from position p_lo + r: the 8 k-mers of the run start at bases 0 .. 7 of the window
                     const uint32_t wa = be32(__ldg(w)), wb = be32(__ldg(w + 1)), wc = be32(__ldg(w + 2));
                     const uint32_t xh = __funnelshift_l(wb, wa, sh), xl = __funnelshift_l(wc, wb, sh);
                     const uint64_t x = ((uint64_t)xh << 32) | xl;
                     const uint64_t rc = CANON ? (((uint64_t)revcomp16(xl) << 32) | revcomp16(xh)) : 0;
                     uint32_t vals[8];
-                    if (PACK16) {
-                        const uint32_t mask2 = (uint32_t)mask * 0x10001u;
-#pragma unroll
-                        for (uint32_t t = 0; t < 4; ++t) {
-                            // k-mer t + 4 in bits 0 .. 2k of z, k-mer t in bits 8 .. 8 + 2k: packed as (t | t + 4)
-                            const uint32_t z = (uint32_t)(x >> (56 - 2 * k - 2 * t));
-                            uint32_t pk = __byte_perm(z, 0, 0x2110);
-                            if (PACK16 == 1) pk &= mask2;
-                            if (CANON) {
-                                const uint32_t y = (uint32_t)(rc >> (2 * t));  // strand -: k-mer t at bit 0, t + 4 at bit 8
-                                uint32_t pr = __byte_perm(y, 0, 0x1021);
-                                if (PACK16 == 1) pr &= mask2;
-                                pk = __vminu2(pk, pr);
-                            }
-                            vals[t] = (uint32_t)finish_key<V, HASH>((V)(pk >> 16), header, c0);
-                            vals[t + 4] = (uint32_t)finish_key<V, HASH>((V)(pk & 0xFFFFu), header, c0);
-                        }
-                    } else {
+                    {
 #pragma unroll
                         for (uint32_t t = 0; t < 8; ++t) {
                             uint32_t key = (uint32_t)(x >> (64 - 2 * k - 2 * t)) & (uint32_t)mask;
@@ -517,6 +526,19 @@ __device__ __forceinline__ void st128(void* p, uint32_t a0, uint32_t a1, uint32_
     asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
 }
 
+// 16 bases from position q of the word stream w
+__device__ __forceinline__ uint32_t window16(const uint32_t* __restrict__ w, uint32_t q) {
+    const uint32_t* a = w + (q >> 4);
+    return __funnelshift_l(be32(__ldg(a + 1)), be32(__ldg(a)), (q & 15) * 2);
+}
+// c ? b : a, bit by bit (one three-input logic op)
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+constexpr uint32_t NT_STEPS = 16;  // positions per run: the granularity of a lane's stretch
 template <bool STRAND>
 __global__ void __launch_bounds__(128) nthash_run_kernel(SeqView b, uint64_t total_bytes, uint32_t k,
                                                           const uint64_t* __restrict__ out_off, uint64_t* __restrict__ out_hash,
@@ -547,54 +569,48 @@ __global__ void __launch_bounds__(128) nthash_run_kernel(SeqView b, uint64_t tot
             uint8_t* os = out_strand + e0;
             const uint32_t* wbase = (const uint32_t*)(b.packed + sb) + (p_lo >> 4);
             const uint32_t q0 = (uint32_t)p_lo & 15;
-            const uint32_t head = min(n, (32u - (uint32_t)(e0 & 31)) & 31u);
-            if (lane < head) {
+            // [0, head) and [head + 16 nruns, n): fewer than 32 positions, one per lane by initialisation alone;
+            // the nruns runs of 16 in between: lane l takes runs [l nruns / 32, (l + 1) nruns / 32)
+            const uint32_t head = min(n, (NT_STEPS - (uint32_t)(e0 & (NT_STEPS - 1))) & (NT_STEPS - 1));
+            const uint32_t nruns = (n - head) / NT_STEPS;
+            const uint32_t nscalar = n - nruns * NT_STEPS;
+            if (lane < nscalar) {
+                const uint32_t q = lane < head ? lane : lane + nruns * NT_STEPS;
                 uint64_t f, r;
-                nt_init(T, window32(wbase, q0 + lane) >> (64 - 2 * k), k, f, r);
+                nt_init(T, window32(wbase, q0 + q) >> (64 - 2 * k), k, f, r);
                 const bool rev = r < f;
-                oh[lane] = rev ? r : f;
-                if (STRAND) os[lane] = rev ? 1 : 0;
+                oh[q] = rev ? r : f;
+                if (STRAND) os[q] = rev ? 1 : 0;
             }
-            const uint32_t body = n - head;
-            const uint32_t stretch = (((body + 31) >> 5) + 31) & ~31u;
-            uint32_t q = head + lane * stretch;
-            const uint32_t q_end = min(q + stretch, n);
-            if (q >= q_end) continue;
-            uint64_t f, r;
-            nt_init(T, window32(wbase, q0 + q) >> (64 - 2 * k), k, f, r);
-            for (; q < q_end; q += 32) {
-                // outgoing bases (positions q + j) and incoming ones (q + j + k): two windows of 32 bases per run
-                const uint64_t OUT = window32(wbase, q0 + q), IN = window32(wbase, q0 + q + k);
-                if (q + 32 <= q_end) {
+            const uint32_t run0 = (lane * nruns) >> 5, run1 = ((lane + 1) * nruns) >> 5;
+            if (run0 < run1) {
+                uint32_t q = head + run0 * NT_STEPS;
+                const uint32_t q_end = head + run1 * NT_STEPS;
+                uint64_t f, r;
+                nt_init(T, window32(wbase, q0 + q) >> (64 - 2 * k), k, f, r);
+                // outgoing bases (positions q + j) and incoming ones (q + j + k); the windows of the next run are loaded
+                // before this run's steps (the read past the stretch stays inside the batch: 64 bytes of slack)
+                uint32_t OUTn = window16(wbase, q0 + q), INn = window16(wbase, q0 + q + k);
+                for (; q < q_end; q += NT_STEPS) {
+                    const uint32_t OUT = OUTn, IN = INn;
+                    OUTn = window16(wbase, q0 + q + NT_STEPS);
+                    INn = window16(wbase, q0 + q + NT_STEPS + k);
                     uint32_t hv[8], sv[4] = {0, 0, 0, 0};
 #pragma unroll
-                    for (uint32_t j = 0; j < 32; ++j) {
-                        const bool rev = r < f;
-                        const uint64_t h = rev ? r : f;
-                        hv[2 * (j & 3)] = (uint32_t)h;
-                        hv[2 * (j & 3) + 1] = (uint32_t)(h >> 32);
-                        if (STRAND && rev) sv[(j & 15) >> 2] |= 1u << (8 * (j & 3));
+                    for (uint32_t j = 0; j < NT_STEPS; ++j) {
+                        const uint32_t rev = r < f ? 0xFFFFFFFFu : 0u;
+                        hv[2 * (j & 3)] = bitsel((uint32_t)f, (uint32_t)r, rev);
+                        hv[2 * (j & 3) + 1] = bitsel((uint32_t)(f >> 32), (uint32_t)(r >> 32), rev);
+                        if (STRAND) sv[j >> 2] |= rev & (1u << (8 * (j & 3)));
                         if ((j & 3) == 3) st256(oh + q + j - 3, hv[0], hv[1], hv[2], hv[3], hv[4], hv[5], hv[6], hv[7]);
-                        if (STRAND && (j & 15) == 15) {
-                            st128(os + q + j - 15, sv[0], sv[1], sv[2], sv[3]);
-                            sv[0] = sv[1] = sv[2] = sv[3] = 0;
-                        }
-                        const uint32_t t = ((uint32_t)(OUT >> (62 - 2 * j)) & 3u) * 4 + ((uint32_t)(IN >> (62 - 2 * j)) & 3u);
+                        const uint32_t t = ((OUT >> (30 - 2 * j)) & 3u) * 4 + ((IN >> (30 - 2 * j)) & 3u);
                         f = ((f << 1) | (f >> 63)) ^ T.FD[t];
                         r = ((r >> 1) | (r << 63)) ^ T.RD[t];
                     }
-                } else {
-                    const uint32_t cnt = q_end - q;
-                    for (uint32_t j = 0; j < cnt; ++j) {
-                        const bool rev = r < f;
-                        oh[q + j] = rev ? r : f;
-                        if (STRAND) os[q + j] = rev ? 1 : 0;
-                        const uint32_t t = ((uint32_t)(OUT >> (62 - 2 * j)) & 3u) * 4 + ((uint32_t)(IN >> (62 - 2 * j)) & 3u);
-                        f = ((f << 1) | (f >> 63)) ^ T.FD[t];
-                        r = ((r >> 1) | (r << 63)) ^ T.RD[t];
-                    }
+                    if (STRAND) st128(os + q, sv[0], sv[1], sv[2], sv[3]);
                 }
             }
+            __syncwarp();
         }
     }
 }
