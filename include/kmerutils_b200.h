@@ -201,10 +201,12 @@ int32_t kmu_count_partition_scatter(kmu_ctx* ctx, const kmu_seqbatch* batch, uin
                                     int32_t canonical, uint32_t nparts, void* const* dests, const uint64_t* dest_offsets);
 /* Fused exchange, one walk (replaces the one-producer / N-consumer hand-off of count_kmer_threaded_one_to_many,
  * kmercount.rs:881-974, owner = DispatchableT::dispatch :382-420): ONE kernel extracts the canonical k-mers of the batch,
- * buckets them by (owner, region of the owner's table) and appends every bucket to its slab inside the owner's receive
- * buffer -- dests[o], local memory for o == self, a peer GPU's buffer opened with kmu_ipc_open otherwise: the stores
- * cross NVLink from inside the kernel.  Every rank creates its counter with the same arguments (same capacity); a
- * receive buffer holds nregions * nowners slabs of slab_cap keys, slab (r, s) = what sender s found for region r.
+ * buckets them by owner and appends every bucket to its slab inside the owner's receive buffer -- dests[o], local memory
+ * for o == self, a peer GPU's buffer opened with kmu_ipc_open otherwise: the stores cross NVLink from inside the kernel.
+ * Every rank creates its counter with the same arguments (same capacity); a receive buffer holds nregions * nowners slabs of
+ * slab_cap keys, slab (r, s) = what sender s found for region r.  Among several owners nregions is 1 (one slab per sender:
+ * long runs for the NVLink stores; the receiver cuts what it got by region of its table inside kmu_count_insert_slabs);
+ * with one owner the buckets are the regions of the local table.
  *   kmu_count_exchange_geometry : nregions for this table and this number of owners;
  *   kmu_count_exchange_scatter  : the kernel; sent_counts[o * nregions + r] = keys this rank appended for (o, r);
  *                                 *overflowed != 0 when a slab was too small (nothing may be inserted from this round);

@@ -312,6 +312,70 @@ int32_t insert_two_phase(kmu_ctx* ctx, kmu_counter* c, const kmu_seqbatch* b, bo
     return KMU_OK;
 }
 
+// The keys of `nseg` segments `stride` keys apart (counts_host[s] = counts_dev[s] keys in segment s: what the senders of
+// an exchange stored into this rank's receive buffer): ONE partition by region of the table over all segments, then the
+// regioned insertion -- one sweep of the table whatever the number of senders.  Segments too large for the slab budget
+// go through insert_two_phase one by one.
+int32_t insert_segments(kmu_ctx* ctx, kmu_counter* c, const void* keys, uint64_t stride, uint32_t nseg, const uint64_t* counts_host,
+                        const unsigned long long* counts_dev, uint64_t total, uint64_t* launches) {
+    const size_t esz = c->key64 ? 8 : 4;
+    if (total == 0) return KMU_OK;
+    const RegionGeom rg = region_geometry(c->capacity, c->key64, 1);
+    const uint64_t slab_cap = slab_capacity(total, rg.ncoarse);
+    const uint64_t need = slab_cap * rg.ncoarse * esz;
+    if (!two_phase_wanted(c, total) || slab_cap >= 0xFFFFFFFFull || (need > ctx->sig_dev.cap && need > slab_budget_bytes(ctx->sig_dev.cap))) {
+        for (uint32_t sg = 0; sg < nseg; ++sg) {
+            if (!counts_host[sg]) continue;
+            const uint8_t* seg = (const uint8_t*)keys + (uint64_t)sg * stride * esz;
+            if (two_phase_wanted(c, counts_host[sg])) {
+                int32_t rc = insert_two_phase(ctx, c, nullptr, false, seg, counts_host[sg], launches);
+                if (rc) return rc;
+            } else {
+                CUDA_TRY(kmu::launch_count_insert_keys(seg, counts_host[sg], c->key64, c->view(), ctx->sm_count, ctx->stream));
+                *launches += 1;
+            }
+        }
+        return KMU_OK;
+    }
+    CUDA_TRY(ctx->sig_dev.reserve(need));
+    CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * PART_SCRATCH_WORDS));
+    unsigned long long* cursors = (unsigned long long*)ctx->counters.p;
+    unsigned long long* flags = cursors + OFF_FLAGS;
+    void** d_dest = (void**)(cursors + OFF_DESTS);
+    void* slab_ptr = ctx->sig_dev.p;
+    CUDA_TRY(cudaMemcpyAsync(d_dest, &slab_ptr, sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(cursors, 0, sizeof(unsigned long long) * (MAX_BUCKETS + 64), ctx->stream));
+    kmu::PartGeom g{};
+    g.nowners = 1;
+    g.nregions = rg.ncoarse;
+    g.capmask = c->capacity - 1;
+    g.shift = rg.coarse_shift;
+    g.nsend = 1;
+    g.self = 0;
+    g.slab_cap = slab_cap;
+    kmu::KeySegs segs;
+    segs.stride = stride;
+    segs.nseg = nseg;
+    segs.counts = counts_dev;
+    segs.count_stride = 1;
+    CUDA_TRY(kmu::launch_count_part_keys(keys, stride, segs, c->key64, g, d_dest, cursors, flags, ctx->sm_count, ctx->stream));
+    *launches += 1;
+    int32_t rc = insert_level1_slabs(ctx, c, slab_ptr, slab_cap, 1, cursors, rg, flags, launches);
+    if (rc) return rc;
+    unsigned long long lost = 0;
+    CUDA_TRY(cudaMemcpyAsync(&lost, flags, sizeof(lost), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (lost) {  // a region slab overflowed (one key repeated millions of times): the insertion was skipped, go in directly
+        for (uint32_t sg = 0; sg < nseg; ++sg) {
+            if (!counts_host[sg]) continue;
+            CUDA_TRY(kmu::launch_count_insert_keys((const uint8_t*)keys + (uint64_t)sg * stride * esz, counts_host[sg], c->key64, c->view(),
+                                                   ctx->sm_count, ctx->stream));
+            *launches += 1;
+        }
+    }
+    return KMU_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -704,9 +768,17 @@ int32_t kmu_count_partition_scatter(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_
 // ---- fused exchange: extraction + (owner, region) bucketing + NVLink stores in ONE kernel and ONE walk -----------------
 // Every rank holds a table of the same capacity (kmu_count_create with the same arguments).  The receive buffer of a
 // rank is nregions * nowners slabs of slab_cap keys: slab (r, s) holds what sender s found for region r of the table.
+// Among several owners the exchange buckets by OWNER ONLY (one slab per sender in every receive buffer: runs of thousands of
+// keys per tile, which is what NVLink stores want) and the receiver partitions what it got by region of its table itself
+// (kmu_count_insert_slabs): bucketing by (owner, region) in one pass needs owners x 1024 buckets, and past ~1000 buckets
+// a tile of 4096 k-mers leaves two keys per run (measured at 2 GPUs: 93 ms of scatter + 116 ms of two-level insertion
+// against 46 + 78 on one GPU).  One owner: the local table's regions, i.e. the partition of the single-GPU path.
+uint32_t exchange_regions(const kmu_counter* c, uint32_t nowners) {
+    return nowners > 1 ? 1u : region_geometry(c->capacity, c->key64, 1).ncoarse;
+}
 int32_t kmu_count_exchange_geometry(const kmu_counter* c, uint32_t nowners, uint32_t* nregions) {
     if (!c || !nregions || nowners < 1 || nowners > 64) return fail(KMU_EINVAL, "bad argument");
-    *nregions = region_geometry(c->capacity, c->key64, nowners).ncoarse;
+    *nregions = exchange_regions(c, nowners);
     return KMU_OK;
 }
 
@@ -720,8 +792,9 @@ int32_t kmu_count_exchange_scatter(kmu_ctx* ctx, const kmu_seqbatch* b, const km
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};
-    const RegionGeom rg = region_geometry(c->capacity, c->key64, nowners);
-    const uint32_t nb = nowners * rg.ncoarse;
+    const RegionGeom rg = region_geometry(c->capacity, c->key64, 1);
+    const uint32_t nreg_x = exchange_regions(c, nowners);
+    const uint32_t nb = nowners * nreg_x;
     if (nb > MAX_BUCKETS) return fail(KMU_EINVAL, "too many (owner, region) buckets: %u", nb);
     CUDA_TRY(ctx->counters.reserve(sizeof(unsigned long long) * PART_SCRATCH_WORDS));
     unsigned long long* cursors = (unsigned long long*)ctx->counters.p;
@@ -731,7 +804,7 @@ int32_t kmu_count_exchange_scatter(kmu_ctx* ctx, const kmu_seqbatch* b, const km
     CUDA_TRY(cudaMemsetAsync(cursors, 0, sizeof(unsigned long long) * (MAX_BUCKETS + 64), ctx->stream));
     kmu::PartGeom g{};
     g.nowners = nowners;
-    g.nregions = rg.ncoarse;
+    g.nregions = nreg_x;
     g.capmask = c->capacity - 1;
     g.shift = rg.coarse_shift;
     g.nsend = nowners;
@@ -763,8 +836,8 @@ int32_t kmu_count_insert_slabs(kmu_ctx* ctx, kmu_counter* c, const void* slabs, 
     std::lock_guard<std::mutex> lk(ctx->mu);
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};
-    const RegionGeom rg = region_geometry(c->capacity, c->key64, nsend);
-    const size_t n = (size_t)nsend * rg.ncoarse;
+    const RegionGeom rg = region_geometry(c->capacity, c->key64, 1);
+    const size_t n = (size_t)nsend * exchange_regions(c, nsend);
     uint64_t total = 0;
     for (size_t i = 0; i < n; ++i) {
         if (counts[i] > slab_cap) return fail(KMU_EOVERFLOW, "a slab holds %llu keys, capacity %llu", (unsigned long long)counts[i], (unsigned long long)slab_cap);
@@ -775,7 +848,9 @@ int32_t kmu_count_insert_slabs(kmu_ctx* ctx, kmu_counter* c, const void* slabs, 
     CUDA_TRY(cudaMemcpyAsync(ctx->misc.p, counts, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, ctx->stream));
     cudaEventRecord(ctx->ev[0], ctx->stream);
     uint64_t nl = 0;
-    int32_t rc0 = insert_level1_slabs(ctx, c, slabs, slab_cap, nsend, (const unsigned long long*)ctx->misc.p, rg, nullptr, &nl);
+    int32_t rc0 = KMU_OK;
+    if (nsend == 1) rc0 = insert_level1_slabs(ctx, c, slabs, slab_cap, 1, (const unsigned long long*)ctx->misc.p, rg, nullptr, &nl);
+    else rc0 = insert_segments(ctx, c, slabs, slab_cap, nsend, counts, (const unsigned long long*)ctx->misc.p, total, &nl);
     if (rc0) return rc0;
     cudaEventRecord(ctx->ev[1], ctx->stream);
     ctx->launches += nl;

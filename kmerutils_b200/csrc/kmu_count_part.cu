@@ -68,8 +68,8 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
     uint16_t* tb = (uint16_t*)(sorted + PART_TILE_KEYS);
     uint16_t* sb = tb + PART_TILE_KEYS;
     uint32_t* hist = (uint32_t*)(sb + PART_TILE_KEYS);  // counts, then the fill cursor of the bucket inside `sorted`
-    uint32_t* boff = hist + NB;
-    uint32_t* gpos = boff + NB;
+    uint32_t* jend = hist + NB;       // one past the last sorted index of the bucket that still fits its slab
+    V** dptr = (V**)(jend + NB);  // slab address of sorted index 0 of the bucket (hist and jend take 8 NB bytes: aligned)
     __shared__ uint32_t tile_n, warp_sums[PART_THREADS / 32];
     __shared__ unsigned long long seg_pref[65], seg_n[64];  // key-array form: tiles before segment s, keys of segment s
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
     if (FROM_SEQ && t0 < t1) s = seq_of_byte(b.byte_off, b.nseq, byte_begin + t0 * PART_TILE_BYTES + (uint64_t)wib * PART_WARP_BYTES);
     __syncthreads();
     bool lost = false;
+    const uint32_t lg_regions = (uint32_t)__ffs((int)g.nregions) - 1;
 
     for (uint64_t t = t0; t < t1; ++t) {
         // ---- phase 1: the tile's keys and bucket ids into shared memory, histogram of the buckets
@@ -192,15 +193,16 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
             for (uint32_t j = 0; j < 8; ++j) {
                 if (j < per_t && first + j < NB) {
                     const uint32_t bk = first + j;
-                    boff[bk] = off;
                     hist[bk] = off;
-                    uint32_t gp = 0;
                     if (c[j]) {
                         const unsigned long long at = atomicAdd(&cursors[bk], (unsigned long long)c[j]);
                         if (at + c[j] > g.slab_cap) lost = true;
-                        gp = at > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)at;
+                        // sorted[off + i] goes to slab[at + i]: one pointer and one bound per bucket, not per key
+                        const uint32_t o = bk >> lg_regions, r = bk & (g.nregions - 1);  // nregions is a power of two
+                        dptr[bk] = dests[o] + ((uint64_t)r * g.nsend + g.self) * g.slab_cap + at - off;
+                        const unsigned long long room = at < g.slab_cap ? g.slab_cap - at : 0ull;
+                        jend[bk] = off + (uint32_t)(room < c[j] ? room : c[j]);
                     }
-                    gpos[bk] = gp;
                     off += c[j];
                 }
             }
@@ -217,12 +219,7 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
         // ---- phase 4: every bucket's run goes to its slab (consecutive threads, consecutive addresses)
         for (uint32_t j = tid; j < n; j += PART_THREADS) {
             const uint32_t bk = sb[j];
-            const uint64_t pos = (uint64_t)gpos[bk] + (j - boff[bk]);
-            if (pos < g.slab_cap) {
-                const uint32_t o = bk / g.nregions, r = bk - o * g.nregions;
-                V* dst = dests[o] + ((uint64_t)r * g.nsend + g.self) * g.slab_cap;
-                dst[pos] = sorted[j];
-            }
+            if (j < jend[bk]) dptr[bk][j] = sorted[j];
         }
         __syncthreads();
         for (uint32_t p = tid; p < NB; p += PART_THREADS) hist[p] = 0;
@@ -288,7 +285,7 @@ __global__ void __launch_bounds__(256) count_insert_slabs_kernel(const V* __rest
 
 size_t count_part_smem_bytes(bool key64, uint32_t nbuckets) {
     const size_t esz = key64 ? 8 : 4;
-    return (size_t)PART_TILE_KEYS * (2 * esz + 4) + (size_t)nbuckets * 12;
+    return (size_t)PART_TILE_KEYS * (2 * esz + 4) + (size_t)nbuckets * 16 + 8;
 }
 
 int count_part_grid(int sm_count) { return sm_count * 2; }

@@ -239,9 +239,9 @@ def exchange_slab_cap(nk_max_per_rank, world, nregions):
 
 def count_round_fused(engine, batch, counter, xchg, nk_bound, canonical=True, group=None, phases=None):
     """One round of multi-GPU counting with the fused exchange (kmu_count_exchange_scatter): a single kernel per rank
-    extracts the canonical k-mers, buckets them by (owner = intNN_hash % world, region of the owner's table) and stores
-    them into the owners' receive buffers over NVLink; the ranks then share their bucket counts (a few KB) and every rank
-    inserts its buffer region after region (kmu_count_insert_slabs).  `nk_bound`: no rank sends more k-mers than this in
+    extracts the canonical k-mers, buckets them by owner (intNN_hash % world) and stores them into the owners' receive
+    buffers over NVLink; the ranks then share their bucket counts (a few KB) and every rank partitions what it received by
+    region of its table and inserts region after region (kmu_count_insert_slabs).  `nk_bound`: no rank sends more k-mers than this in
     a round (fixes the slab size; the same on every rank).  Every rank's `counter` was created with the same arguments.
     -> (keys received, bytes sent to peers)"""
     import kmerutils_b200 as kb
