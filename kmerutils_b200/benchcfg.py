@@ -174,6 +174,11 @@ def run_c3(kb, eng, T, rank, world, steps, warmup, peak, reads_per_step=26_666_6
     it = [0]
 
     def step():
+        if it[0] == warmup:  # the phases of the timed rounds only (the warm-up round allocates the slabs and maps the peers)
+            for key in phases:
+                phases[key] = 0.0
+            sent_bytes[0] = 0
+        t_step = time.perf_counter()
         reads = batches[it[0]]
         it[0] += 1
         if world == 1:
@@ -192,14 +197,36 @@ def run_c3(kb, eng, T, rank, world, steps, warmup, peak, reads_per_step=26_666_6
             counter.insert_kmers(device_ptr=recv.data_ptr(), n=recv.numel())
             phases["insert_ms"] += eng.last_times()["kernel_ms"]
             sent_bytes[0] += 8 * int(sum(int(c) for i, c in enumerate(counts) if i != rank))
+        phases["step_wall_ms"] = phases.get("step_wall_ms", 0.0) + (time.perf_counter() - t_step) * 1e3
 
     def timed_step():
         step()
 
     # warm-up rounds (allocations, IPC mapping), then the timed ones
     ms = T.run(timed_step, steps, warmup)
-    for key in phases:
-        phases[key] = phases[key] / nrounds
+    # every rank's insertion time and SM clock right after the timed rounds (the ranks do the same work: a spread is the GPUs')
+    by_rank = None
+    if world > 1:
+        mhz = -1.0
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("LOCAL_RANK", 0)))
+            mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            pass
+        mine = torch.tensor([phases["insert_ms"] / steps, phases["scatter_ms"] / steps, mhz], dtype=torch.float64, device=T.dev)
+        allr = torch.empty((world, 3), dtype=torch.float64, device=T.dev)
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.cpu().numpy()
+        by_rank = {"insert_ms": [round(float(x), 1) for x in allr[:, 0]], "scatter_ms": [round(float(x), 1) for x in allr[:, 1]],
+                   "sm_mhz_after": [float(x) for x in allr[:, 2]]}
+    # per step, slowest and fastest rank of every phase (the step itself is the max over ranks, barrier waits included)
+    phases_min = {}
+    for key in sorted(phases):
+        phases[key] = phases[key] / steps
+        phases_min[key] = -T.max_over_ranks(-phases[key])
+        phases[key] = T.max_over_ranks(phases[key])
     st = counter.stats()
     tot = kd.allreduce_sum([st["nb_distinct"], st["nb_unique"], st["nb_inserted"]], T.dev)
     ok = tot[2] == nrounds * nk_round * world
@@ -211,7 +238,7 @@ def run_c3(kb, eng, T, rank, world, steps, warmup, peak, reads_per_step=26_666_6
     counter.destroy()
     if xchg:
         xchg.close()
-    lim = max(phases, key=lambda q: phases[q])
+    lim = max((q for q in phases if q not in ('step_wall_ms', 'end_barrier_ms')), key=lambda q: phases[q])
     nk_frac = (read_len - k + 1) / read_len
     return _entry("C3: 150 b reads from a 100 Mb genome (0.5 % substitutions), k=31 canonical Kmer64bit exact counting, "
                   f"{reads_per_step} reads / {reads_per_step * read_len / 1e9:.2f} Gbases per GPU per step", bases, ms,
@@ -219,8 +246,8 @@ def run_c3(kb, eng, T, rank, world, steps, warmup, peak, reads_per_step=26_666_6
                   "count_part_kernel (partition by owner x table region in shared memory) + count_insert_slabs_kernel "
                   "(regioned insertion, updates hit L2)", "table (64 GB+) and inputs far larger than L2",
                   exchange=("none" if world == 1 else exchange), collective_in_timed_region=world > 1,
-                  phases_ms_per_step=phases, limiting_phase=lim,
-                  nvlink_bytes_sent_per_gpu_per_step=int(sent_bytes[0] // max(nrounds, 1)),
+                  phases_ms_per_step=phases, phases_ms_per_step_fastest_rank=phases_min, by_rank=by_rank, limiting_phase=lim,
+                  nvlink_bytes_sent_per_gpu_per_step=int(sent_bytes[0] // max(steps, 1)),
                   nb_distinct=tot[0], nb_unique=tot[1], nb_inserted=tot[2], conservation_ok=bool(ok), table_slots_per_gpu=table_slots,
                   steps=steps, warmup=warmup)
 

@@ -1147,8 +1147,10 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
         ctx->last = kmu_times{};
         cudaStream_t st = ctx->stream;
         // the genomes are independent: NS of them are in flight at once, each on its own stream with its own table and
-        // slots (one 5 Mb genome fills half of the GPU: its 64 MB table sits in L2, its launches are short)
-        const int NS = (int)std::min<uint64_t>(kmu_ctx::GROUP_STREAMS, ngroups);
+        // slots (the launches of one genome are short and leave SMs idle; the tables of the genomes in flight must fit L2)
+        int ns_want = 2;  // measured on 148 genomes of 5 Mb (ms per call): 1 stream 50.5, 2: 37.6, 3: 38.6, 4: 43.9 -- two 64 MB tables fill the L2
+        if (const char* e = std::getenv("KMU_GROUP_STREAMS")) ns_want = std::max(1, std::min(kmu_ctx::GROUP_STREAMS, std::atoi(e)));  // measurements
+        const int NS = (int)std::min<uint64_t>((uint64_t)ns_want, ngroups);
         cudaError_t me = cudaSuccess;
         for (int q = 0; q < NS && me == cudaSuccess; ++q) {
             if (!ctx->group_stream[q]) me = cudaStreamCreateWithFlags(&ctx->group_stream[q], cudaStreamNonBlocking);

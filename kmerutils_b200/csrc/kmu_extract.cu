@@ -164,7 +164,7 @@ __device__ __forceinline__ uint32_t int32_hash_folded(uint32_t v, uint32_t c0) {
     key *= 9u;
     key ^= key >> 6;
     key = key * 0xFFFFF801u - 1u;  // key + ~(key << 11)
-    key ^= key >> 16;
+    key ^= key >> 16;  // (the hash's shifts stay on the alu pipe: as high multiplies, all three 787 -> 739 Gbases/s, one 822 -> 811)
     return key;
 }
 template <typename V, bool HASH>

@@ -275,7 +275,10 @@ def count_round_fused(engine, batch, counter, xchg, nk_bound, canonical=True, gr
     if phases is not None:
         phases["insert_ms"] = phases.get("insert_ms", 0.0) + engine.last_times()["kernel_ms"]
     if world > 1:
+        t_bar = _time.perf_counter()
         dist.barrier(group=group)  # the buffers may be overwritten by the next round
+        if phases is not None:  # what this rank waits for the slowest one
+            phases["end_barrier_ms"] = phases.get("end_barrier_ms", 0.0) + (_time.perf_counter() - t_bar) * 1e3
     sent_peer = int(sent.sum() - sent[rank].sum()) * esz
     return int(counts.sum()), sent_peer
 
