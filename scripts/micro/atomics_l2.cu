@@ -15,26 +15,44 @@ __global__ void k(unsigned long long* tab, uint64_t mask, uint64_t n, uint64_t s
         } else if (MODE == 2) {  // plain (non-volatile) load via ld.global.cg + RED
             unsigned long long cur = __ldcg(tab + 2 * s);
             if (cur != 12345) atomicAdd(tab + 2 * s + 1, 1ULL);
-        } else {  // load only
+        } else if (MODE == 3) {  // load only
             unsigned long long cur = __ldcg(tab + 2 * s);
             if (cur == 12345) tab[0] = 1;
+        } else if (MODE == 4) {  // load of one slot, RED on an UNRELATED slot of the region (is the cost of mode 0 tied to the same sector?)
+            unsigned long long cur = __ldcg(tab + 2 * s);
+            const uint64_t s2 = mix(i + seed + 0x9E3779B97F4A7C15ULL) & mask;
+            if (cur != 12345) atomicAdd(tab + 2 * s2 + 1, 1ULL);
+        } else if (MODE == 5) {  // RED first (fire and forget), then the load of the same slot, nothing depends on it until the end
+            atomicAdd(tab + 2 * s + 1, 1ULL);
+            unsigned long long cur = __ldcg(tab + 2 * s);
+            if (cur == 12345) tab[0] = 1;
+        } else if (MODE == 6) {  // one 128-bit load of the whole slot (key and count), then the RED
+            const ulonglong2 e = __ldcg((const ulonglong2*)(tab + 2 * s));
+            if (e.x != 12345) atomicAdd(tab + 2 * s + 1, 1ULL);
+        } else {  // MODE 7: atomicAdd WITH return on the count word only (one round trip, no load)
+            unsigned long long old = atomicAdd(tab + 2 * s + 1, 1ULL);
+            if (old == 0xFFFFFFFFFFFFull) tab[0] = 1;
         }
     }
 }
 int main() {
     const uint64_t n = 400000000ull;
-    for (uint64_t mb : {16ull, 32ull, 64ull, 256ull, 4096ull}) {
+    for (uint64_t mb : {32ull, 64ull, 4096ull}) {
         uint64_t slots = mb * 1024 * 1024 / 16;
         unsigned long long* tab;
         cudaMalloc(&tab, slots * 16);
         cudaMemset(tab, 0, slots * 16);
-        for (int mode = 0; mode < 4; ++mode) {
+        for (int mode = 0; mode < 8; ++mode) {
             cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
             cudaEventRecord(a);
             if (mode == 0) k<0><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
             if (mode == 1) k<1><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
             if (mode == 2) k<2><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
             if (mode == 3) k<3><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
+            if (mode == 4) k<4><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
+            if (mode == 5) k<5><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
+            if (mode == 6) k<6><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
+            if (mode == 7) k<7><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
             cudaEventRecord(b); cudaEventSynchronize(b);
             float ms; cudaEventElapsedTime(&ms, a, b);
             printf("region %5llu MB mode %d : %.2f ms  %.1f G updates/s\n", (unsigned long long)mb, mode, ms, n / ms / 1e6);
