@@ -141,3 +141,43 @@ def test_exchange_scatter_single_rank(engine, oracle):
         assert np.array_equal(ctr.get_count(keys), np.minimum(cnts, 255).astype(np.uint32))
         ctr.destroy()
     batch.destroy()
+
+
+def test_exchange_two_owners_on_one_gpu(engine, oracle):
+    """The multi-owner exchange on ONE GPU: two read sets play ranks 0 and 1, their scatter kernels bucket by owner only and
+    store into both owners' receive buffers (all local here, peers over NVLink in a job), and every owner partitions the two
+    senders' segments by region of its table and inserts them (kmu_count_insert_slabs with two senders) -- the path every
+    rank of a multi-GPU round runs, checked against the oracle's counts of the union."""
+    import torch
+    from kmerutils_b200.dist import exchange_slab_cap
+    k, ktype = 31, kb.KMER64
+    rng = np.random.default_rng(5)
+    reads = genome_reads(oracle, 13, 60000, 6000, 150, rng)
+    half = len(reads) // 2
+    batches = [engine.batch_from_ascii(reads[:half])[0], engine.batch_from_ascii(reads[half:])[0]]
+    whole, _ = engine.batch_from_ascii(reads)
+    packed, off, nb = whole.download()
+    keys, cnts = oracle.count_kmers(packed, off, nb, k, ktype, True)
+    owner = (oracle.apply_hash(keys, k, ktype, kb.HASH_INVHASH) % np.uint64(2)).astype(np.int64)  # DispatchableT::dispatch
+    for region_kb, min_keys in ((64, 1), (65536, 1 << 40)):  # regioned insertion of the segments / direct insertion (small job)
+        with knobs(KMU_COUNT_REGION_KB=region_kb, KMU_COUNT_TWO_PHASE_MIN_KEYS=min_keys):
+            ctrs = [engine.counter(k, ktype, capacity=1 << 18, count_bits=8) for _ in range(2)]
+            assert ctrs[0].exchange_regions(2) == 1
+            slab_cap = exchange_slab_cap(max(b.kmer_count(k) for b in batches), 2, 1)
+            bufs = [torch.empty(2 * slab_cap, dtype=torch.int64, device="cuda:0") for _ in range(2)]
+            sent = []
+            for r in range(2):
+                s_r, ovf = ctrs[r].exchange_scatter(batches[r], 2, r, slab_cap, [b_.data_ptr() for b_ in bufs], True)
+                assert not ovf and int(s_r.sum()) == batches[r].kmer_count(k)
+                sent.append(s_r)
+            for o in range(2):
+                ctrs[o].insert_slabs(bufs[o].data_ptr(), slab_cap, np.array([[sent[0][o, 0]], [sent[1][o, 0]]], dtype=np.uint64))
+            for o in range(2):
+                mine = owner == o
+                st = ctrs[o].stats()
+                assert st["nb_distinct"] == int(mine.sum()) and st["nb_unique"] == int((cnts[mine] == 1).sum())
+                assert np.array_equal(ctrs[o].get_count(keys[mine]), np.minimum(cnts[mine], 255).astype(np.uint32))
+                assert not ctrs[o].get_count(keys[~mine]).any()
+                ctrs[o].destroy()
+    for b_ in batches + [whole]:
+        b_.destroy()
