@@ -115,18 +115,27 @@ def run_extract(kb, eng, T, rank, world, steps, warmup, peak, batch, bases):
     cases = [
         ("extract k=8: KmerGenerator<Kmer32bit> + canonical + int32_hash, all k-mers materialised (u32)",
          lambda: kb._lib.check(lib.kmu_generate_kmers(ctx, batch.handle, 8, kb.KMER32, kb.HASH_CANON_INVHASH, buf.data_ptr(), None, 1)),
-         0.25 + 4.0 * nk8 / bases, "generate_kmers_vec_kernel<u32>"),
+         0.25 + 4.0 * nk8 / bases, "generate_kmers_run_kernel<u32>"),
         ("extract k=31: KmerGenerator<Kmer64bit> + canonical, all k-mers materialised (u64)",
          lambda: kb._lib.check(lib.kmu_generate_kmers(ctx, batch.handle, 31, kb.KMER64, kb.HASH_CANON_RAW, buf.data_ptr(), None, 1)),
-         0.25 + 8.0 * nk31 / bases, "generate_kmers_vec_kernel<u64>"),
+         0.25 + 8.0 * nk31 / bases, "generate_kmers_run_kernel<u64>"),
         ("ntHash k=31: canonical hash of every k-mer (u64)",
          lambda: kb._lib.check(lib.kmu_nthash_canonical(ctx, batch.handle, 31, 1, buf.data_ptr(), None, 1)),
-         0.25 + 8.0 * nk31 / bases, "nthash_warp_kernel"),
+         0.25 + 8.0 * nk31 / bases, "nthash_run_kernel"),
     ]
     for name, fn, bpb, kernel in cases:
+        # the first call on a batch for a given k also builds and uploads the per-sequence output offsets (host loop over the
+        # lengths + one copy; kept with the batch afterwards, like the processing order of the sketch kernels): timed apart
+        T.barrier()
+        t0 = time.perf_counter()
+        fn()
+        T.barrier()
+        first_ms = (time.perf_counter() - t0) * 1e3
         ms = T.run(fn, steps, warmup)
         out.append(_entry(name + " on the C2 reads", bases * world, ms, bpb, peak, world, "weak", kernel,
-                          "inputs (1.1 GB packed) and outputs (17-35 GB) larger than L2"))
+                          "inputs (1.1 GB packed) and outputs (17-35 GB) larger than L2",
+                          first_call_ms=T.max_over_ranks(first_ms),
+                          note="every step recomputes and rewrites all k-mers; only the output offsets of the batch (metadata) are kept between calls"))
     del buf
     return out
 

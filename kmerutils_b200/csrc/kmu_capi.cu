@@ -239,6 +239,7 @@ void kmu_seqbatch_destroy(kmu_seqbatch* b) {
     ScopedDevice sd(b->device);
     b->order_cache.order.release();
     b->order_cache.cursor_dev.release();
+    b->koff_cache.dev.release();
     if (!b->owns && b->owns_byte_off && b->byte_off) cudaFree(b->byte_off);
     if (b->owns) {
         if (b->packed) cudaFree(b->packed);
@@ -646,22 +647,29 @@ uint64_t kmu_kmer_count(const kmu_seqbatch* b, uint32_t k) {
     return b->kmer_count(k);
 }
 
+// -> *d_off: device array of nseq + 1 output offsets for this k (kept with the batch: KmerOffCache)
 static int32_t upload_kmer_offsets(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, uint64_t* out_off_host,
-                                   uint64_t* total_out) {
-    std::vector<uint64_t> off(b->nseq + 1);
-    uint64_t acc = 0;
-    for (uint64_t i = 0; i < b->nseq; ++i) {
-        off[i] = acc;
-        uint64_t L = b->h_nbases[i];
-        acc += L >= k ? L - k + 1 : 0;
+                                   uint64_t* total_out, const uint64_t** d_off) {
+    KmerOffCache& c = b->koff_cache;
+    if (c.k != k || c.host.size() != b->nseq + 1 || !c.dev.p) {
+        c.k = 0;
+        c.host.resize(b->nseq + 1);
+        uint64_t acc = 0;
+        for (uint64_t i = 0; i < b->nseq; ++i) {
+            c.host[i] = acc;
+            const uint64_t L = b->h_nbases[i];
+            acc += L >= k ? L - k + 1 : 0;
+        }
+        c.host[b->nseq] = acc;
+        c.total = acc;
+        CUDA_TRY(c.dev.reserve(sizeof(uint64_t) * (b->nseq + 1)));
+        CUDA_TRY(cudaMemcpyAsync(c.dev.p, c.host.data(), sizeof(uint64_t) * (b->nseq + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // pageable source
+        c.k = k;
     }
-    off[b->nseq] = acc;
-    *total_out = acc;
-    if (out_off_host) std::copy(off.begin(), off.end(), out_off_host);
-    CUDA_TRY(ctx->misc.reserve(sizeof(uint64_t) * (b->nseq + 1)));
-    CUDA_TRY(cudaMemcpyAsync(ctx->misc.p, off.data(), sizeof(uint64_t) * (b->nseq + 1), cudaMemcpyHostToDevice,
-                             ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // `off` is a stack-lifetime pageable buffer
+    *total_out = c.total;
+    *d_off = (const uint64_t*)c.dev.p;
+    if (out_off_host) std::copy(c.host.begin(), c.host.end(), out_off_host);
     return KMU_OK;
 }
 
@@ -673,7 +681,8 @@ int32_t kmu_generate_kmers(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int3
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};
     uint64_t total = 0;
-    int32_t rc = upload_kmer_offsets(ctx, b, k, out_off, &total);
+    const uint64_t* d_koff = nullptr;
+    int32_t rc = upload_kmer_offsets(ctx, b, k, out_off, &total, &d_koff);
     if (rc) return rc;
     if (total == 0) return KMU_OK;
     if (!out) return fail(KMU_EINVAL, "null output buffer");
@@ -685,7 +694,7 @@ int32_t kmu_generate_kmers(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int3
     }
     kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    CUDA_TRY(kmu::launch_generate_kmers(v, b->packed_bytes, k, kmer_type, hash_kind, (const uint64_t*)ctx->misc.p, dout, ctx->stream));
+    CUDA_TRY(kmu::launch_generate_kmers(v, b->packed_bytes, k, kmer_type, hash_kind, d_koff, dout, ctx->stream));
     cudaEventRecord(ctx->ev[1], ctx->stream);
     ctx->launches += 1;
     ctx->last.launches = 1;
@@ -711,7 +720,8 @@ int32_t kmu_nthash_canonical(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, ui
     ScopedDevice sd(ctx->device);
     ctx->last = kmu_times{};
     uint64_t total = 0;
-    int32_t rc = upload_kmer_offsets(ctx, b, k, nullptr, &total);
+    const uint64_t* d_koff = nullptr;
+    int32_t rc = upload_kmer_offsets(ctx, b, k, nullptr, &total, &d_koff);
     if (rc) return rc;
     if (total == 0) return KMU_OK;
     if (!out_hash) return fail(KMU_EINVAL, "null output buffer");
@@ -725,7 +735,7 @@ int32_t kmu_nthash_canonical(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, ui
     }
     kmu::SeqView v{b->packed, b->byte_off, b->nbases, b->nseq};
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    CUDA_TRY(kmu::launch_nthash(v, b->packed_bytes, k, n_multi, (const uint64_t*)ctx->misc.p, dh, ds, ctx->stream));
+    CUDA_TRY(kmu::launch_nthash(v, b->packed_bytes, k, n_multi, d_koff, dh, ds, ctx->stream));
     cudaEventRecord(ctx->ev[1], ctx->stream);
     ctx->launches += 1;
     ctx->last.launches = 1;

@@ -129,8 +129,18 @@ struct OctaveClass {
     uint64_t nk_max;        // largest k-mer count in the class (the last class also holds sequences without k-mers)
 };
 
+// output offsets of the materialising kernels (exclusive prefix of the k-mer counts, nseq + 1 entries), per k: computed on
+// the host and uploaded once per (batch, k) -- 746 333 reads cost ~1 ms of host loop + copy + synchronisation per call otherwise
+struct KmerOffCache {
+    uint32_t k = 0;
+    uint64_t total = 0;
+    std::vector<uint64_t> host;
+    DevBuf dev;
+};
+
 struct kmu_seqbatch {
     mutable OrderCache order_cache;
+    mutable KmerOffCache koff_cache;
     int device = 0;
     uint8_t* packed = nullptr;
     uint64_t* byte_off = nullptr;
