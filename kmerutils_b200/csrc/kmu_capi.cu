@@ -70,12 +70,14 @@ int32_t batch_alloc(kmu_ctx* ctx, const uint64_t* nbases, uint64_t nseq, kmu_seq
     b->alphabet = alphabet;
     b->h_nbases.assign(nbases, nbases + nseq);
     b->packed_bytes = layout_offsets(nbases, nseq, b->h_byte_off, alphabet);
-    uint64_t shortest = ~0ull - 1;  // kept with the batch: kmer_count(k) is then O(1) whenever every sequence holds a k-mer
+    uint64_t shortest = ~0ull - 1, longest = 0;  // kept with the batch: kmer_count(k) is then O(1) whenever every sequence holds a k-mer
     for (uint64_t i = 0; i < nseq; ++i) {
         b->total_bases += nbases[i];
         shortest = nbases[i] < shortest ? nbases[i] : shortest;
+        longest = nbases[i] > longest ? nbases[i] : longest;
     }
     b->min_nbases = shortest;
+    b->max_nbases = longest;
     cudaError_t e = cudaMalloc((void**)&b->packed, b->packed_bytes + TAIL_SLACK);
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->byte_off, sizeof(uint64_t) * (nseq + 1));
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->nbases, sizeof(uint64_t) * (nseq + 1));
@@ -1264,14 +1266,13 @@ int32_t kmu_sketch_pmh3a(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_t k, int32_
     if (b->nseq == 0) return KMU_OK;
     if (!sig) return fail(KMU_EINVAL, "null signature buffer");
     if (b->nseq >= 0xFFFFFFFFull) return fail(KMU_EINVAL, "more than 2^32-1 sequences in one batch");
-    for (uint64_t L : b->h_nbases)
-        if (L >= (1ull << 30)) return fail(KMU_EINVAL, "a single sequence is limited to 2^30 bases here (kmu_sketch_pmh3a_whole has no limit)");
+    if (b->longest() >= (1ull << 30)) return fail(KMU_EINVAL, "a single sequence is limited to 2^30 bases here (kmu_sketch_pmh3a_whole has no limit)");
     // Genome-sized sequences over a large key space: the team kernel keeps one sequence on one SM (a 5 Mb genome is
     // ~70 ms of one SM), the whole-file procedure (counting table in HBM + item kernel, the whole GPU on one sequence,
     // ~0.4 ms per 5 Mb) gives the same signature.  Taken when every sequence is long enough for its fixed ~0.1 ms.
     if (!kmer_type_is_aa(kmer_type) && k > 8 && !std::getenv("KMU_PMH3A_TEAM_ONLY")) {  // (tests compare the two paths)
-        uint64_t min_nk = ~0ull;
-        for (uint64_t L : b->h_nbases) min_nk = std::min<uint64_t>(min_nk, L >= k ? L - k + 1 : 0);
+        (void)b->kmer_count(k);  // fills min_nbases
+        const uint64_t min_nk = b->min_nbases >= k && b->min_nbases < ~0ull - 1 ? b->min_nbases - k + 1 : 0;
         if (min_nk >= 2000000 || (b->nseq * 2 <= (uint64_t)ctx->sm_count && min_nk >= 250000)) {
             std::vector<uint64_t> ones(b->nseq, 1);
             return kmu_sketch_pmh3a_groups(ctx, b, ones.data(), b->nseq, k, kmer_type, hash_kind, m, sig, sig_on_device);

@@ -157,6 +157,15 @@ struct kmu_seqbatch {
     mutable uint32_t kmer_total_k = 0;
     mutable uint64_t kmer_total = 0;
     mutable uint64_t min_nbases = ~0ull;  // shortest sequence (computed on first use)
+    mutable uint64_t max_nbases = ~0ull;  // longest sequence (computed on first use)
+    uint64_t longest() const {
+        if (max_nbases == ~0ull) {
+            uint64_t m = 0;
+            for (uint64_t L : h_nbases) m = L > m ? L : m;
+            max_nbases = m;
+        }
+        return max_nbases;
+    }
     uint64_t kmer_count(uint32_t k) const {
         if (k == 0) return 0;
         if (min_nbases == ~0ull) {

@@ -29,20 +29,31 @@ __global__ void k(unsigned long long* tab, uint64_t mask, uint64_t n, uint64_t s
         } else if (MODE == 6) {  // one 128-bit load of the whole slot (key and count), then the RED
             const ulonglong2 e = __ldcg((const ulonglong2*)(tab + 2 * s));
             if (e.x != 12345) atomicAdd(tab + 2 * s + 1, 1ULL);
-        } else {  // MODE 7: atomicAdd WITH return on the count word only (one round trip, no load)
+        } else if (MODE == 7) {  // atomicAdd WITH return on the count word only (one round trip, no load)
             unsigned long long old = atomicAdd(tab + 2 * s + 1, 1ULL);
             if (old == 0xFFFFFFFFFFFFull) tab[0] = 1;
+        } else if (MODE == 8) {  // the key read by an ATOMIC (compare-and-swap that changes nothing), then the RED: atomics only
+            unsigned long long cur = atomicCAS(tab + 2 * s, 12345ULL, 12345ULL);
+            if (cur != 12345) atomicAdd(tab + 2 * s + 1, 1ULL);
+        } else if (MODE == 9) {  // as 8 with atomicOr(key, 0)
+            unsigned long long cur = atomicOr(tab + 2 * s, 0ULL);
+            if (cur != 12345) atomicAdd(tab + 2 * s + 1, 1ULL);
+        } else {  // MODE 10: one 128-bit compare-and-swap on the whole slot (key, count) with a guessed count of 0
+            unsigned long long o0, o1;
+            asm volatile("{\n\t.reg .b128 c, n, o;\n\tmov.b128 c, {%3, %4};\n\tmov.b128 n, {%5, %6};\n\tatom.cas.b128 o, [%2], c, n;\n\tmov.b128 {%0, %1}, o;\n\t}"
+                         : "=l"(o0), "=l"(o1) : "l"(tab + 2 * s), "l"(0ULL), "l"(0ULL), "l"(0ULL), "l"(1ULL) : "memory");
+            if (o0 == 12345) tab[0] = 1;
         }
     }
 }
 int main() {
     const uint64_t n = 400000000ull;
-    for (uint64_t mb : {32ull, 64ull, 4096ull}) {
+    for (uint64_t mb : {32ull, 64ull}) {
         uint64_t slots = mb * 1024 * 1024 / 16;
         unsigned long long* tab;
         cudaMalloc(&tab, slots * 16);
         cudaMemset(tab, 0, slots * 16);
-        for (int mode = 0; mode < 8; ++mode) {
+        for (int mode = 0; mode < 11; ++mode) {
             cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
             cudaEventRecord(a);
             if (mode == 0) k<0><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
@@ -53,6 +64,9 @@ int main() {
             if (mode == 5) k<5><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
             if (mode == 6) k<6><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
             if (mode == 7) k<7><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
+            if (mode == 8) k<8><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
+            if (mode == 9) k<9><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
+            if (mode == 10) k<10><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
             cudaEventRecord(b); cudaEventSynchronize(b);
             float ms; cudaEventElapsedTime(&ms, a, b);
             printf("region %5llu MB mode %d : %.2f ms  %.1f G updates/s\n", (unsigned long long)mb, mode, ms, n / ms / 1e6);
