@@ -38,6 +38,20 @@ __global__ void k(unsigned long long* tab, uint64_t mask, uint64_t n, uint64_t s
         } else if (MODE == 9) {  // as 8 with atomicOr(key, 0)
             unsigned long long cur = atomicOr(tab + 2 * s, 0ULL);
             if (cur != 12345) atomicAdd(tab + 2 * s + 1, 1ULL);
+        } else if (MODE == 11) {  // even CTAs only load, odd CTAs only RED (n / 2 of each: n / 2 "updates"): is the mix penalised in L2 or in the SM?
+            if (blockIdx.x & 1) {
+                atomicAdd(tab + 2 * s + 1, 1ULL);
+            } else {
+                unsigned long long cur = __ldcg(tab + 2 * s);
+                if (cur == 12345) tab[0] = 1;
+            }
+        } else if (MODE == 12) {  // inside every CTA: warps 0-3 only load, warps 4-7 only RED
+            if (threadIdx.x & 128) {
+                atomicAdd(tab + 2 * s + 1, 1ULL);
+            } else {
+                unsigned long long cur = __ldcg(tab + 2 * s);
+                if (cur == 12345) tab[0] = 1;
+            }
         } else {  // MODE 10: one 128-bit compare-and-swap on the whole slot (key, count) with a guessed count of 0
             unsigned long long o0, o1;
             asm volatile("{\n\t.reg .b128 c, n, o;\n\tmov.b128 c, {%3, %4};\n\tmov.b128 n, {%5, %6};\n\tatom.cas.b128 o, [%2], c, n;\n\tmov.b128 {%0, %1}, o;\n\t}"
@@ -48,12 +62,12 @@ __global__ void k(unsigned long long* tab, uint64_t mask, uint64_t n, uint64_t s
 }
 int main() {
     const uint64_t n = 400000000ull;
-    for (uint64_t mb : {32ull, 64ull}) {
+    for (uint64_t mb : {64ull}) {
         uint64_t slots = mb * 1024 * 1024 / 16;
         unsigned long long* tab;
         cudaMalloc(&tab, slots * 16);
         cudaMemset(tab, 0, slots * 16);
-        for (int mode = 0; mode < 11; ++mode) {
+        for (int mode = 0; mode < 13; ++mode) {
             cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
             cudaEventRecord(a);
             if (mode == 0) k<0><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
@@ -67,9 +81,11 @@ int main() {
             if (mode == 8) k<8><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
             if (mode == 9) k<9><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
             if (mode == 10) k<10><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
+            if (mode == 11) k<11><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
+            if (mode == 12) k<12><<<148 * 8, 256>>>(tab, slots - 1, n, 7);
             cudaEventRecord(b); cudaEventSynchronize(b);
             float ms; cudaEventElapsedTime(&ms, a, b);
-            printf("region %5llu MB mode %d : %.2f ms  %.1f G updates/s\n", (unsigned long long)mb, mode, ms, n / ms / 1e6);
+            printf("region %5llu MB mode %d : %.2f ms  %.1f G updates/s\n", (unsigned long long)mb, mode, ms, (mode >= 11 ? n / 2 : n) / ms / 1e6);
         }
         cudaFree(tab);
     }
