@@ -98,7 +98,7 @@ def test_two_phase_chunks_and_overflow_fallback(engine, oracle):
 
 
 def test_two_phase_default_geometry(engine):
-    """The default geometry (32 MB regions) on a table of 256 MB: 2 M reads-worth of random 31-mers, conservation of the
+    """The default geometry (64 MB regions) on a table of 256 MB: 2 M reads-worth of random 31-mers, conservation of the
     inserted k-mers and agreement with direct insertion on the table statistics."""
     nb = np.full(20000, 150, dtype=np.uint64)
     batch = engine.batch_synth(41, nb)
