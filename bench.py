@@ -298,6 +298,8 @@ def main():
                 if tr["launch_reads"] == dom["nseq"] and tr["launch_bases"] == dom["nbases"]:
                     precaptured = {"dram_bytes_per_launch": tr["dram_bytes_per_launch"], "source": "profiles/" + name,
                                    "note": "ncu --set full capture committed with the repo, not measured in this run"}
+                    if "issue" in tr:  # the kernel's own bound (instruction issue), from the same capture
+                        precaptured["issue"] = tr["issue"]
                     break
             except Exception:
                 pass
