@@ -165,7 +165,8 @@ void kmu_ctx_destroy(kmu_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto* b : {&c->order, &c->counters, &c->table_scratch, &c->slot_scratch, &c->overflow, &c->sig_dev, &c->misc, &c->memo,
                     &c->whole_table, &c->items_slots, &c->part_fine, &c->group_table[0], &c->group_table[1], &c->group_table[2], &c->group_table[3],
-                    &c->group_slots[0], &c->group_slots[1], &c->group_slots[2], &c->group_slots[3], &c->ascii_dev, &c->ascii_off_dev, &c->ascii_bad_dev, &c->counters_alt, &c->overflow_alt, &c->smh_memo})
+                    &c->group_slots[0], &c->group_slots[1], &c->group_slots[2], &c->group_slots[3], &c->group_seen[0], &c->group_seen[1],
+                    &c->group_seen[2], &c->group_seen[3], &c->ascii_dev, &c->ascii_off_dev, &c->ascii_bad_dev, &c->counters_alt, &c->overflow_alt, &c->smh_memo})
         b->release();
     c->pinned.release();
     c->pinned_small.release();

@@ -1139,8 +1139,27 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
         while (cap < want) cap <<= 1;
         cap_max = std::max(cap_max, cap);
     }
-    std::vector<unsigned long long> tops(ngroups, 0);
+    std::vector<unsigned long long> tops(ngroups, 0), ovfs(ngroups, 0);
     std::vector<double> bounds(ngroups, 0.0);
+    // prefiltered insertion (pmh3a_prefilter_kernel, kmu_count.cu) for groups whose bound is selective: the table holds
+    // the ~(bound + 15 %) of the k-mers that can matter instead of all of them; bits: 8 per k-mer in each of the two bitmaps
+    const bool prefilter_on = std::getenv("KMU_GROUP_NO_PREFILTER") == nullptr;
+    auto prefiltered = [&](uint64_t g, uint64_t* cap_f, uint64_t* bits) {
+        if (!prefilter_on || nk[g] < (1ull << 20)) return false;
+        const double bound = 1.5 * (double)m / (double)nk[g] * std::log((double)m / 1e-4);
+        if (!(bound < 0.25)) return false;
+        uint64_t want = (uint64_t)(1.5 * (double)nk[g] * (bound + 0.15)) + 1024, cap = 1024, nb = 1ull << 16;
+        while (cap < want) cap <<= 1;
+        while (nb < 8 * nk[g]) nb <<= 1;
+        *cap_f = cap;
+        *bits = nb;
+        return true;
+    };
+    uint64_t seen_bytes_max = 0;
+    for (uint64_t g = 0; g < ngroups; ++g) {
+        uint64_t cf = 0, nb = 0;
+        if (prefiltered(g, &cf, &nb)) seen_bytes_max = std::max<uint64_t>(seen_bytes_max, 2 * nb / 8);
+    }
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         ScopedDevice sd(ctx->device);
@@ -1157,17 +1176,19 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
             if (me == cudaSuccess && !ctx->group_ev[q]) me = cudaEventCreateWithFlags(&ctx->group_ev[q], cudaEventDisableTiming);
             if (me == cudaSuccess) me = ctx->group_table[q].reserve(cap_max * slot_bytes + sizeof(unsigned long long) * AUX_WORDS);
             if (me == cudaSuccess) me = ctx->group_slots[q].reserve(sizeof(kmu::Slot) * m + 64);
+            if (me == cudaSuccess && seen_bytes_max) me = ctx->group_seen[q].reserve(seen_bytes_max);
         }
         if (me == cudaSuccess && !ctx->group_ev[kmu_ctx::GROUP_STREAMS])
             me = cudaEventCreateWithFlags(&ctx->group_ev[kmu_ctx::GROUP_STREAMS], cudaEventDisableTiming);
-        if (me == cudaSuccess) me = ctx->misc.reserve(sizeof(uint64_t) * (b->nseq + 1) + sizeof(unsigned long long) * ngroups + 64);
+        if (me == cudaSuccess) me = ctx->misc.reserve(sizeof(uint64_t) * (b->nseq + 1) + 2 * sizeof(unsigned long long) * ngroups + 64);
         if (me == cudaSuccess && !sig_on_device) me = ctx->sig_dev.reserve((size_t)ngroups * m * vsz);
         if (me != cudaSuccess) return fail(KMU_ENOMEM, "group sketch buffers: %s", cudaGetErrorString(me));
         uint64_t* d_rebased = (uint64_t*)ctx->misc.p;
         unsigned long long* d_tops = (unsigned long long*)(d_rebased + b->nseq + 1);
+        unsigned long long* d_ovfs = d_tops + ngroups;  // a group whose filtered table overflowed (many repeated k-mers) is redone
         uint8_t* d_sig = sig_on_device ? (uint8_t*)sig : (uint8_t*)ctx->sig_dev.p;
         CUDA_TRY(cudaMemcpyAsync(d_rebased, rebased.data(), sizeof(uint64_t) * b->nseq, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemsetAsync(d_tops, 0, sizeof(unsigned long long) * ngroups, st));
+        CUDA_TRY(cudaMemsetAsync(d_tops, 0, 2 * sizeof(unsigned long long) * ngroups, st));
         kmu::Pmh3aItemsParams P{};
         P.k = k;
         P.kmer_type = kmer_type;
@@ -1188,10 +1209,13 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
                 CUDA_TRY(cudaMemsetAsync(d_sig + g * (size_t)m * vsz, 0, (size_t)m * vsz, gs));
                 continue;
             }
-            uint64_t want = std::max<uint64_t>(1024, nk[g] + nk[g] / 2 + nk[g] / 16);  // load <= 0.64: a 5 Mb genome's table (64 MB) stays in L2
+            uint64_t want = std::max<uint64_t>(1024, nk[g] + nk[g] / 2 + nk[g] / 16);  // load <= 0.64
             if (2 * k < 40) want = std::min<uint64_t>(want, std::max<uint64_t>(1024, 2ull << (2 * k)));
             uint64_t cap = 1024;
             while (cap < want) cap <<= 1;
+            uint64_t cap_f = 0, seen_bits = 0;
+            const bool filtered = prefiltered(g, &cap_f, &seen_bits) && cap_f < cap;
+            if (filtered) cap = cap_f;
             kmu::CountTable t;
             t.slots = ctx->group_table[q].p;
             t.capmask = cap - 1;
@@ -1204,12 +1228,20 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
             const uint64_t Llast = b->h_nbases[s0 + ns - 1];
             const uint64_t bytes = rebased[s0 + ns - 1] + align_up((Llast + 3) / 4, SEQ_ALIGN);
             kmu::SeqView v{b->packed + b->h_byte_off[s0], d_rebased + s0, b->nbases + s0, ns};
-            CUDA_TRY(kmu::launch_count_insert_seqs(v, bytes, k, key64, kmu::hash_kind_is_canonical_host(hash_kind), t, ctx->sm_count, gs));
+            bounds[g] = 1.5 * (double)m / (double)nk[g] * std::log((double)m / 1e-4);
+            if (filtered) {
+                CUDA_TRY(cudaMemsetAsync(ctx->group_seen[q].p, 0, 2 * seen_bits / 8, gs));
+                CUDA_TRY(kmu::launch_pmh3a_prefilter(v, bytes, k, key64, kmu::hash_kind_is_canonical_host(hash_kind), kmer_type, hash_kind,
+                                                     bounds[g], P.e.c1, t, (uint32_t*)ctx->group_seen[q].p, seen_bits - 1, ctx->sm_count, gs));
+                CUDA_TRY(cudaMemcpyAsync(d_ovfs + g, t.overflow, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, gs));
+                launches += 1;
+            } else {
+                CUDA_TRY(kmu::launch_count_insert_seqs(v, bytes, k, key64, kmu::hash_kind_is_canonical_host(hash_kind), t, ctx->sm_count, gs));
+            }
             P.global_slots = (kmu::Slot*)ctx->group_slots[q].p;
             P.table = t.slots;
             P.special = t.special;
             P.n = cap;
-            bounds[g] = 1.5 * (double)m / (double)nk[g] * std::log((double)m / 1e-4);
             P.bound = bounds[g];
             const uint64_t work = (P.n + 511) / 512;
             const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(work, (uint64_t)ctx->sm_count));
@@ -1224,6 +1256,7 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
         }
         cudaEventRecord(ctx->ev[1], st);
         CUDA_TRY(cudaMemcpyAsync(tops.data(), d_tops, sizeof(unsigned long long) * ngroups, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(ovfs.data(), d_ovfs, sizeof(unsigned long long) * ngroups, cudaMemcpyDeviceToHost, st));
         if (!sig_on_device) {
             CUDA_TRY(cudaMemcpyAsync(sig, d_sig, (size_t)ngroups * m * vsz, cudaMemcpyDeviceToHost, st));
             ctx->last.d2h_bytes = (size_t)ngroups * m * vsz;
@@ -1238,7 +1271,7 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
         if (nk[g] == 0) continue;
         double top;
         std::memcpy(&top, &tops[g], 8);
-        if (top < bounds[g]) continue;
+        if (top < bounds[g] && !ovfs[g]) continue;
         kmu_seqbatch* view = nullptr;
         int32_t rc = kmu_seqbatch_view(b, first[g], group_sizes[g], &view);
         if (rc) return rc;

@@ -53,6 +53,51 @@ __global__ void __launch_bounds__(256) count_insert_seqs_kernel(SeqView b, uint6
     if (!ok) *t.overflow = 1ULL;
 }
 
+// ---- whole-file ProbMinHash3a: only the k-mers that can place a point below the bound are counted ------------------
+// The item kernel cuts every item at the bound B (kmu_pmh3a_items.cu) and the host verifies that every slot ended below
+// B: an item of weight w matters only if its first point x1 / w is below B, and x1 is a function of the key alone (half a
+// seeding, first_point_alive).  For a 5 Mb genome and m = 12 000, B = 0.067: 93 % of the k-mers are items of weight 1
+// with x1 >= B -- they cannot matter, yet counting them exactly is what the per-genome table (64 MB, beyond what stays
+// in L2) and its 5 M claims are for.  Two walks over the sequences instead:
+//   PASS 0  a k-mer with x1 < B goes into the table (exact count, as before); any other sets its bit in `seen1`, or, when
+//           that bit was already set (a second occurrence -- or a collision), its bit in `seen2`;
+//   PASS 1  a k-mer with x1 >= B whose `seen2` bit is set goes into the table: every key that occurs twice or more is
+//           counted exactly (all its occurrences come here), colliding single keys too (harmless).
+// What is left out are exactly keys of weight 1 with x1 >= B.  The table holds ~(B + repeats + collisions) of the k-mers.
+template <typename V, int PASS>
+__global__ void __launch_bounds__(256) pmh3a_prefilter_kernel(SeqView b, uint64_t total_bytes, uint32_t k, int canonical, int kmer_type,
+                                                               int hash_kind, double bound, double c1, CountTable t,
+                                                               uint32_t* __restrict__ seen1, uint32_t* __restrict__ seen2, uint64_t bitmask,
+                                                               uint32_t group_bytes) {
+    const uint64_t ngroups = (total_bytes + group_bytes - 1) / group_bytes;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const V header = (V)word_header(kmer_type, k);
+    bool ok = true;
+    for (uint64_t g = warp; g < ngroups; g += nwarps)
+        warp_for_each_kmer<V>(
+            b, total_bytes, g, k, canonical != 0, lane,
+            [&](V key, bool active) {
+                if (!active) return;
+                const bool alive = first_point_alive<V>(finalize_key<V>(key, header, hash_kind), 1.0, bound, c1);
+                if (alive) {
+                    if (PASS == 0) ok &= CountOps<V>::insert(t, key, 1u);
+                    return;
+                }
+                const uint64_t h = (fmix64((uint64_t)key) >> 24) & bitmask;  // (the table index uses the low bits of the same hash)
+                const uint32_t bit = 1u << (h & 31);
+                if (PASS == 0) {
+                    const uint32_t old = atomicOr(seen1 + (h >> 5), bit);
+                    if (old & bit) atomicOr(seen2 + (h >> 5), bit);
+                } else if (__ldcg(seen2 + (h >> 5)) & bit) {
+                    ok &= CountOps<V>::insert(t, key, 1u);
+                }
+            },
+            group_bytes);
+    if (!ok) *t.overflow = 1ULL;
+}
+
 template <typename V>
 __global__ void __launch_bounds__(256) count_insert_keys_kernel(const V* __restrict__ keys, uint64_t n, CountTable t) {
     bool ok = true;
@@ -232,6 +277,28 @@ cudaError_t launch_count_insert_seqs(const SeqView& b, uint64_t total_bytes, uin
     const int grid = grid_for(ngroups * 32, 256, sm_count, 8);
     if (key64) count_insert_seqs_kernel<uint64_t><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, t, group_bytes, first_group);
     else count_insert_seqs_kernel<uint32_t><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, t, group_bytes, first_group);
+    return cudaGetLastError();
+}
+
+// both walks of the prefiltered insertion (pmh3a_prefilter_kernel); seen: 2 * (bitmask + 1) / 8 zeroed bytes
+cudaError_t launch_pmh3a_prefilter(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical, int kmer_type,
+                                   int hash_kind, double bound, double c1, const CountTable& t, uint32_t* seen, uint64_t bitmask,
+                                   int sm_count, cudaStream_t st) {
+    if (b.nseq == 0 || total_bytes == 0) return cudaSuccess;
+    uint32_t group_bytes = GROUP_BYTES;
+    const uint64_t want_warps = (uint64_t)sm_count * 8 * 8;
+    while (group_bytes > 64 && (total_bytes + group_bytes - 1) / group_bytes < want_warps) group_bytes /= 2;
+    const uint64_t ngroups = (total_bytes + group_bytes - 1) / group_bytes;
+    const int grid = grid_for(ngroups * 32, 256, sm_count, 8);
+    uint32_t* seen1 = seen;
+    uint32_t* seen2 = seen + (bitmask + 1) / 32;
+    if (key64) {
+        pmh3a_prefilter_kernel<uint64_t, 0><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, kmer_type, hash_kind, bound, c1, t, seen1, seen2, bitmask, group_bytes);
+        pmh3a_prefilter_kernel<uint64_t, 1><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, kmer_type, hash_kind, bound, c1, t, seen1, seen2, bitmask, group_bytes);
+    } else {
+        pmh3a_prefilter_kernel<uint32_t, 0><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, kmer_type, hash_kind, bound, c1, t, seen1, seen2, bitmask, group_bytes);
+        pmh3a_prefilter_kernel<uint32_t, 1><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, kmer_type, hash_kind, bound, c1, t, seen1, seen2, bitmask, group_bytes);
+    }
     return cudaGetLastError();
 }
 

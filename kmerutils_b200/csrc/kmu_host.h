@@ -90,7 +90,7 @@ struct kmu_ctx {
     static constexpr int GROUP_STREAMS = 4;
     cudaStream_t group_stream[GROUP_STREAMS]{};
     cudaEvent_t group_ev[GROUP_STREAMS + 1]{};
-    DevBuf group_table[GROUP_STREAMS], group_slots[GROUP_STREAMS];
+    DevBuf group_table[GROUP_STREAMS], group_slots[GROUP_STREAMS], group_seen[GROUP_STREAMS];
     DevBuf part_fine;  // level-2 slabs of the two-phase counting insertion (kmu_capi_count.cu)
     DevBuf whole_table, items_slots;  // whole-file ProbMinHash3a: counting table + global slots
     int p2p_grid = 0;  // kmu_count_partition_counts -> _scatter hand-over

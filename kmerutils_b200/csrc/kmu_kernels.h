@@ -240,6 +240,9 @@ struct CountTable {
     unsigned long long* overflow; // set to 1 when an insertion found no free slot
 };
 cudaError_t launch_count_init(const CountTable& t, bool key64, int sm_count, cudaStream_t st);
+cudaError_t launch_pmh3a_prefilter(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical, int kmer_type,
+                                   int hash_kind, double bound, double c1, const CountTable& t, uint32_t* seen, uint64_t bitmask,
+                                   int sm_count, cudaStream_t st);
 cudaError_t launch_count_insert_seqs(const SeqView& b, uint64_t total_bytes, uint32_t k, bool key64, bool canonical,
                                      const CountTable& t, int sm_count, cudaStream_t st, uint64_t byte_begin = 0);
 cudaError_t launch_count_insert_keys(const void* keys, uint64_t n, bool key64, const CountTable& t, int sm_count,

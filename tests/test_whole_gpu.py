@@ -206,3 +206,41 @@ def test_pmh3a_counter_slots_match_whole_file(engine, oracle):
     with pytest.raises(kb.KmuInvalid):  # a bound no sketch can need (it would emit 1e300 points per key)
         engine.pmh3a_counter_slots(counter, kb.HASH_CANON_INVHASH, m, 1e300)
     counter.destroy()
+
+
+@pytest.mark.parametrize("k,ktype,m", [(16, kb.KMER16B32, 2000), (21, kb.KMER64, 1500)])
+def test_pmh3a_groups_prefiltered_insertion(engine, oracle, k, ktype, m):
+    """Genome-sized groups take the prefiltered insertion (only the k-mers that can place a point below the bound are counted,
+    plus every k-mer seen twice): a random genome in three contigs, a genome with a long segment repeated many times (its
+    repeated k-mers matter through their weights), a genome with a low-complexity stretch -- against the oracle's whole-file
+    signatures, and against the unfiltered path."""
+    import os
+    rng = np.random.default_rng(500 + k)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def rnd(n):
+        return acgt[rng.integers(0, 4, int(n))].tobytes()
+
+    seg = rnd(60000)
+    seqs = [rnd(700000), rnd(500000), rnd(300000)]                      # genome 0: 1.5 Mb, three contigs
+    seqs += [rnd(400000) + seg * 12 + rnd(300000) + seg * 7]            # genome 1: a 60 kb segment 19 times
+    seqs += [rnd(900000) + b"ACACACAC" * 20000 + rnd(400000)]           # genome 2: 160 kb of a dinucleotide repeat
+    groups = [3, 1, 1]
+    batch, bad = engine.batch_from_ascii(seqs)
+    assert bad.sum() == 0
+    packed, off, nb = batch.download()
+    packed = np.concatenate([packed, np.zeros(64, np.uint8)])
+    got = engine.sketch_pmh3a_groups(batch, groups, k, ktype, kb.HASH_CANON_INVHASH, m)
+    os.environ["KMU_GROUP_NO_PREFILTER"] = "1"
+    try:
+        plain = engine.sketch_pmh3a_groups(batch, groups, k, ktype, kb.HASH_CANON_INVHASH, m)
+    finally:
+        del os.environ["KMU_GROUP_NO_PREFILTER"]
+    assert np.array_equal(got, plain)
+    first = 0
+    for gi, g in enumerate(groups):
+        sl = slice(first, first + g)
+        want = oracle.sketch_pmh3a_seqs(packed, off[sl], nb[sl], k, ktype, kb.HASH_CANON_INVHASH, m)
+        assert np.array_equal(got[gi].astype(np.uint64), want), f"group {gi}"
+        first += g
+    batch.destroy()
