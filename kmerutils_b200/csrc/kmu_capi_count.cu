@@ -1167,7 +1167,9 @@ int32_t kmu_sketch_pmh3a_groups(kmu_ctx* ctx, const kmu_seqbatch* b, const uint6
         cudaStream_t st = ctx->stream;
         // the genomes are independent: NS of them are in flight at once, each on its own stream with its own table and
         // slots (the launches of one genome are short and leave SMs idle; the tables of the genomes in flight must fit L2)
-        int ns_want = 2;  // measured on 148 genomes of 5 Mb (ms per call): 1 stream 50.5, 2: 37.6, 3: 38.6, 4: 43.9 -- two 64 MB tables fill the L2
+        // measured on 148 genomes of 5 Mb (ms per call): unfiltered insertion (64 MB tables) 1 stream 50.5, 2: 37.6, 3: 38.6, 4: 43.9;
+        // prefiltered insertion (16 MB tables + 16 MB filters) 1: 33.5, 2: 23.1, 3: 22.2-22.5, 4: 23.3
+        int ns_want = 3;
         if (const char* e = std::getenv("KMU_GROUP_STREAMS")) ns_want = std::max(1, std::min(kmu_ctx::GROUP_STREAMS, std::atoi(e)));  // measurements
         const int NS = (int)std::min<uint64_t>((uint64_t)ns_want, ngroups);
         cudaError_t me = cudaSuccess;

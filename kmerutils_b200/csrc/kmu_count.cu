@@ -59,16 +59,15 @@ __global__ void __launch_bounds__(256) count_insert_seqs_kernel(SeqView b, uint6
 // seeding, first_point_alive).  For a 5 Mb genome and m = 12 000, B = 0.067: 93 % of the k-mers are items of weight 1
 // with x1 >= B -- they cannot matter, yet counting them exactly is what the per-genome table (64 MB, beyond what stays
 // in L2) and its 5 M claims are for.  Two walks over the sequences instead:
-//   PASS 0  a k-mer with x1 < B goes into the table (exact count, as before); any other sets its bit in `seen1`, or, when
-//           that bit was already set (a second occurrence -- or a collision), its bit in `seen2`;
-//   PASS 1  a k-mer with x1 >= B whose `seen2` bit is set goes into the table: every key that occurs twice or more is
+//   PASS 0  a k-mer with x1 < B goes into the table (exact count, as before); any other sets its "seen" bit in the filter, or,
+//           when that bit was already set (a second occurrence -- or a collision), its "seen again" bit;
+//   PASS 1  a k-mer with x1 >= B whose "seen again" bit is set goes into the table: every key that occurs twice or more is
 //           counted exactly (all its occurrences come here), colliding single keys too (harmless).
 // What is left out are exactly keys of weight 1 with x1 >= B.  The table holds ~(B + repeats + collisions) of the k-mers.
 template <typename V, int PASS>
 __global__ void __launch_bounds__(256) pmh3a_prefilter_kernel(SeqView b, uint64_t total_bytes, uint32_t k, int canonical, int kmer_type,
                                                                int hash_kind, double bound, double c1, CountTable t,
-                                                               uint32_t* __restrict__ seen1, uint32_t* __restrict__ seen2, uint64_t bitmask,
-                                                               uint32_t group_bytes) {
+                                                               uint32_t* __restrict__ seen, uint64_t bitmask, uint32_t group_bytes) {
     const uint64_t ngroups = (total_bytes + group_bytes - 1) / group_bytes;
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
@@ -80,18 +79,18 @@ __global__ void __launch_bounds__(256) pmh3a_prefilter_kernel(SeqView b, uint64_
             b, total_bytes, g, k, canonical != 0, lane,
             [&](V key, bool active) {
                 if (!active) return;
-                const bool alive = first_point_alive<V>(finalize_key<V>(key, header, hash_kind), 1.0, bound, c1);
-                if (alive) {
-                    if (PASS == 0) ok &= CountOps<V>::insert(t, key, 1u);
-                    return;
-                }
+                // two bits per position of the filter, side by side: "seen" and "seen again"
                 const uint64_t h = (fmix64((uint64_t)key) >> 24) & bitmask;  // (the table index uses the low bits of the same hash)
-                const uint32_t bit = 1u << (h & 31);
+                uint32_t* word = seen + (h >> 4);
+                const uint32_t once = 1u << ((h & 15) * 2), again = once << 1;
                 if (PASS == 0) {
-                    const uint32_t old = atomicOr(seen1 + (h >> 5), bit);
-                    if (old & bit) atomicOr(seen2 + (h >> 5), bit);
-                } else if (__ldcg(seen2 + (h >> 5)) & bit) {
-                    ok &= CountOps<V>::insert(t, key, 1u);
+                    if (first_point_alive<V>(finalize_key<V>(key, header, hash_kind), 1.0, bound, c1)) {
+                        ok &= CountOps<V>::insert(t, key, 1u);
+                    } else if (atomicOr(word, once) & once) {
+                        atomicOr(word, again);
+                    }
+                } else if ((__ldcg(word) & again) && !first_point_alive<V>(finalize_key<V>(key, header, hash_kind), 1.0, bound, c1)) {
+                    ok &= CountOps<V>::insert(t, key, 1u);  // (a key below the bound went in with all its occurrences in pass 0)
                 }
             },
             group_bytes);
@@ -290,14 +289,12 @@ cudaError_t launch_pmh3a_prefilter(const SeqView& b, uint64_t total_bytes, uint3
     while (group_bytes > 64 && (total_bytes + group_bytes - 1) / group_bytes < want_warps) group_bytes /= 2;
     const uint64_t ngroups = (total_bytes + group_bytes - 1) / group_bytes;
     const int grid = grid_for(ngroups * 32, 256, sm_count, 8);
-    uint32_t* seen1 = seen;
-    uint32_t* seen2 = seen + (bitmask + 1) / 32;
     if (key64) {
-        pmh3a_prefilter_kernel<uint64_t, 0><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, kmer_type, hash_kind, bound, c1, t, seen1, seen2, bitmask, group_bytes);
-        pmh3a_prefilter_kernel<uint64_t, 1><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, kmer_type, hash_kind, bound, c1, t, seen1, seen2, bitmask, group_bytes);
+        pmh3a_prefilter_kernel<uint64_t, 0><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, kmer_type, hash_kind, bound, c1, t, seen, bitmask, group_bytes);
+        pmh3a_prefilter_kernel<uint64_t, 1><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, kmer_type, hash_kind, bound, c1, t, seen, bitmask, group_bytes);
     } else {
-        pmh3a_prefilter_kernel<uint32_t, 0><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, kmer_type, hash_kind, bound, c1, t, seen1, seen2, bitmask, group_bytes);
-        pmh3a_prefilter_kernel<uint32_t, 1><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, kmer_type, hash_kind, bound, c1, t, seen1, seen2, bitmask, group_bytes);
+        pmh3a_prefilter_kernel<uint32_t, 0><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, kmer_type, hash_kind, bound, c1, t, seen, bitmask, group_bytes);
+        pmh3a_prefilter_kernel<uint32_t, 1><<<grid, 256, 0, st>>>(b, total_bytes, k, canonical, kmer_type, hash_kind, bound, c1, t, seen, bitmask, group_bytes);
     }
     return cudaGetLastError();
 }
