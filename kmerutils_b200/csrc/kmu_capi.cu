@@ -12,6 +12,8 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <functional>
+#include <condition_variable>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -99,10 +101,89 @@ int32_t batch_upload_meta(kmu_ctx* ctx, kmu_seqbatch* b) {
     return KMU_OK;
 }
 
+// A small persistent pool for the host-side gathers (one batch of separately allocated sequences is ~750 000 memcpy calls
+// in a dozen chunks: starting 16 threads per chunk cost more than the copies of a small chunk).
+class CopyPool {
+  public:
+    static CopyPool& get() {
+        static CopyPool pool;
+        return pool;
+    }
+    unsigned size() const { return (unsigned)workers.size() + 1; }
+    // runs job(t) for t in [0, njobs) on the pool's threads and the caller; returns when all are done
+    void run(unsigned njobs, const std::function<void(unsigned)>& job) {
+        if (njobs <= 1 || workers.empty()) {
+            for (unsigned t = 0; t < njobs; ++t) job(t);
+            return;
+        }
+        std::lock_guard<std::mutex> one_at_a_time(run_mu);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            cur_job = &job;
+            cur_njobs = njobs;
+            next = 0;
+            pending = njobs;
+            ++generation;
+        }
+        cv.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu);
+        done_cv.wait(lk, [&] { return pending == 0; });
+        cur_job = nullptr;
+    }
+
+  private:
+    CopyPool() {
+        const unsigned nt = std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
+        for (unsigned t = 1; t < nt; ++t) workers.emplace_back([this] { loop(); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto& w : workers) w.join();
+    }
+    void work() {
+        for (;;) {
+            unsigned t;
+            const std::function<void(unsigned)>* job;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (!cur_job || next >= cur_njobs) return;
+                t = next++;
+                job = cur_job;
+            }
+            (*job)(t);
+            std::lock_guard<std::mutex> lk(mu);
+            if (--pending == 0) done_cv.notify_all();
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> workers;
+    std::mutex mu, run_mu;
+    std::condition_variable cv, done_cv;
+    const std::function<void(unsigned)>* cur_job = nullptr;
+    unsigned cur_njobs = 0, next = 0, pending = 0;
+    uint64_t generation = 0;
+    bool stop = false;
+};
+
+// dst_off: byte offset of every sequence in dst (ascending).  The sequences are dealt out in pieces of equal BYTES.
 void parallel_copy(uint8_t* dst, const std::vector<uint64_t>& dst_off, const uint8_t* const* ptrs, const uint8_t* base,
                    const uint64_t* src_off, const uint64_t* nbases, uint64_t nseq) {
-    unsigned nt = std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
-    if (nseq < 4096) nt = 1;
     auto work = [&](uint64_t lo, uint64_t hi) {
         for (uint64_t i = lo; i < hi; ++i) {
             const uint8_t* src = ptrs ? ptrs[i] : base + src_off[i];
@@ -112,17 +193,21 @@ void parallel_copy(uint8_t* dst, const std::vector<uint64_t>& dst_off, const uin
             if (padded > nb) std::memset(dst + dst_off[i] + nb, 0, padded - nb);
         }
     };
-    if (nt == 1) {
+    CopyPool& pool = CopyPool::get();
+    if (nseq < 4096 || pool.size() == 1) {
         work(0, nseq);
         return;
     }
-    std::vector<std::thread> th;
-    uint64_t per = (nseq + nt - 1) / nt;
-    for (unsigned t = 0; t < nt; ++t) {
-        uint64_t lo = t * per, hi = std::min(nseq, lo + per);
-        if (lo < hi) th.emplace_back(work, lo, hi);
+    // pieces of ~equal bytes, four per thread (the threads take the next piece when they are done with one)
+    const unsigned npieces = pool.size() * 4;
+    const uint64_t total = dst_off[nseq - 1] + align_up((nbases[nseq - 1] + 3) / 4, SEQ_ALIGN) - dst_off[0];
+    std::vector<uint64_t> cut(npieces + 1, nseq);
+    cut[0] = 0;
+    for (unsigned p = 1; p < npieces; ++p) {
+        const uint64_t target = dst_off[0] + total / npieces * p;
+        cut[p] = (uint64_t)(std::lower_bound(dst_off.begin(), dst_off.begin() + nseq, target) - dst_off.begin());
     }
-    for (auto& t : th) t.join();
+    pool.run(npieces, [&](unsigned p) { work(cut[p], cut[p + 1]); });
 }
 
 }  // namespace
