@@ -153,7 +153,9 @@ int32_t insert_level1_slabs(kmu_ctx* ctx, kmu_counter* c, const void* slabs, uin
                             const unsigned long long* counts_dev, const RegionGeom& rg, const unsigned long long* skip_flag,
                             uint64_t* launches) {
     const size_t esz = c->key64 ? 8 : 4;
-    const bool prefetch = std::getenv("KMU_COUNT_NO_PREFETCH") == nullptr;
+    // the L2 prefetch of the next region is OFF: measured -2 to -7 ms per 3.2 G keys without it -- ncu: the prefetched lines (31 GB
+    // more DRAM reads) do not serve the atomics, whose L2 misses stay the same (KMU_COUNT_PREFETCH=1 turns it back on)
+    const bool prefetch = std::getenv("KMU_COUNT_PREFETCH") != nullptr;
     unsigned long long* scratch = (unsigned long long*)ctx->counters.p;
     unsigned int* done = std::getenv("KMU_COUNT_FREE_RUNNING") ? nullptr : (unsigned int*)(scratch + OFF_DONE);
     if (done) CUDA_TRY(cudaMemsetAsync(done, 0, sizeof(unsigned int) * rg.regions(), ctx->stream));
