@@ -540,8 +540,51 @@ __device__ __forceinline__ uint64_t kmer_at<uint64_t>(const uint32_t* __restrict
 // f(pre-key, active) is called with all 32 lanes converged (inactive lanes: active == false).
 constexpr uint32_t GROUP_BYTES = 2048;
 
+// the 4 k-mers that start at positions q .. q + 3 of the word stream w (canonical: the smaller strand): one window of packed
+// words and ONE reverse complement of the window serve all four, on both strands (as generate_kmers_run_kernel, kmu_extract.cu)
+__device__ __forceinline__ uint32_t revcomp16_word(uint32_t w) {
+    const uint32_t r = __brev(w);
+    uint32_t d;  // ~(((r << 1) & 0xAAAAAAAA) | ((r >> 1) & 0x55555555)): lut 0x27 of (a, b, c) = ~(c ? b : a)
+    asm("lop3.b32 %0, %1, %2, 0x55555555, 0x27;" : "=r"(d) : "r"(r << 1), "r"(r >> 1));
+    return d;
+}
+__device__ __forceinline__ void kmers4_at(const uint32_t* __restrict__ w, uint32_t q, uint32_t k, bool canonical, uint32_t keys[4]) {
+    const uint32_t* a = w + (q >> 4);
+    const uint32_t sh = (q & 15) * 2;
+    const uint32_t wa = be32(__ldg(a)), wb = be32(__ldg(a + 1)), wc = be32(__ldg(a + 2));
+    const uint32_t xh = __funnelshift_l(wb, wa, sh), xl = __funnelshift_l(wc, wb, sh);
+    const uint64_t x = ((uint64_t)xh << 32) | xl;
+    const uint64_t rc = canonical ? (((uint64_t)revcomp16_word(xl) << 32) | revcomp16_word(xh)) : 0;
+    const uint32_t mask = value_mask<uint32_t>(2 * k);
+#pragma unroll
+    for (uint32_t t = 0; t < 4; ++t) {
+        uint32_t key = (uint32_t)(x >> (64 - 2 * k - 2 * t)) & mask;
+        if (canonical) key = min(key, (uint32_t)(rc >> (2 * t)) & mask);
+        keys[t] = key;
+    }
+}
+__device__ __forceinline__ void kmers4_at(const uint32_t* __restrict__ w, uint32_t q, uint32_t k, bool canonical, uint64_t keys[4]) {
+    const uint32_t* a = w + (q >> 4);
+    const uint32_t sh = (q & 15) * 2;
+    const uint32_t w0 = be32(__ldg(a)), w1 = be32(__ldg(a + 1)), w2 = be32(__ldg(a + 2)), w3 = be32(__ldg(a + 3));
+    const uint32_t a0 = __funnelshift_l(w1, w0, sh), a1 = __funnelshift_l(w2, w1, sh), a2 = __funnelshift_l(w3, w2, sh);
+    const uint32_t r0 = canonical ? revcomp16_word(a0) : 0, r1 = canonical ? revcomp16_word(a1) : 0, r2 = canonical ? revcomp16_word(a2) : 0;
+    const uint64_t mask = value_mask<uint64_t>(2 * k);
+#pragma unroll
+    for (uint32_t t = 0; t < 4; ++t) {
+        const uint64_t x = ((uint64_t)__funnelshift_l(a1, a0, 2 * t) << 32) | __funnelshift_l(a2, a1, 2 * t);
+        uint64_t key = x >> (64 - 2 * k);
+        if (canonical) {
+            const uint64_t y = (((uint64_t)__funnelshift_r(r1, r2, 2 * t) << 32) | __funnelshift_r(r0, r1, 2 * t)) & mask;
+            key = key < y ? key : y;
+        }
+        keys[t] = key;
+    }
+}
+
 // group_bytes: the slice of the packed buffer one warp takes (a multiple of 16; GROUP_BYTES unless the input is so
-// small that slices of that size would leave most of the GPU idle)
+// small that slices of that size would leave most of the GPU idle).  The warp hands 128 consecutive positions of one
+// sequence at a time to its lanes, four consecutive positions per lane (kmers4_at); f is called four times per turn.
 template <typename V, typename F>
 __device__ __forceinline__ void warp_for_each_kmer(const SeqView& b, uint64_t total_bytes, uint64_t group, uint32_t k,
                                                    bool canonical, int lane, F&& f, uint32_t group_bytes = GROUP_BYTES) {
@@ -555,21 +598,18 @@ __device__ __forceinline__ void warp_for_each_kmer(const SeqView& b, uint64_t to
         const uint64_t nk = L >= k ? L - k + 1 : 0;
         const uint64_t p_lo = byte0 > sb ? (byte0 - sb) * 4 : 0;
         const uint64_t p_hi = min(nk, (byte1 - sb) * 4);
-        const uint32_t* words = (const uint32_t*)(b.packed + sb);
-        for (uint64_t p0 = p_lo; p0 < p_hi; p0 += 32) {
-            const uint64_t p = p0 + lane;
-            const bool active = p < p_hi;
-            V key = 0;
-            if (active) {
-                key = kmer_at<V>(words, p, k);
-                if (canonical) {
-                    const V rc = revcomp_val(key, k);
-                    key = key < rc ? key : rc;
-                }
-            }
-            f(key, active);
-        }
         ++s;
+        if (p_lo >= p_hi) continue;
+        const uint32_t n = (uint32_t)(p_hi - p_lo);
+        const uint32_t* wbase = (const uint32_t*)(b.packed + sb) + (p_lo >> 4);
+        const uint32_t q0 = (uint32_t)p_lo & 15;
+        for (uint32_t r0 = 0; r0 < n; r0 += 128) {
+            const uint32_t r = r0 + 4 * (uint32_t)lane;
+            V keys[4] = {0, 0, 0, 0};
+            if (r < n) kmers4_at(wbase, q0 + r, k, canonical, keys);
+#pragma unroll
+            for (uint32_t t = 0; t < 4; ++t) f(keys[t], r + t < n);
+        }
     }
 }
 
