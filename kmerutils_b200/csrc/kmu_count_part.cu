@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
     for (uint32_t p = tid; p < NB; p += PART_THREADS) hist[p] = 0;
     if (tid == 0) tile_n = 0;
     uint64_t s = 0;
-    if (FROM_SEQ && t0 < t1) s = seq_of_byte(b.byte_off, b.nseq, byte_begin + t0 * PART_TILE_BYTES + (uint64_t)wib * PART_WARP_BYTES);
+    if (FROM_SEQ && t0 < t1) s = seq_of_byte_warp(b.byte_off, b.nseq, byte_begin + t0 * PART_TILE_BYTES + (uint64_t)wib * PART_WARP_BYTES);
     __syncthreads();
     bool lost = false;
     const uint32_t lg_regions = (uint32_t)__ffs((int)g.nregions) - 1;

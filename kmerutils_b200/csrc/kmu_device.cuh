@@ -485,6 +485,22 @@ __device__ __forceinline__ uint64_t seq_of_byte(const uint64_t* __restrict__ byt
     return lo;
 }
 
+// the same search by a whole (converged) warp: 32 probes per round, four rounds for a million sequences instead of twenty
+// dependent loads
+__device__ __forceinline__ uint64_t seq_of_byte_warp(const uint64_t* __restrict__ byte_off, uint64_t nseq, uint64_t byte) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t lo = 0, hi = nseq;  // byte_off[lo] <= byte, the answer is in [lo, hi)
+    while (hi - lo > 1) {
+        const uint64_t step = (hi - lo + 30) >> 5;
+        const uint64_t idx = lo + (uint64_t)(lane + 1) * step;
+        const bool le = idx < hi && __ldg(byte_off + idx) <= byte;
+        const uint32_t c = __popc(__ballot_sync(0xFFFFFFFFu, le));  // the offsets ascend: the first c probes
+        lo += c * step;
+        hi = min(hi, lo + step);
+    }
+    return lo;
+}
+
 // Calls f(pre-key) for every k-mer that starts inside chunk `c` (pre-key: canonical or forward value)
 template <typename V, bool AA, typename F>
 __device__ __forceinline__ void for_each_kmer_in_chunk(const SeqView& b, uint64_t total_bytes, uint64_t c, uint32_t k,
@@ -590,7 +606,7 @@ __device__ __forceinline__ void warp_for_each_kmer(const SeqView& b, uint64_t to
                                                    bool canonical, int lane, F&& f, uint32_t group_bytes = GROUP_BYTES) {
     const uint64_t byte0 = group * group_bytes;
     const uint64_t byte1 = min(byte0 + (uint64_t)group_bytes, total_bytes);
-    uint64_t s = seq_of_byte(b.byte_off, b.nseq, byte0);
+    uint64_t s = seq_of_byte_warp(b.byte_off, b.nseq, byte0);
     while (s < b.nseq) {
         const uint64_t sb = __ldg(b.byte_off + s);
         if (sb >= byte1) break;

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) generate_kmers_warp_kernel(SeqView b, uin
     for (uint64_t g = warp; g < ngroups; g += nwarps) {
         const uint64_t byte0 = g * GROUP_BYTES;
         const uint64_t byte1 = min(byte0 + (uint64_t)GROUP_BYTES, total_bytes);
-        uint64_t s = seq_of_byte(b.byte_off, b.nseq, byte0);
+        uint64_t s = seq_of_byte_warp(b.byte_off, b.nseq, byte0);
         while (s < b.nseq) {
             const uint64_t sb = __ldg(b.byte_off + s);
             if (sb >= byte1) break;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) generate_kmers_run_kernel(SeqView b, uint
     for (uint64_t g = warp; g < ngroups; g += nwarps) {
         const uint64_t byte0 = g * GROUP_BYTES;
         const uint64_t byte1 = min(byte0 + (uint64_t)GROUP_BYTES, total_bytes);
-        uint64_t s = seq_of_byte(b.byte_off, b.nseq, byte0);
+        uint64_t s = seq_of_byte_warp(b.byte_off, b.nseq, byte0);
         while (s < b.nseq) {
             const uint64_t sb = __ldg(b.byte_off + s);
             if (sb >= byte1) break;
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(128) nthash_warp_kernel(SeqView b, uint64_t to
     for (uint64_t g = warp; g < ngroups; g += nwarps) {
         const uint64_t byte0 = g * GROUP_BYTES;
         const uint64_t byte1 = min(byte0 + (uint64_t)GROUP_BYTES, total_bytes);
-        uint64_t s = seq_of_byte(b.byte_off, b.nseq, byte0);
+        uint64_t s = seq_of_byte_warp(b.byte_off, b.nseq, byte0);
         while (s < b.nseq) {
             const uint64_t sb = __ldg(b.byte_off + s);
             if (sb >= byte1) break;
@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(128) nthash_run_kernel(SeqView b, uint64_t tot
     for (uint64_t g = warp; g < ngroups; g += nwarps) {
         const uint64_t byte0 = g * GROUP_BYTES;
         const uint64_t byte1 = min(byte0 + (uint64_t)GROUP_BYTES, total_bytes);
-        uint64_t s = seq_of_byte(b.byte_off, b.nseq, byte0);
+        uint64_t s = seq_of_byte_warp(b.byte_off, b.nseq, byte0);
         while (s < b.nseq) {
             const uint64_t sb = __ldg(b.byte_off + s);
             if (sb >= byte1) break;
@@ -574,6 +574,10 @@ __global__ void __launch_bounds__(128) nthash_run_kernel(SeqView b, uint64_t tot
             const uint32_t head = min(n, (NT_STEPS - (uint32_t)(e0 & (NT_STEPS - 1))) & (NT_STEPS - 1));
             const uint32_t nruns = (n - head) / NT_STEPS;
             const uint32_t nscalar = n - nruns * NT_STEPS;
+            const uint32_t run0 = (lane * nruns) >> 5, run1 = ((lane + 1) * nruns) >> 5;
+            // the first window of the lane's stretch is requested before the scalar positions are worked on
+            uint64_t w_run = 0;
+            if (run0 < run1) w_run = window32(wbase, q0 + head + run0 * NT_STEPS);
             if (lane < nscalar) {
                 const uint32_t q = lane < head ? lane : lane + nruns * NT_STEPS;
                 uint64_t f, r;
@@ -582,12 +586,11 @@ __global__ void __launch_bounds__(128) nthash_run_kernel(SeqView b, uint64_t tot
                 oh[q] = rev ? r : f;
                 if (STRAND) os[q] = rev ? 1 : 0;
             }
-            const uint32_t run0 = (lane * nruns) >> 5, run1 = ((lane + 1) * nruns) >> 5;
             if (run0 < run1) {
                 uint32_t q = head + run0 * NT_STEPS;
                 const uint32_t q_end = head + run1 * NT_STEPS;
                 uint64_t f, r;
-                nt_init(T, window32(wbase, q0 + q) >> (64 - 2 * k), k, f, r);
+                nt_init(T, w_run >> (64 - 2 * k), k, f, r);
                 // outgoing bases (positions q + j) and incoming ones (q + j + k); the windows of the next run are loaded
                 // before this run's steps (the read past the stretch stays inside the batch: 64 bytes of slack)
                 uint32_t OUTn = window16(wbase, q0 + q), INn = window16(wbase, q0 + q + k);
@@ -596,6 +599,9 @@ __global__ void __launch_bounds__(128) nthash_run_kernel(SeqView b, uint64_t tot
                     OUTn = window16(wbase, q0 + q + NT_STEPS);
                     INn = window16(wbase, q0 + q + NT_STEPS + k);
                     uint32_t hv[8], sv[4] = {0, 0, 0, 0};
+                    // table index (outgoing base, incoming base) of every step as a nibble: the odd steps in TO, the even
+                    // ones in TE, so that a step costs one shift and one mask instead of two of each
+                    const uint32_t TO = bitsel(IN, OUT << 2, 0xCCCCCCCCu), TE = bitsel(IN >> 2, OUT, 0xCCCCCCCCu);
 #pragma unroll
                     for (uint32_t j = 0; j < NT_STEPS; ++j) {
                         const uint32_t rev = r < f ? 0xFFFFFFFFu : 0u;
@@ -603,9 +609,10 @@ __global__ void __launch_bounds__(128) nthash_run_kernel(SeqView b, uint64_t tot
                         hv[2 * (j & 3) + 1] = bitsel((uint32_t)(f >> 32), (uint32_t)(r >> 32), rev);
                         if (STRAND) sv[j >> 2] |= rev & (1u << (8 * (j & 3)));
                         if ((j & 3) == 3) st256(oh + q + j - 3, hv[0], hv[1], hv[2], hv[3], hv[4], hv[5], hv[6], hv[7]);
-                        const uint32_t t = ((OUT >> (30 - 2 * j)) & 3u) * 4 + ((IN >> (30 - 2 * j)) & 3u);
-                        f = ((f << 1) | (f >> 63)) ^ T.FD[t];
-                        r = ((r >> 1) | (r << 63)) ^ T.RD[t];
+                        const uint32_t W = (j & 1) ? TO : TE, nib = (j & 1) ? (15 - j) / 2 : (14 - j) / 2;
+                        const uint32_t off = (nib ? W >> (4 * nib - 3) : W << 3) & 0x78u;  // 8 t, a byte offset
+                        f = ((f << 1) | (f >> 63)) ^ *(const uint64_t*)((const uint8_t*)T.FD + off);
+                        r = ((r >> 1) | (r << 63)) ^ *(const uint64_t*)((const uint8_t*)T.RD + off);
                     }
                     if (STRAND) st128(os + q, sv[0], sv[1], sv[2], sv[3]);
                 }
