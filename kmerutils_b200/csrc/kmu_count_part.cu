@@ -34,7 +34,6 @@ namespace kmu {
 constexpr int PART_THREADS = 512;
 constexpr uint32_t PART_TILE_BYTES = 1024;               // packed bytes per tile
 constexpr uint32_t PART_TILE_KEYS = PART_TILE_BYTES * 4;  // k-mers per tile (at most one per base)
-constexpr uint32_t PART_WARP_BYTES = PART_TILE_BYTES / (PART_THREADS / 32);
 
 template <typename V>
 __device__ __forceinline__ uint32_t part_bucket(V key, const PartGeom& g) {
@@ -103,7 +102,7 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
     for (uint32_t p = tid; p < NB; p += PART_THREADS) hist[p] = 0;
     if (tid == 0) tile_n = 0;
     uint64_t s = 0;
-    if (FROM_SEQ && t0 < t1) s = seq_of_byte_warp(b.byte_off, b.nseq, byte_begin + t0 * PART_TILE_BYTES + (uint64_t)wib * PART_WARP_BYTES);
+    if (FROM_SEQ && t0 < t1) s = seq_of_byte_warp(b.byte_off, b.nseq, byte_begin + t0 * PART_TILE_BYTES);
     __syncthreads();
     bool lost = false;
     const uint32_t lg_regions = (uint32_t)__ffs((int)g.nregions) - 1;
@@ -111,44 +110,63 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
     for (uint64_t t = t0; t < t1; ++t) {
         // ---- phase 1: the tile's keys and bucket ids into shared memory, histogram of the buckets
         if (FROM_SEQ) {
-            const uint64_t byte0 = byte_begin + t * PART_TILE_BYTES + (uint64_t)wib * PART_WARP_BYTES;
-            const uint64_t byte1 = min(min(byte0 + (uint64_t)PART_WARP_BYTES, byte_end), total_bytes);
-            if (byte0 < byte1) {
-                s = seq_forward(b.byte_off, b.nseq, s, byte0, lane);
-                uint64_t q = s;
-                while (q < b.nseq) {
-                    const uint64_t sbyte = __ldg(b.byte_off + q);
-                    if (sbyte >= byte1) break;
-                    const uint64_t L = __ldg(b.nbases + q);
-                    const uint64_t nk = L >= k ? L - k + 1 : 0;
-                    const uint64_t p_lo = byte0 > sbyte ? (byte0 - sbyte) * 4 : 0;
-                    const uint64_t p_hi = min(nk, (byte1 - sbyte) * 4);
-                    const uint32_t* words = (const uint32_t*)(b.packed + sbyte);
-                    for (uint64_t p0 = p_lo; p0 < p_hi; p0 += 32) {
-                        const uint64_t p = p0 + lane;
-                        const bool active = p < p_hi;
-                        V key = 0;
-                        uint32_t bk = 0;
-                        if (active) {
-                            key = kmer_at<V>(words, p, k);
-                            if (canonical) {
-                                const V rc = revcomp_val(key, k);
-                                key = key < rc ? key : rc;
-                            }
-                            bk = part_bucket<V>(key, g);
-                        }
-                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, active);
+            // the tile's bytes cut the sequences into segments; the segments are cut into chunks of 128 positions and the
+            // warps of the CTA take the chunks in turn, four consecutive k-mers per lane from one packed window
+            const uint64_t T0 = byte_begin + t * PART_TILE_BYTES;
+            const uint64_t T1 = min(min(T0 + (uint64_t)PART_TILE_BYTES, byte_end), total_bytes);
+            if (T0 < T1) {
+                s = seq_forward(b.byte_off, b.nseq, s, T0, lane);
+                uint32_t cbase = 0;  // chunks of the sequences before this batch of 32
+                for (uint64_t qb = s; qb < b.nseq; qb += 32) {
+                    const uint64_t q = qb + lane;
+                    uint64_t sbyte = ~0ULL, p_lo = 0;
+                    uint32_t nseg = 0;
+                    if (q < b.nseq) sbyte = __ldg(b.byte_off + q);
+                    const bool inside = sbyte < T1;  // the offsets ascend: a prefix of the lanes
+                    if (inside) {
+                        const uint64_t L = __ldg(b.nbases + q);
+                        const uint64_t nk = L >= k ? L - k + 1 : 0;
+                        p_lo = T0 > sbyte ? (T0 - sbyte) * 4 : 0;
+                        const uint64_t p_hi = min(nk, (T1 - sbyte) * 4);
+                        nseg = p_hi > p_lo ? (uint32_t)(p_hi - p_lo) : 0u;
+                    }
+                    const uint32_t nch = (nseg + 127) >> 7;
+                    uint32_t incl = nch;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                        if (lane >= d) incl += o;
+                    }
+                    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    const uint32_t excl = incl - nch;
+                    for (uint32_t cl = ((uint32_t)wib - cbase) & (PART_THREADS / 32 - 1); cl < total; cl += PART_THREADS / 32) {
+                        const int j = __popc(__ballot_sync(0xFFFFFFFFu, incl <= cl));  // the lane that holds the chunk's segment
+                        const uint64_t sb_j = __shfl_sync(0xFFFFFFFFu, sbyte, j), pc = __shfl_sync(0xFFFFFFFFu, p_lo, j) +
+                                                                                       (uint64_t)(cl - __shfl_sync(0xFFFFFFFFu, excl, j)) * 128;
+                        const uint32_t left = __shfl_sync(0xFFFFFFFFu, nseg, j) - (cl - __shfl_sync(0xFFFFFFFFu, excl, j)) * 128;
+                        const uint32_t cn = min(128u, left);
+                        V keys[4] = {0, 0, 0, 0};
+                        if (4u * lane < cn)
+                            kmers4_at((const uint32_t*)(b.packed + sb_j) + (pc >> 4), ((uint32_t)pc & 15u) + 4u * lane, k, canonical != 0, keys);
                         uint32_t base = 0;
-                        if (lane == 0) base = atomicAdd(&tile_n, (uint32_t)__popc(bal));
+                        if (lane == 0) base = atomicAdd(&tile_n, cn);
                         base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                        if (active) {
-                            const uint32_t pos = base + __popc(bal & ((1u << lane) - 1));
-                            tkeys[pos] = key;
-                            tb[pos] = (uint16_t)bk;
-                            atomicAdd(&hist[bk], 1u);
+                        // position 4 lane + t of the chunk goes to slot (positions with a smaller t) + lane: consecutive
+                        // lanes, consecutive slots (the order inside the tile is irrelevant, it is sorted next)
+#pragma unroll
+                        for (uint32_t tt = 0; tt < 4; ++tt) {
+                            const uint32_t cnt = cn > tt ? (cn - tt + 3) >> 2 : 0u;
+                            if ((uint32_t)lane < cnt) {
+                                const uint32_t bk = part_bucket<V>(keys[tt], g);
+                                tkeys[base + lane] = keys[tt];
+                                tb[base + lane] = (uint16_t)bk;
+                                atomicAdd(&hist[bk], 1u);
+                            }
+                            base += cnt;
                         }
                     }
-                    ++q;
+                    cbase += total;
+                    if (!__all_sync(0xFFFFFFFFu, inside)) break;
                 }
             }
         } else {
