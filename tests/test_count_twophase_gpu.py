@@ -181,3 +181,43 @@ def test_exchange_two_owners_on_one_gpu(engine, oracle):
                 ctrs[o].destroy()
     for b_ in batches + [whole]:
         b_.destroy()
+
+
+@pytest.mark.parametrize("k,ktype", [(8, kb.KMER32), (16, kb.KMER16B32), (31, kb.KMER64)])
+def test_two_phase_ragged_tiles(engine, oracle, k, ktype):
+    """The partition kernel cuts a 1 KB tile of packed bytes into sequence segments and those into 128-position chunks:
+    tiles with more than 32 sequences (16-byte records), sequences shorter than k and empty ones in between (segments
+    without chunks), segments of one k-mer, and sequences spanning many tiles, in one batch."""
+    rng = np.random.default_rng(7000 + k)
+    reads = []
+    for i in range(6000):
+        m = i % 7
+        if m == 0:
+            n = 0
+        elif m == 1:
+            n = int(rng.integers(1, k))          # too short for a k-mer
+        elif m == 2:
+            n = k                                # exactly one k-mer
+        elif m == 3:
+            n = int(rng.integers(k, 64))         # one 16-byte record
+        elif m == 4:
+            n = int(rng.integers(120, 140))      # one chunk, nearly full
+        elif m == 5:
+            n = int(rng.integers(128, 600))      # several chunks
+        else:
+            n = int(rng.integers(4000, 9000))    # several tiles
+        reads.append(oracle.synth_ascii(9000 + i, 0, n) if n else b"")
+    batch, _ = engine.batch_from_ascii(reads)
+    packed, off, nb = batch.download()
+    keys, cnts = oracle.count_kmers(packed, off, nb, k, ktype, True)
+    with knobs(KMU_COUNT_REGION_KB=16, KMU_COUNT_TWO_PHASE_MIN_KEYS=1, KMU_COUNT_LEVEL1_BUCKETS=512):
+        ctr = engine.counter(k, ktype, capacity=max(len(keys), 1 << 16), count_bits=16)
+        l0 = engine.launch_count()
+        ctr.insert_seqs(batch, canonical=True)
+        assert engine.launch_count() - l0 >= 2
+        st = ctr.stats()
+        assert st["nb_inserted"] == int(cnts.sum()) == batch.kmer_count(k)
+        assert st["nb_distinct"] == len(keys)
+        tk, tc = table_contents(ctr)
+        o = np.argsort(keys, kind="stable")
+        assert np.array_equal(tk, keys[o]) and np.array_equal(tc, np.minimum(cnts[o], 65535))
