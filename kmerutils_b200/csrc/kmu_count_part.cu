@@ -34,6 +34,33 @@ namespace kmu {
 constexpr int PART_THREADS = 512;
 constexpr uint32_t PART_TILE_BYTES = 1024;               // packed bytes per tile
 constexpr uint32_t PART_TILE_KEYS = PART_TILE_BYTES * 4;  // k-mers per tile (at most one per base)
+constexpr uint32_t PART_STAGE_BYTES = PART_TILE_BYTES + 32;  // a window of the tile's last position ends < 16 bytes behind it
+constexpr uint32_t PART_STAGE_SEQS = 64;
+static_assert(PART_STAGE_BYTES / 16 + 2 * PART_STAGE_SEQS <= PART_THREADS, "one staging copy per thread");
+
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* src, int bytes16) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (bytes16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+// the copies of one tile (bytes [T0, T0 + PART_STAGE_BYTES) as far as the batch's tail slack goes; offsets and lengths of the
+// sequences first .. first + 63): one copy per thread, committed as one group
+__device__ __forceinline__ void part_stage(const SeqView& b, uint64_t T0, uint64_t total_bytes, uint64_t first, unsigned char* st_bytes,
+                                           unsigned long long* st_off, unsigned long long* st_len, int tid) {
+    constexpr int NP = PART_STAGE_BYTES / 16;
+    if (tid < NP) {
+        if (T0 + 16ull * tid + 16 <= total_bytes + 64) cp_async(st_bytes + 16 * tid, b.packed + T0 + 16ull * tid, 1);
+    } else if (tid < NP + (int)PART_STAGE_SEQS) {
+        const uint64_t q = first + (tid - NP);
+        if (q < b.nseq) cp_async(st_off + (tid - NP), b.byte_off + q, 0);
+    } else if (tid < NP + 2 * (int)PART_STAGE_SEQS) {
+        const uint64_t q = first + (tid - NP - PART_STAGE_SEQS);
+        if (q < b.nseq) cp_async(st_len + (tid - NP - PART_STAGE_SEQS), b.nbases + q, 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
 template <typename V>
 __device__ __forceinline__ uint32_t part_bucket(V key, const PartGeom& g) {
@@ -70,6 +97,10 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
     uint32_t* jend = hist + NB;       // one past the last sorted index of the bucket that still fits its slab
     V** dptr = (V**)(jend + NB);  // slab address of sorted index 0 of the bucket (hist and jend take 8 NB bytes: aligned)
     __shared__ uint32_t tile_n, warp_sums[PART_THREADS / 32];
+    // read form: the tile's packed bytes and the offsets / lengths of the sequences around it, copied a tile ahead
+    // (cp.async, behind the sort and copy-out of the tile before) -- phase 1 then starts without a global load
+    __shared__ __align__(16) unsigned char st_bytes[PART_STAGE_BYTES];
+    __shared__ unsigned long long st_off[PART_STAGE_SEQS], st_len[PART_STAGE_SEQS], st_first, st_next;
     __shared__ unsigned long long seg_pref[65], seg_n[64];  // key-array form: tiles before segment s, keys of segment s
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 
@@ -102,7 +133,12 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
     for (uint32_t p = tid; p < NB; p += PART_THREADS) hist[p] = 0;
     if (tid == 0) tile_n = 0;
     uint64_t s = 0;
-    if (FROM_SEQ && t0 < t1) s = seq_of_byte_warp(b.byte_off, b.nseq, byte_begin + t0 * PART_TILE_BYTES);
+    if (FROM_SEQ && t0 < t1) {
+        s = seq_of_byte_warp(b.byte_off, b.nseq, byte_begin + t0 * PART_TILE_BYTES);
+        part_stage(b, byte_begin + t0 * PART_TILE_BYTES, total_bytes, s, st_bytes, st_off, st_len, tid);
+        if (tid == 0) st_first = s;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
     bool lost = false;
     const uint32_t lg_regions = (uint32_t)__ffs((int)g.nregions) - 1;
@@ -115,34 +151,34 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
             const uint64_t T0 = byte_begin + t * PART_TILE_BYTES;
             const uint64_t T1 = min(min(T0 + (uint64_t)PART_TILE_BYTES, byte_end), total_bytes);
             if (T0 < T1) {
-                s = seq_forward(b.byte_off, b.nseq, s, T0, lane);
-                if (wib == 0 && t + 1 < t1) {
-                    // the next tile starts with three dependent loads (offsets, lengths, packed words) that every warp of the
-                    // CTA waits for: its bytes and the metadata lines behind this tile's first sequence are requested into L2
-                    // now (42.7 -> 41.0 ms; real loads into L1 with unused results: no gain, the warp waits for them)
-                    const void* pf = nullptr;
-                    if (lane < 8) {
-                        if (T1 + (uint64_t)lane * 128 < total_bytes) pf = b.packed + T1 + (uint64_t)lane * 128;
-                    } else if (lane < 20) {
-                        const uint64_t q = s + 16ull * ((lane - 8) % 6 + 1);
-                        if (q < b.nseq) pf = lane < 14 ? (const void*)(b.byte_off + q) : (const void*)(b.nbases + q);
-                    }
-                    if (pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                // s: the last sequence that starts at or before T0 -- among the staged offsets (they start at the last
+                // sequence of the tile before), else by the forward search in global memory
+                const uint64_t first = st_first;
+                {
+                    const uint64_t q = first + lane;
+                    const bool le = q < b.nseq && st_off[lane] <= T0;
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, le);
+                    s = first + (bal ? __popc(bal) - 1 : 0);
+                    if (bal == 0xFFFFFFFFu) s = seq_forward(b.byte_off, b.nseq, s, T0, lane);
                 }
                 uint32_t cbase = 0;  // chunks of the sequences before this batch of 32
+                uint64_t last_inside = s;
                 for (uint64_t qb = s; qb < b.nseq; qb += 32) {
                     const uint64_t q = qb + lane;
+                    const bool staged = q - first < PART_STAGE_SEQS;  // q >= first
                     uint64_t sbyte = ~0ULL, p_lo = 0;
                     uint32_t nseg = 0;
-                    if (q < b.nseq) sbyte = __ldg(b.byte_off + q);
+                    if (q < b.nseq) sbyte = staged ? st_off[q - first] : __ldg(b.byte_off + q);
                     const bool inside = sbyte < T1;  // the offsets ascend: a prefix of the lanes
                     if (inside) {
-                        const uint64_t L = __ldg(b.nbases + q);
+                        const uint64_t L = staged ? st_len[q - first] : __ldg(b.nbases + q);
                         const uint64_t nk = L >= k ? L - k + 1 : 0;
                         p_lo = T0 > sbyte ? (T0 - sbyte) * 4 : 0;
                         const uint64_t p_hi = min(nk, (T1 - sbyte) * 4);
                         nseg = p_hi > p_lo ? (uint32_t)(p_hi - p_lo) : 0u;
                     }
+                    const uint32_t nin = __popc(__ballot_sync(0xFFFFFFFFu, inside));
+                    if (nin) last_inside = qb + nin - 1;
                     const uint32_t nch = (nseg + 127) >> 7;
                     uint32_t incl = nch;
 #pragma unroll
@@ -159,8 +195,11 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
                         const uint32_t left = __shfl_sync(0xFFFFFFFFu, nseg, j) - (cl - __shfl_sync(0xFFFFFFFFu, excl, j)) * 128;
                         const uint32_t cn = min(128u, left);
                         V keys[4] = {0, 0, 0, 0};
+                        // the chunk's first word lies at or behind T0 (a sequence starts on a multiple of 16 bytes, the tile on
+                        // a multiple of 1024), its last window ends inside the staged bytes
                         if (4u * lane < cn)
-                            kmers4_at((const uint32_t*)(b.packed + sb_j) + (pc >> 4), ((uint32_t)pc & 15u) + 4u * lane, k, canonical != 0, keys);
+                            kmers4_at<false>((const uint32_t*)(st_bytes + (sb_j + (pc >> 4) * 4 - T0)), ((uint32_t)pc & 15u) + 4u * lane, k,
+                                             canonical != 0, keys);
                         uint32_t base = 0;
                         if (lane == 0) base = atomicAdd(&tile_n, cn);
                         base = __shfl_sync(0xFFFFFFFFu, base, 0);
@@ -181,6 +220,9 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
                     cbase += total;
                     if (!__all_sync(0xFFFFFFFFu, inside)) break;
                 }
+                if (tid == 0) st_next = last_inside;  // the next tile's staged metadata starts here (read behind the barrier)
+            } else if (tid == 0) {
+                st_next = s;
             }
         } else {
             uint32_t sg = 0;
@@ -199,6 +241,10 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
         }
         __syncthreads();
         const uint32_t n = tile_n;
+        if (FROM_SEQ && t + 1 < t1) {
+            // this tile's staged bytes are dead from here on: the next tile's take their place while this one is sorted
+            part_stage(b, byte_begin + (t + 1) * PART_TILE_BYTES, total_bytes, st_next, st_bytes, st_off, st_len, tid);
+        }
         // ---- phase 2: exclusive scan of the histogram; one global atomic per non-empty bucket reserves its run
         {
             const uint32_t per_t = (NB + PART_THREADS - 1) / PART_THREADS;  // <= 8
@@ -255,6 +301,10 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
         __syncthreads();
         for (uint32_t p = tid; p < NB; p += PART_THREADS) hist[p] = 0;
         if (tid == 0) tile_n = 0;
+        if (FROM_SEQ) {
+            if (tid == 0) st_first = st_next;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
         __syncthreads();
     }
     if (lost) *flag = 1ULL;

@@ -564,10 +564,15 @@ __device__ __forceinline__ uint32_t revcomp16_word(uint32_t w) {
     asm("lop3.b32 %0, %1, %2, 0x55555555, 0x27;" : "=r"(d) : "r"(r << 1), "r"(r >> 1));
     return d;
 }
+template <bool GLOBAL = true>
+__device__ __forceinline__ uint32_t packed_word(const uint32_t* a) {
+    return GLOBAL ? __ldg(a) : *a;  // !GLOBAL: a staged copy in shared memory
+}
+template <bool GLOBAL = true>
 __device__ __forceinline__ void kmers4_at(const uint32_t* __restrict__ w, uint32_t q, uint32_t k, bool canonical, uint32_t keys[4]) {
     const uint32_t* a = w + (q >> 4);
     const uint32_t sh = (q & 15) * 2;
-    const uint32_t wa = be32(__ldg(a)), wb = be32(__ldg(a + 1)), wc = be32(__ldg(a + 2));
+    const uint32_t wa = be32(packed_word<GLOBAL>(a)), wb = be32(packed_word<GLOBAL>(a + 1)), wc = be32(packed_word<GLOBAL>(a + 2));
     const uint32_t xh = __funnelshift_l(wb, wa, sh), xl = __funnelshift_l(wc, wb, sh);
     const uint64_t x = ((uint64_t)xh << 32) | xl;
     const uint64_t rc = canonical ? (((uint64_t)revcomp16_word(xl) << 32) | revcomp16_word(xh)) : 0;
@@ -579,10 +584,12 @@ __device__ __forceinline__ void kmers4_at(const uint32_t* __restrict__ w, uint32
         keys[t] = key;
     }
 }
+template <bool GLOBAL = true>
 __device__ __forceinline__ void kmers4_at(const uint32_t* __restrict__ w, uint32_t q, uint32_t k, bool canonical, uint64_t keys[4]) {
     const uint32_t* a = w + (q >> 4);
     const uint32_t sh = (q & 15) * 2;
-    const uint32_t w0 = be32(__ldg(a)), w1 = be32(__ldg(a + 1)), w2 = be32(__ldg(a + 2)), w3 = be32(__ldg(a + 3));
+    const uint32_t w0 = be32(packed_word<GLOBAL>(a)), w1 = be32(packed_word<GLOBAL>(a + 1)), w2 = be32(packed_word<GLOBAL>(a + 2)),
+                   w3 = be32(packed_word<GLOBAL>(a + 3));
     const uint32_t a0 = __funnelshift_l(w1, w0, sh), a1 = __funnelshift_l(w2, w1, sh), a2 = __funnelshift_l(w3, w2, sh);
     const uint32_t r0 = canonical ? revcomp16_word(a0) : 0, r1 = canonical ? revcomp16_word(a1) : 0, r2 = canonical ? revcomp16_word(a2) : 0;
     const uint64_t mask = value_mask<uint64_t>(2 * k);
