@@ -62,11 +62,13 @@ uint64_t region_bytes_setting() {
         const uint64_t kb = (uint64_t)std::atoll(e);
         if (kb >= 1) return kb << 10;
     }
-    return 64ull << 20;
+    return 128ull << 20;
 }
 
-// The table is cut into `nfine_total` regions of region_bytes_setting() (64 MB, half of the L2: they sit there while they take their
-// updates).  The partition kernel is efficient up to a few hundred buckets per pass (a tile of 4096 k-mers sorted in shared
+// The table is cut into `nfine_total` regions of region_bytes_setting() (128 MB, the size of the L2: measured on 3.2 G 31-mers
+// into a 64 GB table, partition + insertion: 256 regions of 256 MB 31.1 + 92.3 ms, 512 of 128 MB 32.9 + 75.4, 1024 of 64 MB
+// 39.3 + 73.0, 2048 of 32 MB 55.0 + 77.9 -- fewer buckets make longer runs per tile in the partition kernel, and the
+// insertion, bound by the L2's dependent load + RED rate rather than by misses, loses little until the region is twice the L2).  The partition kernel is efficient up to a few hundred buckets per pass (a tile of 4096 k-mers sorted in shared
 // memory: with thousands of buckets every bucket gets one key per tile, i.e. one global atomic and one 8-byte store per
 // key -- measured 14.7 G keys/s at 4096 buckets against 77 G at 512), so large tables are partitioned in TWO levels:
 // level 1 (from the reads; across GPUs: owner x coarse region) makes ncoarse coarse regions per owner, level 2 cuts

@@ -246,6 +246,8 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
             part_stage(b, byte_begin + (t + 1) * PART_TILE_BYTES, total_bytes, st_next, st_bytes, st_off, st_len, tid);
         }
         // ---- phase 2: exclusive scan of the histogram; one global atomic per non-empty bucket reserves its run
+        unsigned long long at2[2] = {0, 0};
+        uint32_t off2[2] = {0, 0}, c2[2] = {0, 0};
         {
             const uint32_t per_t = (NB + PART_THREADS - 1) / PART_THREADS;  // <= 8
             const uint32_t first = tid * per_t;
@@ -266,37 +268,96 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
             uint32_t wbase = 0;
             for (int w = 0; w < wib; ++w) wbase += warp_sums[w];
             uint32_t off = wbase + incl - sum;
+            // the slab positions come back from L2 while the tile is sorted: the first two buckets of a thread (all of
+            // them up to 1024 buckets) keep theirs in registers until then
+            auto place = [&](uint32_t bk, uint32_t cnt, uint32_t o0, unsigned long long at) {
+                if (at + cnt > g.slab_cap) lost = true;
+                // sorted[o0 + i] goes to slab[at + i]: one pointer and one bound per bucket, not per key
+                const uint32_t o = bk >> lg_regions, r = bk & (g.nregions - 1);  // nregions is a power of two
+                dptr[bk] = dests[o] + ((uint64_t)r * g.nsend + g.self) * g.slab_cap + at - o0;
+                const unsigned long long room = at < g.slab_cap ? g.slab_cap - at : 0ull;
+                jend[bk] = o0 + (uint32_t)(room < cnt ? room : cnt);
+            };
 #pragma unroll
             for (uint32_t j = 0; j < 8; ++j) {
                 if (j < per_t && first + j < NB) {
                     const uint32_t bk = first + j;
                     hist[bk] = off;
+                    if (j < 2) off2[j] = off;
                     if (c[j]) {
                         const unsigned long long at = atomicAdd(&cursors[bk], (unsigned long long)c[j]);
-                        if (at + c[j] > g.slab_cap) lost = true;
-                        // sorted[off + i] goes to slab[at + i]: one pointer and one bound per bucket, not per key
-                        const uint32_t o = bk >> lg_regions, r = bk & (g.nregions - 1);  // nregions is a power of two
-                        dptr[bk] = dests[o] + ((uint64_t)r * g.nsend + g.self) * g.slab_cap + at - off;
-                        const unsigned long long room = at < g.slab_cap ? g.slab_cap - at : 0ull;
-                        jend[bk] = off + (uint32_t)(room < c[j] ? room : c[j]);
+                        if (j < 2)
+                            at2[j] = at;
+                        else
+                            place(bk, c[j], off, at);
                     }
                     off += c[j];
                 }
             }
+            c2[0] = c[0];
+            c2[1] = c[1];
         }
         __syncthreads();
-        // ---- phase 3: the tile sorted by bucket
-        for (uint32_t i = tid; i < n; i += PART_THREADS) {
-            const uint32_t bk = tb[i];
-            const uint32_t r = atomicAdd(&hist[bk], 1u);
-            sorted[r] = tkeys[i];
-            sb[r] = (uint16_t)bk;
+        // ---- phase 3: the tile sorted by bucket (four keys in flight per thread, then the rest one by one)
+        {
+            uint32_t i = tid;
+            for (; i + 3 * PART_THREADS < n; i += 4 * PART_THREADS) {
+                uint32_t bk[4], r[4];
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) bk[u] = tb[i + u * PART_THREADS];
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) r[u] = atomicAdd(&hist[bk[u]], 1u);
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) {
+                    sorted[r[u]] = tkeys[i + u * PART_THREADS];
+                    sb[r[u]] = (uint16_t)bk[u];
+                }
+            }
+            for (; i < n; i += PART_THREADS) {
+                const uint32_t bk = tb[i];
+                const uint32_t r = atomicAdd(&hist[bk], 1u);
+                sorted[r] = tkeys[i];
+                sb[r] = (uint16_t)bk;
+            }
+        }
+        {
+            const uint32_t per_t = (NB + PART_THREADS - 1) / PART_THREADS, first = tid * per_t;
+#pragma unroll
+            for (uint32_t j = 0; j < 2; ++j)
+                if (j < per_t && first + j < NB && c2[j]) {
+                    const uint32_t bk = first + j, cnt = c2[j], o0 = off2[j];
+                    const unsigned long long at = at2[j];
+                    if (at + cnt > g.slab_cap) lost = true;
+                    const uint32_t o = bk >> lg_regions, r = bk & (g.nregions - 1);
+                    dptr[bk] = dests[o] + ((uint64_t)r * g.nsend + g.self) * g.slab_cap + at - o0;
+                    const unsigned long long room = at < g.slab_cap ? g.slab_cap - at : 0ull;
+                    jend[bk] = o0 + (uint32_t)(room < cnt ? room : cnt);
+                }
         }
         __syncthreads();
         // ---- phase 4: every bucket's run goes to its slab (consecutive threads, consecutive addresses)
-        for (uint32_t j = tid; j < n; j += PART_THREADS) {
-            const uint32_t bk = sb[j];
-            if (j < jend[bk]) dptr[bk][j] = sorted[j];
+        {
+            uint32_t j = tid;
+            for (; j + 3 * PART_THREADS < n; j += 4 * PART_THREADS) {
+                uint32_t bk[4], je[4];
+                V* dp[4];
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) bk[u] = sb[j + u * PART_THREADS];
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) {
+                    je[u] = jend[bk[u]];
+                    dp[u] = dptr[bk[u]];
+                }
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) {
+                    const uint32_t ju = j + u * PART_THREADS;
+                    if (ju < je[u]) dp[u][ju] = sorted[ju];
+                }
+            }
+            for (; j < n; j += PART_THREADS) {
+                const uint32_t bk = sb[j];
+                if (j < jend[bk]) dptr[bk][j] = sorted[j];
+            }
         }
         __syncthreads();
         for (uint32_t p = tid; p < NB; p += PART_THREADS) hist[p] = 0;
