@@ -777,8 +777,16 @@ int32_t kmu_count_partition_scatter(kmu_ctx* ctx, const kmu_seqbatch* b, uint32_
 // (kmu_count_insert_slabs): bucketing by (owner, region) in one pass needs owners x 1024 buckets, and past ~1000 buckets
 // a tile of 4096 k-mers leaves two keys per run (measured at 2 GPUs: 93 ms of scatter + 116 ms of two-level insertion
 // against 46 + 78 on one GPU).  One owner: the local table's regions, i.e. the partition of the single-GPU path.
+// The one-pass form (buckets by owner AND region, plain regioned insertion at the receiver) stays available behind
+// KMU_COUNT_EXCHANGE_BUCKETS (the largest owners x regions product that still takes it; default 1: always by owner).  Measured
+// again with regions of 128 MB at 2 GPUs (2 x 512 buckets): scatter 94 ms + insertion 72 ms against 52 + 109 for the
+// owner-only form -- the runs of two or three keys that a 1024-bucket tile leaves are what NVLink stores are worst at.
 uint32_t exchange_regions(const kmu_counter* c, uint32_t nowners) {
-    return nowners > 1 ? 1u : region_geometry(c->capacity, c->key64, 1).ncoarse;
+    const uint32_t ncoarse = region_geometry(c->capacity, c->key64, 1).ncoarse;
+    if (nowners <= 1) return ncoarse;
+    uint64_t limit = 1;
+    if (const char* e = std::getenv("KMU_COUNT_EXCHANGE_BUCKETS")) limit = (uint64_t)std::max(1ll, std::atoll(e));
+    return (uint64_t)nowners * ncoarse <= limit ? ncoarse : 1u;
 }
 int32_t kmu_count_exchange_geometry(const kmu_counter* c, uint32_t nowners, uint32_t* nregions) {
     if (!c || !nregions || nowners < 1 || nowners > 64) return fail(KMU_EINVAL, "bad argument");
@@ -853,7 +861,8 @@ int32_t kmu_count_insert_slabs(kmu_ctx* ctx, kmu_counter* c, const void* slabs, 
     cudaEventRecord(ctx->ev[0], ctx->stream);
     uint64_t nl = 0;
     int32_t rc0 = KMU_OK;
-    if (nsend == 1) rc0 = insert_level1_slabs(ctx, c, slabs, slab_cap, 1, (const unsigned long long*)ctx->misc.p, rg, nullptr, &nl);
+    if (nsend == 1 || exchange_regions(c, nsend) > 1)
+        rc0 = insert_level1_slabs(ctx, c, slabs, slab_cap, nsend, (const unsigned long long*)ctx->misc.p, rg, nullptr, &nl);
     else rc0 = insert_segments(ctx, c, slabs, slab_cap, nsend, counts, (const unsigned long long*)ctx->misc.p, total, &nl);
     if (rc0) return rc0;
     cudaEventRecord(ctx->ev[1], ctx->stream);

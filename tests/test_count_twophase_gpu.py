@@ -144,10 +144,10 @@ def test_exchange_scatter_single_rank(engine, oracle):
 
 
 def test_exchange_two_owners_on_one_gpu(engine, oracle):
-    """The multi-owner exchange on ONE GPU: two read sets play ranks 0 and 1, their scatter kernels bucket by owner only and
-    store into both owners' receive buffers (all local here, peers over NVLink in a job), and every owner partitions the two
-    senders' segments by region of its table and inserts them (kmu_count_insert_slabs with two senders) -- the path every
-    rank of a multi-GPU round runs, checked against the oracle's counts of the union."""
+    """The multi-owner exchange on ONE GPU: two read sets play ranks 0 and 1, their scatter kernels bucket by (owner, region)
+    or by owner only and store into both owners' receive buffers (all local here, peers over NVLink in a job), and every
+    owner inserts the two senders' slabs (kmu_count_insert_slabs with two senders; the owner-only form partitions them by
+    region first) -- the path every rank of a multi-GPU round runs, checked against the oracle's counts of the union."""
     import torch
     from kmerutils_b200.dist import exchange_slab_cap
     k, ktype = 31, kb.KMER64
@@ -159,19 +159,22 @@ def test_exchange_two_owners_on_one_gpu(engine, oracle):
     packed, off, nb = whole.download()
     keys, cnts = oracle.count_kmers(packed, off, nb, k, ktype, True)
     owner = (oracle.apply_hash(keys, k, ktype, kb.HASH_INVHASH) % np.uint64(2)).astype(np.int64)  # DispatchableT::dispatch
-    for region_kb, min_keys in ((64, 1), (65536, 1 << 40)):  # regioned insertion of the segments / direct insertion (small job)
-        with knobs(KMU_COUNT_REGION_KB=region_kb, KMU_COUNT_TWO_PHASE_MIN_KEYS=min_keys):
+    # (owner, region) buckets in one pass and the plain regioned insertion at the receiver (up to 2048 buckets) / buckets by
+    # owner only, the receiver partitions the senders' segments by region / by owner only and direct insertion (small job)
+    for region_kb, min_keys, bucket_limit in ((64, 1, 2048), (64, 1, 1), (65536, 1 << 40, 1)):
+        with knobs(KMU_COUNT_REGION_KB=region_kb, KMU_COUNT_TWO_PHASE_MIN_KEYS=min_keys, KMU_COUNT_EXCHANGE_BUCKETS=bucket_limit):
             ctrs = [engine.counter(k, ktype, capacity=1 << 18, count_bits=8) for _ in range(2)]
-            assert ctrs[0].exchange_regions(2) == 1
-            slab_cap = exchange_slab_cap(max(b.kmer_count(k) for b in batches), 2, 1)
-            bufs = [torch.empty(2 * slab_cap, dtype=torch.int64, device="cuda:0") for _ in range(2)]
+            nreg = ctrs[0].exchange_regions(2)
+            assert (nreg > 1) == (bucket_limit > 1)
+            slab_cap = exchange_slab_cap(max(b.kmer_count(k) for b in batches), 2, nreg)
+            bufs = [torch.empty(2 * nreg * slab_cap, dtype=torch.int64, device="cuda:0") for _ in range(2)]
             sent = []
             for r in range(2):
                 s_r, ovf = ctrs[r].exchange_scatter(batches[r], 2, r, slab_cap, [b_.data_ptr() for b_ in bufs], True)
                 assert not ovf and int(s_r.sum()) == batches[r].kmer_count(k)
-                sent.append(s_r)
+                sent.append(np.asarray(s_r).reshape(2, nreg))
             for o in range(2):
-                ctrs[o].insert_slabs(bufs[o].data_ptr(), slab_cap, np.array([[sent[0][o, 0]], [sent[1][o, 0]]], dtype=np.uint64))
+                ctrs[o].insert_slabs(bufs[o].data_ptr(), slab_cap, np.stack([sent[0][o], sent[1][o]]).astype(np.uint64))
             for o in range(2):
                 mine = owner == o
                 st = ctrs[o].stats()
