@@ -181,7 +181,10 @@ constexpr int MAX_PARTS = 4096;
 //          (two-phase insertion: k-mers are grouped by table region so that the inserts of a region hit L2)
 template <typename V, int PMODE>
 __device__ __forceinline__ uint32_t part_of(V key, uint32_t nparts, uint64_t capmask, uint32_t shift) {
-    if (PMODE == 0) return (uint32_t)(inv_hash(key) % (V)nparts);
+    if (PMODE == 0) {
+        const V h = inv_hash(key);
+        return (nparts & (nparts - 1)) == 0 ? (uint32_t)h & (nparts - 1) : (uint32_t)(h % (V)nparts);  // a mask for 2 / 4 / 8 parts
+    }
     return (uint32_t)((fmix64((uint64_t)key) & capmask) >> shift);
 }
 

@@ -65,7 +65,13 @@ __device__ __forceinline__ void part_stage(const SeqView& b, uint64_t T0, uint64
 template <typename V>
 __device__ __forceinline__ uint32_t part_bucket(V key, const PartGeom& g) {
     uint32_t b = g.nregions > 1 ? (uint32_t)((fmix64((uint64_t)key) & g.capmask) >> g.shift) : 0u;
-    if (g.nowners > 1) b += (uint32_t)(inv_hash(key) % (V)g.nowners) * g.nregions;
+    if (g.nowners > 1) {
+        // DispatchableT::dispatch: intNN_hash(v) % N -- a mask for 2 / 4 / 8 GPUs (a 64-bit remainder by a run-time divisor is
+        // ~100 instructions, four times per lane and chunk)
+        const V h = inv_hash(key);
+        const uint32_t o = (g.nowners & (g.nowners - 1)) == 0 ? (uint32_t)h & (g.nowners - 1) : (uint32_t)(h % (V)g.nowners);
+        b += o * g.nregions;
+    }
     return b;
 }
 
