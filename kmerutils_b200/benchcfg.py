@@ -211,8 +211,34 @@ def run_c3(kb, eng, T, rank, world, steps, warmup, peak, reads_per_step=26_666_6
     def timed_step():
         step()
 
+    # every rank samples its own GPU while the rounds run (the ranks do the same work: is a spread of their times the GPUs'?)
+    import threading
+    samples = {"sm": [], "mem": [], "w": [], "reasons": 0}
+    stop = threading.Event()
+
+    def sampler():
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("LOCAL_RANK", 0)))
+            while not stop.is_set():
+                if it[0] > warmup:
+                    samples["sm"].append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    samples["mem"].append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_MEM))
+                    samples["w"].append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    samples["reasons"] |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                stop.wait(0.005)
+        except Exception:
+            pass
+
+    th = threading.Thread(target=sampler, daemon=True) if world > 1 else None
+    if th:
+        th.start()
     # warm-up rounds (allocations, IPC mapping), then the timed ones
     ms = T.run(timed_step, steps, warmup)
+    stop.set()
+    if th:
+        th.join(timeout=1.0)
     # every rank's insertion time and SM clock right after the timed rounds (the ranks do the same work: a spread is the GPUs')
     by_rank = None
     if world > 1:
@@ -224,12 +250,19 @@ def run_c3(kb, eng, T, rank, world, steps, warmup, peak, reads_per_step=26_666_6
             mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
         except Exception:
             pass
-        mine = torch.tensor([phases["insert_ms"] / steps, phases["scatter_ms"] / steps, mhz], dtype=torch.float64, device=T.dev)
-        allr = torch.empty((world, 3), dtype=torch.float64, device=T.dev)
+        med = lambda v: float(np.median(v)) if v else -1.0  # noqa: E731
+        mine = torch.tensor([phases["insert_ms"] / steps, phases["scatter_ms"] / steps, mhz, med(samples["sm"]), min(samples["sm"] or [-1]),
+                             med(samples["mem"]), med(samples["w"]), max(samples["w"] or [-1]), float(samples["reasons"]),
+                             float(len(samples["sm"]))], dtype=torch.float64, device=T.dev)
+        allr = torch.empty((world, mine.numel()), dtype=torch.float64, device=T.dev)
         dist.all_gather_into_tensor(allr, mine)
         allr = allr.cpu().numpy()
         by_rank = {"insert_ms": [round(float(x), 1) for x in allr[:, 0]], "scatter_ms": [round(float(x), 1) for x in allr[:, 1]],
-                   "sm_mhz_after": [float(x) for x in allr[:, 2]]}
+                   "sm_mhz_after": [float(x) for x in allr[:, 2]],
+                   "during_the_rounds": {"sm_mhz_median": [float(x) for x in allr[:, 3]], "sm_mhz_min": [float(x) for x in allr[:, 4]],
+                                         "mem_mhz_median": [float(x) for x in allr[:, 5]], "power_w_median": [round(float(x)) for x in allr[:, 6]],
+                                         "power_w_max": [round(float(x)) for x in allr[:, 7]],
+                                         "clock_event_reasons_or": [int(x) for x in allr[:, 8]], "samples": [int(x) for x in allr[:, 9]]}}
     # per step, slowest and fastest rank of every phase (the step itself is the max over ranks, barrier waits included)
     phases_min = {}
     for key in sorted(phases):
