@@ -2,20 +2,25 @@
 //
 // Why: a k-mer inserted straight into a table far larger than L2 costs one random DRAM read-modify-write of a
 // 32-byte sector per k-mer -- measured 163 B of DRAM traffic per 31-mer against 32 B algorithmic, 15.5 G updates/s
-// whatever the kernel does (profiles/r1d_micro_atomics.txt).  The same updates on a table region that sits in L2
-// run at 60-70 G/s.  So the batch is first PARTITIONED by the region of the table each k-mer hashes to (phase 1,
-// streaming), then inserted region after region by the whole grid (phase 2): the region is streamed into L2 once
-// (prefetch, coalesced), takes all its updates there, and is written back once.
+// whatever the kernel does (profiles/r1d_micro_atomics.txt).  So the batch is first PARTITIONED by the region of the
+// table each k-mer hashes to (phase 1, streaming), then inserted region after region by the whole grid (phase 2): a
+// region's sectors are fetched once per pass, take all their updates in L2 and are written back once (36.8 B of DRAM
+// traffic per 31-mer for both phases, profiles/r2c_count_traffic.csv; the updates themselves run at the L2's rate for a
+// look followed by a RED, 48-54 G/s, profiles/r2c_micro_warm_l2.txt).
 //
 //   phase 1  count_part_kernel      one walk over the packed reads (or over a key array): canonical k-mer ->
-//                                   bucket = owner * nregions + region; a CTA collects a tile of 4096 k-mers in
-//                                   shared memory, sorts it by bucket there (histogram, scan, scatter) and appends
-//                                   every bucket's run to that bucket's slab with ONE global atomic per (tile,
-//                                   bucket) and coalesced stores.  Slabs have a fixed capacity (expected share +
-//                                   8 sigma): an overflow (pathological input: one k-mer repeated millions of
-//                                   times) raises a flag and the caller falls back to direct insertion.
-//   phase 2  count_insert_slabs_kernel   for r in regions: prefetch region r + 1 of the table into L2; all CTAs
-//                                   insert the keys of region r (look, atomicCAS claim, RED add) -- L2 hits.
+//                                   bucket = owner * nregions + region.  A CTA takes tiles of 1 KB of packed bytes; the
+//                                   tile's bytes and the offsets / lengths of its sequences are copied into shared memory
+//                                   a tile ahead (cp.async); the sequence segments inside the tile are cut into chunks of
+//                                   128 positions that the 16 warps take in turn, four consecutive k-mers per lane from
+//                                   one window (kmers4_at).  The tile's <= 4096 k-mers are sorted by bucket in shared
+//                                   memory (histogram, scan, rank) and every bucket's run is appended to that bucket's
+//                                   slab with ONE global atomic per (tile, bucket) and stores from consecutive threads.
+//                                   Slabs have a fixed capacity (expected share + 8 sigma): an overflow (pathological
+//                                   input: one k-mer repeated millions of times) raises a flag and the caller falls back
+//                                   to direct insertion.
+//   phase 2  count_insert_slabs_kernel   for r in regions: all CTAs insert the keys of region r (look, atomicCAS claim,
+//                                   RED add), kept within two regions of each other by `done` counters.
 //
 // Multi-GPU (reference: DispatchableT::dispatch, kmercount.rs:382-420, and the one-producer / N-consumer hand-off of
 // count_kmer_threaded_one_to_many, :881-974): owner = intNN_hash(key) % nowners.  dests[o] is the receive buffer of
@@ -251,7 +256,17 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
             // this tile's staged bytes are dead from here on: the next tile's take their place while this one is sorted
             part_stage(b, byte_begin + (t + 1) * PART_TILE_BYTES, total_bytes, st_next, st_bytes, st_off, st_len, tid);
         }
-        // ---- phase 2: exclusive scan of the histogram; one global atomic per non-empty bucket reserves its run
+        // ---- phase 2: exclusive scan of the histogram; one global atomic per non-empty bucket reserves its run.
+        // The slab positions come back from L2 while the tile is sorted: the first two buckets of a thread (all of them up to
+        // 1024 buckets) keep theirs in registers until then.
+        auto place = [&](uint32_t bk, uint32_t cnt, uint32_t o0, unsigned long long at) {
+            if (at + cnt > g.slab_cap) lost = true;
+            // sorted[o0 + i] goes to slab[at + i]: one pointer and one bound per bucket, not per key
+            const uint32_t o = bk >> lg_regions, r = bk & (g.nregions - 1);  // nregions is a power of two
+            dptr[bk] = dests[o] + ((uint64_t)r * g.nsend + g.self) * g.slab_cap + at - o0;
+            const unsigned long long room = at < g.slab_cap ? g.slab_cap - at : 0ull;
+            jend[bk] = o0 + (uint32_t)(room < cnt ? room : cnt);
+        };
         unsigned long long at2[2] = {0, 0};
         uint32_t off2[2] = {0, 0}, c2[2] = {0, 0};
         {
@@ -274,16 +289,6 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
             uint32_t wbase = 0;
             for (int w = 0; w < wib; ++w) wbase += warp_sums[w];
             uint32_t off = wbase + incl - sum;
-            // the slab positions come back from L2 while the tile is sorted: the first two buckets of a thread (all of
-            // them up to 1024 buckets) keep theirs in registers until then
-            auto place = [&](uint32_t bk, uint32_t cnt, uint32_t o0, unsigned long long at) {
-                if (at + cnt > g.slab_cap) lost = true;
-                // sorted[o0 + i] goes to slab[at + i]: one pointer and one bound per bucket, not per key
-                const uint32_t o = bk >> lg_regions, r = bk & (g.nregions - 1);  // nregions is a power of two
-                dptr[bk] = dests[o] + ((uint64_t)r * g.nsend + g.self) * g.slab_cap + at - o0;
-                const unsigned long long room = at < g.slab_cap ? g.slab_cap - at : 0ull;
-                jend[bk] = o0 + (uint32_t)(room < cnt ? room : cnt);
-            };
 #pragma unroll
             for (uint32_t j = 0; j < 8; ++j) {
                 if (j < per_t && first + j < NB) {
@@ -330,15 +335,7 @@ __global__ void __launch_bounds__(PART_THREADS, 2)
             const uint32_t per_t = (NB + PART_THREADS - 1) / PART_THREADS, first = tid * per_t;
 #pragma unroll
             for (uint32_t j = 0; j < 2; ++j)
-                if (j < per_t && first + j < NB && c2[j]) {
-                    const uint32_t bk = first + j, cnt = c2[j], o0 = off2[j];
-                    const unsigned long long at = at2[j];
-                    if (at + cnt > g.slab_cap) lost = true;
-                    const uint32_t o = bk >> lg_regions, r = bk & (g.nregions - 1);
-                    dptr[bk] = dests[o] + ((uint64_t)r * g.nsend + g.self) * g.slab_cap + at - o0;
-                    const unsigned long long room = at < g.slab_cap ? g.slab_cap - at : 0ull;
-                    jend[bk] = o0 + (uint32_t)(room < cnt ? room : cnt);
-                }
+                if (j < per_t && first + j < NB && c2[j]) place(first + j, c2[j], off2[j], at2[j]);
         }
         __syncthreads();
         // ---- phase 4: every bucket's run goes to its slab (consecutive threads, consecutive addresses)
