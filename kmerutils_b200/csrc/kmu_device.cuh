@@ -552,8 +552,9 @@ __device__ __forceinline__ uint64_t kmer_at<uint64_t>(const uint32_t* __restrict
 }
 
 // Warp-cooperative traversal of a whole batch: the byte buffer is cut into groups of 2 KB; a warp
-// owns the k-mers that START in its group and hands 32 consecutive positions at a time to its lanes.
-// f(pre-key, active) is called with all 32 lanes converged (inactive lanes: active == false).
+// owns the k-mers that START in its group and hands 128 consecutive positions at a time to its lanes,
+// four per lane (warp_for_each_kmer below).  f(pre-key, active) is called four times per turn with all
+// 32 lanes converged (inactive lanes: active == false).
 constexpr uint32_t GROUP_BYTES = 2048;
 
 // the 4 k-mers that start at positions q .. q + 3 of the word stream w (canonical: the smaller strand): one window of packed

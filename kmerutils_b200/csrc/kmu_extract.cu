@@ -479,11 +479,12 @@ __global__ void __launch_bounds__(128) nthash_warp_kernel(SeqView b, uint64_t to
 }
 
 // Run form of ntHash (one hash per k-mer, 32-byte aligned outputs): the k-mers of a (group, sequence) segment are cut
-// into 32 contiguous stretches, one per lane, each a multiple of 32 positions that starts on a multiple of 32 of the
-// OUTPUT index.  A lane initialises once (O(k)) and then only rolls; every 4 steps it writes its 4 hashes with one 256-bit
+// into 32 contiguous stretches, one per lane, each a multiple of 16 positions (a run) that starts on a multiple of 16 of
+// the OUTPUT index.  A lane initialises once (O(k)) and then only rolls; every 4 steps it writes its 4 hashes with one 256-bit
 // store (a full 32-byte sector: no shared-memory transposition, no partial sectors), every 16 steps the 16 strand bytes
-// with one 128-bit store.  The elements before the first aligned index of a segment (< 32) are computed one per lane by
-// initialisation alone; the last, partial run of a segment rolls with scalar stores.
+// with one 128-bit store.  The elements before the first aligned index of a segment and behind its last whole run (< 32
+// together) are computed one per lane by initialisation alone.  The search for the group's first sequence is the warp's
+// (seq_of_byte_warp); the table index of every step comes from two nibble words built once per run.
 struct NtTables {
     uint64_t SEED[4], SEEDC[4], FD[16], RD[16], F2[16], R2[16];
 };

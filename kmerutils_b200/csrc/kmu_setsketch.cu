@@ -313,8 +313,8 @@ __global__ void __launch_bounds__(512, 2) ssk_whole_kernel(const SskParams P, Se
     }
 }
 
-// DNA form of the whole-batch kernel, warp-cooperative: the lanes of a warp take 32 consecutive positions of the warp's
-// slice at a time and stay together, which allows two phases -- (1) half a seeding per item: the first output of
+// DNA form of the whole-batch kernel, warp-cooperative: the lanes of a warp take 128 consecutive positions of the warp's
+// slice at a time (four per lane, warp_for_each_kmer) and stay together, which allows two phases -- (1) half a seeding per item: the first output of
 // Xoshiro256++ needs only s0 and s3 (SplitMix64 outputs 1 and 4 of the seed), and almost every item of a long input stops
 // on that draw; (2) the items whose ziggurat draw is not accepted at once, or whose first point falls below the cut
 // (about one in 90), are queued per warp and finished 32 at a time with the full generator.  (In the per-thread-chunk

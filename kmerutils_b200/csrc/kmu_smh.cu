@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(512, 2) smh_whole_kernel(const SmhParams P, Se
 }
 
 // DNA, long inputs (one point per item): warp-cooperative form of the whole-batch kernel with the value cut of
-// smh_fast_kernel -- the lanes take 32 consecutive positions of the warp's slice at a time, half a seeding gives an item's
+// smh_fast_kernel -- the lanes take 128 consecutive positions of the warp's slice at a time (four per lane), half a seeding gives an item's
 // value, an item not below `cut` is dropped there, the others are queued per warp and finished 32 at a time.  The host
 // verifies that every merged slot ends below the cut.
 constexpr uint32_t SMH_WHOLE_WARPS = 16;
