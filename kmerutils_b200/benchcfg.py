@@ -213,7 +213,7 @@ def run_c3(kb, eng, T, rank, world, steps, warmup, peak, reads_per_step=26_666_6
 
     # every rank samples its own GPU while the rounds run (the ranks do the same work: is a spread of their times the GPUs'?)
     import threading
-    samples = {"sm": [], "mem": [], "w": [], "reasons": 0}
+    samples = {"sm": [], "mem": [], "w": [], "reasons": 0, "t_gpu": [], "t_mem": []}
     stop = threading.Event()
 
     def sampler():
@@ -227,6 +227,13 @@ def run_c3(kb, eng, T, rank, world, steps, warmup, peak, reads_per_step=26_666_6
                     samples["mem"].append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_MEM))
                     samples["w"].append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
                     samples["reasons"] |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    try:  # temperatures: HBM refreshes more often when hot, which random accesses feel first
+                        samples["t_gpu"].append(pynvml.nvmlDeviceGetTemperature(h, pynvml.NVML_TEMPERATURE_GPU))
+                        fv = pynvml.nvmlDeviceGetFieldValues(h, [pynvml.NVML_FI_DEV_MEMORY_TEMP])[0]
+                        if fv.nvmlReturn == 0:
+                            samples["t_mem"].append(int(fv.value.uiVal))
+                    except Exception:
+                        pass
                 stop.wait(0.005)
         except Exception:
             pass
@@ -253,7 +260,8 @@ def run_c3(kb, eng, T, rank, world, steps, warmup, peak, reads_per_step=26_666_6
         med = lambda v: float(np.median(v)) if v else -1.0  # noqa: E731
         mine = torch.tensor([phases["insert_ms"] / steps, phases["scatter_ms"] / steps, mhz, med(samples["sm"]), min(samples["sm"] or [-1]),
                              med(samples["mem"]), med(samples["w"]), max(samples["w"] or [-1]), float(samples["reasons"]),
-                             float(len(samples["sm"]))], dtype=torch.float64, device=T.dev)
+                             float(len(samples["sm"])), max(samples["t_gpu"] or [-1]), max(samples["t_mem"] or [-1])],
+                            dtype=torch.float64, device=T.dev)
         allr = torch.empty((world, mine.numel()), dtype=torch.float64, device=T.dev)
         dist.all_gather_into_tensor(allr, mine)
         allr = allr.cpu().numpy()
@@ -262,7 +270,8 @@ def run_c3(kb, eng, T, rank, world, steps, warmup, peak, reads_per_step=26_666_6
                    "during_the_rounds": {"sm_mhz_median": [float(x) for x in allr[:, 3]], "sm_mhz_min": [float(x) for x in allr[:, 4]],
                                          "mem_mhz_median": [float(x) for x in allr[:, 5]], "power_w_median": [round(float(x)) for x in allr[:, 6]],
                                          "power_w_max": [round(float(x)) for x in allr[:, 7]],
-                                         "clock_event_reasons_or": [int(x) for x in allr[:, 8]], "samples": [int(x) for x in allr[:, 9]]}}
+                                         "clock_event_reasons_or": [int(x) for x in allr[:, 8]], "samples": [int(x) for x in allr[:, 9]],
+                                         "gpu_temp_c_max": [int(x) for x in allr[:, 10]], "hbm_temp_c_max": [int(x) for x in allr[:, 11]]}}
     # per step, slowest and fastest rank of every phase (the step itself is the max over ranks, barrier waits included)
     phases_min = {}
     for key in sorted(phases):
